@@ -1,0 +1,188 @@
+/*
+ * orag.h -- C ABI of the B200-native hybrid-retrieval hot path.
+ *
+ * The reference (gabrielcheda/optimized-rag) is pure Python and has no FFI of
+ * its own: the drop-in boundary is the duck-typed Python surface
+ * (DocumentStore.search, HybridRetriever.retrieve/hybrid_search,
+ * ReciprocalRankFusion.fuse -- optimized_rag_b200/*.py mirror those), and this
+ * header is the plain-C layer directly below it that a maintainer binds with
+ * ctypes/cffi.  Each entry point names the reference
+ * arithmetic it replaces (file:line under the reference tree).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ORAG_E* code on failure;
+ *     orag_last_error() returns a thread-local message for the last failure.
+ *   - all pointers named d_* are DEVICE pointers (sm_100a, current device);
+ *     the library never allocates device memory: callers pass every buffer,
+ *     including a workspace whose size they query first.
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work
+ *     (no hidden synchronisation) unless stated otherwise.
+ *   - ids are int64 global chunk ids = row_id_base + local row; missing
+ *     entries (fewer than k results) are -1 with score 0.
+ *   - ordering everywhere: score descending, ties -> ascending chunk id
+ *     (Python's stable sorted(reverse=True) over index-ordered input,
+ *     rag/retrieval.py:320), except RRF, whose tie rule is the reference's
+ *     dict-insertion order (rag/reranker.py:250-261).
+ */
+#ifndef ORAG_H
+#define ORAG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORAG_OK 0
+#define ORAG_EINVAL (-1)   /* bad argument */
+#define ORAG_ECUDA (-2)    /* CUDA runtime / driver error */
+#define ORAG_EWORKSPACE (-3) /* workspace too small */
+#define ORAG_EUNSUPPORTED (-4)
+
+/* cosine scan modes */
+#define ORAG_COS_EXACT 0 /* fp64 CUDA-core scan of every row (anchor / fallback / small N) */
+#define ORAG_COS_TF32 1  /* tcgen05 kind::tf32 first pass straight off the fp32 corpus + fp64 re-score */
+#define ORAG_COS_BF16 2  /* tcgen05 kind::f16 (bf16) first pass over a bf16 shadow copy + fp64 re-score */
+
+/* per-query status bits written by the *_topk entry points */
+#define ORAG_STATUS_OK 0
+#define ORAG_STATUS_OVERFLOW 1 /* candidate buffer overflowed: result for this query is NOT valid,
+                                  caller must re-run the query with ORAG_COS_EXACT / dense BM25 */
+
+int orag_version(void);
+const char *orag_last_error(void);
+/* sm count / compute capability of the current device */
+int orag_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------------------
+ * Synthetic inputs: bit-identical to optimized_rag_b200/synthetic.py
+ * ------------------------------------------------------------------------- */
+int orag_gen_embeddings(float *d_out, int64_t n_rows, int dim, int64_t row_start, uint64_t seed,
+                        int dup_per_mille, void *stream);
+int orag_gen_doc_lengths(int32_t *d_out, int64_t n_docs, int64_t doc_start, uint64_t seed, int lmin, int lmax,
+                         void *stream);
+int orag_gen_tokens(int32_t *d_out, const int64_t *d_doc_off, int64_t n_docs, int64_t doc_start, uint64_t seed,
+                    const uint64_t *d_thresholds, int vocab, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Ingest-side helpers for the cosine scan
+ * ------------------------------------------------------------------------- */
+/* d_inv_norm[r] = 1/||corpus[r]|| as fp32 (0 for an all-zero row).  Used only by the
+ * low-precision first pass; final scores never depend on it. */
+int orag_row_inv_norms(const float *d_corpus, int64_t n_rows, int dim, float *d_inv_norm, void *stream);
+/* fp32 -> bf16 (round-to-nearest-even) shadow copy for ORAG_COS_BF16 */
+int orag_f32_to_bf16(const float *d_src, void *d_dst_bf16, int64_t count, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Cosine top-k.  Replaces the pgvector statement at rag/document_store.py:448-460
+ * (`ORDER BY embedding <=> q LIMIT k`, exact instead of HNSW) and the Python loop
+ * at rag/retrieval.py:252-256 + 362-371.  Scores are the reference's float64
+ * arithmetic (Neumaier-compensated sums as CPython >= 3.12 `sum()` performs them,
+ * sqrt, one multiply, one divide; 0.0 when either magnitude is 0).
+ *
+ *   d_corpus     fp32 [n_rows, dim] row-major (16-byte aligned, dim % 4 == 0;
+ *                tensor-core modes additionally need dim % 32 == 0 (tf32) / % 64 (bf16))
+ *   d_inv_norm   fp32 [n_rows] from orag_row_inv_norms (tensor-core modes; may be NULL for EXACT)
+ *   d_shadow     bf16 [n_rows, dim] (ORAG_COS_BF16 only, else NULL)
+ *   d_queries    fp32 [n_queries, dim]
+ *   d_out_ids    int64 [n_queries, k]; d_out_scores fp64 [n_queries, k]
+ *   d_out_status int32 [n_queries] ORAG_STATUS_* (may be NULL)
+ * ------------------------------------------------------------------------- */
+size_t orag_cosine_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k, int mode);
+int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, const void *d_shadow, int64_t n_rows, int dim,
+                     int64_t row_id_base, const float *d_queries, int n_queries, int k, int mode,
+                     int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_status, void *d_workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* Dense float64 cosine matrix, d_out[q * n_rows + r] (test / small-N helper; same arithmetic).
+ * d_out must hold n_queries * n_rows + n_queries doubles (the tail receives sum(q*q) per query). */
+int orag_cosine_dense(const float *d_corpus, int64_t n_rows, int dim, const float *d_queries, int n_queries,
+                      double *d_out, void *stream);
+
+/* First-pass debug/test hook: raw tensor-core similarities (dot * inv_norm[row]) for rows
+ * [0, n_rows) as fp32 d_out[r * 256 + q]; n_rows is rounded up to 128 internally, d_out must
+ * hold round_up(n_rows,128) * 256 floats.  mode = ORAG_COS_TF32 / ORAG_COS_BF16. */
+int orag_cosine_firstpass_dense(const float *d_corpus, const float *d_inv_norm, const void *d_shadow, int64_t n_rows,
+                                int dim, const float *d_queries, int n_queries, int mode, float *d_out,
+                                void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * BM25 top-k over a GPU-resident, doc-range-tiled inverted index.  Replaces
+ * rank_bm25.BM25Okapi.get_scores + the normalisation/sort glue at
+ * rag/retrieval.py:324-347, 320.  Bit-exact float64 (no FMA contraction, query
+ * terms accumulated per document in query order).
+ * ------------------------------------------------------------------------- */
+typedef struct orag_bm25_index {
+    int64_t n_docs;                /* docs in this shard */
+    int32_t vocab;                 /* term ids are [0, vocab) */
+    int32_t tile_docs;             /* docs per tile (power of two, <= 65536) */
+    int32_t n_tiles;               /* ceil(n_docs / tile_docs) */
+    int32_t has_negative_idf;      /* 1 if a negative idf survives the epsilon floor (forces the dense path) */
+    const int64_t *d_tile_base;    /* [n_tiles + 1] first posting of each tile */
+    const int32_t *d_tile_term_off;/* [n_tiles, vocab + 1] term offsets relative to the tile base */
+    const uint32_t *d_postings;    /* [P] (doc_in_tile << 16) | tf, ascending doc within (tile, term) */
+    const double *d_doc_t4;        /* [n_docs] k1 * (1 - b + b * dl / avgdl), global avgdl */
+    const double *d_idf;           /* [vocab] global idf incl. epsilon floor; 0 for unseen terms */
+} orag_bm25_index_t;
+
+/*   d_query_terms int32 [n_queries, max_terms], entries < 0 or >= vocab are OOV / padding
+ *   d_query_lens  int32 [n_queries]
+ *   outputs: top-k by (normalised score desc, id asc) with ORAG_BM25_NORMALIZE, and
+ *   d_out_max[q] = the divisor the reference uses (max raw score, or 1.0 when that max is <= 0);
+ *   without it the raw scores are returned (multi-GPU: normalise after the gather) and
+ *   d_out_max[q] is the shard's max raw score. */
+#define ORAG_BM25_NORMALIZE 1    /* divide by the max raw score (rag/retrieval.py:343-345) */
+#define ORAG_BM25_FORCE_SPARSE 2 /* candidate path even for small corpora (tests) */
+#define ORAG_BM25_FORCE_DENSE 4  /* dense accumulate + exact select (small N, negative idf, fallback) */
+size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *index, int n_queries, int k, int flags);
+int orag_bm25_topk(const orag_bm25_index_t *index, int64_t doc_id_base, const int32_t *d_query_terms,
+                   const int32_t *d_query_lens, int n_queries, int max_terms, int k, int flags,
+                   int64_t *d_out_ids, double *d_out_scores, double *d_out_max, int32_t *d_out_status,
+                   void *d_workspace, size_t workspace_bytes, void *stream);
+/* Dense raw scores d_out[q * n_docs + d] (same arithmetic; test / fallback / small N). */
+int orag_bm25_dense(const orag_bm25_index_t *index, const int32_t *d_query_terms, const int32_t *d_query_lens,
+                    int n_queries, int max_terms, double *d_out, void *stream);
+
+/* Top-k of dense fp64 score rows: d_scores[q * ld + i], i in [0, n).  With `normalize`,
+ * rows are first divided by max(row) if that max is > 0 (rag/retrieval.py:343-345). */
+int orag_dense_topk(const double *d_scores, int64_t n, int64_t ld, int n_queries, int k, int64_t id_base,
+                    int normalize, int64_t *d_out_ids, double *d_out_scores, double *d_out_max, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Merge of per-shard candidate lists after the all-gather:
+ * d_cand_ids/scores [n_queries, m] (id -1 = empty) -> top-k by (score desc, id asc).
+ * With d_shard_max != NULL ([n_queries, n_shards] raw BM25 maxima) scores are divided
+ * by the global max first (or 1.0 when it is <= 0) and *d_out_max receives it.
+ * ------------------------------------------------------------------------- */
+int orag_topk_merge(const int64_t *d_cand_ids, const double *d_cand_scores, int m, int n_queries, int k,
+                    const double *d_shard_max, int n_shards, int64_t *d_out_ids, double *d_out_scores,
+                    double *d_out_max, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Reciprocal Rank Fusion.  Replaces ReciprocalRankFusion.fuse (rag/reranker.py:224-271):
+ * score[id] = sum over lists of 1/(rrf_k + rank), float64, lists walked in order;
+ * stable descending sort over first-sighting order (tie_mode 0) or ascending id
+ * (tie_mode 1).  d_list_ids [n_queries, n_lists, list_len] (id < 0 = padding, skipped
+ * WITHOUT consuming a rank only at the tail of a list).
+ *   d_out_src (optional, int32 [n_queries, top_k, n_lists]) 1-based rank of the fused
+ *   item in each input list, 0 if absent.
+ * ------------------------------------------------------------------------- */
+int orag_rrf_fuse(const int64_t *d_list_ids, int n_queries, int n_lists, int list_len, int rrf_k, int top_k,
+                  int tie_mode, int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_src, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Pairwise cosine candidates (rag/consistency_checker.py:169-189): all i<j with
+ * doc_idx[i] != doc_idx[j] and float64 cosine >= threshold.  Pairs are written
+ * unordered; *d_out_count receives the total (may exceed cap -> truncated).
+ * ------------------------------------------------------------------------- */
+size_t orag_pairwise_workspace_bytes(int64_t m, int dim);
+int orag_pairwise_cosine_threshold(const float *d_emb, int64_t m, int dim, const int32_t *d_doc_idx,
+                                   double threshold, int64_t cap, int32_t *d_out_i, int32_t *d_out_j,
+                                   double *d_out_sim, unsigned long long *d_out_count, void *d_workspace,
+                                   size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORAG_H */

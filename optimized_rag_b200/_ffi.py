@@ -1,0 +1,99 @@
+"""ctypes binding of include/orag.h -- the only door from Python into the CUDA kernels.
+
+There is NO fallback: if csrc/liborag.so is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "csrc" / "liborag.so"
+
+ORAG_COS_EXACT, ORAG_COS_TF32, ORAG_COS_BF16 = 0, 1, 2
+ORAG_STATUS_OVERFLOW = 1
+ORAG_BM25_NORMALIZE, ORAG_BM25_FORCE_SPARSE, ORAG_BM25_FORCE_DENSE = 1, 2, 4
+
+# every symbol include/orag.h declares (tests check the .so exports each one)
+SYMBOLS = [
+    "orag_version", "orag_last_error", "orag_device_info",
+    "orag_gen_embeddings", "orag_gen_doc_lengths", "orag_gen_tokens",
+    "orag_row_inv_norms", "orag_f32_to_bf16",
+    "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_dense", "orag_cosine_firstpass_dense",
+    "orag_bm25_workspace_bytes", "orag_bm25_topk", "orag_bm25_dense", "orag_dense_topk",
+    "orag_topk_merge", "orag_rrf_fuse",
+    "orag_pairwise_workspace_bytes", "orag_pairwise_cosine_threshold",
+]
+
+
+class OragError(RuntimeError):
+    pass
+
+
+class Bm25IndexStruct(Structure):
+    _fields_ = [
+        ("n_docs", c_int64),
+        ("vocab", c_int32),
+        ("tile_docs", c_int32),
+        ("n_tiles", c_int32),
+        ("has_negative_idf", c_int32),
+        ("d_tile_base", c_void_p),
+        ("d_tile_term_off", c_void_p),
+        ("d_postings", c_void_p),
+        ("d_doc_t4", c_void_p),
+        ("d_idf", c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise OragError(
+            f"{LIB_PATH} is missing: build it with `python -m optimized_rag_b200.build` "
+            "(there is no CPU or PyTorch fallback for the retrieval hot path)")
+    L = ctypes.CDLL(str(LIB_PATH))
+    vp = c_void_p
+    L.orag_version.restype = c_int
+    L.orag_last_error.restype = c_char_p
+    L.orag_device_info.argtypes = [POINTER(c_int), POINTER(c_int), POINTER(c_int)]
+    L.orag_gen_embeddings.argtypes = [vp, c_int64, c_int, c_int64, c_uint64, c_int, vp]
+    L.orag_gen_doc_lengths.argtypes = [vp, c_int64, c_int64, c_uint64, c_int, c_int, vp]
+    L.orag_gen_tokens.argtypes = [vp, vp, c_int64, c_int64, c_uint64, vp, c_int, vp]
+    L.orag_row_inv_norms.argtypes = [vp, c_int64, c_int, vp, vp]
+    L.orag_f32_to_bf16.argtypes = [vp, vp, c_int64, vp]
+    L.orag_cosine_workspace_bytes.restype = c_size_t
+    L.orag_cosine_workspace_bytes.argtypes = [c_int64, c_int, c_int, c_int, c_int]
+    L.orag_cosine_topk.argtypes = [vp, vp, vp, c_int64, c_int, c_int64, vp, c_int, c_int, c_int, vp, vp, vp, vp,
+                                   c_size_t, vp]
+    L.orag_cosine_dense.argtypes = [vp, c_int64, c_int, vp, c_int, vp, vp]
+    L.orag_cosine_firstpass_dense.argtypes = [vp, vp, vp, c_int64, c_int, vp, c_int, c_int, vp, vp, c_size_t, vp]
+    L.orag_bm25_workspace_bytes.restype = c_size_t
+    L.orag_bm25_workspace_bytes.argtypes = [POINTER(Bm25IndexStruct), c_int, c_int, c_int]
+    L.orag_bm25_topk.argtypes = [POINTER(Bm25IndexStruct), c_int64, vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp, vp,
+                                 vp, c_size_t, vp]
+    L.orag_bm25_dense.argtypes = [POINTER(Bm25IndexStruct), vp, vp, c_int, c_int, vp, vp]
+    L.orag_dense_topk.argtypes = [vp, c_int64, c_int64, c_int, c_int, c_int64, c_int, vp, vp, vp, vp]
+    L.orag_topk_merge.argtypes = [vp, vp, c_int, c_int, c_int, vp, c_int, vp, vp, vp, vp]
+    L.orag_rrf_fuse.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp]
+    L.orag_pairwise_workspace_bytes.restype = c_size_t
+    L.orag_pairwise_workspace_bytes.argtypes = [c_int64, c_int]
+    L.orag_pairwise_cosine_threshold.argtypes = [vp, c_int64, c_int, vp, c_double, c_int64, vp, vp, vp, vp, vp,
+                                                 c_size_t, vp]
+    for name in SYMBOLS:
+        f = getattr(L, name)
+        if name not in ("orag_last_error", "orag_cosine_workspace_bytes", "orag_bm25_workspace_bytes",
+                        "orag_pairwise_workspace_bytes"):
+            f.restype = c_int
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().orag_last_error()
+        raise OragError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

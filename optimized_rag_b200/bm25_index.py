@@ -1,0 +1,238 @@
+"""GPU-resident, doc-range-tiled BM25 index (ingest side; torch is used for the sort/scan plumbing).
+
+Layout consumed by csrc/bm25.cu (see include/orag.h `orag_bm25_index_t`):
+  tile t = docs [t*T, (t+1)*T) of the shard
+  postings      uint32 [(doc_in_tile << 16) | tf], grouped by (tile, term), ascending doc
+  tile_base     int64 [n_tiles+1]   first posting of each tile
+  tile_term_off int32 [n_tiles, V+1] offsets of each term's run inside its tile
+  doc_t4        float64 [n_docs]    k1*(1 - b + b*dl/avgdl)   (global avgdl)
+  idf           float64 [V]         global idf with the epsilon floor (rank_bm25 0.2.2 BM25Okapi._calc_idf)
+
+Global statistics (N, avgdl, df, first-seen order -> idf, eps) follow the reference's
+`BM25Okapi(tokenized_corpus)` construction at rag/retrieval.py:338; they are computed over the WHOLE
+corpus (all shards) so that sharded and single-GPU results are identical.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _ffi
+
+K1 = 1.5
+B = 0.75
+EPSILON = 0.25
+
+
+@dataclass
+class Bm25Stats:
+    """Corpus-wide statistics; `first_seen` is the global token position of each term's first occurrence
+    (int64 max for unseen terms) -- its argsort is the dict-insertion order rank_bm25 sums idf in."""
+    n_docs: int
+    total_len: int
+    df: np.ndarray          # int64 [V]
+    first_seen: np.ndarray  # int64 [V]
+
+    @property
+    def avgdl(self) -> float:
+        return self.total_len / self.n_docs if self.n_docs else 0.0
+
+    def merged(self, other: "Bm25Stats") -> "Bm25Stats":
+        return Bm25Stats(self.n_docs + other.n_docs, self.total_len + other.total_len, self.df + other.df,
+                         np.minimum(self.first_seen, other.first_seen))
+
+
+def idf_table(stats: Bm25Stats):
+    """rank_bm25 BM25Okapi._calc_idf: idf = log(N - df + .5) - log(df + .5) walked in first-seen order with a
+    running `+=` sum; negatives replaced by epsilon * average_idf.  Returns (idf float64 [V], average_idf, eps)."""
+    V = stats.df.shape[0]
+    idf = np.zeros(V, dtype=np.float64)
+    seen = np.nonzero(stats.df > 0)[0]
+    order = seen[np.argsort(stats.first_seen[seen], kind="stable")]
+    n = stats.n_docs
+    running = 0
+    negatives = []
+    df = stats.df
+    for t in order.tolist():
+        f = int(df[t])
+        v = math.log(n - f + 0.5) - math.log(f + 0.5)
+        idf[t] = v
+        running += v
+        if v < 0:
+            negatives.append(t)
+    average_idf = running / len(order) if len(order) else 0.0
+    eps = EPSILON * average_idf
+    for t in negatives:
+        idf[t] = eps
+    return idf, average_idf, eps
+
+
+def t4_table(max_dl: int, avgdl: float) -> np.ndarray:
+    """k1 * (1 - b + b * dl / avgdl) for dl = 0..max_dl with numpy float64 in rank_bm25's operation order."""
+    dl = np.arange(max_dl + 1)
+    if avgdl == 0:
+        return np.full(max_dl + 1, K1 * (1 - B), dtype=np.float64)
+    return K1 * (1 - B + B * dl / avgdl)
+
+
+def local_stats(doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, token_pos_base: int = 0,
+                chunk_docs: int = 1 << 20) -> Bm25Stats:
+    """df / first-seen / lengths of one shard.  doc_off int64 [n+1], tokens int32 [total] (same device)."""
+    dev = tokens.device
+    n = doc_off.numel() - 1
+    df = torch.zeros(vocab, dtype=torch.int64, device=dev)
+    big = torch.iinfo(torch.int64).max
+    first = torch.full((vocab,), big, dtype=torch.int64, device=dev)
+    total = int(doc_off[-1].item()) if n > 0 else 0
+    for d0 in range(0, n, chunk_docs):
+        d1 = min(n, d0 + chunk_docs)
+        lo, hi = int(doc_off[d0].item()), int(doc_off[d1].item())
+        if hi == lo:
+            continue
+        tok = tokens[lo:hi].long()
+        pos = torch.arange(lo, hi, dtype=torch.int64, device=dev) + token_pos_base
+        first.scatter_reduce_(0, tok, pos, reduce="amin", include_self=True)
+        lens = (doc_off[d0 + 1:d1 + 1] - doc_off[d0:d1])
+        doc = torch.repeat_interleave(torch.arange(d1 - d0, dtype=torch.int64, device=dev), lens)
+        pair = torch.unique(doc * vocab + tok)
+        df += torch.bincount(pair % vocab, minlength=vocab)
+        del tok, pos, doc, pair
+    return Bm25Stats(n, total, df.cpu().numpy(), first.cpu().numpy())
+
+
+class Bm25Index:
+    """One shard of the inverted index, resident on `device`."""
+
+    def __init__(self, doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, tile_docs: int = 4096,
+                 stats: Bm25Stats | None = None, doc_id_base: int = 0, chunk_docs: int = 1 << 20):
+        assert doc_off.dtype == torch.int64 and tokens.dtype == torch.int32
+        assert tile_docs & (tile_docs - 1) == 0 and 32 <= tile_docs <= 8192
+        dev = tokens.device
+        self.device = dev
+        self.vocab = int(vocab)
+        self.tile_docs = int(tile_docs)
+        self.n_docs = int(doc_off.numel() - 1)
+        self.doc_id_base = int(doc_id_base)
+        self.n_tiles = (self.n_docs + tile_docs - 1) // tile_docs
+        if stats is None:
+            stats = local_stats(doc_off, tokens, vocab, chunk_docs=chunk_docs)
+        self.stats = stats
+        idf, self.average_idf, self.eps = idf_table(stats)
+        self.avgdl = stats.avgdl
+        self.has_negative_idf = bool((idf < 0).any())
+        self.idf = torch.from_numpy(idf).to(dev)
+
+        dl = (doc_off[1:] - doc_off[:-1])
+        self.dl = dl.to(torch.int32)
+        max_dl = int(dl.max().item()) if self.n_docs else 0
+        t4 = torch.from_numpy(t4_table(max_dl, self.avgdl)).to(dev)
+        self.doc_t4 = t4[dl] if self.n_docs else torch.zeros(0, dtype=torch.float64, device=dev)
+
+        V1 = self.vocab + 1
+        T = self.tile_docs
+        chunk_docs = max(T, chunk_docs // T * T)
+        post_chunks, cnt_chunks = [], []
+        for d0 in range(0, self.n_docs, chunk_docs):
+            d1 = min(self.n_docs, d0 + chunk_docs)
+            lo, hi = int(doc_off[d0].item()), int(doc_off[d1].item())
+            n_t = (d1 - d0 + T - 1) // T
+            if hi == lo:
+                cnt_chunks.append(torch.zeros(n_t * self.vocab, dtype=torch.int64, device=dev))
+                continue
+            tok = tokens[lo:hi].long()
+            doc = torch.repeat_interleave(torch.arange(d1 - d0, dtype=torch.int64, device=dev), dl[d0:d1])
+            # key orders postings by (tile, term, doc_in_tile)
+            key = ((doc // T) * self.vocab + tok) * T + (doc % T)
+            del tok, doc
+            key, tf = torch.unique(key, return_counts=True)  # sorted
+            if int(tf.max().item()) > 0xFFFF:
+                raise ValueError("term frequency above 65535 is not representable in the posting format")
+            post_chunks.append((((key % T) << 16) | tf).to(torch.int32))
+            cnt_chunks.append(torch.bincount(key // T, minlength=n_t * self.vocab))
+            del key, tf
+        if post_chunks:
+            self.postings = torch.cat(post_chunks)
+        else:
+            self.postings = torch.zeros(1, dtype=torch.int32, device=dev)
+        del post_chunks
+        if cnt_chunks:
+            counts = torch.cat(cnt_chunks).view(self.n_tiles, self.vocab)
+        else:
+            counts = torch.zeros((0, self.vocab), dtype=torch.int64, device=dev)
+        off = torch.zeros((self.n_tiles, V1), dtype=torch.int64, device=dev)
+        torch.cumsum(counts, dim=1, out=off[:, 1:])
+        per_tile = off[:, -1] if self.n_tiles else torch.zeros(0, dtype=torch.int64, device=dev)
+        self.tile_base = torch.zeros(self.n_tiles + 1, dtype=torch.int64, device=dev)
+        if self.n_tiles:
+            torch.cumsum(per_tile, dim=0, out=self.tile_base[1:])
+            assert int(per_tile.max().item()) < 2 ** 31
+        self.tile_term_off = off.to(torch.int32).contiguous()
+        self.n_postings = int(self.tile_base[-1].item())
+        del counts, off
+
+        self.struct = _ffi.Bm25IndexStruct(
+            n_docs=self.n_docs, vocab=self.vocab, tile_docs=self.tile_docs, n_tiles=self.n_tiles,
+            has_negative_idf=int(self.has_negative_idf),
+            d_tile_base=self.tile_base.data_ptr(), d_tile_term_off=self.tile_term_off.data_ptr(),
+            d_postings=self.postings.data_ptr(), d_doc_t4=self.doc_t4.data_ptr(), d_idf=self.idf.data_ptr())
+        self._ws = None
+
+    # ------------------------------------------------------------------ queries
+    def _workspace(self, n_queries: int, k: int, flags: int) -> torch.Tensor:
+        need = int(_ffi.lib().orag_bm25_workspace_bytes(ctypes.byref(self.struct), n_queries, k, flags))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def topk(self, query_terms: torch.Tensor, query_lens: torch.Tensor, k: int, normalize: bool = True,
+             force: str | None = None, check_overflow: bool = True):
+        """query_terms int32 [B, max_terms] (negative = OOV/padding), query_lens int32 [B].
+        Returns ids int64 [B,k], scores f64 [B,k], max f64 [B] (divisor if normalize else shard max raw)."""
+        assert query_terms.dtype == torch.int32 and query_lens.dtype == torch.int32
+        assert query_terms.is_cuda and query_terms.is_contiguous() and query_lens.is_contiguous()
+        Bq, mt = query_terms.shape
+        flags = (_ffi.ORAG_BM25_NORMALIZE if normalize else 0)
+        flags |= {None: 0, "sparse": _ffi.ORAG_BM25_FORCE_SPARSE, "dense": _ffi.ORAG_BM25_FORCE_DENSE}[force]
+        ids = torch.empty((Bq, k), dtype=torch.int64, device=self.device)
+        sc = torch.empty((Bq, k), dtype=torch.float64, device=self.device)
+        mx = torch.empty(Bq, dtype=torch.float64, device=self.device)
+        status = torch.empty(Bq, dtype=torch.int32, device=self.device)
+        ws = self._workspace(Bq, k, flags)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _ffi.check(_ffi.lib().orag_bm25_topk(ctypes.byref(self.struct), self.doc_id_base, query_terms.data_ptr(),
+                                             query_lens.data_ptr(), Bq, mt, k, flags, ids.data_ptr(), sc.data_ptr(),
+                                             mx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), st),
+                   "orag_bm25_topk")
+        if check_overflow and force != "dense":
+            bad = torch.nonzero(status != 0).flatten()
+            if bad.numel():
+                # candidate buffer overflowed for these queries: exact dense path (never a CPU fallback)
+                i2, s2, m2 = self.topk(query_terms[bad].contiguous(), query_lens[bad].contiguous(), k, normalize,
+                                       force="dense", check_overflow=False)
+                ids[bad], sc[bad], mx[bad] = i2, s2, m2
+        return ids, sc, mx
+
+    def dense_scores(self, query_terms: torch.Tensor, query_lens: torch.Tensor) -> torch.Tensor:
+        """Raw float64 scores [B, n_docs] (tests / small corpora / weighted hybrid)."""
+        Bq, mt = query_terms.shape
+        out = torch.empty((Bq, max(self.n_docs, 1)), dtype=torch.float64, device=self.device)[:, :self.n_docs]
+        out = out.contiguous()
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _ffi.check(_ffi.lib().orag_bm25_dense(ctypes.byref(self.struct), query_terms.data_ptr(),
+                                              query_lens.data_ptr(), Bq, mt, out.data_ptr(), st), "orag_bm25_dense")
+        return out
+
+    def posting_bytes(self, query_terms: torch.Tensor, query_lens: torch.Tensor) -> int:
+        """Algorithmic bytes of a batch: sum over query tokens of df_shard(t) * 6."""
+        off = self.tile_term_off.long()
+        df_shard = (off[:, 1:] - off[:, :-1]).sum(dim=0)
+        idf_nz = self.idf != 0
+        t = query_terms.long()
+        mask = (t >= 0) & (t < self.vocab) & (torch.arange(t.shape[1], device=t.device)[None, :] < query_lens[:, None])
+        tc = t.clamp(0, self.vocab - 1)
+        per = torch.where(mask & idf_nz[tc], df_shard[tc], torch.zeros_like(tc))
+        return int(per.sum().item()) * 6

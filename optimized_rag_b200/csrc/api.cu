@@ -1,0 +1,251 @@
+// api.cu -- C-ABI entry points that orchestrate several kernels (cosine top-k pipeline), plus
+// error plumbing.  See include/orag.h for the contract of every symbol.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "cosine_tc.cuh"
+#include "exact.cuh"
+
+namespace orag {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// First-pass error bounds in cosine units (DESIGN.md "exactness of the first pass"):
+//   tf32: operands truncated to 10 mantissa bits -> |rel err per product| < 2^-9 + 2^-20
+//   bf16: operands rounded to nearest, 8 bits      -> |rel err per product| < 2^-8 + 2^-18
+// sum |a_i b_i| <= |a||b| turns that into an absolute bound on the cosine; 2.5e-4 covers fp32
+// accumulation in the tensor core (1536 terms), the fp32 inv-norm and the epilogue multiply.
+constexpr float kEpsTf32 = 1.954e-3f + 2.5e-4f;
+constexpr float kEpsBf16 = 3.91e-3f + 2.5e-4f;
+
+constexpr int kGroup = 256;     // queries per tensor-core pass (UMMA N)
+constexpr int kSeedRows = 2048; // rows of the dense seed pass that initialises the thresholds
+constexpr int kCandCap = 4096;  // candidate slots per query
+
+struct CosineWs {
+    double *sq_q;       // [G]
+    float *qnorm;       // [G]
+    float *inv_qnorm;   // [G]
+    uint32_t *thr_key;  // [G]
+    uint32_t *cnt;      // [G]
+    uint32_t *hist;     // [G, 1024]
+    int32_t *cand;      // [G, cap]
+    double *cand_score; // [G, cap]
+    int64_t *cand_id;   // [G, cap]
+    float *seed;        // [kSeedRows, 256]
+    void *q_bf16;       // [G, dim] bf16
+    size_t bytes;
+};
+
+static CosineWs carve_tc(void *base, int dim)
+{
+    CosineWs w{};
+    uint8_t *p = (uint8_t *)base;
+    auto take = [&](size_t n) {
+        uint8_t *r = p;
+        p += align_up(n, 256);
+        return r;
+    };
+    w.sq_q = (double *)take(kGroup * 8);
+    w.qnorm = (float *)take(kGroup * 4);
+    w.inv_qnorm = (float *)take(kGroup * 4);
+    w.thr_key = (uint32_t *)take(kGroup * 4);
+    w.cnt = (uint32_t *)take(kGroup * 4);
+    w.hist = (uint32_t *)take((size_t)kGroup * tc::kHistBins * 4);
+    w.cand = (int32_t *)take((size_t)kGroup * kCandCap * 4);
+    w.cand_score = (double *)take((size_t)kGroup * kCandCap * 8);
+    w.cand_id = (int64_t *)take((size_t)kGroup * kCandCap * 8);
+    w.seed = (float *)take((size_t)kSeedRows * 256 * 4);
+    w.q_bf16 = take((size_t)kGroup * dim * 2);
+    w.bytes = (size_t)(p - (uint8_t *)base);
+    return w;
+}
+
+}  // namespace orag
+
+using namespace orag;
+
+extern "C" int orag_version(void) { return 1; }
+extern "C" const char *orag_last_error(void) { return orag::g_err; }
+
+extern "C" int orag_device_info(int *sm, int *major, int *minor)
+{
+    int dev = 0;
+    ORAG_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    ORAG_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (sm) *sm = prop.multiProcessorCount;
+    if (major) *major = prop.major;
+    if (minor) *minor = prop.minor;
+    return ORAG_OK;
+}
+
+extern "C" size_t orag_cosine_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k, int mode)
+{
+    (void)k;
+    if (n_queries <= 0 || dim <= 0) return 0;
+    if (mode == ORAG_COS_EXACT) {
+        // queries are processed in chunks whose dense score block stays under ~512 MiB
+        size_t per_q = (size_t)(n_rows > 0 ? n_rows : 1) * 8;
+        size_t chunk = ((size_t)512 << 20) / per_q;
+        if (chunk < 1) chunk = 1;
+        if (chunk > (size_t)n_queries) chunk = (size_t)n_queries;
+        return align_up((size_t)n_queries * 8, 256) + align_up(chunk * per_q, 256);
+    }
+    return carve_tc(nullptr, dim).bytes;
+}
+
+static int cosine_exact_path(const float *corpus, int64_t n_rows, int dim, int64_t id_base, const float *queries,
+                             int n_queries, int k, int64_t *out_ids, double *out_scores, void *ws, cudaStream_t st)
+{
+    double *sq = (double *)ws;
+    double *dense = (double *)((uint8_t *)ws + align_up((size_t)n_queries * 8, 256));
+    int rc = launch_query_sq(queries, n_queries, dim, sq, st);
+    if (rc) return rc;
+    size_t per_q = (size_t)(n_rows > 0 ? n_rows : 1) * 8;
+    size_t chunk = ((size_t)512 << 20) / per_q;
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)n_queries) chunk = (size_t)n_queries;
+    for (int q0 = 0; q0 < n_queries; q0 += (int)chunk) {
+        int nq = n_queries - q0 < (int)chunk ? n_queries - q0 : (int)chunk;
+        if (n_rows > 0) {
+            rc = launch_cosine_dense(corpus, n_rows, dim, queries + (int64_t)q0 * dim, nq, sq + q0, dense, st);
+            if (rc) return rc;
+        }
+        rc = launch_select_topk(dense, nullptr, nullptr, n_rows, n_rows, nq, k, id_base, 0, nullptr, 0,
+                                out_ids + (int64_t)q0 * k, out_scores + (int64_t)q0 * k, nullptr, nullptr, st);
+        if (rc) return rc;
+    }
+    return ORAG_OK;
+}
+
+extern "C" int orag_f32_to_bf16(const float *d_src, void *d_dst, int64_t count, void *stream);
+
+extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, const void *d_shadow, int64_t n_rows,
+                                int dim, int64_t row_id_base, const float *d_queries, int n_queries, int k, int mode,
+                                int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_status, void *d_workspace,
+                                size_t workspace_bytes, void *stream)
+{
+    ORAG_REQUIRE(d_queries && d_out_ids && d_out_scores && n_queries > 0 && k > 0 && dim > 0 && n_rows >= 0,
+                 "cosine_topk");
+    ORAG_REQUIRE(n_rows == 0 || d_corpus, "corpus");
+    ORAG_REQUIRE(n_rows < ((int64_t)1 << 31), "n_rows per shard must fit int32");
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t need = orag_cosine_workspace_bytes(n_rows, dim, n_queries, k, mode);
+    if (workspace_bytes < need || !d_workspace) {
+        set_error("cosine_topk: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return ORAG_EWORKSPACE;
+    }
+    if (d_out_status) ORAG_CUDA_CHECK(cudaMemsetAsync(d_out_status, 0, (size_t)n_queries * sizeof(int32_t), st));
+    if (mode == ORAG_COS_EXACT)
+        return cosine_exact_path(d_corpus, n_rows, dim, row_id_base, d_queries, n_queries, k, d_out_ids, d_out_scores,
+                                 d_workspace, st);
+
+    ORAG_REQUIRE(mode == ORAG_COS_TF32 || mode == ORAG_COS_BF16, "mode");
+    const bool bf16 = mode == ORAG_COS_BF16;
+    ORAG_REQUIRE(dim % (bf16 ? 64 : 32) == 0, "dim must be a multiple of 32 (tf32) / 64 (bf16)");
+    ORAG_REQUIRE(d_inv_norm != nullptr || n_rows == 0, "inv_norm required for tensor-core modes");
+    ORAG_REQUIRE(!bf16 || d_shadow != nullptr || n_rows == 0, "bf16 shadow required");
+    ORAG_REQUIRE((reinterpret_cast<uintptr_t>(d_corpus) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_queries) & 15) == 0,
+                 "16-byte alignment");
+    ORAG_REQUIRE(k <= 1024, "k <= 1024 for tensor-core modes");
+    CosineWs w = carve_tc(d_workspace, dim);
+    const float margin = 2.f * (bf16 ? kEpsBf16 : kEpsTf32);
+    const int n_seed = (int)(n_rows < kSeedRows ? n_rows : kSeedRows);
+
+    for (int q0 = 0; q0 < n_queries; q0 += kGroup) {
+        const int nq = n_queries - q0 < kGroup ? n_queries - q0 : kGroup;
+        const float *q = d_queries + (int64_t)q0 * dim;
+        int rc = launch_query_sq(q, nq, dim, w.sq_q, st);
+        if (rc) return rc;
+        rc = tc::launch_query_norms(w.sq_q, nq, w.qnorm, w.inv_qnorm, st);
+        if (rc) return rc;
+        const void *qop = q;
+        if (bf16) {
+            rc = orag_f32_to_bf16(q, w.q_bf16, (int64_t)nq * dim, st);
+            if (rc) return rc;
+            qop = w.q_bf16;
+        }
+        const void *aop = bf16 ? d_shadow : (const void *)d_corpus;
+        tc::ScanParams p{};
+        p.n_queries = nq;
+        p.inv_norm = d_inv_norm;
+        p.thr_key = w.thr_key;
+        p.cnt = w.cnt;
+        p.hist = w.hist;
+        p.cand = w.cand;
+        p.cap = kCandCap;
+        p.qnorm = w.qnorm;
+        p.inv_qnorm = w.inv_qnorm;
+        p.margin = margin;
+        p.k = k;
+        // seed: dense first pass over the first rows -> histogram, threshold, first candidates
+        p.row_begin = 0;
+        p.row_end = n_seed;
+        p.dense = 1;
+        p.dense_out = w.seed;
+        rc = tc::launch_scan(bf16, aop, n_rows, qop, dim, p, st);
+        if (rc) return rc;
+        rc = tc::launch_seed_finalize(w.seed, n_seed, nq, k, margin, w.qnorm, w.inv_qnorm, w.thr_key, w.cnt, w.hist,
+                                      w.cand, kCandCap, st);
+        if (rc) return rc;
+        // main scan over the rest of the shard
+        p.row_begin = n_seed;
+        p.row_end = n_rows;
+        p.dense = 0;
+        p.dense_out = nullptr;
+        rc = tc::launch_scan(bf16, aop, n_rows, qop, dim, p, st);
+        if (rc) return rc;
+        // exact float64 re-score of the survivors, then exact selection
+        rc = launch_rescore(d_corpus, dim, row_id_base, q, w.sq_q, w.cand, w.cnt, kCandCap, nq, w.cand_score, w.cand_id,
+                            st);
+        if (rc) return rc;
+        rc = launch_select_topk(w.cand_score, w.cand_id, w.cnt, kCandCap, kCandCap, nq, k, 0, 0, nullptr, 0,
+                                d_out_ids + (int64_t)q0 * k, d_out_scores + (int64_t)q0 * k, nullptr,
+                                d_out_status ? d_out_status + q0 : nullptr, st);
+        if (rc) return rc;
+    }
+    return ORAG_OK;
+}
+
+extern "C" int orag_cosine_firstpass_dense(const float *d_corpus, const float *d_inv_norm, const void *d_shadow,
+                                           int64_t n_rows, int dim, const float *d_queries, int n_queries, int mode,
+                                           float *d_out, void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    ORAG_REQUIRE(d_corpus && d_inv_norm && d_queries && d_out && n_rows > 0 && n_queries > 0 && n_queries <= kGroup,
+                 "firstpass_dense");
+    ORAG_REQUIRE(mode == ORAG_COS_TF32 || mode == ORAG_COS_BF16, "mode");
+    const bool bf16 = mode == ORAG_COS_BF16;
+    ORAG_REQUIRE(dim % (bf16 ? 64 : 32) == 0, "dim multiple of 32/64");
+    cudaStream_t st = (cudaStream_t)stream;
+    const void *qop = d_queries;
+    if (bf16) {
+        ORAG_REQUIRE(d_shadow && d_workspace && workspace_bytes >= (size_t)n_queries * dim * 2, "bf16 workspace");
+        int rc = orag_f32_to_bf16(d_queries, d_workspace, (int64_t)n_queries * dim, st);
+        if (rc) return rc;
+        qop = d_workspace;
+    }
+    tc::ScanParams p{};
+    p.n_queries = n_queries;
+    p.inv_norm = d_inv_norm;
+    p.row_begin = 0;
+    p.row_end = n_rows;
+    p.dense = 1;
+    p.dense_out = d_out;
+    return tc::launch_scan(bf16, bf16 ? d_shadow : (const void *)d_corpus, n_rows, qop, dim, p, st);
+}
+
+extern "C" size_t orag_pairwise_workspace_bytes(int64_t m, int dim)
+{
+    (void)dim;
+    return align_up((size_t)(m > 0 ? m : 1) * 8, 256);
+}

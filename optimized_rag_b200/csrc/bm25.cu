@@ -1,0 +1,455 @@
+// bm25.cu -- bit-exact BM25 (rank_bm25.BM25Okapi.get_scores + rag/retrieval.py:324-347 glue)
+// over a GPU-resident, doc-range-tiled inverted index.
+//
+// Index layout (built by optimized_rag_b200/bm25_index.py): documents are cut into tiles of
+// `tile_docs` consecutive docs; each tile owns a contiguous run of 4-byte postings
+// ((doc_in_tile << 16) | tf) grouped by term, ascending doc inside a term, plus a row of
+// vocab+1 term offsets.  A tile is the unit of work: one CTA keeps a float64 accumulator and the
+// per-document length term t4 = k1*(1 - b + b*dl/avgdl) for its docs in shared memory and
+// streams, for every query of the batch, the posting runs of the query's terms with coalesced
+// 4-byte reads.
+//
+// Exactness: the reference adds, per query token IN QUERY ORDER,
+//     idf * (tf*(k1+1) / (tf + t4[d]))          (numpy float64, this operation order)
+// to score[d].  Here one term is processed at a time (each doc occurs at most once per term, so
+// there are no intra-term conflicts) with a CTA barrier between terms, using __dmul_rn /
+// __ddiv_rn / __dadd_rn only -- no FMA contraction, no atomics on scores -- so every score is
+// bit-identical to the oracle.  Selection: touched docs are drained with an atomic exchange
+// (each doc is reported exactly once with its final score, and the accumulator is reset);
+// docs whose score clears the query's running threshold go to its candidate list; the
+// threshold is tightened from a log-scale histogram of emitted scores (a lower bound of the
+// k-th best score so far, so no true top-k doc is ever dropped).
+#include "common.cuh"
+#include "select.cuh"
+#include "exact.cuh"
+
+namespace orag {
+namespace bm25 {
+
+constexpr int kThreads = 256;
+constexpr int kMaxTerms = 64;
+constexpr int kHistBins = 2048;
+constexpr int kBinBase = (1023 - 20) << 5;  // bins start at 2^-20, 32 bins per octave
+
+struct Params {
+    orag_bm25_index_t ix;
+    const int32_t *q_terms;  // [n_queries, max_terms]
+    const int32_t *q_lens;
+    int n_queries;
+    int max_terms;
+    int k;
+    // sparse path
+    unsigned long long *thr_bits;  // [n_queries] bits of the (positive) threshold score
+    uint32_t *cnt;
+    uint32_t *hist;                // [n_queries, kHistBins]
+    int32_t *cand_doc;             // [n_queries, cap] local doc id
+    double *cand_score;            // [n_queries, cap]
+    int cap;
+    // dense path
+    double *dense_out;             // [n_queries, n_docs] pre-zeroed
+    int q_begin;                   // dense chunking: queries [q_begin, q_begin + n_queries)
+};
+
+__device__ __forceinline__ int score_bin(double v)
+{
+    long long e = (__double_as_longlong(v) >> 47) - kBinBase;
+    return e < 0 ? 0 : (e > kHistBins - 1 ? kHistBins - 1 : (int)e);
+}
+__device__ __forceinline__ unsigned long long bin_floor_bits(int b)
+{
+    return (unsigned long long)(b + kBinBase) << 47;
+}
+
+__device__ __noinline__ void emit(const Params &p, int q, int32_t doc, double v)
+{
+    uint32_t slot = atomicAdd(p.cnt + q, 1u);
+    if (slot < (uint32_t)p.cap) {
+        p.cand_doc[(int64_t)q * p.cap + slot] = doc;
+        p.cand_score[(int64_t)q * p.cap + slot] = v;
+    }
+    uint32_t *h = p.hist + (int64_t)q * kHistBins;
+    atomicAdd(h + score_bin(v), 1u);
+    if ((slot & 7u) == 0u) {
+        uint32_t acc = 0;
+        int b = kHistBins - 1;
+        for (; b >= 0; --b) {
+            acc += __ldcg(h + b);
+            if (acc >= (uint32_t)p.k) break;
+        }
+        // one bin below the k-th best's bin: also keeps docs whose NORMALISED score could tie with it
+        if (b >= 2) atomicMax(p.thr_bits + q, bin_floor_bits(b - 1));
+    }
+}
+
+template <bool kDense>
+__global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_constant__ Params p)
+{
+    extern __shared__ double smem_d[];
+    const int T = p.ix.tile_docs;
+    double *acc = smem_d;       // [T]
+    double *t4s = smem_d + T;   // [T]
+    __shared__ int s_start[kMaxTerms];
+    __shared__ int s_len[kMaxTerms];
+    __shared__ double s_idf[kMaxTerms];
+
+    const int V1 = p.ix.vocab + 1;
+    for (int tile = blockIdx.x; tile < p.ix.n_tiles; tile += gridDim.x) {
+        const int64_t base_doc = (int64_t)tile * T;
+        const int nd = (int)min((int64_t)T, p.ix.n_docs - base_doc);
+        __syncthreads();
+        for (int i = threadIdx.x; i < T; i += kThreads) {
+            acc[i] = 0.0;
+            t4s[i] = i < nd ? p.ix.d_doc_t4[base_doc + i] : 1.0;
+        }
+        const uint32_t *tile_post = p.ix.d_postings + p.ix.d_tile_base[tile];
+        const int32_t *toff = p.ix.d_tile_term_off + (int64_t)tile * V1;
+        // stagger the query order across CTAs so a query's threshold is established by few CTAs
+        const int q_shift = (int)(((int64_t)blockIdx.x * 7919) % p.n_queries);
+        for (int qi = 0; qi < p.n_queries; ++qi) {
+            const int q = (qi + q_shift) % p.n_queries;
+            const int nt = min(p.q_lens[q], p.max_terms);
+            __syncthreads();  // previous query's drain is done; term arrays and acc are free
+            if (threadIdx.x < nt) {
+                int t = p.q_terms[(int64_t)q * p.max_terms + threadIdx.x];
+                int st = 0, ln = 0;
+                double idf = 0.0;
+                if (t >= 0 && t < p.ix.vocab) {
+                    idf = p.ix.d_idf[t];
+                    if (idf != 0.0) {
+                        st = toff[t];
+                        ln = toff[t + 1] - st;
+                    }
+                }
+                s_start[threadIdx.x] = st;
+                s_len[threadIdx.x] = ln;
+                s_idf[threadIdx.x] = idf;
+            }
+            __syncthreads();
+            bool touched = false;
+            for (int i = 0; i < nt; ++i) {
+                const int ln = s_len[i];
+                if (ln == 0) continue;  // OOV, zero idf, or no posting in this tile (uniform)
+                touched = true;
+                const double idf = s_idf[i];
+                const uint32_t *pp = tile_post + s_start[i];
+                for (int j = threadIdx.x; j < ln; j += kThreads) {
+                    const uint32_t post = __ldg(pp + j);
+                    const int d = (int)(post >> 16);
+                    const double tf = (double)(post & 0xFFFFu);
+                    const double den = __dadd_rn(tf, t4s[d]);
+                    const double num = __dmul_rn(tf, 2.5);
+                    const double c = __dmul_rn(idf, __ddiv_rn(num, den));
+                    acc[d] = __dadd_rn(acc[d], c);
+                }
+                __syncthreads();  // term i fully applied before term i+1 (query order per doc)
+            }
+            if (!touched) continue;
+            // drain: every touched doc is reported once with its final score; accumulator reset
+            double thr = 0.0;
+            if (!kDense) thr = __longlong_as_double((long long)__ldcg(p.thr_bits + q));
+            for (int i = 0; i < nt; ++i) {
+                const int ln = s_len[i];
+                if (ln == 0) continue;
+                const uint32_t *pp = tile_post + s_start[i];
+                for (int j = threadIdx.x; j < ln; j += kThreads) {
+                    const int d = (int)(__ldg(pp + j) >> 16);
+                    const unsigned long long bits = atomicExch((unsigned long long *)(acc + d), 0ull);
+                    const double v = __longlong_as_double((long long)bits);
+                    if (v != 0.0) {
+                        if (kDense) p.dense_out[(int64_t)(q - p.q_begin) * p.ix.n_docs + base_doc + d] = v;
+                        else if (v >= thr) emit(p, q, (int32_t)(base_doc + d), v);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Exact score of one doc for one query (binary search in each term's run); used only for the
+// rare zero-fill at the end of the sparse path.
+__device__ double score_doc(const orag_bm25_index_t &ix, const int32_t *terms, int nt, int64_t doc)
+{
+    const int T = ix.tile_docs;
+    const int tile = (int)(doc / T);
+    const uint32_t want = (uint32_t)(doc - (int64_t)tile * T);
+    const uint32_t *tile_post = ix.d_postings + ix.d_tile_base[tile];
+    const int32_t *toff = ix.d_tile_term_off + (int64_t)tile * (ix.vocab + 1);
+    const double t4 = ix.d_doc_t4[doc];
+    double s = 0.0;
+    for (int i = 0; i < nt; ++i) {
+        int t = terms[i];
+        if (t < 0 || t >= ix.vocab) continue;
+        double idf = ix.d_idf[t];
+        if (idf == 0.0) continue;
+        int lo = toff[t], hi = toff[t + 1];
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if ((tile_post[mid] >> 16) < want) lo = mid + 1; else hi = mid;
+        }
+        if (lo < toff[t + 1] && (tile_post[lo] >> 16) == want) {
+            double tf = (double)(tile_post[lo] & 0xFFFFu);
+            double c = __dmul_rn(idf, __ddiv_rn(__dmul_rn(tf, 2.5), __dadd_rn(tf, t4)));
+            s = __dadd_rn(s, c);
+        }
+    }
+    return s;
+}
+
+// One CTA per query: exact top-k over the candidate list by (score/max desc, id asc), then
+// zero-score fill (docs untouched by the query rank after all positive ones, in id order).
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ Params p, int64_t doc_id_base, int normalize,
+                                                      int64_t *__restrict__ out_ids, double *__restrict__ out_scores,
+                                                      double *__restrict__ out_max, int32_t *__restrict__ status)
+{
+    __shared__ Pick scratch[32];
+    __shared__ double dscratch[32];
+    const int q = blockIdx.x;
+    const int k = p.k;
+    uint32_t n = p.cnt[q];
+    if (n > (uint32_t)p.cap) {
+        if (status && threadIdx.x == 0) status[q] |= ORAG_STATUS_OVERFLOW;
+        n = p.cap;
+    }
+    const int32_t *cd = p.cand_doc + (int64_t)q * p.cap;
+    const double *cs = p.cand_score + (int64_t)q * p.cap;
+    double mx = -INFINITY;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) mx = fmax(mx, cs[i]);
+    mx = block_max(mx, dscratch);
+    const double raw_max = mx > 0.0 ? mx : 0.0;
+    const double m = mx > 0.0 ? mx : 1.0;
+    if (out_max && threadIdx.x == 0) out_max[q] = normalize ? m : raw_max;
+    double prev_s = INFINITY;
+    int64_t prev_id = -1;
+    int found = 0;
+    for (int r = 0; r < k; ++r) {
+        Pick best;
+        best.valid = 0; best.s = 0.0; best.id = 0;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const int64_t id = doc_id_base + cd[i];
+            const double v = normalize ? __ddiv_rn(cs[i], m) : cs[i];
+            if (r > 0 && !ranks_before(prev_s, prev_id, v, id)) continue;
+            Pick c;
+            c.s = v; c.id = id; c.valid = 1;
+            best = better(best, c);
+        }
+        best = block_best(best, scratch);
+        if (!best.valid) break;
+        if (threadIdx.x == 0) {
+            out_ids[(int64_t)q * k + r] = best.id;
+            out_scores[(int64_t)q * k + r] = best.s;
+        }
+        prev_s = best.s;
+        prev_id = best.id;
+        ++found;
+    }
+    if (found < k && threadIdx.x == 0) {
+        // fewer than k docs with a positive score: the rest of the list is zero-score docs in id order
+        const int nt = min(p.q_lens[q], p.max_terms);
+        const int32_t *terms = p.q_terms + (int64_t)q * p.max_terms;
+        int r = found;
+        for (int64_t d = 0; d < p.ix.n_docs && r < k; ++d) {
+            if (score_doc(p.ix, terms, nt, d) == 0.0) {
+                out_ids[(int64_t)q * k + r] = doc_id_base + d;
+                out_scores[(int64_t)q * k + r] = 0.0;
+                ++r;
+            }
+        }
+        for (; r < k; ++r) {
+            out_ids[(int64_t)q * k + r] = -1;
+            out_scores[(int64_t)q * k + r] = 0.0;
+        }
+    }
+}
+
+__global__ void init_state_kernel(unsigned long long *thr_bits, uint32_t *cnt, uint32_t *hist, int n_queries)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)n_queries * kHistBins;
+    if (i < total) hist[i] = 0;
+    if (i < n_queries) {
+        thr_bits[i] = 1ull;  // smallest positive double: "score > 0"
+        cnt[i] = 0;
+    }
+}
+
+}  // namespace bm25
+
+}  // namespace orag
+
+using orag::bm25::Params;
+
+static int validate_index(const orag_bm25_index_t *ix)
+{
+    ORAG_REQUIRE(ix != nullptr, "index");
+    ORAG_REQUIRE(ix->n_docs >= 0 && ix->vocab > 0, "index sizes");
+    ORAG_REQUIRE(ix->tile_docs >= 32 && ix->tile_docs <= 65536 && (ix->tile_docs & (ix->tile_docs - 1)) == 0,
+                 "tile_docs must be a power of two in [32, 65536]");
+    ORAG_REQUIRE((int64_t)ix->n_tiles == (ix->n_docs + ix->tile_docs - 1) / ix->tile_docs, "n_tiles");
+    ORAG_REQUIRE(ix->tile_docs * 16 <= 200 * 1024, "tile_docs too large for shared memory");
+    if (ix->n_docs > 0)
+        ORAG_REQUIRE(ix->d_tile_base && ix->d_tile_term_off && ix->d_postings && ix->d_doc_t4 && ix->d_idf,
+                     "index pointers");
+    return ORAG_OK;
+}
+
+static size_t dense_chunk_queries(const orag_bm25_index_t *ix, int n_queries)
+{
+    const size_t budget = (size_t)256 << 20;
+    size_t per_q = (size_t)(ix->n_docs > 0 ? ix->n_docs : 1) * sizeof(double);
+    size_t c = budget / per_q;
+    if (c < 1) c = 1;
+    if (c > (size_t)n_queries) c = (size_t)n_queries;
+    return c;
+}
+
+static bool use_dense(const orag_bm25_index_t *ix, int n_queries, int flags)
+{
+    if (flags & ORAG_BM25_FORCE_DENSE) return true;
+    if (ix->has_negative_idf) return true;
+    if (flags & ORAG_BM25_FORCE_SPARSE) return false;
+    return (size_t)n_queries * (size_t)ix->n_docs * sizeof(double) <= ((size_t)64 << 20);
+}
+
+static int sparse_cap(int n_queries)
+{
+    // ~96 MiB of candidate storage shared by the batch, at least 8192 slots per query
+    int64_t cap = ((int64_t)96 << 20) / 12 / (n_queries > 0 ? n_queries : 1);
+    if (cap < 8192) cap = 8192;
+    if (cap > (1 << 22)) cap = 1 << 22;
+    return (int)cap;
+}
+
+extern "C" size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *ix, int n_queries, int k, int flags)
+{
+    if (!ix || n_queries <= 0) return 0;
+    (void)k;
+    if (use_dense(ix, n_queries, flags))
+        return orag::align_up(dense_chunk_queries(ix, n_queries) * (size_t)(ix->n_docs > 0 ? ix->n_docs : 1) * 8, 256);
+    const size_t cap = sparse_cap(n_queries);
+    size_t b = 0;
+    b += orag::align_up((size_t)n_queries * 8, 256);                        // thr_bits
+    b += orag::align_up((size_t)n_queries * 4, 256);                        // cnt
+    b += orag::align_up((size_t)n_queries * orag::bm25::kHistBins * 4, 256);  // hist
+    b += orag::align_up((size_t)n_queries * cap * 4, 256);                  // cand_doc
+    b += orag::align_up((size_t)n_queries * cap * 8, 256);                  // cand_score
+    return b;
+}
+
+static int launch_tiles(const Params &p, bool dense, cudaStream_t st)
+{
+    const size_t smem = (size_t)p.ix.tile_docs * 16;
+    int grid = p.ix.n_tiles;
+    int per_sm = (int)((200 * 1024) / (smem + 2048));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 6) per_sm = 6;
+    int lim = orag::sm_count() * per_sm;
+    if (grid > lim) grid = lim;
+    if (grid < 1) return ORAG_OK;
+    if (dense) {
+        ORAG_CUDA_CHECK(cudaFuncSetAttribute(orag::bm25::bm25_tile_kernel<true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        orag::bm25::bm25_tile_kernel<true><<<grid, orag::bm25::kThreads, smem, st>>>(p);
+    } else {
+        ORAG_CUDA_CHECK(cudaFuncSetAttribute(orag::bm25::bm25_tile_kernel<false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        orag::bm25::bm25_tile_kernel<false><<<grid, orag::bm25::kThreads, smem, st>>>(p);
+    }
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+extern "C" int orag_bm25_dense(const orag_bm25_index_t *ix, const int32_t *d_query_terms, const int32_t *d_query_lens,
+                               int n_queries, int max_terms, double *d_out, void *stream)
+{
+    int rc = validate_index(ix);
+    if (rc) return rc;
+    ORAG_REQUIRE(d_query_terms && d_query_lens && d_out && n_queries > 0, "bm25_dense");
+    ORAG_REQUIRE(max_terms > 0 && max_terms <= orag::bm25::kMaxTerms, "max_terms in [1, 64]");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ix->n_docs == 0) return ORAG_OK;
+    ORAG_CUDA_CHECK(cudaMemsetAsync(d_out, 0, (size_t)n_queries * ix->n_docs * sizeof(double), st));
+    Params p{};
+    p.ix = *ix;
+    p.q_terms = d_query_terms;
+    p.q_lens = d_query_lens;
+    p.n_queries = n_queries;
+    p.max_terms = max_terms;
+    p.dense_out = d_out;
+    p.q_begin = 0;
+    return launch_tiles(p, true, st);
+}
+
+extern "C" int orag_bm25_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_query_terms,
+                              const int32_t *d_query_lens, int n_queries, int max_terms, int k, int flags,
+                              int64_t *d_out_ids, double *d_out_scores, double *d_out_max, int32_t *d_out_status,
+                              void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    int rc = validate_index(ix);
+    if (rc) return rc;
+    ORAG_REQUIRE(d_query_terms && d_query_lens && d_out_ids && d_out_scores && n_queries > 0 && k > 0, "bm25_topk");
+    ORAG_REQUIRE(max_terms > 0 && max_terms <= orag::bm25::kMaxTerms, "max_terms in [1, 64]");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int normalize = (flags & ORAG_BM25_NORMALIZE) ? 1 : 0;
+    if (workspace_bytes < orag_bm25_workspace_bytes(ix, n_queries, k, flags) || (!d_workspace && ix->n_docs > 0)) {
+        orag::set_error("bm25_topk: workspace too small (%zu < %zu)", workspace_bytes,
+                        orag_bm25_workspace_bytes(ix, n_queries, k, flags));
+        return ORAG_EWORKSPACE;
+    }
+    if (d_out_status) ORAG_CUDA_CHECK(cudaMemsetAsync(d_out_status, 0, (size_t)n_queries * sizeof(int32_t), st));
+
+    if (use_dense(ix, n_queries, flags)) {
+        const int chunk = (int)dense_chunk_queries(ix, n_queries);
+        double *dense = (double *)d_workspace;
+        for (int q0 = 0; q0 < n_queries; q0 += chunk) {
+            const int nq = (n_queries - q0) < chunk ? (n_queries - q0) : chunk;
+            if (ix->n_docs > 0) {
+                ORAG_CUDA_CHECK(cudaMemsetAsync(dense, 0, (size_t)nq * ix->n_docs * sizeof(double), st));
+                Params p{};
+                p.ix = *ix;
+                p.q_terms = d_query_terms + (int64_t)q0 * max_terms;
+                p.q_lens = d_query_lens + q0;
+                p.n_queries = nq;
+                p.max_terms = max_terms;
+                p.dense_out = dense;
+                p.q_begin = 0;
+                rc = launch_tiles(p, true, st);
+                if (rc) return rc;
+            }
+            rc = orag::launch_select_topk(dense, nullptr, nullptr, ix->n_docs, ix->n_docs, nq, k, doc_id_base,
+                                          normalize ? 1 : 2, nullptr, 0, d_out_ids + (int64_t)q0 * k,
+                                          d_out_scores + (int64_t)q0 * k, d_out_max ? d_out_max + q0 : nullptr, nullptr,
+                                          st);
+            if (rc) return rc;
+        }
+        return ORAG_OK;
+    }
+
+    // ---- sparse (candidate) path ----
+    const int cap = sparse_cap(n_queries);
+    uint8_t *w = (uint8_t *)d_workspace;
+    Params p{};
+    p.ix = *ix;
+    p.q_terms = d_query_terms;
+    p.q_lens = d_query_lens;
+    p.n_queries = n_queries;
+    p.max_terms = max_terms;
+    p.k = k;
+    p.cap = cap;
+    p.thr_bits = (unsigned long long *)w; w += orag::align_up((size_t)n_queries * 8, 256);
+    p.cnt = (uint32_t *)w;                w += orag::align_up((size_t)n_queries * 4, 256);
+    p.hist = (uint32_t *)w;               w += orag::align_up((size_t)n_queries * orag::bm25::kHistBins * 4, 256);
+    p.cand_doc = (int32_t *)w;            w += orag::align_up((size_t)n_queries * cap * 4, 256);
+    p.cand_score = (double *)w;
+    {
+        int64_t total = (int64_t)n_queries * orag::bm25::kHistBins;
+        orag::bm25::init_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.thr_bits, p.cnt, p.hist,
+                                                                                      n_queries);
+        ORAG_LAUNCH_CHECK();
+    }
+    rc = launch_tiles(p, false, st);
+    if (rc) return rc;
+    orag::bm25::finalize_kernel<<<n_queries, 256, 0, st>>>(p, doc_id_base, normalize, d_out_ids, d_out_scores, d_out_max,
+                                                           d_out_status);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}

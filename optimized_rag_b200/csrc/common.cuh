@@ -1,0 +1,121 @@
+// common.cuh -- shared helpers for the sm_100a kernels (error plumbing, hashing,
+// the reference's float64 cosine arithmetic as device functions).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/orag.h"
+
+namespace orag {
+
+void set_error(const char *fmt, ...);
+
+#define ORAG_CUDA_CHECK(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            orag::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return ORAG_ECUDA;                                                             \
+        }                                                                                  \
+    } while (0)
+
+#define ORAG_REQUIRE(cond, msg)                                                            \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            orag::set_error("invalid argument: %s (%s) (%s:%d)", msg, #cond, __FILE__, __LINE__); \
+            return ORAG_EINVAL;                                                            \
+        }                                                                                  \
+    } while (0)
+
+#define ORAG_LAUNCH_CHECK()                                                                \
+    do {                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) {                                                           \
+            orag::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return ORAG_ECUDA;                                                             \
+        }                                                                                  \
+    } while (0)
+
+inline int sm_count()
+{
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        if (cached <= 0) cached = 148;
+    }
+    return cached;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- counter-based hashing (mirrors optimized_rag_b200/synthetic.py) --------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+#define ORAG_K_ROW 0xD1B54A32D192ED03ull
+#define ORAG_K_DOC 0x9FB21C651E98DF25ull
+#define ORAG_K_DUP 0xA24BAED4963EE407ull
+
+__host__ __device__ __forceinline__ uint64_t row_key(uint64_t seed, uint64_t row)
+{
+    return mix64(seed ^ (row * ORAG_K_ROW));
+}
+
+// ---- the reference's float64 cosine (rag/retrieval.py:362-371 under CPython >= 3.12) ---------
+// Neumaier-compensated running sum, exactly as builtin_sum() performs it for floats.
+struct NeuSum {
+    double s, c;
+    bool first;
+    __device__ __forceinline__ void init() { s = 0.0; c = 0.0; first = true; }
+    __device__ __forceinline__ void add(double x)
+    {
+        if (first) { s = x; first = false; return; }
+        double t = __dadd_rn(s, x);
+        if (fabs(s) >= fabs(x)) c = __dadd_rn(c, __dadd_rn(__dadd_rn(s, -t), x));
+        else                    c = __dadd_rn(c, __dadd_rn(__dadd_rn(x, -t), s));
+        s = t;
+    }
+    __device__ __forceinline__ double result() const
+    {
+        if (first) return 0.0;
+        if (c != 0.0 && isfinite(c)) return __dadd_rn(s, c);
+        return s;
+    }
+};
+
+// cosine from the three sums
+__device__ __forceinline__ double cosine_from_sums(double dot, double sq_q, double sq_r)
+{
+    double m1 = sqrt(sq_q);
+    double m2 = sqrt(sq_r);
+    if (m1 == 0.0 || m2 == 0.0) return 0.0;
+    return __ddiv_rn(dot, __dmul_rn(m1, m2));
+}
+
+// ---- ordering helpers ---------------------------------------------------------------------------
+// true when (s1,id1) ranks strictly before (s2,id2): score desc, id asc
+__device__ __forceinline__ bool ranks_before(double s1, int64_t id1, double s2, int64_t id2)
+{
+    return (s1 > s2) || (s1 == s2 && id1 < id2);
+}
+
+// monotone map float -> uint32 so that unsigned compare == float compare (for atomicMax)
+__device__ __forceinline__ uint32_t float_to_ordered(float f)
+{
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u)
+{
+    uint32_t b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    return __uint_as_float(b);
+}
+
+}  // namespace orag

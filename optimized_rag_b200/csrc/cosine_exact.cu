@@ -1,0 +1,313 @@
+// cosine_exact.cu -- the reference's float64 cosine on CUDA cores, plus exact selection.
+//
+//   * warp_score_rows: lane <-> corpus row, rows staged through shared memory with coalesced
+//     128-byte loads, every (row, query) pair accumulated sequentially in the exact order and
+//     arithmetic of rag/retrieval.py:362-371 (Neumaier sums, see common.cuh) -> BIT-EXACT scores.
+//   * cosine_dense_kernel: all rows x all queries (anchor, small-N path, overflow fallback)
+//   * rescore_kernel: the candidate rows emitted by the tensor-core first pass (cosine_tc.cu)
+//   * select_topk_kernel: generic exact top-k by (score desc, id asc), optional max-normalisation
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "select.cuh"
+#include "exact.cuh"
+
+namespace orag {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_inv_norms_kernel(const float *__restrict__ corpus, int64_t n_rows, int dim,
+                                                           float *__restrict__ inv_norm)
+{
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+        const float4 *p = reinterpret_cast<const float4 *>(corpus + r * (int64_t)dim);
+        float acc = 0.f;
+        int n4 = dim >> 2;
+        for (int j = lane; j < n4; j += 32) {
+            float4 v = __ldg(p + j);
+            acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) inv_norm[r] = acc > 0.f ? rsqrtf(acc) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4 *__restrict__ src, uint2 *__restrict__ dst,
+                                                         int64_t n4)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        float4 v = __ldg(src + i);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t *>(&lo);
+        o.y = *reinterpret_cast<uint32_t *>(&hi);
+        dst[i] = o;
+    }
+}
+
+// sum(q*q) per query, sequential Neumaier (one thread per query; B is at most a few thousand)
+__global__ void query_sq_kernel(const float *__restrict__ queries, int n_queries, int dim, double *__restrict__ sq)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries) return;
+    const float *p = queries + (int64_t)q * dim;
+    NeuSum s;
+    s.init();
+    for (int j = 0; j < dim; ++j) {
+        double a = (double)p[j];
+        s.add(__dmul_rn(a, a));
+    }
+    sq[q] = s.result();
+}
+
+constexpr int kDenseQB = 4;
+
+// out[q * n_rows + r] = cosine(query q, row r)
+__global__ void __launch_bounds__(256) cosine_dense_kernel(const float *__restrict__ corpus, int64_t n_rows, int dim,
+                                                          const float *__restrict__ queries, int n_queries,
+                                                          const double *__restrict__ sq_q, double *__restrict__ out)
+{
+    __shared__ float stage_all[8][32 * 33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float *stage = stage_all[wib];
+    int64_t warp = blockIdx.x * (int64_t)(blockDim.x >> 5) + wib;
+    int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t n_blocks = (n_rows + 31) / 32;
+    for (int64_t rb = warp; rb < n_blocks; rb += n_warps) {
+        int64_t r = rb * 32 + lane;
+        const float *rowptr = r < n_rows ? corpus + r * (int64_t)dim : nullptr;
+        double sq_r = 0.0;
+        for (int q0 = 0; q0 < n_queries; q0 += kDenseQB) {
+            const float *qp[kDenseQB];
+#pragma unroll
+            for (int b = 0; b < kDenseQB; ++b) qp[b] = (q0 + b < n_queries) ? queries + (int64_t)(q0 + b) * dim : nullptr;
+            NeuSum dot[kDenseQB], sq;
+            warp_score_rows<kDenseQB>(rowptr, qp, dim, stage, dot, sq, q0 == 0);
+            if (q0 == 0) sq_r = sq.result();
+            if (r < n_rows) {
+#pragma unroll
+                for (int b = 0; b < kDenseQB; ++b)
+                    if (q0 + b < n_queries)
+                        out[(int64_t)(q0 + b) * n_rows + r] = cosine_from_sums(dot[b].result(), sq_q[q0 + b], sq_r);
+            }
+        }
+    }
+}
+
+// Re-score candidate rows: cand[q * cap + slot] (local row) -> scores / global ids.
+// grid.x covers (query, 32-slot chunk) pairs; blocks past the query's count exit at once.
+__global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ corpus, int dim, int64_t row_id_base,
+                                                     const float *__restrict__ queries, const double *__restrict__ sq_q,
+                                                     const int32_t *__restrict__ cand, const uint32_t *__restrict__ cnt,
+                                                     int cap, int n_queries, double *__restrict__ out_scores,
+                                                     int64_t *__restrict__ out_ids)
+{
+    __shared__ float stage_all[8][32 * 33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int chunks_per_q = (cap + 31) / 32;
+    int64_t warp = blockIdx.x * (int64_t)(blockDim.x >> 5) + wib;
+    int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t w = warp; w < (int64_t)n_queries * chunks_per_q; w += n_warps) {
+        int q = (int)(w / chunks_per_q);
+        int chunk = (int)(w % chunks_per_q);
+        uint32_t n = min(cnt[q], (uint32_t)cap);
+        if ((uint32_t)chunk * 32u >= n) continue;
+        uint32_t slot = chunk * 32 + lane;
+        int32_t row = slot < n ? cand[(int64_t)q * cap + slot] : -1;
+        const float *rowptr = row >= 0 ? corpus + (int64_t)row * dim : nullptr;
+        const float *qp[1] = {queries + (int64_t)q * dim};
+        NeuSum dot[1], sq;
+        warp_score_rows<1>(rowptr, qp, dim, stage_all[wib], dot, sq, true);
+        if (row >= 0) {
+            out_scores[(int64_t)q * cap + slot] = cosine_from_sums(dot[0].result(), sq_q[q], sq.result());
+            out_ids[(int64_t)q * cap + slot] = row_id_base + row;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic exact top-k.  Entry i of query q: score = scores[q*ld + i]; id = ids ? ids[q*ld + i] : id_base + i
+// (entries with id < 0 are skipped).  n_q = counts ? min(counts[q], cap_n) : n.
+// normalize: divide by max (if > 0, else 1.0) before ranking; ext_max [q, n_ext] supplies extra
+// maxima (per-shard BM25 maxima after the all-gather).
+__global__ void __launch_bounds__(256) select_topk_kernel(const double *__restrict__ scores, const int64_t *__restrict__ ids,
+                                                         const uint32_t *__restrict__ counts, int64_t n, int64_t ld,
+                                                         int k, int64_t id_base, int normalize,
+                                                         const double *__restrict__ ext_max, int n_ext,
+                                                         int64_t *__restrict__ out_ids, double *__restrict__ out_scores,
+                                                         double *__restrict__ out_max, int32_t *__restrict__ status)
+{
+    __shared__ Pick scratch[32];
+    __shared__ double dscratch[32];
+    const int q = blockIdx.x;
+    const double *s = scores + (int64_t)q * ld;
+    const int64_t *idp = ids ? ids + (int64_t)q * ld : nullptr;
+    int64_t nq = n;
+    if (counts) {
+        uint32_t c = counts[q];
+        if ((int64_t)c > n) {
+            if (status && threadIdx.x == 0) status[q] |= ORAG_STATUS_OVERFLOW;
+            c = (uint32_t)n;
+        }
+        nq = c;
+    }
+    // normalize: 0 = rank raw scores; 1 = divide by max (if > 0 else 1.0) and report that divisor;
+    //            2 = rank raw scores but report max(raw max, 0) (per-shard maximum for a later merge)
+    double m = 1.0;
+    if (normalize) {
+        double mx = -INFINITY;
+        for (int64_t i = threadIdx.x; i < nq; i += blockDim.x)
+            if (!idp || idp[i] >= 0) mx = fmax(mx, s[i]);
+        for (int e = threadIdx.x; e < n_ext; e += blockDim.x) mx = fmax(mx, ext_max[(int64_t)q * n_ext + e]);
+        mx = block_max(mx, dscratch);
+        if (mx > 0.0) m = mx;
+        if (out_max && threadIdx.x == 0) out_max[q] = (normalize == 2) ? (mx > 0.0 ? mx : 0.0) : m;
+        if (normalize == 2) normalize = 0;
+    }
+    double prev_s = INFINITY;
+    int64_t prev_id = -1;
+    for (int r = 0; r < k; ++r) {
+        Pick best;
+        best.valid = 0; best.s = 0.0; best.id = 0;
+        for (int64_t i = threadIdx.x; i < nq; i += blockDim.x) {
+            int64_t id = idp ? idp[i] : id_base + i;
+            if (id < 0) continue;
+            double v = normalize ? __ddiv_rn(s[i], m) : s[i];
+            // strictly after the previous pick
+            if (r > 0 && !ranks_before(prev_s, prev_id, v, id)) continue;
+            Pick c;
+            c.s = v; c.id = id; c.valid = 1;
+            best = better(best, c);
+        }
+        best = block_best(best, scratch);
+        if (threadIdx.x == 0) {
+            out_ids[(int64_t)q * k + r] = best.valid ? best.id : -1;
+            out_scores[(int64_t)q * k + r] = best.valid ? best.s : 0.0;
+        }
+        if (!best.valid) {
+            for (int r2 = r + 1 + threadIdx.x; r2 < k; r2 += blockDim.x) {
+                out_ids[(int64_t)q * k + r2] = -1;
+                out_scores[(int64_t)q * k + r2] = 0.0;
+            }
+            break;
+        }
+        prev_s = best.s;
+        prev_id = best.id;
+    }
+}
+
+int launch_select_topk(const double *scores, const int64_t *ids, const uint32_t *counts, int64_t n, int64_t ld,
+                       int n_queries, int k, int64_t id_base, int normalize, const double *ext_max, int n_ext,
+                       int64_t *out_ids, double *out_scores, double *out_max, int32_t *status, cudaStream_t st)
+{
+    if (n_queries <= 0 || k <= 0) return ORAG_OK;
+    select_topk_kernel<<<n_queries, 256, 0, st>>>(scores, ids, counts, n, ld, k, id_base, normalize, ext_max, n_ext,
+                                                   out_ids, out_scores, out_max, status);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+int launch_query_sq(const float *queries, int n_queries, int dim, double *sq, cudaStream_t st)
+{
+    query_sq_kernel<<<(n_queries + 63) / 64, 64, 0, st>>>(queries, n_queries, dim, sq);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+int launch_cosine_dense(const float *corpus, int64_t n_rows, int dim, const float *queries, int n_queries,
+                        const double *sq_q, double *out, cudaStream_t st)
+{
+    int64_t blocks = ((n_rows + 31) / 32 + 7) / 8;
+    int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    cosine_dense_kernel<<<(unsigned)blocks, 256, 0, st>>>(corpus, n_rows, dim, queries, n_queries, sq_q, out);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+int launch_rescore(const float *corpus, int dim, int64_t row_id_base, const float *queries, const double *sq_q,
+                   const int32_t *cand, const uint32_t *cnt, int cap, int n_queries, double *out_scores,
+                   int64_t *out_ids, cudaStream_t st)
+{
+    int64_t warps = (int64_t)n_queries * ((cap + 31) / 32);
+    int64_t blocks = (warps + 7) / 8;
+    int64_t lim = (int64_t)sm_count() * 8;
+    if (blocks > lim) blocks = lim;
+    if (blocks < 1) blocks = 1;
+    rescore_kernel<<<(unsigned)blocks, 256, 0, st>>>(corpus, dim, row_id_base, queries, sq_q, cand, cnt, cap,
+                                                     n_queries, out_scores, out_ids);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+}  // namespace orag
+
+// ================================================================================================
+extern "C" int orag_row_inv_norms(const float *d_corpus, int64_t n_rows, int dim, float *d_inv_norm, void *stream)
+{
+    ORAG_REQUIRE(d_corpus && d_inv_norm && n_rows >= 0 && dim > 0 && dim % 4 == 0, "row_inv_norms");
+    ORAG_REQUIRE((reinterpret_cast<uintptr_t>(d_corpus) & 15) == 0, "corpus must be 16-byte aligned");
+    if (n_rows == 0) return ORAG_OK;
+    int64_t blocks = (n_rows + 7) / 8;
+    int64_t cap = (int64_t)orag::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    orag::row_inv_norms_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_corpus, n_rows, dim, d_inv_norm);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+extern "C" int orag_f32_to_bf16(const float *d_src, void *d_dst, int64_t count, void *stream)
+{
+    ORAG_REQUIRE(d_src && d_dst && count >= 0 && count % 4 == 0, "f32_to_bf16: count % 4 == 0");
+    ORAG_REQUIRE((reinterpret_cast<uintptr_t>(d_src) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_dst) & 7) == 0,
+                 "alignment");
+    if (count == 0) return ORAG_OK;
+    int64_t n4 = count / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    int64_t cap = (int64_t)orag::sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    orag::f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(d_src), reinterpret_cast<uint2 *>(d_dst), n4);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+extern "C" int orag_dense_topk(const double *d_scores, int64_t n, int64_t ld, int n_queries, int k, int64_t id_base,
+                               int normalize, int64_t *d_out_ids, double *d_out_scores, double *d_out_max, void *stream)
+{
+    ORAG_REQUIRE(d_scores && d_out_ids && d_out_scores && n >= 0 && ld >= n && k > 0 && n_queries >= 0, "dense_topk");
+    return orag::launch_select_topk(d_scores, nullptr, nullptr, n, ld, n_queries, k, id_base, normalize, nullptr, 0,
+                                    d_out_ids, d_out_scores, d_out_max, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int orag_topk_merge(const int64_t *d_cand_ids, const double *d_cand_scores, int m, int n_queries, int k,
+                               const double *d_shard_max, int n_shards, int64_t *d_out_ids, double *d_out_scores,
+                               double *d_out_max, void *stream)
+{
+    ORAG_REQUIRE(d_cand_ids && d_cand_scores && d_out_ids && d_out_scores && m >= 0 && k > 0, "topk_merge");
+    int normalize = d_shard_max != nullptr;
+    return orag::launch_select_topk(d_cand_scores, d_cand_ids, nullptr, m, m, n_queries, k, 0, normalize, d_shard_max,
+                                    normalize ? n_shards : 0, d_out_ids, d_out_scores, d_out_max, nullptr,
+                                    (cudaStream_t)stream);
+}
+
+extern "C" int orag_cosine_dense(const float *d_corpus, int64_t n_rows, int dim, const float *d_queries, int n_queries,
+                                 double *d_out, void *stream)
+{
+    ORAG_REQUIRE(d_corpus && d_queries && d_out && n_rows >= 0 && dim > 0 && n_queries > 0, "cosine_dense");
+    // sq_q lives at the tail of d_out?  No: keep the ABI allocation-free by computing it into the
+    // first n_queries doubles of a row that is overwritten afterwards is not possible either, so the
+    // caller-visible contract is: d_out holds n_queries * n_rows + n_queries doubles.
+    double *sq = d_out + (int64_t)n_queries * n_rows;
+    int rc = orag::launch_query_sq(d_queries, n_queries, dim, sq, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (n_rows == 0) return ORAG_OK;
+    return orag::launch_cosine_dense(d_corpus, n_rows, dim, d_queries, n_queries, sq, d_out, (cudaStream_t)stream);
+}

@@ -1,0 +1,54 @@
+// cosine_tc.cuh -- shared declarations of the tcgen05 similarity scan (cosine_tc.cu) for api.cu / pairwise.cu
+#pragma once
+#include "common.cuh"
+
+namespace orag {
+namespace tc {
+
+constexpr int kTileM = 128;
+constexpr int kMaxN = 256;
+constexpr int kStages = 4;
+constexpr int kABytes = kTileM * 128;  // 16 KiB
+constexpr int kBBytes = kMaxN * 128;   // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kEpiThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr int kHistBins = 1024;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ +
+                              2 * kMaxN * sizeof(float);
+
+struct ScanParams {
+    int64_t row_begin;      // first corpus row of this launch (multiple of 128 not required)
+    int64_t row_end;        // one past the last valid row
+    int num_tiles;
+    int k_chunks;           // dim * elem_bytes / 128
+    int chunk_elems;        // 32 (tf32) or 64 (bf16)
+    int n_queries;
+    int umma_n;             // round_up(n_queries, 16)
+    uint32_t idesc;
+    const float *inv_norm;  // [rows]
+    int dense;              // 1: store every v to dense_out[(row - row_begin) * 256 + q]
+    float *dense_out;
+    // scan-mode state (per query)
+    uint32_t *thr_key;      // ordered-uint of the threshold cosine
+    uint32_t *cnt;
+    uint32_t *hist;         // [n_queries, kHistBins]
+    int32_t *cand;          // [n_queries, cap] local row ids
+    int cap;
+    const float *qnorm;     // |q| as fp32
+    const float *inv_qnorm;
+    float margin;           // 2 * eps (cosine units)
+    int k;
+};
+
+int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_base, int dim, ScanParams p,
+                cudaStream_t st);
+int launch_seed_finalize(const float *seed, int n_seed, int n_queries, int k, float margin, const float *qnorm,
+                         const float *inv_qnorm, uint32_t *thr_key, uint32_t *cnt, uint32_t *hist, int32_t *cand,
+                         int cap, cudaStream_t st);
+int launch_query_norms(const double *sq, int n, float *qnorm, float *inv_qnorm, cudaStream_t st);
+
+}  // namespace tc
+}  // namespace orag

@@ -1,0 +1,248 @@
+"""Tensor-level Python surface over the C ABI (include/orag.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every computation on the retrieval
+hot path is a call into csrc/liborag.so.  Nothing in this module falls back to torch or CPU math.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _ffi
+from .bm25_index import Bm25Index
+
+MODE = {"exact": _ffi.ORAG_COS_EXACT, "tf32": _ffi.ORAG_COS_TF32, "bf16": _ffi.ORAG_COS_BF16}
+SMALL_N = 4096  # below this the exact CUDA-core scan is used directly
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _ffi.OragError(f"{name} must live on a CUDA device (no CPU path exists)")
+
+
+# --------------------------------------------------------------------------- synthetic fills
+def gen_embeddings(n_rows: int, dim: int, row_start: int, seed: int, dup_per_mille: int = 0,
+                   device="cuda", out: torch.Tensor | None = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty((n_rows, dim), dtype=torch.float32, device=device)
+    _ffi.check(_ffi.lib().orag_gen_embeddings(out.data_ptr(), n_rows, dim, row_start, seed, dup_per_mille,
+                                              _stream(out.device)), "orag_gen_embeddings")
+    return out
+
+
+def gen_token_corpus(n_docs: int, doc_start: int, seed: int, thresholds: np.ndarray, vocab: int, lmin: int = 100,
+                     lmax: int = 300, device="cuda"):
+    """(doc_off int64 [n+1], tokens int32 [total]) on `device`, bit-identical to synthetic.token_corpus."""
+    dev = torch.device(device)
+    lens = torch.empty(n_docs, dtype=torch.int32, device=dev)
+    _ffi.check(_ffi.lib().orag_gen_doc_lengths(lens.data_ptr(), n_docs, doc_start, seed, lmin, lmax, _stream(dev)),
+               "orag_gen_doc_lengths")
+    doc_off = torch.zeros(n_docs + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens, dim=0, out=doc_off[1:])
+    total = int(doc_off[-1].item())
+    thr = torch.from_numpy(thresholds.view(np.int64)).to(dev)
+    tokens = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    _ffi.check(_ffi.lib().orag_gen_tokens(tokens.data_ptr(), doc_off.data_ptr(), n_docs, doc_start, seed,
+                                          thr.data_ptr(), vocab, _stream(dev)), "orag_gen_tokens")
+    return doc_off, tokens[:total]
+
+
+# --------------------------------------------------------------------------- cosine
+class CosineIndex:
+    """One shard of chunk embeddings resident in HBM: fp32 rows (+ fp32 inverse norms, + optional bf16
+    shadow copy for the bf16 first pass).  `topk` = exact float64 cosine top-k (see orag_cosine_topk)."""
+
+    def __init__(self, corpus: torch.Tensor, row_id_base: int = 0, mode: str = "auto", shadow: bool | None = None):
+        _require_cuda(corpus, "corpus")
+        assert corpus.dtype == torch.float32 and corpus.dim() == 2 and corpus.is_contiguous()
+        self.corpus = corpus
+        self.device = corpus.device
+        self.n_rows, self.dim = corpus.shape
+        self.row_id_base = int(row_id_base)
+        if mode == "auto":
+            if self.n_rows < SMALL_N or self.dim % 32 != 0:
+                mode = "exact"
+            else:
+                mode = "bf16" if (shadow and self.dim % 64 == 0) else "tf32"
+        self.mode = mode
+        self.inv_norm = None
+        self.shadow = None
+        if mode != "exact":
+            self.inv_norm = torch.empty(self.n_rows, dtype=torch.float32, device=self.device)
+            _ffi.check(_ffi.lib().orag_row_inv_norms(corpus.data_ptr(), self.n_rows, self.dim,
+                                                     self.inv_norm.data_ptr(), _stream(self.device)),
+                       "orag_row_inv_norms")
+        if mode == "bf16":
+            self.shadow = torch.empty((self.n_rows, self.dim), dtype=torch.bfloat16, device=self.device)
+            # convert in slabs to keep the launch grid bounded
+            _ffi.check(_ffi.lib().orag_f32_to_bf16(corpus.data_ptr(), self.shadow.data_ptr(),
+                                                   self.n_rows * self.dim, _stream(self.device)), "orag_f32_to_bf16")
+        self._ws = {}
+
+    def _workspace(self, n_queries: int, k: int, mode: int) -> torch.Tensor:
+        need = int(_ffi.lib().orag_cosine_workspace_bytes(self.n_rows, self.dim, n_queries, k, mode))
+        ws = self._ws.get(mode)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+            self._ws[mode] = ws
+        return ws
+
+    def topk(self, queries: torch.Tensor, k: int, mode: str | None = None, check_overflow: bool = True):
+        """queries fp32 [B, dim] on the same device -> (ids int64 [B,k], scores float64 [B,k])."""
+        _require_cuda(queries, "queries")
+        assert queries.dtype == torch.float32 and queries.is_contiguous() and queries.shape[1] == self.dim
+        m = MODE[mode or self.mode]
+        if m != _ffi.ORAG_COS_EXACT and self.inv_norm is None:
+            raise _ffi.OragError("index was built for the exact path only")
+        if m == _ffi.ORAG_COS_BF16 and self.shadow is None:
+            raise _ffi.OragError("index has no bf16 shadow copy")
+        Bq = queries.shape[0]
+        ids = torch.empty((Bq, k), dtype=torch.int64, device=self.device)
+        sc = torch.empty((Bq, k), dtype=torch.float64, device=self.device)
+        status = torch.empty(Bq, dtype=torch.int32, device=self.device)
+        ws = self._workspace(Bq, k, m)
+        _ffi.check(_ffi.lib().orag_cosine_topk(
+            self.corpus.data_ptr(), self.inv_norm.data_ptr() if self.inv_norm is not None else None,
+            self.shadow.data_ptr() if self.shadow is not None else None, self.n_rows, self.dim, self.row_id_base,
+            queries.data_ptr(), Bq, k, m, ids.data_ptr(), sc.data_ptr(), status.data_ptr(), ws.data_ptr(),
+            ws.numel(), _stream(self.device)), "orag_cosine_topk")
+        if check_overflow and m != _ffi.ORAG_COS_EXACT:
+            bad = torch.nonzero(status != 0).flatten()
+            if bad.numel():
+                # more near-ties than candidate slots: exact scan for these queries (still on the GPU)
+                i2, s2 = self.topk(queries[bad].contiguous(), k, mode="exact", check_overflow=False)
+                ids[bad], sc[bad] = i2, s2
+        return ids, sc
+
+    def dense(self, queries: torch.Tensor) -> torch.Tensor:
+        """float64 cosine matrix [B, n_rows] (reference arithmetic; tests, small corpora, weighted hybrid)."""
+        Bq = queries.shape[0]
+        buf = torch.empty(Bq * self.n_rows + Bq, dtype=torch.float64, device=self.device)
+        _ffi.check(_ffi.lib().orag_cosine_dense(self.corpus.data_ptr(), self.n_rows, self.dim, queries.data_ptr(), Bq,
+                                                buf.data_ptr(), _stream(self.device)), "orag_cosine_dense")
+        return buf[:Bq * self.n_rows].view(Bq, self.n_rows)
+
+    def firstpass_dense(self, queries: torch.Tensor, mode: str) -> torch.Tensor:
+        """Raw tensor-core first-pass values (dot * inv_norm[row]) fp32 [n_rows, B] -- test hook."""
+        Bq = queries.shape[0]
+        rows_pad = (self.n_rows + 127) // 128 * 128
+        out = torch.zeros((rows_pad, 256), dtype=torch.float32, device=self.device)
+        ws = torch.empty(max(Bq * self.dim * 2, 256), dtype=torch.uint8, device=self.device)
+        _ffi.check(_ffi.lib().orag_cosine_firstpass_dense(
+            self.corpus.data_ptr(), self.inv_norm.data_ptr(),
+            self.shadow.data_ptr() if self.shadow is not None else None, self.n_rows, self.dim, queries.data_ptr(),
+            Bq, MODE[mode], out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(self.device)),
+            "orag_cosine_firstpass_dense")
+        return out[:self.n_rows, :Bq]
+
+    def stream_bytes(self, n_queries: int, mode: str | None = None) -> int:
+        """Bytes of corpus the first pass streams per batch of <= 256 queries."""
+        m = mode or self.mode
+        per = 2 if m == "bf16" else 4
+        groups = (n_queries + 255) // 256
+        return self.n_rows * self.dim * per * groups
+
+
+# --------------------------------------------------------------------------- selection / fusion
+def dense_topk(scores: torch.Tensor, k: int, id_base: int = 0, normalize: bool = False):
+    """scores float64 [B, n] -> ids, scores, max (exact (score desc, id asc) selection)."""
+    _require_cuda(scores, "scores")
+    assert scores.dtype == torch.float64 and scores.dim() == 2 and scores.stride(1) == 1
+    Bq, n = scores.shape
+    ids = torch.empty((Bq, k), dtype=torch.int64, device=scores.device)
+    sc = torch.empty((Bq, k), dtype=torch.float64, device=scores.device)
+    mx = torch.ones(Bq, dtype=torch.float64, device=scores.device)
+    _ffi.check(_ffi.lib().orag_dense_topk(scores.data_ptr(), n, scores.stride(0) if n else 0, Bq, k, id_base,
+                                          int(normalize), ids.data_ptr(), sc.data_ptr(), mx.data_ptr(),
+                                          _stream(scores.device)), "orag_dense_topk")
+    return ids, sc, mx
+
+
+def topk_merge(cand_ids: torch.Tensor, cand_scores: torch.Tensor, k: int, shard_max: torch.Tensor | None = None):
+    """cand_* [B, m] gathered from all shards -> global top-k.  With shard_max [B, G] (raw BM25 maxima) the
+    scores are normalised by the global max first (rag/retrieval.py:343-345)."""
+    _require_cuda(cand_ids, "cand_ids")
+    assert cand_ids.dtype == torch.int64 and cand_scores.dtype == torch.float64
+    assert cand_ids.is_contiguous() and cand_scores.is_contiguous()
+    Bq, m = cand_ids.shape
+    ids = torch.empty((Bq, k), dtype=torch.int64, device=cand_ids.device)
+    sc = torch.empty((Bq, k), dtype=torch.float64, device=cand_ids.device)
+    mx = torch.ones(Bq, dtype=torch.float64, device=cand_ids.device)
+    g = 0
+    if shard_max is not None:
+        assert shard_max.dtype == torch.float64 and shard_max.is_contiguous()
+        g = shard_max.shape[1]
+    _ffi.check(_ffi.lib().orag_topk_merge(cand_ids.data_ptr(), cand_scores.data_ptr(), m, Bq, k,
+                                          shard_max.data_ptr() if shard_max is not None else None, g,
+                                          ids.data_ptr(), sc.data_ptr(), mx.data_ptr(), _stream(cand_ids.device)),
+               "orag_topk_merge")
+    return ids, sc, mx
+
+
+def rrf_fuse(list_ids: torch.Tensor, rrf_k: int = 60, top_k: int = 10, tie: str = "reference",
+             want_src: bool = False):
+    """list_ids int64 [B, L, len] (-1 tail padding) -> fused ids [B, top_k], rrf scores, (src ranks [B,top_k,L])."""
+    _require_cuda(list_ids, "list_ids")
+    assert list_ids.dtype == torch.int64 and list_ids.dim() == 3 and list_ids.is_contiguous()
+    Bq, L, n = list_ids.shape
+    ids = torch.empty((Bq, top_k), dtype=torch.int64, device=list_ids.device)
+    sc = torch.empty((Bq, top_k), dtype=torch.float64, device=list_ids.device)
+    src = torch.empty((Bq, top_k, L), dtype=torch.int32, device=list_ids.device) if want_src else None
+    _ffi.check(_ffi.lib().orag_rrf_fuse(list_ids.data_ptr(), Bq, L, n, rrf_k, top_k, 0 if tie == "reference" else 1,
+                                        ids.data_ptr(), sc.data_ptr(), src.data_ptr() if want_src else None,
+                                        _stream(list_ids.device)), "orag_rrf_fuse")
+    return (ids, sc, src) if want_src else (ids, sc)
+
+
+def pairwise_cosine_threshold(emb: torch.Tensor, doc_idx: torch.Tensor, threshold: float = 0.85,
+                              cap: int = 1 << 20):
+    """All i<j, doc_idx differ, float64 cosine >= threshold (rag/consistency_checker.py:169-189).
+    Returns (i, j, sim) sorted by (i, j)."""
+    _require_cuda(emb, "emb")
+    assert emb.dtype == torch.float32 and emb.is_contiguous() and doc_idx.dtype == torch.int32
+    m, dim = emb.shape
+    dev = emb.device
+    oi = torch.empty(cap, dtype=torch.int32, device=dev)
+    oj = torch.empty(cap, dtype=torch.int32, device=dev)
+    osim = torch.empty(cap, dtype=torch.float64, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    need = int(_ffi.lib().orag_pairwise_workspace_bytes(m, dim))
+    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+    _ffi.check(_ffi.lib().orag_pairwise_cosine_threshold(emb.data_ptr(), m, dim, doc_idx.data_ptr(), threshold, cap,
+                                                         oi.data_ptr(), oj.data_ptr(), osim.data_ptr(), cnt.data_ptr(),
+                                                         ws.data_ptr(), ws.numel(), _stream(dev)),
+               "orag_pairwise_cosine_threshold")
+    n = int(cnt.item())
+    if n > cap:
+        raise _ffi.OragError(f"pair capacity exceeded ({n} > {cap})")
+    key = oi[:n].long() * m + oj[:n].long()
+    order = torch.argsort(key)
+    return oi[:n][order], oj[:n][order], osim[:n][order]
+
+
+# --------------------------------------------------------------------------- hybrid (one shard)
+class HybridShard:
+    """Cosine list + BM25 list -> RRF for the rows/docs of one GPU (SURVEY.md 'three facts' #1:
+    the composition the README describes, each piece in the reference's own arithmetic)."""
+
+    def __init__(self, cosine: CosineIndex, bm25: Bm25Index, rrf_k: int = 60):
+        assert cosine.n_rows == bm25.n_docs and cosine.row_id_base == bm25.doc_id_base
+        self.cosine = cosine
+        self.bm25 = bm25
+        self.rrf_k = rrf_k
+
+    def search(self, query_emb: torch.Tensor, query_terms: torch.Tensor, query_lens: torch.Tensor, k: int = 10,
+               fetch_k: int | None = None, check_overflow: bool = True):
+        fetch_k = fetch_k or k
+        ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=check_overflow)
+        bi, bs, bmax = self.bm25.topk(query_terms, query_lens, fetch_k, normalize=True, check_overflow=check_overflow)
+        lists = torch.stack([ci, bi], dim=1).contiguous()
+        fi, fs, src = rrf_fuse(lists, self.rrf_k, k, want_src=True)
+        return {"ids": fi, "rrf_scores": fs, "src_ranks": src, "cos_ids": ci, "cos_scores": cs, "bm25_ids": bi,
+                "bm25_scores": bs, "bm25_max": bmax}

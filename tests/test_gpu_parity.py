@@ -1,0 +1,328 @@
+"""GPU parity tests proper (-m gpu): every kernel, called through the C ABI, against the CPU oracle
+on the same seeded inputs and against the committed golden vectors.
+
+Bars (BASELINE.json north_star): BM25 / RRF bit-exact ids, ranks and scores; cosine exact ids with
+scores within 1e-5 relative (we additionally assert bitwise equality, which the float64 re-score
+achieves), ties broken by chunk id.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from optimized_rag_b200 import synthetic as syn
+from conftest import fromhex
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from optimized_rag_b200 import engine
+    assert torch.cuda.is_available()
+    return engine
+
+
+def _t(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+# ------------------------------------------------------------------------------------------------ generators
+def test_gen_embeddings_bit_identical(eng):
+    for n, dim, start, dup in [(300, 1536, 0, 0), (257, 64, 1000, 50), (5, 96, 123456789, 0)]:
+        got = eng.gen_embeddings(n, dim, start, syn.SEED_CORPUS, dup, device=DEV).cpu().numpy()
+        want = syn.embeddings(syn.SEED_CORPUS, start, n, dim, dup)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_gen_tokens_bit_identical(eng):
+    for n, start, vocab, lmin, lmax in [(500, 0, 50000, 100, 300), (64, 777, 50, 1, 9)]:
+        thr = syn.zipf_thresholds(vocab)
+        off, tok = eng.gen_token_corpus(n, start, syn.SEED_TOKENS, thr, vocab, lmin, lmax, device=DEV)
+        off_w, tok_w = syn.token_corpus(syn.SEED_TOKENS, start, n, vocab, lmin, lmax, thr)
+        assert np.array_equal(off.cpu().numpy(), off_w)
+        assert np.array_equal(tok.cpu().numpy(), tok_w)
+
+
+# ------------------------------------------------------------------------------------------------ cosine, exact path
+def _cos_inputs(case):
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, case["n"], case["dim"], case["dup_per_mille"])
+    queries = syn.query_embeddings(case["n_queries"], case["n"], case["dim"], dup_per_mille=case["dup_per_mille"])
+    if case.get("zero_row") is not None:
+        corpus[case["zero_row"], :] = 0.0
+    return corpus, queries
+
+
+def test_cosine_dense_golden_bit_exact(eng, golden):
+    for case in golden["cosine"]:
+        corpus, queries = _cos_inputs(case)
+        idx = eng.CosineIndex(_t(corpus), mode="exact")
+        if case["name"] == "zero_query":
+            got = idx.dense(torch.zeros((1, case["dim"]), dtype=torch.float32, device=DEV)).cpu().numpy()[0]
+            assert np.array_equal(got, np.array([fromhex(x) for x in case["zero_query_scores"]]))
+            continue
+        got = idx.dense(_t(queries)).cpu().numpy()
+        want = np.array([[fromhex(x) for x in row] for row in case["scores"]])
+        assert np.array_equal(_bits(got), _bits(want)), case["name"]
+
+
+@pytest.mark.parametrize("n,dim,nq,dup", [(1000, 1536, 9, 0), (3000, 128, 17, 30), (37, 100, 3, 0), (5, 64, 2, 0)])
+def test_cosine_exact_topk_vs_oracle(eng, n, dim, nq, dup):
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim, dup)
+    queries = syn.query_embeddings(nq, n, dim, dup_per_mille=dup)
+    idx = eng.CosineIndex(_t(corpus), row_id_base=1000, mode="exact")
+    ids, sc = idx.topk(_t(queries), 10)
+    wi, ws = oracle.cosine_topk(corpus, queries, 10, id_base=1000)
+    assert np.array_equal(ids.cpu().numpy(), wi)
+    valid = wi >= 0
+    assert np.array_equal(_bits(sc.cpu().numpy()[valid]), _bits(ws[valid]))
+
+
+# ------------------------------------------------------------------------------------------------ cosine, tensor-core path
+@pytest.mark.parametrize("mode,eps", [("tf32", 2.3e-3), ("bf16", 4.3e-3)])
+def test_firstpass_dense_within_bound(eng, mode, eps):
+    n, dim, nq = 1000, 1536, 70
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim)
+    queries = syn.query_embeddings(nq, n, dim)
+    idx = eng.CosineIndex(_t(corpus), mode=mode)
+    got = idx.firstpass_dense(_t(queries), mode).cpu().numpy().astype(np.float64)  # [n, nq] = cos * |q|
+    c64, q64 = corpus.astype(np.float64), queries.astype(np.float64)
+    want = (c64 @ q64.T) / np.linalg.norm(c64, axis=1)[:, None]
+    err = np.abs(got - want) / np.linalg.norm(q64, axis=1)[None, :]
+    assert err.max() < eps, (mode, err.max())
+    # and it is a real low-precision product, not garbage that happens to be small
+    assert np.corrcoef(got.ravel(), want.ravel())[0, 1] > 0.999
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("n,dim,nq,dup", [(20000, 1536, 40, 0), (9000, 256, 256, 20), (4500, 64, 3, 0)])
+def test_cosine_tc_topk_vs_oracle(eng, mode, n, dim, nq, dup):
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim, dup)
+    queries = syn.query_embeddings(nq, n, dim, dup_per_mille=dup)
+    if n == 9000:
+        corpus[4000:4040] = corpus[17]  # a block of exact duplicates straddling the top-k boundary
+        queries[5] = 0.0               # zero query -> all cosines 0.0 -> ids 0..k-1
+    idx = eng.CosineIndex(_t(corpus), row_id_base=7, mode=mode)
+    ids, sc = idx.topk(_t(queries), 10)
+    sub = list(range(0, nq, max(1, nq // 12)))
+    if n == 9000:
+        sub = sorted(set(sub + [5, 17 * 0 + 2]))
+    wi, ws = oracle.cosine_topk(corpus, queries[sub], 10, id_base=7)
+    assert np.array_equal(ids.cpu().numpy()[sub], wi), mode
+    assert np.array_equal(_bits(sc.cpu().numpy()[sub]), _bits(ws)), mode
+
+
+def test_cosine_tc_matches_exact_path_all_queries(eng):
+    n, dim, nq = 30000, 1536, 256
+    corpus = eng.gen_embeddings(n, dim, 0, syn.SEED_CORPUS, 1, device=DEV)
+    queries = _t(syn.query_embeddings(nq, n, dim, dup_per_mille=1))
+    a = eng.CosineIndex(corpus, mode="exact").topk(queries, 10)
+    for mode in ("tf32", "bf16"):
+        b = eng.CosineIndex(corpus, mode=mode).topk(queries, 10)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), mode
+
+
+# ------------------------------------------------------------------------------------------------ BM25
+def _bm25_case(n, vocab, lmin, lmax, nq, min_rank, tile_docs, eng):
+    thr = syn.zipf_thresholds(vocab)
+    doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, lmin, lmax, thr)
+    qtok, qlen = syn.keyword_queries(nq, vocab, min_rank=min_rank, thresholds=thr)
+    from optimized_rag_b200.bm25_index import Bm25Index
+    ix = Bm25Index(_t(doc_off), _t(tok), vocab, tile_docs=tile_docs, doc_id_base=100)
+    orc = oracle.BM25Index(doc_off, tok, vocab)
+    return ix, orc, qtok, qlen
+
+
+def test_bm25_golden_bit_exact(eng, golden):
+    from optimized_rag_b200.bm25_index import Bm25Index
+    for case in golden["bm25"]["cases"]:
+        thr = syn.zipf_thresholds(case["vocab"])
+        doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, case["n"], case["vocab"], case["lmin"], case["lmax"], thr)
+        ix = Bm25Index(_t(doc_off), _t(tok), case["vocab"], tile_docs=32)
+        mt = max(len(q["terms"]) for q in case["queries"])
+        qt = np.full((len(case["queries"]), mt), -2, dtype=np.int32)
+        ql = np.zeros(len(case["queries"]), dtype=np.int32)
+        for i, q in enumerate(case["queries"]):
+            qt[i, :len(q["terms"])] = q["terms"]
+            ql[i] = len(q["terms"])
+        raw = ix.dense_scores(_t(qt), _t(ql)).cpu().numpy()
+        for i, q in enumerate(case["queries"]):
+            want = np.array([fromhex(x) for x in q["normalized"]])
+            m = raw[i].max() if raw[i].max() > 0 else 1.0
+            assert np.array_equal(_bits(raw[i] / m), _bits(want)), (case["name"], i)
+        # and the top-k entry point, both paths, equals the oracle's ranking of those scores
+        for force in ("dense", "sparse"):
+            if force == "sparse" and ix.has_negative_idf:
+                continue
+            ids, sc, mx = ix.topk(_t(qt), _t(ql), 10, normalize=True, force=force)
+            for i, q in enumerate(case["queries"]):
+                want = np.array([fromhex(x) for x in q["normalized"]])
+                wi, wv = oracle.topk(want, 10)
+                got_i = ids[i].cpu().numpy()
+                assert np.array_equal(got_i[:len(wi)], wi), (case["name"], force, i)
+                assert np.array_equal(_bits(sc[i].cpu().numpy()[:len(wi)]), _bits(wv)), (case["name"], force, i)
+
+
+@pytest.mark.parametrize("force", ["sparse", "dense"])
+@pytest.mark.parametrize("n,vocab,lmin,lmax,nq,min_rank,tile", [
+    (20000, 5000, 20, 120, 64, 20, 4096),
+    (3000, 300, 5, 60, 40, 3, 256),
+    (70000, 50000, 100, 300, 32, 100, 4096),
+])
+def test_bm25_topk_vs_oracle(eng, force, n, vocab, lmin, lmax, nq, min_rank, tile):
+    ix, orc, qtok, qlen = _bm25_case(n, vocab, lmin, lmax, nq, min_rank, tile, eng)
+    assert ix.avgdl == orc.avgdl and ix.eps == orc.eps
+    assert np.array_equal(_bits(ix.idf.cpu().numpy()), _bits(orc.idf))
+    if force == "sparse" and ix.has_negative_idf:
+        pytest.skip("negative idf -> dense path only")
+    for normalize in (True, False):
+        ids, sc, mx = ix.topk(_t(qtok), _t(qlen), 10, normalize=normalize, force=force)
+        for b in range(nq):
+            raw = orc.scores_raw(qtok[b, :qlen[b]])
+            m = raw.max() if raw.max() > 0 else 1.0
+            want = raw / m if normalize else raw
+            wi, wv = oracle.topk(want, 10, id_base=100)
+            assert np.array_equal(ids[b].cpu().numpy(), wi), (force, normalize, b)
+            assert np.array_equal(_bits(sc[b].cpu().numpy()), _bits(wv)), (force, normalize, b)
+            assert float(mx[b]) == (m if normalize else max(raw.max(), 0.0))
+
+
+def test_bm25_rare_terms_zero_fill(eng):
+    """Queries matching fewer than k docs: the list continues with zero-score docs in id order."""
+    ix, orc, _, _ = _bm25_case(5000, 5000, 20, 120, 1, 20, 1024, eng)
+    df = orc.df
+    rare = [int(t) for t in np.nonzero((df > 0) & (df < 4))[0][:3]]
+    qt = np.array([rare + [-1], [rare[0], rare[0], -2, -2], [-1, -1, -2, -2]], dtype=np.int32)
+    ql = np.array([4, 2, 2], dtype=np.int32)
+    for force in ("sparse", "dense"):
+        ids, sc, _ = ix.topk(_t(qt), _t(ql), 10, force=force)
+        for b in range(3):
+            norm, _ = orc.scores(qt[b, :ql[b]])
+            wi, wv = oracle.topk(norm, 10, id_base=100)
+            assert np.array_equal(ids[b].cpu().numpy(), wi), (force, b)
+            assert np.array_equal(_bits(sc[b].cpu().numpy()), _bits(wv)), (force, b)
+
+
+# ------------------------------------------------------------------------------------------------ RRF / merge
+def test_rrf_golden_bit_exact(eng, golden):
+    for case in golden["rrf"]:
+        L = len(case["lists"])
+        n = max(1, max((len(l) for l in case["lists"]), default=1))
+        arr = np.full((1, L, n), -1, dtype=np.int64)
+        for i, l in enumerate(case["lists"]):
+            arr[0, i, :len(l)] = l
+        ids, sc = eng.rrf_fuse(_t(arr), case["k"], case["top_k"])
+        got_ids = [int(x) for x in ids[0].cpu().numpy() if x >= 0]
+        assert got_ids == case["ids"], case["name"]
+        assert sc[0].cpu().numpy()[:len(got_ids)].tolist() == [fromhex(x) for x in case["scores"]], case["name"]
+
+
+def test_rrf_batch_vs_oracle(eng):
+    rng = np.random.default_rng(3)
+    B, L, n = 300, 3, 12
+    arr = np.stack([np.stack([rng.permutation(30)[:n] for _ in range(L)]) for _ in range(B)]).astype(np.int64)
+    arr[5, 1, 7:] = -1
+    for tie in ("reference", "chunk_id"):
+        ids, sc, src = eng.rrf_fuse(_t(arr), 60, 10, tie=tie, want_src=True)
+        for b in range(B):
+            lists = [[int(x) for x in arr[b, l] if x >= 0] for l in range(L)]
+            wi, ws = oracle.rrf_fuse(lists, 60, 10, tie=tie)
+            assert np.array_equal(ids[b].cpu().numpy(), wi) and np.array_equal(sc[b].cpu().numpy(), ws)
+            for r in range(10):
+                for l in range(L):
+                    want_rank = lists[l].index(int(wi[r])) + 1 if int(wi[r]) in lists[l] else 0
+                    assert int(src[b, r, l]) == want_rank
+
+
+def test_topk_merge(eng):
+    rng = np.random.default_rng(5)
+    B, m = 50, 48
+    ids = np.stack([rng.permutation(1000)[:m] for _ in range(B)]).astype(np.int64)
+    sc = rng.integers(0, 8, (B, m)).astype(np.float64) / 4.0  # many ties
+    ids[3, 10:] = -1
+    gi, gs, _ = eng.topk_merge(_t(ids), _t(sc), 10)
+    for b in range(B):
+        ok = ids[b] >= 0
+        order = sorted(np.nonzero(ok)[0], key=lambda i: (-sc[b, i], ids[b, i]))[:10]
+        assert gi[b].cpu().numpy()[:len(order)].tolist() == ids[b, order].tolist()
+        assert gs[b].cpu().numpy()[:len(order)].tolist() == sc[b, order].tolist()
+    smax = rng.random((B, 4)) * 3
+    gi, gs, gm = eng.topk_merge(_t(ids), _t(sc), 10, shard_max=_t(smax))
+    for b in range(B):
+        m_ = max(smax[b].max(), sc[b][ids[b] >= 0].max())
+        assert float(gm[b]) == m_
+        ok = ids[b] >= 0
+        norm = sc[b] / m_
+        order = sorted(np.nonzero(ok)[0], key=lambda i: (-norm[i], ids[b, i]))[:10]
+        assert gs[b].cpu().numpy()[:len(order)].tolist() == norm[order].tolist()
+
+
+# ------------------------------------------------------------------------------------------------ pairwise / config 1 / hybrid
+def test_pairwise_golden(eng, golden):
+    g = golden["pairwise"]
+    m, d = g["m"], g["dim"]
+    emb = syn.embeddings(syn.SEED_CORPUS, 0, m, d)
+    for i in range(0, m, 4):
+        emb[i + 1] = (emb[i] + np.float32(0.25) * emb[i + 1]).astype(np.float32)
+        emb[i + 3] = (emb[i] + np.float32(0.5) * emb[i + 3]).astype(np.float32)
+    oi, oj, sim = eng.pairwise_cosine_threshold(_t(emb), _t(np.array(g["doc_idx"], dtype=np.int32)), g["threshold"])
+    got = [[int(a), int(b), round(float(s), 3)] for a, b, s in zip(oi.cpu(), oj.cpu(), sim.cpu())]
+    assert got == g["pairs"]
+    wi, wj, ws = oracle.pairwise_candidates(emb, g["doc_idx"], g["threshold"])
+    assert np.array_equal(_bits(sim.cpu().numpy()), _bits(ws))
+
+
+def test_config1_golden(eng, golden):
+    from optimized_rag_b200.bm25_index import Bm25Index
+    g = golden["config1"]
+    dim = g["dim"]
+    emb = np.concatenate([syn.embeddings(s, 0, 1, dim) for s in g["chunk_seeds"]], axis=0)
+    toks = np.concatenate([np.array(t, dtype=np.int32) for t in g["chunk_tokens"]])
+    off = np.cumsum([0] + [len(t) for t in g["chunk_tokens"]]).astype(np.int64)
+    shard = eng.HybridShard(eng.CosineIndex(_t(emb), mode="exact"),
+                            Bm25Index(_t(off), _t(toks), g["vocab_size"], tile_docs=32))
+    nq = len(g["queries"])
+    mt = max(len(q["query_terms"]) for q in g["queries"])
+    qt = np.full((nq, mt), -2, dtype=np.int32)
+    ql = np.zeros(nq, dtype=np.int32)
+    qe = np.zeros((nq, dim), dtype=np.float32)
+    for i, q in enumerate(g["queries"]):
+        qt[i, :len(q["query_terms"])] = q["query_terms"]
+        ql[i] = len(q["query_terms"])
+        qe[i] = (syn.embeddings(q["query_noise_seed"], 0, 1, dim)[0]
+                 + np.float32(0.75) * emb[q["query_base_chunk"]]).astype(np.float32)
+    res = shard.search(_t(qe), _t(qt), _t(ql), k=10)
+    for i, q in enumerate(g["queries"]):
+        assert res["cos_ids"][i].cpu().tolist() == q["cos_ids"]
+        assert res["cos_scores"][i].cpu().tolist() == [fromhex(x) for x in q["cos_scores"]]
+        assert res["bm25_ids"][i].cpu().tolist() == q["bm25_ids"]
+        assert res["bm25_scores"][i].cpu().tolist() == [fromhex(x) for x in q["bm25_scores"]]
+        assert res["ids"][i].cpu().tolist() == q["rrf_ids"]
+        assert res["rrf_scores"][i].cpu().tolist() == [fromhex(x) for x in q["rrf_scores"]]
+
+
+def test_hybrid_vs_oracle_mid_size(eng):
+    from optimized_rag_b200.bm25_index import Bm25Index
+    n, dim, vocab, nq = 12000, 256, 3000, 48
+    thr = syn.zipf_thresholds(vocab)
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim, 2)
+    queries = syn.query_embeddings(nq, n, dim, dup_per_mille=2)
+    doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, 20, 100, thr)
+    qtok, qlen = syn.keyword_queries(nq, vocab, min_rank=10, thresholds=thr)
+    shard = eng.HybridShard(eng.CosineIndex(_t(corpus), mode="tf32"),
+                            Bm25Index(_t(doc_off), _t(tok), vocab, tile_docs=2048))
+    res = shard.search(_t(queries), _t(qtok), _t(qlen), k=10)
+    orc = oracle.BM25Index(doc_off, tok, vocab)
+    want = oracle.hybrid_topk(corpus, queries, orc, [qtok[b, :qlen[b]] for b in range(nq)], k=10)
+    for b in range(nq):
+        assert res["ids"][b].cpu().tolist() == want[b]["ids"].tolist(), b
+        assert res["rrf_scores"][b].cpu().tolist() == want[b]["rrf_scores"].tolist(), b
+        assert res["cos_ids"][b].cpu().tolist() == want[b]["cos_ids"].tolist(), b
+        assert res["bm25_ids"][b].cpu().tolist() == want[b]["bm25_ids"].tolist(), b

@@ -1,0 +1,126 @@
+"""CPU tests (-m "not gpu"): host-side logic, the C-ABI library's exports, the index builder's layout.
+No compute call into the CUDA library is made here (there is no GPU in the build container)."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from optimized_rag_b200 import synthetic as syn
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from optimized_rag_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from optimized_rag_b200 import _ffi
+    header = (ROOT / "include" / "orag.h").read_text()
+    declared = set(re.findall(r"\b(orag_[a-z0-9_]+)\s*\(", header))
+    declared -= {"orag_bm25_index"}
+    assert declared == set(_ffi.SYMBOLS), declared ^ set(_ffi.SYMBOLS)
+    L = ctypes.CDLL(str(built_lib))
+    for name in declared:
+        assert hasattr(L, name), name
+    # argument-free calls are safe without a GPU
+    assert _ffi.lib().orag_version() == 1
+    assert _ffi.lib().orag_last_error() is not None
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma(built_lib):
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", str(built_lib)], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "optimized_rag_b200").rglob("*.py"):
+        src = p.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, p
+
+
+def test_no_cpu_path_for_cpu_tensors(built_lib):
+    from optimized_rag_b200 import _ffi, engine
+    with pytest.raises(_ffi.OragError):
+        engine.CosineIndex(torch.zeros((4, 32), dtype=torch.float32))
+    with pytest.raises(_ffi.OragError):
+        engine.rrf_fuse(torch.zeros((1, 2, 3), dtype=torch.int64))
+
+
+def test_synthetic_generators_are_shard_consistent():
+    a = syn.embeddings(syn.SEED_CORPUS, 0, 300, 128, 20)
+    b = np.concatenate([syn.embeddings(syn.SEED_CORPUS, s, 100, 128, 20) for s in (0, 100, 200)])
+    assert np.array_equal(a, b)
+    # exact representability: every value is a multiple of 2**-28 below 2**-5
+    assert np.all(np.abs(a) < 2.0 ** -5) and np.array_equal(a * 2.0 ** 28, np.round(a * 2.0 ** 28))
+    src = syn.source_rows(syn.SEED_CORPUS, np.arange(300), 20)
+    dup = np.nonzero(src != np.arange(300))[0]
+    assert len(dup) > 0 and all(np.array_equal(a[r], syn.embeddings(syn.SEED_CORPUS, int(src[r]), 1, 128, 0)[0])
+                                for r in dup)
+    thr = syn.zipf_thresholds(1000)
+    o1, t1 = syn.token_corpus(syn.SEED_TOKENS, 0, 50, 1000, 5, 20, thr)
+    o2, t2 = syn.token_corpus(syn.SEED_TOKENS, 30, 20, 1000, 5, 20, thr)
+    assert np.array_equal(t1[o1[30]:], t2)
+    q, ql = syn.keyword_queries(500, 1000, thresholds=thr)
+    assert ql.min() >= 3 and ql.max() <= 8 and ((q == -1).sum(axis=1) > 0).sum() > 0
+
+
+@pytest.mark.parametrize("n,vocab,lmin,lmax,tile", [(300, 200, 3, 40, 64), (1000, 5000, 20, 60, 256), (5, 8, 1, 6, 32)])
+def test_index_builder_layout_matches_oracle(built_lib, n, vocab, lmin, lmax, tile):
+    """The torch-built tiled index decodes to exactly the oracle's postings / idf / t4."""
+    from optimized_rag_b200.bm25_index import Bm25Index
+    thr = syn.zipf_thresholds(vocab)
+    doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, lmin, lmax, thr)
+    ix = Bm25Index(torch.from_numpy(doc_off), torch.from_numpy(tok), vocab, tile_docs=tile)
+    orc = oracle.BM25Index(doc_off, tok, vocab)
+    assert ix.avgdl == orc.avgdl and ix.average_idf == orc.average_idf and ix.eps == orc.eps
+    assert np.array_equal(ix.idf.numpy().view(np.uint64), orc.idf.view(np.uint64))
+    assert ix.has_negative_idf == bool((orc.idf < 0).any())
+    # t4 = k1 * (1 - b + b * dl / avgdl) in the oracle's operation order
+    dl = orc.dl.astype(np.float64)
+    assert np.array_equal(ix.doc_t4.numpy(), 1.5 * (0.25 + (0.75 * dl) / orc.avgdl))
+    off, pdoc, ptf = orc.postings()
+    post = ix.postings.numpy().view(np.uint32)
+    tbase = ix.tile_base.numpy()
+    toff = ix.tile_term_off.numpy()
+    assert ix.n_postings == len(pdoc)
+    for t in range(vocab):
+        docs, tfs = [], []
+        for tl in range(ix.n_tiles):
+            s, e = tbase[tl] + toff[tl, t], tbase[tl] + toff[tl, t + 1]
+            p = post[s:e]
+            docs.extend((tl * tile + (p >> 16)).tolist())
+            tfs.extend((p & 0xFFFF).tolist())
+        assert docs == pdoc[off[t]:off[t + 1]].tolist(), t
+        assert tfs == ptf[off[t]:off[t + 1]].tolist(), t
+
+
+def test_sharded_stats_merge_equals_global(built_lib):
+    from optimized_rag_b200.bm25_index import idf_table, local_stats
+    vocab, n = 400, 900
+    thr = syn.zipf_thresholds(vocab)
+    doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, 5, 50, thr)
+    whole = local_stats(torch.from_numpy(doc_off), torch.from_numpy(tok), vocab)
+    parts = None
+    for s, e in [(0, 300), (300, 650), (650, 900)]:
+        off = doc_off[s:e + 1] - doc_off[s]
+        st = local_stats(torch.from_numpy(off), torch.from_numpy(tok[doc_off[s]:doc_off[e]]), vocab,
+                         token_pos_base=int(doc_off[s]))
+        parts = st if parts is None else parts.merged(st)
+    assert parts.n_docs == whole.n_docs and parts.total_len == whole.total_len
+    assert np.array_equal(parts.df, whole.df) and np.array_equal(parts.first_seen, whole.first_seen)
+    a, b = idf_table(parts), idf_table(whole)
+    assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+    orc = oracle.BM25Index(doc_off, tok, vocab)
+    assert np.array_equal(a[0].view(np.uint64), orc.idf.view(np.uint64))
+    order = np.argsort(whole.first_seen[whole.df > 0], kind="stable")
+    assert np.array_equal(np.nonzero(whole.df > 0)[0][order], orc.first_seen)
