@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: hybrid top-10 queries/sec at 10M x 1536 chunks on 1/2/4/8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun ... bench.py --gpus N ...        (one rank per GPU, corpus row-sharded)
+
+A "step" is one hybrid retrieval (exact cosine top-10 + BM25 top-10 + RRF) of a batch of 256
+queries against the whole synthetic corpus (10M chunks x 1536-d fp32 + Zipf token corpus, V=50k).
+`value` = whole-job queries/s with inputs resident in HBM; `e2e` = the same through the public
+search call with HOST query buffers (H2D + D2H inside the timed region).  One JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "hybrid_top10_queries_per_sec_10Mx1536"
+UNIT = "queries/s"
+DIM = 1536
+VOCAB = 50000
+TOPK = 10
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--rows", type=int, default=int(os.environ.get("ORAG_BENCH_ROWS", 10_000_000)))
+    ap.add_argument("--queries", type=int, default=256)
+    ap.add_argument("--mode", default=os.environ.get("ORAG_BENCH_MODE", "bf16"), choices=["tf32", "bf16"])
+    ap.add_argument("--tile-docs", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
+    ap.add_argument("--ref-sample-rows", type=int, default=20_000)
+    ap.add_argument("--ref-sample-queries", type=int, default=4)
+    return ap.parse_args()
+
+
+def workload_config(args, extra=None):
+    cfg = {"workload": f"{args.rows} chunks x {DIM}-d fp32 hybrid (exact cosine + BM25 + RRF) top-{TOPK}, "
+                       f"query batch {args.queries}, Zipf(s=1) token corpus V={VOCAB} L~U[100,300]",
+           "rows": args.rows, "dim": DIM, "query_batch": args.queries, "top_k": TOPK, "vocab": VOCAB,
+           "l2": "inputs larger than L2 (corpus streamed from HBM every step)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_hybrid_sample(oracle, corpus, bm25, queries, qtok, qlen, k):
+    """One pass of the oracle's hybrid path over a row sample; returns seconds."""
+    t0 = time.perf_counter()
+    for b in range(len(queries)):
+        ci, _ = oracle.topk(oracle.cosine_scores(corpus, queries[b]), k)
+        bi, _, _ = bm25.topk(qtok[b, :qlen[b]], k)
+        oracle.rrf_fuse([ci, bi], 60, k)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """The reference's CPU path (oracle port of rag/retrieval.py:362-371, 324-347 and rag/reranker.py:224-271;
+    the Python reference itself cannot travel to the GPU box) on the host cores, on a bounded row sample,
+    scaled linearly in N (every piece is O(N) per query)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from optimized_rag_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    oracle.build()
+    S, Bs = args.ref_sample_rows, args.ref_sample_queries
+    thr = syn.zipf_thresholds(VOCAB)
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, S, DIM)
+    queries = syn.query_embeddings(Bs, S, DIM)
+    doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, S, VOCAB, 100, 300, thr)
+    qtok, qlen = syn.keyword_queries(Bs, VOCAB, thresholds=thr)
+    bm25 = oracle.BM25Index(doc_off, tok, VOCAB)
+    for _ in range(args.warmup):
+        cpu_hybrid_sample(oracle, corpus, bm25, queries, qtok, qlen, TOPK)
+    times = [cpu_hybrid_sample(oracle, corpus, bm25, queries, qtok, qlen, TOPK) for _ in range(args.steps)]
+    t = sum(times)
+    scale = args.rows / S
+    value = (Bs * args.steps) / (t * scale)
+    sample = (f"{Bs} queries x {S} rows per step (cosine fp64 Neumaier + BM25 over a prebuilt index + RRF), "
+              f"scaled x{scale:.0f} to {args.rows} rows (O(N) per query); BM25Okapi rebuild per call "
+              f"(rag/retrieval.py:338) NOT charged")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid: str):
+        self.uuid = uuid
+        self.proc = None
+        self.path = ROOT / "gpurun_out" / f"clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.path.parent.mkdir(exist_ok=True)
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.uuid, f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.path.read_text().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from optimized_rag_b200 import _ffi, engine, synthetic as syn
+    from optimized_rag_b200.bm25_index import Bm25Index
+    from optimized_rag_b200.dist import ShardedHybrid, shard_range, sharded_stats
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a GPU: there is no CPU fallback for the retrieval hot path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _ffi.lib()
+    N, Bq, k = args.rows, args.queries, TOPK
+    lo, hi = shard_range(N, rank, world)
+    n_local = hi - lo
+
+    # ---- build the shard: embeddings (+ inverse norms, + bf16 shadow), token corpus, inverted index
+    t_setup = time.perf_counter()
+    corpus = engine.gen_embeddings(n_local, DIM, lo, syn.SEED_CORPUS, 0, device=dev)
+    cos = engine.CosineIndex(corpus, row_id_base=lo, mode=args.mode)
+    thr = syn.zipf_thresholds(VOCAB)
+    doc_off, tokens = engine.gen_token_corpus(n_local, lo, syn.SEED_TOKENS, thr, VOCAB, 100, 300, device=dev)
+    stats = sharded_stats(doc_off, tokens, VOCAB)
+    bm25 = Bm25Index(doc_off, tokens, VOCAB, tile_docs=args.tile_docs, stats=stats, doc_id_base=lo)
+    cpu_sample = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        S = min(args.cpu_sample_rows, n_local)
+        cpu_sample = (corpus[:S].cpu().numpy(), doc_off[:S + 1].cpu().numpy(),
+                      tokens[:int(doc_off[S].item())].cpu().numpy())
+    del tokens
+    torch.cuda.empty_cache()
+    shard = engine.HybridShard(cos, bm25)
+    sh = ShardedHybrid(shard)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+
+    # ---- queries: generated on the host, staged in pinned memory (replicated on every rank)
+    q_emb_h = torch.from_numpy(syn.query_embeddings(Bq, N, DIM)).pin_memory()
+    qt_np, ql_np = syn.keyword_queries(Bq, VOCAB, thresholds=thr)
+    q_tok_h = torch.from_numpy(qt_np).pin_memory()
+    q_len_h = torch.from_numpy(ql_np).pin_memory()
+    q_emb, q_tok, q_len = q_emb_h.to(dev), q_tok_h.to(dev), q_len_h.to(dev)
+    out_ids_h = torch.empty((Bq, k), dtype=torch.int64).pin_memory()
+    out_sc_h = torch.empty((Bq, k), dtype=torch.float64).pin_memory()
+    h2d = q_emb_h.numel() * 4 + q_tok_h.numel() * 4 + q_len_h.numel() * 4
+    d2h = out_ids_h.numel() * 8 + out_sc_h.numel() * 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up
+    res = None
+    for _ in range(max(args.warmup, 3)):
+        res = sh.search(q_emb, q_tok, q_len, k)
+    barrier()
+
+    # ---- timed: inputs resident in HBM
+    uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+    L.orag_profile_enable(1)
+    scan_ms, bm_ms = [], []
+    launches0 = int(L.orag_launch_count())
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    import ctypes
+    a, b = ctypes.c_float(), ctypes.c_float()
+    for _ in range(args.steps):
+        res = sh.search(q_emb, q_tok, q_len, k)
+        L.orag_profile_read(ctypes.byref(a), ctypes.byref(b))  # waits for the step's scan / BM25 kernels only
+        scan_ms.append(a.value); bm_ms.append(b.value)
+    ev1.record()
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = int(L.orag_launch_count()) - launches0
+    L.orag_profile_enable(0)
+
+    # ---- timed: end to end through the public call with HOST buffers
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        q_emb.copy_(q_emb_h, non_blocking=True)
+        q_tok.copy_(q_tok_h, non_blocking=True)
+        q_len.copy_(q_len_h, non_blocking=True)
+        r = sh.search(q_emb, q_tok, q_len, k)
+        out_ids_h.copy_(r["ids"], non_blocking=True)
+        out_sc_h.copy_(r["rrf_scores"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+
+    # ---- self-check outside the timed region: re-derive a few queries' lists with the exact kernels
+    verified = None
+    if world == 1:
+        sub = torch.tensor([0, 1, Bq // 2, Bq - 1], device=dev)
+        ei, es = cos.topk(q_emb[sub].contiguous(), k, mode="exact")
+        bi, bs, _ = bm25.topk(q_tok[sub].contiguous(), q_len[sub].contiguous(), k, force="dense")
+        ok = (torch.equal(ei, res["cos_ids"][sub]) and torch.equal(es, res["cos_scores"][sub])
+              and torch.equal(bi, res["bm25_ids"][sub]) and torch.equal(bs, res["bm25_scores"][sub]))
+        top1 = (res["cos_ids"][:, 0].cpu().numpy() == (np.arange(Bq) * syn.QUERY_STRIDE) % N).all()
+        verified = bool(ok and top1)
+        if not verified:
+            raise SystemExit("bench self-check FAILED: fast path differs from the exact kernels")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    n_scan_rows = max(n_local - 2048, 0)
+    t_scan = statistics.mean(scan_ms) * 1e-3
+    t_bm = statistics.mean([x for x in bm_ms if x >= 0] or [0.0]) * 1e-3
+    groups = (Bq + 255) // 256
+    fp32_bytes = n_scan_rows * DIM * 4
+    streamed = n_scan_rows * DIM * (2 if args.mode == "bf16" else 4)
+    flops = 2.0 * min(Bq, 256) * n_scan_rows * DIM
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get(f"cosine_scan_{args.mode}")
+    hbm = {"bound": "hbm", "achieved": streamed / t_scan / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+           "frac": streamed / t_scan / 1e9 / pk["hbm_gbs"], "traffic": traffic,
+           "bytes": "bf16 shadow copy actually streamed (N*D*2)" if args.mode == "bf16" else "fp32 corpus (N*D*4)"}
+    tens = {"bound": "tensor", "achieved": flops / t_scan / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+            "frac": flops / t_scan / 1e12 / pk["tf_sustained"], "traffic": traffic,
+            "peak_kind": "bf16 dense sustained" if args.mode == "bf16" else
+                         "bf16 dense sustained (tf32 runs at half the bf16 rate: x2 for the tf32 ceiling)"}
+    # which resource bounds the kernel: bf16 at B=256 has 256 flop/B of streamed data > the ~207 flop/B ridge
+    primary = tens if (args.mode == "bf16" and Bq >= 208) else hbm
+    roofline = dict(primary)
+    roofline.update({"kernel": f"cosine_scan_kernel<{args.mode}> (main scan, {n_scan_rows} rows x {min(Bq, 256)} queries)",
+                     "peak_source": pk["source"], "launch_ms": t_scan * 1e3 / 1.0, "launches_per_step": groups,
+                     "fp32_equivalent_gbs": fp32_bytes / t_scan / 1e9,
+                     "fp32_equivalent_frac_of_hbm_peak": fp32_bytes / t_scan / 1e9 / pk["hbm_gbs"],
+                     "other_view": tens if primary is hbm else hbm})
+    post_bytes = bm25.posting_bytes(q_tok, q_len)
+    roof_bm = {"bound": "hbm", "achieved": post_bytes / t_bm / 1e9 if t_bm > 0 else None, "peak": pk["hbm_gbs"],
+               "unit": "GB/s", "frac": (post_bytes / t_bm / 1e9 / pk["hbm_gbs"]) if t_bm > 0 else None,
+               "kernel": "bm25_tile_kernel", "launch_ms": t_bm * 1e3,
+               "algorithmic_bytes": post_bytes, "traffic": None}
+
+    value = Bq * args.steps / (dev_ms * 1e-3)
+    e2e_val = Bq * args.steps / (e2e_ms * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 scores (first pass " + args.mode + ")",
+            "data": "synthetic",
+            "config": workload_config(args, {"first_pass": args.mode, "rows_per_gpu": n_local,
+                                             "parallelism": f"row-sharded x{world}", "setup_s": round(t_setup, 1),
+                                             "bm25_postings_local": bm25.n_postings}),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_bm25": roof_bm,
+            "hbm_roofline_queries_per_sec_fp32_corpus": Bq / (n_local * DIM * 4 / (pk["hbm_gbs"] * 1e9)),
+            "verified_against_exact_kernels": verified}
+
+    if cpu_sample is not None:
+        import oracle
+        cores = os.cpu_count() or 1
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        oracle.build()
+        c_np, off_np, tok_np = cpu_sample
+        S = c_np.shape[0]
+        ob = oracle.BM25Index(off_np, tok_np, VOCAB)
+        qs = q_emb_h.numpy()
+        nq_cpu, t_cpu = 0, 0.0
+        while t_cpu < 10.0 and nq_cpu < 64:
+            t_cpu += cpu_hybrid_sample(oracle, c_np, ob, qs[nq_cpu:nq_cpu + 2], qt_np[nq_cpu:nq_cpu + 2],
+                                       ql_np[nq_cpu:nq_cpu + 2], k)
+            nq_cpu += 2
+        scale = N / S
+        line["cpu_baseline"] = {"value": nq_cpu / (t_cpu * scale), "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{nq_cpu} queries x first {S} rows/docs of the same corpus through the "
+                                          f"oracle (C port of the reference arithmetic, OpenMP), scaled x{scale:.0f} "
+                                          f"to {N} rows; BM25Okapi rebuild per call not charged"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

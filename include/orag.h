@@ -55,6 +55,14 @@ const char *orag_last_error(void);
 /* sm count / compute capability of the current device */
 int orag_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* Measurement hooks (bench.py): number of kernels this library has launched so far, and CUDA-event
+ * brackets (recorded on the caller's stream) around the two dominant kernels of the most recent
+ * calls -- the cosine main scan and the BM25 tile kernel.  orag_profile_read synchronises on those
+ * events; a slot that has not run since orag_profile_enable reports -1. */
+unsigned long long orag_launch_count(void);
+int orag_profile_enable(int on);
+int orag_profile_read(float *scan_ms, float *bm25_ms);
+
 /* ---------------------------------------------------------------------------
  * Synthetic inputs: bit-identical to optimized_rag_b200/synthetic.py
  * ------------------------------------------------------------------------- */

@@ -17,6 +17,7 @@ ORAG_BM25_NORMALIZE, ORAG_BM25_FORCE_SPARSE, ORAG_BM25_FORCE_DENSE = 1, 2, 4
 # every symbol include/orag.h declares (tests check the .so exports each one)
 SYMBOLS = [
     "orag_version", "orag_last_error", "orag_device_info",
+    "orag_launch_count", "orag_profile_enable", "orag_profile_read",
     "orag_gen_embeddings", "orag_gen_doc_lengths", "orag_gen_tokens",
     "orag_row_inv_norms", "orag_f32_to_bf16",
     "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_dense", "orag_cosine_firstpass_dense",
@@ -61,6 +62,9 @@ def lib() -> ctypes.CDLL:
     L.orag_version.restype = c_int
     L.orag_last_error.restype = c_char_p
     L.orag_device_info.argtypes = [POINTER(c_int), POINTER(c_int), POINTER(c_int)]
+    L.orag_launch_count.restype = ctypes.c_ulonglong
+    L.orag_profile_enable.argtypes = [c_int]
+    L.orag_profile_read.argtypes = [POINTER(ctypes.c_float), POINTER(ctypes.c_float)]
     L.orag_gen_embeddings.argtypes = [vp, c_int64, c_int, c_int64, c_uint64, c_int, vp]
     L.orag_gen_doc_lengths.argtypes = [vp, c_int64, c_int64, c_uint64, c_int, c_int, vp]
     L.orag_gen_tokens.argtypes = [vp, vp, c_int64, c_int64, c_uint64, vp, c_int, vp]
@@ -86,7 +90,7 @@ def lib() -> ctypes.CDLL:
                                                  c_size_t, vp]
     for name in SYMBOLS:
         f = getattr(L, name)
-        if name not in ("orag_last_error", "orag_cosine_workspace_bytes", "orag_bm25_workspace_bytes",
+        if name not in ("orag_last_error", "orag_launch_count", "orag_cosine_workspace_bytes", "orag_bm25_workspace_bytes",
                         "orag_pairwise_workspace_bytes"):
             f.restype = c_int
     _lib = L

@@ -19,6 +19,25 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+// ---- profiling hooks ------------------------------------------------------------------------------
+static unsigned long long g_launches = 0;
+static int g_profile = 0;
+static cudaEvent_t g_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+static int g_ev_used[2] = {0, 0};
+
+void count_launch() { ++g_launches; }
+
+void profile_mark(int slot, int end, cudaStream_t st)
+{
+    if (!g_profile || slot < 0 || slot > 1) return;
+    if (!g_ev[slot][0]) {
+        cudaEventCreate(&g_ev[slot][0]);
+        cudaEventCreate(&g_ev[slot][1]);
+    }
+    cudaEventRecord(g_ev[slot][end ? 1 : 0], st);
+    if (end) g_ev_used[slot] = 1;
+}
+
 // First-pass error bounds in cosine units (DESIGN.md "exactness of the first pass"):
 //   tf32: operands truncated to 10 mantissa bits -> |rel err per product| < 2^-9 + 2^-20
 //   bf16: operands rounded to nearest, 8 bits      -> |rel err per product| < 2^-8 + 2^-18
@@ -76,6 +95,28 @@ using namespace orag;
 
 extern "C" int orag_version(void) { return 1; }
 extern "C" const char *orag_last_error(void) { return orag::g_err; }
+
+extern "C" unsigned long long orag_launch_count(void) { return orag::g_launches; }
+
+extern "C" int orag_profile_enable(int on)
+{
+    orag::g_profile = on ? 1 : 0;
+    orag::g_ev_used[0] = orag::g_ev_used[1] = 0;
+    return ORAG_OK;
+}
+
+extern "C" int orag_profile_read(float *scan_ms, float *bm25_ms)
+{
+    float *out[2] = {scan_ms, bm25_ms};
+    for (int s = 0; s < 2; ++s) {
+        if (!out[s]) continue;
+        *out[s] = -1.f;
+        if (!orag::g_ev_used[s]) continue;
+        ORAG_CUDA_CHECK(cudaEventSynchronize(orag::g_ev[s][1]));
+        ORAG_CUDA_CHECK(cudaEventElapsedTime(out[s], orag::g_ev[s][0], orag::g_ev[s][1]));
+    }
+    return ORAG_OK;
+}
 
 extern "C" int orag_device_info(int *sm, int *major, int *minor)
 {

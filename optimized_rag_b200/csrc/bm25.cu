@@ -345,6 +345,7 @@ static int launch_tiles(const Params &p, bool dense, cudaStream_t st)
     int lim = orag::sm_count() * per_sm;
     if (grid > lim) grid = lim;
     if (grid < 1) return ORAG_OK;
+    orag::profile_mark(1, 0, st);
     if (dense) {
         ORAG_CUDA_CHECK(cudaFuncSetAttribute(orag::bm25::bm25_tile_kernel<true>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -354,6 +355,7 @@ static int launch_tiles(const Params &p, bool dense, cudaStream_t st)
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         orag::bm25::bm25_tile_kernel<false><<<grid, orag::bm25::kThreads, smem, st>>>(p);
     }
+    orag::profile_mark(1, 1, st);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }

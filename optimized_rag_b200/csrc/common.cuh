@@ -10,6 +10,10 @@
 namespace orag {
 
 void set_error(const char *fmt, ...);
+// profiling hooks (api.cu): kernel-launch counter and optional event brackets around the two
+// dominant kernels (slot 0 = cosine main scan, slot 1 = BM25 tile kernel)
+void count_launch();
+void profile_mark(int slot, int end, cudaStream_t st);
 
 #define ORAG_CUDA_CHECK(expr)                                                              \
     do {                                                                                   \
@@ -30,6 +34,7 @@ void set_error(const char *fmt, ...);
 
 #define ORAG_LAUNCH_CHECK()                                                                \
     do {                                                                                   \
+        orag::count_launch();                                                              \
         cudaError_t _e = cudaGetLastError();                                               \
         if (_e != cudaSuccess) {                                                           \
             orag::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

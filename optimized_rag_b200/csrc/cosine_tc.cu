@@ -447,6 +447,7 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
     p.num_tiles = (int)((p.row_end - p.row_begin + kTileM - 1) / kTileM);
     p.idesc = make_idesc(bf16, p.umma_n);
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    if (!p.dense) profile_mark(0, 0, st);
     if (bf16) {
         ORAG_CUDA_CHECK(cudaFuncSetAttribute(cosine_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kSmemBytes));
@@ -456,6 +457,7 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
                                              (int)kSmemBytes));
         cosine_scan_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(map_a, map_b, p);
     }
+    if (!p.dense) profile_mark(0, 1, st);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }
