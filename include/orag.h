@@ -127,10 +127,13 @@ typedef struct orag_bm25_index {
     int32_t tile_docs;             /* docs per tile (power of two, <= 65536) */
     int32_t n_tiles;               /* ceil(n_docs / tile_docs) */
     int32_t has_negative_idf;      /* 1 if a negative idf survives the epsilon floor (forces the dense path) */
+    int32_t max_doc_len;           /* size of d_t4_table - 1 */
+    int32_t reserved;
     const int64_t *d_tile_base;    /* [n_tiles + 1] first posting of each tile */
     const int32_t *d_tile_term_off;/* [n_tiles, vocab + 1] term offsets relative to the tile base */
     const uint32_t *d_postings;    /* [P] (doc_in_tile << 16) | tf, ascending doc within (tile, term) */
-    const double *d_doc_t4;        /* [n_docs] k1 * (1 - b + b * dl / avgdl), global avgdl */
+    const int32_t *d_doc_len;      /* [n_docs] tokens per doc (<= 65535) */
+    const double *d_t4_table;      /* [max_doc_len + 1] k1 * (1 - b + b * dl / avgdl), global avgdl */
     const double *d_idf;           /* [vocab] global idf incl. epsilon floor; 0 for unseen terms */
 } orag_bm25_index_t;
 

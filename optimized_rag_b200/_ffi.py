@@ -38,10 +38,13 @@ class Bm25IndexStruct(Structure):
         ("tile_docs", c_int32),
         ("n_tiles", c_int32),
         ("has_negative_idf", c_int32),
+        ("max_doc_len", c_int32),
+        ("reserved", c_int32),
         ("d_tile_base", c_void_p),
         ("d_tile_term_off", c_void_p),
         ("d_postings", c_void_p),
-        ("d_doc_t4", c_void_p),
+        ("d_doc_len", c_void_p),
+        ("d_t4_table", c_void_p),
         ("d_idf", c_void_p),
     ]
 

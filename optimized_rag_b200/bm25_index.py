@@ -5,7 +5,7 @@ Layout consumed by csrc/bm25.cu (see include/orag.h `orag_bm25_index_t`):
   postings      uint32 [(doc_in_tile << 16) | tf], grouped by (tile, term), ascending doc
   tile_base     int64 [n_tiles+1]   first posting of each tile
   tile_term_off int32 [n_tiles, V+1] offsets of each term's run inside its tile
-  doc_t4        float64 [n_docs]    k1*(1 - b + b*dl/avgdl)   (global avgdl)
+  doc_len       int32 [n_docs]; t4_table float64 [max_dl+1] = k1*(1 - b + b*dl/avgdl) (global avgdl)
   idf           float64 [V]         global idf with the epsilon floor (rank_bm25 0.2.2 BM25Okapi._calc_idf)
 
 Global statistics (N, avgdl, df, first-seen order -> idf, eps) follow the reference's
@@ -129,8 +129,10 @@ class Bm25Index:
         dl = (doc_off[1:] - doc_off[:-1])
         self.dl = dl.to(torch.int32)
         max_dl = int(dl.max().item()) if self.n_docs else 0
-        t4 = torch.from_numpy(t4_table(max_dl, self.avgdl)).to(dev)
-        self.doc_t4 = t4[dl] if self.n_docs else torch.zeros(0, dtype=torch.float64, device=dev)
+        if max_dl > 0xFFFF:
+            raise ValueError("documents longer than 65535 tokens are not representable in the tile layout")
+        self.max_dl = max_dl
+        self.t4_table = torch.from_numpy(t4_table(max_dl, self.avgdl)).to(dev)
 
         V1 = self.vocab + 1
         T = self.tile_docs
@@ -178,8 +180,13 @@ class Bm25Index:
             n_docs=self.n_docs, vocab=self.vocab, tile_docs=self.tile_docs, n_tiles=self.n_tiles,
             has_negative_idf=int(self.has_negative_idf),
             d_tile_base=self.tile_base.data_ptr(), d_tile_term_off=self.tile_term_off.data_ptr(),
-            d_postings=self.postings.data_ptr(), d_doc_t4=self.doc_t4.data_ptr(), d_idf=self.idf.data_ptr())
+            max_doc_len=self.max_dl, reserved=0, d_postings=self.postings.data_ptr(), d_doc_len=self.dl.data_ptr(),
+            d_t4_table=self.t4_table.data_ptr(), d_idf=self.idf.data_ptr())
         self._ws = None
+
+    @property
+    def doc_t4(self) -> torch.Tensor:
+        return self.t4_table[self.dl.long()]
 
     # ------------------------------------------------------------------ queries
     def _workspace(self, n_queries: int, k: int, flags: int) -> torch.Tensor:

@@ -5,7 +5,7 @@
 // `tile_docs` consecutive docs; each tile owns a contiguous run of 4-byte postings
 // ((doc_in_tile << 16) | tf) grouped by term, ascending doc inside a term, plus a row of
 // vocab+1 term offsets.  A tile is the unit of work: one CTA keeps a float64 accumulator and the
-// per-document length term t4 = k1*(1 - b + b*dl/avgdl) for its docs in shared memory and
+// per-document length (u16; t4 = k1*(1 - b + b*dl/avgdl) comes from a small dl-indexed table) in shared memory and
 // streams, for every query of the batch, the posting runs of the query's terms with coalesced
 // 4-byte reads.
 //
@@ -42,6 +42,7 @@ struct Params {
     unsigned long long *thr_bits;  // [n_queries] bits of the (positive) threshold score
     uint32_t *cnt;
     uint32_t *hist;                // [n_queries, kHistBins]
+    uint32_t *topbin;              // [n_queries] highest occupied histogram bin
     int32_t *cand_doc;             // [n_queries, cap] local doc id
     double *cand_score;            // [n_queries, cap]
     int cap;
@@ -60,107 +61,227 @@ __device__ __forceinline__ unsigned long long bin_floor_bits(int b)
     return (unsigned long long)(b + kBinBase) << 47;
 }
 
+// Candidate emission + threshold tightening.  Every 8th emission of a query re-derives its
+// threshold from the log-scale histogram, scanning down from the highest occupied bin in batches
+// of 16 bins fetched with four independent 16-byte loads.
 __device__ __noinline__ void emit(const Params &p, int q, int32_t doc, double v)
 {
-    uint32_t slot = atomicAdd(p.cnt + q, 1u);
+    const uint32_t slot = atomicAdd(p.cnt + q, 1u);
     if (slot < (uint32_t)p.cap) {
         p.cand_doc[(int64_t)q * p.cap + slot] = doc;
         p.cand_score[(int64_t)q * p.cap + slot] = v;
     }
     uint32_t *h = p.hist + (int64_t)q * kHistBins;
-    atomicAdd(h + score_bin(v), 1u);
-    if ((slot & 7u) == 0u) {
-        uint32_t acc = 0;
-        int b = kHistBins - 1;
-        for (; b >= 0; --b) {
-            acc += __ldcg(h + b);
-            if (acc >= (uint32_t)p.k) break;
+    const int bin = score_bin(v);
+    atomicAdd(h + bin, 1u);
+    const int old_top = (int)atomicMax(p.topbin + q, (uint32_t)bin);
+    if ((slot & 7u) != 7u) return;
+    const int hi = old_top > bin ? old_top : bin;
+    const uint4 *h4 = reinterpret_cast<const uint4 *>(h);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    uint32_t acc = 0;
+    int found = -1;
+    for (int c = hi >> 2; c >= 0 && found < 0; c -= 4) {
+        const uint4 w0 = __ldcg(h4 + c);
+        const uint4 w1 = c >= 1 ? __ldcg(h4 + c - 1) : zero;
+        const uint4 w2 = c >= 2 ? __ldcg(h4 + c - 2) : zero;
+        const uint4 w3 = c >= 3 ? __ldcg(h4 + c - 3) : zero;
+        const uint32_t vals[16] = {w0.w, w0.z, w0.y, w0.x, w1.w, w1.z, w1.y, w1.x,
+                                   w2.w, w2.z, w2.y, w2.x, w3.w, w3.z, w3.y, w3.x};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            acc += vals[j];
+            if (found < 0 && acc >= (uint32_t)p.k) found = 4 * c + 3 - j;
         }
-        // one bin below the k-th best's bin: also keeps docs whose NORMALISED score could tie with it
-        if (b >= 2) atomicMax(p.thr_bits + q, bin_floor_bits(b - 1));
     }
+    // one bin below the k-th best's bin: also keeps docs whose NORMALISED score could tie with it
+    if (found >= 2) atomicMax(p.thr_bits + q, bin_floor_bits(found - 1));
 }
 
+constexpr int kRegTerms = 8;   // query terms whose tile runs are staged in registers
+constexpr int kRegPosts = 2;   // postings per thread per staged term (runs up to 512 entries)
+
+struct TermRun {  // one query term inside one tile
+    int start;
+    int len;
+    double idf;
+};
+
+// offsets / idf of query q's terms in this tile (threads 0..nt-1 each fetch one term)
+__device__ __forceinline__ TermRun fetch_run(const Params &p, const int32_t *toff, int q, int i)
+{
+    TermRun r;
+    r.start = 0; r.len = 0; r.idf = 0.0;
+    const int t = p.q_terms[(int64_t)q * p.max_terms + i];
+    if (t >= 0 && t < p.ix.vocab) {
+        const double idf = p.ix.d_idf[t];
+        if (idf != 0.0) {
+            r.idf = idf;
+            r.start = toff[t];
+            r.len = toff[t + 1] - r.start;
+        }
+    }
+    return r;
+}
+
+// Software pipeline over the queries of the batch (per tile):
+//   iteration i:  issue the posting loads of query i+1 and the offset loads of query i+2,
+//                 then accumulate + drain query i out of registers.
+// so the only global-memory latency on the critical path is the first query of a tile.
 template <bool kDense>
 __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_constant__ Params p)
 {
     extern __shared__ double smem_d[];
     const int T = p.ix.tile_docs;
-    double *acc = smem_d;       // [T]
-    double *t4s = smem_d + T;   // [T]
-    __shared__ int s_start[kMaxTerms];
-    __shared__ int s_len[kMaxTerms];
-    __shared__ double s_idf[kMaxTerms];
+    double *acc = smem_d;                                   // [T]
+    uint16_t *dls = reinterpret_cast<uint16_t *>(smem_d + T);  // [T] document lengths
+    __shared__ int s_start[3][kMaxTerms];
+    __shared__ int s_len[3][kMaxTerms];
+    __shared__ double s_idf[3][kMaxTerms];
+    __shared__ int s_nt[3];
 
     const int V1 = p.ix.vocab + 1;
+    const int nq = p.n_queries;
+    const double *__restrict__ t4tab = p.ix.d_t4_table;
     for (int tile = blockIdx.x; tile < p.ix.n_tiles; tile += gridDim.x) {
         const int64_t base_doc = (int64_t)tile * T;
         const int nd = (int)min((int64_t)T, p.ix.n_docs - base_doc);
         __syncthreads();
         for (int i = threadIdx.x; i < T; i += kThreads) {
             acc[i] = 0.0;
-            t4s[i] = i < nd ? p.ix.d_doc_t4[base_doc + i] : 1.0;
+            dls[i] = i < nd ? (uint16_t)p.ix.d_doc_len[base_doc + i] : (uint16_t)0;
         }
         const uint32_t *tile_post = p.ix.d_postings + p.ix.d_tile_base[tile];
         const int32_t *toff = p.ix.d_tile_term_off + (int64_t)tile * V1;
         // stagger the query order across CTAs so a query's threshold is established by few CTAs
-        const int q_shift = (int)(((int64_t)blockIdx.x * 7919) % p.n_queries);
-        for (int qi = 0; qi < p.n_queries; ++qi) {
-            const int q = (qi + q_shift) % p.n_queries;
+        const int q_shift = (int)(((int64_t)blockIdx.x * 7919) % nq);
+
+        // prologue: runs of queries 0 and 1 -> smem buffers 0 and 1
+        for (int pre = 0; pre < 2 && pre < nq; ++pre) {
+            const int q = (pre + q_shift) % nq;
             const int nt = min(p.q_lens[q], p.max_terms);
-            __syncthreads();  // previous query's drain is done; term arrays and acc are free
             if (threadIdx.x < nt) {
-                int t = p.q_terms[(int64_t)q * p.max_terms + threadIdx.x];
-                int st = 0, ln = 0;
-                double idf = 0.0;
-                if (t >= 0 && t < p.ix.vocab) {
-                    idf = p.ix.d_idf[t];
-                    if (idf != 0.0) {
-                        st = toff[t];
-                        ln = toff[t + 1] - st;
-                    }
-                }
-                s_start[threadIdx.x] = st;
-                s_len[threadIdx.x] = ln;
-                s_idf[threadIdx.x] = idf;
+                TermRun r = fetch_run(p, toff, q, threadIdx.x);
+                s_start[pre][threadIdx.x] = r.start;
+                s_len[pre][threadIdx.x] = r.len;
+                s_idf[pre][threadIdx.x] = r.idf;
             }
-            __syncthreads();
+            if (threadIdx.x == 0) s_nt[pre] = nt;
+        }
+        __syncthreads();
+        uint32_t cur[kRegTerms * kRegPosts], nxt[kRegTerms * kRegPosts];
+        auto load_posts = [&](int buf, uint32_t (&dst)[kRegTerms * kRegPosts]) {
+            const int nt = min(s_nt[buf], kRegTerms);
+#pragma unroll
+            for (int i = 0; i < kRegTerms; ++i) {
+#pragma unroll
+                for (int r = 0; r < kRegPosts; ++r) {
+                    const int j = threadIdx.x + r * kThreads;
+                    dst[i * kRegPosts + r] = (i < nt && j < s_len[buf][i]) ? __ldg(tile_post + s_start[buf][i] + j) : 0u;
+                }
+            }
+        };
+        load_posts(0, cur);
+
+        for (int qi = 0; qi < nq; ++qi) {
+            const int buf = qi % 3;
+            const int q = (qi + q_shift) % nq;
+            // ---- prefetch: postings of query qi+1, runs of query qi+2
+            if (qi + 1 < nq) load_posts((qi + 1) % 3, nxt);
+            TermRun pre;
+            int pre_nt = 0;
+            pre.start = 0; pre.len = 0; pre.idf = 0.0;
+            if (qi + 2 < nq) {
+                const int q2 = (qi + 2 + q_shift) % nq;
+                pre_nt = min(p.q_lens[q2], p.max_terms);
+                if (threadIdx.x < pre_nt) pre = fetch_run(p, toff, q2, threadIdx.x);
+            }
+            // ---- accumulate query qi, one term at a time (query order per doc)
+            const int nt = s_nt[buf];
             bool touched = false;
             for (int i = 0; i < nt; ++i) {
-                const int ln = s_len[i];
+                const int ln = s_len[buf][i];
                 if (ln == 0) continue;  // OOV, zero idf, or no posting in this tile (uniform)
                 touched = true;
-                const double idf = s_idf[i];
-                const uint32_t *pp = tile_post + s_start[i];
-                for (int j = threadIdx.x; j < ln; j += kThreads) {
+                const double idf = s_idf[buf][i];
+                if (i < kRegTerms) {
+#pragma unroll
+                    for (int r = 0; r < kRegPosts; ++r) {
+                        // static register index: select by i through an unrolled compare chain
+                        uint32_t post = 0;
+#pragma unroll
+                        for (int ii = 0; ii < kRegTerms; ++ii) post = (ii == i) ? cur[ii * kRegPosts + r] : post;
+                        if (threadIdx.x + r * kThreads < ln) {
+                            const int d = (int)(post >> 16);
+                            const double tf = (double)(post & 0xFFFFu);
+                            const double den = __dadd_rn(tf, __ldg(t4tab + dls[d]));
+                            const double c = __dmul_rn(idf, __ddiv_rn(__dmul_rn(tf, 2.5), den));
+                            acc[d] = __dadd_rn(acc[d], c);
+                        }
+                    }
+                }
+                const int j0 = (i < kRegTerms) ? kRegPosts * kThreads : 0;
+                const uint32_t *pp = tile_post + s_start[buf][i];
+                for (int j = j0 + threadIdx.x; j < ln; j += kThreads) {
                     const uint32_t post = __ldg(pp + j);
                     const int d = (int)(post >> 16);
                     const double tf = (double)(post & 0xFFFFu);
-                    const double den = __dadd_rn(tf, t4s[d]);
-                    const double num = __dmul_rn(tf, 2.5);
-                    const double c = __dmul_rn(idf, __ddiv_rn(num, den));
+                    const double den = __dadd_rn(tf, __ldg(t4tab + dls[d]));
+                    const double c = __dmul_rn(idf, __ddiv_rn(__dmul_rn(tf, 2.5), den));
                     acc[d] = __dadd_rn(acc[d], c);
                 }
-                __syncthreads();  // term i fully applied before term i+1 (query order per doc)
+                __syncthreads();  // term i fully applied before term i+1
             }
-            if (!touched) continue;
-            // drain: every touched doc is reported once with its final score; accumulator reset
-            double thr = 0.0;
-            if (!kDense) thr = __longlong_as_double((long long)__ldcg(p.thr_bits + q));
-            for (int i = 0; i < nt; ++i) {
-                const int ln = s_len[i];
-                if (ln == 0) continue;
-                const uint32_t *pp = tile_post + s_start[i];
-                for (int j = threadIdx.x; j < ln; j += kThreads) {
-                    const int d = (int)(__ldg(pp + j) >> 16);
-                    const unsigned long long bits = atomicExch((unsigned long long *)(acc + d), 0ull);
-                    const double v = __longlong_as_double((long long)bits);
-                    if (v != 0.0) {
-                        if (kDense) p.dense_out[(int64_t)(q - p.q_begin) * p.ix.n_docs + base_doc + d] = v;
-                        else if (v >= thr) emit(p, q, (int32_t)(base_doc + d), v);
+            // ---- drain: every touched doc is reported once with its final score; accumulator reset
+            if (touched) {
+                double thr = 0.0;
+                if (!kDense) thr = __longlong_as_double((long long)__ldcg(p.thr_bits + q));
+                for (int i = 0; i < nt; ++i) {
+                    const int ln = s_len[buf][i];
+                    if (ln == 0) continue;
+                    const uint32_t *pp = tile_post + s_start[buf][i];
+                    const int j0 = (i < kRegTerms) ? kRegPosts * kThreads : 0;
+                    for (int r = 0; r < (i < kRegTerms ? kRegPosts : 0); ++r) {
+                        uint32_t post = 0;
+#pragma unroll
+                        for (int ii = 0; ii < kRegTerms; ++ii)
+#pragma unroll
+                            for (int rr = 0; rr < kRegPosts; ++rr)
+                                post = (ii == i && rr == r) ? cur[ii * kRegPosts + rr] : post;
+                        if (threadIdx.x + r * kThreads < ln) {
+                            const int d = (int)(post >> 16);
+                            const unsigned long long bits = atomicExch((unsigned long long *)(acc + d), 0ull);
+                            const double v = __longlong_as_double((long long)bits);
+                            if (v != 0.0) {
+                                if (kDense) p.dense_out[(int64_t)q * p.ix.n_docs + base_doc + d] = v;
+                                else if (v >= thr) emit(p, q, (int32_t)(base_doc + d), v);
+                            }
+                        }
+                    }
+                    for (int j = j0 + threadIdx.x; j < ln; j += kThreads) {
+                        const int d = (int)(__ldg(pp + j) >> 16);
+                        const unsigned long long bits = atomicExch((unsigned long long *)(acc + d), 0ull);
+                        const double v = __longlong_as_double((long long)bits);
+                        if (v != 0.0) {
+                            if (kDense) p.dense_out[(int64_t)q * p.ix.n_docs + base_doc + d] = v;
+                            else if (v >= thr) emit(p, q, (int32_t)(base_doc + d), v);
+                        }
                     }
                 }
             }
+            // ---- rotate: publish the runs of query qi+2 (buffer last read in iteration qi-1), shift registers
+            if (qi + 2 < nq) {
+                const int b2 = (qi + 2) % 3;
+                if (threadIdx.x < pre_nt) {
+                    s_start[b2][threadIdx.x] = pre.start;
+                    s_len[b2][threadIdx.x] = pre.len;
+                    s_idf[b2][threadIdx.x] = pre.idf;
+                }
+                if (threadIdx.x == 0) s_nt[b2] = pre_nt;
+            }
+#pragma unroll
+            for (int x = 0; x < kRegTerms * kRegPosts; ++x) cur[x] = nxt[x];
+            __syncthreads();  // drain of qi done (acc free) and runs of qi+2 visible before iteration qi+1
         }
     }
 }
@@ -174,7 +295,7 @@ __device__ double score_doc(const orag_bm25_index_t &ix, const int32_t *terms, i
     const uint32_t want = (uint32_t)(doc - (int64_t)tile * T);
     const uint32_t *tile_post = ix.d_postings + ix.d_tile_base[tile];
     const int32_t *toff = ix.d_tile_term_off + (int64_t)tile * (ix.vocab + 1);
-    const double t4 = ix.d_doc_t4[doc];
+    const double t4 = ix.d_t4_table[ix.d_doc_len[doc]];
     double s = 0.0;
     for (int i = 0; i < nt; ++i) {
         int t = terms[i];
@@ -261,7 +382,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ P
     }
 }
 
-__global__ void init_state_kernel(unsigned long long *thr_bits, uint32_t *cnt, uint32_t *hist, int n_queries)
+__global__ void init_state_kernel(unsigned long long *thr_bits, uint32_t *cnt, uint32_t *hist, uint32_t *topbin,
+                                  int n_queries)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t total = (int64_t)n_queries * kHistBins;
@@ -269,6 +391,7 @@ __global__ void init_state_kernel(unsigned long long *thr_bits, uint32_t *cnt, u
     if (i < n_queries) {
         thr_bits[i] = 1ull;  // smallest positive double: "score > 0"
         cnt[i] = 0;
+        topbin[i] = 0;
     }
 }
 
@@ -285,10 +408,12 @@ static int validate_index(const orag_bm25_index_t *ix)
     ORAG_REQUIRE(ix->tile_docs >= 32 && ix->tile_docs <= 65536 && (ix->tile_docs & (ix->tile_docs - 1)) == 0,
                  "tile_docs must be a power of two in [32, 65536]");
     ORAG_REQUIRE((int64_t)ix->n_tiles == (ix->n_docs + ix->tile_docs - 1) / ix->tile_docs, "n_tiles");
-    ORAG_REQUIRE(ix->tile_docs * 16 <= 200 * 1024, "tile_docs too large for shared memory");
+    ORAG_REQUIRE(ix->tile_docs * 10 <= 200 * 1024, "tile_docs too large for shared memory");
     if (ix->n_docs > 0)
-        ORAG_REQUIRE(ix->d_tile_base && ix->d_tile_term_off && ix->d_postings && ix->d_doc_t4 && ix->d_idf,
+        ORAG_REQUIRE(ix->d_tile_base && ix->d_tile_term_off && ix->d_postings && ix->d_doc_len && ix->d_t4_table &&
+                         ix->d_idf,
                      "index pointers");
+    ORAG_REQUIRE(ix->max_doc_len >= 0 && ix->max_doc_len <= 65535, "document length above 65535 tokens");
     return ORAG_OK;
 }
 
@@ -329,6 +454,7 @@ extern "C" size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *ix, int n_q
     size_t b = 0;
     b += orag::align_up((size_t)n_queries * 8, 256);                        // thr_bits
     b += orag::align_up((size_t)n_queries * 4, 256);                        // cnt
+    b += orag::align_up((size_t)n_queries * 4, 256);                        // topbin
     b += orag::align_up((size_t)n_queries * orag::bm25::kHistBins * 4, 256);  // hist
     b += orag::align_up((size_t)n_queries * cap * 4, 256);                  // cand_doc
     b += orag::align_up((size_t)n_queries * cap * 8, 256);                  // cand_score
@@ -337,11 +463,11 @@ extern "C" size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *ix, int n_q
 
 static int launch_tiles(const Params &p, bool dense, cudaStream_t st)
 {
-    const size_t smem = (size_t)p.ix.tile_docs * 16;
+    const size_t smem = (size_t)p.ix.tile_docs * 10;
     int grid = p.ix.n_tiles;
     int per_sm = (int)((200 * 1024) / (smem + 2048));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 6) per_sm = 6;
+    if (per_sm > 8) per_sm = 8;
     int lim = orag::sm_count() * per_sm;
     if (grid > lim) grid = lim;
     if (grid < 1) return ORAG_OK;
@@ -439,13 +565,14 @@ extern "C" int orag_bm25_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, 
     p.cap = cap;
     p.thr_bits = (unsigned long long *)w; w += orag::align_up((size_t)n_queries * 8, 256);
     p.cnt = (uint32_t *)w;                w += orag::align_up((size_t)n_queries * 4, 256);
+    p.topbin = (uint32_t *)w;             w += orag::align_up((size_t)n_queries * 4, 256);
     p.hist = (uint32_t *)w;               w += orag::align_up((size_t)n_queries * orag::bm25::kHistBins * 4, 256);
     p.cand_doc = (int32_t *)w;            w += orag::align_up((size_t)n_queries * cap * 4, 256);
     p.cand_score = (double *)w;
     {
         int64_t total = (int64_t)n_queries * orag::bm25::kHistBins;
         orag::bm25::init_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.thr_bits, p.cnt, p.hist,
-                                                                                      n_queries);
+                                                                                      p.topbin, n_queries);
         ORAG_LAUNCH_CHECK();
     }
     rc = launch_tiles(p, false, st);

@@ -125,26 +125,35 @@ __device__ __forceinline__ int cos_bin(float c)
     int b = (int)floorf((c + 1.0f) * (kHistBins / 2));
     return b < 0 ? 0 : (b > kHistBins - 1 ? kHistBins - 1 : b);
 }
-// lower edge of bin b, lowered by one more bin (guards float rounding at the edge)
-__device__ __forceinline__ float bin_floor(int b) { return (float)(b - 1) * (2.0f / kHistBins) - 1.0f; }
+// lower edge of bin b: a valid lower bound of every value binned into b (float rounding at the
+// edge is covered by the slack inside the first-pass margin)
+__device__ __forceinline__ float bin_floor(int b) { return (float)b * (2.0f / kHistBins) - 1.0f; }
 
-// Candidate emission + threshold tightening (rare path).
+// Candidate emission + threshold tightening (rare path).  Every 8th emission of a query re-derives
+// its threshold from the histogram: largest bin b with count(bins >= b) >= k.  The scan walks down
+// from the top in batches of 16 bins fetched with four independent 16-byte loads.
 __device__ __noinline__ void emit_candidate(const ScanParams &p, int q, int32_t local_row, float v)
 {
-    uint32_t slot = atomicAdd(p.cnt + q, 1u);
+    const uint32_t slot = atomicAdd(p.cnt + q, 1u);
     if (slot < (uint32_t)p.cap) p.cand[(int64_t)q * p.cap + slot] = local_row;
-    int bin = cos_bin(v * p.inv_qnorm[q]);
+    const int bin = cos_bin(v * p.inv_qnorm[q]);
     uint32_t *h = p.hist + (int64_t)q * kHistBins;
     atomicAdd(h + bin, 1u);
-    if ((slot & 3u) == 0u) {
-        uint32_t acc = 0;
-        int b = kHistBins - 1;
-        for (; b >= 0; --b) {
-            acc += __ldcg(h + b);
-            if (acc >= (uint32_t)p.k) break;
+    if ((slot & 7u) != 7u) return;
+    const uint4 *h4 = reinterpret_cast<const uint4 *>(h);
+    uint32_t acc = 0;
+    int found = -1;
+    for (int c = kHistBins / 4 - 1; c >= 3 && found < 0; c -= 4) {
+        const uint4 w0 = __ldcg(h4 + c), w1 = __ldcg(h4 + c - 1), w2 = __ldcg(h4 + c - 2), w3 = __ldcg(h4 + c - 3);
+        const uint32_t vals[16] = {w0.w, w0.z, w0.y, w0.x, w1.w, w1.z, w1.y, w1.x,
+                                   w2.w, w2.z, w2.y, w2.x, w3.w, w3.z, w3.y, w3.x};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            acc += vals[j];
+            if (found < 0 && acc >= (uint32_t)p.k) found = 4 * c + 3 - j;
         }
-        if (b >= 1) atomicMax(p.thr_key + q, float_to_ordered(bin_floor(b)));
     }
+    if (found >= 1) atomicMax(p.thr_key + q, float_to_ordered(bin_floor(found)));
 }
 
 template <bool kBf16>
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(256) seed_finalize_kernel(const float *__restr
             acc += h[b];
             if (acc >= (uint32_t)k) break;
         }
-        s_thr = (b >= 1) ? bin_floor(b) : -INFINITY;
+        s_thr = (b >= 1) ? bin_floor(b) : -INFINITY;  // fewer than k rows seen: keep everything
     }
     __syncthreads();
     const float thr = s_thr;

@@ -15,7 +15,7 @@ constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
-constexpr int kHistBins = 1024;
+constexpr int kHistBins = 512;  // bins of width 2/512 over cos in [-1, 1]
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ +
                               2 * kMaxN * sizeof(float);
 
