@@ -134,6 +134,7 @@ typedef struct orag_bm25_index {
     const uint32_t *d_postings;    /* [P] (doc_in_tile << 16) | tf, ascending doc within (tile, term) */
     const int32_t *d_doc_len;      /* [n_docs] tokens per doc (<= 65535) */
     const double *d_t4_table;      /* [max_doc_len + 1] k1 * (1 - b + b * dl / avgdl), global avgdl */
+    const double *d_r_table;       /* [max_doc_len + 1, 4] tf*(k1+1) / (tf + t4[dl]) for tf = 1..4 */
     const double *d_idf;           /* [vocab] global idf incl. epsilon floor; 0 for unseen terms */
 } orag_bm25_index_t;
 

@@ -45,6 +45,7 @@ class Bm25IndexStruct(Structure):
         ("d_postings", c_void_p),
         ("d_doc_len", c_void_p),
         ("d_t4_table", c_void_p),
+        ("d_r_table", c_void_p),
         ("d_idf", c_void_p),
     ]
 

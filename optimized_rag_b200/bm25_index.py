@@ -132,7 +132,11 @@ class Bm25Index:
         if max_dl > 0xFFFF:
             raise ValueError("documents longer than 65535 tokens are not representable in the tile layout")
         self.max_dl = max_dl
-        self.t4_table = torch.from_numpy(t4_table(max_dl, self.avgdl)).to(dev)
+        t4_np = t4_table(max_dl, self.avgdl)
+        self.t4_table = torch.from_numpy(t4_np).to(dev)
+        # r[dl, tf-1] = tf*(k1+1) / (tf + t4[dl]) for tf = 1..4, numpy float64 in rank_bm25's operation order
+        tf_np = np.arange(1, 5)[None, :]
+        self.r_table = torch.from_numpy(np.ascontiguousarray(tf_np * (K1 + 1) / (tf_np + t4_np[:, None]))).to(dev)
 
         V1 = self.vocab + 1
         T = self.tile_docs
@@ -181,7 +185,7 @@ class Bm25Index:
             has_negative_idf=int(self.has_negative_idf),
             d_tile_base=self.tile_base.data_ptr(), d_tile_term_off=self.tile_term_off.data_ptr(),
             max_doc_len=self.max_dl, reserved=0, d_postings=self.postings.data_ptr(), d_doc_len=self.dl.data_ptr(),
-            d_t4_table=self.t4_table.data_ptr(), d_idf=self.idf.data_ptr())
+            d_t4_table=self.t4_table.data_ptr(), d_r_table=self.r_table.data_ptr(), d_idf=self.idf.data_ptr())
         self._ws = None
 
     @property

@@ -26,7 +26,7 @@
 namespace orag {
 namespace bm25 {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 constexpr int kMaxTerms = 64;
 constexpr int kHistBins = 2048;
 constexpr int kBinBase = (1023 - 20) << 5;  // bins start at 2^-20, 32 bins per octave
@@ -98,56 +98,104 @@ __device__ __noinline__ void emit(const Params &p, int q, int32_t doc, double v)
     if (found >= 2) atomicMax(p.thr_bits + q, bin_floor_bits(found - 1));
 }
 
-constexpr int kRegTerms = 8;   // query terms whose tile runs are staged in registers
-constexpr int kRegPosts = 2;   // postings per thread per staged term (runs up to 512 entries)
+constexpr int kStageCap = 2048;  // postings of one query staged in shared memory per buffer
+constexpr int kRTf = 4;          // r = tf*(k1+1)/(tf + t4[dl]) is tabulated for tf = 1..kRTf
 
-struct TermRun {  // one query term inside one tile
-    int start;
-    int len;
-    double idf;
-};
-
-// offsets / idf of query q's terms in this tile (threads 0..nt-1 each fetch one term)
-__device__ __forceinline__ TermRun fetch_run(const Params &p, const int32_t *toff, int q, int i)
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
 {
-    TermRun r;
-    r.start = 0; r.len = 0; r.idf = 0.0;
-    const int t = p.q_terms[(int64_t)q * p.max_terms + i];
-    if (t >= 0 && t < p.ix.vocab) {
-        const double idf = p.ix.d_idf[t];
-        if (idf != 0.0) {
-            r.idf = idf;
-            r.start = toff[t];
-            r.len = toff[t + 1] - r.start;
-        }
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// contribution of one posting, in the reference's operation order (see file header)
+__device__ __forceinline__ double contribution(const Params &p, uint32_t post, uint32_t dl, double idf)
+{
+    const uint32_t tf = post & 0xFFFFu;
+    double r;
+    if (tf <= (uint32_t)kRTf) {
+        r = __ldg(p.ix.d_r_table + dl * kRTf + (tf - 1));  // same IEEE ops, evaluated once at index build
+    } else {
+        const double f = (double)tf;
+        r = __ddiv_rn(__dmul_rn(f, 2.5), __dadd_rn(f, __ldg(p.ix.d_t4_table + dl)));
     }
-    return r;
+    return __dmul_rn(idf, r);
 }
 
-// Software pipeline over the queries of the batch (per tile):
-//   iteration i:  issue the posting loads of query i+1 and the offset loads of query i+2,
-//                 then accumulate + drain query i out of registers.
-// so the only global-memory latency on the critical path is the first query of a tile.
+// One CTA per doc-range tile, looping over the queries of the batch as a software pipeline:
+//   iteration i: cp.async the posting runs of query i+1 into the other staging buffer and fetch the
+//   run descriptors of query i+2, while query i is accumulated and drained out of shared memory.
 template <bool kDense>
 __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_constant__ Params p)
 {
     extern __shared__ double smem_d[];
     const int T = p.ix.tile_docs;
-    double *acc = smem_d;                                   // [T]
-    uint16_t *dls = reinterpret_cast<uint16_t *>(smem_d + T);  // [T] document lengths
-    __shared__ int s_start[3][kMaxTerms];
-    __shared__ int s_len[3][kMaxTerms];
+    double *acc = smem_d;                                          // [T]
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_d + T);    // [2][kStageCap]
+    uint16_t *dls = reinterpret_cast<uint16_t *>(stage + 2 * kStageCap);  // [T] document lengths
+    __shared__ int s_start[3][kMaxTerms];  // run start inside the tile's postings
+    __shared__ int s_len[3][kMaxTerms];    // run length
+    __shared__ int s_soff[3][kMaxTerms];   // offset of the staged part inside the staging buffer
+    __shared__ int s_slen[3][kMaxTerms];   // staged length (<= run length)
     __shared__ double s_idf[3][kMaxTerms];
     __shared__ int s_nt[3];
 
     const int V1 = p.ix.vocab + 1;
     const int nq = p.n_queries;
-    const double *__restrict__ t4tab = p.ix.d_t4_table;
+    const int tid = threadIdx.x;
+
+    // run descriptors of query slot `qi` -> buffer `buf` (threads < nt fetch, thread 0 lays out the staging)
+    auto fetch_runs = [&](const int32_t *toff, int qi, int q_shift, int buf) {
+        const int q = (qi + q_shift) % nq;
+        const int nt = min(p.q_lens[q], p.max_terms);
+        if (tid < nt) {
+            int st = 0, ln = 0;
+            double idf = 0.0;
+            const int t = p.q_terms[(int64_t)q * p.max_terms + tid];
+            if (t >= 0 && t < p.ix.vocab) {
+                idf = p.ix.d_idf[t];
+                if (idf != 0.0) {
+                    st = toff[t];
+                    ln = toff[t + 1] - st;
+                } else {
+                    idf = 0.0;
+                }
+            }
+            s_start[buf][tid] = st;
+            s_len[buf][tid] = ln;
+            s_idf[buf][tid] = idf;
+        }
+        if (tid == 0) s_nt[buf] = nt;
+    };
+    auto layout_stage = [&](int buf) {  // thread 0 only, after fetch_runs is visible
+        int off = 0;
+        const int nt = s_nt[buf];
+        for (int i = 0; i < nt; ++i) {
+            const int take = min(s_len[buf][i], kStageCap - off);
+            s_soff[buf][i] = off;
+            s_slen[buf][i] = take;
+            off += take;
+        }
+    };
+    auto issue_stage = [&](const uint32_t *tile_post, int buf, int sbuf) {
+        const int nt = s_nt[buf];
+        uint32_t *dst = stage + sbuf * kStageCap;
+        for (int i = 0; i < nt; ++i) {
+            const int n = s_slen[buf][i];
+            const uint32_t *src = tile_post + s_start[buf][i];
+            uint32_t *d = dst + s_soff[buf][i];
+            for (int j = tid; j < n; j += kThreads) cp_async4(d + j, src + j);
+        }
+        cp_async_commit();
+    };
+
     for (int tile = blockIdx.x; tile < p.ix.n_tiles; tile += gridDim.x) {
         const int64_t base_doc = (int64_t)tile * T;
         const int nd = (int)min((int64_t)T, p.ix.n_docs - base_doc);
         __syncthreads();
-        for (int i = threadIdx.x; i < T; i += kThreads) {
+        for (int i = tid; i < T; i += kThreads) {
             acc[i] = 0.0;
             dls[i] = i < nd ? (uint16_t)p.ix.d_doc_len[base_doc + i] : (uint16_t)0;
         }
@@ -156,46 +204,26 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
         // stagger the query order across CTAs so a query's threshold is established by few CTAs
         const int q_shift = (int)(((int64_t)blockIdx.x * 7919) % nq);
 
-        // prologue: runs of queries 0 and 1 -> smem buffers 0 and 1
-        for (int pre = 0; pre < 2 && pre < nq; ++pre) {
-            const int q = (pre + q_shift) % nq;
-            const int nt = min(p.q_lens[q], p.max_terms);
-            if (threadIdx.x < nt) {
-                TermRun r = fetch_run(p, toff, q, threadIdx.x);
-                s_start[pre][threadIdx.x] = r.start;
-                s_len[pre][threadIdx.x] = r.len;
-                s_idf[pre][threadIdx.x] = r.idf;
-            }
-            if (threadIdx.x == 0) s_nt[pre] = nt;
+        // prologue: descriptors of queries 0, 1; postings of query 0
+        fetch_runs(toff, 0, q_shift, 0);
+        if (nq > 1) fetch_runs(toff, 1, q_shift, 1);
+        __syncthreads();
+        if (tid == 0) {
+            layout_stage(0);
+            if (nq > 1) layout_stage(1);
         }
         __syncthreads();
-        uint32_t cur[kRegTerms * kRegPosts], nxt[kRegTerms * kRegPosts];
-        auto load_posts = [&](int buf, uint32_t (&dst)[kRegTerms * kRegPosts]) {
-            const int nt = min(s_nt[buf], kRegTerms);
-#pragma unroll
-            for (int i = 0; i < kRegTerms; ++i) {
-#pragma unroll
-                for (int r = 0; r < kRegPosts; ++r) {
-                    const int j = threadIdx.x + r * kThreads;
-                    dst[i * kRegPosts + r] = (i < nt && j < s_len[buf][i]) ? __ldg(tile_post + s_start[buf][i] + j) : 0u;
-                }
-            }
-        };
-        load_posts(0, cur);
+        issue_stage(tile_post, 0, 0);
+        cp_async_wait_all();
+        __syncthreads();
 
         for (int qi = 0; qi < nq; ++qi) {
             const int buf = qi % 3;
             const int q = (qi + q_shift) % nq;
-            // ---- prefetch: postings of query qi+1, runs of query qi+2
-            if (qi + 1 < nq) load_posts((qi + 1) % 3, nxt);
-            TermRun pre;
-            int pre_nt = 0;
-            pre.start = 0; pre.len = 0; pre.idf = 0.0;
-            if (qi + 2 < nq) {
-                const int q2 = (qi + 2 + q_shift) % nq;
-                pre_nt = min(p.q_lens[q2], p.max_terms);
-                if (threadIdx.x < pre_nt) pre = fetch_run(p, toff, q2, threadIdx.x);
-            }
+            const uint32_t *sp = stage + (qi & 1) * kStageCap;
+            // ---- prefetch: postings of query qi+1 (async), descriptors of query qi+2
+            if (qi + 1 < nq) issue_stage(tile_post, (qi + 1) % 3, (qi + 1) & 1);
+            if (qi + 2 < nq) fetch_runs(toff, qi + 2, q_shift, (qi + 2) % 3);
             // ---- accumulate query qi, one term at a time (query order per doc)
             const int nt = s_nt[buf];
             bool touched = false;
@@ -204,31 +232,18 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
                 if (ln == 0) continue;  // OOV, zero idf, or no posting in this tile (uniform)
                 touched = true;
                 const double idf = s_idf[buf][i];
-                if (i < kRegTerms) {
-#pragma unroll
-                    for (int r = 0; r < kRegPosts; ++r) {
-                        // static register index: select by i through an unrolled compare chain
-                        uint32_t post = 0;
-#pragma unroll
-                        for (int ii = 0; ii < kRegTerms; ++ii) post = (ii == i) ? cur[ii * kRegPosts + r] : post;
-                        if (threadIdx.x + r * kThreads < ln) {
-                            const int d = (int)(post >> 16);
-                            const double tf = (double)(post & 0xFFFFu);
-                            const double den = __dadd_rn(tf, __ldg(t4tab + dls[d]));
-                            const double c = __dmul_rn(idf, __ddiv_rn(__dmul_rn(tf, 2.5), den));
-                            acc[d] = __dadd_rn(acc[d], c);
-                        }
-                    }
+                const int sl = s_slen[buf][i];
+                const uint32_t *ss = sp + s_soff[buf][i];
+                for (int j = tid; j < sl; j += kThreads) {
+                    const uint32_t post = ss[j];
+                    const uint32_t d = post >> 16;
+                    acc[d] = __dadd_rn(acc[d], contribution(p, post, dls[d], idf));
                 }
-                const int j0 = (i < kRegTerms) ? kRegPosts * kThreads : 0;
                 const uint32_t *pp = tile_post + s_start[buf][i];
-                for (int j = j0 + threadIdx.x; j < ln; j += kThreads) {
+                for (int j = sl + tid; j < ln; j += kThreads) {  // part of a long run that was not staged
                     const uint32_t post = __ldg(pp + j);
-                    const int d = (int)(post >> 16);
-                    const double tf = (double)(post & 0xFFFFu);
-                    const double den = __dadd_rn(tf, __ldg(t4tab + dls[d]));
-                    const double c = __dmul_rn(idf, __ddiv_rn(__dmul_rn(tf, 2.5), den));
-                    acc[d] = __dadd_rn(acc[d], c);
+                    const uint32_t d = post >> 16;
+                    acc[d] = __dadd_rn(acc[d], contribution(p, post, dls[d], idf));
                 }
                 __syncthreads();  // term i fully applied before term i+1
             }
@@ -239,49 +254,36 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
                 for (int i = 0; i < nt; ++i) {
                     const int ln = s_len[buf][i];
                     if (ln == 0) continue;
+                    const int sl = s_slen[buf][i];
+                    const uint32_t *ss = sp + s_soff[buf][i];
                     const uint32_t *pp = tile_post + s_start[buf][i];
-                    const int j0 = (i < kRegTerms) ? kRegPosts * kThreads : 0;
-                    for (int r = 0; r < (i < kRegTerms ? kRegPosts : 0); ++r) {
-                        uint32_t post = 0;
-#pragma unroll
-                        for (int ii = 0; ii < kRegTerms; ++ii)
-#pragma unroll
-                            for (int rr = 0; rr < kRegPosts; ++rr)
-                                post = (ii == i && rr == r) ? cur[ii * kRegPosts + rr] : post;
-                        if (threadIdx.x + r * kThreads < ln) {
-                            const int d = (int)(post >> 16);
+                    for (int j = tid; j < ln; j += kThreads) {
+                        const uint32_t d = (j < sl ? ss[j] : __ldg(pp + j)) >> 16;
+                        if (kDense) {
                             const unsigned long long bits = atomicExch((unsigned long long *)(acc + d), 0ull);
                             const double v = __longlong_as_double((long long)bits);
-                            if (v != 0.0) {
-                                if (kDense) p.dense_out[(int64_t)q * p.ix.n_docs + base_doc + d] = v;
-                                else if (v >= thr) emit(p, q, (int32_t)(base_doc + d), v);
+                            if (v != 0.0) p.dense_out[(int64_t)q * p.ix.n_docs + base_doc + d] = v;
+                        } else {
+                            const double v = acc[d];
+                            if (v == 0.0) continue;       // untouched-by-now or already drained by another run
+                            if (v < thr) {
+                                acc[d] = 0.0;             // idempotent: a racing drainer stores the same zero
+                            } else {
+                                const unsigned long long bits = atomicExch((unsigned long long *)(acc + d), 0ull);
+                                const double w = __longlong_as_double((long long)bits);
+                                if (w != 0.0) emit(p, q, (int32_t)(base_doc + d), w);
                             }
                         }
                     }
-                    for (int j = j0 + threadIdx.x; j < ln; j += kThreads) {
-                        const int d = (int)(__ldg(pp + j) >> 16);
-                        const unsigned long long bits = atomicExch((unsigned long long *)(acc + d), 0ull);
-                        const double v = __longlong_as_double((long long)bits);
-                        if (v != 0.0) {
-                            if (kDense) p.dense_out[(int64_t)q * p.ix.n_docs + base_doc + d] = v;
-                            else if (v >= thr) emit(p, q, (int32_t)(base_doc + d), v);
-                        }
-                    }
                 }
             }
-            // ---- rotate: publish the runs of query qi+2 (buffer last read in iteration qi-1), shift registers
-            if (qi + 2 < nq) {
-                const int b2 = (qi + 2) % 3;
-                if (threadIdx.x < pre_nt) {
-                    s_start[b2][threadIdx.x] = pre.start;
-                    s_len[b2][threadIdx.x] = pre.len;
-                    s_idf[b2][threadIdx.x] = pre.idf;
-                }
-                if (threadIdx.x == 0) s_nt[b2] = pre_nt;
-            }
-#pragma unroll
-            for (int x = 0; x < kRegTerms * kRegPosts; ++x) cur[x] = nxt[x];
-            __syncthreads();  // drain of qi done (acc free) and runs of qi+2 visible before iteration qi+1
+            // ---- rotate
+            cp_async_wait_all();  // this thread's copies for query qi+1 have landed
+            __syncthreads();      // ... and everyone's; drain of qi done; descriptors of qi+2 visible
+            if (qi + 2 < nq && tid == 0) layout_stage((qi + 2) % 3);
+            // (the layout is consumed by issue_stage in iteration qi+1, after the barrier that ends it --
+            //  but issue_stage runs at the START of iteration qi+1, so publish it with one more barrier)
+            __syncthreads();
         }
     }
 }
@@ -408,7 +410,8 @@ static int validate_index(const orag_bm25_index_t *ix)
     ORAG_REQUIRE(ix->tile_docs >= 32 && ix->tile_docs <= 65536 && (ix->tile_docs & (ix->tile_docs - 1)) == 0,
                  "tile_docs must be a power of two in [32, 65536]");
     ORAG_REQUIRE((int64_t)ix->n_tiles == (ix->n_docs + ix->tile_docs - 1) / ix->tile_docs, "n_tiles");
-    ORAG_REQUIRE(ix->tile_docs * 10 <= 200 * 1024, "tile_docs too large for shared memory");
+    ORAG_REQUIRE(ix->tile_docs * 10 + 16384 <= 200 * 1024, "tile_docs too large for shared memory");
+    ORAG_REQUIRE(ix->n_docs == 0 || ix->d_r_table, "r table");
     if (ix->n_docs > 0)
         ORAG_REQUIRE(ix->d_tile_base && ix->d_tile_term_off && ix->d_postings && ix->d_doc_len && ix->d_t4_table &&
                          ix->d_idf,
@@ -463,11 +466,11 @@ extern "C" size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *ix, int n_q
 
 static int launch_tiles(const Params &p, bool dense, cudaStream_t st)
 {
-    const size_t smem = (size_t)p.ix.tile_docs * 10;
+    const size_t smem = (size_t)p.ix.tile_docs * 10 + 2 * orag::bm25::kStageCap * 4;
     int grid = p.ix.n_tiles;
     int per_sm = (int)((200 * 1024) / (smem + 2048));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > 12) per_sm = 12;
     int lim = orag::sm_count() * per_sm;
     if (grid > lim) grid = lim;
     if (grid < 1) return ORAG_OK;
