@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=int(os.environ.get("ORAG_BENCH_ROWS", 10_000_000)))
     ap.add_argument("--queries", type=int, default=256)
     ap.add_argument("--mode", default=os.environ.get("ORAG_BENCH_MODE", "bf16"), choices=["tf32", "bf16"])
-    ap.add_argument("--tile-docs", type=int, default=4096)
+    ap.add_argument("--tile-docs", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
     ap.add_argument("--ref-sample-rows", type=int, default=20_000)

@@ -107,10 +107,10 @@ def local_stats(doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, token_p
 class Bm25Index:
     """One shard of the inverted index, resident on `device`."""
 
-    def __init__(self, doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, tile_docs: int = 4096,
+    def __init__(self, doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, tile_docs: int = 1024,
                  stats: Bm25Stats | None = None, doc_id_base: int = 0, chunk_docs: int = 1 << 20):
         assert doc_off.dtype == torch.int64 and tokens.dtype == torch.int32
-        assert tile_docs & (tile_docs - 1) == 0 and 32 <= tile_docs <= 8192
+        assert tile_docs & (tile_docs - 1) == 0 and 32 <= tile_docs <= 2048
         dev = tokens.device
         self.device = dev
         self.vocab = int(vocab)

@@ -4,7 +4,7 @@
 // Index layout (built by optimized_rag_b200/bm25_index.py): documents are cut into tiles of
 // `tile_docs` consecutive docs; each tile owns a contiguous run of 4-byte postings
 // ((doc_in_tile << 16) | tf) grouped by term, ascending doc inside a term, plus a row of
-// vocab+1 term offsets.  A tile is the unit of work: one CTA keeps a float64 accumulator and the
+// vocab+1 term offsets.  A tile is the unit of work: one WARP keeps a float64 accumulator and the
 // per-document length (u16; t4 = k1*(1 - b + b*dl/avgdl) comes from a small dl-indexed table) in shared memory and
 // streams, for every query of the batch, the posting runs of the query's terms with coalesced
 // 4-byte reads.
@@ -26,7 +26,8 @@
 namespace orag {
 namespace bm25 {
 
-constexpr int kThreads = 128;
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
 constexpr int kMaxTerms = 64;
 constexpr int kHistBins = 2048;
 constexpr int kBinBase = (1023 - 20) << 5;  // bins start at 2^-20, 32 bins per octave
@@ -98,17 +99,8 @@ __device__ __noinline__ void emit(const Params &p, int q, int32_t doc, double v)
     if (found >= 2) atomicMax(p.thr_bits + q, bin_floor_bits(found - 1));
 }
 
-constexpr int kStageCap = 2048;  // postings of one query staged in shared memory per buffer
-constexpr int kRTf = 4;          // r = tf*(k1+1)/(tf + t4[dl]) is tabulated for tf = 1..kRTf
-
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gmem_src)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+constexpr int kRTf = 4;      // r = tf*(k1+1)/(tf + t4[dl]) is tabulated for tf = 1..kRTf
+constexpr int kStash = 1024; // doc ids touched by the current query, per warp (drain list)
 
 // contribution of one posting, in the reference's operation order (see file header)
 __device__ __forceinline__ double contribution(const Params &p, uint32_t post, uint32_t dl, double idf)
@@ -124,166 +116,168 @@ __device__ __forceinline__ double contribution(const Params &p, uint32_t post, u
     return __dmul_rn(idf, r);
 }
 
-// One CTA per doc-range tile, looping over the queries of the batch as a software pipeline:
-//   iteration i: cp.async the posting runs of query i+1 into the other staging buffer and fetch the
-//   run descriptors of query i+2, while query i is accumulated and drained out of shared memory.
+struct LaneRun {  // lane i holds the run of query term i inside the warp's tile
+    int start;
+    int len;
+    double idf;
+};
+
+// Every warp owns one tile (a doc range of tile_docs docs, accumulators in its slice of shared
+// memory) and walks the whole query batch on its own: no CTA barrier anywhere in the loop.
+//   lanes <-> query terms   while fetching run descriptors (term id -> idf, run offsets)
+//   lanes <-> postings      while accumulating / draining a run (coalesced 4-byte reads)
+// Software pipeline per warp: term ids of query i+2 and run descriptors of query i+1 are in
+// flight while query i is processed.  Terms are applied in query order (ascending lane), each
+// run fully before the next (__syncwarp), so per-document sums follow the reference's order.
 template <bool kDense>
 __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_constant__ Params p)
 {
     extern __shared__ double smem_d[];
     const int T = p.ix.tile_docs;
-    double *acc = smem_d;                                          // [T]
-    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_d + T);    // [2][kStageCap]
-    uint16_t *dls = reinterpret_cast<uint16_t *>(stage + 2 * kStageCap);  // [T] document lengths
-    __shared__ int s_start[3][kMaxTerms];  // run start inside the tile's postings
-    __shared__ int s_len[3][kMaxTerms];    // run length
-    __shared__ int s_soff[3][kMaxTerms];   // offset of the staged part inside the staging buffer
-    __shared__ int s_slen[3][kMaxTerms];   // staged length (<= run length)
-    __shared__ double s_idf[3][kMaxTerms];
-    __shared__ int s_nt[3];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t per_warp = (size_t)T * 10 + kStash * 2;  // bytes (multiple of 8)
+    uint8_t *mine = reinterpret_cast<uint8_t *>(smem_d) + wib * per_warp;
+    double *acc = reinterpret_cast<double *>(mine);                    // [T]
+    uint16_t *dls = reinterpret_cast<uint16_t *>(mine + (size_t)T * 8);  // [T] document lengths
+    uint16_t *stash = dls + T;                                         // [kStash]
 
     const int V1 = p.ix.vocab + 1;
     const int nq = p.n_queries;
-    const int tid = threadIdx.x;
+    const int mt = p.max_terms;
+    const int warps_total = gridDim.x * kWarps;
 
-    // run descriptors of query slot `qi` -> buffer `buf` (threads < nt fetch, thread 0 lays out the staging)
-    auto fetch_runs = [&](const int32_t *toff, int qi, int q_shift, int buf) {
-        const int q = (qi + q_shift) % nq;
-        const int nt = min(p.q_lens[q], p.max_terms);
-        if (tid < nt) {
-            int st = 0, ln = 0;
-            double idf = 0.0;
-            const int t = p.q_terms[(int64_t)q * p.max_terms + tid];
-            if (t >= 0 && t < p.ix.vocab) {
-                idf = p.ix.d_idf[t];
-                if (idf != 0.0) {
-                    st = toff[t];
-                    ln = toff[t + 1] - st;
-                } else {
-                    idf = 0.0;
-                }
-            }
-            s_start[buf][tid] = st;
-            s_len[buf][tid] = ln;
-            s_idf[buf][tid] = idf;
-        }
-        if (tid == 0) s_nt[buf] = nt;
-    };
-    auto layout_stage = [&](int buf) {  // thread 0 only, after fetch_runs is visible
-        int off = 0;
-        const int nt = s_nt[buf];
-        for (int i = 0; i < nt; ++i) {
-            const int take = min(s_len[buf][i], kStageCap - off);
-            s_soff[buf][i] = off;
-            s_slen[buf][i] = take;
-            off += take;
-        }
-    };
-    auto issue_stage = [&](const uint32_t *tile_post, int buf, int sbuf) {
-        const int nt = s_nt[buf];
-        uint32_t *dst = stage + sbuf * kStageCap;
-        for (int i = 0; i < nt; ++i) {
-            const int n = s_slen[buf][i];
-            const uint32_t *src = tile_post + s_start[buf][i];
-            uint32_t *d = dst + s_soff[buf][i];
-            for (int j = tid; j < n; j += kThreads) cp_async4(d + j, src + j);
-        }
-        cp_async_commit();
-    };
-
-    for (int tile = blockIdx.x; tile < p.ix.n_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x * kWarps + wib; tile < p.ix.n_tiles; tile += warps_total) {
         const int64_t base_doc = (int64_t)tile * T;
         const int nd = (int)min((int64_t)T, p.ix.n_docs - base_doc);
-        __syncthreads();
-        for (int i = tid; i < T; i += kThreads) {
+        for (int i = lane; i < T; i += 32) {
             acc[i] = 0.0;
             dls[i] = i < nd ? (uint16_t)p.ix.d_doc_len[base_doc + i] : (uint16_t)0;
         }
         const uint32_t *tile_post = p.ix.d_postings + p.ix.d_tile_base[tile];
         const int32_t *toff = p.ix.d_tile_term_off + (int64_t)tile * V1;
-        // stagger the query order across CTAs so a query's threshold is established by few CTAs
-        const int q_shift = (int)(((int64_t)blockIdx.x * 7919) % nq);
+        // stagger the query order across tiles so a query's threshold is established by few warps
+        const int q_shift = (int)(((int64_t)tile * 7919) % nq);
+        __syncwarp();
 
-        // prologue: descriptors of queries 0, 1; postings of query 0
-        fetch_runs(toff, 0, q_shift, 0);
-        if (nq > 1) fetch_runs(toff, 1, q_shift, 1);
-        __syncthreads();
-        if (tid == 0) {
-            layout_stage(0);
-            if (nq > 1) layout_stage(1);
-        }
-        __syncthreads();
-        issue_stage(tile_post, 0, 0);
-        cp_async_wait_all();
-        __syncthreads();
-
-        for (int qi = 0; qi < nq; ++qi) {
-            const int buf = qi % 3;
+        auto load_term = [&](int qi) -> int {  // lane i: canonical id of term i of query slot qi (-1 = none)
+            if (qi >= nq) return -1;
             const int q = (qi + q_shift) % nq;
-            const uint32_t *sp = stage + (qi & 1) * kStageCap;
-            // ---- prefetch: postings of query qi+1 (async), descriptors of query qi+2
-            if (qi + 1 < nq) issue_stage(tile_post, (qi + 1) % 3, (qi + 1) & 1);
-            if (qi + 2 < nq) fetch_runs(toff, qi + 2, q_shift, (qi + 2) % 3);
-            // ---- accumulate query qi, one term at a time (query order per doc)
-            const int nt = s_nt[buf];
-            bool touched = false;
-            for (int i = 0; i < nt; ++i) {
-                const int ln = s_len[buf][i];
-                if (ln == 0) continue;  // OOV, zero idf, or no posting in this tile (uniform)
-                touched = true;
-                const double idf = s_idf[buf][i];
-                const int sl = s_slen[buf][i];
-                const uint32_t *ss = sp + s_soff[buf][i];
-                for (int j = tid; j < sl; j += kThreads) {
-                    const uint32_t post = ss[j];
-                    const uint32_t d = post >> 16;
-                    acc[d] = __dadd_rn(acc[d], contribution(p, post, dls[d], idf));
-                }
-                const uint32_t *pp = tile_post + s_start[buf][i];
-                for (int j = sl + tid; j < ln; j += kThreads) {  // part of a long run that was not staged
-                    const uint32_t post = __ldg(pp + j);
-                    const uint32_t d = post >> 16;
-                    acc[d] = __dadd_rn(acc[d], contribution(p, post, dls[d], idf));
-                }
-                __syncthreads();  // term i fully applied before term i+1
+            const int nt = min(__ldg(p.q_lens + q), mt);
+            int t = -1;
+            if (lane < nt) {
+                t = __ldg(p.q_terms + (int64_t)q * mt + lane);
+                if (t < 0 || t >= p.ix.vocab) t = -1;
             }
+            return t;
+        };
+        auto load_run = [&](int t) -> LaneRun {
+            LaneRun r;
+            r.start = 0; r.len = 0; r.idf = 0.0;
+            if (t >= 0) {
+                r.idf = __ldg(p.ix.d_idf + t);
+                r.start = __ldg(toff + t);
+                r.len = __ldg(toff + t + 1) - r.start;
+                if (r.idf == 0.0) r.len = 0;  // `idf.get(q) or 0`: contributes nothing
+            }
+            return r;
+        };
+
+        int t1 = load_term(1);
+        LaneRun cur = load_run(load_term(0));
+        for (int qi = 0; qi < nq; ++qi) {
+            const int q = (qi + q_shift) % nq;
+            // ---- prefetch (registers only; consumed next iteration)
+            const int t2 = load_term(qi + 2);
+            const LaneRun nxt = load_run(t1);
+            double thr = 0.0;
+            if (!kDense) thr = __longlong_as_double((long long)__ldcg(p.thr_bits + q));
+
+            // queries longer than 32 terms: extra chunks are fetched synchronously (rare)
+            const int nt_all = min(__ldg(p.q_lens + q), mt);
+            int total = 0;
+            bool overflow = false;
+            for (int c0 = 0; c0 < nt_all; c0 += 32) {
+                LaneRun run = cur;
+                if (c0 > 0) {
+                    int t = -1;
+                    if (c0 + lane < nt_all) {
+                        t = __ldg(p.q_terms + (int64_t)q * mt + c0 + lane);
+                        if (t < 0 || t >= p.ix.vocab) t = -1;
+                    }
+                    run = load_run(t);
+                }
+                unsigned active = __ballot_sync(0xffffffffu, run.len > 0);
+                while (active) {
+                    const int i = __ffs(active) - 1;  // ascending lane == query order
+                    active &= active - 1;
+                    const int st = __shfl_sync(0xffffffffu, run.start, i);
+                    const int ln = __shfl_sync(0xffffffffu, run.len, i);
+                    const double idf = __shfl_sync(0xffffffffu, run.idf, i);
+                    const uint32_t *pp = tile_post + st;
+                    for (int j = lane; j < ln; j += 32) {
+                        const uint32_t post = __ldg(pp + j);
+                        const uint32_t d = post >> 16;
+                        acc[d] = __dadd_rn(acc[d], contribution(p, post, dls[d], idf));
+                        if (total + j < kStash) stash[total + j] = (uint16_t)d;
+                    }
+                    total += ln;
+                    __syncwarp();  // run i fully applied before run i+1
+                }
+            }
+            overflow = total > kStash;
+
             // ---- drain: every touched doc is reported once with its final score; accumulator reset
-            if (touched) {
-                double thr = 0.0;
-                if (!kDense) thr = __longlong_as_double((long long)__ldcg(p.thr_bits + q));
-                for (int i = 0; i < nt; ++i) {
-                    const int ln = s_len[buf][i];
-                    if (ln == 0) continue;
-                    const int sl = s_slen[buf][i];
-                    const uint32_t *ss = sp + s_soff[buf][i];
-                    const uint32_t *pp = tile_post + s_start[buf][i];
-                    for (int j = tid; j < ln; j += kThreads) {
-                        const uint32_t d = (j < sl ? ss[j] : __ldg(pp + j)) >> 16;
-                        if (kDense) {
-                            const unsigned long long bits = atomicExch((unsigned long long *)(acc + d), 0ull);
-                            const double v = __longlong_as_double((long long)bits);
-                            if (v != 0.0) p.dense_out[(int64_t)q * p.ix.n_docs + base_doc + d] = v;
-                        } else {
-                            const double v = acc[d];
-                            if (v == 0.0) continue;       // untouched-by-now or already drained by another run
-                            if (v < thr) {
-                                acc[d] = 0.0;             // idempotent: a racing drainer stores the same zero
-                            } else {
-                                const unsigned long long bits = atomicExch((unsigned long long *)(acc + d), 0ull);
-                                const double w = __longlong_as_double((long long)bits);
-                                if (w != 0.0) emit(p, q, (int32_t)(base_doc + d), w);
+            auto drain_doc = [&](uint32_t d) {
+                if (kDense) {
+                    const double v = acc[d];
+                    if (v != 0.0) {
+                        acc[d] = 0.0;
+                        p.dense_out[(int64_t)q * p.ix.n_docs + base_doc + d] = v;
+                    }
+                } else {
+                    const double v = acc[d];
+                    if (v == 0.0) return;  // already drained through another run of this query
+                    if (v < thr) {
+                        acc[d] = 0.0;      // idempotent: a racing lane stores the same zero
+                    } else {
+                        const unsigned long long bits = atomicExch((unsigned long long *)(acc + d), 0ull);
+                        const double w = __longlong_as_double((long long)bits);
+                        if (w != 0.0) emit(p, q, (int32_t)(base_doc + d), w);
+                    }
+                }
+            };
+            if (total > 0) {
+                const int n_st = min(total, kStash);
+                for (int j = lane; j < n_st; j += 32) drain_doc(stash[j]);
+                if (overflow) {  // long runs: walk the runs again for the part that did not fit the stash
+                    int seen = 0;
+                    for (int c0 = 0; c0 < nt_all; c0 += 32) {
+                        LaneRun run = cur;
+                        if (c0 > 0) {
+                            int t = -1;
+                            if (c0 + lane < nt_all) {
+                                t = __ldg(p.q_terms + (int64_t)q * mt + c0 + lane);
+                                if (t < 0 || t >= p.ix.vocab) t = -1;
                             }
+                            run = load_run(t);
+                        }
+                        unsigned active = __ballot_sync(0xffffffffu, run.len > 0);
+                        while (active) {
+                            const int i = __ffs(active) - 1;
+                            active &= active - 1;
+                            const int st = __shfl_sync(0xffffffffu, run.start, i);
+                            const int ln = __shfl_sync(0xffffffffu, run.len, i);
+                            const uint32_t *pp = tile_post + st;
+                            for (int j = lane; j < ln; j += 32)
+                                if (seen + j >= kStash) drain_doc(__ldg(pp + j) >> 16);
+                            seen += ln;
                         }
                     }
                 }
+                __syncwarp();
             }
-            // ---- rotate
-            cp_async_wait_all();  // this thread's copies for query qi+1 have landed
-            __syncthreads();      // ... and everyone's; drain of qi done; descriptors of qi+2 visible
-            if (qi + 2 < nq && tid == 0) layout_stage((qi + 2) % 3);
-            // (the layout is consumed by issue_stage in iteration qi+1, after the barrier that ends it --
-            //  but issue_stage runs at the START of iteration qi+1, so publish it with one more barrier)
-            __syncthreads();
+            cur = nxt;
+            t1 = t2;
         }
     }
 }
@@ -410,7 +404,7 @@ static int validate_index(const orag_bm25_index_t *ix)
     ORAG_REQUIRE(ix->tile_docs >= 32 && ix->tile_docs <= 65536 && (ix->tile_docs & (ix->tile_docs - 1)) == 0,
                  "tile_docs must be a power of two in [32, 65536]");
     ORAG_REQUIRE((int64_t)ix->n_tiles == (ix->n_docs + ix->tile_docs - 1) / ix->tile_docs, "n_tiles");
-    ORAG_REQUIRE(ix->tile_docs * 10 + 16384 <= 200 * 1024, "tile_docs too large for shared memory");
+    ORAG_REQUIRE(ix->tile_docs <= 2048, "tile_docs must be <= 2048 (per-warp accumulators in shared memory)");
     ORAG_REQUIRE(ix->n_docs == 0 || ix->d_r_table, "r table");
     if (ix->n_docs > 0)
         ORAG_REQUIRE(ix->d_tile_base && ix->d_tile_term_off && ix->d_postings && ix->d_doc_len && ix->d_t4_table &&
@@ -466,11 +460,11 @@ extern "C" size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *ix, int n_q
 
 static int launch_tiles(const Params &p, bool dense, cudaStream_t st)
 {
-    const size_t smem = (size_t)p.ix.tile_docs * 10 + 2 * orag::bm25::kStageCap * 4;
-    int grid = p.ix.n_tiles;
-    int per_sm = (int)((200 * 1024) / (smem + 2048));
+    const size_t smem = (size_t)orag::bm25::kWarps * ((size_t)p.ix.tile_docs * 10 + orag::bm25::kStash * 2);
+    int grid = (p.ix.n_tiles + orag::bm25::kWarps - 1) / orag::bm25::kWarps;
+    int per_sm = (int)((224 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 12) per_sm = 12;
+    if (per_sm > 8) per_sm = 8;
     int lim = orag::sm_count() * per_sm;
     if (grid > lim) grid = lim;
     if (grid < 1) return ORAG_OK;

@@ -172,9 +172,9 @@ def test_bm25_golden_bit_exact(eng, golden):
 
 @pytest.mark.parametrize("force", ["sparse", "dense"])
 @pytest.mark.parametrize("n,vocab,lmin,lmax,nq,min_rank,tile", [
-    (20000, 5000, 20, 120, 64, 20, 4096),
+    (20000, 5000, 20, 120, 64, 20, 2048),
     (3000, 300, 5, 60, 40, 3, 256),
-    (70000, 50000, 100, 300, 32, 100, 4096),
+    (70000, 50000, 100, 300, 32, 100, 1024),
 ])
 def test_bm25_topk_vs_oracle(eng, force, n, vocab, lmin, lmax, nq, min_rank, tile):
     ix, orc, qtok, qlen = _bm25_case(n, vocab, lmin, lmax, nq, min_rank, tile, eng)
