@@ -122,13 +122,30 @@ struct LaneRun {  // lane i holds the run of query term i inside the warp's tile
     double idf;
 };
 
+constexpr int kPre = 12;                    // 32-posting slots of a query fetched ahead into registers
+constexpr uint32_t kNoPost = 0xFFFFFFFFu;   // (doc_in_tile <= 2047, so no real posting has this value)
+
+struct Staged {  // postings of one query, in flight or ready, plus what is needed to consume them
+    uint32_t post[kPre];
+    unsigned long long srun;  // 5 bits per slot: which lane holds the slot's run descriptor
+    int nslot;                // slots in use
+    int rest_run, rest_off;   // where on-demand loading resumes when the query needs more than kPre slots
+    LaneRun run;
+    int q;                    // query index
+    int nt_all;               // query length
+};
+
 // Every warp owns one tile (a doc range of tile_docs docs, accumulators in its slice of shared
 // memory) and walks the whole query batch on its own: no CTA barrier anywhere in the loop.
 //   lanes <-> query terms   while fetching run descriptors (term id -> idf, run offsets)
 //   lanes <-> postings      while accumulating / draining a run (coalesced 4-byte reads)
-// Software pipeline per warp: term ids of query i+2 and run descriptors of query i+1 are in
-// flight while query i is processed.  Terms are applied in query order (ascending lane), each
-// run fully before the next (__syncwarp), so per-document sums follow the reference's order.
+// Four-stage software pipeline per warp, all state in registers:
+//   iteration i issues   term ids of query i+3, run descriptors of query i+2, postings of query i+1
+//   and consumes         the postings of query i (issued one iteration earlier)
+// so every load issued in an iteration is independent of everything the iteration consumes, and a
+// warp keeps up to kPre*32 posting reads + descriptors in flight instead of one dependent DRAM
+// round trip per 32 postings.  Terms are applied in query order (ascending lane), slot by slot with
+// __syncwarp in between, so per-document sums follow the reference's order.
 template <bool kDense>
 __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_constant__ Params p)
 {
@@ -145,6 +162,7 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
     const int nq = p.n_queries;
     const int mt = p.max_terms;
     const int warps_total = gridDim.x * kWarps;
+    const unsigned FULL = 0xffffffffu;
 
     for (int tile = blockIdx.x * kWarps + wib; tile < p.ix.n_tiles; tile += warps_total) {
         const int64_t base_doc = (int64_t)tile * T;
@@ -159,125 +177,183 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
         const int q_shift = (int)(((int64_t)tile * 7919) % nq);
         __syncwarp();
 
-        auto load_term = [&](int qi) -> int {  // lane i: canonical id of term i of query slot qi (-1 = none)
-            if (qi >= nq) return -1;
-            const int q = (qi + q_shift) % nq;
-            const int nt = min(__ldg(p.q_lens + q), mt);
-            int t = -1;
-            if (lane < nt) {
-                t = __ldg(p.q_terms + (int64_t)q * mt + lane);
-                if (t < 0 || t >= p.ix.vocab) t = -1;
+        // ---- stage A: raw term id + query length (two independent loads)
+        auto stage_terms = [&](int qi, int &t, int &nt) {
+            t = -1; nt = 0;
+            if (qi < nq) {
+                const int q = (qi + q_shift) % nq;
+                nt = __ldg(p.q_lens + q);
+                if (lane < mt) t = __ldg(p.q_terms + (int64_t)q * mt + lane);
             }
-            return t;
         };
-        auto load_run = [&](int t) -> LaneRun {
+        // ---- stage B: run descriptor of (validated) term t
+        auto stage_run = [&](int t, int nt) -> LaneRun {
             LaneRun r;
             r.start = 0; r.len = 0; r.idf = 0.0;
-            if (t >= 0) {
+            if (lane < min(nt, mt) && t >= 0 && t < p.ix.vocab) {
                 r.idf = __ldg(p.ix.d_idf + t);
                 r.start = __ldg(toff + t);
-                r.len = __ldg(toff + t + 1) - r.start;
-                if (r.idf == 0.0) r.len = 0;  // `idf.get(q) or 0`: contributes nothing
+                r.len = __ldg(toff + t + 1);  // end offset for now; turned into a length when staged
             }
             return r;
         };
+        // ---- stage C: issue the posting loads of a query (first 32 terms, up to kPre slots)
+        auto stage_posts = [&](LaneRun run, int qi, int nt) -> Staged {
+            Staged s;
+            run.len = (run.idf != 0.0) ? run.len - run.start : 0;  // `idf.get(q) or 0`: zero idf adds nothing
+            s.run = run;
+            s.q = (qi < nq) ? (qi + q_shift) % nq : 0;
+            s.nt_all = min(nt, mt);
+            s.srun = 0ull;
+            s.nslot = 0;
+            unsigned active = __ballot_sync(FULL, run.len > 0);
+            int i = active ? __ffs(active) - 1 : 32;
+            int off = 0;
+#pragma unroll
+            for (int k = 0; k < kPre; ++k) {
+                const int st = __shfl_sync(FULL, run.start, i & 31);
+                const int ln = __shfl_sync(FULL, run.len, i & 31);
+                uint32_t v = kNoPost;
+                if (i < 32 && off + lane < ln) v = __ldg(tile_post + st + off + lane);
+                s.post[k] = v;
+                if (i < 32) {
+                    s.srun |= (unsigned long long)i << (5 * k);
+                    s.nslot = k + 1;
+                    off += 32;
+                    if (off >= ln) {
+                        active &= active - 1;
+                        i = active ? __ffs(active) - 1 : 32;
+                        off = 0;
+                    }
+                }
+            }
+            s.rest_run = i;
+            s.rest_off = off;
+            return s;
+        };
 
-        int t1 = load_term(1);
-        LaneRun cur = load_run(load_term(0));
+        // prologue: fill the pipeline
+        int tA, ntA;
+        stage_terms(0, tA, ntA);
+        Staged cur = stage_posts(stage_run(tA, ntA), 0, ntA);  // query 0: postings in flight
+        stage_terms(1, tA, ntA);
+        LaneRun runB = stage_run(tA, ntA);                     // query 1: descriptors in flight
+        int ntRunB = ntA;
+        stage_terms(2, tA, ntA);                               // query 2: term ids in flight
+
         for (int qi = 0; qi < nq; ++qi) {
-            const int q = (qi + q_shift) % nq;
-            // ---- prefetch (registers only; consumed next iteration)
-            const int t2 = load_term(qi + 2);
-            const LaneRun nxt = load_run(t1);
+            // ---- issue: postings of query qi+1, descriptors of query qi+2, terms of query qi+3
+            Staged nxt = stage_posts(runB, qi + 1, ntRunB);
+            runB = stage_run(tA, ntA);
+            ntRunB = ntA;
+            stage_terms(qi + 3, tA, ntA);
+
+            const int q = cur.q;
             double thr = 0.0;
             if (!kDense) thr = __longlong_as_double((long long)__ldcg(p.thr_bits + q));
 
-            // queries longer than 32 terms: extra chunks are fetched synchronously (rare)
-            const int nt_all = min(__ldg(p.q_lens + q), mt);
+            // ---- consume query qi: staged slots first (registers), then whatever did not fit
             int total = 0;
-            bool overflow = false;
-            for (int c0 = 0; c0 < nt_all; c0 += 32) {
-                LaneRun run = cur;
-                if (c0 > 0) {
-                    int t = -1;
-                    if (c0 + lane < nt_all) {
-                        t = __ldg(p.q_terms + (int64_t)q * mt + c0 + lane);
-                        if (t < 0 || t >= p.ix.vocab) t = -1;
+#pragma unroll
+            for (int k = 0; k < kPre; ++k) {
+                if (k < cur.nslot) {
+                    const int i = (int)((cur.srun >> (5 * k)) & 31ull);
+                    const double idf = __shfl_sync(FULL, cur.run.idf, i);
+                    const uint32_t post = cur.post[k];
+                    if (post != kNoPost) {
+                        const uint32_t d = post >> 16;
+                        acc[d] = __dadd_rn(acc[d], contribution(p, post, dls[d], idf));
+                        if (total + lane < kStash) stash[total + lane] = (uint16_t)d;
                     }
-                    run = load_run(t);
+                    total += __popc(__ballot_sync(FULL, post != kNoPost));  // valid lanes form a prefix
+                    __syncwarp();
                 }
-                unsigned active = __ballot_sync(0xffffffffu, run.len > 0);
-                while (active) {
-                    const int i = __ffs(active) - 1;  // ascending lane == query order
-                    active &= active - 1;
-                    const int st = __shfl_sync(0xffffffffu, run.start, i);
-                    const int ln = __shfl_sync(0xffffffffu, run.len, i);
-                    const double idf = __shfl_sync(0xffffffffu, run.idf, i);
-                    const uint32_t *pp = tile_post + st;
-                    for (int j = lane; j < ln; j += 32) {
+            }
+            // on-demand continuation (long runs / many terms): same order, loads issued as needed
+            auto walk_rest = [&](auto &&body) {
+                // remaining part of the first 32 terms
+                if (cur.rest_run < 32) {
+                    unsigned active = __ballot_sync(FULL, cur.run.len > 0) & (0xffffffffu << cur.rest_run);
+                    int off0 = cur.rest_off;
+                    while (active) {
+                        const int i = __ffs(active) - 1;
+                        active &= active - 1;
+                        const int st = __shfl_sync(FULL, cur.run.start, i);
+                        const int ln = __shfl_sync(FULL, cur.run.len, i);
+                        const double idf = __shfl_sync(FULL, cur.run.idf, i);
+                        body(tile_post + st, off0, ln, idf);
+                        off0 = 0;
+                    }
+                }
+                // terms 32.. of very long queries
+                for (int c0 = 32; c0 < cur.nt_all; c0 += 32) {
+                    LaneRun run;
+                    run.start = 0; run.len = 0; run.idf = 0.0;
+                    if (c0 + lane < cur.nt_all) {
+                        const int t = __ldg(p.q_terms + (int64_t)q * mt + c0 + lane);
+                        if (t >= 0 && t < p.ix.vocab) {
+                            run.idf = __ldg(p.ix.d_idf + t);
+                            run.start = __ldg(toff + t);
+                            run.len = (run.idf != 0.0) ? __ldg(toff + t + 1) - run.start : 0;
+                        }
+                    }
+                    unsigned active = __ballot_sync(FULL, run.len > 0);
+                    while (active) {
+                        const int i = __ffs(active) - 1;
+                        active &= active - 1;
+                        const int st = __shfl_sync(FULL, run.start, i);
+                        const int ln = __shfl_sync(FULL, run.len, i);
+                        const double idf = __shfl_sync(FULL, run.idf, i);
+                        body(tile_post + st, 0, ln, idf);
+                    }
+                }
+            };
+            const bool has_rest = cur.rest_run < 32 || cur.nt_all > 32;
+            if (has_rest) {
+                walk_rest([&](const uint32_t *pp, int off0, int ln, double idf) {
+                    for (int j = off0 + lane; j < ln; j += 32) {
                         const uint32_t post = __ldg(pp + j);
                         const uint32_t d = post >> 16;
                         acc[d] = __dadd_rn(acc[d], contribution(p, post, dls[d], idf));
-                        if (total + j < kStash) stash[total + j] = (uint16_t)d;
+                        const int slot = total + (j - off0);
+                        if (slot < kStash) stash[slot] = (uint16_t)d;
                     }
-                    total += ln;
-                    __syncwarp();  // run i fully applied before run i+1
-                }
+                    total += ln - off0;
+                    __syncwarp();
+                });
             }
-            overflow = total > kStash;
 
             // ---- drain: every touched doc is reported once with its final score; accumulator reset
             auto drain_doc = [&](uint32_t d) {
+                const double v = acc[d];
+                if (v == 0.0) return;  // already drained through another run of this query
                 if (kDense) {
-                    const double v = acc[d];
-                    if (v != 0.0) {
-                        acc[d] = 0.0;
-                        p.dense_out[(int64_t)q * p.ix.n_docs + base_doc + d] = v;
-                    }
+                    acc[d] = 0.0;      // idempotent: racing lanes store the same values
+                    p.dense_out[(int64_t)q * p.ix.n_docs + base_doc + d] = v;
+                } else if (v < thr) {
+                    acc[d] = 0.0;
                 } else {
-                    const double v = acc[d];
-                    if (v == 0.0) return;  // already drained through another run of this query
-                    if (v < thr) {
-                        acc[d] = 0.0;      // idempotent: a racing lane stores the same zero
-                    } else {
-                        const unsigned long long bits = atomicExch((unsigned long long *)(acc + d), 0ull);
-                        const double w = __longlong_as_double((long long)bits);
-                        if (w != 0.0) emit(p, q, (int32_t)(base_doc + d), w);
-                    }
+                    const unsigned long long bits = atomicExch((unsigned long long *)(acc + d), 0ull);
+                    const double w = __longlong_as_double((long long)bits);
+                    if (w != 0.0) emit(p, q, (int32_t)(base_doc + d), w);
                 }
             };
             if (total > 0) {
                 const int n_st = min(total, kStash);
                 for (int j = lane; j < n_st; j += 32) drain_doc(stash[j]);
-                if (overflow) {  // long runs: walk the runs again for the part that did not fit the stash
-                    int seen = 0;
-                    for (int c0 = 0; c0 < nt_all; c0 += 32) {
-                        LaneRun run = cur;
-                        if (c0 > 0) {
-                            int t = -1;
-                            if (c0 + lane < nt_all) {
-                                t = __ldg(p.q_terms + (int64_t)q * mt + c0 + lane);
-                                if (t < 0 || t >= p.ix.vocab) t = -1;
-                            }
-                            run = load_run(t);
-                        }
-                        unsigned active = __ballot_sync(0xffffffffu, run.len > 0);
-                        while (active) {
-                            const int i = __ffs(active) - 1;
-                            active &= active - 1;
-                            const int st = __shfl_sync(0xffffffffu, run.start, i);
-                            const int ln = __shfl_sync(0xffffffffu, run.len, i);
-                            const uint32_t *pp = tile_post + st;
-                            for (int j = lane; j < ln; j += 32)
-                                if (seen + j >= kStash) drain_doc(__ldg(pp + j) >> 16);
-                            seen += ln;
-                        }
-                    }
+                if (total > kStash) {
+                    // the stash overflowed: walk every run of the query again and drain straight from the
+                    // posting lists (draining is idempotent, so re-visiting stashed docs is harmless)
+#pragma unroll
+                    for (int k = 0; k < kPre; ++k)
+                        if (k < cur.nslot && cur.post[k] != kNoPost) drain_doc(cur.post[k] >> 16);
+                    walk_rest([&](const uint32_t *pp, int off0, int ln, double) {
+                        for (int j = off0 + lane; j < ln; j += 32) drain_doc(__ldg(pp + j) >> 16);
+                    });
                 }
                 __syncwarp();
             }
             cur = nxt;
-            t1 = t2;
         }
     }
 }
