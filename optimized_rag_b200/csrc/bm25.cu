@@ -101,14 +101,17 @@ __device__ __noinline__ void emit(const Params &p, int q, int32_t doc, double v)
 
 constexpr int kRTf = 4;      // r = tf*(k1+1)/(tf + t4[dl]) is tabulated for tf = 1..kRTf
 constexpr int kStash = 1024; // doc ids touched by the current query, per warp (drain list)
+constexpr int kRCacheDl = 384; // document lengths whose r-table rows are cached in shared memory
 
 // contribution of one posting, in the reference's operation order (see file header)
-__device__ __forceinline__ double contribution(const Params &p, uint32_t post, uint32_t dl, double idf)
+__device__ __forceinline__ double contribution(const Params &p, const double *r_s, int rc, uint32_t post, uint32_t dl,
+                                               double idf)
 {
     const uint32_t tf = post & 0xFFFFu;
     double r;
     if (tf <= (uint32_t)kRTf) {
-        r = __ldg(p.ix.d_r_table + dl * kRTf + (tf - 1));  // same IEEE ops, evaluated once at index build
+        // same IEEE ops as the slow branch, evaluated once at index build (bm25_index.py r_table)
+        r = (int)dl < rc ? r_s[dl * kRTf + (tf - 1)] : __ldg(p.ix.d_r_table + dl * kRTf + (tf - 1));
     } else {
         const double f = (double)tf;
         r = __ddiv_rn(__dmul_rn(f, 2.5), __dadd_rn(f, __ldg(p.ix.d_t4_table + dl)));
@@ -153,7 +156,12 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
     const int T = p.ix.tile_docs;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const size_t per_warp = (size_t)T * 10 + kStash * 2;  // bytes (multiple of 8)
-    uint8_t *mine = reinterpret_cast<uint8_t *>(smem_d) + wib * per_warp;
+    // CTA-shared cache of the first rows of the r table (read-only after this point)
+    double *r_s = smem_d;
+    const int rc = min(p.ix.max_doc_len + 1, kRCacheDl);
+    for (int i = threadIdx.x; i < rc * kRTf; i += kThreads) r_s[i] = p.ix.d_r_table[i];
+    __syncthreads();
+    uint8_t *mine = reinterpret_cast<uint8_t *>(smem_d + kRCacheDl * kRTf) + wib * per_warp;
     double *acc = reinterpret_cast<double *>(mine);                    // [T]
     uint16_t *dls = reinterpret_cast<uint16_t *>(mine + (size_t)T * 8);  // [T] document lengths
     uint16_t *stash = dls + T;                                         // [kStash]
@@ -255,18 +263,32 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
             // ---- consume query qi: staged slots first (registers), then whatever did not fit
             int total = 0;
 #pragma unroll
-            for (int k = 0; k < kPre; ++k) {
-                if (k < cur.nslot) {
-                    const int i = (int)((cur.srun >> (5 * k)) & 31ull);
-                    const double idf = __shfl_sync(FULL, cur.run.idf, i);
-                    const uint32_t post = cur.post[k];
-                    if (post != kNoPost) {
-                        const uint32_t d = post >> 16;
-                        acc[d] = __dadd_rn(acc[d], contribution(p, post, dls[d], idf));
-                        if (total + lane < kStash) stash[total + lane] = (uint16_t)d;
+            for (int g = 0; g < kPre; g += 4) {
+                if (g < cur.nslot) {
+                    // contributions of four slots first (independent table lookups overlap) ...
+                    double c[4];
+#pragma unroll
+                    for (int k = g; k < g + 4; ++k) {
+                        const int i = (int)((cur.srun >> (5 * k)) & 31ull);
+                        const double idf = __shfl_sync(FULL, cur.run.idf, i);
+                        const uint32_t post = cur.post[k];
+                        c[k - g] = (k < cur.nslot && post != kNoPost)
+                                       ? contribution(p, r_s, rc, post, dls[post >> 16], idf) : 0.0;
                     }
-                    total += __popc(__ballot_sync(FULL, post != kNoPost));  // valid lanes form a prefix
-                    __syncwarp();
+                    // ... then the accumulator updates strictly slot by slot
+#pragma unroll
+                    for (int k = g; k < g + 4; ++k) {
+                        if (k < cur.nslot) {
+                            const uint32_t post = cur.post[k];
+                            if (post != kNoPost) {
+                                const uint32_t d = post >> 16;
+                                acc[d] = __dadd_rn(acc[d], c[k - g]);
+                                if (total + lane < kStash) stash[total + lane] = (uint16_t)d;
+                            }
+                            total += __popc(__ballot_sync(FULL, post != kNoPost));  // valid lanes form a prefix
+                            __syncwarp();
+                        }
+                    }
                 }
             }
             // on-demand continuation (long runs / many terms): same order, loads issued as needed
@@ -314,7 +336,7 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
                     for (int j = off0 + lane; j < ln; j += 32) {
                         const uint32_t post = __ldg(pp + j);
                         const uint32_t d = post >> 16;
-                        acc[d] = __dadd_rn(acc[d], contribution(p, post, dls[d], idf));
+                        acc[d] = __dadd_rn(acc[d], contribution(p, r_s, rc, post, dls[d], idf));
                         const int slot = total + (j - off0);
                         if (slot < kStash) stash[slot] = (uint16_t)d;
                     }
@@ -340,6 +362,7 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
             };
             if (total > 0) {
                 const int n_st = min(total, kStash);
+#pragma unroll 4
                 for (int j = lane; j < n_st; j += 32) drain_doc(stash[j]);
                 if (total > kStash) {
                     // the stash overflowed: walk every run of the query again and drain straight from the
@@ -536,7 +559,8 @@ extern "C" size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *ix, int n_q
 
 static int launch_tiles(const Params &p, bool dense, cudaStream_t st)
 {
-    const size_t smem = (size_t)orag::bm25::kWarps * ((size_t)p.ix.tile_docs * 10 + orag::bm25::kStash * 2);
+    const size_t smem = (size_t)orag::bm25::kWarps * ((size_t)p.ix.tile_docs * 10 + orag::bm25::kStash * 2) +
+                        (size_t)orag::bm25::kRCacheDl * orag::bm25::kRTf * 8;
     int grid = (p.ix.n_tiles + orag::bm25::kWarps - 1) / orag::bm25::kWarps;
     int per_sm = (int)((224 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
