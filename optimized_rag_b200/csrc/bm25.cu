@@ -100,7 +100,6 @@ __device__ __noinline__ void emit(const Params &p, int q, int32_t doc, double v)
 }
 
 constexpr int kRTf = 4;      // r = tf*(k1+1)/(tf + t4[dl]) is tabulated for tf = 1..kRTf
-constexpr int kStash = 1024; // doc ids touched by the current query, per warp (drain list)
 constexpr int kRCacheDl = 384; // document lengths whose r-table rows are cached in shared memory
 
 // contribution of one posting, in the reference's operation order (see file header)
@@ -125,46 +124,52 @@ struct LaneRun {  // lane i holds the run of query term i inside the warp's tile
     double idf;
 };
 
-constexpr int kPre = 12;                    // 32-posting slots of a query fetched ahead into registers
-constexpr uint32_t kNoPost = 0xFFFFFFFFu;   // (doc_in_tile <= 2047, so no real posting has this value)
+constexpr int kStage = 256;  // postings of one query staged per buffer (two buffers per warp)
 
-struct Staged {  // postings of one query, in flight or ready, plus what is needed to consume them
-    uint32_t post[kPre];
-    unsigned long long srun;  // 5 bits per slot: which lane holds the slot's run descriptor
-    int nslot;                // slots in use
-    int rest_run, rest_off;   // where on-demand loading resumes when the query needs more than kPre slots
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+struct Staged {   // one query's runs (lane i = term i) and where their staged parts sit in the buffer
     LaneRun run;
-    int q;                    // query index
-    int nt_all;               // query length
+    int soff;     // offset of the run's staged part in the staging buffer
+    int slen;     // staged length (<= run.len); the rest is read on demand
+    int q;        // query index
+    int nt_all;   // query length
 };
 
 // Every warp owns one tile (a doc range of tile_docs docs, accumulators in its slice of shared
 // memory) and walks the whole query batch on its own: no CTA barrier anywhere in the loop.
 //   lanes <-> query terms   while fetching run descriptors (term id -> idf, run offsets)
-//   lanes <-> postings      while accumulating / draining a run (coalesced 4-byte reads)
-// Four-stage software pipeline per warp, all state in registers:
-//   iteration i issues   term ids of query i+3, run descriptors of query i+2, postings of query i+1
-//   and consumes         the postings of query i (issued one iteration earlier)
-// so every load issued in an iteration is independent of everything the iteration consumes, and a
-// warp keeps up to kPre*32 posting reads + descriptors in flight instead of one dependent DRAM
-// round trip per 32 postings.  Terms are applied in query order (ascending lane), slot by slot with
-// __syncwarp in between, so per-document sums follow the reference's order.
+//   lanes <-> postings      while staging / accumulating / draining a run (coalesced 4-byte reads)
+// Four-stage software pipeline per warp:
+//   iteration i issues   term ids of query i+3 (registers), run descriptors of query i+2
+//                        (registers), cp.async of the posting runs of query i+1 (shared memory)
+//   and consumes         the staged postings of query i
+// so every load issued in an iteration is independent of everything the iteration consumes.
+// Terms are applied in query order (ascending lane), run by run with __syncwarp in between, so
+// per-document sums follow the reference's order.  The staged postings double as the drain list.
 template <bool kDense>
-__global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_constant__ Params p)
+__global__ void __launch_bounds__(kThreads, 2) bm25_tile_kernel(const __grid_constant__ Params p)
 {
     extern __shared__ double smem_d[];
     const int T = p.ix.tile_docs;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)T * 10 + kStash * 2;  // bytes (multiple of 8)
+    const size_t per_warp = (size_t)T * 10 + 2 * kStage * 4;  // bytes (multiple of 8)
     // CTA-shared cache of the first rows of the r table (read-only after this point)
     double *r_s = smem_d;
     const int rc = min(p.ix.max_doc_len + 1, kRCacheDl);
     for (int i = threadIdx.x; i < rc * kRTf; i += kThreads) r_s[i] = p.ix.d_r_table[i];
     __syncthreads();
     uint8_t *mine = reinterpret_cast<uint8_t *>(smem_d + kRCacheDl * kRTf) + wib * per_warp;
-    double *acc = reinterpret_cast<double *>(mine);                    // [T]
-    uint16_t *dls = reinterpret_cast<uint16_t *>(mine + (size_t)T * 8);  // [T] document lengths
-    uint16_t *stash = dls + T;                                         // [kStash]
+    double *acc = reinterpret_cast<double *>(mine);                         // [T]
+    uint32_t *stage = reinterpret_cast<uint32_t *>(mine + (size_t)T * 8);   // [2][kStage]
+    uint16_t *dls = reinterpret_cast<uint16_t *>(stage + 2 * kStage);       // [T] document lengths
 
     const int V1 = p.ix.vocab + 1;
     const int nq = p.n_queries;
@@ -194,49 +199,43 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
                 if (lane < mt) t = __ldg(p.q_terms + (int64_t)q * mt + lane);
             }
         };
-        // ---- stage B: run descriptor of (validated) term t
+        // ---- stage B: run descriptor of (validated) term t; len holds the END offset until staged
         auto stage_run = [&](int t, int nt) -> LaneRun {
             LaneRun r;
             r.start = 0; r.len = 0; r.idf = 0.0;
             if (lane < min(nt, mt) && t >= 0 && t < p.ix.vocab) {
                 r.idf = __ldg(p.ix.d_idf + t);
                 r.start = __ldg(toff + t);
-                r.len = __ldg(toff + t + 1);  // end offset for now; turned into a length when staged
+                r.len = __ldg(toff + t + 1);
             }
             return r;
         };
-        // ---- stage C: issue the posting loads of a query (first 32 terms, up to kPre slots)
+        // ---- stage C: lay the runs out in the staging buffer and issue their copies
         auto stage_posts = [&](LaneRun run, int qi, int nt) -> Staged {
             Staged s;
             run.len = (run.idf != 0.0) ? run.len - run.start : 0;  // `idf.get(q) or 0`: zero idf adds nothing
             s.run = run;
             s.q = (qi < nq) ? (qi + q_shift) % nq : 0;
             s.nt_all = min(nt, mt);
-            s.srun = 0ull;
-            s.nslot = 0;
-            unsigned active = __ballot_sync(FULL, run.len > 0);
-            int i = active ? __ffs(active) - 1 : 32;
-            int off = 0;
+            int incl = run.len;
 #pragma unroll
-            for (int k = 0; k < kPre; ++k) {
-                const int st = __shfl_sync(FULL, run.start, i & 31);
-                const int ln = __shfl_sync(FULL, run.len, i & 31);
-                uint32_t v = kNoPost;
-                if (i < 32 && off + lane < ln) v = __ldg(tile_post + st + off + lane);
-                s.post[k] = v;
-                if (i < 32) {
-                    s.srun |= (unsigned long long)i << (5 * k);
-                    s.nslot = k + 1;
-                    off += 32;
-                    if (off >= ln) {
-                        active &= active - 1;
-                        i = active ? __ffs(active) - 1 : 32;
-                        off = 0;
-                    }
-                }
+            for (int d = 1; d < 32; d <<= 1) {
+                const int n = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += n;
             }
-            s.rest_run = i;
-            s.rest_off = off;
+            s.soff = min(incl - run.len, kStage);
+            s.slen = min(run.len, kStage - s.soff);
+            uint32_t *buf = stage + (qi & 1) * kStage;
+            unsigned active = __ballot_sync(FULL, s.slen > 0);
+            while (active) {
+                const int i = __ffs(active) - 1;
+                active &= active - 1;
+                const int st = __shfl_sync(FULL, run.start, i);
+                const int so = __shfl_sync(FULL, s.soff, i);
+                const int sl = __shfl_sync(FULL, s.slen, i);
+                for (int j = lane; j < sl; j += 32) cp_async4(buf + so + j, tile_post + st + j);
+            }
+            cp_async_commit();
             return s;
         };
 
@@ -251,7 +250,7 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
 
         for (int qi = 0; qi < nq; ++qi) {
             // ---- issue: postings of query qi+1, descriptors of query qi+2, terms of query qi+3
-            Staged nxt = stage_posts(runB, qi + 1, ntRunB);
+            const Staged nxt = stage_posts(runB, qi + 1, ntRunB);
             runB = stage_run(tA, ntA);
             ntRunB = ntA;
             stage_terms(qi + 3, tA, ntA);
@@ -259,93 +258,15 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
             const int q = cur.q;
             double thr = 0.0;
             if (!kDense) thr = __longlong_as_double((long long)__ldcg(p.thr_bits + q));
+            const uint32_t *buf = stage + (qi & 1) * kStage;
+            cp_async_wait_1();  // everything but the copies just issued has landed (this lane's part)
+            __syncwarp();       // ... and every lane's part
 
-            // ---- consume query qi: staged slots first (registers), then whatever did not fit
-            int total = 0;
-#pragma unroll
-            for (int g = 0; g < kPre; g += 4) {
-                if (g < cur.nslot) {
-                    // contributions of four slots first (independent table lookups overlap) ...
-                    double c[4];
-#pragma unroll
-                    for (int k = g; k < g + 4; ++k) {
-                        const int i = (int)((cur.srun >> (5 * k)) & 31ull);
-                        const double idf = __shfl_sync(FULL, cur.run.idf, i);
-                        const uint32_t post = cur.post[k];
-                        c[k - g] = (k < cur.nslot && post != kNoPost)
-                                       ? contribution(p, r_s, rc, post, dls[post >> 16], idf) : 0.0;
-                    }
-                    // ... then the accumulator updates strictly slot by slot
-#pragma unroll
-                    for (int k = g; k < g + 4; ++k) {
-                        if (k < cur.nslot) {
-                            const uint32_t post = cur.post[k];
-                            if (post != kNoPost) {
-                                const uint32_t d = post >> 16;
-                                acc[d] = __dadd_rn(acc[d], c[k - g]);
-                                if (total + lane < kStash) stash[total + lane] = (uint16_t)d;
-                            }
-                            total += __popc(__ballot_sync(FULL, post != kNoPost));  // valid lanes form a prefix
-                            __syncwarp();
-                        }
-                    }
-                }
-            }
-            // on-demand continuation (long runs / many terms): same order, loads issued as needed
-            auto walk_rest = [&](auto &&body) {
-                // remaining part of the first 32 terms
-                if (cur.rest_run < 32) {
-                    unsigned active = __ballot_sync(FULL, cur.run.len > 0) & (0xffffffffu << cur.rest_run);
-                    int off0 = cur.rest_off;
-                    while (active) {
-                        const int i = __ffs(active) - 1;
-                        active &= active - 1;
-                        const int st = __shfl_sync(FULL, cur.run.start, i);
-                        const int ln = __shfl_sync(FULL, cur.run.len, i);
-                        const double idf = __shfl_sync(FULL, cur.run.idf, i);
-                        body(tile_post + st, off0, ln, idf);
-                        off0 = 0;
-                    }
-                }
-                // terms 32.. of very long queries
-                for (int c0 = 32; c0 < cur.nt_all; c0 += 32) {
-                    LaneRun run;
-                    run.start = 0; run.len = 0; run.idf = 0.0;
-                    if (c0 + lane < cur.nt_all) {
-                        const int t = __ldg(p.q_terms + (int64_t)q * mt + c0 + lane);
-                        if (t >= 0 && t < p.ix.vocab) {
-                            run.idf = __ldg(p.ix.d_idf + t);
-                            run.start = __ldg(toff + t);
-                            run.len = (run.idf != 0.0) ? __ldg(toff + t + 1) - run.start : 0;
-                        }
-                    }
-                    unsigned active = __ballot_sync(FULL, run.len > 0);
-                    while (active) {
-                        const int i = __ffs(active) - 1;
-                        active &= active - 1;
-                        const int st = __shfl_sync(FULL, run.start, i);
-                        const int ln = __shfl_sync(FULL, run.len, i);
-                        const double idf = __shfl_sync(FULL, run.idf, i);
-                        body(tile_post + st, 0, ln, idf);
-                    }
-                }
+            // ---- accumulate query qi, run by run in query order
+            auto apply = [&](uint32_t post, double idf) {
+                const uint32_t d = post >> 16;
+                acc[d] = __dadd_rn(acc[d], contribution(p, r_s, rc, post, dls[d], idf));
             };
-            const bool has_rest = cur.rest_run < 32 || cur.nt_all > 32;
-            if (has_rest) {
-                walk_rest([&](const uint32_t *pp, int off0, int ln, double idf) {
-                    for (int j = off0 + lane; j < ln; j += 32) {
-                        const uint32_t post = __ldg(pp + j);
-                        const uint32_t d = post >> 16;
-                        acc[d] = __dadd_rn(acc[d], contribution(p, r_s, rc, post, dls[d], idf));
-                        const int slot = total + (j - off0);
-                        if (slot < kStash) stash[slot] = (uint16_t)d;
-                    }
-                    total += ln - off0;
-                    __syncwarp();
-                });
-            }
-
-            // ---- drain: every touched doc is reported once with its final score; accumulator reset
             auto drain_doc = [&](uint32_t d) {
                 const double v = acc[d];
                 if (v == 0.0) return;  // already drained through another run of this query
@@ -360,20 +281,50 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const __grid_consta
                     if (w != 0.0) emit(p, q, (int32_t)(base_doc + d), w);
                 }
             };
-            if (total > 0) {
-                const int n_st = min(total, kStash);
-#pragma unroll 4
-                for (int j = lane; j < n_st; j += 32) drain_doc(stash[j]);
-                if (total > kStash) {
-                    // the stash overflowed: walk every run of the query again and drain straight from the
-                    // posting lists (draining is idempotent, so re-visiting stashed docs is harmless)
-#pragma unroll
-                    for (int k = 0; k < kPre; ++k)
-                        if (k < cur.nslot && cur.post[k] != kNoPost) drain_doc(cur.post[k] >> 16);
-                    walk_rest([&](const uint32_t *pp, int off0, int ln, double) {
-                        for (int j = off0 + lane; j < ln; j += 32) drain_doc(__ldg(pp + j) >> 16);
-                    });
+            // walks the runs of the first 32 terms; mode 0 = accumulate, 1 = drain the non-staged parts
+            auto walk = [&](const LaneRun &run, int soff, int slen, bool staged_ok, int mode) {
+                unsigned active = __ballot_sync(FULL, run.len > 0);
+                while (active) {
+                    const int i = __ffs(active) - 1;
+                    active &= active - 1;
+                    const int st = __shfl_sync(FULL, run.start, i);
+                    const int ln = __shfl_sync(FULL, run.len, i);
+                    const int so = __shfl_sync(FULL, soff, i);
+                    const int sl = staged_ok ? __shfl_sync(FULL, slen, i) : 0;
+                    if (mode == 0) {
+                        const double idf = __shfl_sync(FULL, run.idf, i);
+                        for (int j = lane; j < sl; j += 32) apply(buf[so + j], idf);
+                        for (int j = sl + lane; j < ln; j += 32) apply(__ldg(tile_post + st + j), idf);
+                        __syncwarp();  // run i fully applied before run i+1
+                    } else {
+                        for (int j = sl + lane; j < ln; j += 32) drain_doc(__ldg(tile_post + st + j) >> 16);
+                    }
                 }
+            };
+            auto long_query_runs = [&](int c0) -> LaneRun {  // terms 32.. of very long queries (rare)
+                LaneRun run;
+                run.start = 0; run.len = 0; run.idf = 0.0;
+                if (c0 + lane < cur.nt_all) {
+                    const int t = __ldg(p.q_terms + (int64_t)q * mt + c0 + lane);
+                    if (t >= 0 && t < p.ix.vocab) {
+                        run.idf = __ldg(p.ix.d_idf + t);
+                        run.start = __ldg(toff + t);
+                        run.len = (run.idf != 0.0) ? __ldg(toff + t + 1) - run.start : 0;
+                    }
+                }
+                return run;
+            };
+            const int staged_total = __shfl_sync(FULL, cur.soff + cur.slen, 31);
+            const bool any = __any_sync(FULL, cur.run.len > 0) || cur.nt_all > 32;
+            if (any) {
+                walk(cur.run, cur.soff, cur.slen, true, 0);
+                for (int c0 = 32; c0 < cur.nt_all; c0 += 32) walk(long_query_runs(c0), 0, 0, false, 0);
+
+                // ---- drain: every touched doc is reported once with its final score; accumulator reset
+#pragma unroll 4
+                for (int j = lane; j < staged_total; j += 32) drain_doc(buf[j] >> 16);
+                if (__any_sync(FULL, cur.run.len > cur.slen)) walk(cur.run, cur.soff, cur.slen, true, 1);
+                for (int c0 = 32; c0 < cur.nt_all; c0 += 32) walk(long_query_runs(c0), 0, 0, false, 1);
                 __syncwarp();
             }
             cur = nxt;
@@ -559,7 +510,7 @@ extern "C" size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *ix, int n_q
 
 static int launch_tiles(const Params &p, bool dense, cudaStream_t st)
 {
-    const size_t smem = (size_t)orag::bm25::kWarps * ((size_t)p.ix.tile_docs * 10 + orag::bm25::kStash * 2) +
+    const size_t smem = (size_t)orag::bm25::kWarps * ((size_t)p.ix.tile_docs * 10 + 2 * orag::bm25::kStage * 4) +
                         (size_t)orag::bm25::kRCacheDl * orag::bm25::kRTf * 8;
     int grid = (p.ix.n_tiles + orag::bm25::kWarps - 1) / orag::bm25::kWarps;
     int per_sm = (int)((224 * 1024) / (smem + 1024));
