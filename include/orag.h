@@ -183,6 +183,14 @@ int orag_topk_merge(const int64_t *d_cand_ids, const double *d_cand_scores, int 
 int orag_rrf_fuse(const int64_t *d_list_ids, int n_queries, int n_lists, int list_len, int rrf_k, int top_k,
                   int tie_mode, int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_src, void *stream);
 
+/* Weighted hybrid score of HybridRetriever.hybrid_search (rag/retrieval.py:302):
+ * out[i] = (alpha*sem[i] + beta*kw[i]) + gamma*temp[i] in float64 without contraction
+ * (d_temp may be NULL = all zero).  Rank the result with orag_dense_topk. */
+int orag_weighted_sum3(const double *d_sem, const double *d_kw, const double *d_temp, int64_t n, double alpha,
+                       double beta, double gamma, double *d_out, void *stream);
+/* d_out[i] = d_in[i] / divisor, one IEEE division each (`s / max_score`, rag/retrieval.py:345). */
+int orag_div_scalar(const double *d_in, int64_t n, double divisor, double *d_out, void *stream);
+
 /* ---------------------------------------------------------------------------
  * Pairwise cosine candidates (rag/consistency_checker.py:169-189): all i<j with
  * doc_idx[i] != doc_idx[j] and float64 cosine >= threshold.  Pairs are written

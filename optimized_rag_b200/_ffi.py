@@ -22,7 +22,7 @@ SYMBOLS = [
     "orag_row_inv_norms", "orag_f32_to_bf16",
     "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_dense", "orag_cosine_firstpass_dense",
     "orag_bm25_workspace_bytes", "orag_bm25_topk", "orag_bm25_dense", "orag_dense_topk",
-    "orag_topk_merge", "orag_rrf_fuse",
+    "orag_topk_merge", "orag_rrf_fuse", "orag_weighted_sum3", "orag_div_scalar",
     "orag_pairwise_workspace_bytes", "orag_pairwise_cosine_threshold",
 ]
 
@@ -88,6 +88,8 @@ def lib() -> ctypes.CDLL:
     L.orag_dense_topk.argtypes = [vp, c_int64, c_int64, c_int, c_int, c_int64, c_int, vp, vp, vp, vp]
     L.orag_topk_merge.argtypes = [vp, vp, c_int, c_int, c_int, vp, c_int, vp, vp, vp, vp]
     L.orag_rrf_fuse.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp]
+    L.orag_weighted_sum3.argtypes = [vp, vp, vp, c_int64, c_double, c_double, c_double, vp, vp]
+    L.orag_div_scalar.argtypes = [vp, c_int64, c_double, vp, vp]
     L.orag_pairwise_workspace_bytes.restype = c_size_t
     L.orag_pairwise_workspace_bytes.argtypes = [c_int64, c_int]
     L.orag_pairwise_cosine_threshold.argtypes = [vp, c_int64, c_int, vp, c_double, c_int64, vp, vp, vp, vp, vp,

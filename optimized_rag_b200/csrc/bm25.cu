@@ -29,8 +29,8 @@ namespace bm25 {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxTerms = 64;
-constexpr int kHistBins = 2048;
-constexpr int kBinBase = (1023 - 20) << 5;  // bins start at 2^-20, 32 bins per octave
+constexpr int kHistBins = 4096;
+constexpr int kBinBase = (1023 - 20) << 6;  // bins start at 2^-20, 64 bins per octave (1.1 % wide)
 
 struct Params {
     orag_bm25_index_t ix;
@@ -54,12 +54,12 @@ struct Params {
 
 __device__ __forceinline__ int score_bin(double v)
 {
-    long long e = (__double_as_longlong(v) >> 47) - kBinBase;
+    long long e = (__double_as_longlong(v) >> 46) - kBinBase;
     return e < 0 ? 0 : (e > kHistBins - 1 ? kHistBins - 1 : (int)e);
 }
 __device__ __forceinline__ unsigned long long bin_floor_bits(int b)
 {
-    return (unsigned long long)(b + kBinBase) << 47;
+    return (unsigned long long)(b + kBinBase) << 46;
 }
 
 // Candidate emission + threshold tightening.  Every 8th emission of a query re-derives its

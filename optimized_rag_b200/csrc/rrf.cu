@@ -85,3 +85,56 @@ extern "C" int orag_rrf_fuse(const int64_t *d_list_ids, int n_queries, int n_lis
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Weighted hybrid score of HybridRetriever.hybrid_search (rag/retrieval.py:302):
+//   h = alpha*sem + beta*kw + gamma*temp        Python float64, left to right, no contraction
+namespace orag {
+__global__ void weighted_sum3_kernel(const double *__restrict__ a, const double *__restrict__ b,
+                                     const double *__restrict__ c, int64_t n, double alpha, double beta, double gamma,
+                                     double *__restrict__ out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const double t = c ? c[i] : 0.0;
+        out[i] = __dadd_rn(__dadd_rn(__dmul_rn(alpha, a[i]), __dmul_rn(beta, b[i])), __dmul_rn(gamma, t));
+    }
+}
+}  // namespace orag
+
+extern "C" int orag_weighted_sum3(const double *d_sem, const double *d_kw, const double *d_temp, int64_t n, double alpha,
+                                  double beta, double gamma, double *d_out, void *stream)
+{
+    ORAG_REQUIRE(d_sem && d_kw && d_out && n >= 0, "weighted_sum3");
+    if (n == 0) return ORAG_OK;
+    int64_t blocks = (n + 255) / 256;
+    int64_t lim = (int64_t)orag::sm_count() * 16;
+    if (blocks > lim) blocks = lim;
+    orag::weighted_sum3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_sem, d_kw, d_temp, n, alpha, beta,
+                                                                                   gamma, d_out);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+// out[i] = in[i] / divisor (one IEEE division per element: `s / max_score`, rag/retrieval.py:345)
+namespace orag {
+__global__ void div_scalar_kernel(const double *__restrict__ in, int64_t n, double divisor, double *__restrict__ out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = __ddiv_rn(in[i], divisor);
+}
+}  // namespace orag
+
+extern "C" int orag_div_scalar(const double *d_in, int64_t n, double divisor, double *d_out, void *stream)
+{
+    ORAG_REQUIRE(d_in && d_out && n >= 0, "div_scalar");
+    if (n == 0) return ORAG_OK;
+    int64_t blocks = (n + 255) / 256;
+    int64_t lim = (int64_t)orag::sm_count() * 16;
+    if (blocks > lim) blocks = lim;
+    orag::div_scalar_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_in, n, divisor, d_out);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}

@@ -200,6 +200,28 @@ def rrf_fuse(list_ids: torch.Tensor, rrf_k: int = 60, top_k: int = 10, tie: str 
     return (ids, sc, src) if want_src else (ids, sc)
 
 
+def weighted_sum3(sem: torch.Tensor, kw: torch.Tensor, temp: torch.Tensor | None, alpha: float, beta: float,
+                  gamma: float) -> torch.Tensor:
+    """(alpha*sem + beta*kw) + gamma*temp in float64 without contraction (rag/retrieval.py:302)."""
+    _require_cuda(sem, "sem")
+    assert sem.dtype == torch.float64 and kw.dtype == torch.float64 and sem.is_contiguous() and kw.is_contiguous()
+    out = torch.empty_like(sem)
+    _ffi.check(_ffi.lib().orag_weighted_sum3(sem.data_ptr(), kw.data_ptr(),
+                                             temp.data_ptr() if temp is not None else None, sem.numel(), alpha, beta,
+                                             gamma, out.data_ptr(), _stream(sem.device)), "orag_weighted_sum3")
+    return out
+
+
+def div_scalar(x: torch.Tensor, divisor: float) -> torch.Tensor:
+    """x / divisor in float64, one IEEE division per element (rag/retrieval.py:345)."""
+    _require_cuda(x, "x")
+    assert x.dtype == torch.float64 and x.is_contiguous()
+    out = torch.empty_like(x)
+    _ffi.check(_ffi.lib().orag_div_scalar(x.data_ptr(), x.numel(), divisor, out.data_ptr(), _stream(x.device)),
+               "orag_div_scalar")
+    return out
+
+
 def pairwise_cosine_threshold(emb: torch.Tensor, doc_idx: torch.Tensor, threshold: float = 0.85,
                               cap: int = 1 << 20):
     """All i<j, doc_idx differ, float64 cosine >= threshold (rag/consistency_checker.py:169-189).
