@@ -1,0 +1,54 @@
+"""torchrun --nproc-per-node G scripts/check_dist.py [rows]
+
+Row-sharded hybrid search over G GPUs must equal the single-shard search over the same corpus,
+bit for bit (ids, cosine / BM25 / RRF scores).  Rank 0 additionally builds the whole corpus on its
+own GPU as the comparison point."""
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from optimized_rag_b200 import engine, synthetic as syn  # noqa: E402
+from optimized_rag_b200.bm25_index import Bm25Index  # noqa: E402
+from optimized_rag_b200.dist import ShardedHybrid, shard_range, sharded_stats  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 300_000
+DIM, VOCAB, B, K = 1536, 50000, 64, 10
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+thr = syn.zipf_thresholds(VOCAB)
+
+
+def build(lo, hi, stats=None, mode="tf32"):
+    corpus = engine.gen_embeddings(hi - lo, DIM, lo, syn.SEED_CORPUS, 1, device=dev)
+    off, tok = engine.gen_token_corpus(hi - lo, lo, syn.SEED_TOKENS, thr, VOCAB, 100, 300, device=dev)
+    st = stats(off, tok) if stats else None
+    return engine.HybridShard(engine.CosineIndex(corpus, row_id_base=lo, mode=mode),
+                              Bm25Index(off, tok, VOCAB, stats=st, doc_id_base=lo))
+
+
+lo, hi = shard_range(N, rank, world)
+q_emb = torch.from_numpy(syn.query_embeddings(B, N, DIM, dup_per_mille=1)).to(dev)
+qt, ql = syn.keyword_queries(B, VOCAB, thresholds=thr)
+qt, ql = torch.from_numpy(qt).to(dev), torch.from_numpy(ql).to(dev)
+ok = True
+for mode in ("tf32", "bf16"):
+    sh = ShardedHybrid(build(lo, hi, lambda o, t: sharded_stats(o, t, VOCAB), mode))
+    res = sh.search(q_emb, qt, ql, K)
+    torch.cuda.synchronize()
+    if rank == 0:
+        ref = build(0, N, None, mode).search(q_emb, qt, ql, K)
+        for key in ("ids", "rrf_scores", "cos_ids", "cos_scores", "bm25_ids", "bm25_scores", "bm25_max"):
+            same = torch.equal(res[key], ref[key])
+            ok &= same
+            print(f"[{mode}] world={world} rows={N}: {key:12s} {'identical' if same else 'DIFFERENT'}", flush=True)
+    dist.barrier()
+if rank == 0:
+    print("DIST CHECK", "PASSED" if ok else "FAILED", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
