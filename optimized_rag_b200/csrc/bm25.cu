@@ -29,8 +29,8 @@ namespace bm25 {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxTerms = 64;
-constexpr int kHistBins = 4096;
-constexpr int kBinBase = (1023 - 20) << 6;  // bins start at 2^-20, 64 bins per octave (1.1 % wide)
+constexpr int kHistBins = 8192;
+constexpr int kBinBase = (1023 - 20) << 7;  // bins start at 2^-20, 128 bins per octave (0.54 % wide)
 
 struct Params {
     orag_bm25_index_t ix;
@@ -54,12 +54,12 @@ struct Params {
 
 __device__ __forceinline__ int score_bin(double v)
 {
-    long long e = (__double_as_longlong(v) >> 46) - kBinBase;
+    long long e = (__double_as_longlong(v) >> 45) - kBinBase;
     return e < 0 ? 0 : (e > kHistBins - 1 ? kHistBins - 1 : (int)e);
 }
 __device__ __forceinline__ unsigned long long bin_floor_bits(int b)
 {
-    return (unsigned long long)(b + kBinBase) << 46;
+    return (unsigned long long)(b + kBinBase) << 45;
 }
 
 // Candidate emission + threshold tightening.  Every 8th emission of a query re-derives its
@@ -95,8 +95,9 @@ __device__ __noinline__ void emit(const Params &p, int q, int32_t doc, double v)
             if (found < 0 && acc >= (uint32_t)p.k) found = 4 * c + 3 - j;
         }
     }
-    // one bin below the k-th best's bin: also keeps docs whose NORMALISED score could tie with it
-    if (found >= 2) atomicMax(p.thr_bits + q, bin_floor_bits(found - 1));
+    // lower edge of the k-th best's bin, minus 4 ulps: also keeps docs whose NORMALISED score could tie
+    // with the k-th best (x/m == y/m in float64 only for raw scores a couple of ulps apart)
+    if (found >= 1) atomicMax(p.thr_bits + q, bin_floor_bits(found) - 4ull);
 }
 
 constexpr int kRTf = 4;      // r = tf*(k1+1)/(tf + t4[dl]) is tabulated for tf = 1..kRTf
@@ -484,8 +485,8 @@ static bool use_dense(const orag_bm25_index_t *ix, int n_queries, int flags)
 
 static int sparse_cap(int n_queries)
 {
-    // ~96 MiB of candidate storage shared by the batch, at least 8192 slots per query
-    int64_t cap = ((int64_t)96 << 20) / 12 / (n_queries > 0 ? n_queries : 1);
+    // ~256 MiB of candidate storage shared by the batch, at least 8192 slots per query
+    int64_t cap = ((int64_t)256 << 20) / 12 / (n_queries > 0 ? n_queries : 1);
     if (cap < 8192) cap = 8192;
     if (cap > (1 << 22)) cap = 1 << 22;
     return (int)cap;
