@@ -48,7 +48,8 @@ constexpr float kEpsBf16 = 3.91e-3f + 2.5e-4f;
 
 constexpr int kGroup = 256;     // queries per tensor-core pass (UMMA N)
 constexpr int kSeedRows = 2048; // rows of the dense seed pass that initialises the thresholds
-constexpr int kCandCap = 4096;  // candidate slots per query
+constexpr int kCandCap = 4096;  // first-pass candidate slots per query
+constexpr int kSurvCap = 512;   // candidates that survive the fp32 re-score (k <= 128 leaves ample room)
 
 struct CosineWs {
     double *sq_q;       // [G]
@@ -57,9 +58,12 @@ struct CosineWs {
     uint32_t *thr_key;  // [G]
     uint32_t *cnt;      // [G]
     uint32_t *hist;     // [G, 1024]
-    int32_t *cand;      // [G, cap]
-    double *cand_score; // [G, cap]
-    int64_t *cand_id;   // [G, cap]
+    int32_t *cand;      // [G, cap]   first-pass survivors (local row ids)
+    float *cos32;       // [G, cap]   their fp32 re-scored cosines
+    int32_t *surv;      // [G, cap2]  rows within 2*eps32 of the k-th best fp32 cosine
+    uint32_t *surv_cnt; // [G]
+    double *cand_score; // [G, cap2]  float64 cosines of the survivors
+    int64_t *cand_id;   // [G, cap2]
     float *seed;        // [kSeedRows, 256]
     void *q_bf16;       // [G, dim] bf16
     size_t bytes;
@@ -81,8 +85,11 @@ static CosineWs carve_tc(void *base, int dim)
     w.cnt = (uint32_t *)take(kGroup * 4);
     w.hist = (uint32_t *)take((size_t)kGroup * tc::kHistBins * 4);
     w.cand = (int32_t *)take((size_t)kGroup * kCandCap * 4);
-    w.cand_score = (double *)take((size_t)kGroup * kCandCap * 8);
-    w.cand_id = (int64_t *)take((size_t)kGroup * kCandCap * 8);
+    w.cos32 = (float *)take((size_t)kGroup * kCandCap * 4);
+    w.surv = (int32_t *)take((size_t)kGroup * kSurvCap * 4);
+    w.surv_cnt = (uint32_t *)take(kGroup * 4);
+    w.cand_score = (double *)take((size_t)kGroup * kSurvCap * 8);
+    w.cand_id = (int64_t *)take((size_t)kGroup * kSurvCap * 8);
     w.seed = (float *)take((size_t)kSeedRows * 256 * 4);
     w.q_bf16 = take((size_t)kGroup * dim * 2);
     w.bytes = (size_t)(p - (uint8_t *)base);
@@ -198,7 +205,7 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
     ORAG_REQUIRE(!bf16 || d_shadow != nullptr || n_rows == 0, "bf16 shadow required");
     ORAG_REQUIRE((reinterpret_cast<uintptr_t>(d_corpus) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_queries) & 15) == 0,
                  "16-byte alignment");
-    ORAG_REQUIRE(k <= 1024, "k <= 1024 for tensor-core modes");
+    ORAG_REQUIRE(k <= 128, "k <= 128 for tensor-core modes");
     CosineWs w = carve_tc(d_workspace, dim);
     const float margin = 2.f * (bf16 ? kEpsBf16 : kEpsTf32);
     const int n_seed = (int)(n_rows < kSeedRows ? n_rows : kSeedRows);
@@ -246,11 +253,15 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
         p.dense_out = nullptr;
         rc = tc::launch_scan(bf16, aop, n_rows, qop, dim, p, st);
         if (rc) return rc;
-        // exact float64 re-score of the survivors, then exact selection
-        rc = launch_rescore(d_corpus, dim, row_id_base, q, w.sq_q, w.cand, w.cnt, kCandCap, nq, w.cand_score, w.cand_id,
-                            st);
+        // fp32 re-score of the candidate set -> the few rows that can still reach the top-k ...
+        rc = launch_prefilter(d_corpus, dim, q, w.inv_qnorm, w.cand, w.cnt, kCandCap, nq, k, w.cos32, kSurvCap, w.surv,
+                              w.surv_cnt, d_out_status ? d_out_status + q0 : nullptr, st);
         if (rc) return rc;
-        rc = launch_select_topk(w.cand_score, w.cand_id, w.cnt, kCandCap, kCandCap, nq, k, 0, 0, nullptr, 0,
+        // ... exact float64 re-score of those (the reference's arithmetic), then exact selection
+        rc = launch_rescore(d_corpus, dim, row_id_base, q, w.sq_q, w.surv, w.surv_cnt, kSurvCap, nq, w.cand_score,
+                            w.cand_id, st);
+        if (rc) return rc;
+        rc = launch_select_topk(w.cand_score, w.cand_id, w.surv_cnt, kSurvCap, kSurvCap, nq, k, 0, 0, nullptr, 0,
                                 d_out_ids + (int64_t)q0 * k, d_out_scores + (int64_t)q0 * k, nullptr,
                                 d_out_status ? d_out_status + q0 : nullptr, st);
         if (rc) return rc;

@@ -247,6 +247,118 @@ int launch_rescore(const float *corpus, int dim, int64_t row_id_base, const floa
     return ORAG_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32 re-score of the first-pass candidates (the "fp32 re-score of the candidate set" stage).
+// One warp per candidate row: coalesced 16-byte loads, fp32 FMA dot product and row sum of squares,
+// shuffle reduction.  Per lane 48 sequential FMAs (dim 1536) + 5 shuffle adds: the result is within
+// ~53 * 2^-24 * |a||b| of the exact dot product, i.e. the cosine is within eps32(dim) (1e-5 at
+// dim 1536: a 2x cushion that also covers the norm, rsqrt and the final multiplies) of the float64 value.
+// Task t = slot * n_queries + q, so that the work of all queries interleaves evenly over the warps.
+static float eps32(int dim) { return fmaxf(1e-5f, (float)(dim / 32 + 16) * 1.2e-7f); }
+
+__global__ void __launch_bounds__(256) prefilter_kernel(const float *__restrict__ corpus, int dim,
+                                                       const float *__restrict__ queries,
+                                                       const float *__restrict__ inv_qnorm,
+                                                       const int32_t *__restrict__ cand, const uint32_t *__restrict__ cnt,
+                                                       int cap, int n_queries, float *__restrict__ out_cos)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t mx = 0;
+    for (int q = lane; q < n_queries; q += 32) mx = max(mx, min(cnt[q], (uint32_t)cap));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int64_t n_tasks = (int64_t)mx * n_queries;
+    const int n4 = dim >> 2;
+    for (int64_t t = warp; t < n_tasks; t += n_warps) {
+        const int q = (int)(t % n_queries);
+        const uint32_t slot = (uint32_t)(t / n_queries);
+        if (slot >= min(cnt[q], (uint32_t)cap)) continue;
+        const int32_t row = cand[(int64_t)q * cap + slot];
+        const float4 *rp = reinterpret_cast<const float4 *>(corpus + (int64_t)row * dim);
+        const float4 *qp = reinterpret_cast<const float4 *>(queries + (int64_t)q * dim);
+        float dot = 0.f, sq = 0.f;
+        for (int j = lane; j < n4; j += 32) {
+            const float4 a = __ldg(rp + j);
+            const float4 b = __ldg(qp + j);
+            dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot); dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
+            sq = fmaf(a.x, a.x, sq); sq = fmaf(a.y, a.y, sq); sq = fmaf(a.z, a.z, sq); sq = fmaf(a.w, a.w, sq);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        }
+        if (lane == 0) out_cos[(int64_t)q * cap + slot] = sq > 0.f ? dot * rsqrtf(sq) * inv_qnorm[q] : 0.f;
+    }
+}
+
+// One CTA per query: k-th best fp32 cosine among the candidates -> keep everything within 2*kEps32
+// of it (every row whose float64 cosine can reach the true top-k), compacted into surv[q][*].
+// Proof sketch: k rows have cos32 >= kth32, hence cos64 >= kth32 - eps, so kth64 >= kth32 - eps; a true
+// top-k row r has cos32(r) >= cos64(r) - eps >= kth64 - eps >= kth32 - 2 eps.
+__global__ void __launch_bounds__(256) prune_kernel(const float *__restrict__ cos32, const int32_t *__restrict__ cand,
+                                                   const uint32_t *__restrict__ cnt, int cap, int k, int cap2,
+                                                   float eps, int32_t *__restrict__ surv,
+                                                   uint32_t *__restrict__ surv_cnt, int32_t *__restrict__ status)
+{
+    __shared__ Pick scratch[32];
+    __shared__ uint32_t s_n;
+    const int q = blockIdx.x;
+    uint32_t n = cnt[q];
+    if (n > (uint32_t)cap) {
+        if (status && threadIdx.x == 0) status[q] |= ORAG_STATUS_OVERFLOW;
+        n = cap;
+    }
+    const float *c = cos32 + (int64_t)q * cap;
+    const int32_t *rows = cand + (int64_t)q * cap;
+    if (threadIdx.x == 0) s_n = 0;
+    float thr = -INFINITY;
+    if (n > (uint32_t)k) {
+        // k rounds of block arg-max under (value desc, slot asc); after round k-1 `prev` is the k-th best
+        double prev_s = INFINITY;
+        int64_t prev_id = -1;
+        for (int r = 0; r < k; ++r) {
+            Pick best;
+            best.valid = 0; best.s = 0.0; best.id = 0;
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const double v = (double)c[i];
+                if (r > 0 && !ranks_before(prev_s, prev_id, v, (int64_t)i)) continue;
+                Pick p;
+                p.s = v; p.id = i; p.valid = 1;
+                best = better(best, p);
+            }
+            best = block_best(best, scratch);
+            prev_s = best.s;
+            prev_id = best.id;
+        }
+        thr = (float)prev_s - 2.f * eps;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        if (c[i] >= thr) {
+            const uint32_t slot = atomicAdd(&s_n, 1u);
+            if (slot < (uint32_t)cap2) surv[(int64_t)q * cap2 + slot] = rows[i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        surv_cnt[q] = s_n;  // > cap2 is flagged as overflow by the final selection
+    }
+}
+
+int launch_prefilter(const float *corpus, int dim, const float *queries, const float *inv_qnorm, const int32_t *cand,
+                     const uint32_t *cnt, int cap, int n_queries, int k, float *cos32, int cap2, int32_t *surv,
+                     uint32_t *surv_cnt, int32_t *status, cudaStream_t st)
+{
+    prefilter_kernel<<<sm_count() * 8, 256, 0, st>>>(corpus, dim, queries, inv_qnorm, cand, cnt, cap, n_queries, cos32);
+    ORAG_LAUNCH_CHECK();
+    prune_kernel<<<n_queries, 256, 0, st>>>(cos32, cand, cnt, cap, k, cap2, eps32(dim), surv, surv_cnt, status);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
 }  // namespace orag
 
 // ================================================================================================
