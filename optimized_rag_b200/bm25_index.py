@@ -200,8 +200,10 @@ class Bm25Index:
         return self._ws
 
     def topk(self, query_terms: torch.Tensor, query_lens: torch.Tensor, k: int, normalize: bool = True,
-             force: str | None = None, check_overflow: bool = True):
+             force: str | None = None, check_overflow: bool = True, status_out: list | None = None):
         """query_terms int32 [B, max_terms] (negative = OOV/padding), query_lens int32 [B].
+        `status_out` (a list) receives the per-query status tensor so that a caller can defer the overflow
+        check and pay one host sync for several calls (see engine.HybridShard.local_lists).
         Returns ids int64 [B,k], scores f64 [B,k], max f64 [B] (divisor if normalize else shard max raw)."""
         assert query_terms.dtype == torch.int32 and query_lens.dtype == torch.int32
         assert query_terms.is_cuda and query_terms.is_contiguous() and query_lens.is_contiguous()
@@ -218,6 +220,8 @@ class Bm25Index:
                                              query_lens.data_ptr(), Bq, mt, k, flags, ids.data_ptr(), sc.data_ptr(),
                                              mx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), st),
                    "orag_bm25_topk")
+        if status_out is not None:
+            status_out.append(status)
         if check_overflow and force != "dense":
             bad = torch.nonzero(status != 0).flatten()
             if bad.numel():

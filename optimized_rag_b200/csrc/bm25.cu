@@ -50,6 +50,7 @@ struct Params {
     // dense path
     double *dense_out;             // [n_queries, n_docs] pre-zeroed
     int q_begin;                   // dense chunking: queries [q_begin, q_begin + n_queries)
+    int q_split;                   // work items per tile (slices of the query batch), >= 1
 };
 
 __device__ __forceinline__ int score_bin(double v)
@@ -178,7 +179,14 @@ __global__ void __launch_bounds__(kThreads, 2) bm25_tile_kernel(const __grid_con
     const int warps_total = gridDim.x * kWarps;
     const unsigned FULL = 0xffffffffu;
 
-    for (int tile = blockIdx.x * kWarps + wib; tile < p.ix.n_tiles; tile += warps_total) {
+    // work item = (tile, slice of the query batch): q_split > 1 keeps all warps busy when a shard has
+    // fewer tiles than the GPU has resident warps (multi-GPU sharding, small corpora)
+    const int S = p.q_split;
+    for (int item = blockIdx.x * kWarps + wib; item < p.ix.n_tiles * S; item += warps_total) {
+        const int tile = item / S;
+        const int part = item - tile * S;
+        const int qi0 = (int)(((int64_t)nq * part) / S);
+        const int qi1 = (int)(((int64_t)nq * (part + 1)) / S);
         const int64_t base_doc = (int64_t)tile * T;
         const int nd = (int)min((int64_t)T, p.ix.n_docs - base_doc);
         for (int i = lane; i < T; i += 32) {
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 2) bm25_tile_kernel(const __grid_con
         // ---- stage A: raw term id + query length (two independent loads)
         auto stage_terms = [&](int qi, int &t, int &nt) {
             t = -1; nt = 0;
-            if (qi < nq) {
+            if (qi < qi1) {
                 const int q = (qi + q_shift) % nq;
                 nt = __ldg(p.q_lens + q);
                 if (lane < mt) t = __ldg(p.q_terms + (int64_t)q * mt + lane);
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 2) bm25_tile_kernel(const __grid_con
             Staged s;
             run.len = (run.idf != 0.0) ? run.len - run.start : 0;  // `idf.get(q) or 0`: zero idf adds nothing
             s.run = run;
-            s.q = (qi < nq) ? (qi + q_shift) % nq : 0;
+            s.q = (qi < qi1) ? (qi + q_shift) % nq : 0;
             s.nt_all = min(nt, mt);
             int incl = run.len;
 #pragma unroll
@@ -242,14 +250,14 @@ __global__ void __launch_bounds__(kThreads, 2) bm25_tile_kernel(const __grid_con
 
         // prologue: fill the pipeline
         int tA, ntA;
-        stage_terms(0, tA, ntA);
-        Staged cur = stage_posts(stage_run(tA, ntA), 0, ntA);  // query 0: postings in flight
-        stage_terms(1, tA, ntA);
-        LaneRun runB = stage_run(tA, ntA);                     // query 1: descriptors in flight
+        stage_terms(qi0, tA, ntA);
+        Staged cur = stage_posts(stage_run(tA, ntA), qi0, ntA);  // first query: postings in flight
+        stage_terms(qi0 + 1, tA, ntA);
+        LaneRun runB = stage_run(tA, ntA);                       // second query: descriptors in flight
         int ntRunB = ntA;
-        stage_terms(2, tA, ntA);                               // query 2: term ids in flight
+        stage_terms(qi0 + 2, tA, ntA);                           // third query: term ids in flight
 
-        for (int qi = 0; qi < nq; ++qi) {
+        for (int qi = qi0; qi < qi1; ++qi) {
             // ---- issue: postings of query qi+1, descriptors of query qi+2, terms of query qi+3
             const Staged nxt = stage_posts(runB, qi + 1, ntRunB);
             runB = stage_run(tA, ntA);
@@ -365,7 +373,7 @@ __device__ double score_doc(const orag_bm25_index_t &ix, const int32_t *terms, i
 
 // One CTA per query: exact top-k over the candidate list by (score/max desc, id asc), then
 // zero-score fill (docs untouched by the query rank after all positive ones, in id order).
-__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ Params p, int64_t doc_id_base, int normalize,
+__global__ void __launch_bounds__(1024) finalize_kernel(const __grid_constant__ Params p, int64_t doc_id_base, int normalize,
                                                       int64_t *__restrict__ out_ids, double *__restrict__ out_scores,
                                                       double *__restrict__ out_max, int32_t *__restrict__ status)
 {
@@ -513,22 +521,31 @@ static int launch_tiles(const Params &p, bool dense, cudaStream_t st)
 {
     const size_t smem = (size_t)orag::bm25::kWarps * ((size_t)p.ix.tile_docs * 10 + 2 * orag::bm25::kStage * 4) +
                         (size_t)orag::bm25::kRCacheDl * orag::bm25::kRTf * 8;
-    int grid = (p.ix.n_tiles + orag::bm25::kWarps - 1) / orag::bm25::kWarps;
     int per_sm = (int)((224 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
-    int lim = orag::sm_count() * per_sm;
+    const int lim = orag::sm_count() * per_sm;
+    // split the query batch so that there are ~4 work items per resident warp even for small shards
+    Params pp = p;
+    int64_t want = (int64_t)4 * lim * orag::bm25::kWarps;
+    int split = (int)((want + p.ix.n_tiles - 1) / (p.ix.n_tiles > 0 ? p.ix.n_tiles : 1));
+    if (split > 16) split = 16;
+    if (split > p.n_queries) split = p.n_queries;
+    if (split < 1) split = 1;
+    pp.q_split = split;
+    int64_t items = (int64_t)p.ix.n_tiles * split;
+    int grid = (int)((items + orag::bm25::kWarps - 1) / orag::bm25::kWarps);
     if (grid > lim) grid = lim;
     if (grid < 1) return ORAG_OK;
     orag::profile_mark(1, 0, st);
     if (dense) {
         ORAG_CUDA_CHECK(cudaFuncSetAttribute(orag::bm25::bm25_tile_kernel<true>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        orag::bm25::bm25_tile_kernel<true><<<grid, orag::bm25::kThreads, smem, st>>>(p);
+        orag::bm25::bm25_tile_kernel<true><<<grid, orag::bm25::kThreads, smem, st>>>(pp);
     } else {
         ORAG_CUDA_CHECK(cudaFuncSetAttribute(orag::bm25::bm25_tile_kernel<false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        orag::bm25::bm25_tile_kernel<false><<<grid, orag::bm25::kThreads, smem, st>>>(p);
+        orag::bm25::bm25_tile_kernel<false><<<grid, orag::bm25::kThreads, smem, st>>>(pp);
     }
     orag::profile_mark(1, 1, st);
     ORAG_LAUNCH_CHECK();
@@ -626,7 +643,7 @@ extern "C" int orag_bm25_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, 
     }
     rc = launch_tiles(p, false, st);
     if (rc) return rc;
-    orag::bm25::finalize_kernel<<<n_queries, 256, 0, st>>>(p, doc_id_base, normalize, d_out_ids, d_out_scores, d_out_max,
+    orag::bm25::finalize_kernel<<<n_queries, 1024, 0, st>>>(p, doc_id_base, normalize, d_out_ids, d_out_scores, d_out_max,
                                                            d_out_status);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;

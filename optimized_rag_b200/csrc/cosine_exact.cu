@@ -51,19 +51,19 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4 *__restri
     }
 }
 
-// sum(q*q) per query, sequential Neumaier (one thread per query; B is at most a few thousand)
-__global__ void query_sq_kernel(const float *__restrict__ queries, int n_queries, int dim, double *__restrict__ sq)
+// sum(q*q) per query in the reference's order (sequential Neumaier per query): lane <-> query, the
+// query rows staged through shared memory with coalesced loads (same scheme as the row scorer).
+__global__ void __launch_bounds__(256) query_sq_kernel(const float *__restrict__ queries, int n_queries, int dim,
+                                                      double *__restrict__ sq)
 {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_queries) return;
-    const float *p = queries + (int64_t)q * dim;
-    NeuSum s;
-    s.init();
-    for (int j = 0; j < dim; ++j) {
-        double a = (double)p[j];
-        s.add(__dmul_rn(a, a));
-    }
-    sq[q] = s.result();
+    __shared__ float stage_all[8][32 * 33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int q = (blockIdx.x * 8 + wib) * 32 + lane;
+    const float *rowptr = q < n_queries ? queries + (int64_t)q * dim : nullptr;
+    const float *qp[1] = {nullptr};
+    NeuSum dot[1], s;
+    warp_score_rows<1>(rowptr, qp, dim, stage_all[wib], dot, s, true);
+    if (q < n_queries) sq[q] = s.result();
 }
 
 constexpr int kDenseQB = 4;
@@ -215,7 +215,7 @@ int launch_select_topk(const double *scores, const int64_t *ids, const uint32_t 
 
 int launch_query_sq(const float *queries, int n_queries, int dim, double *sq, cudaStream_t st)
 {
-    query_sq_kernel<<<(n_queries + 63) / 64, 64, 0, st>>>(queries, n_queries, dim, sq);
+    query_sq_kernel<<<(n_queries + 255) / 256, 256, 0, st>>>(queries, n_queries, dim, sq);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }

@@ -87,8 +87,8 @@ class ShardedHybrid:
         if self.world == 1:
             return self.shard.search(query_emb, query_terms, query_lens, k, fetch_k, check_overflow)
         kk = fetch_k + BM25_GUARD
-        ci, cs = self.shard.cosine.topk(query_emb, fetch_k, check_overflow=check_overflow)
-        bi, bs, bm = self.shard.bm25.topk(query_terms, query_lens, kk, normalize=False, check_overflow=check_overflow)
+        ci, cs, bi, bs, bm = self.shard.local_lists(query_emb, query_terms, query_lens, fetch_k, kk, False,
+                                                    check_overflow)
         mine = pack_local(ci, cs, bi, bs, bm)
         Bq, W = mine.shape
         if self._gather_buf is None or self._gather_buf.shape != (self.world, Bq, W):

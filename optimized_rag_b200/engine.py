@@ -93,8 +93,10 @@ class CosineIndex:
             self._ws[mode] = ws
         return ws
 
-    def topk(self, queries: torch.Tensor, k: int, mode: str | None = None, check_overflow: bool = True):
-        """queries fp32 [B, dim] on the same device -> (ids int64 [B,k], scores float64 [B,k])."""
+    def topk(self, queries: torch.Tensor, k: int, mode: str | None = None, check_overflow: bool = True,
+             status_out: list | None = None):
+        """queries fp32 [B, dim] on the same device -> (ids int64 [B,k], scores float64 [B,k]).
+        `status_out` (a list) receives the per-query status tensor for a deferred overflow check."""
         _require_cuda(queries, "queries")
         assert queries.dtype == torch.float32 and queries.is_contiguous() and queries.shape[1] == self.dim
         m = MODE[mode or self.mode]
@@ -112,6 +114,8 @@ class CosineIndex:
             self.shadow.data_ptr() if self.shadow is not None else None, self.n_rows, self.dim, self.row_id_base,
             queries.data_ptr(), Bq, k, m, ids.data_ptr(), sc.data_ptr(), status.data_ptr(), ws.data_ptr(),
             ws.numel(), _stream(self.device)), "orag_cosine_topk")
+        if status_out is not None:
+            status_out.append(status)
         if check_overflow and m != _ffi.ORAG_COS_EXACT:
             bad = torch.nonzero(status != 0).flatten()
             if bad.numel():
@@ -259,11 +263,34 @@ class HybridShard:
         self.bm25 = bm25
         self.rrf_k = rrf_k
 
+    def local_lists(self, query_emb: torch.Tensor, query_terms: torch.Tensor, query_lens: torch.Tensor, fetch_k: int,
+                    bm25_k: int, normalize: bool, check_overflow: bool = True):
+        """Cosine top-fetch_k and BM25 top-bm25_k of this shard.  Both kernels pipelines are enqueued back to
+        back; candidate-buffer overflow of either is checked with ONE host sync afterwards and the affected
+        queries are re-run through the exact dense kernels (still on the GPU)."""
+        st: list = []
+        ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=False, status_out=st)
+        bi, bs, bmax = self.bm25.topk(query_terms, query_lens, bm25_k, normalize=normalize, check_overflow=False,
+                                      status_out=st)
+        if check_overflow:
+            bad_c, bad_b = st[0] != 0, st[1] != 0
+            any_bad = torch.stack([bad_c.any(), bad_b.any()]).cpu()
+            if bool(any_bad[0]):
+                bad = torch.nonzero(bad_c).flatten()
+                i2, s2 = self.cosine.topk(query_emb[bad].contiguous(), fetch_k, mode="exact", check_overflow=False)
+                ci[bad], cs[bad] = i2, s2
+            if bool(any_bad[1]):
+                bad = torch.nonzero(bad_b).flatten()
+                i2, s2, m2 = self.bm25.topk(query_terms[bad].contiguous(), query_lens[bad].contiguous(), bm25_k,
+                                            normalize, force="dense", check_overflow=False)
+                bi[bad], bs[bad], bmax[bad] = i2, s2, m2
+        return ci, cs, bi, bs, bmax
+
     def search(self, query_emb: torch.Tensor, query_terms: torch.Tensor, query_lens: torch.Tensor, k: int = 10,
                fetch_k: int | None = None, check_overflow: bool = True):
         fetch_k = fetch_k or k
-        ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=check_overflow)
-        bi, bs, bmax = self.bm25.topk(query_terms, query_lens, fetch_k, normalize=True, check_overflow=check_overflow)
+        ci, cs, bi, bs, bmax = self.local_lists(query_emb, query_terms, query_lens, fetch_k, fetch_k, True,
+                                                check_overflow)
         lists = torch.stack([ci, bi], dim=1).contiguous()
         fi, fs, src = rrf_fuse(lists, self.rrf_k, k, want_src=True)
         return {"ids": fi, "rrf_scores": fs, "src_ranks": src, "cos_ids": ci, "cos_scores": cs, "bm25_ids": bi,
