@@ -17,19 +17,28 @@ __device__ __forceinline__ void warp_score_rows(const float *rowptr, const float
 #pragma unroll
     for (int b = 0; b < QB; ++b) dot[b].init();
     sq.init();
-    for (int c0 = 0; c0 < dim; c0 += 32) {
+    // software pipeline: the 32x32 block of chunk c+1 is in flight (registers) while chunk c is summed
+    float nxt[32], qnxt[QB];
+    auto fetch = [&](int c0) {
         const int col = c0 + lane;
         const bool col_ok = col < dim;
-#pragma unroll 8
+#pragma unroll
         for (int i = 0; i < 32; ++i) {
             const float *p = (const float *)(uintptr_t)__shfl_sync(0xffffffffu, myp, i);
-            float v = (p != nullptr && col_ok) ? __ldg(p + col) : 0.f;
-            stage[i * 33 + lane] = v;
+            nxt[i] = (p != nullptr && col_ok) ? __ldg(p + col) : 0.f;
         }
+#pragma unroll
+        for (int b = 0; b < QB; ++b) qnxt[b] = (qptr[b] != nullptr && col_ok) ? __ldg(qptr[b] + col) : 0.f;
+    };
+    fetch(0);
+    for (int c0 = 0; c0 < dim; c0 += 32) {
         float qreg[QB];
 #pragma unroll
-        for (int b = 0; b < QB; ++b) qreg[b] = (qptr[b] != nullptr && col_ok) ? __ldg(qptr[b] + col) : 0.f;
+        for (int i = 0; i < 32; ++i) stage[i * 33 + lane] = nxt[i];
+#pragma unroll
+        for (int b = 0; b < QB; ++b) qreg[b] = qnxt[b];
         __syncwarp();
+        if (c0 + 32 < dim) fetch(c0 + 32);
         const int jmax = min(32, dim - c0);
         for (int j = 0; j < jmax; ++j) {
             double a = (double)stage[lane * 33 + j];
