@@ -127,6 +127,7 @@ struct LaneRun {  // lane i holds the run of query term i inside the warp's tile
 };
 
 constexpr int kStage = 256;  // postings of one query staged per buffer (two buffers per warp)
+constexpr uint32_t kNoPost = 0xFFFFFFFFu;  // doc_in_tile <= 2047, so no real posting has this value
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
 {
@@ -203,7 +204,8 @@ __global__ void __launch_bounds__(kThreads, 2) bm25_tile_kernel(const __grid_con
         auto stage_terms = [&](int qi, int &t, int &nt) {
             t = -1; nt = 0;
             if (qi < qi1) {
-                const int q = (qi + q_shift) % nq;
+                int q = qi + q_shift;  // q_shift < nq and qi < nq: one conditional subtract, no modulo
+                if (q >= nq) q -= nq;
                 nt = __ldg(p.q_lens + q);
                 if (lane < mt) t = __ldg(p.q_terms + (int64_t)q * mt + lane);
             }
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 2) bm25_tile_kernel(const __grid_con
             Staged s;
             run.len = (run.idf != 0.0) ? run.len - run.start : 0;  // `idf.get(q) or 0`: zero idf adds nothing
             s.run = run;
-            s.q = (qi < qi1) ? (qi + q_shift) % nq : 0;
+            s.q = (qi < qi1) ? (qi + q_shift >= nq ? qi + q_shift - nq : qi + q_shift) : 0;
             s.nt_all = min(nt, mt);
             int incl = run.len;
 #pragma unroll
@@ -303,7 +305,16 @@ __global__ void __launch_bounds__(kThreads, 2) bm25_tile_kernel(const __grid_con
                     if (mode == 0) {
                         const double idf = __shfl_sync(FULL, run.idf, i);
                         for (int j = lane; j < sl; j += 32) apply(buf[so + j], idf);
-                        for (int j = sl + lane; j < ln; j += 32) apply(__ldg(tile_post + st + j), idf);
+                        // non-staged tail of a long run: four independent loads in flight per lane
+                        for (int j = sl + lane; j < ln; j += 128) {
+                            uint32_t pv[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                pv[u] = (j + 32 * u < ln) ? __ldg(tile_post + st + j + 32 * u) : kNoPost;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (pv[u] != kNoPost) apply(pv[u], idf);
+                        }
                         __syncwarp();  // run i fully applied before run i+1
                     } else {
                         for (int j = sl + lane; j < ln; j += 32) drain_doc(__ldg(tile_post + st + j) >> 16);
@@ -330,10 +341,14 @@ __global__ void __launch_bounds__(kThreads, 2) bm25_tile_kernel(const __grid_con
                 for (int c0 = 32; c0 < cur.nt_all; c0 += 32) walk(long_query_runs(c0), 0, 0, false, 0);
 
                 // ---- drain: every touched doc is reported once with its final score; accumulator reset
+                const bool long_runs = __any_sync(FULL, cur.run.len > cur.slen) || cur.nt_all > 32;
+                if (long_runs) {
+                    // some postings were not staged: sweep the whole tile instead of re-reading them
+                    for (int d = lane; d < T; d += 32) drain_doc((uint32_t)d);
+                } else {
 #pragma unroll 4
-                for (int j = lane; j < staged_total; j += 32) drain_doc(buf[j] >> 16);
-                if (__any_sync(FULL, cur.run.len > cur.slen)) walk(cur.run, cur.soff, cur.slen, true, 1);
-                for (int c0 = 32; c0 < cur.nt_all; c0 += 32) walk(long_query_runs(c0), 0, 0, false, 1);
+                    for (int j = lane; j < staged_total; j += 32) drain_doc(buf[j] >> 16);
+                }
                 __syncwarp();
             }
             cur = nxt;
