@@ -202,6 +202,17 @@ int orag_pairwise_cosine_threshold(const float *d_emb, int64_t m, int dim, const
                                    double *d_out_sim, unsigned long long *d_out_count, void *d_workspace,
                                    size_t workspace_bytes, void *stream);
 
+/* Tensor-core variant (BASELINE config 5, 64k x 1536): tcgen05 tf32 first pass with a fixed threshold
+ * (threshold - first-pass error bound) over row blocks of 256, then the same float64 re-score and
+ * filter -> identical pair set.  Needs dim % 32 == 0 and threshold > 2.3e-3.  d_out_count has TWO
+ * elements: [0] = number of pairs, [1] = 1 if a per-row candidate buffer overflowed (result
+ * incomplete: re-run with orag_pairwise_cosine_threshold). */
+size_t orag_pairwise_tc_workspace_bytes(int64_t m, int dim);
+int orag_pairwise_cosine_threshold_tc(const float *d_emb, int64_t m, int dim, const int32_t *d_doc_idx,
+                                      double threshold, int64_t cap, int32_t *d_out_i, int32_t *d_out_j,
+                                      double *d_out_sim, unsigned long long *d_out_count, void *d_workspace,
+                                      size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ SYMBOLS = [
     "orag_bm25_workspace_bytes", "orag_bm25_topk", "orag_bm25_dense", "orag_dense_topk",
     "orag_topk_merge", "orag_rrf_fuse", "orag_weighted_sum3", "orag_div_scalar",
     "orag_pairwise_workspace_bytes", "orag_pairwise_cosine_threshold",
+    "orag_pairwise_tc_workspace_bytes", "orag_pairwise_cosine_threshold_tc",
 ]
 
 
@@ -94,10 +95,13 @@ def lib() -> ctypes.CDLL:
     L.orag_pairwise_workspace_bytes.argtypes = [c_int64, c_int]
     L.orag_pairwise_cosine_threshold.argtypes = [vp, c_int64, c_int, vp, c_double, c_int64, vp, vp, vp, vp, vp,
                                                  c_size_t, vp]
+    L.orag_pairwise_tc_workspace_bytes.restype = c_size_t
+    L.orag_pairwise_tc_workspace_bytes.argtypes = [c_int64, c_int]
+    L.orag_pairwise_cosine_threshold_tc.argtypes = L.orag_pairwise_cosine_threshold.argtypes
     for name in SYMBOLS:
         f = getattr(L, name)
         if name not in ("orag_last_error", "orag_launch_count", "orag_cosine_workspace_bytes", "orag_bm25_workspace_bytes",
-                        "orag_pairwise_workspace_bytes"):
+                        "orag_pairwise_workspace_bytes", "orag_pairwise_tc_workspace_bytes"):
             f.restype = c_int
     _lib = L
     return L

@@ -136,6 +136,7 @@ __device__ __noinline__ void emit_candidate(const ScanParams &p, int q, int32_t 
 {
     const uint32_t slot = atomicAdd(p.cnt + q, 1u);
     if (slot < (uint32_t)p.cap) p.cand[(int64_t)q * p.cap + slot] = local_row;
+    if (p.fixed_thr) return;
     const int bin = cos_bin(v * p.inv_qnorm[q]);
     uint32_t *h = p.hist + (int64_t)q * kHistBins;
     atomicAdd(h + bin, 1u);

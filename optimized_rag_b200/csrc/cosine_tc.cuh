@@ -41,6 +41,7 @@ struct ScanParams {
     const float *inv_qnorm;
     float margin;           // 2 * eps (cosine units)
     int k;
+    int fixed_thr;          // 1: thresholds are given (pairwise >= t search): no histogram, no tightening
 };
 
 int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_base, int dim, ScanParams p,

@@ -227,24 +227,38 @@ def div_scalar(x: torch.Tensor, divisor: float) -> torch.Tensor:
 
 
 def pairwise_cosine_threshold(emb: torch.Tensor, doc_idx: torch.Tensor, threshold: float = 0.85,
-                              cap: int = 1 << 20):
+                              cap: int = 1 << 20, mode: str = "auto"):
     """All i<j, doc_idx differ, float64 cosine >= threshold (rag/consistency_checker.py:169-189).
-    Returns (i, j, sim) sorted by (i, j)."""
+    Returns (i, j, sim) sorted by (i, j).  mode: "exact" = float64 CUDA-core sweep of every pair,
+    "tc" = tcgen05 first pass + float64 re-score (same pair set), "auto" = tc for large inputs."""
     _require_cuda(emb, "emb")
     assert emb.dtype == torch.float32 and emb.is_contiguous() and doc_idx.dtype == torch.int32
     m, dim = emb.shape
     dev = emb.device
+    if mode == "auto":
+        mode = "tc" if (m >= 2048 and dim % 32 == 0 and threshold > 0.01) else "exact"
     oi = torch.empty(cap, dtype=torch.int32, device=dev)
     oj = torch.empty(cap, dtype=torch.int32, device=dev)
     osim = torch.empty(cap, dtype=torch.float64, device=dev)
-    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-    need = int(_ffi.lib().orag_pairwise_workspace_bytes(m, dim))
-    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
-    _ffi.check(_ffi.lib().orag_pairwise_cosine_threshold(emb.data_ptr(), m, dim, doc_idx.data_ptr(), threshold, cap,
-                                                         oi.data_ptr(), oj.data_ptr(), osim.data_ptr(), cnt.data_ptr(),
-                                                         ws.data_ptr(), ws.numel(), _stream(dev)),
-               "orag_pairwise_cosine_threshold")
-    n = int(cnt.item())
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    L = _ffi.lib()
+    if mode == "tc":
+        need = int(L.orag_pairwise_tc_workspace_bytes(m, dim))
+        ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+        _ffi.check(L.orag_pairwise_cosine_threshold_tc(emb.data_ptr(), m, dim, doc_idx.data_ptr(), threshold, cap,
+                                                       oi.data_ptr(), oj.data_ptr(), osim.data_ptr(), cnt.data_ptr(),
+                                                       ws.data_ptr(), ws.numel(), _stream(dev)),
+                   "orag_pairwise_cosine_threshold_tc")
+        if int(cnt[1].item()) != 0:  # a row had more first-pass candidates than slots: exact sweep instead
+            return pairwise_cosine_threshold(emb, doc_idx, threshold, cap, mode="exact")
+    else:
+        need = int(L.orag_pairwise_workspace_bytes(m, dim))
+        ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+        _ffi.check(L.orag_pairwise_cosine_threshold(emb.data_ptr(), m, dim, doc_idx.data_ptr(), threshold, cap,
+                                                    oi.data_ptr(), oj.data_ptr(), osim.data_ptr(), cnt.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), _stream(dev)),
+                   "orag_pairwise_cosine_threshold")
+    n = int(cnt[0].item())
     if n > cap:
         raise _ffi.OragError(f"pair capacity exceeded ({n} > {cap})")
     key = oi[:n].long() * m + oj[:n].long()

@@ -326,3 +326,25 @@ def test_hybrid_vs_oracle_mid_size(eng):
         assert res["rrf_scores"][b].cpu().tolist() == want[b]["rrf_scores"].tolist(), b
         assert res["cos_ids"][b].cpu().tolist() == want[b]["cos_ids"].tolist(), b
         assert res["bm25_ids"][b].cpu().tolist() == want[b]["bm25_ids"].tolist(), b
+
+
+def test_pairwise_tensor_core_equals_exact(eng):
+    """Config-5 path: tcgen05 first pass + float64 re-score finds exactly the pairs of the exact sweep."""
+    m, d = 3000, 256
+    emb = syn.embeddings(syn.SEED_CORPUS, 0, m, d)
+    rng = np.random.default_rng(11)
+    for i in range(0, m, 7):  # planted near-duplicates at assorted similarities around the threshold
+        j = int(rng.integers(0, m))
+        w = np.float32(rng.choice([0.3, 0.55, 0.6, 0.62, 0.65, 0.8]))
+        emb[i] = (emb[j] + w * emb[i]).astype(np.float32)
+    emb[5] = 0.0
+    doc = (np.arange(m) // 4).astype(np.int32)
+    a = eng.pairwise_cosine_threshold(_t(emb), _t(doc), 0.85, mode="exact")
+    b = eng.pairwise_cosine_threshold(_t(emb), _t(doc), 0.85, mode="tc")
+    assert len(a[0]) > 50
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    wi, wj, ws = oracle.pairwise_candidates(emb[:400], doc[:400], 0.85)
+    c = eng.pairwise_cosine_threshold(_t(emb[:400]), _t(doc[:400]), 0.85, mode="tc")
+    assert np.array_equal(c[0].cpu().numpy(), wi) and np.array_equal(c[1].cpu().numpy(), wj)
+    assert np.array_equal(_bits(c[2].cpu().numpy()), _bits(ws))
