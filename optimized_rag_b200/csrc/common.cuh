@@ -77,19 +77,20 @@ __host__ __device__ __forceinline__ uint64_t row_key(uint64_t seed, uint64_t row
 // Neumaier-compensated running sum, exactly as builtin_sum() performs it for floats.
 struct NeuSum {
     double s, c;
-    bool first;
-    __device__ __forceinline__ void init() { s = 0.0; c = 0.0; first = true; }
+    // builtin_sum() starts from int 0: the first float item x0 enters as 0 + x0 == 0.0 + x0, after which
+    // the compensated loop runs; starting the loop itself from s = 0.0, c = 0.0 is bit-identical (the
+    // first step adds an exact zero to c) and needs no special case.
+    __device__ __forceinline__ void init() { s = 0.0; c = 0.0; }
     __device__ __forceinline__ void add(double x)
     {
-        if (first) { s = x; first = false; return; }
-        double t = __dadd_rn(s, x);
-        if (fabs(s) >= fabs(x)) c = __dadd_rn(c, __dadd_rn(__dadd_rn(s, -t), x));
-        else                    c = __dadd_rn(c, __dadd_rn(__dadd_rn(x, -t), s));
+        const double t = __dadd_rn(s, x);
+        const double hi = fabs(s) >= fabs(x) ? s : x;
+        const double lo = fabs(s) >= fabs(x) ? x : s;
+        c = __dadd_rn(c, __dadd_rn(__dadd_rn(hi, -t), lo));
         s = t;
     }
     __device__ __forceinline__ double result() const
     {
-        if (first) return 0.0;
         if (c != 0.0 && isfinite(c)) return __dadd_rn(s, c);
         return s;
     }

@@ -114,8 +114,9 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
     int64_t warp = blockIdx.x * (int64_t)(blockDim.x >> 5) + wib;
     int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t w = warp; w < (int64_t)n_queries * chunks_per_q; w += n_warps) {
-        int q = (int)(w / chunks_per_q);
-        int chunk = (int)(w % chunks_per_q);
+        // chunk-major task order: the (few) non-empty chunks of all queries land on distinct warps
+        int q = (int)(w % n_queries);
+        int chunk = (int)(w / n_queries);
         uint32_t n = min(cnt[q], (uint32_t)cap);
         if ((uint32_t)chunk * 32u >= n) continue;
         uint32_t slot = chunk * 32 + lane;

@@ -40,13 +40,36 @@ __device__ __forceinline__ void warp_score_rows(const float *rowptr, const float
         __syncwarp();
         if (c0 + 32 < dim) fetch(c0 + 32);
         const int jmax = min(32, dim - c0);
-        for (int j = 0; j < jmax; ++j) {
-            double a = (double)stage[lane * 33 + j];
-            if (want_sq) sq.add(__dmul_rn(a, a));
+        if (jmax == 32) {
+            // products of 8 elements are formed ahead of the (inherently sequential) compensated sums so that
+            // shared-memory reads, shuffles and multiplies overlap the dependent add chains
 #pragma unroll
-            for (int b = 0; b < QB; ++b) {
-                double qv = (double)__shfl_sync(0xffffffffu, qreg[b], j);
-                dot[b].add(__dmul_rn(qv, a));
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+                double pa[8], pq[QB][8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double a = (double)stage[lane * 33 + j0 + u];
+                    pa[u] = __dmul_rn(a, a);
+#pragma unroll
+                    for (int b = 0; b < QB; ++b)
+                        pq[b][u] = __dmul_rn((double)__shfl_sync(0xffffffffu, qreg[b], j0 + u), a);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (want_sq) sq.add(pa[u]);
+#pragma unroll
+                    for (int b = 0; b < QB; ++b) dot[b].add(pq[b][u]);
+                }
+            }
+        } else {
+            for (int j = 0; j < jmax; ++j) {
+                double a = (double)stage[lane * 33 + j];
+                if (want_sq) sq.add(__dmul_rn(a, a));
+#pragma unroll
+                for (int b = 0; b < QB; ++b) {
+                    double qv = (double)__shfl_sync(0xffffffffu, qreg[b], j);
+                    dot[b].add(__dmul_rn(qv, a));
+                }
             }
         }
         __syncwarp();

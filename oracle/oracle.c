@@ -42,7 +42,8 @@ static double sum_prod(const float *a, const float *b, int d, int neumaier)
 {
     if (d <= 0) return 0.0;
     /* fp32 widened exactly to binary64; product of two widened fp32 is exact */
-    double s = (double)a[0] * (double)b[0];
+    /* sum() starts from int 0, so the first item enters as 0 + x0 (== 0.0 + x0 in binary64) */
+    double s = 0.0 + (double)a[0] * (double)b[0];
     if (!neumaier) {
         for (int i = 1; i < d; ++i) s = s + (double)a[i] * (double)b[i];
         return s;
