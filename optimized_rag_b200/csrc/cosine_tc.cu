@@ -157,6 +157,23 @@ __device__ __noinline__ void emit_candidate(const ScanParams &p, int q, int32_t 
     if (found >= 1) atomicMax(p.thr_key + q, float_to_ordered(bin_floor(found)));
 }
 
+// tile index -> (first corpus row, first query row).  Scan mode: tiles walk the row range, one query
+// block.  Pair mode (all-pairs search over one matrix): query block qb = rows [256 qb, 256 qb + 256) is
+// matched against the row tiles below its end, tiles [qb (qb+1), (qb+1)(qb+2)) of a triangular enumeration.
+__device__ __forceinline__ void decode_tile(const ScanParams &p, int tile, int64_t &row0, int &qoff)
+{
+    if (!p.pair_mode) {
+        row0 = p.row_begin + (int64_t)tile * kTileM;
+        qoff = 0;
+        return;
+    }
+    int qb = (int)((sqrtf(1.0f + 4.0f * (float)tile) - 1.0f) * 0.5f);
+    while ((qb + 1) * (qb + 2) <= tile) ++qb;
+    while (qb * (qb + 1) > tile) --qb;
+    row0 = (int64_t)(tile - qb * (qb + 1)) * kTileM;
+    qoff = qb * kMaxN;
+}
+
 template <bool kBf16>
 __global__ void __launch_bounds__(kThreads, 1)
 cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -212,13 +229,16 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int row = (int)(p.row_begin + (int64_t)tile * kTileM);
+                int64_t row0;
+                int qoff;
+                decode_tile(p, tile, row0, qoff);
+                const int row = (int)row0;
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
                     const uint32_t fb = smem_u32(full_bar + stage);
                     mbar_expect_tx(fb, tx);
                     tma_load_2d(smem_u32(smem_a + stage * kABytes), &map_a, kc * p.chunk_elems, row, fb, pol_stream);
-                    tma_load_2d(smem_u32(smem_b + stage * kBBytes), &map_b, kc * p.chunk_elems, 0, fb, pol_keep);
+                    tma_load_2d(smem_u32(smem_b + stage * kBBytes), &map_b, kc * p.chunk_elems, qoff, fb, pol_keep);
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -259,11 +279,14 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             float *thrv = thrv_s + as * kMaxN;
+            int64_t row0;
+            int qoff;
+            decode_tile(p, tile, row0, qoff);
             if (!p.dense) {
                 float t = INFINITY;
-                if (et < p.n_queries) {
-                    float thr = ordered_to_float(__ldcg(p.thr_key + et));
-                    t = (thr - p.margin) * p.qnorm[et];
+                if (qoff + et < p.n_queries) {
+                    float thr = ordered_to_float(__ldcg(p.thr_key + qoff + et));
+                    t = (thr - p.margin) * p.qnorm[qoff + et];
                     if (!(t == t)) t = INFINITY;  // |q| == 0: nothing passes (handled by the seed pass)
                 }
                 thrv[et] = t;
@@ -271,7 +294,7 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             mbar_wait(smem_u32(tmem_full + as), ((uint32_t)it >> 1) & 1u);
             tc_fence_after();
-            const int64_t row = p.row_begin + (int64_t)tile * kTileM + quarter * 32 + lane;
+            const int64_t row = row0 + quarter * 32 + lane;
             const bool valid = row < p.row_end;
             const float scale = valid ? __ldg(p.inv_norm + row) : 0.f;
             const int32_t local_row = (int32_t)row;
@@ -305,9 +328,11 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     if (any && valid) {
 #pragma unroll  // static register indices: a dynamic r[j] would push the whole tile row to local memory
                         for (int j = 0; j < 32; ++j) {
-                            const int q = col0 + j;
+                            const int q = qoff + col0 + j;
                             const float v = __uint_as_float(r[j]) * scale;
-                            if (q < p.n_queries && v >= thrv[q]) emit_candidate(p, q, local_row, v);
+                            // pair mode keeps i < j only (each unordered pair once, no self pairs)
+                            if (q < p.n_queries && v >= thrv[col0 + j] && (!p.pair_mode || local_row < q))
+                                emit_candidate(p, q, local_row, v);
                         }
                     }
                 }
@@ -450,11 +475,16 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
     if (p.umma_n < 16) p.umma_n = 16;
     int rc = make_map(&map_a, a_base, bf16, a_rows, dim, kTileM);
     if (rc) return rc;
-    rc = make_map(&map_b, q_base, bf16, p.n_queries, dim, p.umma_n);
+    rc = make_map(&map_b, q_base, bf16, p.n_queries, dim, p.pair_mode ? kMaxN : p.umma_n);
     if (rc) return rc;
     p.chunk_elems = bf16 ? 64 : 32;
     p.k_chunks = dim / p.chunk_elems;
     p.num_tiles = (int)((p.row_end - p.row_begin + kTileM - 1) / kTileM);
+    if (p.pair_mode) {
+        const int nb = (p.n_queries + kMaxN - 1) / kMaxN;
+        p.num_tiles = nb * (nb + 1);
+        p.umma_n = kMaxN;
+    }
     p.idesc = make_idesc(bf16, p.umma_n);
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     if (!p.dense) profile_mark(0, 0, st);

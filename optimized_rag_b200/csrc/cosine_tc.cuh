@@ -42,6 +42,7 @@ struct ScanParams {
     float margin;           // 2 * eps (cosine units)
     int k;
     int fixed_thr;          // 1: thresholds are given (pairwise >= t search): no histogram, no tightening
+    int pair_mode;          // 1: all-pairs search, queries = corpus rows, triangular (query block, row tile) tiles
 };
 
 int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_base, int dim, ScanParams p,

@@ -102,22 +102,22 @@ extern "C" int orag_pairwise_cosine_threshold(const float *d_emb, int64_t m, int
 
 // ================================================================================================
 // Tensor-core path (BASELINE config 5: 64k claims x 1536): the similarity scan of cosine_tc.cu with
-// a FIXED threshold.  For each block of 256 rows taken as "queries" j, rows i < j0+256 are scanned
-// (tf32 straight off the fp32 embeddings); every (i, j) whose first-pass cosine clears
+// a FIXED threshold, in pair mode: ONE launch walks the triangular space of (256-row query block j,
+// 128-row tile i below the block's end), tf32 straight off the fp32 embeddings; every (i < j) whose
+// first-pass cosine clears
 // threshold - eps_tf32 is re-scored in the reference's float64 arithmetic and kept if i < j,
 // doc_idx differ and the exact cosine >= threshold.  |first pass - exact| <= eps, so no pair is lost.
 #include "cosine_tc.cuh"
 
 namespace orag {
 
-constexpr int kPairBlock = 256;
-constexpr int kPairCap = 8192;                    // first-pass candidates per query row
+constexpr int kPairCap = 64;                      // first-pass candidates (i < j) per row j
 constexpr float kPairEps = 1.954e-3f + 2.5e-4f;  // tf32 first-pass bound (see api.cu)
 
-__global__ void pair_thr_init_kernel(const float *__restrict__ qnorm, int n, float thr, uint32_t *__restrict__ thr_key,
-                                     uint32_t *__restrict__ cnt)
+__global__ void pair_thr_init_kernel(const float *__restrict__ qnorm, int64_t n, float thr,
+                                     uint32_t *__restrict__ thr_key, uint32_t *__restrict__ cnt)
 {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= n) return;
     // a zero-norm row has cosine 0.0 with everything: it can only pair up when thr <= 0 (handled by the
     // exact path); here it must not flood the candidate lists
@@ -125,30 +125,33 @@ __global__ void pair_thr_init_kernel(const float *__restrict__ qnorm, int n, flo
     cnt[q] = 0;
 }
 
+// one warp per row j: keep the re-scored candidates that really clear the threshold
 __global__ void __launch_bounds__(256) pair_filter_kernel(const double *__restrict__ scores, const int64_t *__restrict__ ids,
-                                                         const uint32_t *__restrict__ cnt, int cap, int nq, int64_t j0,
+                                                         const uint32_t *__restrict__ cnt, int cap, int64_t m,
                                                          const int32_t *__restrict__ doc_idx, double thr, int64_t out_cap,
                                                          int32_t *__restrict__ out_i, int32_t *__restrict__ out_j,
                                                          double *__restrict__ out_sim,
                                                          unsigned long long *__restrict__ out_count)
 {
-    const int q = blockIdx.x;
-    if (q >= nq) return;
-    uint32_t n = cnt[q];
-    if (n > (uint32_t)cap) {
-        if (threadIdx.x == 0) atomicExch(out_count + 1, 1ull);  // overflow flag: caller falls back to the exact path
-        n = cap;
-    }
-    const int64_t j = j0 + q;
-    for (uint32_t s = threadIdx.x; s < n; s += blockDim.x) {
-        const int64_t i = ids[(int64_t)q * cap + s];
-        const double c = scores[(int64_t)q * cap + s];
-        if (i < j && doc_idx[i] != doc_idx[j] && c >= thr) {
-            unsigned long long slot = atomicAdd(out_count, 1ull);
-            if ((int64_t)slot < out_cap) {
-                out_i[slot] = (int32_t)i;
-                out_j[slot] = (int32_t)j;
-                out_sim[slot] = c;
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = warp; j < m; j += n_warps) {
+        uint32_t n = cnt[j];
+        if (n > (uint32_t)cap) {
+            if (lane == 0) atomicExch(out_count + 1, 1ull);  // overflow flag: caller falls back to the exact path
+            n = cap;
+        }
+        for (uint32_t s = lane; s < n; s += 32) {
+            const int64_t i = ids[j * cap + s];
+            const double c = scores[j * cap + s];
+            if (i < j && doc_idx[i] != doc_idx[j] && c >= thr) {
+                unsigned long long slot = atomicAdd(out_count, 1ull);
+                if ((int64_t)slot < out_cap) {
+                    out_i[slot] = (int32_t)i;
+                    out_j[slot] = (int32_t)j;
+                    out_sim[slot] = c;
+                }
             }
         }
     }
@@ -173,15 +176,16 @@ static PairWs carve_pair(void *base, int64_t m)
         p += align_up(n, 256);
         return r;
     };
-    w.sq = (double *)take((size_t)(m > 0 ? m : 1) * 8);
-    w.inv_norm = (float *)take((size_t)(m > 0 ? m : 1) * 4);
-    w.qnorm = (float *)take(kPairBlock * 4);
-    w.inv_qnorm = (float *)take(kPairBlock * 4);
-    w.thr_key = (uint32_t *)take(kPairBlock * 4);
-    w.cnt = (uint32_t *)take(kPairBlock * 4);
-    w.cand = (int32_t *)take((size_t)kPairBlock * kPairCap * 4);
-    w.scores = (double *)take((size_t)kPairBlock * kPairCap * 8);
-    w.ids = (int64_t *)take((size_t)kPairBlock * kPairCap * 8);
+    const size_t mm = (size_t)(m > 0 ? m : 1);
+    w.sq = (double *)take(mm * 8);
+    w.inv_norm = (float *)take(mm * 4);
+    w.qnorm = (float *)take(mm * 4);
+    w.inv_qnorm = (float *)take(mm * 4);
+    w.thr_key = (uint32_t *)take(mm * 4);
+    w.cnt = (uint32_t *)take(mm * 4);
+    w.cand = (int32_t *)take(mm * kPairCap * 4);
+    w.scores = (double *)take(mm * kPairCap * 8);
+    w.ids = (int64_t *)take(mm * kPairCap * 8);
     w.bytes = (size_t)(p - (uint8_t *)base);
     return w;
 }
@@ -205,6 +209,7 @@ extern "C" int orag_pairwise_cosine_threshold_tc(const float *d_emb, int64_t m, 
     ORAG_REQUIRE(d_emb && d_doc_idx && d_out_i && d_out_j && d_out_sim && d_out_count && m >= 0 && dim > 0 && cap >= 0,
                  "pairwise_tc");
     ORAG_REQUIRE(dim % 32 == 0 && m < ((int64_t)1 << 31), "dim % 32 == 0");
+    ORAG_REQUIRE(m <= 256 * 1024, "pairwise_tc: at most 262144 rows (triangular tile index)");
     ORAG_REQUIRE(threshold > (double)kPairEps, "tensor-core path needs threshold > first-pass error bound");
     if (workspace_bytes < orag_pairwise_tc_workspace_bytes(m, dim) || !d_workspace) {
         set_error("pairwise_tc: workspace too small");
@@ -219,35 +224,35 @@ extern "C" int orag_pairwise_cosine_threshold_tc(const float *d_emb, int64_t m, 
     ORAG_LAUNCH_CHECK();
     int rc = orag_row_inv_norms(d_emb, m, dim, w.inv_norm, st);
     if (rc) return rc;
-    for (int64_t j0 = 0; j0 < m; j0 += kPairBlock) {
-        const int nq = (int)(m - j0 < kPairBlock ? m - j0 : kPairBlock);
-        rc = tc::launch_query_norms(w.sq + j0, nq, w.qnorm, w.inv_qnorm, st);
-        if (rc) return rc;
-        pair_thr_init_kernel<<<1, 256, 0, st>>>(w.qnorm, nq, (float)threshold, w.thr_key, w.cnt);
-        ORAG_LAUNCH_CHECK();
-        tc::ScanParams p{};
-        p.n_queries = nq;
-        p.inv_norm = w.inv_norm;
-        p.thr_key = w.thr_key;
-        p.cnt = w.cnt;
-        p.hist = nullptr;
-        p.cand = w.cand;
-        p.cap = kPairCap;
-        p.qnorm = w.qnorm;
-        p.inv_qnorm = w.inv_qnorm;
-        p.margin = kPairEps + 1e-6f;  // one-sided: cos >= t  =>  first pass >= t - eps (+ float(threshold) rounding)
-        p.k = 0x7fffffff;
-        p.fixed_thr = 1;
-        p.row_begin = 0;
-        p.row_end = j0 + nq;          // only rows i < j can pair with query row j
-        p.dense = 0;
-        rc = tc::launch_scan(false, d_emb, m, d_emb + j0 * dim, dim, p, st);
-        if (rc) return rc;
-        rc = launch_rescore(d_emb, dim, 0, d_emb + j0 * dim, w.sq + j0, w.cand, w.cnt, kPairCap, nq, w.scores, w.ids, st);
-        if (rc) return rc;
-        pair_filter_kernel<<<nq, 256, 0, st>>>(w.scores, w.ids, w.cnt, kPairCap, nq, j0, d_doc_idx, threshold, cap,
-                                               d_out_i, d_out_j, d_out_sim, d_out_count);
-        ORAG_LAUNCH_CHECK();
-    }
+    rc = tc::launch_query_norms(w.sq, (int)m, w.qnorm, w.inv_qnorm, st);
+    if (rc) return rc;
+    pair_thr_init_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(w.qnorm, m, (float)threshold, w.thr_key, w.cnt);
+    ORAG_LAUNCH_CHECK();
+    // ONE tensor-core launch over the triangular (query block, row tile) space
+    tc::ScanParams p{};
+    p.n_queries = (int)m;
+    p.inv_norm = w.inv_norm;
+    p.thr_key = w.thr_key;
+    p.cnt = w.cnt;
+    p.hist = nullptr;
+    p.cand = w.cand;
+    p.cap = kPairCap;
+    p.qnorm = w.qnorm;
+    p.inv_qnorm = w.inv_qnorm;
+    p.margin = kPairEps + 1e-6f;  // one-sided: cos >= t  =>  first pass >= t - eps (+ float(threshold) rounding)
+    p.k = 0x7fffffff;
+    p.fixed_thr = 1;
+    p.pair_mode = 1;
+    p.row_begin = 0;
+    p.row_end = m;
+    p.dense = 0;
+    rc = tc::launch_scan(false, d_emb, m, d_emb, dim, p, st);
+    if (rc) return rc;
+    // float64 re-score of every surviving (i, j) in the reference's arithmetic, then the exact filter
+    rc = launch_rescore(d_emb, dim, 0, d_emb, w.sq, w.cand, w.cnt, kPairCap, (int)m, w.scores, w.ids, st);
+    if (rc) return rc;
+    pair_filter_kernel<<<sm_count() * 8, 256, 0, st>>>(w.scores, w.ids, w.cnt, kPairCap, m, d_doc_idx, threshold, cap,
+                                                       d_out_i, d_out_j, d_out_sim, d_out_count);
+    ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }
