@@ -348,3 +348,80 @@ def test_pairwise_tensor_core_equals_exact(eng):
     c = eng.pairwise_cosine_threshold(_t(emb[:400]), _t(doc[:400]), 0.85, mode="tc")
     assert np.array_equal(c[0].cpu().numpy(), wi) and np.array_equal(c[1].cpu().numpy(), wj)
     assert np.array_equal(_bits(c[2].cpu().numpy()), _bits(ws))
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_cosine_tc_ragged_sizes_and_batches(eng, mode):
+    """N not a multiple of the 128-row tile, B > 256 (two query groups), B = 1, k = 1 and k = 64, id base."""
+    n, dim = 4097 + 128 * 3 + 5, 192
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim, 3)
+    idx = eng.CosineIndex(_t(corpus), row_id_base=10_000_000_000, mode=mode)
+    for nq, k in [(300, 10), (1, 1), (7, 64)]:
+        queries = syn.query_embeddings(nq, n, dim, dup_per_mille=3)
+        ids, sc = idx.topk(_t(queries), k)
+        sub = sorted(set([0, nq - 1, nq // 2, min(nq - 1, 257)]))
+        wi, ws = oracle.cosine_topk(corpus, queries[sub], k, id_base=10_000_000_000)
+        assert np.array_equal(ids.cpu().numpy()[sub], wi), (mode, nq, k)
+        assert np.array_equal(_bits(sc.cpu().numpy()[sub]), _bits(ws)), (mode, nq, k)
+
+
+def test_cosine_candidate_overflow_falls_back_to_exact_scan(eng):
+    """6000 identical rows tie for the top: more near-ties than candidate slots -> status bit -> exact scan."""
+    n, dim = 12000, 64
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim)
+    corpus[3000:9000] = corpus[11]
+    queries = np.stack([corpus[11], syn.query_embeddings(1, n, dim)[0]]).astype(np.float32)
+    idx = eng.CosineIndex(_t(corpus), mode="tf32")
+    ids, sc = idx.topk(_t(queries), 10)
+    wi, ws = oracle.cosine_topk(corpus, queries, 10)
+    assert np.array_equal(ids.cpu().numpy(), wi) and np.array_equal(_bits(sc.cpu().numpy()), _bits(ws))
+    assert wi[0].tolist() == [11] + list(range(3000, 3009))  # ties broken by chunk id
+    raw_ids, _ = idx.topk(_t(queries), 10, check_overflow=False)  # without the fallback the flag must be set
+    st = []
+    idx.topk(_t(queries), 10, check_overflow=False, status_out=st)
+    assert int(st[0][0]) == 1 and int(st[0][1]) == 0
+
+
+def test_cosine_k_larger_than_corpus_and_auto_mode(eng):
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, 6, 100)  # dim % 32 != 0 -> auto picks the exact path
+    idx = eng.CosineIndex(_t(corpus))
+    assert idx.mode == "exact"
+    ids, sc = idx.topk(_t(syn.query_embeddings(2, 6, 100)), 10)
+    assert (ids[:, 6:] == -1).all() and (ids[:, :6] >= 0).all() and (sc[:, 6:] == 0).all()
+    assert sorted(ids[0, :6].cpu().tolist()) == list(range(6))
+
+
+def test_bm25_long_and_degenerate_queries(eng):
+    """Queries longer than 32 terms (chunked path), all-OOV, empty, single query, duplicate-heavy."""
+    ix, orc, _, _ = _bm25_case(6000, 800, 10, 80, 1, 5, 512, eng)
+    rng = np.random.default_rng(4)
+    mt = 48
+    rows = [rng.integers(0, 800, 48), rng.integers(300, 800, 33), np.full(5, -1), np.zeros(0, int),
+            np.array([7, 7, 7, 7, 9]), rng.integers(0, 20, 40)]
+    qt = np.full((len(rows), mt), -2, dtype=np.int32)
+    ql = np.zeros(len(rows), dtype=np.int32)
+    for i, r in enumerate(rows):
+        qt[i, :len(r)] = r
+        ql[i] = len(r)
+    for force in ("sparse", "dense"):
+        if force == "sparse" and ix.has_negative_idf:
+            continue
+        ids, sc, mx = ix.topk(_t(qt), _t(ql), 10, force=force)
+        for b in range(len(rows)):
+            norm, m = orc.scores(qt[b, :ql[b]])
+            wi, wv = oracle.topk(norm, 10, id_base=100)
+            assert np.array_equal(ids[b].cpu().numpy(), wi), (force, b)
+            assert np.array_equal(_bits(sc[b].cpu().numpy()), _bits(wv)), (force, b)
+            assert float(mx[b]) == m
+    one = ix.topk(_t(qt[:1]), _t(ql[:1]), 10, force="sparse" if not ix.has_negative_idf else "dense")
+    assert torch.equal(one[0][0], ids[0])
+
+
+def test_dense_topk_normalisation_edges(eng):
+    s = torch.tensor([[0.0, 0.0, 0.0, 0.0], [-1.0, -2.0, -0.5, -3.0], [2.0, 4.0, 4.0, 1.0]], dtype=torch.float64,
+                     device=DEV)
+    ids, sc, mx = eng.dense_topk(s, 3, normalize=True)
+    assert ids.cpu().tolist() == [[0, 1, 2], [2, 0, 1], [1, 2, 0]]
+    assert mx.cpu().tolist() == [1.0, 1.0, 4.0]  # max <= 0 -> divisor 1.0 (rag/retrieval.py:344)
+    assert sc.cpu().tolist() == [[0.0, 0.0, 0.0], [-0.5, -1.0, -2.0], [1.0, 1.0, 0.5]]
