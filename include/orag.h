@@ -119,7 +119,11 @@ int orag_cosine_firstpass_dense(const float *d_corpus, const float *d_inv_norm, 
  * BM25 top-k over a GPU-resident, doc-range-tiled inverted index.  Replaces
  * rank_bm25.BM25Okapi.get_scores + the normalisation/sort glue at
  * rag/retrieval.py:324-347, 320.  Bit-exact float64 (no FMA contraction, query
- * terms accumulated per document in query order).
+ * terms accumulated per document in query order).  Two candidate paths produce the same result:
+ *   - float64 scatter of every posting (bm25.cu), and
+ *   - when the index carries d_postings_r16: an fp32 MaxScore first pass (bm25_ms.cu) that only scatters the
+ *     postings of a query's "essential" terms, looks the others up for the docs that could still reach the
+ *     running threshold, and re-scores the surviving candidates in the float64 arithmetic above.
  * ------------------------------------------------------------------------- */
 typedef struct orag_bm25_index {
     int64_t n_docs;                /* docs in this shard */
@@ -136,6 +140,12 @@ typedef struct orag_bm25_index {
     const double *d_t4_table;      /* [max_doc_len + 1] k1 * (1 - b + b * dl / avgdl), global avgdl */
     const double *d_r_table;       /* [max_doc_len + 1, 4] tf*(k1+1) / (tf + t4[dl]) for tf = 1..4 */
     const double *d_idf;           /* [vocab] global idf incl. epsilon floor; 0 for unseen terms */
+    /* Optional first-pass view (both NULL = exact tile kernel only).  Same order and offsets as d_postings:
+     * (doc_in_tile << 16) | fp16 bits of r = tf*(k1+1)/(tf + t4[dl]) rounded to nearest (every r must be a
+     * NORMAL fp16 number); the array carries 4 trailing padding elements and is 16-byte aligned.
+     * d_term_max_r[t] = max over this shard's postings of term t of that fp16 value (0 if none). */
+    const uint32_t *d_postings_r16;
+    const float *d_term_max_r;     /* [vocab] */
 } orag_bm25_index_t;
 
 /*   d_query_terms int32 [n_queries, max_terms], entries < 0 or >= vocab are OOV / padding
@@ -147,6 +157,8 @@ typedef struct orag_bm25_index {
 #define ORAG_BM25_NORMALIZE 1    /* divide by the max raw score (rag/retrieval.py:343-345) */
 #define ORAG_BM25_FORCE_SPARSE 2 /* candidate path even for small corpora (tests) */
 #define ORAG_BM25_FORCE_DENSE 4  /* dense accumulate + exact select (small N, negative idf, fallback) */
+#define ORAG_BM25_EXACT_TILES 8  /* candidate path through the float64 scatter kernel even when the index carries
+                                    the fp16 first-pass view (A/B tests; queries longer than 32 terms use it anyway) */
 size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *index, int n_queries, int k, int flags);
 int orag_bm25_topk(const orag_bm25_index_t *index, int64_t doc_id_base, const int32_t *d_query_terms,
                    const int32_t *d_query_lens, int n_queries, int max_terms, int k, int flags,

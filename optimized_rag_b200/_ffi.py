@@ -12,7 +12,7 @@ LIB_PATH = Path(__file__).resolve().parent / "csrc" / "liborag.so"
 
 ORAG_COS_EXACT, ORAG_COS_TF32, ORAG_COS_BF16 = 0, 1, 2
 ORAG_STATUS_OVERFLOW = 1
-ORAG_BM25_NORMALIZE, ORAG_BM25_FORCE_SPARSE, ORAG_BM25_FORCE_DENSE = 1, 2, 4
+ORAG_BM25_NORMALIZE, ORAG_BM25_FORCE_SPARSE, ORAG_BM25_FORCE_DENSE, ORAG_BM25_EXACT_TILES = 1, 2, 4, 8
 
 # every symbol include/orag.h declares (tests check the .so exports each one)
 SYMBOLS = [
@@ -48,6 +48,8 @@ class Bm25IndexStruct(Structure):
         ("d_t4_table", c_void_p),
         ("d_r_table", c_void_p),
         ("d_idf", c_void_p),
+        ("d_postings_r16", c_void_p),
+        ("d_term_max_r", c_void_p),
     ]
 
 

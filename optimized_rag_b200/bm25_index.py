@@ -7,6 +7,9 @@ Layout consumed by csrc/bm25.cu (see include/orag.h `orag_bm25_index_t`):
   tile_term_off int32 [n_tiles, V+1] offsets of each term's run inside its tile
   doc_len       int32 [n_docs]; t4_table float64 [max_dl+1] = k1*(1 - b + b*dl/avgdl) (global avgdl)
   idf           float64 [V]         global idf with the epsilon floor (rank_bm25 0.2.2 BM25Okapi._calc_idf)
+  postings_r16  uint32 [(doc_in_tile << 16) | fp16(tf*(k1+1)/(tf + t4[dl]))], same order/offsets as postings
+                (+4 padding elements): the view the fp32 MaxScore first pass streams (csrc/bm25_ms.cu)
+  term_max_r    float32 [V]         max fp16 r over this shard's postings of each term (MaxScore upper bounds)
 
 Global statistics (N, avgdl, df, first-seen order -> idf, eps) follow the reference's
 `BM25Okapi(tokenized_corpus)` construction at rag/retrieval.py:338; they are computed over the WHOLE
@@ -108,7 +111,8 @@ class Bm25Index:
     """One shard of the inverted index, resident on `device`."""
 
     def __init__(self, doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, tile_docs: int = 1024,
-                 stats: Bm25Stats | None = None, doc_id_base: int = 0, chunk_docs: int = 1 << 20):
+                 stats: Bm25Stats | None = None, doc_id_base: int = 0, chunk_docs: int = 1 << 20,
+                 first_pass: bool = True):
         assert doc_off.dtype == torch.int64 and tokens.dtype == torch.int32
         assert tile_docs & (tile_docs - 1) == 0 and 32 <= tile_docs <= 2048
         dev = tokens.device
@@ -141,7 +145,9 @@ class Bm25Index:
         V1 = self.vocab + 1
         T = self.tile_docs
         chunk_docs = max(T, chunk_docs // T * T)
-        post_chunks, cnt_chunks = [], []
+        post_chunks, cnt_chunks, r16_chunks = [], [], []
+        term_max = torch.zeros(self.vocab, dtype=torch.float32, device=dev)
+        r16_ok = first_pass and not self.has_negative_idf
         for d0 in range(0, self.n_docs, chunk_docs):
             d1 = min(self.n_docs, d0 + chunk_docs)
             lo, hi = int(doc_off[d0].item()), int(doc_off[d1].item())
@@ -159,12 +165,33 @@ class Bm25Index:
                 raise ValueError("term frequency above 65535 is not representable in the posting format")
             post_chunks.append((((key % T) << 16) | tf).to(torch.int32))
             cnt_chunks.append(torch.bincount(key // T, minlength=n_t * self.vocab))
+            if r16_ok:
+                # first-pass view: r in fp16 (round to nearest) next to the doc id; all r must be normal fp16
+                tt = key // T
+                doc_abs = (tt // self.vocab) * T + (key % T) + d0
+                tf_f = tf.double()
+                r = tf_f * (K1 + 1) / (tf_f + self.t4_table[self.dl[doc_abs].long()])
+                r16 = r.to(torch.float32).to(torch.float16)
+                if float(r16.min().item()) < 6.2e-5:
+                    r16_ok = False
+                else:
+                    term_max.scatter_reduce_(0, tt % self.vocab, r16.float(), reduce="amax", include_self=True)
+                    r16_chunks.append((((key % T) << 16) | (r16.view(torch.int16).long() & 0xFFFF)).to(torch.int32))
+                del tt, doc_abs, tf_f, r, r16
             del key, tf
         if post_chunks:
             self.postings = torch.cat(post_chunks)
         else:
             self.postings = torch.zeros(1, dtype=torch.int32, device=dev)
         del post_chunks
+        self.postings_r16 = None
+        self.term_max_r = None
+        if r16_ok and r16_chunks:
+            r16_chunks.append(torch.zeros(4, dtype=torch.int32, device=dev))  # 16-byte over-read padding
+            self.postings_r16 = torch.cat(r16_chunks)
+            self.term_max_r = term_max
+            assert self.postings_r16.data_ptr() % 16 == 0
+        del r16_chunks
         if cnt_chunks:
             counts = torch.cat(cnt_chunks).view(self.n_tiles, self.vocab)
         else:
@@ -185,7 +212,9 @@ class Bm25Index:
             has_negative_idf=int(self.has_negative_idf),
             d_tile_base=self.tile_base.data_ptr(), d_tile_term_off=self.tile_term_off.data_ptr(),
             max_doc_len=self.max_dl, reserved=0, d_postings=self.postings.data_ptr(), d_doc_len=self.dl.data_ptr(),
-            d_t4_table=self.t4_table.data_ptr(), d_r_table=self.r_table.data_ptr(), d_idf=self.idf.data_ptr())
+            d_t4_table=self.t4_table.data_ptr(), d_r_table=self.r_table.data_ptr(), d_idf=self.idf.data_ptr(),
+            d_postings_r16=self.postings_r16.data_ptr() if self.postings_r16 is not None else None,
+            d_term_max_r=self.term_max_r.data_ptr() if self.term_max_r is not None else None)
         self._ws = None
 
     @property
@@ -209,7 +238,8 @@ class Bm25Index:
         assert query_terms.is_cuda and query_terms.is_contiguous() and query_lens.is_contiguous()
         Bq, mt = query_terms.shape
         flags = (_ffi.ORAG_BM25_NORMALIZE if normalize else 0)
-        flags |= {None: 0, "sparse": _ffi.ORAG_BM25_FORCE_SPARSE, "dense": _ffi.ORAG_BM25_FORCE_DENSE}[force]
+        flags |= {None: 0, "sparse": _ffi.ORAG_BM25_FORCE_SPARSE, "dense": _ffi.ORAG_BM25_FORCE_DENSE,
+                  "exact_tiles": _ffi.ORAG_BM25_FORCE_SPARSE | _ffi.ORAG_BM25_EXACT_TILES}[force]
         ids = torch.empty((Bq, k), dtype=torch.int64, device=self.device)
         sc = torch.empty((Bq, k), dtype=torch.float64, device=self.device)
         mx = torch.empty(Bq, dtype=torch.float64, device=self.device)

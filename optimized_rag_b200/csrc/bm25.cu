@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "select.cuh"
 #include "exact.cuh"
+#include "bm25_shared.cuh"
 
 namespace orag {
 namespace bm25 {
@@ -29,9 +30,6 @@ namespace bm25 {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxTerms = 64;
-constexpr int kHistBins = 8192;
-constexpr int kBinBase = (1023 - 20) << 7;  // bins start at 2^-20, 128 bins per octave (0.54 % wide)
-
 struct Params {
     orag_bm25_index_t ix;
     const int32_t *q_terms;  // [n_queries, max_terms]
@@ -53,16 +51,6 @@ struct Params {
     int q_split;                   // work items per tile (slices of the query batch), >= 1
 };
 
-__device__ __forceinline__ int score_bin(double v)
-{
-    long long e = (__double_as_longlong(v) >> 45) - kBinBase;
-    return e < 0 ? 0 : (e > kHistBins - 1 ? kHistBins - 1 : (int)e);
-}
-__device__ __forceinline__ unsigned long long bin_floor_bits(int b)
-{
-    return (unsigned long long)(b + kBinBase) << 45;
-}
-
 // Candidate emission + threshold tightening.  Every 8th emission of a query re-derives its
 // threshold from the log-scale histogram, scanning down from the highest occupied bin in batches
 // of 16 bins fetched with four independent 16-byte loads.
@@ -78,27 +66,7 @@ __device__ __noinline__ void emit(const Params &p, int q, int32_t doc, double v)
     atomicAdd(h + bin, 1u);
     const int old_top = (int)atomicMax(p.topbin + q, (uint32_t)bin);
     if ((slot & 7u) != 7u) return;
-    const int hi = old_top > bin ? old_top : bin;
-    const uint4 *h4 = reinterpret_cast<const uint4 *>(h);
-    const uint4 zero = make_uint4(0, 0, 0, 0);
-    uint32_t acc = 0;
-    int found = -1;
-    for (int c = hi >> 2; c >= 0 && found < 0; c -= 4) {
-        const uint4 w0 = __ldcg(h4 + c);
-        const uint4 w1 = c >= 1 ? __ldcg(h4 + c - 1) : zero;
-        const uint4 w2 = c >= 2 ? __ldcg(h4 + c - 2) : zero;
-        const uint4 w3 = c >= 3 ? __ldcg(h4 + c - 3) : zero;
-        const uint32_t vals[16] = {w0.w, w0.z, w0.y, w0.x, w1.w, w1.z, w1.y, w1.x,
-                                   w2.w, w2.z, w2.y, w2.x, w3.w, w3.z, w3.y, w3.x};
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            acc += vals[j];
-            if (found < 0 && acc >= (uint32_t)p.k) found = 4 * c + 3 - j;
-        }
-    }
-    // lower edge of the k-th best's bin, minus 4 ulps: also keeps docs whose NORMALISED score could tie
-    // with the k-th best (x/m == y/m in float64 only for raw scores a couple of ulps apart)
-    if (found >= 1) atomicMax(p.thr_bits + q, bin_floor_bits(found) - 4ull);
+    tighten_threshold(h, old_top > bin ? old_top : bin, p.k, p.thr_bits + q);
 }
 
 constexpr int kRTf = 4;      // r = tf*(k1+1)/(tf + t4[dl]) is tabulated for tf = 1..kRTf
@@ -356,36 +324,6 @@ __global__ void __launch_bounds__(kThreads, 2) bm25_tile_kernel(const __grid_con
     }
 }
 
-// Exact score of one doc for one query (binary search in each term's run); used only for the
-// rare zero-fill at the end of the sparse path.
-__device__ double score_doc(const orag_bm25_index_t &ix, const int32_t *terms, int nt, int64_t doc)
-{
-    const int T = ix.tile_docs;
-    const int tile = (int)(doc / T);
-    const uint32_t want = (uint32_t)(doc - (int64_t)tile * T);
-    const uint32_t *tile_post = ix.d_postings + ix.d_tile_base[tile];
-    const int32_t *toff = ix.d_tile_term_off + (int64_t)tile * (ix.vocab + 1);
-    const double t4 = ix.d_t4_table[ix.d_doc_len[doc]];
-    double s = 0.0;
-    for (int i = 0; i < nt; ++i) {
-        int t = terms[i];
-        if (t < 0 || t >= ix.vocab) continue;
-        double idf = ix.d_idf[t];
-        if (idf == 0.0) continue;
-        int lo = toff[t], hi = toff[t + 1];
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if ((tile_post[mid] >> 16) < want) lo = mid + 1; else hi = mid;
-        }
-        if (lo < toff[t + 1] && (tile_post[lo] >> 16) == want) {
-            double tf = (double)(tile_post[lo] & 0xFFFFu);
-            double c = __dmul_rn(idf, __ddiv_rn(__dmul_rn(tf, 2.5), __dadd_rn(tf, t4)));
-            s = __dadd_rn(s, c);
-        }
-    }
-    return s;
-}
-
 // One CTA per query: exact top-k over the candidate list by (score/max desc, id asc), then
 // zero-score fill (docs untouched by the query rank after all positive ones, in id order).
 __global__ void __launch_bounds__(1024) finalize_kernel(const __grid_constant__ Params p, int64_t doc_id_base, int normalize,
@@ -401,55 +339,10 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const __grid_constant__ 
         if (status && threadIdx.x == 0) status[q] |= ORAG_STATUS_OVERFLOW;
         n = p.cap;
     }
-    const int32_t *cd = p.cand_doc + (int64_t)q * p.cap;
-    const double *cs = p.cand_score + (int64_t)q * p.cap;
-    double mx = -INFINITY;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) mx = fmax(mx, cs[i]);
-    mx = block_max(mx, dscratch);
-    const double raw_max = mx > 0.0 ? mx : 0.0;
-    const double m = mx > 0.0 ? mx : 1.0;
-    if (out_max && threadIdx.x == 0) out_max[q] = normalize ? m : raw_max;
-    double prev_s = INFINITY;
-    int64_t prev_id = -1;
-    int found = 0;
-    for (int r = 0; r < k; ++r) {
-        Pick best;
-        best.valid = 0; best.s = 0.0; best.id = 0;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const int64_t id = doc_id_base + cd[i];
-            const double v = normalize ? __ddiv_rn(cs[i], m) : cs[i];
-            if (r > 0 && !ranks_before(prev_s, prev_id, v, id)) continue;
-            Pick c;
-            c.s = v; c.id = id; c.valid = 1;
-            best = better(best, c);
-        }
-        best = block_best(best, scratch);
-        if (!best.valid) break;
-        if (threadIdx.x == 0) {
-            out_ids[(int64_t)q * k + r] = best.id;
-            out_scores[(int64_t)q * k + r] = best.s;
-        }
-        prev_s = best.s;
-        prev_id = best.id;
-        ++found;
-    }
-    if (found < k && threadIdx.x == 0) {
-        // fewer than k docs with a positive score: the rest of the list is zero-score docs in id order
-        const int nt = min(p.q_lens[q], p.max_terms);
-        const int32_t *terms = p.q_terms + (int64_t)q * p.max_terms;
-        int r = found;
-        for (int64_t d = 0; d < p.ix.n_docs && r < k; ++d) {
-            if (score_doc(p.ix, terms, nt, d) == 0.0) {
-                out_ids[(int64_t)q * k + r] = doc_id_base + d;
-                out_scores[(int64_t)q * k + r] = 0.0;
-                ++r;
-            }
-        }
-        for (; r < k; ++r) {
-            out_ids[(int64_t)q * k + r] = -1;
-            out_scores[(int64_t)q * k + r] = 0.0;
-        }
-    }
+    select_from_list(p.ix, p.q_terms + (int64_t)q * p.max_terms, min(p.q_lens[q], p.max_terms), k,
+                     p.cand_doc + (int64_t)q * p.cap, p.cand_score + (int64_t)q * p.cap, n, doc_id_base, normalize,
+                     out_ids + (int64_t)q * k, out_scores + (int64_t)q * k, out_max ? out_max + q : nullptr, scratch,
+                     dscratch);
 }
 
 __global__ void init_state_kernel(unsigned long long *thr_bits, uint32_t *cnt, uint32_t *hist, uint32_t *topbin,
@@ -522,6 +415,8 @@ extern "C" size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *ix, int n_q
     if (use_dense(ix, n_queries, flags))
         return orag::align_up(dense_chunk_queries(ix, n_queries) * (size_t)(ix->n_docs > 0 ? ix->n_docs : 1) * 8, 256);
     const size_t cap = sparse_cap(n_queries);
+    const size_t ms = (ix->d_postings_r16 && !(flags & ORAG_BM25_EXACT_TILES))
+                          ? orag::bm25::ms_workspace_bytes(ix, n_queries) : 0;
     size_t b = 0;
     b += orag::align_up((size_t)n_queries * 8, 256);                        // thr_bits
     b += orag::align_up((size_t)n_queries * 4, 256);                        // cnt
@@ -529,7 +424,7 @@ extern "C" size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *ix, int n_q
     b += orag::align_up((size_t)n_queries * orag::bm25::kHistBins * 4, 256);  // hist
     b += orag::align_up((size_t)n_queries * cap * 4, 256);                  // cand_doc
     b += orag::align_up((size_t)n_queries * cap * 8, 256);                  // cand_score
-    return b;
+    return b > ms ? b : ms;
 }
 
 static int launch_tiles(const Params &p, bool dense, cudaStream_t st)
@@ -633,7 +528,10 @@ extern "C" int orag_bm25_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, 
         return ORAG_OK;
     }
 
-    // ---- sparse (candidate) path ----
+    // ---- sparse (candidate) paths ----
+    if (orag::bm25::ms_eligible(ix, max_terms, flags))
+        return orag::bm25::ms_topk(ix, doc_id_base, d_query_terms, d_query_lens, n_queries, max_terms, k, normalize,
+                                   d_out_ids, d_out_scores, d_out_max, d_out_status, d_workspace, st);
     const int cap = sparse_cap(n_queries);
     uint8_t *w = (uint8_t *)d_workspace;
     Params p{};

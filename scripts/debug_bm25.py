@@ -24,17 +24,27 @@ qt_d, ql_d = torch.from_numpy(qt).to(dev), torch.from_numpy(ql).to(dev)
 L = _ffi.lib()
 L.orag_profile_enable(1)
 a, b = ctypes.c_float(), ctypes.c_float()
-for it in range(3):
-    ids, sc, mx = ix.topk(qt_d, ql_d, 10, force="sparse", check_overflow=False)
-    torch.cuda.synchronize()
-    L.orag_profile_read(ctypes.byref(a), ctypes.byref(b))
-    ws = ix._ws
-    off = 0
-    al = lambda x: (x + 255) // 256 * 256
-    off += al(B * 8)
-    cnt = ws[off:off + B * 4].view(torch.int32).cpu().numpy()
-    print(f"iter {it}: sparse tile kernel {b.value:.3f} ms; emissions per query: min {cnt.min()} mean {cnt.mean():.0f} "
-          f"max {cnt.max()} total {cnt.sum()}; postings(6B) {ix.posting_bytes(qt_d, ql_d) / 6:.3e}")
+res = {}
+for force in ("exact_tiles", "sparse"):
+    for it in range(3):
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        ids, sc, mx = ix.topk(qt_d, ql_d, 10, force=force, check_overflow=False, status_out=(st := []))
+        t1.record()
+        torch.cuda.synchronize()
+        L.orag_profile_read(ctypes.byref(a), ctypes.byref(b))
+        ws = ix._ws
+        off = 0
+        al = lambda x: (x + 255) // 256 * 256
+        off += al(B * 8)
+        cnt = ws[off:off + B * 4].view(torch.int32).cpu().numpy()
+        print(f"{force} iter {it}: tile kernel {b.value:.3f} ms, whole call {t0.elapsed_time(t1):.3f} ms; emissions per "
+              f"query: min {cnt.min()} mean {cnt.mean():.0f} max {cnt.max()} total {cnt.sum()}; overflow "
+              f"{int((st[0] != 0).sum())}; postings(6B) {ix.posting_bytes(qt_d, ql_d) / 6:.3e}", flush=True)
+    res[force] = (ids, sc, mx)
+print("ms == exact_tiles:", all(torch.equal(x, y) for x, y in zip(res["sparse"], res["exact_tiles"])))
+if "--no-dense" in sys.argv:
+    sys.exit(0)
 ids2, sc2, mx2 = ix.topk(qt_d, ql_d, 10, force="dense")
 torch.cuda.synchronize()
 L.orag_profile_read(ctypes.byref(a), ctypes.byref(b))

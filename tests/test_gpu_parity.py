@@ -158,8 +158,8 @@ def test_bm25_golden_bit_exact(eng, golden):
             m = raw[i].max() if raw[i].max() > 0 else 1.0
             assert np.array_equal(_bits(raw[i] / m), _bits(want)), (case["name"], i)
         # and the top-k entry point, both paths, equals the oracle's ranking of those scores
-        for force in ("dense", "sparse"):
-            if force == "sparse" and ix.has_negative_idf:
+        for force in ("dense", "sparse", "exact_tiles"):
+            if force != "dense" and ix.has_negative_idf:
                 continue
             ids, sc, mx = ix.topk(_t(qt), _t(ql), 10, normalize=True, force=force)
             for i, q in enumerate(case["queries"]):
@@ -170,7 +170,7 @@ def test_bm25_golden_bit_exact(eng, golden):
                 assert np.array_equal(_bits(sc[i].cpu().numpy()[:len(wi)]), _bits(wv)), (case["name"], force, i)
 
 
-@pytest.mark.parametrize("force", ["sparse", "dense"])
+@pytest.mark.parametrize("force", ["sparse", "exact_tiles", "dense"])
 @pytest.mark.parametrize("n,vocab,lmin,lmax,nq,min_rank,tile", [
     (20000, 5000, 20, 120, 64, 20, 2048),
     (3000, 300, 5, 60, 40, 3, 256),
@@ -180,8 +180,10 @@ def test_bm25_topk_vs_oracle(eng, force, n, vocab, lmin, lmax, nq, min_rank, til
     ix, orc, qtok, qlen = _bm25_case(n, vocab, lmin, lmax, nq, min_rank, tile, eng)
     assert ix.avgdl == orc.avgdl and ix.eps == orc.eps
     assert np.array_equal(_bits(ix.idf.cpu().numpy()), _bits(orc.idf))
-    if force == "sparse" and ix.has_negative_idf:
+    if force != "dense" and ix.has_negative_idf:
         pytest.skip("negative idf -> dense path only")
+    if force == "sparse":
+        assert ix.postings_r16 is not None  # the MaxScore first pass is the path under test
     for normalize in (True, False):
         ids, sc, mx = ix.topk(_t(qtok), _t(qlen), 10, normalize=normalize, force=force)
         for b in range(nq):
@@ -201,7 +203,7 @@ def test_bm25_rare_terms_zero_fill(eng):
     rare = [int(t) for t in np.nonzero((df > 0) & (df < 4))[0][:3]]
     qt = np.array([rare + [-1], [rare[0], rare[0], -2, -2], [-1, -1, -2, -2]], dtype=np.int32)
     ql = np.array([4, 2, 2], dtype=np.int32)
-    for force in ("sparse", "dense"):
+    for force in ("sparse", "exact_tiles", "dense"):
         ids, sc, _ = ix.topk(_t(qt), _t(ql), 10, force=force)
         for b in range(3):
             norm, _ = orc.scores(qt[b, :ql[b]])
@@ -404,8 +406,8 @@ def test_bm25_long_and_degenerate_queries(eng):
     for i, r in enumerate(rows):
         qt[i, :len(r)] = r
         ql[i] = len(r)
-    for force in ("sparse", "dense"):
-        if force == "sparse" and ix.has_negative_idf:
+    for force in ("sparse", "exact_tiles", "dense"):
+        if force != "dense" and ix.has_negative_idf:
             continue
         ids, sc, mx = ix.topk(_t(qt), _t(ql), 10, force=force)
         for b in range(len(rows)):
