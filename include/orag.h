@@ -140,12 +140,17 @@ typedef struct orag_bm25_index {
     const double *d_t4_table;      /* [max_doc_len + 1] k1 * (1 - b + b * dl / avgdl), global avgdl */
     const double *d_r_table;       /* [max_doc_len + 1, 4] tf*(k1+1) / (tf + t4[dl]) for tf = 1..4 */
     const double *d_idf;           /* [vocab] global idf incl. epsilon floor; 0 for unseen terms */
-    /* Optional first-pass view (both NULL = exact tile kernel only).  Same order and offsets as d_postings:
+    /* Optional first-pass view (pointers NULL = float64 scatter kernel only): a second tiling of the same
+     * postings with tiles of fp_tile_docs docs (power of two, 32..16384),
      * (doc_in_tile << 16) | fp16 bits of r = tf*(k1+1)/(tf + t4[dl]) rounded to nearest (every r must be a
-     * NORMAL fp16 number); the array carries 4 trailing padding elements and is 16-byte aligned.
+     * NORMAL fp16 number), 16-byte aligned, ascending doc within (tile, term).
      * d_term_max_r[t] = max over this shard's postings of term t of that fp16 value (0 if none). */
     const uint32_t *d_postings_r16;
-    const float *d_term_max_r;     /* [vocab] */
+    const float *d_term_max_r;          /* [vocab] */
+    int32_t fp_tile_docs;
+    int32_t fp_n_tiles;                 /* ceil(n_docs / fp_tile_docs) */
+    const int64_t *d_fp_tile_base;      /* [fp_n_tiles + 1] */
+    const int32_t *d_fp_tile_term_off;  /* [fp_n_tiles, vocab + 1] */
 } orag_bm25_index_t;
 
 /*   d_query_terms int32 [n_queries, max_terms], entries < 0 or >= vocab are OOV / padding

@@ -50,6 +50,10 @@ class Bm25IndexStruct(Structure):
         ("d_idf", c_void_p),
         ("d_postings_r16", c_void_p),
         ("d_term_max_r", c_void_p),
+        ("fp_tile_docs", c_int32),
+        ("fp_n_tiles", c_int32),
+        ("d_fp_tile_base", c_void_p),
+        ("d_fp_tile_term_off", c_void_p),
     ]
 
 

@@ -7,8 +7,8 @@ Layout consumed by csrc/bm25.cu (see include/orag.h `orag_bm25_index_t`):
   tile_term_off int32 [n_tiles, V+1] offsets of each term's run inside its tile
   doc_len       int32 [n_docs]; t4_table float64 [max_dl+1] = k1*(1 - b + b*dl/avgdl) (global avgdl)
   idf           float64 [V]         global idf with the epsilon floor (rank_bm25 0.2.2 BM25Okapi._calc_idf)
-  postings_r16  uint32 [(doc_in_tile << 16) | fp16(tf*(k1+1)/(tf + t4[dl]))], same order/offsets as postings
-                (+4 padding elements): the view the fp32 MaxScore first pass streams (csrc/bm25_ms.cu)
+  first-pass view (csrc/bm25_ms.cu), a second tiling with tiles of fp_tile_docs (up to 16384) docs:
+  postings_r16  uint32 [(doc_in_tile << 16) | fp16(tf*(k1+1)/(tf + t4[dl]))], fp_tile_base, fp_tile_term_off
   term_max_r    float32 [V]         max fp16 r over this shard's postings of each term (MaxScore upper bounds)
 
 Global statistics (N, avgdl, df, first-seen order -> idf, eps) follow the reference's
@@ -112,7 +112,7 @@ class Bm25Index:
 
     def __init__(self, doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, tile_docs: int = 1024,
                  stats: Bm25Stats | None = None, doc_id_base: int = 0, chunk_docs: int = 1 << 20,
-                 first_pass: bool = True):
+                 first_pass: bool = True, fp_tile_docs: int | None = None):
         assert doc_off.dtype == torch.int64 and tokens.dtype == torch.int32
         assert tile_docs & (tile_docs - 1) == 0 and 32 <= tile_docs <= 2048
         dev = tokens.device
@@ -142,12 +142,46 @@ class Bm25Index:
         tf_np = np.arange(1, 5)[None, :]
         self.r_table = torch.from_numpy(np.ascontiguousarray(tf_np * (K1 + 1) / (tf_np + t4_np[:, None]))).to(dev)
 
+        # exact view: (doc_in_tile << 16) | tf over tiles of `tile_docs` docs
+        self.postings, self.tile_base, self.tile_term_off, _ = self._tiled_view(doc_off, tokens, dl, self.tile_docs,
+                                                                               chunk_docs, want_r16=False)
+        self.n_postings = int(self.tile_base[-1].item())
+        # first-pass view: (doc_in_tile << 16) | fp16(r) over (much larger) tiles of `fp_tile_docs` docs
+        self.postings_r16 = self.term_max_r = self.fp_tile_base = self.fp_tile_term_off = None
+        if fp_tile_docs is None:
+            fp_tile_docs = min(16384, max(32, 1 << max(0, (max(self.n_docs, 1) // 16 - 1).bit_length())))
+        assert fp_tile_docs & (fp_tile_docs - 1) == 0 and 32 <= fp_tile_docs <= 16384
+        self.fp_tile_docs = int(fp_tile_docs)
+        self.fp_n_tiles = (self.n_docs + self.fp_tile_docs - 1) // self.fp_tile_docs
+        if first_pass and not self.has_negative_idf and self.n_docs > 0:
+            post, base, off, tmax = self._tiled_view(doc_off, tokens, dl, self.fp_tile_docs, chunk_docs, want_r16=True)
+            if post is not None:
+                self.postings_r16, self.fp_tile_base, self.fp_tile_term_off, self.term_max_r = post, base, off, tmax
+                assert self.postings_r16.data_ptr() % 16 == 0
+
+        self.struct = _ffi.Bm25IndexStruct(
+            n_docs=self.n_docs, vocab=self.vocab, tile_docs=self.tile_docs, n_tiles=self.n_tiles,
+            has_negative_idf=int(self.has_negative_idf),
+            d_tile_base=self.tile_base.data_ptr(), d_tile_term_off=self.tile_term_off.data_ptr(),
+            max_doc_len=self.max_dl, reserved=0, d_postings=self.postings.data_ptr(), d_doc_len=self.dl.data_ptr(),
+            d_t4_table=self.t4_table.data_ptr(), d_r_table=self.r_table.data_ptr(), d_idf=self.idf.data_ptr(),
+            d_postings_r16=self.postings_r16.data_ptr() if self.postings_r16 is not None else None,
+            d_term_max_r=self.term_max_r.data_ptr() if self.term_max_r is not None else None,
+            fp_tile_docs=self.fp_tile_docs, fp_n_tiles=self.fp_n_tiles,
+            d_fp_tile_base=self.fp_tile_base.data_ptr() if self.fp_tile_base is not None else None,
+            d_fp_tile_term_off=self.fp_tile_term_off.data_ptr() if self.fp_tile_term_off is not None else None)
+        self._ws = None
+
+    def _tiled_view(self, doc_off, tokens, dl, T: int, chunk_docs: int, want_r16: bool):
+        """Postings sorted by (tile, term, doc_in_tile) for tiles of T docs -> (postings int32, tile_base int64
+        [n_tiles+1], tile_term_off int32 [n_tiles, V+1], term_max_r float32 [V] | None).  With want_r16 the low
+        half-word is fp16(tf*(k1+1)/(tf + t4[dl])) instead of tf; returns (None,)*4 if an r is not a normal fp16."""
+        dev = self.device
         V1 = self.vocab + 1
-        T = self.tile_docs
+        n_tiles = (self.n_docs + T - 1) // T
         chunk_docs = max(T, chunk_docs // T * T)
-        post_chunks, cnt_chunks, r16_chunks = [], [], []
-        term_max = torch.zeros(self.vocab, dtype=torch.float32, device=dev)
-        r16_ok = first_pass and not self.has_negative_idf
+        post_chunks, cnt_chunks = [], []
+        term_max = torch.zeros(self.vocab, dtype=torch.float32, device=dev) if want_r16 else None
         for d0 in range(0, self.n_docs, chunk_docs):
             d1 = min(self.n_docs, d0 + chunk_docs)
             lo, hi = int(doc_off[d0].item()), int(doc_off[d1].item())
@@ -163,59 +197,36 @@ class Bm25Index:
             key, tf = torch.unique(key, return_counts=True)  # sorted
             if int(tf.max().item()) > 0xFFFF:
                 raise ValueError("term frequency above 65535 is not representable in the posting format")
-            post_chunks.append((((key % T) << 16) | tf).to(torch.int32))
-            cnt_chunks.append(torch.bincount(key // T, minlength=n_t * self.vocab))
-            if r16_ok:
-                # first-pass view: r in fp16 (round to nearest) next to the doc id; all r must be normal fp16
-                tt = key // T
+            tt = key // T
+            cnt_chunks.append(torch.bincount(tt, minlength=n_t * self.vocab))
+            if not want_r16:
+                post_chunks.append((((key % T) << 16) | tf).to(torch.int32))
+            else:
                 doc_abs = (tt // self.vocab) * T + (key % T) + d0
                 tf_f = tf.double()
                 r = tf_f * (K1 + 1) / (tf_f + self.t4_table[self.dl[doc_abs].long()])
                 r16 = r.to(torch.float32).to(torch.float16)
-                if float(r16.min().item()) < 6.2e-5:
-                    r16_ok = False
-                else:
-                    term_max.scatter_reduce_(0, tt % self.vocab, r16.float(), reduce="amax", include_self=True)
-                    r16_chunks.append((((key % T) << 16) | (r16.view(torch.int16).long() & 0xFFFF)).to(torch.int32))
-                del tt, doc_abs, tf_f, r, r16
-            del key, tf
-        if post_chunks:
-            self.postings = torch.cat(post_chunks)
-        else:
-            self.postings = torch.zeros(1, dtype=torch.int32, device=dev)
+                if float(r16.min().item()) < 6.2e-5 or not bool(torch.isfinite(r16).all()):
+                    return None, None, None, None
+                term_max.scatter_reduce_(0, tt % self.vocab, r16.float(), reduce="amax", include_self=True)
+                post_chunks.append((((key % T) << 16) | (r16.view(torch.int16).long() & 0xFFFF)).to(torch.int32))
+                del doc_abs, tf_f, r, r16
+            del key, tf, tt
+        post_chunks.append(torch.zeros(4, dtype=torch.int32, device=dev))  # padding (16-byte reads never fault)
+        postings = torch.cat(post_chunks)
         del post_chunks
-        self.postings_r16 = None
-        self.term_max_r = None
-        if r16_ok and r16_chunks:
-            r16_chunks.append(torch.zeros(4, dtype=torch.int32, device=dev))  # 16-byte over-read padding
-            self.postings_r16 = torch.cat(r16_chunks)
-            self.term_max_r = term_max
-            assert self.postings_r16.data_ptr() % 16 == 0
-        del r16_chunks
         if cnt_chunks:
-            counts = torch.cat(cnt_chunks).view(self.n_tiles, self.vocab)
+            counts = torch.cat(cnt_chunks).view(n_tiles, self.vocab)
         else:
             counts = torch.zeros((0, self.vocab), dtype=torch.int64, device=dev)
-        off = torch.zeros((self.n_tiles, V1), dtype=torch.int64, device=dev)
+        off = torch.zeros((n_tiles, V1), dtype=torch.int64, device=dev)
         torch.cumsum(counts, dim=1, out=off[:, 1:])
-        per_tile = off[:, -1] if self.n_tiles else torch.zeros(0, dtype=torch.int64, device=dev)
-        self.tile_base = torch.zeros(self.n_tiles + 1, dtype=torch.int64, device=dev)
-        if self.n_tiles:
-            torch.cumsum(per_tile, dim=0, out=self.tile_base[1:])
+        per_tile = off[:, -1] if n_tiles else torch.zeros(0, dtype=torch.int64, device=dev)
+        tile_base = torch.zeros(n_tiles + 1, dtype=torch.int64, device=dev)
+        if n_tiles:
+            torch.cumsum(per_tile, dim=0, out=tile_base[1:])
             assert int(per_tile.max().item()) < 2 ** 31
-        self.tile_term_off = off.to(torch.int32).contiguous()
-        self.n_postings = int(self.tile_base[-1].item())
-        del counts, off
-
-        self.struct = _ffi.Bm25IndexStruct(
-            n_docs=self.n_docs, vocab=self.vocab, tile_docs=self.tile_docs, n_tiles=self.n_tiles,
-            has_negative_idf=int(self.has_negative_idf),
-            d_tile_base=self.tile_base.data_ptr(), d_tile_term_off=self.tile_term_off.data_ptr(),
-            max_doc_len=self.max_dl, reserved=0, d_postings=self.postings.data_ptr(), d_doc_len=self.dl.data_ptr(),
-            d_t4_table=self.t4_table.data_ptr(), d_r_table=self.r_table.data_ptr(), d_idf=self.idf.data_ptr(),
-            d_postings_r16=self.postings_r16.data_ptr() if self.postings_r16 is not None else None,
-            d_term_max_r=self.term_max_r.data_ptr() if self.term_max_r is not None else None)
-        self._ws = None
+        return postings, tile_base, off.to(torch.int32).contiguous(), term_max
 
     @property
     def doc_t4(self) -> torch.Tensor:

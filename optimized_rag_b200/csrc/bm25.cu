@@ -335,14 +335,15 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const __grid_constant__ 
     const int q = blockIdx.x;
     const int k = p.k;
     uint32_t n = p.cnt[q];
-    if (n > (uint32_t)p.cap) {
+    const bool overflow = n > (uint32_t)p.cap;
+    if (overflow) {
         if (status && threadIdx.x == 0) status[q] |= ORAG_STATUS_OVERFLOW;
         n = p.cap;
     }
     select_from_list(p.ix, p.q_terms + (int64_t)q * p.max_terms, min(p.q_lens[q], p.max_terms), k,
                      p.cand_doc + (int64_t)q * p.cap, p.cand_score + (int64_t)q * p.cap, n, doc_id_base, normalize,
                      out_ids + (int64_t)q * k, out_scores + (int64_t)q * k, out_max ? out_max + q : nullptr, scratch,
-                     dscratch);
+                     dscratch, !overflow);
 }
 
 __global__ void init_state_kernel(unsigned long long *thr_bits, uint32_t *cnt, uint32_t *hist, uint32_t *topbin,

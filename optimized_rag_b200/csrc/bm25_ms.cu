@@ -1,23 +1,33 @@
-// bm25_ms.cu -- BM25 top-k, fp32 MaxScore first pass + exact float64 re-score.
+// bm25_ms.cu -- BM25 top-k, fp32 MaxScore first pass over big tiles + exact float64 re-score.
 //
 // Same result as bm25.cu (bit-exact float64 scores of rank_bm25.BM25Okapi.get_scores + the glue at
-// rag/retrieval.py:324-347), an order of magnitude fewer instructions per (query, tile) pair.
+// rag/retrieval.py:324-347) at a fraction of the instructions per posting.
 //
-// First pass.  The index carries a second view of the postings, (doc_in_tile << 16) | fp16(r) with
-// r = tf*(k1+1)/(tf + t4[dl]) rounded to nearest, so a posting's contribution is one fp32 multiply
-// w*r (w = fp32 idf, duplicates of a query term merged into one weight) and needs no document-length
-// or table lookup.  Every approximate score s~ satisfies |s~ - s| <= eps*s with
+// First-pass view.  The index carries a second tiling of the postings with much larger tiles (up to 16384
+// docs): (doc_in_tile << 16) | fp16(r), r = tf*(k1+1)/(tf + t4[dl]) rounded to nearest, so a posting's
+// contribution is one fp32 multiply w*r (w = fp32 idf, duplicates of a query term merged into one weight)
+// and needs no document-length or table lookup.  Every approximate score s~ satisfies |s~ - s| <= eps*s with
 // eps = 2^-11 (fp16 r) + (n_terms + 2) * 2^-24 (fp32 weight, products, sums) < 5e-4: all terms are positive.
 //
 // MaxScore.  prepare_queries_kernel sorts a query's terms by ascending upper bound
 // ub_t = w_t * max_r(t) (max over the shard's postings of t) and stores the inclusive prefix sums.
 // With the query's running threshold thr (a lower bound of the k-th best s~ seen so far, from the same
 // log-scale histogram bm25.cu uses) the terms whose prefix sum stays below thr' = thr * (1 - 2^-9) are
-// "non-essential": a document that contains only those cannot reach thr', so their posting runs are never
-// scattered.  Only the essential runs are added into the warp's fp32 accumulators (shared-memory atomics,
-// any order); each touched document is then claimed once (atomicExch resets the accumulator), and the
-// non-essential terms are looked up for it by binary search in the staged runs, most valuable term first,
-// stopping as soon as partial + remaining upper bound < thr'.  Documents that end at s~ >= thr' are emitted.
+// "non-essential": a document that contains only those cannot reach thr'.
+//
+// One warp works on one (query, tile) pair at a time with three small shared-memory structures: a bitmap of
+// the tile's docs, per-word prefix popcounts, and a compact fp32 accumulator indexed by a doc's RANK among
+// the marked docs (so the accumulator is sized by the docs a query touches, not by the tile):
+//   E1  mark the docs of the essential runs in the bitmap (shared-memory atomicOr)
+//   R   prefix popcounts -> rank(d); the number of marked docs must fit the accumulator, otherwise the pair
+//       is processed in doc sub-ranges (runs are doc-sorted: a sub-range is a contiguous part of every run,
+//       found by one binary search per run and boundary)
+//   E2  add the essential contributions into acc[rank(d)]
+//   N   stream the non-essential runs with 16-byte loads; a posting only matters when its doc is marked
+//       (one shared-memory word test), in which case its contribution completes acc[rank(d)]
+//   X   claim every marked doc once, reset, emit those with s~ >= thr'
+// Docs are distinct inside a run, and runs are applied one at a time with __syncwarp in between, so plain
+// read-modify-writes suffice (no floating-point atomics).
 //
 // Superset argument (as for the cosine first pass): let S_k be the true k-th best score and S~_k the k-th
 // best approximate score.  At most k-1 docs have s > S_k, so S~_k <= S_k (1 + eps); thr <= S~_k always.  A
@@ -26,23 +36,25 @@
 // are rounded up, thr' down).  ms_finalize_kernel keeps the candidates with s~ >= final thr', re-scores them
 // with score_doc() (float64, query order, duplicates twice) and selects by (score desc, id asc).
 //
-// Work decomposition and pipeline follow bm25.cu: one warp per (tile, query slice), four stages in flight
-// (descriptor of query i+3, run offsets of query i+2, 16-byte cp.async of the runs of query i+1 into a
-// per-warp two-buffer ring, query i consumed), no CTA barrier in the loop.
+// Work items are (tile, slice of the query batch), handed out through an atomic counter; the prepared query
+// of pair i+2 and the run offsets (+ an L2 prefetch of the run heads) of pair i+1 are in flight while pair i
+// is consumed.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "bm25_shared.cuh"
 
 namespace orag {
 namespace bm25 {
 
-constexpr int kMsWarps = 8;
+constexpr int kMsWarps = 12;
 constexpr int kMsThreads = kMsWarps * 32;
 constexpr int kMsTerms = 32;      // scoring terms per query on this path (one per lane)
-constexpr int kMsStage = 736;     // postings per staging buffer (two per warp); multiple of 4
+constexpr int kMsAccCap = 1024;   // marked docs per (query, tile sub-range)
+constexpr int kMsSubTarget = 512; // essential postings per sub-range the splitter aims for
+constexpr int kMsMaxTile = 16384;
 constexpr int kMsSurvCap = 2048;  // candidates re-scored per query
 constexpr float kMsGuard = 1.0f - 1.0f / 512.0f;
-constexpr float kMsMinR = 6.103515625e-05f;  // smallest normal fp16
 
 struct MsParams {
     orag_bm25_index_t ix;
@@ -51,9 +63,8 @@ struct MsParams {
     int n_queries;
     int max_terms;
     int k;
-    // prepared queries: terms sorted by ascending upper bound
     int32_t *qd;       // [n_queries, kMsTerms, 4] = {term, fp32 weight (idf * multiplicity), inclusive prefix sum
-                       //  of the upper bounds (rounded up), number of terms}
+                       //  of the upper bounds (rounded up), number of terms}; terms by ascending upper bound
     // threshold state (same scheme as bm25.cu)
     unsigned long long *thr_bits;
     uint32_t *cnt;
@@ -64,7 +75,10 @@ struct MsParams {
     int cap;
     int32_t *surv_doc;  // [n_queries, kMsSurvCap]
     double *surv_score; // [n_queries, kMsSurvCap]
+    uint32_t *work;     // [1] next work item
+    int32_t *status;    // [n_queries] or null
     int q_split;
+    int n_items;
 };
 
 // One thread per query: drop OOV / zero-idf tokens, merge duplicates, sort by upper bound.
@@ -134,23 +148,12 @@ __device__ __forceinline__ float thr_to_float(unsigned long long bits)
     return __fmul_rd(__double2float_rd(__longlong_as_double((long long)bits)), kMsGuard);
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gmem_src)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void *gmem_src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void ms_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void ms_cp_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-
 __device__ __forceinline__ float post_r(uint32_t post)
 {
     return __half2float(__ushort_as_half((unsigned short)(post & 0xFFFFu)));
 }
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct MsDesc {  // lane i = i-th term of the prepared query
     int term;
@@ -158,50 +161,54 @@ struct MsDesc {  // lane i = i-th term of the prepared query
     int n, q;
 };
 struct MsRun {
-    int rel;     // first posting of the run, relative to the tile's 16-byte aligned base pointer
-    int len;     // holds the END offset until the run is staged
+    int rel;     // first posting of the run relative to the tile's first posting
+    int len;
     float w, pre;
     int n, q;
-};
-struct MsStaged {
-    MsRun r;
-    int soff;    // position of the run's first posting in the staging buffer
-    int slen;    // postings available in the buffer (<= len); the rest is read from global memory
 };
 
 __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_constant__ MsParams p)
 {
     extern __shared__ uint4 ms_smem[];
-    const int T = p.ix.tile_docs;
+    const int T = p.ix.fp_tile_docs;
+    const int words = (T + 31) >> 5;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)T * 4 + 2 * kMsStage * 4;
+    const size_t per_warp = (size_t)words * 4 + (size_t)((words * 2 + 15) & ~15) + (size_t)kMsAccCap * 4;
     uint8_t *mine = reinterpret_cast<uint8_t *>(ms_smem) + wib * per_warp;
-    float *acc = reinterpret_cast<float *>(mine);                          // [T], all zero between queries
-    uint32_t *stage = reinterpret_cast<uint32_t *>(mine + (size_t)T * 4);  // [2][kMsStage]
-    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
-    for (int i = lane; i < T; i += 32) acc[i] = 0.f;
+    uint32_t *bm = reinterpret_cast<uint32_t *>(mine);                                // [words] marked docs
+    float *acc = reinterpret_cast<float *>(mine + (size_t)words * 4);                 // [kMsAccCap], zero between pairs
+    uint16_t *pre = reinterpret_cast<uint16_t *>(mine + (size_t)words * 4 + (size_t)kMsAccCap * 4);  // [words]
+    for (int i = lane; i < words; i += 32) bm[i] = 0u;
+    for (int i = lane; i < kMsAccCap; i += 32) acc[i] = 0.f;
     __syncwarp();
 
     const int V1 = p.ix.vocab + 1;
     const int nq = p.n_queries;
-    const int warps_total = gridDim.x * kMsWarps;
     const unsigned FULL = 0xffffffffu;
     const int S = p.q_split;
     const int4 *qd = reinterpret_cast<const int4 *>(p.qd);
+    const int wpl = (words + 31) >> 5;  // bitmap words per lane in the rank pass
 
-    for (int item = blockIdx.x * kMsWarps + wib; item < p.ix.n_tiles * S; item += warps_total) {
+    auto rank_of = [&](uint32_t d) -> int {
+        const uint32_t wd = bm[d >> 5];
+        return (int)pre[d >> 5] + __popc(wd & ((1u << (d & 31)) - 1u));
+    };
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(p.work, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= p.n_items) break;
         const int tile = item / S;
         const int part = item - tile * S;
         const int qi0 = (int)(((int64_t)nq * part) / S);
         const int qi1 = (int)(((int64_t)nq * (part + 1)) / S);
         const int64_t base_doc = (int64_t)tile * T;
-        const int64_t tile_g0 = p.ix.d_tile_base[tile];
-        const int tb = (int)(tile_g0 & 3);
-        const uint32_t *tp_al = p.ix.d_postings_r16 + (tile_g0 - tb);  // 16-byte aligned
-        const int32_t *toff = p.ix.d_tile_term_off + (int64_t)tile * V1;
+        const uint32_t *tp = p.ix.d_postings_r16 + p.ix.d_fp_tile_base[tile];
+        const int32_t *toff = p.ix.d_fp_tile_term_off + (int64_t)tile * V1;
+        // stagger the query order across tiles so a query's threshold is established by few warps
         const int q_shift = (int)(((int64_t)tile * 7919) % nq);
 
-        // ---- stage A: the prepared query (one 16-byte load per lane)
         auto stage_desc = [&](int qi) -> MsDesc {
             MsDesc d;
             d.term = -1; d.w = 0.f; d.pre = 0.f; d.n = 0; d.q = 0;
@@ -217,138 +224,174 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
             }
             return d;
         };
-        // ---- stage B: run offsets of every term inside this tile
         auto stage_run = [&](const MsDesc &d) -> MsRun {
             MsRun r;
             r.rel = 0; r.len = 0; r.w = d.w; r.pre = d.pre; r.n = d.n; r.q = d.q;
             if (lane < d.n) {
                 r.rel = __ldg(toff + d.term);
-                r.len = __ldg(toff + d.term + 1);
+                r.len = __ldg(toff + d.term + 1) - r.rel;
+                if (r.len > 0) prefetch_l2(tp + r.rel);
             }
             return r;
         };
-        // ---- stage C: lay the runs out in the staging buffer (16-byte aligned source windows) and copy
-        auto stage_posts = [&](MsRun run, int qi) -> MsStaged {
-            MsStaged s;
-            run.len -= run.rel;
-            run.rel += tb;
-            s.r = run;
-            const int shift = run.rel & 3;
-            const int alen = run.len > 0 ? ((shift + run.len + 3) & ~3) : 0;
-            int incl = alen;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, d);
-                if (lane >= d) incl += v;
-            }
-            const int excl = incl - alen;
-            const int avail = max(0, min(alen, kMsStage - excl));  // multiple of 4
-            s.soff = excl + shift;
-            s.slen = max(0, min(run.len, avail - shift));
-            const int n16 = s.slen > 0 ? (avail >> 2) : 0;
-            const uint32_t dst_s = stage_s + (uint32_t)((qi & 1) * kMsStage + excl) * 4u;
-            const uint32_t *src = tp_al + (run.rel & ~3);
-            // every lane copies the first two 16-byte chunks of its own run (most runs are that short) ...
-            if (n16 > 0) cp_async16_s(dst_s, src);
-            if (n16 > 1) cp_async16_s(dst_s + 16, src + 4);
-            // ... and the long runs are copied by the whole warp, 512 bytes per instruction
-            unsigned active = __ballot_sync(FULL, n16 > 2);
-            while (active) {
-                const int i = __ffs(active) - 1;
-                active &= active - 1;
-                const uint32_t d0 = __shfl_sync(FULL, dst_s, i);
-                const unsigned long long s0 = __shfl_sync(FULL, (unsigned long long)(uintptr_t)src, i);
-                const int cnt = __shfl_sync(FULL, n16, i);
-                const uint32_t *sp = reinterpret_cast<const uint32_t *>((uintptr_t)s0);
-#pragma unroll 1
-                for (int c = 2 + lane; c < cnt; c += 32) cp_async16_s(d0 + 16u * c, sp + 4 * c);
-            }
-            ms_cp_commit();
-            return s;
-        };
 
-        // prologue: fill the pipeline
-        MsStaged cur = stage_posts(stage_run(stage_desc(qi0)), qi0);
-        MsRun runB = stage_run(stage_desc(qi0 + 1));
-        MsDesc descA = stage_desc(qi0 + 2);
+        MsRun cur = stage_run(stage_desc(qi0));
+        MsDesc descA = stage_desc(qi0 + 1);
 
         for (int qi = qi0; qi < qi1; ++qi) {
-            // the current query's threshold: issued first, consumed after the stage-C work below
             unsigned long long thr_bits = 0;
-            if (cur.r.n > 0) thr_bits = __ldcg(p.thr_bits + cur.r.q);
-            const MsStaged nxt = stage_posts(runB, qi + 1);
-            runB = stage_run(descA);
-            descA = stage_desc(qi + 3);
+            if (cur.n > 0) thr_bits = __ldcg(p.thr_bits + cur.q);
+            const MsRun nxt = stage_run(descA);
+            descA = stage_desc(qi + 2);
 
-            const uint32_t *buf = stage + (qi & 1) * kMsStage;
-            ms_cp_wait_1();
-            __syncwarp();
-
-            const int n = cur.r.n;  // warp-uniform
-            const float thr = thr_to_float(thr_bits);
-            const int q = cur.r.q;
-            const bool mine_ok = lane < n && cur.r.len > 0;
-            const int n_ne = __popc(__ballot_sync(FULL, lane < n && cur.r.pre < thr));  // a prefix of the lanes
-            const unsigned ess = __ballot_sync(FULL, mine_ok && lane >= n_ne);
+            const int n = cur.n;  // warp-uniform
+            float thr = thr_to_float(thr_bits);
+            const int q = cur.q;
+            const bool mine_ok = lane < n && cur.len > 0;
+            int n_ne = __popc(__ballot_sync(FULL, lane < n && cur.pre < thr));  // a prefix of the lanes
+            unsigned ess = __ballot_sync(FULL, mine_ok && lane >= n_ne);
             if (ess) {
-                const unsigned non = __ballot_sync(FULL, mine_ok && lane < n_ne);
-                // per-run views are broadcast with shuffles; postings beyond the staged part come from global memory
-#define MS_RUN_VIEW(i)                                                         \
-    const int len_ = __shfl_sync(FULL, cur.r.len, i);                          \
-    const int so_ = __shfl_sync(FULL, cur.soff, i);                            \
-    const int sl_ = __shfl_sync(FULL, cur.slen, i);                            \
-    const int rel_ = __shfl_sync(FULL, cur.r.rel, i)
-#define MS_POST(j) ((j) < sl_ ? buf[so_ + (j)] : __ldg(tp_al + rel_ + (j)))
-                // ---- S: scatter the essential runs (docs are distinct inside a run: plain read-modify-write)
-                for (unsigned a = ess; a; a &= a - 1) {
-                    const int i = __ffs(a) - 1;
-                    MS_RUN_VIEW(i);
-                    const float w = __shfl_sync(FULL, cur.r.w, i);
-#pragma unroll 1
-                    for (int j = lane; j < len_; j += 32) {
-                        const uint32_t post = MS_POST(j);
-                        float *slot = acc + (post >> 16);
-                        *slot = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
+                int etot = (mine_ok && lane >= n_ne) ? cur.len : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) etot += __shfl_xor_sync(FULL, etot, o);
+                // number of doc sub-ranges: marked docs per sub-range must fit the compact accumulator
+                int nsub = 1;
+                while (nsub * kMsSubTarget < etot && nsub * 32 < T) nsub <<= 1;
+                const int sub_docs = T / nsub;
+                int cpos = 0;  // this lane's run: first posting of the current sub-range
+                for (int sub = 0; sub < nsub; ++sub) {
+                    if (sub > 0) {
+                        // a pair that needs several sub-ranges is a cold one: its own emissions have raised the
+                        // threshold since, so re-read it and re-partition (fewer essential runs, fewer emissions)
+                        thr = thr_to_float(__ldcg(p.thr_bits + q));
+                        n_ne = __popc(__ballot_sync(FULL, lane < n && cur.pre < thr));
+                        ess = __ballot_sync(FULL, mine_ok && lane >= n_ne);
+                        if (!ess) break;  // nothing left in this tile can reach the threshold
                     }
-                    __syncwarp();
-                }
-                // ---- N: the non-essential runs only complete documents an essential term has touched
-                for (unsigned a = non; a; a &= a - 1) {
-                    const int i = __ffs(a) - 1;
-                    MS_RUN_VIEW(i);
-                    const float w = __shfl_sync(FULL, cur.r.w, i);
-#pragma unroll 1
-                    for (int j = lane; j < len_; j += 32) {
-                        const uint32_t post = MS_POST(j);
-                        float *slot = acc + (post >> 16);
-                        const float v = *slot;
-                        if (v != 0.f) *slot = __fadd_rn(v, __fmul_rn(w, post_r(post)));
+                    const unsigned non = __ballot_sync(FULL, mine_ok && lane < n_ne);
+                    int s_end = cur.len;
+                    if (sub + 1 < nsub && mine_ok) {
+                        // first posting of this lane's run with doc >= the sub-range's upper boundary
+                        const uint32_t bound = (uint32_t)((sub + 1) * sub_docs);
+                        int lo = cpos, hi = cur.len;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if ((__ldg(tp + cur.rel + mid) >> 16) < bound) lo = mid + 1; else hi = mid;
+                        }
+                        s_end = lo;
                     }
-                    __syncwarp();
-                }
-                // ---- X: claim every touched doc once (first essential run that holds it), reset, emit
-                for (unsigned a = ess; a; a &= a - 1) {
-                    const int i = __ffs(a) - 1;
-                    MS_RUN_VIEW(i);
+                    const int v_rel = cur.rel + cpos;
+                    const int v_len = mine_ok ? s_end - cpos : 0;
+                    cpos = s_end;
+#define MS_VIEW(i)                                         \
+    const int len_ = __shfl_sync(FULL, v_len, i);          \
+    const uint32_t *gp_ = tp + __shfl_sync(FULL, v_rel, i)
+                    // ---- E1: mark the docs of the essential runs
+                    for (unsigned a = ess; a; a &= a - 1) {
+                        const int i = __ffs(a) - 1;
+                        MS_VIEW(i);
 #pragma unroll 1
-                    for (int j = lane; j < len_; j += 32) {
-                        const uint32_t d = MS_POST(j) >> 16;
-                        const float v = acc[d];
-                        if (v != 0.f) {
-                            acc[d] = 0.f;
-                            if (v >= thr) ms_emit(p, q, (int32_t)(base_doc + d), v);
+                        for (int j = lane; j < len_; j += 32) {
+                            const uint32_t d = __ldg(gp_ + j) >> 16;
+                            atomicOr(bm + (d >> 5), 1u << (d & 31));
                         }
                     }
                     __syncwarp();
+                    // ---- R: prefix popcounts (lane l owns words [l*wpl, (l+1)*wpl))
+                    int mycnt = 0;
+                    for (int t = 0; t < wpl; ++t) {
+                        const int wi = lane * wpl + t;
+                        if (wi < words) mycnt += __popc(bm[wi]);
+                    }
+                    int incl = mycnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    const int marked = __shfl_sync(FULL, incl, 31);
+                    int run_sum = incl - mycnt;
+                    for (int t = 0; t < wpl; ++t) {
+                        const int wi = lane * wpl + t;
+                        if (wi < words) {
+                            pre[wi] = (uint16_t)run_sum;
+                            run_sum += __popc(bm[wi]);
+                        }
+                    }
+                    __syncwarp();
+                    if (marked <= kMsAccCap) {
+                        // ---- E2: essential contributions into the compact accumulator
+                        for (unsigned a = ess; a; a &= a - 1) {
+                            const int i = __ffs(a) - 1;
+                            MS_VIEW(i);
+                            const float w = __shfl_sync(FULL, cur.w, i);
+#pragma unroll 1
+                            for (int j = lane; j < len_; j += 32) {
+                                const uint32_t post = __ldg(gp_ + j);
+                                float *slot = acc + rank_of(post >> 16);
+                                *slot = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
+                            }
+                            __syncwarp();
+                        }
+                        // ---- N: non-essential runs complete the marked docs only
+                        for (unsigned a = non; a; a &= a - 1) {
+                            const int i = __ffs(a) - 1;
+                            MS_VIEW(i);
+                            const float w = __shfl_sync(FULL, cur.w, i);
+                            auto one = [&](uint32_t post) {
+                                const uint32_t d = post >> 16;
+                                const uint32_t wd = bm[d >> 5];
+                                if ((wd >> (d & 31)) & 1u) {
+                                    float *slot = acc + (int)pre[d >> 5] + __popc(wd & ((1u << (d & 31)) - 1u));
+                                    *slot = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
+                                }
+                            };
+                            // up to 3 head and 3 tail postings around the 16-byte aligned body
+                            const int head = min(len_, (int)((16u - ((uint32_t)(uintptr_t)gp_ & 15u)) & 15u) >> 2);
+                            const int body4 = (len_ - head) >> 2;
+                            const int tail = len_ - head - 4 * body4;
+                            {
+                                int idx = -1;
+                                if (lane < head) idx = lane;
+                                else if (lane >= 3 && lane - 3 < tail) idx = head + 4 * body4 + (lane - 3);
+                                if (idx >= 0) one(__ldg(gp_ + idx));
+                            }
+                            const uint4 *g4 = reinterpret_cast<const uint4 *>(gp_ + head);
+#pragma unroll 2
+                            for (int c = lane; c < body4; c += 32) {
+                                const uint4 v = __ldg(g4 + c);
+                                one(v.x); one(v.y); one(v.z); one(v.w);
+                            }
+                            __syncwarp();
+                        }
+                        // ---- X: claim every marked doc once (first essential run that holds it), reset, emit
+                        for (unsigned a = ess; a; a &= a - 1) {
+                            const int i = __ffs(a) - 1;
+                            MS_VIEW(i);
+#pragma unroll 1
+                            for (int j = lane; j < len_; j += 32) {
+                                const uint32_t d = __ldg(gp_ + j) >> 16;
+                                float *slot = acc + rank_of(d);
+                                const float v = *slot;
+                                if (v != 0.f) {
+                                    *slot = 0.f;
+                                    if (v >= thr) ms_emit(p, q, (int32_t)(base_doc + d), v);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    } else if (p.status && lane == 0) {
+                        // a skewed sub-range marked more docs than the accumulator holds: the caller re-runs the query
+                        atomicOr(p.status + q, ORAG_STATUS_OVERFLOW);
+                    }
+#undef MS_VIEW
+                    // ---- clear the bitmap
+                    for (int i = lane; i < words; i += 32) bm[i] = 0u;
+                    __syncwarp();
                 }
-#undef MS_RUN_VIEW
-#undef MS_POST
             }
             cur = nxt;
         }
-        // drain the (empty) copy groups still outstanding before the buffers are reused by the next item
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
     }
 }
 
@@ -393,21 +436,23 @@ __global__ void __launch_bounds__(1024) ms_finalize_kernel(const __grid_constant
     const int nt = min(p.q_lens[q], p.max_terms);
     for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) ss[i] = score_doc(p.ix, terms, nt, sd[i]);
     __syncthreads();
+    // (an overflowed query is re-run by the caller: skip the serial zero-score fill for it)
     select_from_list(p.ix, terms, nt, k, sd, ss, ns, doc_id_base, normalize, out_ids + (int64_t)q * k,
-                     out_scores + (int64_t)q * k, out_max ? out_max + q : nullptr, scratch, dscratch);
+                     out_scores + (int64_t)q * k, out_max ? out_max + q : nullptr, scratch, dscratch, !overflow);
 }
 
 __global__ void ms_init_state_kernel(unsigned long long *thr_bits, uint32_t *cnt, uint32_t *hist, uint32_t *topbin,
-                                     int n_queries)
+                                     uint32_t *work, int n_queries, int keep_thr)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t total = (int64_t)n_queries * kHistBins;
     if (i < total) hist[i] = 0;
     if (i < n_queries) {
-        thr_bits[i] = 1ull;  // smallest positive double: "score > 0"
+        if (!keep_thr) thr_bits[i] = 1ull;  // smallest positive double: "score > 0"
         cnt[i] = 0;
         topbin[i] = 0;
     }
+    if (i == 0) *work = 0;
 }
 
 static int ms_cap(int n_queries)
@@ -421,8 +466,10 @@ static int ms_cap(int n_queries)
 
 bool ms_eligible(const orag_bm25_index_t *ix, int max_terms, int flags)
 {
-    return ix->d_postings_r16 != nullptr && ix->d_term_max_r != nullptr && !ix->has_negative_idf &&
-           max_terms <= kMsTerms && !(flags & (ORAG_BM25_EXACT_TILES | ORAG_BM25_FORCE_DENSE)) && ix->tile_docs <= 4096;
+    return ix->d_postings_r16 != nullptr && ix->d_term_max_r != nullptr && ix->d_fp_tile_base != nullptr &&
+           ix->d_fp_tile_term_off != nullptr && !ix->has_negative_idf && max_terms <= kMsTerms &&
+           !(flags & (ORAG_BM25_EXACT_TILES | ORAG_BM25_FORCE_DENSE)) && ix->fp_tile_docs >= 32 &&
+           ix->fp_tile_docs <= kMsMaxTile && (ix->fp_tile_docs & (ix->fp_tile_docs - 1)) == 0;
 }
 
 struct MsCarve {
@@ -447,6 +494,7 @@ static MsCarve ms_carve(void *base, int n_queries)
     c.p.topbin = (uint32_t *)take(nq * 4);
     c.p.hist = (uint32_t *)take(nq * kHistBins * 4);
     c.p.qd = (int32_t *)take(nq * kMsTerms * 16);
+    c.p.work = (uint32_t *)take(256);
     c.p.cand_doc = (int32_t *)take(nq * cap * 4);
     c.p.cand_val = (float *)take(nq * cap * 4);
     c.p.surv_doc = (int32_t *)take(nq * kMsSurvCap * 4);
@@ -472,28 +520,29 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
     p.n_queries = n_queries;
     p.max_terms = max_terms;
     p.k = k;
+    p.status = d_out_status;
     {
         int64_t total = (int64_t)n_queries * kHistBins;
         ms_init_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.thr_bits, p.cnt, p.hist, p.topbin,
-                                                                              n_queries);
+                                                                              p.work, n_queries,
+                                                                              getenv("ORAG_MS_KEEP_THR") != nullptr);
         ORAG_LAUNCH_CHECK();
         prepare_queries_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(p);
         ORAG_LAUNCH_CHECK();
     }
-    if (ix->n_tiles > 0) {
-        const size_t smem = (size_t)kMsWarps * ((size_t)ix->tile_docs * 4 + 2 * kMsStage * 4);
-        int per_sm = (int)((226 * 1024) / (smem + 1024));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 2) per_sm = 2;
-        const int lim = sm_count() * per_sm;
-        int64_t want = (int64_t)4 * lim * kMsWarps;
-        int split = (int)((want + ix->n_tiles - 1) / ix->n_tiles);
-        if (split > 16) split = 16;
+    if (ix->fp_n_tiles > 0) {
+        const int words = (ix->fp_tile_docs + 31) / 32;
+        const size_t per_warp = (size_t)words * 4 + (size_t)((words * 2 + 15) & ~15) + (size_t)kMsAccCap * 4;
+        const size_t smem = (size_t)kMsWarps * per_warp;
+        const int lim = sm_count() * 2;
+        // ~8 work items per resident warp so that the atomic hand-out can balance cold and warm pairs
+        int64_t want = (int64_t)8 * lim * kMsWarps;
+        int64_t split = (want + ix->fp_n_tiles - 1) / ix->fp_n_tiles;
         if (split > n_queries) split = n_queries;
         if (split < 1) split = 1;
-        p.q_split = split;
-        const int64_t items = (int64_t)ix->n_tiles * split;
-        int grid = (int)((items + kMsWarps - 1) / kMsWarps);
+        p.q_split = (int)split;
+        p.n_items = (int)((int64_t)ix->fp_n_tiles * split);
+        int grid = (p.n_items + kMsWarps - 1) / kMsWarps;
         if (grid > lim) grid = lim;
         ORAG_CUDA_CHECK(cudaFuncSetAttribute(bm25_ms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         profile_mark(1, 0, st);

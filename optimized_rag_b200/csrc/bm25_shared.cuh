@@ -86,7 +86,7 @@ __device__ inline double score_doc(const orag_bm25_index_t &ix, const int32_t *t
 __device__ inline void select_from_list(const orag_bm25_index_t &ix, const int32_t *q_terms_row, int nt, int k,
                                         const int32_t *cd, const double *cs, uint32_t n, int64_t doc_id_base,
                                         int normalize, int64_t *out_ids, double *out_scores, double *out_max_slot,
-                                        Pick *scratch, double *dscratch)
+                                        Pick *scratch, double *dscratch, bool zero_fill = true)
 {
     double mx = -INFINITY;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) mx = fmax(mx, cs[i]);
@@ -121,7 +121,7 @@ __device__ inline void select_from_list(const orag_bm25_index_t &ix, const int32
     if (found < k && threadIdx.x == 0) {
         // fewer than k docs with a positive score: the rest of the list is zero-score docs in id order
         int r = found;
-        for (int64_t d = 0; d < ix.n_docs && r < k; ++d) {
+        for (int64_t d = 0; zero_fill && d < ix.n_docs && r < k; ++d) {
             if (score_doc(ix, q_terms_row, nt, d) == 0.0) {
                 out_ids[r] = doc_id_base + d;
                 out_scores[r] = 0.0;

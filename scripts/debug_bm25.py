@@ -17,7 +17,8 @@ dev = "cuda:0"
 V = 50000
 thr = syn.zipf_thresholds(V)
 doc_off, tokens = engine.gen_token_corpus(n, 0, syn.SEED_TOKENS, thr, V, 100, 300, device=dev)
-ix = Bm25Index(doc_off, tokens, V, tile_docs=tile)
+fp_tile = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else None
+ix = Bm25Index(doc_off, tokens, V, tile_docs=tile, fp_tile_docs=fp_tile)
 del tokens
 qt, ql = syn.keyword_queries(B, V, thresholds=thr)
 qt_d, ql_d = torch.from_numpy(qt).to(dev), torch.from_numpy(ql).to(dev)
@@ -42,6 +43,32 @@ for force in ("exact_tiles", "sparse"):
               f"query: min {cnt.min()} mean {cnt.mean():.0f} max {cnt.max()} total {cnt.sum()}; overflow "
               f"{int((st[0] != 0).sum())}; postings(6B) {ix.posting_bytes(qt_d, ql_d) / 6:.3e}", flush=True)
     res[force] = (ids, sc, mx)
+# MaxScore statistics from the workspace of the last "sparse" call (layout: bm25_ms.cu ms_carve)
+if ix.postings_r16 is not None:
+    ws = ix._ws
+    al = lambda x: (x + 255) // 256 * 256
+    o_thr = 0
+    o_qd = al(B * 8) + al(B * 4) + al(B * 4) + al(B * 8192 * 4)
+    thr_f = ws[o_thr:o_thr + B * 8].view(torch.float64).float() * (1 - 1 / 512)
+    qd_raw = ws[o_qd:o_qd + B * 32 * 16].view(torch.int32).view(B, 32, 4)
+    term = qd_raw[:, :, 0].long()
+    pre = qd_raw[:, :, 2].contiguous().view(torch.float32)
+    nn = qd_raw[:, 0, 3]
+    off = ix.fp_tile_term_off.long()
+    df = (off[:, 1:] - off[:, :-1]).sum(0)
+    valid = torch.arange(32, device=dev)[None, :] < nn[:, None]
+    dfq = torch.where(valid, df[term.clamp(min=0)], torch.zeros_like(term))
+    ne = valid & (pre < thr_f[:, None])
+    tot = dfq.sum().item(); ess = dfq[valid & ~ne].sum().item()
+    print(f"MaxScore at final thresholds: essential postings {ess:.3e} of {tot:.3e} = {ess / tot:.1%}; "
+          f"queries with no non-essential term: {int((ne.sum(1) == 0).sum())}/{B}; mean terms {nn.float().mean():.2f}, "
+          f"mean non-essential {ne.sum(1).float().mean():.2f}")
+    frac = (dfq * (valid & ~ne)).sum(1).float() / dfq.sum(1).float().clamp(min=1)
+    print("per-query essential fraction deciles:", [round(float(x), 3) for x in torch.quantile(frac, torch.linspace(0, 1, 11, device=dev))])
+    heavy = torch.argsort(-(dfq * (valid & ~ne)).sum(1))[:5]
+    for h in heavy.tolist():
+        print("  heavy query", h, "n", int(nn[h]), "thr", float(thr_f[h]), "pre", [round(float(x), 2) for x in pre[h, :nn[h]]],
+              "df/N", [round(float(x) / n, 4) for x in dfq[h, :nn[h]]])
 print("ms == exact_tiles:", all(torch.equal(x, y) for x, y in zip(res["sparse"], res["exact_tiles"])))
 if "--no-dense" in sys.argv:
     sys.exit(0)
