@@ -149,7 +149,7 @@ class Bm25Index:
         # first-pass view: (doc_in_tile << 16) | fp16(r) over (much larger) tiles of `fp_tile_docs` docs
         self.postings_r16 = self.term_max_r = self.fp_tile_base = self.fp_tile_term_off = None
         if fp_tile_docs is None:
-            fp_tile_docs = min(16384, max(32, 1 << max(0, (max(self.n_docs, 1) // 16 - 1).bit_length())))
+            fp_tile_docs = min(8192, max(32, 1 << max(0, (max(self.n_docs, 1) // 16 - 1).bit_length())))
         assert fp_tile_docs & (fp_tile_docs - 1) == 0 and 32 <= fp_tile_docs <= 16384
         self.fp_tile_docs = int(fp_tile_docs)
         self.fp_n_tiles = (self.n_docs + self.fp_tile_docs - 1) // self.fp_tile_docs

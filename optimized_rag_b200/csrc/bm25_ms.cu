@@ -52,9 +52,16 @@ constexpr int kMsThreads = kMsWarps * 32;
 constexpr int kMsTerms = 32;      // scoring terms per query on this path (one per lane)
 constexpr int kMsAccCap = 1024;   // marked docs per (query, tile sub-range)
 constexpr int kMsSubTarget = 512; // essential postings per sub-range the splitter aims for
+constexpr int kMsStage = 512;     // postings of the essential runs staged in shared memory per pair (multiple of 4)
 constexpr int kMsMaxTile = 16384;
 constexpr int kMsSurvCap = 2048;  // candidates re-scored per query
 constexpr float kMsGuard = 1.0f - 1.0f / 512.0f;
+
+// per-warp shared memory: staging buffer | compact accumulator | bitmap | per-word ranks
+__host__ __device__ inline size_t ms_smem_per_warp(int words)
+{
+    return ((size_t)kMsStage * 4 + (size_t)kMsAccCap * 4 + (size_t)words * 4 + (size_t)words * 2 + 15) & ~(size_t)15;
+}
 
 struct MsParams {
     orag_bm25_index_t ix;
@@ -161,11 +168,18 @@ struct MsDesc {  // lane i = i-th term of the prepared query
     int n, q;
 };
 struct MsRun {
-    int rel;     // first posting of the run relative to the tile's first posting
+    int rel;     // first posting of the run relative to the tile's 16-byte aligned base pointer
     int len;
     float w, pre;
     int n, q;
+    int soff;    // position of the run's first posting in the staging buffer
+    int slen;    // leading postings of the run available in the staging buffer (0 = not staged)
 };
+
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
 
 __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_constant__ MsParams p)
 {
@@ -173,11 +187,13 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
     const int T = p.ix.fp_tile_docs;
     const int words = (T + 31) >> 5;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)words * 4 + (size_t)((words * 2 + 15) & ~15) + (size_t)kMsAccCap * 4;
+    const size_t per_warp = ms_smem_per_warp(words);
     uint8_t *mine = reinterpret_cast<uint8_t *>(ms_smem) + wib * per_warp;
-    uint32_t *bm = reinterpret_cast<uint32_t *>(mine);                                // [words] marked docs
-    float *acc = reinterpret_cast<float *>(mine + (size_t)words * 4);                 // [kMsAccCap], zero between pairs
-    uint16_t *pre = reinterpret_cast<uint16_t *>(mine + (size_t)words * 4 + (size_t)kMsAccCap * 4);  // [words]
+    uint32_t *stage = reinterpret_cast<uint32_t *>(mine);                             // [kMsStage] essential runs
+    float *acc = reinterpret_cast<float *>(mine + (size_t)kMsStage * 4);              // [kMsAccCap], zero between pairs
+    uint32_t *bm = reinterpret_cast<uint32_t *>(mine + (size_t)(kMsStage + kMsAccCap) * 4);  // [words] marked docs
+    uint16_t *pre = reinterpret_cast<uint16_t *>(bm + words);                         // [words] rank of a word's bit 0
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
     for (int i = lane; i < words; i += 32) bm[i] = 0u;
     for (int i = lane; i < kMsAccCap; i += 32) acc[i] = 0.f;
     __syncwarp();
@@ -187,7 +203,7 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
     const unsigned FULL = 0xffffffffu;
     const int S = p.q_split;
     const int4 *qd = reinterpret_cast<const int4 *>(p.qd);
-    const int wpl = (words + 31) >> 5;  // bitmap words per lane in the rank pass
+    const int wpl = (words + 31) >> 5;  // bitmap words per lane in the rank / claim passes
 
     auto rank_of = [&](uint32_t d) -> int {
         const uint32_t wd = bm[d >> 5];
@@ -204,11 +220,14 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
         const int qi0 = (int)(((int64_t)nq * part) / S);
         const int qi1 = (int)(((int64_t)nq * (part + 1)) / S);
         const int64_t base_doc = (int64_t)tile * T;
-        const uint32_t *tp = p.ix.d_postings_r16 + p.ix.d_fp_tile_base[tile];
+        const int64_t tile_g0 = p.ix.d_fp_tile_base[tile];
+        const int tb = (int)(tile_g0 & 3);
+        const uint32_t *tp = p.ix.d_postings_r16 + (tile_g0 - tb);  // 16-byte aligned; run offsets get +tb
         const int32_t *toff = p.ix.d_fp_tile_term_off + (int64_t)tile * V1;
         // stagger the query order across tiles so a query's threshold is established by few warps
         const int q_shift = (int)(((int64_t)tile * 7919) % nq);
 
+        // ---- stage A: the prepared query (one 16-byte load per lane)
         auto stage_desc = [&](int qi) -> MsDesc {
             MsDesc d;
             d.term = -1; d.w = 0.f; d.pre = 0.f; d.n = 0; d.q = 0;
@@ -224,25 +243,70 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
             }
             return d;
         };
+        // ---- stage B: run offsets inside this tile, L2 prefetch of the head of every run
         auto stage_run = [&](const MsDesc &d) -> MsRun {
             MsRun r;
-            r.rel = 0; r.len = 0; r.w = d.w; r.pre = d.pre; r.n = d.n; r.q = d.q;
+            r.rel = 0; r.len = 0; r.w = d.w; r.pre = d.pre; r.n = d.n; r.q = d.q; r.soff = 0; r.slen = 0;
             if (lane < d.n) {
                 r.rel = __ldg(toff + d.term);
                 r.len = __ldg(toff + d.term + 1) - r.rel;
-                if (r.len > 0) prefetch_l2(tp + r.rel);
+                r.rel += tb;
+                if (r.len > 0) {
+                    prefetch_l2(tp + r.rel);
+                    if (r.len > 32) prefetch_l2(tp + r.rel + 32);
+                    if (r.len > 64) prefetch_l2(tp + r.rel + 64);
+                    if (r.len > 96) prefetch_l2(tp + r.rel + 96);
+                }
             }
             return r;
         };
+        // ---- stage C: copy the runs that are (by the threshold as of now) essential into the staging buffer,
+        // most valuable term first, through 16-byte aligned source windows
+        auto stage_posts = [&](MsRun &run) {
+            float thr_now = 0.f;
+            if (run.n > 0) thr_now = thr_to_float(__ldcg(p.thr_bits + run.q));
+            const bool want = lane < run.n && run.len > 0 && !(run.pre < thr_now);
+            const int shift = run.rel & 3;
+            const int alen = want ? ((shift + run.len + 3) & ~3) : 0;
+            int incl = alen;  // suffix sums: lanes above this one come first in the buffer
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_down_sync(FULL, incl, d);
+                if (lane + d < 32) incl += v;
+            }
+            const int excl = incl - alen;
+            const int avail = max(0, min(alen, kMsStage - excl));  // multiple of 4
+            run.soff = excl + shift;
+            run.slen = max(0, min(run.len, avail - shift));
+            const int n16 = run.slen > 0 ? (avail >> 2) : 0;
+            const uint32_t dst_s = stage_s + (uint32_t)excl * 4u;
+            const uint32_t *src = tp + (run.rel & ~3);
+            if (n16 > 0) cp_async16_s(dst_s, src);
+            if (n16 > 1) cp_async16_s(dst_s + 16, src + 4);
+            unsigned active = __ballot_sync(FULL, n16 > 2);
+            while (active) {
+                const int i = __ffs(active) - 1;
+                active &= active - 1;
+                const uint32_t d0 = __shfl_sync(FULL, dst_s, i);
+                const unsigned long long s0 = __shfl_sync(FULL, (unsigned long long)(uintptr_t)src, i);
+                const int cnt = __shfl_sync(FULL, n16, i);
+                const uint32_t *sp = reinterpret_cast<const uint32_t *>((uintptr_t)s0);
+#pragma unroll 1
+                for (int c = 2 + lane; c < cnt; c += 32) cp_async16_s(d0 + 16u * c, sp + 4 * c);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
 
         MsRun cur = stage_run(stage_desc(qi0));
-        MsDesc descA = stage_desc(qi0 + 1);
+        stage_posts(cur);
+        MsRun nxt = stage_run(stage_desc(qi0 + 1));
+        MsDesc descA = stage_desc(qi0 + 2);
 
         for (int qi = qi0; qi < qi1; ++qi) {
             unsigned long long thr_bits = 0;
             if (cur.n > 0) thr_bits = __ldcg(p.thr_bits + cur.q);
-            const MsRun nxt = stage_run(descA);
-            descA = stage_desc(qi + 2);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
 
             const int n = cur.n;  // warp-uniform
             float thr = thr_to_float(thr_bits);
@@ -250,6 +314,7 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
             const bool mine_ok = lane < n && cur.len > 0;
             int n_ne = __popc(__ballot_sync(FULL, lane < n && cur.pre < thr));  // a prefix of the lanes
             unsigned ess = __ballot_sync(FULL, mine_ok && lane >= n_ne);
+            bool staged_next = false;
             if (ess) {
                 int etot = (mine_ok && lane >= n_ne) ? cur.len : 0;
 #pragma unroll
@@ -280,18 +345,28 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                         }
                         s_end = lo;
                     }
+                    // this lane's view of its run in the sub-range: global part + staged prefix
                     const int v_rel = cur.rel + cpos;
                     const int v_len = mine_ok ? s_end - cpos : 0;
+                    const int v_sl = staged_next ? 0 : max(0, min(v_len, cur.slen - cpos));
+                    const int v_so = cur.soff + cpos;
                     cpos = s_end;
 #define MS_VIEW(i)                                         \
     const int len_ = __shfl_sync(FULL, v_len, i);          \
+    const int sl_ = __shfl_sync(FULL, v_sl, i);            \
+    const uint32_t *sp_ = stage + __shfl_sync(FULL, v_so, i); \
     const uint32_t *gp_ = tp + __shfl_sync(FULL, v_rel, i)
                     // ---- E1: mark the docs of the essential runs
                     for (unsigned a = ess; a; a &= a - 1) {
                         const int i = __ffs(a) - 1;
                         MS_VIEW(i);
 #pragma unroll 1
-                        for (int j = lane; j < len_; j += 32) {
+                        for (int j = lane; j < sl_; j += 32) {
+                            const uint32_t d = sp_[j] >> 16;
+                            atomicOr(bm + (d >> 5), 1u << (d & 31));
+                        }
+#pragma unroll 1
+                        for (int j = sl_ + lane; j < len_; j += 32) {
                             const uint32_t d = __ldg(gp_ + j) >> 16;
                             atomicOr(bm + (d >> 5), 1u << (d & 31));
                         }
@@ -310,33 +385,51 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                         if (lane >= o) incl += v;
                     }
                     const int marked = __shfl_sync(FULL, incl, 31);
-                    int run_sum = incl - mycnt;
-                    for (int t = 0; t < wpl; ++t) {
-                        const int wi = lane * wpl + t;
-                        if (wi < words) {
-                            pre[wi] = (uint16_t)run_sum;
-                            run_sum += __popc(bm[wi]);
+                    const int my_base = incl - mycnt;
+                    {
+                        int run_sum = my_base;
+                        for (int t = 0; t < wpl; ++t) {
+                            const int wi = lane * wpl + t;
+                            if (wi < words) {
+                                pre[wi] = (uint16_t)run_sum;
+                                run_sum += __popc(bm[wi]);
+                            }
                         }
                     }
                     __syncwarp();
-                    if (marked <= kMsAccCap) {
+                    const bool fits = marked <= kMsAccCap;
+                    if (fits) {
                         // ---- E2: essential contributions into the compact accumulator
                         for (unsigned a = ess; a; a &= a - 1) {
                             const int i = __ffs(a) - 1;
                             MS_VIEW(i);
                             const float w = __shfl_sync(FULL, cur.w, i);
 #pragma unroll 1
-                            for (int j = lane; j < len_; j += 32) {
+                            for (int j = lane; j < sl_; j += 32) {
+                                const uint32_t post = sp_[j];
+                                float *slot = acc + rank_of(post >> 16);
+                                *slot = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
+                            }
+#pragma unroll 1
+                            for (int j = sl_ + lane; j < len_; j += 32) {
                                 const uint32_t post = __ldg(gp_ + j);
                                 float *slot = acc + rank_of(post >> 16);
                                 *slot = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
                             }
                             __syncwarp();
                         }
-                        // ---- N: non-essential runs complete the marked docs only
+                    }
+                    // the staging buffer is free from here on: start copying the next pair's essential runs
+                    if (!staged_next) {
+                        stage_posts(nxt);
+                        staged_next = true;
+                    }
+                    if (fits) {
+                        // ---- N: non-essential runs complete the marked docs only (streamed, one load ahead)
                         for (unsigned a = non; a; a &= a - 1) {
                             const int i = __ffs(a) - 1;
-                            MS_VIEW(i);
+                            const int len_ = __shfl_sync(FULL, v_len, i);
+                            const uint32_t *gp_ = tp + __shfl_sync(FULL, v_rel, i);
                             const float w = __shfl_sync(FULL, cur.w, i);
                             auto one = [&](uint32_t post) {
                                 const uint32_t d = post >> 16;
@@ -350,48 +443,61 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                             const int head = min(len_, (int)((16u - ((uint32_t)(uintptr_t)gp_ & 15u)) & 15u) >> 2);
                             const int body4 = (len_ - head) >> 2;
                             const int tail = len_ - head - 4 * body4;
+                            const uint4 *g4 = reinterpret_cast<const uint4 *>(gp_ + head);
+                            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+                            if (lane < body4) v0 = __ldg(g4 + lane);
+                            if (lane + 32 < body4) v1 = __ldg(g4 + lane + 32);
                             {
                                 int idx = -1;
                                 if (lane < head) idx = lane;
                                 else if (lane >= 3 && lane - 3 < tail) idx = head + 4 * body4 + (lane - 3);
                                 if (idx >= 0) one(__ldg(gp_ + idx));
                             }
-                            const uint4 *g4 = reinterpret_cast<const uint4 *>(gp_ + head);
-#pragma unroll 2
-                            for (int c = lane; c < body4; c += 32) {
-                                const uint4 v = __ldg(g4 + c);
-                                one(v.x); one(v.y); one(v.z); one(v.w);
+#pragma unroll 1
+                            for (int c = lane; c < body4; c += 64) {
+                                const uint4 u0 = v0, u1 = v1;
+                                if (c + 64 < body4) v0 = __ldg(g4 + c + 64);
+                                if (c + 96 < body4) v1 = __ldg(g4 + c + 96);
+                                one(u0.x); one(u0.y); one(u0.z); one(u0.w);
+                                if (c + 32 < body4) { one(u1.x); one(u1.y); one(u1.z); one(u1.w); }
                             }
                             __syncwarp();
                         }
-                        // ---- X: claim every marked doc once (first essential run that holds it), reset, emit
-                        for (unsigned a = ess; a; a &= a - 1) {
-                            const int i = __ffs(a) - 1;
-                            MS_VIEW(i);
-#pragma unroll 1
-                            for (int j = lane; j < len_; j += 32) {
-                                const uint32_t d = __ldg(gp_ + j) >> 16;
-                                float *slot = acc + rank_of(d);
-                                const float v = *slot;
-                                if (v != 0.f) {
-                                    *slot = 0.f;
-                                    if (v >= thr) ms_emit(p, q, (int32_t)(base_doc + d), v);
+                        // ---- X: every lane claims the marked docs of its own bitmap words: emit, reset
+                        {
+                            int rk = my_base;
+                            for (int t = 0; t < wpl; ++t) {
+                                const int wi = lane * wpl + t;
+                                if (wi >= words) break;
+                                uint32_t wd = bm[wi];
+                                if (wd == 0u) continue;
+                                bm[wi] = 0u;
+                                while (wd) {
+                                    const int b = __ffs(wd) - 1;
+                                    wd &= wd - 1;
+                                    const float v = acc[rk];
+                                    acc[rk] = 0.f;
+                                    ++rk;
+                                    if (v >= thr) ms_emit(p, q, (int32_t)(base_doc + wi * 32 + b), v);
                                 }
                             }
-                            __syncwarp();
                         }
-                    } else if (p.status && lane == 0) {
+                    } else {
                         // a skewed sub-range marked more docs than the accumulator holds: the caller re-runs the query
-                        atomicOr(p.status + q, ORAG_STATUS_OVERFLOW);
+                        if (p.status && lane == 0) atomicOr(p.status + q, ORAG_STATUS_OVERFLOW);
+                        for (int i = lane; i < words; i += 32) bm[i] = 0u;
                     }
 #undef MS_VIEW
-                    // ---- clear the bitmap
-                    for (int i = lane; i < words; i += 32) bm[i] = 0u;
                     __syncwarp();
                 }
             }
+            if (!staged_next) stage_posts(nxt);
             cur = nxt;
+            nxt = stage_run(descA);
+            descA = stage_desc(qi + 3);
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
     }
 }
 
@@ -532,8 +638,7 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
     }
     if (ix->fp_n_tiles > 0) {
         const int words = (ix->fp_tile_docs + 31) / 32;
-        const size_t per_warp = (size_t)words * 4 + (size_t)((words * 2 + 15) & ~15) + (size_t)kMsAccCap * 4;
-        const size_t smem = (size_t)kMsWarps * per_warp;
+        const size_t smem = (size_t)kMsWarps * ms_smem_per_warp(words);
         const int lim = sm_count() * 2;
         // ~8 work items per resident warp so that the atomic hand-out can balance cold and warm pairs
         int64_t want = (int64_t)8 * lim * kMsWarps;
