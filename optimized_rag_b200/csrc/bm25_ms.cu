@@ -82,10 +82,11 @@ struct MsParams {
     int cap;
     int32_t *surv_doc;  // [n_queries, kMsSurvCap]
     double *surv_score; // [n_queries, kMsSurvCap]
-    uint32_t *work;     // [1] next work item
+    uint32_t *work;     // [2] next work item of the seed / main launch
     int32_t *status;    // [n_queries] or null
     int q_split;
     int n_items;
+    int tile_begin;     // this launch covers tiles [tile_begin, tile_begin + n_items / q_split)
 };
 
 // One thread per query: drop OOV / zero-idf tokens, merge duplicates, sort by upper bound.
@@ -215,8 +216,9 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
         if (lane == 0) item = (int)atomicAdd(p.work, 1u);
         item = __shfl_sync(FULL, item, 0);
         if (item >= p.n_items) break;
-        const int tile = item / S;
-        const int part = item - tile * S;
+        const int tile_rel = item / S;
+        const int part = item - tile_rel * S;
+        const int tile = p.tile_begin + tile_rel;
         const int qi0 = (int)(((int64_t)nq * part) / S);
         const int qi1 = (int)(((int64_t)nq * (part + 1)) / S);
         const int64_t base_doc = (int64_t)tile * T;
@@ -463,6 +465,28 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                             }
                             __syncwarp();
                         }
+                        // ---- cold pair: before emitting, derive a threshold from this sub-range alone.  Every lane
+                        // takes the maximum of a strided subset of the marked docs' scores; the k-th largest of the 32
+                        // lane maxima is the score of k distinct docs' worth of evidence, i.e. a lower bound of the k-th
+                        // best approximate score overall -- publish it and emit only what clears it.
+                        if ((nsub > 1 || thr == 0.f) && p.k <= 32 && marked >= 2 * p.k) {
+                            float mx = 0.f;
+                            for (int r = lane; r < marked; r += 32) mx = fmaxf(mx, acc[r]);
+                            float kth = 0.f;
+                            for (int r = 0; r < p.k; ++r) {
+                                float m = mx;
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+                                kth = m;
+                                const unsigned who = __ballot_sync(FULL, mx == m);
+                                if (lane == __ffs(who) - 1) mx = -1.f;
+                            }
+                            if (kth > 0.f) {
+                                const unsigned long long kb = (unsigned long long)__double_as_longlong((double)kth);
+                                if (lane == 0) atomicMax(p.thr_bits + q, kb);
+                                thr = fmaxf(thr, thr_to_float(kb));
+                            }
+                        }
                         // ---- X: every lane claims the marked docs of its own bitmap words: emit, reset
                         {
                             int rk = my_base;
@@ -558,7 +582,7 @@ __global__ void ms_init_state_kernel(unsigned long long *thr_bits, uint32_t *cnt
         cnt[i] = 0;
         topbin[i] = 0;
     }
-    if (i == 0) *work = 0;
+    if (i == 0) work[0] = work[1] = 0;
 }
 
 static int ms_cap(int n_queries)
@@ -640,20 +664,26 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
         const int words = (ix->fp_tile_docs + 31) / 32;
         const size_t smem = (size_t)kMsWarps * ms_smem_per_warp(words);
         const int lim = sm_count() * 2;
-        // ~8 work items per resident warp so that the atomic hand-out can balance cold and warm pairs
-        int64_t want = (int64_t)8 * lim * kMsWarps;
-        int64_t split = (want + ix->fp_n_tiles - 1) / ix->fp_n_tiles;
-        if (split > n_queries) split = n_queries;
-        if (split < 1) split = 1;
-        p.q_split = (int)split;
-        p.n_items = (int)((int64_t)ix->fp_n_tiles * split);
-        int grid = (p.n_items + kMsWarps - 1) / kMsWarps;
-        if (grid > lim) grid = lim;
         ORAG_CUDA_CHECK(cudaFuncSetAttribute(bm25_ms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uint32_t *work = p.work;
         profile_mark(1, 0, st);
-        bm25_ms_kernel<<<grid, kMsThreads, smem, st>>>(p);
+        {
+            const int tiles = ix->fp_n_tiles;
+            // ~8 work items per resident warp so that the atomic hand-out can balance uneven pairs
+            int64_t want = (int64_t)8 * lim * kMsWarps;
+            int64_t split = (want + tiles - 1) / tiles;
+            if (split > n_queries) split = n_queries;
+            if (split < 1) split = 1;
+            p.tile_begin = 0;
+            p.q_split = (int)split;
+            p.n_items = (int)((int64_t)tiles * split);
+            p.work = work;
+            int grid = (p.n_items + kMsWarps - 1) / kMsWarps;
+            if (grid > lim) grid = lim;
+            bm25_ms_kernel<<<grid, kMsThreads, smem, st>>>(p);
+            ORAG_LAUNCH_CHECK();
+        }
         profile_mark(1, 1, st);
-        ORAG_LAUNCH_CHECK();
     }
     ms_finalize_kernel<<<n_queries, 1024, 0, st>>>(p, doc_id_base, normalize, d_out_ids, d_out_scores, d_out_max,
                                                    d_out_status);
