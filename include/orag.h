@@ -200,6 +200,20 @@ int orag_topk_merge(const int64_t *d_cand_ids, const double *d_cand_scores, int 
 int orag_rrf_fuse(const int64_t *d_list_ids, int n_queries, int n_lists, int list_len, int rrf_k, int top_k,
                   int tie_mode, int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_src, void *stream);
 
+/* Everything after the all-gather of a row-sharded hybrid search in one launch: d_gathered is
+ * [n_shards, n_queries, W] int64 with W = 2*fetch_k + 2*kk + 2 holding, per shard and query,
+ * cosine ids | cosine float64 score bits | BM25 ids | BM25 RAW float64 score bits | the shard's max raw
+ * BM25 score bits | ORAG_STATUS_* bits.  Cosine winners are merged by (score desc, id asc); BM25 raw scores
+ * are divided by the global max (or 1.0 if it is <= 0; rag/retrieval.py:343-345) and merged the same way;
+ * the two fetch_k-long lists are fused as in orag_rrf_fuse.  Outputs: fused ids/scores [n_queries, top_k],
+ * d_out_src int32 [n_queries, top_k, 2] (optional), the two merged lists [n_queries, fetch_k], the BM25
+ * divisor [n_queries] and the OR of the shards' status bits [n_queries] (optional).
+ * Limits: n_shards * kk <= 256, fetch_k <= 64, 2 * fetch_k <= 128. */
+int orag_hybrid_merge(const int64_t *d_gathered, int n_shards, int n_queries, int fetch_k, int kk, int rrf_k,
+                      int top_k, int tie_mode, int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_src,
+                      int64_t *d_cos_ids, double *d_cos_scores, int64_t *d_bm25_ids, double *d_bm25_scores,
+                      double *d_bm25_max, int32_t *d_out_status, void *stream);
+
 /* Weighted hybrid score of HybridRetriever.hybrid_search (rag/retrieval.py:302):
  * out[i] = (alpha*sem[i] + beta*kw[i]) + gamma*temp[i] in float64 without contraction
  * (d_temp may be NULL = all zero).  Rank the result with orag_dense_topk. */

@@ -22,7 +22,7 @@ SYMBOLS = [
     "orag_row_inv_norms", "orag_f32_to_bf16",
     "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_dense", "orag_cosine_firstpass_dense",
     "orag_bm25_workspace_bytes", "orag_bm25_topk", "orag_bm25_dense", "orag_dense_topk",
-    "orag_topk_merge", "orag_rrf_fuse", "orag_weighted_sum3", "orag_div_scalar",
+    "orag_topk_merge", "orag_rrf_fuse", "orag_hybrid_merge", "orag_weighted_sum3", "orag_div_scalar",
     "orag_pairwise_workspace_bytes", "orag_pairwise_cosine_threshold",
     "orag_pairwise_tc_workspace_bytes", "orag_pairwise_cosine_threshold_tc",
 ]
@@ -95,6 +95,8 @@ def lib() -> ctypes.CDLL:
     L.orag_dense_topk.argtypes = [vp, c_int64, c_int64, c_int, c_int, c_int64, c_int, vp, vp, vp, vp]
     L.orag_topk_merge.argtypes = [vp, vp, c_int, c_int, c_int, vp, c_int, vp, vp, vp, vp]
     L.orag_rrf_fuse.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp]
+    L.orag_hybrid_merge.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp,
+                                    vp, vp]
     L.orag_weighted_sum3.argtypes = [vp, vp, vp, c_int64, c_double, c_double, c_double, vp, vp]
     L.orag_div_scalar.argtypes = [vp, c_int64, c_double, vp, vp]
     L.orag_pairwise_workspace_bytes.restype = c_size_t

@@ -149,7 +149,10 @@ class Bm25Index:
         # first-pass view: (doc_in_tile << 16) | fp16(r) over (much larger) tiles of `fp_tile_docs` docs
         self.postings_r16 = self.term_max_r = self.fp_tile_base = self.fp_tile_term_off = None
         if fp_tile_docs is None:
-            fp_tile_docs = min(8192, max(32, 1 << max(0, (max(self.n_docs, 1) // 16 - 1).bit_length())))
+            # measured on B200 (scripts/debug_bm25.py): 8192-doc tiles win for multi-million-doc shards, 4096 below
+            # (more pairs in flight, cheaper cold start); tiny corpora keep >= 16 tiles
+            cap = 8192 if self.n_docs >= 4_000_000 else 4096
+            fp_tile_docs = min(cap, max(32, 1 << max(0, (max(self.n_docs, 1) // 16 - 1).bit_length())))
         assert fp_tile_docs & (fp_tile_docs - 1) == 0 and 32 <= fp_tile_docs <= 16384
         self.fp_tile_docs = int(fp_tile_docs)
         self.fp_n_tiles = (self.n_docs + self.fp_tile_docs - 1) // self.fp_tile_docs

@@ -14,22 +14,18 @@ namespace orag {
 constexpr int kRrfMaxUnion = 128;
 constexpr int kRrfMaxLists = 8;
 
-__global__ void __launch_bounds__(128) rrf_kernel(const int64_t *__restrict__ list_ids, int n_queries, int n_lists,
-                                                 int list_len, int rrf_k, int top_k, int tie_mode,
-                                                 int64_t *__restrict__ out_ids, double *__restrict__ out_scores,
-                                                 int32_t *__restrict__ out_src)
+// Fuses the lists of ONE query.  base[l * list_stride + r] = id at rank r+1 of list l (id < 0 = tail padding).
+__device__ inline void rrf_one(const int64_t *base, int n_lists, int list_len, int list_stride, int rrf_k, int top_k,
+                               int tie_mode, int64_t *out_ids, double *out_scores, int32_t *out_src)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_queries) return;
     int64_t keys[kRrfMaxUnion];
     double sc[kRrfMaxUnion];
     uint8_t src[kRrfMaxUnion][kRrfMaxLists];
     uint8_t ord[kRrfMaxUnion];
     int m = 0;
-    const int64_t *base = list_ids + (int64_t)q * n_lists * list_len;
     for (int l = 0; l < n_lists; ++l) {
         for (int r = 0; r < list_len; ++r) {
-            const int64_t id = base[l * list_len + r];
+            const int64_t id = base[l * list_stride + r];
             if (id < 0) break;  // tail padding
             const double c = __ddiv_rn(1.0, (double)(rrf_k + r + 1));
             int j = 0;
@@ -62,10 +58,104 @@ __global__ void __launch_bounds__(128) rrf_kernel(const int64_t *__restrict__ li
     for (int r = 0; r < top_k; ++r) {
         const bool have = r < m;
         const int e = have ? ord[r] : 0;
-        out_ids[(int64_t)q * top_k + r] = have ? keys[e] : -1;
-        out_scores[(int64_t)q * top_k + r] = have ? sc[e] : 0.0;
+        out_ids[r] = have ? keys[e] : -1;
+        out_scores[r] = have ? sc[e] : 0.0;
         if (out_src)
-            for (int l = 0; l < n_lists; ++l) out_src[((int64_t)q * top_k + r) * n_lists + l] = have ? src[e][l] : 0;
+            for (int l = 0; l < n_lists; ++l) out_src[r * n_lists + l] = have ? src[e][l] : 0;
+    }
+}
+
+__global__ void __launch_bounds__(128) rrf_kernel(const int64_t *__restrict__ list_ids, int n_queries, int n_lists,
+                                                 int list_len, int rrf_k, int top_k, int tie_mode,
+                                                 int64_t *__restrict__ out_ids, double *__restrict__ out_scores,
+                                                 int32_t *__restrict__ out_src)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries) return;
+    rrf_one(list_ids + (int64_t)q * n_lists * list_len, n_lists, list_len, list_len, rrf_k, top_k, tie_mode,
+            out_ids + (int64_t)q * top_k, out_scores + (int64_t)q * top_k,
+            out_src ? out_src + (int64_t)q * top_k * n_lists : nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Everything that follows the all-gather of a row-sharded hybrid search, in ONE launch (one 64-thread
+// CTA per query): merge the G shards' cosine winners by (score desc, id asc); divide the shards' raw
+// BM25 winners by the GLOBAL max raw score (rag/retrieval.py:343-345) and merge them the same way;
+// fuse the two lists with RRF.  The gathered buffer is [G, B, W] int64 with
+// W = 2*fetch_k + 2*kk + 2: cosine ids | cosine score bits | BM25 ids | BM25 raw score bits |
+// shard max raw BM25 score bits | status bits (optimized_rag_b200/dist.py pack_local).
+constexpr int kMergeMax = 256;  // candidates of one kind per query (G * kk)
+
+__global__ void __launch_bounds__(64) hybrid_merge_kernel(const int64_t *__restrict__ gathered, int G, int B, int fetch_k,
+                                                         int kk, int rrf_k, int top_k, int tie_mode,
+                                                         int64_t *__restrict__ out_ids, double *__restrict__ out_scores,
+                                                         int32_t *__restrict__ out_src, int64_t *__restrict__ cos_ids,
+                                                         double *__restrict__ cos_scores, int64_t *__restrict__ bm_ids,
+                                                         double *__restrict__ bm_scores, double *__restrict__ bm_max,
+                                                         int32_t *__restrict__ out_status)
+{
+    __shared__ int64_t c_id[kMergeMax];
+    __shared__ double c_sc[kMergeMax];
+    __shared__ int64_t lists[2 * 128];  // [2][fetch_k] merged lists for the RRF step
+    __shared__ double l_sc[2 * 128];
+    __shared__ double s_max;
+    __shared__ int s_status;
+    const int q = blockIdx.x;
+    const int W = 2 * fetch_k + 2 * kk + 2;
+    if (threadIdx.x == 0) {
+        double mx = -INFINITY;
+        int st = 0;
+        for (int g = 0; g < G; ++g) {
+            const int64_t *row = gathered + ((int64_t)g * B + q) * W;
+            mx = fmax(mx, __longlong_as_double(row[2 * fetch_k + 2 * kk]));
+            st |= (int)row[2 * fetch_k + 2 * kk + 1];
+        }
+        s_max = mx > 0.0 ? mx : 1.0;
+        s_status = st;
+    }
+    for (int kind = 0; kind < 2; ++kind) {
+        const int per = kind == 0 ? fetch_k : kk;
+        const int off = kind == 0 ? 0 : 2 * fetch_k;
+        const int n = G * per;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int g = i / per, r = i - g * per;
+            const int64_t *row = gathered + ((int64_t)g * B + q) * W + off;
+            c_id[i] = row[r];
+            const double v = __longlong_as_double(row[per + r]);
+            c_sc[i] = kind == 0 ? v : __ddiv_rn(v, s_max);
+        }
+        for (int i = threadIdx.x; i < fetch_k; i += blockDim.x) {
+            lists[kind * fetch_k + i] = -1;
+            l_sc[kind * fetch_k + i] = 0.0;
+        }
+        __syncthreads();
+        // rank of every candidate = number of candidates that rank strictly before it (ids are unique)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int64_t id = c_id[i];
+            if (id < 0) continue;
+            const double v = c_sc[i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j)
+                if (c_id[j] >= 0 && ranks_before(c_sc[j], c_id[j], v, id)) ++rank;
+            if (rank < fetch_k) {
+                lists[kind * fetch_k + rank] = id;
+                l_sc[kind * fetch_k + rank] = v;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < fetch_k; i += blockDim.x) {
+        cos_ids[(int64_t)q * fetch_k + i] = lists[i];
+        cos_scores[(int64_t)q * fetch_k + i] = l_sc[i];
+        bm_ids[(int64_t)q * fetch_k + i] = lists[fetch_k + i];
+        bm_scores[(int64_t)q * fetch_k + i] = l_sc[fetch_k + i];
+    }
+    if (threadIdx.x == 0) {
+        bm_max[q] = s_max;
+        if (out_status) out_status[q] = s_status;
+        rrf_one(lists, 2, fetch_k, fetch_k, rrf_k, top_k, tie_mode, out_ids + (int64_t)q * top_k,
+                out_scores + (int64_t)q * top_k, out_src ? out_src + (int64_t)q * top_k * 2 : nullptr);
     }
 }
 
@@ -82,6 +172,25 @@ extern "C" int orag_rrf_fuse(const int64_t *d_list_ids, int n_queries, int n_lis
     if (n_queries == 0) return ORAG_OK;
     orag::rrf_kernel<<<(n_queries + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         d_list_ids, n_queries, n_lists, list_len, rrf_k, top_k, tie_mode, d_out_ids, d_out_scores, d_out_src);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+extern "C" int orag_hybrid_merge(const int64_t *d_gathered, int n_shards, int n_queries, int fetch_k, int kk, int rrf_k,
+                                 int top_k, int tie_mode, int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_src,
+                                 int64_t *d_cos_ids, double *d_cos_scores, int64_t *d_bm25_ids, double *d_bm25_scores,
+                                 double *d_bm25_max, int32_t *d_out_status, void *stream)
+{
+    ORAG_REQUIRE(d_gathered && d_out_ids && d_out_scores && d_cos_ids && d_cos_scores && d_bm25_ids && d_bm25_scores &&
+                     d_bm25_max,
+                 "hybrid_merge pointers");
+    ORAG_REQUIRE(n_shards >= 1 && n_queries >= 0 && fetch_k >= 1 && kk >= fetch_k && top_k >= 1 && rrf_k >= 0,
+                 "hybrid_merge sizes");
+    ORAG_REQUIRE(n_shards * kk <= orag::kMergeMax && fetch_k <= 64, "n_shards * kk <= 256 and fetch_k <= 64");
+    if (n_queries == 0) return ORAG_OK;
+    orag::hybrid_merge_kernel<<<n_queries, 64, 0, (cudaStream_t)stream>>>(
+        d_gathered, n_shards, n_queries, fetch_k, kk, rrf_k, top_k, tie_mode, d_out_ids, d_out_scores, d_out_src,
+        d_cos_ids, d_cos_scores, d_bm25_ids, d_bm25_scores, d_bm25_max, d_out_status);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }

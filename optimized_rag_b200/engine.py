@@ -276,36 +276,54 @@ class HybridShard:
         self.cosine = cosine
         self.bm25 = bm25
         self.rrf_k = rrf_k
+        self._side = None
 
     def local_lists(self, query_emb: torch.Tensor, query_terms: torch.Tensor, query_lens: torch.Tensor, fetch_k: int,
-                    bm25_k: int, normalize: bool, check_overflow: bool = True):
-        """Cosine top-fetch_k and BM25 top-bm25_k of this shard.  Both kernels pipelines are enqueued back to
-        back; candidate-buffer overflow of either is checked with ONE host sync afterwards and the affected
-        queries are re-run through the exact dense kernels (still on the GPU)."""
-        st: list = []
-        ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=False, status_out=st)
-        bi, bs, bmax = self.bm25.topk(query_terms, query_lens, bm25_k, normalize=normalize, check_overflow=False,
-                                      status_out=st)
-        if check_overflow:
-            bad_c, bad_b = st[0] != 0, st[1] != 0
-            any_bad = torch.stack([bad_c.any(), bad_b.any()]).cpu()
-            if bool(any_bad[0]):
-                bad = torch.nonzero(bad_c).flatten()
-                i2, s2 = self.cosine.topk(query_emb[bad].contiguous(), fetch_k, mode="exact", check_overflow=False)
-                ci[bad], cs[bad] = i2, s2
-            if bool(any_bad[1]):
-                bad = torch.nonzero(bad_b).flatten()
-                i2, s2, m2 = self.bm25.topk(query_terms[bad].contiguous(), query_lens[bad].contiguous(), bm25_k,
-                                            normalize, force="dense", check_overflow=False)
-                bi[bad], bs[bad], bmax[bad] = i2, s2, m2
+                    bm25_k: int, normalize: bool):
+        """Cosine top-fetch_k and BM25 top-bm25_k of this shard, enqueued WITHOUT any host synchronisation.
+        The BM25 pipeline runs on a side stream next to the cosine pipeline, so the small latency-bound kernels
+        of either (query norms, candidate re-score, selection, finalize) overlap the other's main kernel.
+        Returns (cos ids, cos scores, bm25 ids, bm25 scores, bm25 max, status) where status int32 [B] is the OR
+        of both candidate-overflow flags; callers check it once, at the end of the whole step (`repair`)."""
+        dev = query_emb.device
+        cur = torch.cuda.current_stream(dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)
+        side = self._side
+        side.wait_stream(cur)
+        st_c: list = []
+        st_b: list = []
+        with torch.cuda.stream(side):
+            bi, bs, bmax = self.bm25.topk(query_terms, query_lens, bm25_k, normalize=normalize, check_overflow=False,
+                                          status_out=st_b)
+        ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=False, status_out=st_c)
+        cur.wait_stream(side)
+        status = st_c[0] | st_b[0]
+        return ci, cs, bi, bs, bmax, status
+
+    def exact_lists(self, query_emb: torch.Tensor, query_terms: torch.Tensor, query_lens: torch.Tensor, fetch_k: int,
+                    bm25_k: int, normalize: bool):
+        """The same lists through the exhaustive kernels (exact float64 scan, dense BM25): the repair path for
+        queries whose candidate buffers overflowed (thousands of duplicate rows / near-ties).  Still on the GPU."""
+        ci, cs = self.cosine.topk(query_emb, fetch_k, mode="exact", check_overflow=False)
+        bi, bs, bmax = self.bm25.topk(query_terms, query_lens, bm25_k, normalize, force="dense", check_overflow=False)
         return ci, cs, bi, bs, bmax
 
     def search(self, query_emb: torch.Tensor, query_terms: torch.Tensor, query_lens: torch.Tensor, k: int = 10,
                fetch_k: int | None = None, check_overflow: bool = True):
         fetch_k = fetch_k or k
-        ci, cs, bi, bs, bmax = self.local_lists(query_emb, query_terms, query_lens, fetch_k, fetch_k, True,
-                                                check_overflow)
+        ci, cs, bi, bs, bmax, status = self.local_lists(query_emb, query_terms, query_lens, fetch_k, fetch_k, True)
         lists = torch.stack([ci, bi], dim=1).contiguous()
         fi, fs, src = rrf_fuse(lists, self.rrf_k, k, want_src=True)
-        return {"ids": fi, "rrf_scores": fs, "src_ranks": src, "cos_ids": ci, "cos_scores": cs, "bm25_ids": bi,
-                "bm25_scores": bs, "bm25_max": bmax}
+        out = {"ids": fi, "rrf_scores": fs, "src_ranks": src, "cos_ids": ci, "cos_scores": cs, "bm25_ids": bi,
+               "bm25_scores": bs, "bm25_max": bmax}
+        # one host round trip per step, after everything has been enqueued (the caller reads the result anyway)
+        if check_overflow and bool(status.any()):
+            bad = torch.nonzero(status).flatten()
+            ci2, cs2, bi2, bs2, bm2 = self.exact_lists(query_emb[bad].contiguous(), query_terms[bad].contiguous(),
+                                                       query_lens[bad].contiguous(), fetch_k, fetch_k, True)
+            f2, s2, r2 = rrf_fuse(torch.stack([ci2, bi2], dim=1).contiguous(), self.rrf_k, k, want_src=True)
+            for key, val in (("ids", f2), ("rrf_scores", s2), ("src_ranks", r2), ("cos_ids", ci2), ("cos_scores", cs2),
+                             ("bm25_ids", bi2), ("bm25_scores", bs2), ("bm25_max", bm2)):
+                out[key][bad] = val
+        return out

@@ -60,11 +60,12 @@ def _worker(rank, world, port, out_q):
             m = raw.max() if raw.max() > 0 else 1.0
             want.append((oracle.topk(cos, K), oracle.topk(raw / m, K), m))
         mine = pack_local(torch.from_numpy(ci), torch.from_numpy(cs), torch.from_numpy(bi), torch.from_numpy(bs),
-                          torch.from_numpy(bm))
+                          torch.from_numpy(bm), torch.full((NQ,), rank, dtype=torch.int32))
         buf = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64)
         dist.all_gather_into_tensor(buf.view(-1), mine.view(-1))
-        gci, gcs, gbi, gbs, gbm = unpack_gathered(buf, K, kk)
+        gci, gcs, gbi, gbs, gbm, gst = unpack_gathered(buf, K, kk)
         assert gci.shape == (NQ, world * K) and gbm.shape == (NQ, world)
+        assert gst.tolist() == [list(range(world))] * NQ  # status column travels with the winners
         for b in range(NQ):
             order = sorted(np.nonzero(gci[b].numpy() >= 0)[0], key=lambda j: (-gcs[b, j].item(), gci[b, j].item()))[:K]
             assert gci[b, order].tolist() == want[b][0][0].tolist()

@@ -266,6 +266,38 @@ def test_topk_merge(eng):
         assert gs[b].cpu().numpy()[:len(order)].tolist() == norm[order].tolist()
 
 
+def test_hybrid_merge_equals_merge_then_rrf(eng):
+    """The single post-all-gather launch (orag_hybrid_merge) == the step-by-step path it replaces, which is
+    itself pinned to the oracle above (topk_merge with global-max normalisation, then rrf_fuse)."""
+    from optimized_rag_b200.dist import hybrid_merge, pack_local, unpack_gathered
+    rng = np.random.default_rng(11)
+    G, B, fk, kk, k = 4, 37, 10, 16, 10
+    shards = []
+    for g in range(G):
+        ci = np.stack([rng.permutation(500)[:fk] + 1000 * g for _ in range(B)]).astype(np.int64)
+        cs = rng.integers(0, 6, (B, fk)).astype(np.float64) / 8.0          # many exact ties across shards
+        bi = np.stack([rng.permutation(500)[:kk] + 1000 * g for _ in range(B)]).astype(np.int64)
+        bs = rng.integers(1, 9, (B, kk)).astype(np.float64) / 3.0
+        if g == 1:
+            ci[:, fk - 2:] = -1   # a shard with fewer than fetch_k rows
+            bi[5, :] = -1         # a shard where the query matched nothing
+            bs[5, :] = 0.0
+        bm = np.where((bi >= 0).any(1), np.where(bi >= 0, bs, 0).max(1), 0.0)
+        st = np.zeros(B, np.int32)
+        st[7] = 1 if g == 2 else 0
+        shards.append(pack_local(_t(ci), _t(cs), _t(bi), _t(bs), _t(bm), _t(st)))
+    buf = torch.stack(shards).contiguous()
+    out, status = hybrid_merge(buf, fk, kk, 60, k)
+    gci, gcs, gbi, gbs, gbm, gst = unpack_gathered(buf, fk, kk)
+    ci, cs, _ = eng.topk_merge(gci, gcs, fk)
+    bi, bs, bmax = eng.topk_merge(gbi, gbs, fk, shard_max=gbm)
+    fi, fs, src = eng.rrf_fuse(torch.stack([ci, bi], dim=1).contiguous(), 60, k, want_src=True)
+    for key, want in (("cos_ids", ci), ("cos_scores", cs), ("bm25_ids", bi), ("bm25_scores", bs), ("bm25_max", bmax),
+                      ("ids", fi), ("rrf_scores", fs), ("src_ranks", src)):
+        assert torch.equal(out[key], want), key
+    assert status.cpu().tolist() == [1 if b == 7 else 0 for b in range(B)]
+
+
 # ------------------------------------------------------------------------------------------------ pairwise / config 1 / hybrid
 def test_pairwise_golden(eng, golden):
     g = golden["pairwise"]
