@@ -103,6 +103,14 @@ int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, const void 
                      int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_status, void *d_workspace,
                      size_t workspace_bytes, void *stream);
 
+/* Co-scheduling hook: with orag_cosine_mark_prescan(1), every orag_cosine_topk in a tensor-core mode records an
+ * internal CUDA event on its stream right BEFORE launching the main scan kernel; orag_stream_wait_prescan(s) makes
+ * stream s wait for that event (cudaStreamWaitEvent; no host sync).  A BM25 call enqueued on s afterwards with
+ * ORAG_BM25_BACKGROUND starts once the scan's CTAs are (about to be) resident and fills the SM resources the scan
+ * leaves idle, instead of grabbing the SMs first and delaying the scan. */
+int orag_cosine_mark_prescan(int enable);
+int orag_stream_wait_prescan(void *stream);
+
 /* Dense float64 cosine matrix, d_out[q * n_rows + r] (test / small-N helper; same arithmetic).
  * d_out must hold n_queries * n_rows + n_queries doubles (the tail receives sum(q*q) per query). */
 int orag_cosine_dense(const float *d_corpus, int64_t n_rows, int dim, const float *d_queries, int n_queries,
@@ -164,6 +172,9 @@ typedef struct orag_bm25_index {
 #define ORAG_BM25_FORCE_DENSE 4  /* dense accumulate + exact select (small N, negative idf, fallback) */
 #define ORAG_BM25_EXACT_TILES 8  /* candidate path through the float64 scatter kernel even when the index carries
                                     the fp16 first-pass view (A/B tests; queries longer than 32 terms use it anyway) */
+#define ORAG_BM25_BACKGROUND 16  /* size the first-pass launch (8-warp CTAs, < 31 KB shared memory) so that it runs NEXT TO a
+                                    resident cosine scan CTA on every SM instead of after it; meant for a side stream,
+                                    enqueued after orag_stream_wait_prescan (below) */
 size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *index, int n_queries, int k, int flags);
 int orag_bm25_topk(const orag_bm25_index_t *index, int64_t doc_id_base, const int32_t *d_query_terms,
                    const int32_t *d_query_lens, int n_queries, int max_terms, int k, int flags,

@@ -149,10 +149,9 @@ class Bm25Index:
         # first-pass view: (doc_in_tile << 16) | fp16(r) over (much larger) tiles of `fp_tile_docs` docs
         self.postings_r16 = self.term_max_r = self.fp_tile_base = self.fp_tile_term_off = None
         if fp_tile_docs is None:
-            # measured on B200 (scripts/debug_bm25.py): 8192-doc tiles win for multi-million-doc shards, 4096 below
-            # (more pairs in flight, cheaper cold start); tiny corpora keep >= 16 tiles
-            cap = 8192 if self.n_docs >= 4_000_000 else 4096
-            fp_tile_docs = min(cap, max(32, 1 << max(0, (max(self.n_docs, 1) // 16 - 1).bit_length())))
+            # measured on B200 (scripts/debug_bm25.py): 4096..8192-doc tiles are within 5 % of each other stand-alone;
+            # 4096 keeps the per-warp bitmap small enough for the background configuration (csrc/bm25_ms.cu)
+            fp_tile_docs = min(4096, max(32, 1 << max(0, (max(self.n_docs, 1) // 16 - 1).bit_length())))
         assert fp_tile_docs & (fp_tile_docs - 1) == 0 and 32 <= fp_tile_docs <= 16384
         self.fp_tile_docs = int(fp_tile_docs)
         self.fp_n_tiles = (self.n_docs + self.fp_tile_docs - 1) // self.fp_tile_docs
@@ -243,7 +242,8 @@ class Bm25Index:
         return self._ws
 
     def topk(self, query_terms: torch.Tensor, query_lens: torch.Tensor, k: int, normalize: bool = True,
-             force: str | None = None, check_overflow: bool = True, status_out: list | None = None):
+             force: str | None = None, check_overflow: bool = True, status_out: list | None = None,
+             background: bool = False):
         """query_terms int32 [B, max_terms] (negative = OOV/padding), query_lens int32 [B].
         `status_out` (a list) receives the per-query status tensor so that a caller can defer the overflow
         check and pay one host sync for several calls (see engine.HybridShard.local_lists).
@@ -254,6 +254,8 @@ class Bm25Index:
         flags = (_ffi.ORAG_BM25_NORMALIZE if normalize else 0)
         flags |= {None: 0, "sparse": _ffi.ORAG_BM25_FORCE_SPARSE, "dense": _ffi.ORAG_BM25_FORCE_DENSE,
                   "exact_tiles": _ffi.ORAG_BM25_FORCE_SPARSE | _ffi.ORAG_BM25_EXACT_TILES}[force]
+        if background:
+            flags |= _ffi.ORAG_BM25_BACKGROUND
         ids = torch.empty((Bq, k), dtype=torch.int64, device=self.device)
         sc = torch.empty((Bq, k), dtype=torch.float64, device=self.device)
         mx = torch.empty(Bq, dtype=torch.float64, device=self.device)

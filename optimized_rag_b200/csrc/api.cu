@@ -38,6 +38,10 @@ void profile_mark(int slot, int end, cudaStream_t st)
     if (end) g_ev_used[slot] = 1;
 }
 
+// ---- co-scheduling hook ---------------------------------------------------------------------------
+static int g_mark_prescan = 0;
+static cudaEvent_t g_prescan_ev = nullptr;
+
 // First-pass error bounds in cosine units (DESIGN.md "exactness of the first pass"):
 //   tf32: operands truncated to 10 mantissa bits -> |rel err per product| < 2^-9 + 2^-20
 //   bf16: operands rounded to nearest, 8 bits      -> |rel err per product| < 2^-8 + 2^-18
@@ -246,7 +250,11 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
         rc = tc::launch_seed_finalize(w.seed, n_seed, nq, k, margin, w.qnorm, w.inv_qnorm, w.thr_key, w.cnt, w.hist,
                                       w.cand, kCandCap, st);
         if (rc) return rc;
-        // main scan over the rest of the shard
+        // main scan over the rest of the shard (co-scheduling hook: see orag_cosine_mark_prescan)
+        if (g_mark_prescan) {
+            if (!g_prescan_ev) ORAG_CUDA_CHECK(cudaEventCreateWithFlags(&g_prescan_ev, cudaEventDisableTiming));
+            ORAG_CUDA_CHECK(cudaEventRecord(g_prescan_ev, st));
+        }
         p.row_begin = n_seed;
         p.row_end = n_rows;
         p.dense = 0;
@@ -300,4 +308,17 @@ extern "C" size_t orag_pairwise_workspace_bytes(int64_t m, int dim)
 {
     (void)dim;
     return align_up((size_t)(m > 0 ? m : 1) * 8, 256);
+}
+
+extern "C" int orag_cosine_mark_prescan(int enable)
+{
+    orag::g_mark_prescan = enable ? 1 : 0;
+    return ORAG_OK;
+}
+
+extern "C" int orag_stream_wait_prescan(void *stream)
+{
+    if (!orag::g_prescan_ev) return ORAG_OK;  // nothing recorded yet: nothing to wait for
+    ORAG_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, orag::g_prescan_ev, 0));
+    return ORAG_OK;
 }

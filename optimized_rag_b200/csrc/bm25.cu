@@ -532,7 +532,8 @@ extern "C" int orag_bm25_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, 
     // ---- sparse (candidate) paths ----
     if (orag::bm25::ms_eligible(ix, max_terms, flags))
         return orag::bm25::ms_topk(ix, doc_id_base, d_query_terms, d_query_lens, n_queries, max_terms, k, normalize,
-                                   d_out_ids, d_out_scores, d_out_max, d_out_status, d_workspace, st);
+                                   (flags & ORAG_BM25_BACKGROUND) != 0, d_out_ids, d_out_scores, d_out_max,
+                                   d_out_status, d_workspace, st);
     const int cap = sparse_cap(n_queries);
     uint8_t *w = (uint8_t *)d_workspace;
     Params p{};

@@ -47,20 +47,25 @@
 namespace orag {
 namespace bm25 {
 
-constexpr int kMsWarps = 12;
+constexpr int kMsWarps = 12;      // warps per CTA of the stand-alone configuration (2 CTAs per SM)
 constexpr int kMsThreads = kMsWarps * 32;
+constexpr int kMsBgWarps = 8;     // ... and of the background configuration (see ms_topk)
 constexpr int kMsTerms = 32;      // scoring terms per query on this path (one per lane)
-constexpr int kMsAccCap = 1024;   // marked docs per (query, tile sub-range)
-constexpr int kMsSubTarget = 512; // essential postings per sub-range the splitter aims for
-constexpr int kMsStage = 512;     // postings of the essential runs staged in shared memory per pair (multiple of 4)
+// per-warp working set: {marked docs per (query, tile sub-range), essential postings per sub-range the splitter
+// aims for, postings of the essential runs staged in shared memory per pair (multiple of 4)}
+struct MsShape {
+    int acc_cap, sub_target, stage;
+};
+constexpr MsShape kMsAlone = {1024, 512, 512};
+constexpr MsShape kMsBackground = {512, 256, 256};
 constexpr int kMsMaxTile = 16384;
 constexpr int kMsSurvCap = 2048;  // candidates re-scored per query
 constexpr float kMsGuard = 1.0f - 1.0f / 512.0f;
 
 // per-warp shared memory: staging buffer | compact accumulator | bitmap | per-word ranks
-__host__ __device__ inline size_t ms_smem_per_warp(int words)
+__host__ __device__ inline size_t ms_smem_per_warp(int words, const MsShape &sh)
 {
-    return ((size_t)kMsStage * 4 + (size_t)kMsAccCap * 4 + (size_t)words * 4 + (size_t)words * 2 + 15) & ~(size_t)15;
+    return ((size_t)sh.stage * 4 + (size_t)sh.acc_cap * 4 + (size_t)words * 4 + (size_t)words * 2 + 15) & ~(size_t)15;
 }
 
 struct MsParams {
@@ -87,6 +92,7 @@ struct MsParams {
     int q_split;
     int n_items;
     int tile_begin;     // this launch covers tiles [tile_begin, tile_begin + n_items / q_split)
+    MsShape shape;
 };
 
 // One thread per query: drop OOV / zero-idf tokens, merge duplicates, sort by upper bound.
@@ -188,7 +194,8 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
     const int T = p.ix.fp_tile_docs;
     const int words = (T + 31) >> 5;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t per_warp = ms_smem_per_warp(words);
+    const int kMsStage = p.shape.stage, kMsAccCap = p.shape.acc_cap, kMsSubTarget = p.shape.sub_target;
+    const size_t per_warp = ms_smem_per_warp(words, p.shape);
     uint8_t *mine = reinterpret_cast<uint8_t *>(ms_smem) + wib * per_warp;
     uint32_t *stage = reinterpret_cast<uint32_t *>(mine);                             // [kMsStage] essential runs
     float *acc = reinterpret_cast<float *>(mine + (size_t)kMsStage * 4);              // [kMsAccCap], zero between pairs
@@ -640,8 +647,9 @@ size_t ms_workspace_bytes(const orag_bm25_index_t *ix, int n_queries)
 }
 
 int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_query_terms,
-            const int32_t *d_query_lens, int n_queries, int max_terms, int k, int normalize, int64_t *d_out_ids,
-            double *d_out_scores, double *d_out_max, int32_t *d_out_status, void *d_workspace, cudaStream_t st)
+            const int32_t *d_query_lens, int n_queries, int max_terms, int k, int normalize, bool background,
+            int64_t *d_out_ids, double *d_out_scores, double *d_out_max, int32_t *d_out_status, void *d_workspace,
+            cudaStream_t st)
 {
     MsParams p = ms_carve(d_workspace, n_queries).p;
     p.ix = *ix;
@@ -662,7 +670,14 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
     }
     if (ix->fp_n_tiles > 0) {
         const int words = (ix->fp_tile_docs + 31) / 32;
-        const size_t smem = (size_t)kMsWarps * ms_smem_per_warp(words);
+        // Stand-alone: 2 CTAs x 12 warps per SM.  Background (ORAG_BM25_BACKGROUND): CTAs of 8 warps and < 31 KB of
+        // shared memory, so that ONE of them fits next to a resident CTA of the cosine scan (199.9 KB, 384 threads,
+        // 96 registers) -- the issue-bound BM25 pass then rides along the tensor-bound scan on the SM resources
+        // the scan leaves idle; at most two per SM once the scan has left, which keeps registers free for the
+        // small re-score / selection kernels of the cosine pipeline.
+        const int warps = background ? kMsBgWarps : kMsWarps;
+        p.shape = background ? kMsBackground : kMsAlone;
+        const size_t smem = (size_t)warps * ms_smem_per_warp(words, p.shape);
         const int lim = sm_count() * 2;
         ORAG_CUDA_CHECK(cudaFuncSetAttribute(bm25_ms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         uint32_t *work = p.work;
@@ -670,7 +685,7 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
         {
             const int tiles = ix->fp_n_tiles;
             // ~8 work items per resident warp so that the atomic hand-out can balance uneven pairs
-            int64_t want = (int64_t)8 * lim * kMsWarps;
+            int64_t want = (int64_t)8 * lim * warps;
             int64_t split = (want + tiles - 1) / tiles;
             if (split > n_queries) split = n_queries;
             if (split < 1) split = 1;
@@ -678,9 +693,9 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
             p.q_split = (int)split;
             p.n_items = (int)((int64_t)tiles * split);
             p.work = work;
-            int grid = (p.n_items + kMsWarps - 1) / kMsWarps;
+            int grid = (p.n_items + warps - 1) / warps;
             if (grid > lim) grid = lim;
-            bm25_ms_kernel<<<grid, kMsThreads, smem, st>>>(p);
+            bm25_ms_kernel<<<grid, warps * 32, smem, st>>>(p);
             ORAG_LAUNCH_CHECK();
         }
         profile_mark(1, 1, st);

@@ -139,8 +139,9 @@ __device__ inline void select_from_list(const orag_bm25_index_t &ix, const int32
 bool ms_eligible(const orag_bm25_index_t *ix, int max_terms, int flags);
 size_t ms_workspace_bytes(const orag_bm25_index_t *ix, int n_queries);
 int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_query_terms,
-            const int32_t *d_query_lens, int n_queries, int max_terms, int k, int normalize, int64_t *d_out_ids,
-            double *d_out_scores, double *d_out_max, int32_t *d_out_status, void *d_workspace, cudaStream_t st);
+            const int32_t *d_query_lens, int n_queries, int max_terms, int k, int normalize, bool background,
+            int64_t *d_out_ids, double *d_out_scores, double *d_out_max, int32_t *d_out_status, void *d_workspace,
+            cudaStream_t st);
 
 }  // namespace bm25
 }  // namespace orag
