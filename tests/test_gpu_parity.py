@@ -452,6 +452,75 @@ def test_bm25_long_and_degenerate_queries(eng):
     assert torch.equal(one[0][0], ids[0])
 
 
+def _check_bm25_vs_oracle(ix, orc, qt, ql, force, k=10, **kw):
+    ids, sc, mx = ix.topk(_t(qt), _t(ql), k, force=force, **kw)
+    for b in range(qt.shape[0]):
+        norm, m = orc.scores(qt[b, :ql[b]])
+        wi, wv = oracle.topk(norm, k, id_base=ix.doc_id_base)
+        assert np.array_equal(ids[b].cpu().numpy(), wi), (force, kw, b)
+        assert np.array_equal(_bits(sc[b].cpu().numpy()), _bits(wv)), (force, kw, b)
+        assert float(mx[b]) == m
+
+
+@pytest.mark.parametrize("fp_tile", [32, 256, 4096, 16384])
+def test_bm25_first_pass_tile_sizes_and_shapes(eng, fp_tile):
+    """MaxScore first pass (csrc/bm25_ms.cu) over every first-pass tile size, in the stand-alone and in the
+    background working-set shape, with queries of up to 32 tokens incl. repeated and OOV tokens."""
+    from optimized_rag_b200.bm25_index import Bm25Index
+    vocab, n = 3000, 40000
+    thr = syn.zipf_thresholds(vocab)
+    doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, 30, 90, thr)
+    ix = Bm25Index(_t(doc_off), _t(tok), vocab, tile_docs=1024, fp_tile_docs=fp_tile, doc_id_base=7)
+    assert ix.postings_r16 is not None and ix.fp_tile_docs == fp_tile
+    orc = oracle.BM25Index(doc_off, tok, vocab)
+    rng = np.random.default_rng(fp_tile)
+    qt, ql = syn.keyword_queries(24, vocab, min_rank=30, thresholds=thr)
+    long_q = np.full((8, 32), -2, dtype=np.int32)
+    long_len = np.zeros(8, dtype=np.int32)
+    for i in range(8):
+        m = int(rng.integers(9, 33))
+        row = rng.integers(30, vocab, m)
+        row[rng.integers(0, m, 3)] = row[0]          # repeated tokens count twice in the reference
+        row[rng.integers(0, m)] = vocab + 5           # OOV
+        long_q[i, :m], long_len[i] = row, m
+    wide = np.full((qt.shape[0], 32), -2, dtype=np.int32)
+    wide[:, :qt.shape[1]] = qt
+    qt2, ql2 = np.concatenate([wide, long_q]), np.concatenate([ql, long_len])
+    for background in (False, True):
+        _check_bm25_vs_oracle(ix, orc, qt2, ql2, "sparse", background=background)
+    for k in (1, 32, 50):   # k > 32 switches the in-tile local threshold off
+        _check_bm25_vs_oracle(ix, orc, qt2[:6], ql2[:6], "sparse", k=k)
+
+
+def test_bm25_first_pass_skewed_docs_overflow_and_repair(eng):
+    """All postings of the query's term sit in one narrow doc range: the sub-range splitter (which assumes
+    roughly uniform docs) marks more docs than the compact accumulator holds -> the per-query overflow flag is
+    raised and the caller's repair path (dense kernel) returns the exact list."""
+    from optimized_rag_b200.bm25_index import Bm25Index
+    vocab, n, hot = 50, 20000, 1500
+    rng = np.random.default_rng(3)
+    docs = []
+    for d in range(n):
+        body = rng.integers(2, vocab, int(rng.integers(5, 12))).tolist()
+        if d < hot:
+            body += [0] * int(rng.integers(1, 4))     # term 0 only in docs [0, hot)
+        if d % 7 == 0:
+            body.append(1)
+        docs.append(body)
+    doc_off = np.zeros(n + 1, dtype=np.int64)
+    doc_off[1:] = np.cumsum([len(x) for x in docs])
+    tok = np.concatenate([np.asarray(x, dtype=np.int32) for x in docs])
+    ix = Bm25Index(_t(doc_off), _t(tok), vocab, tile_docs=2048, fp_tile_docs=8192)
+    orc = oracle.BM25Index(doc_off, tok, vocab)
+    assert ix.postings_r16 is not None
+    qt = np.array([[0, -2], [0, 1]], dtype=np.int32)
+    ql = np.array([1, 2], dtype=np.int32)
+    st = []
+    ix.topk(_t(qt), _t(ql), 10, force="sparse", check_overflow=False, status_out=st)
+    assert int(st[0][0]) & 1 == 1, "the skewed query must raise the overflow flag"
+    _check_bm25_vs_oracle(ix, orc, qt, ql, "sparse")      # with the repair path: exact
+
+
 def test_dense_topk_normalisation_edges(eng):
     s = torch.tensor([[0.0, 0.0, 0.0, 0.0], [-1.0, -2.0, -0.5, -3.0], [2.0, 4.0, 4.0, 1.0]], dtype=torch.float64,
                      device=DEV)
