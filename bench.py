@@ -326,7 +326,8 @@ def run_native(args):
     roof_bm = {"bound": "hbm", "achieved": post_bytes / t_bm / 1e9 if t_bm > 0 else None, "peak": pk["hbm_gbs"],
                "unit": "GB/s", "frac": (post_bytes / t_bm / 1e9 / pk["hbm_gbs"]) if t_bm > 0 else None,
                "kernel": "bm25_ms_kernel (fp32 MaxScore first pass over the fp16-r posting view)", "launch_ms": t_bm * 1e3,
-               "algorithmic_bytes": post_bytes, "traffic": None}
+               "algorithmic_bytes": post_bytes,
+               "traffic": json.loads(tp.read_text()).get("bm25_ms") if tp.exists() else None}
 
     value = Bq * args.steps / (dev_ms * 1e-3)
     e2e_val = Bq * args.steps / (e2e_ms * 1e-3)

@@ -1,7 +1,7 @@
 """Summarise one hybrid step out of an ncu launch list (gpu__time_duration.sum CSV).
 
 usage: python scripts/launch_list.py launches.csv [step_index]
-A step starts at a query_sq_kernel launch (first kernel of orag_cosine_topk)."""
+A step ends with rrf_kernel (one GPU) or hybrid_merge_kernel (row-sharded)."""
 import csv
 import sys
 
@@ -10,9 +10,9 @@ hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 h = rows[hi]
 ki, vi = h.index("Kernel Name"), h.index("Metric Value")
 L = [(r[ki], float(r[vi].replace(",", ""))) for r in rows[hi + 1:] if len(r) > vi]
-idx = [i for i, (n, _) in enumerate(L) if "query_sq" in n]
-which = int(sys.argv[2]) if len(sys.argv) > 2 else len(idx) - 2
-s, e = idx[which], idx[which + 1] if which + 1 < len(idx) else len(L)
+ends = [i for i, (n, _) in enumerate(L) if "rrf_kernel" in n or "hybrid_merge" in n]
+which = int(sys.argv[2]) if len(sys.argv) > 2 else len(ends) - 1
+s, e = ends[which - 1] + 1, ends[which] + 1
 tot = sum(v for _, v in L[s:e]) / 1e6
 print("kernel,duration_ms,share")
 for n, v in L[s:e]:
