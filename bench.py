@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--rows", type=int, default=int(os.environ.get("ORAG_BENCH_ROWS", 10_000_000)))
     ap.add_argument("--queries", type=int, default=256)
-    ap.add_argument("--mode", default=os.environ.get("ORAG_BENCH_MODE", "bf16"), choices=["tf32", "bf16"])
+    ap.add_argument("--mode", default=os.environ.get("ORAG_BENCH_MODE", "f16"), choices=["tf32", "bf16", "f16"])
     ap.add_argument("--tile-docs", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
@@ -301,21 +301,22 @@ def run_native(args):
     t_bm = statistics.mean([x for x in bm_ms if x >= 0] or [0.0]) * 1e-3
     groups = (Bq + 255) // 256
     fp32_bytes = n_scan_rows * DIM * 4
-    streamed = n_scan_rows * DIM * (2 if args.mode == "bf16" else 4)
+    half = args.mode in ("bf16", "f16")
+    streamed = n_scan_rows * DIM * (2 if half else 4)
     flops = 2.0 * min(Bq, 256) * n_scan_rows * DIM
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
-        traffic = json.loads(tp.read_text()).get(f"cosine_scan_{args.mode}")
+        traffic = json.loads(tp.read_text()).get("cosine_scan_bf16" if half else f"cosine_scan_{args.mode}")
     hbm = {"bound": "hbm", "achieved": streamed / t_scan / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
            "frac": streamed / t_scan / 1e9 / pk["hbm_gbs"], "traffic": traffic,
-           "bytes": "bf16 shadow copy actually streamed (N*D*2)" if args.mode == "bf16" else "fp32 corpus (N*D*4)"}
+           "bytes": f"{args.mode} shadow copy actually streamed (N*D*2)" if half else "fp32 corpus (N*D*4)"}
     tens = {"bound": "tensor", "achieved": flops / t_scan / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
             "frac": flops / t_scan / 1e12 / pk["tf_sustained"], "traffic": traffic,
-            "peak_kind": "bf16 dense sustained" if args.mode == "bf16" else
+            "peak_kind": "bf16 dense sustained (fp16 and bf16 share the kind::f16 rate)" if half else
                          "bf16 dense sustained (tf32 runs at half the bf16 rate: x2 for the tf32 ceiling)"}
     # which resource bounds the kernel: bf16 at B=256 has 256 flop/B of streamed data > the ~207 flop/B ridge
-    primary = tens if (args.mode == "bf16" and Bq >= 208) else hbm
+    primary = tens if (half and Bq >= 208) else hbm
     roofline = dict(primary)
     roofline.update({"kernel": f"cosine_scan_kernel<{args.mode}> (main scan, {n_scan_rows} rows x {min(Bq, 256)} queries)",
                      "peak_source": pk["source"], "launch_ms": t_scan * 1e3 / 1.0, "launches_per_step": groups,

@@ -10,7 +10,7 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "csrc" / "liborag.so"
 
-ORAG_COS_EXACT, ORAG_COS_TF32, ORAG_COS_BF16 = 0, 1, 2
+ORAG_COS_EXACT, ORAG_COS_TF32, ORAG_COS_BF16, ORAG_COS_F16 = 0, 1, 2, 3
 ORAG_STATUS_OVERFLOW = 1
 ORAG_BM25_NORMALIZE, ORAG_BM25_FORCE_SPARSE, ORAG_BM25_FORCE_DENSE, ORAG_BM25_EXACT_TILES = 1, 2, 4, 8
 ORAG_BM25_BACKGROUND = 16
@@ -20,7 +20,7 @@ SYMBOLS = [
     "orag_version", "orag_last_error", "orag_device_info",
     "orag_launch_count", "orag_profile_enable", "orag_profile_read",
     "orag_gen_embeddings", "orag_gen_doc_lengths", "orag_gen_tokens",
-    "orag_row_inv_norms", "orag_f32_to_bf16",
+    "orag_row_inv_norms", "orag_f32_to_bf16", "orag_f32_to_f16_rows",
     "orag_cosine_mark_prescan", "orag_stream_wait_prescan",
     "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_dense", "orag_cosine_firstpass_dense",
     "orag_bm25_workspace_bytes", "orag_bm25_topk", "orag_bm25_dense", "orag_dense_topk",
@@ -83,6 +83,7 @@ def lib() -> ctypes.CDLL:
     L.orag_gen_tokens.argtypes = [vp, vp, c_int64, c_int64, c_uint64, vp, c_int, vp]
     L.orag_row_inv_norms.argtypes = [vp, c_int64, c_int, vp, vp]
     L.orag_f32_to_bf16.argtypes = [vp, vp, c_int64, vp]
+    L.orag_f32_to_f16_rows.argtypes = [vp, c_int64, c_int, vp, vp, vp, vp]
     L.orag_cosine_mark_prescan.argtypes = [c_int]
     L.orag_stream_wait_prescan.argtypes = [vp]
     L.orag_cosine_workspace_bytes.restype = c_size_t

@@ -38,17 +38,38 @@ void profile_mark(int slot, int end, cudaStream_t st)
     if (end) g_ev_used[slot] = 1;
 }
 
+__global__ void scale_norms_kernel(const float *qnorm, const float *inv_qnorm, const float *scale, int n, float *qnorm_s,
+                                   float *inv_qnorm_s)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        qnorm_s[i] = qnorm[i] * scale[i];          // exact: scale is a power of two
+        inv_qnorm_s[i] = inv_qnorm[i] / scale[i];
+    }
+}
+
+__global__ void unscale_columns_kernel(float *out, int64_t n, const float *scale, int n_queries)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int q = (int)(i & 255);
+    if (i < n && q < n_queries) out[i] = out[i] / scale[q];
+}
+
 // ---- co-scheduling hook ---------------------------------------------------------------------------
 static int g_mark_prescan = 0;
 static cudaEvent_t g_prescan_ev = nullptr;
 
 // First-pass error bounds in cosine units (DESIGN.md "exactness of the first pass"):
 //   tf32: operands truncated to 10 mantissa bits -> |rel err per product| < 2^-9 + 2^-20
-//   bf16: operands rounded to nearest, 8 bits      -> |rel err per product| < 2^-8 + 2^-18
+//   bf16: both operands rounded to nearest, 8 significant bits (unit roundoff 2^-8 each)
+//                                                   -> |rel err per product| < 2^-7 + 2^-16
+//   fp16: both operands rounded to nearest, 11 significant bits, rows and queries pre-scaled by powers of two
+//         (cosine_exact.cu f32_to_f16_rows_kernel)  -> |rel err per product| < 2^-10 + 2^-22
 // sum |a_i b_i| <= |a||b| turns that into an absolute bound on the cosine; 2.5e-4 covers fp32
 // accumulation in the tensor core (1536 terms), the fp32 inv-norm and the epilogue multiply.
 constexpr float kEpsTf32 = 1.954e-3f + 2.5e-4f;
-constexpr float kEpsBf16 = 3.91e-3f + 2.5e-4f;
+constexpr float kEpsBf16 = 7.83e-3f + 2.5e-4f;
+constexpr float kEpsF16 = 9.77e-4f + 2.5e-4f;
 
 constexpr int kGroup = 256;     // queries per tensor-core pass (UMMA N)
 constexpr int kSeedRows = 2048; // rows of the dense seed pass that initialises the thresholds
@@ -69,7 +90,10 @@ struct CosineWs {
     double *cand_score; // [G, cap2]  float64 cosines of the survivors
     int64_t *cand_id;   // [G, cap2]
     float *seed;        // [kSeedRows, 256]
-    void *q_bf16;       // [G, dim] bf16
+    void *q_bf16;       // [G, dim] bf16 / fp16 copy of the query block
+    float *q_scale;     // [G] power-of-two scale of each fp16 query row
+    float *qnorm_s;     // [G] |q| * scale     (the units the fp16 scan's accumulators are in)
+    float *inv_qnorm_s; // [G] 1 / (|q| * scale)
     size_t bytes;
 };
 
@@ -96,6 +120,9 @@ static CosineWs carve_tc(void *base, int dim)
     w.cand_id = (int64_t *)take((size_t)kGroup * kSurvCap * 8);
     w.seed = (float *)take((size_t)kSeedRows * 256 * 4);
     w.q_bf16 = take((size_t)kGroup * dim * 2);
+    w.q_scale = (float *)take(kGroup * 4);
+    w.qnorm_s = (float *)take(kGroup * 4);
+    w.inv_qnorm_s = (float *)take(kGroup * 4);
     w.bytes = (size_t)(p - (uint8_t *)base);
     return w;
 }
@@ -181,6 +208,8 @@ static int cosine_exact_path(const float *corpus, int64_t n_rows, int dim, int64
 }
 
 extern "C" int orag_f32_to_bf16(const float *d_src, void *d_dst, int64_t count, void *stream);
+extern "C" int orag_f32_to_f16_rows(const float *d_src, int64_t n_rows, int dim, void *d_dst_f16,
+                                    float *d_inv_norm_scaled, float *d_scale, void *stream);
 
 extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, const void *d_shadow, int64_t n_rows,
                                 int dim, int64_t row_id_base, const float *d_queries, int n_queries, int k, int mode,
@@ -202,16 +231,17 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
         return cosine_exact_path(d_corpus, n_rows, dim, row_id_base, d_queries, n_queries, k, d_out_ids, d_out_scores,
                                  d_workspace, st);
 
-    ORAG_REQUIRE(mode == ORAG_COS_TF32 || mode == ORAG_COS_BF16, "mode");
-    const bool bf16 = mode == ORAG_COS_BF16;
-    ORAG_REQUIRE(dim % (bf16 ? 64 : 32) == 0, "dim must be a multiple of 32 (tf32) / 64 (bf16)");
+    ORAG_REQUIRE(mode == ORAG_COS_TF32 || mode == ORAG_COS_BF16 || mode == ORAG_COS_F16, "mode");
+    const bool f16 = mode == ORAG_COS_F16;
+    const bool bf16 = mode == ORAG_COS_BF16 || f16;  // 16-bit operands (kind::f16)
+    ORAG_REQUIRE(dim % (bf16 ? 64 : 32) == 0, "dim must be a multiple of 32 (tf32) / 64 (bf16, fp16)");
     ORAG_REQUIRE(d_inv_norm != nullptr || n_rows == 0, "inv_norm required for tensor-core modes");
-    ORAG_REQUIRE(!bf16 || d_shadow != nullptr || n_rows == 0, "bf16 shadow required");
+    ORAG_REQUIRE(!bf16 || d_shadow != nullptr || n_rows == 0, "16-bit shadow required");
     ORAG_REQUIRE((reinterpret_cast<uintptr_t>(d_corpus) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_queries) & 15) == 0,
                  "16-byte alignment");
     ORAG_REQUIRE(k <= 128, "k <= 128 for tensor-core modes");
     CosineWs w = carve_tc(d_workspace, dim);
-    const float margin = 2.f * (bf16 ? kEpsBf16 : kEpsTf32);
+    const float margin = 2.f * (f16 ? kEpsF16 : bf16 ? kEpsBf16 : kEpsTf32);
     const int n_seed = (int)(n_rows < kSeedRows ? n_rows : kSeedRows);
 
     for (int q0 = 0; q0 < n_queries; q0 += kGroup) {
@@ -222,13 +252,24 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
         rc = tc::launch_query_norms(w.sq_q, nq, w.qnorm, w.inv_qnorm, st);
         if (rc) return rc;
         const void *qop = q;
-        if (bf16) {
+        const float *qnorm_scan = w.qnorm, *inv_qnorm_scan = w.inv_qnorm;
+        if (f16) {
+            rc = orag_f32_to_f16_rows(q, nq, dim, w.q_bf16, nullptr, w.q_scale, st);
+            if (rc) return rc;
+            scale_norms_kernel<<<(nq + 255) / 256, 256, 0, st>>>(w.qnorm, w.inv_qnorm, w.q_scale, nq, w.qnorm_s,
+                                                               w.inv_qnorm_s);
+            ORAG_LAUNCH_CHECK();
+            qop = w.q_bf16;
+            qnorm_scan = w.qnorm_s;
+            inv_qnorm_scan = w.inv_qnorm_s;
+        } else if (bf16) {
             rc = orag_f32_to_bf16(q, w.q_bf16, (int64_t)nq * dim, st);
             if (rc) return rc;
             qop = w.q_bf16;
         }
         const void *aop = bf16 ? d_shadow : (const void *)d_corpus;
         tc::ScanParams p{};
+        p.f16 = f16 ? 1 : 0;
         p.n_queries = nq;
         p.inv_norm = d_inv_norm;
         p.thr_key = w.thr_key;
@@ -236,8 +277,8 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
         p.hist = w.hist;
         p.cand = w.cand;
         p.cap = kCandCap;
-        p.qnorm = w.qnorm;
-        p.inv_qnorm = w.inv_qnorm;
+        p.qnorm = qnorm_scan;
+        p.inv_qnorm = inv_qnorm_scan;
         p.margin = margin;
         p.k = k;
         // seed: dense first pass over the first rows -> histogram, threshold, first candidates
@@ -247,7 +288,7 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
         p.dense_out = w.seed;
         rc = tc::launch_scan(bf16, aop, n_rows, qop, dim, p, st);
         if (rc) return rc;
-        rc = tc::launch_seed_finalize(w.seed, n_seed, nq, k, margin, w.qnorm, w.inv_qnorm, w.thr_key, w.cnt, w.hist,
+        rc = tc::launch_seed_finalize(w.seed, n_seed, nq, k, margin, qnorm_scan, inv_qnorm_scan, w.thr_key, w.cnt, w.hist,
                                       w.cand, kCandCap, st);
         if (rc) return rc;
         // main scan over the rest of the shard (co-scheduling hook: see orag_cosine_mark_prescan)
@@ -283,25 +324,42 @@ extern "C" int orag_cosine_firstpass_dense(const float *d_corpus, const float *d
 {
     ORAG_REQUIRE(d_corpus && d_inv_norm && d_queries && d_out && n_rows > 0 && n_queries > 0 && n_queries <= kGroup,
                  "firstpass_dense");
-    ORAG_REQUIRE(mode == ORAG_COS_TF32 || mode == ORAG_COS_BF16, "mode");
-    const bool bf16 = mode == ORAG_COS_BF16;
+    ORAG_REQUIRE(mode == ORAG_COS_TF32 || mode == ORAG_COS_BF16 || mode == ORAG_COS_F16, "mode");
+    const bool f16 = mode == ORAG_COS_F16;
+    const bool bf16 = mode == ORAG_COS_BF16 || f16;
     ORAG_REQUIRE(dim % (bf16 ? 64 : 32) == 0, "dim multiple of 32/64");
     cudaStream_t st = (cudaStream_t)stream;
     const void *qop = d_queries;
+    float *q_scale = nullptr;
     if (bf16) {
-        ORAG_REQUIRE(d_shadow && d_workspace && workspace_bytes >= (size_t)n_queries * dim * 2, "bf16 workspace");
-        int rc = orag_f32_to_bf16(d_queries, d_workspace, (int64_t)n_queries * dim, st);
+        ORAG_REQUIRE(d_shadow && d_workspace && workspace_bytes >= (size_t)n_queries * dim * 2 + 1024, "16-bit workspace");
+        int rc;
+        if (f16) {
+            q_scale = (float *)((uint8_t *)d_workspace + align_up((size_t)n_queries * dim * 2, 256));
+            ORAG_REQUIRE(workspace_bytes >= align_up((size_t)n_queries * dim * 2, 256) + (size_t)n_queries * 4,
+                         "fp16 workspace");
+            rc = orag_f32_to_f16_rows(d_queries, n_queries, dim, d_workspace, nullptr, q_scale, st);
+        } else {
+            rc = orag_f32_to_bf16(d_queries, d_workspace, (int64_t)n_queries * dim, st);
+        }
         if (rc) return rc;
         qop = d_workspace;
     }
     tc::ScanParams p{};
+    p.f16 = f16 ? 1 : 0;
     p.n_queries = n_queries;
     p.inv_norm = d_inv_norm;
     p.row_begin = 0;
     p.row_end = n_rows;
     p.dense = 1;
     p.dense_out = d_out;
-    return tc::launch_scan(bf16, bf16 ? d_shadow : (const void *)d_corpus, n_rows, qop, dim, p, st);
+    int rc = tc::launch_scan(bf16, bf16 ? d_shadow : (const void *)d_corpus, n_rows, qop, dim, p, st);
+    if (rc || !f16) return rc;
+    // fp16: the accumulators carry the queries' power-of-two scales; divide them out (exact)
+    const int64_t total = (n_rows + 127) / 128 * 128 * 256;
+    unscale_columns_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_out, total, q_scale, n_queries);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
 }
 
 extern "C" size_t orag_pairwise_workspace_bytes(int64_t m, int dim)

@@ -7,6 +7,7 @@
 //   * rescore_kernel: the candidate rows emitted by the tensor-core first pass (cosine_tc.cu)
 //   * select_topk_kernel: generic exact top-k by (score desc, id asc), optional max-normalisation
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "select.cuh"
@@ -48,6 +49,57 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4 *__restri
         o.x = *reinterpret_cast<uint32_t *>(&lo);
         o.y = *reinterpret_cast<uint32_t *>(&hi);
         dst[i] = o;
+    }
+}
+
+// fp32 rows -> IEEE fp16 rows scaled by a per-row power of two (warp per row).  s = 2^e is chosen so that the
+// largest |x| lands in [2^14, 2^15): x * s is exact, the only rounding is the final fp16 RN (relative 2^-11 for
+// normal results; results below 2^-14 are >= 2^28 times smaller than the row maximum and their absolute error
+// 2^-25 is irrelevant).  inv_norm_scaled[r] = 1 / (|x| * s) so that (fp16 dot) * inv_norm_scaled is in the same
+// units as the fp32 path; scale_out[r] = s.
+__global__ void __launch_bounds__(256) f32_to_f16_rows_kernel(const float *__restrict__ src, int64_t n_rows, int dim,
+                                                             __half *__restrict__ dst, float *__restrict__ inv_norm_scaled,
+                                                             float *__restrict__ scale_out)
+{
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int n4 = dim >> 2;
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+        const float4 *p = reinterpret_cast<const float4 *>(src + r * (int64_t)dim);
+        float mx = 0.f, sq = 0.f;
+        for (int j = lane; j < n4; j += 32) {
+            const float4 v = __ldg(p + j);
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+            sq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        }
+        int e = 0;
+        if (mx > 0.f && isfinite(mx)) {
+            int ex;
+            frexpf(mx, &ex);        // mx = m * 2^ex, m in [0.5, 1)  ->  mx * 2^(15 - ex) in [2^14, 2^15)
+            e = 15 - ex;
+            e = e > 100 ? 100 : (e < -100 ? -100 : e);
+        }
+        const float s = ldexpf(1.f, e);
+        uint2 *q = reinterpret_cast<uint2 *>(dst + r * (int64_t)dim);
+        for (int j = lane; j < n4; j += 32) {
+            const float4 v = __ldg(p + j);
+            const __half2 lo = __floats2half2_rn(v.x * s, v.y * s);
+            const __half2 hi = __floats2half2_rn(v.z * s, v.w * s);
+            uint2 o;
+            o.x = *reinterpret_cast<const uint32_t *>(&lo);
+            o.y = *reinterpret_cast<const uint32_t *>(&hi);
+            q[j] = o;
+        }
+        if (lane == 0) {
+            if (inv_norm_scaled) inv_norm_scaled[r] = sq > 0.f ? rsqrtf(sq) * ldexpf(1.f, -e) : 0.f;
+            if (scale_out) scale_out[r] = s;
+        }
     }
 }
 
@@ -388,6 +440,22 @@ extern "C" int orag_f32_to_bf16(const float *d_src, void *d_dst, int64_t count, 
     if (blocks > cap) blocks = cap;
     orag::f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4 *>(d_src), reinterpret_cast<uint2 *>(d_dst), n4);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+extern "C" int orag_f32_to_f16_rows(const float *d_src, int64_t n_rows, int dim, void *d_dst_f16,
+                                    float *d_inv_norm_scaled, float *d_scale, void *stream)
+{
+    ORAG_REQUIRE(d_src && d_dst_f16 && n_rows >= 0 && dim > 0 && dim % 4 == 0, "f32_to_f16_rows: dim % 4 == 0");
+    ORAG_REQUIRE((reinterpret_cast<uintptr_t>(d_src) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_dst_f16) & 7) == 0,
+                 "alignment");
+    if (n_rows == 0) return ORAG_OK;
+    int64_t blocks = (n_rows + 7) / 8;
+    int64_t cap = (int64_t)orag::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    orag::f32_to_f16_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        d_src, n_rows, dim, reinterpret_cast<__half *>(d_dst_f16), d_inv_norm_scaled, d_scale);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }

@@ -435,7 +435,7 @@ static EncodeTiledFn get_encode()
     return fn;
 }
 
-static int make_map(CUtensorMap *map, const void *base, bool bf16, int64_t rows, int dim, int box_rows)
+static int make_map(CUtensorMap *map, const void *base, bool bf16, bool f16, int64_t rows, int dim, int box_rows)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
@@ -447,7 +447,8 @@ static int make_map(CUtensorMap *map, const void *base, bool bf16, int64_t rows,
     cuuint64_t gstride[1] = {(cuuint64_t)dim * eb};
     cuuint32_t box[2] = {(cuuint32_t)(128 / eb), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+    CUresult r = enc(map, bf16 ? (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)
+                               : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                      const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -458,9 +459,9 @@ static int make_map(CUtensorMap *map, const void *base, bool bf16, int64_t rows,
     return ORAG_OK;
 }
 
-static uint32_t make_idesc(bool bf16, int umma_n)
+static uint32_t make_idesc(bool bf16, bool f16, int umma_n)
 {
-    const uint32_t fmt = bf16 ? 1u : 2u;  // F16F32Format: BF16 = 1, TF32 = 2
+    const uint32_t fmt = bf16 ? (f16 ? 0u : 1u) : 2u;  // F16F32Format: F16 = 0, BF16 = 1, TF32 = 2
     return (1u << 4) /* D = f32 */ | (fmt << 7) | (fmt << 10) | ((uint32_t)(umma_n >> 3) << 17) |
            ((uint32_t)(kTileM >> 4) << 24);
 }
@@ -473,9 +474,9 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
     CUtensorMap map_a, map_b;
     p.umma_n = (p.n_queries + 15) / 16 * 16;
     if (p.umma_n < 16) p.umma_n = 16;
-    int rc = make_map(&map_a, a_base, bf16, a_rows, dim, kTileM);
+    int rc = make_map(&map_a, a_base, bf16, p.f16 != 0, a_rows, dim, kTileM);
     if (rc) return rc;
-    rc = make_map(&map_b, q_base, bf16, p.n_queries, dim, p.pair_mode ? kMaxN : p.umma_n);
+    rc = make_map(&map_b, q_base, bf16, p.f16 != 0, p.n_queries, dim, p.pair_mode ? kMaxN : p.umma_n);
     if (rc) return rc;
     p.chunk_elems = bf16 ? 64 : 32;
     p.k_chunks = dim / p.chunk_elems;
@@ -485,7 +486,7 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
         p.num_tiles = nb * (nb + 1);
         p.umma_n = kMaxN;
     }
-    p.idesc = make_idesc(bf16, p.umma_n);
+    p.idesc = make_idesc(bf16, p.f16 != 0, p.umma_n);
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     if (!p.dense) profile_mark(0, 0, st);
     if (bf16) {

@@ -24,7 +24,8 @@ struct ScanParams {
     int64_t row_end;        // one past the last valid row
     int num_tiles;
     int k_chunks;           // dim * elem_bytes / 128
-    int chunk_elems;        // 32 (tf32) or 64 (bf16)
+    int chunk_elems;        // 32 (tf32) or 64 (bf16 / fp16)
+    int f16;                // 16-bit operands are IEEE fp16 (1) or bf16 (0)
     int n_queries;
     int umma_n;             // round_up(n_queries, 16)
     uint32_t idesc;

@@ -14,7 +14,7 @@ import torch
 from . import _ffi
 from .bm25_index import Bm25Index
 
-MODE = {"exact": _ffi.ORAG_COS_EXACT, "tf32": _ffi.ORAG_COS_TF32, "bf16": _ffi.ORAG_COS_BF16}
+MODE = {"exact": _ffi.ORAG_COS_EXACT, "tf32": _ffi.ORAG_COS_TF32, "bf16": _ffi.ORAG_COS_BF16, "f16": _ffi.ORAG_COS_F16}
 SMALL_N = 4096  # below this the exact CUDA-core scan is used directly
 
 
@@ -56,8 +56,9 @@ def gen_token_corpus(n_docs: int, doc_start: int, seed: int, thresholds: np.ndar
 
 # --------------------------------------------------------------------------- cosine
 class CosineIndex:
-    """One shard of chunk embeddings resident in HBM: fp32 rows (+ fp32 inverse norms, + optional bf16
-    shadow copy for the bf16 first pass).  `topk` = exact float64 cosine top-k (see orag_cosine_topk)."""
+    """One shard of chunk embeddings resident in HBM: fp32 rows (+ fp32 inverse norms, + optional 16-bit shadow copy
+    for the first pass: "f16" = IEEE fp16 rows scaled by powers of two (preferred), "bf16").  `topk` = exact float64
+    cosine top-k (see orag_cosine_topk)."""
 
     def __init__(self, corpus: torch.Tensor, row_id_base: int = 0, mode: str = "auto", shadow: bool | None = None):
         _require_cuda(corpus, "corpus")
@@ -70,20 +71,26 @@ class CosineIndex:
             if self.n_rows < SMALL_N or self.dim % 32 != 0:
                 mode = "exact"
             else:
-                mode = "bf16" if (shadow and self.dim % 64 == 0) else "tf32"
+                mode = "f16" if (shadow and self.dim % 64 == 0) else "tf32"
         self.mode = mode
         self.inv_norm = None
         self.shadow = None
-        if mode != "exact":
+        if mode in ("tf32", "bf16"):
             self.inv_norm = torch.empty(self.n_rows, dtype=torch.float32, device=self.device)
             _ffi.check(_ffi.lib().orag_row_inv_norms(corpus.data_ptr(), self.n_rows, self.dim,
                                                      self.inv_norm.data_ptr(), _stream(self.device)),
                        "orag_row_inv_norms")
         if mode == "bf16":
             self.shadow = torch.empty((self.n_rows, self.dim), dtype=torch.bfloat16, device=self.device)
-            # convert in slabs to keep the launch grid bounded
             _ffi.check(_ffi.lib().orag_f32_to_bf16(corpus.data_ptr(), self.shadow.data_ptr(),
                                                    self.n_rows * self.dim, _stream(self.device)), "orag_f32_to_bf16")
+        if mode == "f16":
+            # fp16 rows scaled by a per-row power of two; inv_norm carries the same scale
+            self.shadow = torch.empty((self.n_rows, self.dim), dtype=torch.float16, device=self.device)
+            self.inv_norm = torch.empty(self.n_rows, dtype=torch.float32, device=self.device)
+            _ffi.check(_ffi.lib().orag_f32_to_f16_rows(corpus.data_ptr(), self.n_rows, self.dim, self.shadow.data_ptr(),
+                                                       self.inv_norm.data_ptr(), None, _stream(self.device)),
+                       "orag_f32_to_f16_rows")
         self._ws = {}
 
     def _workspace(self, n_queries: int, k: int, mode: int) -> torch.Tensor:
@@ -103,8 +110,8 @@ class CosineIndex:
         m = MODE[mode or self.mode]
         if m != _ffi.ORAG_COS_EXACT and self.inv_norm is None:
             raise _ffi.OragError("index was built for the exact path only")
-        if m == _ffi.ORAG_COS_BF16 and self.shadow is None:
-            raise _ffi.OragError("index has no bf16 shadow copy")
+        if m != _ffi.ORAG_COS_EXACT and m != MODE[self.mode]:
+            raise _ffi.OragError(f"index was built for the {self.mode} first pass")
         Bq = queries.shape[0]
         ids = torch.empty((Bq, k), dtype=torch.int64, device=self.device)
         sc = torch.empty((Bq, k), dtype=torch.float64, device=self.device)
@@ -138,7 +145,7 @@ class CosineIndex:
         Bq = queries.shape[0]
         rows_pad = (self.n_rows + 127) // 128 * 128
         out = torch.zeros((rows_pad, 256), dtype=torch.float32, device=self.device)
-        ws = torch.empty(max(Bq * self.dim * 2, 256), dtype=torch.uint8, device=self.device)
+        ws = torch.empty(Bq * self.dim * 2 + 4096, dtype=torch.uint8, device=self.device)
         _ffi.check(_ffi.lib().orag_cosine_firstpass_dense(
             self.corpus.data_ptr(), self.inv_norm.data_ptr(),
             self.shadow.data_ptr() if self.shadow is not None else None, self.n_rows, self.dim, queries.data_ptr(),
@@ -149,7 +156,7 @@ class CosineIndex:
     def stream_bytes(self, n_queries: int, mode: str | None = None) -> int:
         """Bytes of corpus the first pass streams per batch of <= 256 queries."""
         m = mode or self.mode
-        per = 2 if m == "bf16" else 4
+        per = 2 if m in ("bf16", "f16") else 4
         groups = (n_queries + 255) // 256
         return self.n_rows * self.dim * per * groups
 

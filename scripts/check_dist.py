@@ -37,7 +37,7 @@ q_emb = torch.from_numpy(syn.query_embeddings(B, N, DIM, dup_per_mille=1)).to(de
 qt, ql = syn.keyword_queries(B, VOCAB, thresholds=thr)
 qt, ql = torch.from_numpy(qt).to(dev), torch.from_numpy(ql).to(dev)
 ok = True
-for mode in ("tf32", "bf16"):
+for mode in ("tf32", "f16"):
     sh = ShardedHybrid(build(lo, hi, lambda o, t: sharded_stats(o, t, VOCAB), mode))
     res = sh.search(q_emb, qt, ql, K)
     torch.cuda.synchronize()

@@ -11,12 +11,12 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 B = 256
 dev = torch.device("cuda:0")
 corpus = engine.gen_embeddings(N, 1536, 0, syn.SEED_CORPUS, 0, device=dev)
-cos = engine.CosineIndex(corpus, mode="bf16")
+cos = engine.CosineIndex(corpus, mode="f16")
 q = torch.from_numpy(syn.query_embeddings(B, N, 1536)).to(dev)
 for _ in range(2):
     cos.topk(q, 10, check_overflow=False)
 torch.cuda.synchronize()
-ws = cos._ws[engine.MODE["bf16"]]
+ws = cos._ws[engine.MODE["f16"]]
 al = lambda x: (x + 255) // 256 * 256
 o = al(256 * 8) + al(256 * 4) * 3
 cnt = ws[o:o + 1024].view(torch.int32).cpu().numpy()

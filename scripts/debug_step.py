@@ -15,7 +15,7 @@ dev = torch.device("cuda:0")
 V, DIM, K = 50000, 1536, 10
 thr = syn.zipf_thresholds(V)
 corpus = engine.gen_embeddings(N, DIM, 0, syn.SEED_CORPUS, 0, device=dev)
-cos = engine.CosineIndex(corpus, mode="bf16")
+cos = engine.CosineIndex(corpus, mode="f16")
 off, tok = engine.gen_token_corpus(N, 0, syn.SEED_TOKENS, thr, V, 100, 300, device=dev)
 bm = Bm25Index(off, tok, V, tile_docs=2048)
 del tok

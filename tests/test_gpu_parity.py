@@ -86,7 +86,7 @@ def test_cosine_exact_topk_vs_oracle(eng, n, dim, nq, dup):
 
 
 # ------------------------------------------------------------------------------------------------ cosine, tensor-core path
-@pytest.mark.parametrize("mode,eps", [("tf32", 2.3e-3), ("bf16", 4.3e-3)])
+@pytest.mark.parametrize("mode,eps", [("tf32", 2.3e-3), ("bf16", 8.1e-3), ("f16", 1.3e-3)])
 def test_firstpass_dense_within_bound(eng, mode, eps):
     n, dim, nq = 1000, 1536, 70
     corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim)
@@ -101,7 +101,7 @@ def test_firstpass_dense_within_bound(eng, mode, eps):
     assert np.corrcoef(got.ravel(), want.ravel())[0, 1] > 0.999
 
 
-@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["tf32", "bf16", "f16"])
 @pytest.mark.parametrize("n,dim,nq,dup", [(20000, 1536, 40, 0), (9000, 256, 256, 20), (4500, 64, 3, 0)])
 def test_cosine_tc_topk_vs_oracle(eng, mode, n, dim, nq, dup):
     corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim, dup)
@@ -124,9 +124,28 @@ def test_cosine_tc_matches_exact_path_all_queries(eng):
     corpus = eng.gen_embeddings(n, dim, 0, syn.SEED_CORPUS, 1, device=DEV)
     queries = _t(syn.query_embeddings(nq, n, dim, dup_per_mille=1))
     a = eng.CosineIndex(corpus, mode="exact").topk(queries, 10)
-    for mode in ("tf32", "bf16"):
+    for mode in ("tf32", "bf16", "f16"):
         b = eng.CosineIndex(corpus, mode=mode).topk(queries, 10)
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), mode
+
+
+def test_cosine_f16_rows_of_wildly_different_scale(eng):
+    """The fp16 shadow scales every row (and every query) by its own power of two: rows and queries whose
+    magnitudes span 60 binary orders, far outside fp16's range, must still give the exact top-k (kernels must not
+    assume unit norm: the reference divides by both magnitudes, rag/retrieval.py:365-371)."""
+    n, dim, nq = 12000, 256, 48
+    rng = np.random.default_rng(8)
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim)
+    corpus *= (2.0 ** rng.integers(-30, 31, n)).astype(np.float32)[:, None]
+    corpus[100] = 0.0
+    queries = syn.query_embeddings(nq, n, dim)
+    queries *= (2.0 ** rng.integers(-30, 31, nq)).astype(np.float32)[:, None]
+    queries[3] = 0.0
+    idx = eng.CosineIndex(_t(corpus), mode="f16")
+    ids, sc = idx.topk(_t(queries), 10)
+    wi, ws = oracle.cosine_topk(corpus, queries, 10)
+    assert np.array_equal(ids.cpu().numpy(), wi)
+    assert np.array_equal(_bits(sc.cpu().numpy()), _bits(ws))
 
 
 # ------------------------------------------------------------------------------------------------ BM25
@@ -385,7 +404,7 @@ def test_pairwise_tensor_core_equals_exact(eng):
 
 
 # ------------------------------------------------------------------------------------------------ edge cases
-@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["tf32", "bf16", "f16"])
 def test_cosine_tc_ragged_sizes_and_batches(eng, mode):
     """N not a multiple of the 128-row tile, B > 256 (two query groups), B = 1, k = 1 and k = 64, id base."""
     n, dim = 4097 + 128 * 3 + 5, 192
