@@ -82,6 +82,9 @@ int orag_gen_tokens(int32_t *d_out, const int64_t *d_doc_off, int64_t n_docs, in
 /* d_inv_norm[r] = 1/||corpus[r]|| as fp32 (0 for an all-zero row).  Used only by the
  * low-precision first pass; final scores never depend on it. */
 int orag_row_inv_norms(const float *d_corpus, int64_t n_rows, int dim, float *d_inv_norm, void *stream);
+/* d_row_sq[r] = sum(a*a for a in row r) in the reference's float64 arithmetic (sequential Neumaier sum,
+ * rag/retrieval.py:366 under CPython >= 3.12): a per-row constant the final re-score would otherwise recompute. */
+int orag_row_sq(const float *d_corpus, int64_t n_rows, int dim, double *d_row_sq, void *stream);
 /* fp32 -> bf16 (round-to-nearest-even) shadow copy for ORAG_COS_BF16 */
 int orag_f32_to_bf16(const float *d_src, void *d_dst_bf16, int64_t count, void *stream);
 /* fp32 rows -> fp16 shadow rows for ORAG_COS_F16: row r is multiplied by s_r = 2^e (largest |x| lands in
@@ -101,13 +104,15 @@ int orag_f32_to_f16_rows(const float *d_src, int64_t n_rows, int dim, void *d_ds
  *                tensor-core modes additionally need dim % 32 == 0 (tf32) / % 64 (bf16))
  *   d_inv_norm   fp32 [n_rows] from orag_row_inv_norms (TF32, BF16) or orag_f32_to_f16_rows (F16); NULL for EXACT
  *   d_shadow     bf16 / fp16 [n_rows, dim] (ORAG_COS_BF16 / ORAG_COS_F16, else NULL)
+ *   d_row_sq     fp64 [n_rows] from orag_row_sq, or NULL: the reference's sum(a*a) of every row; with the table the
+ *                final re-score only runs the dot-product chain (same bits either way)
  *   d_queries    fp32 [n_queries, dim]
  *   d_out_ids    int64 [n_queries, k]; d_out_scores fp64 [n_queries, k]
  *   d_out_status int32 [n_queries] ORAG_STATUS_* (may be NULL)
  * ------------------------------------------------------------------------- */
 size_t orag_cosine_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k, int mode);
-int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, const void *d_shadow, int64_t n_rows, int dim,
-                     int64_t row_id_base, const float *d_queries, int n_queries, int k, int mode,
+int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, const void *d_shadow, const double *d_row_sq,
+                     int64_t n_rows, int dim, int64_t row_id_base, const float *d_queries, int n_queries, int k, int mode,
                      int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_status, void *d_workspace,
                      size_t workspace_bytes, void *stream);
 

@@ -20,7 +20,7 @@ SYMBOLS = [
     "orag_version", "orag_last_error", "orag_device_info",
     "orag_launch_count", "orag_profile_enable", "orag_profile_read",
     "orag_gen_embeddings", "orag_gen_doc_lengths", "orag_gen_tokens",
-    "orag_row_inv_norms", "orag_f32_to_bf16", "orag_f32_to_f16_rows",
+    "orag_row_inv_norms", "orag_row_sq", "orag_f32_to_bf16", "orag_f32_to_f16_rows",
     "orag_cosine_mark_prescan", "orag_stream_wait_prescan",
     "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_dense", "orag_cosine_firstpass_dense",
     "orag_bm25_workspace_bytes", "orag_bm25_topk", "orag_bm25_dense", "orag_dense_topk",
@@ -82,13 +82,14 @@ def lib() -> ctypes.CDLL:
     L.orag_gen_doc_lengths.argtypes = [vp, c_int64, c_int64, c_uint64, c_int, c_int, vp]
     L.orag_gen_tokens.argtypes = [vp, vp, c_int64, c_int64, c_uint64, vp, c_int, vp]
     L.orag_row_inv_norms.argtypes = [vp, c_int64, c_int, vp, vp]
+    L.orag_row_sq.argtypes = [vp, c_int64, c_int, vp, vp]
     L.orag_f32_to_bf16.argtypes = [vp, vp, c_int64, vp]
     L.orag_f32_to_f16_rows.argtypes = [vp, c_int64, c_int, vp, vp, vp, vp]
     L.orag_cosine_mark_prescan.argtypes = [c_int]
     L.orag_stream_wait_prescan.argtypes = [vp]
     L.orag_cosine_workspace_bytes.restype = c_size_t
     L.orag_cosine_workspace_bytes.argtypes = [c_int64, c_int, c_int, c_int, c_int]
-    L.orag_cosine_topk.argtypes = [vp, vp, vp, c_int64, c_int, c_int64, vp, c_int, c_int, c_int, vp, vp, vp, vp,
+    L.orag_cosine_topk.argtypes = [vp, vp, vp, vp, c_int64, c_int, c_int64, vp, c_int, c_int, c_int, vp, vp, vp, vp,
                                    c_size_t, vp]
     L.orag_cosine_dense.argtypes = [vp, c_int64, c_int, vp, c_int, vp, vp]
     L.orag_cosine_firstpass_dense.argtypes = [vp, vp, vp, c_int64, c_int, vp, c_int, c_int, vp, vp, c_size_t, vp]

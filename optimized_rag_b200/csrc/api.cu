@@ -38,15 +38,22 @@ void profile_mark(int slot, int end, cudaStream_t st)
     if (end) g_ev_used[slot] = 1;
 }
 
-__global__ void scale_norms_kernel(const float *qnorm, const float *inv_qnorm, const float *scale, int n, float *qnorm_s,
-                                   float *inv_qnorm_s)
+// inv_qnorm_s = 1 / (|q| * scale) from the fp16 conversion of the query block -> the other three views of the norm
+__global__ void scale_norms_kernel(const float *inv_qnorm_s, const float *scale, int n, float *qnorm_s, float *qnorm,
+                                   float *inv_qnorm)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        qnorm_s[i] = qnorm[i] * scale[i];          // exact: scale is a power of two
-        inv_qnorm_s[i] = inv_qnorm[i] / scale[i];
+        const float inv = inv_qnorm_s[i];
+        const float ns = inv > 0.f ? 1.f / inv : 0.f;
+        qnorm_s[i] = ns;
+        qnorm[i] = ns / scale[i];        // exact: scale is a power of two
+        inv_qnorm[i] = inv * scale[i];
     }
 }
+
+static cudaStream_t g_aux_stream = nullptr;
+static cudaEvent_t g_aux_fork = nullptr, g_aux_join = nullptr;
 
 __global__ void unscale_columns_kernel(float *out, int64_t n, const float *scale, int n_queries)
 {
@@ -211,7 +218,8 @@ extern "C" int orag_f32_to_bf16(const float *d_src, void *d_dst, int64_t count, 
 extern "C" int orag_f32_to_f16_rows(const float *d_src, int64_t n_rows, int dim, void *d_dst_f16,
                                     float *d_inv_norm_scaled, float *d_scale, void *stream);
 
-extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, const void *d_shadow, int64_t n_rows,
+extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, const void *d_shadow,
+                                const double *d_row_sq, int64_t n_rows,
                                 int dim, int64_t row_id_base, const float *d_queries, int n_queries, int k, int mode,
                                 int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_status, void *d_workspace,
                                 size_t workspace_bytes, void *stream)
@@ -247,25 +255,41 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
     for (int q0 = 0; q0 < n_queries; q0 += kGroup) {
         const int nq = n_queries - q0 < kGroup ? n_queries - q0 : kGroup;
         const float *q = d_queries + (int64_t)q0 * dim;
-        int rc = launch_query_sq(q, nq, dim, w.sq_q, st);
-        if (rc) return rc;
-        rc = tc::launch_query_norms(w.sq_q, nq, w.qnorm, w.inv_qnorm, st);
-        if (rc) return rc;
+        int rc;
         const void *qop = q;
         const float *qnorm_scan = w.qnorm, *inv_qnorm_scan = w.inv_qnorm;
         if (f16) {
-            rc = orag_f32_to_f16_rows(q, nq, dim, w.q_bf16, nullptr, w.q_scale, st);
+            // The exact float64 sum(q*q) (one sequential compensated chain per query, ~65 us) is only needed by
+            // the final re-score: it runs on an auxiliary stream next to the scan.  The scan's thresholds use fp32
+            // norms that fall out of the fp16 conversion of the query block (error far inside the 2.5e-4 slack).
+            if (!g_aux_stream) {
+                ORAG_CUDA_CHECK(cudaStreamCreateWithFlags(&g_aux_stream, cudaStreamNonBlocking));
+                ORAG_CUDA_CHECK(cudaEventCreateWithFlags(&g_aux_fork, cudaEventDisableTiming));
+                ORAG_CUDA_CHECK(cudaEventCreateWithFlags(&g_aux_join, cudaEventDisableTiming));
+            }
+            ORAG_CUDA_CHECK(cudaEventRecord(g_aux_fork, st));
+            ORAG_CUDA_CHECK(cudaStreamWaitEvent(g_aux_stream, g_aux_fork, 0));
+            rc = launch_query_sq(q, nq, dim, w.sq_q, g_aux_stream);
             if (rc) return rc;
-            scale_norms_kernel<<<(nq + 255) / 256, 256, 0, st>>>(w.qnorm, w.inv_qnorm, w.q_scale, nq, w.qnorm_s,
-                                                               w.inv_qnorm_s);
+            ORAG_CUDA_CHECK(cudaEventRecord(g_aux_join, g_aux_stream));
+            rc = orag_f32_to_f16_rows(q, nq, dim, w.q_bf16, w.inv_qnorm_s, w.q_scale, st);
+            if (rc) return rc;
+            scale_norms_kernel<<<(nq + 255) / 256, 256, 0, st>>>(w.inv_qnorm_s, w.q_scale, nq, w.qnorm_s, w.qnorm,
+                                                               w.inv_qnorm);
             ORAG_LAUNCH_CHECK();
             qop = w.q_bf16;
             qnorm_scan = w.qnorm_s;
             inv_qnorm_scan = w.inv_qnorm_s;
-        } else if (bf16) {
-            rc = orag_f32_to_bf16(q, w.q_bf16, (int64_t)nq * dim, st);
+        } else {
+            rc = launch_query_sq(q, nq, dim, w.sq_q, st);
             if (rc) return rc;
-            qop = w.q_bf16;
+            rc = tc::launch_query_norms(w.sq_q, nq, w.qnorm, w.inv_qnorm, st);
+            if (rc) return rc;
+            if (bf16) {
+                rc = orag_f32_to_bf16(q, w.q_bf16, (int64_t)nq * dim, st);
+                if (rc) return rc;
+                qop = w.q_bf16;
+            }
         }
         const void *aop = bf16 ? d_shadow : (const void *)d_corpus;
         tc::ScanParams p{};
@@ -307,8 +331,9 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
                               w.surv_cnt, d_out_status ? d_out_status + q0 : nullptr, st);
         if (rc) return rc;
         // ... exact float64 re-score of those (the reference's arithmetic), then exact selection
-        rc = launch_rescore(d_corpus, dim, row_id_base, q, w.sq_q, w.surv, w.surv_cnt, kSurvCap, nq, w.cand_score,
-                            w.cand_id, st);
+        if (f16) ORAG_CUDA_CHECK(cudaStreamWaitEvent(st, g_aux_join, 0));
+        rc = launch_rescore(d_corpus, dim, row_id_base, q, w.sq_q, w.surv, w.surv_cnt, kSurvCap, nq, d_row_sq,
+                            w.cand_score, w.cand_id, st);
         if (rc) return rc;
         rc = launch_select_topk(w.cand_score, w.cand_id, w.surv_cnt, kSurvCap, kSurvCap, nq, k, 0, 0, nullptr, 0,
                                 d_out_ids + (int64_t)q0 * k, d_out_scores + (int64_t)q0 * k, nullptr,

@@ -40,7 +40,6 @@
 // of pair i+2 and the run offsets (+ an L2 prefetch of the run heads) of pair i+1 are in flight while pair i
 // is consumed.
 #include <cuda_fp16.h>
-#include <stdlib.h>
 
 #include "bm25_shared.cuh"
 
@@ -579,13 +578,13 @@ __global__ void __launch_bounds__(1024) ms_finalize_kernel(const __grid_constant
 }
 
 __global__ void ms_init_state_kernel(unsigned long long *thr_bits, uint32_t *cnt, uint32_t *hist, uint32_t *topbin,
-                                     uint32_t *work, int n_queries, int keep_thr)
+                                     uint32_t *work, int n_queries)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t total = (int64_t)n_queries * kHistBins;
     if (i < total) hist[i] = 0;
     if (i < n_queries) {
-        if (!keep_thr) thr_bits[i] = 1ull;  // smallest positive double: "score > 0"
+        thr_bits[i] = 1ull;  // smallest positive double: "score > 0"
         cnt[i] = 0;
         topbin[i] = 0;
     }
@@ -662,8 +661,7 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
     {
         int64_t total = (int64_t)n_queries * kHistBins;
         ms_init_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.thr_bits, p.cnt, p.hist, p.topbin,
-                                                                              p.work, n_queries,
-                                                                              getenv("ORAG_MS_KEEP_THR") != nullptr);
+                                                                              p.work, n_queries);
         ORAG_LAUNCH_CHECK();
         prepare_queries_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(p);
         ORAG_LAUNCH_CHECK();

@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(256) cosine_dense_kernel(const float *__restri
 __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ corpus, int dim, int64_t row_id_base,
                                                      const float *__restrict__ queries, const double *__restrict__ sq_q,
                                                      const int32_t *__restrict__ cand, const uint32_t *__restrict__ cnt,
-                                                     int cap, int n_queries, double *__restrict__ out_scores,
-                                                     int64_t *__restrict__ out_ids)
+                                                     int cap, int n_queries, const double *__restrict__ row_sq,
+                                                     double *__restrict__ out_scores, int64_t *__restrict__ out_ids)
 {
     __shared__ float stage_all[8][32 * 33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -176,9 +176,11 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
         const float *rowptr = row >= 0 ? corpus + (int64_t)row * dim : nullptr;
         const float *qp[1] = {queries + (int64_t)q * dim};
         NeuSum dot[1], sq;
-        warp_score_rows<1>(rowptr, qp, dim, stage_all[wib], dot, sq, true);
+        // sum(x*x) of a row does not depend on the query: with the ingest-time table only the dot chain remains
+        warp_score_rows<1>(rowptr, qp, dim, stage_all[wib], dot, sq, row_sq == nullptr);
         if (row >= 0) {
-            out_scores[(int64_t)q * cap + slot] = cosine_from_sums(dot[0].result(), sq_q[q], sq.result());
+            const double sq_r = row_sq ? row_sq[row] : sq.result();
+            out_scores[(int64_t)q * cap + slot] = cosine_from_sums(dot[0].result(), sq_q[q], sq_r);
             out_ids[(int64_t)q * cap + slot] = row_id_base + row;
         }
     }
@@ -268,7 +270,7 @@ int launch_select_topk(const double *scores, const int64_t *ids, const uint32_t 
 
 int launch_query_sq(const float *queries, int n_queries, int dim, double *sq, cudaStream_t st)
 {
-    query_sq_kernel<<<(n_queries + 255) / 256, 256, 0, st>>>(queries, n_queries, dim, sq);
+    query_sq_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, st>>>(queries, n_queries, dim, sq);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }
@@ -286,8 +288,8 @@ int launch_cosine_dense(const float *corpus, int64_t n_rows, int dim, const floa
 }
 
 int launch_rescore(const float *corpus, int dim, int64_t row_id_base, const float *queries, const double *sq_q,
-                   const int32_t *cand, const uint32_t *cnt, int cap, int n_queries, double *out_scores,
-                   int64_t *out_ids, cudaStream_t st)
+                   const int32_t *cand, const uint32_t *cnt, int cap, int n_queries, const double *row_sq,
+                   double *out_scores, int64_t *out_ids, cudaStream_t st)
 {
     int64_t warps = (int64_t)n_queries * ((cap + 31) / 32);
     int64_t blocks = (warps + 7) / 8;
@@ -295,7 +297,7 @@ int launch_rescore(const float *corpus, int dim, int64_t row_id_base, const floa
     if (blocks > lim) blocks = lim;
     if (blocks < 1) blocks = 1;
     rescore_kernel<<<(unsigned)blocks, 256, 0, st>>>(corpus, dim, row_id_base, queries, sq_q, cand, cnt, cap,
-                                                     n_queries, out_scores, out_ids);
+                                                     n_queries, row_sq, out_scores, out_ids);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }
@@ -332,11 +334,22 @@ __global__ void __launch_bounds__(256) prefilter_kernel(const float *__restrict_
         const float4 *rp = reinterpret_cast<const float4 *>(corpus + (int64_t)row * dim);
         const float4 *qp = reinterpret_cast<const float4 *>(queries + (int64_t)q * dim);
         float dot = 0.f, sq = 0.f;
-        for (int j = lane; j < n4; j += 32) {
-            const float4 a = __ldg(rp + j);
-            const float4 b = __ldg(qp + j);
-            dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot); dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
-            sq = fmaf(a.x, a.x, sq); sq = fmaf(a.y, a.y, sq); sq = fmaf(a.z, a.z, sq); sq = fmaf(a.w, a.w, sq);
+        // the row is read once from HBM with no reuse: keep eight 16-byte loads per lane in flight
+        for (int j0 = lane; j0 < n4; j0 += 32 * 4) {
+            float4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u;
+                a[u] = j < n4 ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                b[u] = j < n4 ? __ldg(qp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                dot = fmaf(a[u].x, b[u].x, dot); dot = fmaf(a[u].y, b[u].y, dot);
+                dot = fmaf(a[u].z, b[u].z, dot); dot = fmaf(a[u].w, b[u].w, dot);
+                sq = fmaf(a[u].x, a[u].x, sq); sq = fmaf(a[u].y, a[u].y, sq);
+                sq = fmaf(a[u].z, a[u].z, sq); sq = fmaf(a[u].w, a[u].w, sq);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -441,6 +454,21 @@ extern "C" int orag_f32_to_bf16(const float *d_src, void *d_dst, int64_t count, 
     orag::f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4 *>(d_src), reinterpret_cast<uint2 *>(d_dst), n4);
     ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+extern "C" int orag_row_sq(const float *d_corpus, int64_t n_rows, int dim, double *d_row_sq, void *stream)
+{
+    ORAG_REQUIRE(d_corpus && d_row_sq && n_rows >= 0 && dim > 0, "row_sq");
+    if (n_rows == 0) return ORAG_OK;
+    // the reference's sum(a * a for a in row): sequential Neumaier sum per row (lane <-> row), 2^31 rows at most
+    ORAG_REQUIRE(n_rows < ((int64_t)1 << 31), "row_sq: n_rows < 2^31");
+    const int chunk = 1 << 22;
+    for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+        const int n = (int)(n_rows - r0 < chunk ? n_rows - r0 : chunk);
+        int rc = orag::launch_query_sq(d_corpus + r0 * dim, n, dim, d_row_sq + r0, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     return ORAG_OK;
 }
 

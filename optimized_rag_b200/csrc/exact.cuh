@@ -87,7 +87,7 @@ int launch_prefilter(const float *corpus, int dim, const float *queries, const f
                      const uint32_t *cnt, int cap, int n_queries, int k, float *cos32, int cap2, int32_t *surv,
                      uint32_t *surv_cnt, int32_t *status, cudaStream_t st);
 int launch_rescore(const float *corpus, int dim, int64_t row_id_base, const float *queries, const double *sq_q,
-                   const int32_t *cand, const uint32_t *cnt, int cap, int n_queries, double *out_scores,
-                   int64_t *out_ids, cudaStream_t st);
+                   const int32_t *cand, const uint32_t *cnt, int cap, int n_queries, const double *row_sq,
+                   double *out_scores, int64_t *out_ids, cudaStream_t st);
 
 }  // namespace orag

@@ -249,7 +249,7 @@ extern "C" int orag_pairwise_cosine_threshold_tc(const float *d_emb, int64_t m, 
     rc = tc::launch_scan(false, d_emb, m, d_emb, dim, p, st);
     if (rc) return rc;
     // float64 re-score of every surviving (i, j) in the reference's arithmetic, then the exact filter
-    rc = launch_rescore(d_emb, dim, 0, d_emb, w.sq, w.cand, w.cnt, kPairCap, (int)m, w.scores, w.ids, st);
+    rc = launch_rescore(d_emb, dim, 0, d_emb, w.sq, w.cand, w.cnt, kPairCap, (int)m, w.sq, w.scores, w.ids, st);
     if (rc) return rc;
     pair_filter_kernel<<<sm_count() * 8, 256, 0, st>>>(w.scores, w.ids, w.cnt, kPairCap, m, d_doc_idx, threshold, cap,
                                                        d_out_i, d_out_j, d_out_sim, d_out_count);

@@ -91,6 +91,12 @@ class CosineIndex:
             _ffi.check(_ffi.lib().orag_f32_to_f16_rows(corpus.data_ptr(), self.n_rows, self.dim, self.shadow.data_ptr(),
                                                        self.inv_norm.data_ptr(), None, _stream(self.device)),
                        "orag_f32_to_f16_rows")
+        self.row_sq = None
+        if mode != "exact":
+            # sum(a*a) of every row in the reference's float64 arithmetic: a per-row constant of the final re-score
+            self.row_sq = torch.empty(self.n_rows, dtype=torch.float64, device=self.device)
+            _ffi.check(_ffi.lib().orag_row_sq(corpus.data_ptr(), self.n_rows, self.dim, self.row_sq.data_ptr(),
+                                              _stream(self.device)), "orag_row_sq")
         self._ws = {}
 
     def _workspace(self, n_queries: int, k: int, mode: int) -> torch.Tensor:
@@ -119,8 +125,9 @@ class CosineIndex:
         ws = self._workspace(Bq, k, m)
         _ffi.check(_ffi.lib().orag_cosine_topk(
             self.corpus.data_ptr(), self.inv_norm.data_ptr() if self.inv_norm is not None else None,
-            self.shadow.data_ptr() if self.shadow is not None else None, self.n_rows, self.dim, self.row_id_base,
-            queries.data_ptr(), Bq, k, m, ids.data_ptr(), sc.data_ptr(), status.data_ptr(), ws.data_ptr(),
+            self.shadow.data_ptr() if self.shadow is not None else None,
+            self.row_sq.data_ptr() if (self.row_sq is not None and m != _ffi.ORAG_COS_EXACT) else None,
+            self.n_rows, self.dim, self.row_id_base, queries.data_ptr(), Bq, k, m, ids.data_ptr(), sc.data_ptr(), status.data_ptr(), ws.data_ptr(),
             ws.numel(), _stream(self.device)), "orag_cosine_topk")
         if status_out is not None:
             status_out.append(status)
