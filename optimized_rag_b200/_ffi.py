@@ -60,6 +60,12 @@ class Bm25IndexStruct(Structure):
 
 
 _lib = None
+# The library keeps per-process state (profiling brackets, auxiliary stream, co-scheduling event) and the Python
+# wrappers cache workspaces per index: the drop-in classes serialise their GPU sections on this lock, which is what
+# the reference's own sharing model needs (one agent used from several threads: ThreadedConnectionPool /
+# EmbeddingService lock, SURVEY.md §8b "Threading").
+import threading  # noqa: E402
+GPU_LOCK = threading.RLock()
 
 
 def lib() -> ctypes.CDLL:

@@ -22,10 +22,21 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 import torch
 
-from . import engine
+import functools
+
+from . import _ffi, engine
 from .bm25_index import Bm25Index
 
 logger = logging.getLogger(__name__)
+
+
+def _gpu_locked(fn):
+    """Serialise the GPU section of a public method on the process-wide lock (see _ffi.GPU_LOCK)."""
+    @functools.wraps(fn)
+    def wrapper(*a, **kw):
+        with _ffi.GPU_LOCK:
+            return fn(*a, **kw)
+    return wrapper
 
 
 class TextVocab:
@@ -152,6 +163,7 @@ class DocumentStore:
             t = self._tables[agent_id] = ChunkTable(self.embedding_dim, self.device)
         return t
 
+    @_gpu_locked
     def upload_and_index(self, agent_id: str, file_path: str, file_content: Optional[str] = None,
                          metadata: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
         try:
@@ -220,6 +232,7 @@ class DocumentStore:
         return {"content": rec["content"], "filename": rec["filename"], "file_type": rec["file_type"],
                 "score": float(score), "metadata": dict(rec["metadata"])}
 
+    @_gpu_locked
     def search(self, agent_id: str, query: str, top_k: int = 5) -> List[Dict[str, Any]]:
         """Search document chunks (rag/document_store.py:424-485)."""
         try:
@@ -237,6 +250,7 @@ class DocumentStore:
             logger.error(f"Search failed: {e}")
             return []
 
+    @_gpu_locked
     def hybrid_search(self, agent_id: str, query: str, top_k: int = 5, fetch_k: Optional[int] = None
                       ) -> List[Dict[str, Any]]:
         """Cosine top-fetch_k + BM25 top-fetch_k -> RRF top_k, all on the GPU."""
@@ -279,6 +293,7 @@ class DocumentStore:
             return []
 
     # ------------------------------------------------------------------ bookkeeping (rag/document_store.py:487-542)
+    @_gpu_locked
     def list_documents(self, agent_id: str) -> List[Dict[str, Any]]:
         try:
             table = self._tables.get(agent_id)
@@ -296,6 +311,7 @@ class DocumentStore:
             logger.error(f"List documents failed: {e}")
             return []
 
+    @_gpu_locked
     def delete_document(self, agent_id: str, document_id: int) -> bool:
         try:
             r = self._documents.get(document_id)

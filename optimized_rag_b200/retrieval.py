@@ -23,7 +23,7 @@ import torch
 
 from . import engine
 from .bm25_index import Bm25Index
-from .document_store import TextVocab
+from .document_store import TextVocab, _gpu_locked
 
 logger = logging.getLogger(__name__)
 
@@ -175,6 +175,7 @@ class HybridRetriever:
             out.append(score)
         return np.asarray(out, dtype=np.float64)
 
+    @_gpu_locked
     def hybrid_search(self, query: str, corpus: List[str], embeddings: List[List[float]],
                       query_embedding: List[float], top_k: int = 10,
                       documents_metadata: Optional[List[Dict[str, Any]]] = None,

@@ -93,6 +93,31 @@ def test_document_store_hybrid_matches_oracle(store):
         assert [r["score"] for r in res] == [cos[i] for i in want["ids"]]  # `score` stays a cosine
 
 
+def test_document_store_is_thread_safe(store):
+    """One store shared by several threads (the reference shares one agent across a connection pool): concurrent
+    searches return exactly what serial searches return."""
+    import threading
+    queries = ["w3 w10 w25", "w1 w7 unique12", "w40 w41 w2 w2", "Doc5 w9"]
+    want = {q: (store.search("agent-a", q, top_k=5), store.hybrid_search("agent-a", q, top_k=5)) for q in queries}
+    errors = []
+
+    def worker(q):
+        try:
+            for _ in range(5):
+                assert store.search("agent-a", q, top_k=5) == want[q][0]
+                assert store.hybrid_search("agent-a", q, top_k=5) == want[q][1]
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(q,)) for q in queries for _ in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert all(len(v[0]) > 0 for v in want.values())
+
+
 def test_document_store_bookkeeping(store):
     docs = store.list_documents("agent-a")
     assert len(docs) == 40 and {"id", "filename", "file_type", "quality_score", "chunk_count", "uploaded_at"} <= set(docs[0])
