@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
     const unsigned FULL = 0xffffffffu;
     const int S = p.q_split;
     const int4 *qd = reinterpret_cast<const int4 *>(p.qd);
-    const int wpl = (words + 31) >> 5;  // bitmap words per lane in the rank / claim passes
+    const int wpl = (words + 31) >> 5;  // bitmap words per lane in the rank pass
+    const bool wpl4 = words == 128;     // (bm and pre are 16-byte aligned: see ms_smem_per_warp)
 
     auto rank_of = [&](uint32_t d) -> int {
         const uint32_t wd = bm[d >> 5];
@@ -382,9 +383,16 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                     __syncwarp();
                     // ---- R: prefix popcounts (lane l owns words [l*wpl, (l+1)*wpl))
                     int mycnt = 0;
-                    for (int t = 0; t < wpl; ++t) {
-                        const int wi = lane * wpl + t;
-                        if (wi < words) mycnt += __popc(bm[wi]);
+                    uint4 w4 = make_uint4(0u, 0u, 0u, 0u);
+                    if (wpl4) {
+                        // 4096-doc tiles: one 16-byte load, one 8-byte store per lane
+                        w4 = reinterpret_cast<const uint4 *>(bm)[lane];
+                        mycnt = __popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w);
+                    } else {
+                        for (int t = 0; t < wpl; ++t) {
+                            const int wi = lane * wpl + t;
+                            if (wi < words) mycnt += __popc(bm[wi]);
+                        }
                     }
                     int incl = mycnt;
 #pragma unroll
@@ -394,7 +402,11 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                     }
                     const int marked = __shfl_sync(FULL, incl, 31);
                     const int my_base = incl - mycnt;
-                    {
+                    if (wpl4) {
+                        const uint32_t p0 = (uint32_t)my_base, p1 = p0 + __popc(w4.x), p2 = p1 + __popc(w4.y),
+                                       p3 = p2 + __popc(w4.z);
+                        reinterpret_cast<uint2 *>(pre)[lane] = make_uint2(p0 | (p1 << 16), p2 | (p3 << 16));
+                    } else {
                         int run_sum = my_base;
                         for (int t = 0; t < wpl; ++t) {
                             const int wi = lane * wpl + t;
@@ -493,25 +505,24 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                                 thr = fmaxf(thr, thr_to_float(kb));
                             }
                         }
-                        // ---- X: every lane claims the marked docs of its own bitmap words: emit, reset
-                        {
-                            int rk = my_base;
-                            for (int t = 0; t < wpl; ++t) {
-                                const int wi = lane * wpl + t;
-                                if (wi >= words) break;
-                                uint32_t wd = bm[wi];
-                                if (wd == 0u) continue;
-                                bm[wi] = 0u;
-                                while (wd) {
-                                    const int b = __ffs(wd) - 1;
-                                    wd &= wd - 1;
-                                    const float v = acc[rk];
-                                    acc[rk] = 0.f;
-                                    ++rk;
-                                    if (v >= thr) ms_emit(p, q, (int32_t)(base_doc + wi * 32 + b), v);
+                        // ---- X: claim by RANK (lane-balanced, conflict-free): read and reset acc[r]; only the rare
+                        // score that clears the threshold needs its doc id -- the word whose rank range holds r
+                        // (binary search in the prefix counts), then the (r - pre[word])-th set bit of that word
+                        for (int r = lane; r < marked; r += 32) {
+                            const float v = acc[r];
+                            acc[r] = 0.f;
+                            if (v >= thr) {
+                                int lo = 0, hi = words - 1;  // last word with pre[word] <= r
+                                while (lo < hi) {
+                                    const int mid = (lo + hi + 1) >> 1;
+                                    if ((int)pre[mid] <= r) lo = mid; else hi = mid - 1;
                                 }
+                                const int b = (int)__fns(bm[lo], 0u, r - (int)pre[lo] + 1);
+                                ms_emit(p, q, (int32_t)(base_doc + lo * 32 + b), v);
                             }
                         }
+                        __syncwarp();
+                        for (int i = lane; i < words; i += 32) bm[i] = 0u;
                     } else {
                         // a skewed sub-range marked more docs than the accumulator holds: the caller re-runs the query
                         if (p.status && lane == 0) atomicOr(p.status + q, ORAG_STATUS_OVERFLOW);
