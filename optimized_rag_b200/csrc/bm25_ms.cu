@@ -59,6 +59,7 @@ constexpr MsShape kMsAlone = {1024, 512, 512};
 constexpr MsShape kMsBackground = {512, 256, 256};
 constexpr int kMsMaxTile = 16384;
 constexpr int kMsSurvCap = 2048;  // candidates re-scored per query
+constexpr int kMsContrib = 4096;  // (survivor, token) contributions staged in shared memory by ms_finalize_kernel
 constexpr float kMsGuard = 1.0f - 1.0f / 512.0f;
 
 // per-warp shared memory: staging buffer | compact accumulator | bitmap | per-word ranks
@@ -581,7 +582,21 @@ __global__ void __launch_bounds__(1024) ms_finalize_kernel(const __grid_constant
     if (overflow && status && threadIdx.x == 0) status[q] |= ORAG_STATUS_OVERFLOW;
     const int32_t *terms = p.q_terms + (int64_t)q * p.max_terms;
     const int nt = min(p.q_lens[q], p.max_terms);
-    for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) ss[i] = score_doc(p.ix, terms, nt, sd[i]);
+    // exact re-score: one thread per (survivor, query token) runs the binary search, then one thread per survivor
+    // adds the contributions in query order (the reference's order)
+    __shared__ double contrib[kMsContrib];
+    if (nt > 0 && (uint64_t)ns * (uint64_t)nt <= (uint64_t)kMsContrib) {
+        for (uint32_t t = threadIdx.x; t < ns * (uint32_t)nt; t += blockDim.x)
+            contrib[t] = term_contribution(p.ix, terms[t % nt], sd[t / nt]);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) {
+            double acc = 0.0;
+            for (int j = 0; j < nt; ++j) acc = __dadd_rn(acc, contrib[i * nt + j]);
+            ss[i] = acc;
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) ss[i] = score_doc(p.ix, terms, nt, sd[i]);
+    }
     __syncthreads();
     // (an overflowed query is re-run by the caller: skip the serial zero-score fill for it)
     select_from_list(p.ix, terms, nt, k, sd, ss, ns, doc_id_base, normalize, out_ids + (int64_t)q * k,

@@ -49,34 +49,38 @@ __device__ __forceinline__ void tighten_threshold(const uint32_t *h, int hi, int
     if (found >= 1) atomicMax(thr_slot, bin_floor_bits(found) - 4ull);
 }
 
-// Exact score of one doc for one query in the reference's arithmetic and order (binary search in each
-// term's run): idf * (tf*(k1+1) / (tf + t4[d])) added per query token in query order, duplicates twice.
-__device__ inline double score_doc(const orag_bm25_index_t &ix, const int32_t *terms, int nt, int64_t doc)
+// Contribution of one query token to one doc in the reference's arithmetic: idf * (tf*(k1+1) / (tf + t4[d])) if the
+// doc contains the term (binary search in the term's run of the doc's tile), else 0.
+__device__ inline double term_contribution(const orag_bm25_index_t &ix, int t, int64_t doc)
 {
+    if (t < 0 || t >= ix.vocab) return 0.0;
+    const double idf = ix.d_idf[t];
+    if (idf == 0.0) return 0.0;
     const int T = ix.tile_docs;
     const int tile = (int)(doc / T);
     const uint32_t want = (uint32_t)(doc - (int64_t)tile * T);
     const uint32_t *tile_post = ix.d_postings + ix.d_tile_base[tile];
     const int32_t *toff = ix.d_tile_term_off + (int64_t)tile * (ix.vocab + 1);
-    const double t4 = ix.d_t4_table[ix.d_doc_len[doc]];
-    double s = 0.0;
-    for (int i = 0; i < nt; ++i) {
-        int t = terms[i];
-        if (t < 0 || t >= ix.vocab) continue;
-        double idf = ix.d_idf[t];
-        if (idf == 0.0) continue;
-        int lo = toff[t], hi = toff[t + 1];
-        const int end = hi;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if ((tile_post[mid] >> 16) < want) lo = mid + 1; else hi = mid;
-        }
-        if (lo < end && (tile_post[lo] >> 16) == want) {
-            double tf = (double)(tile_post[lo] & 0xFFFFu);
-            double c = __dmul_rn(idf, __ddiv_rn(__dmul_rn(tf, 2.5), __dadd_rn(tf, t4)));
-            s = __dadd_rn(s, c);
-        }
+    int lo = toff[t], hi = toff[t + 1];
+    const int end = hi;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if ((tile_post[mid] >> 16) < want) lo = mid + 1; else hi = mid;
     }
+    if (lo < end && (tile_post[lo] >> 16) == want) {
+        const double tf = (double)(tile_post[lo] & 0xFFFFu);
+        const double t4 = ix.d_t4_table[ix.d_doc_len[doc]];
+        return __dmul_rn(idf, __ddiv_rn(__dmul_rn(tf, 2.5), __dadd_rn(tf, t4)));
+    }
+    return 0.0;
+}
+
+// Exact score of one doc for one query in the reference's arithmetic and order: the contributions of the query
+// tokens added in query order, duplicates twice (adding the exact 0.0 of an absent token changes nothing).
+__device__ inline double score_doc(const orag_bm25_index_t &ix, const int32_t *terms, int nt, int64_t doc)
+{
+    double s = 0.0;
+    for (int i = 0; i < nt; ++i) s = __dadd_rn(s, term_contribution(ix, terms[i], doc));
     return s;
 }
 

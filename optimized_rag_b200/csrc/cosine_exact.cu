@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) query_sq_kernel(const float *__restrict__
 {
     __shared__ float stage_all[8][32 * 33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int q = (blockIdx.x * 8 + wib) * 32 + lane;
+    const int q = (blockIdx.x * (blockDim.x >> 5) + wib) * 32 + lane;
     const float *rowptr = q < n_queries ? queries + (int64_t)q * dim : nullptr;
     const float *qp[1] = {nullptr};
     NeuSum dot[1], s;
@@ -153,20 +153,20 @@ __global__ void __launch_bounds__(256) cosine_dense_kernel(const float *__restri
 }
 
 // Re-score candidate rows: cand[q * cap + slot] (local row) -> scores / global ids.
-// grid.x covers (query, 32-slot chunk) pairs; blocks past the query's count exit at once.
-__global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ corpus, int dim, int64_t row_id_base,
-                                                     const float *__restrict__ queries, const double *__restrict__ sq_q,
-                                                     const int32_t *__restrict__ cand, const uint32_t *__restrict__ cnt,
-                                                     int cap, int n_queries, const double *__restrict__ row_sq,
-                                                     double *__restrict__ out_scores, int64_t *__restrict__ out_ids)
+// One warp per CTA, one (query, 32-slot chunk) task per warp: a task is one long dependent chain per lane (1536
+// compensated float64 adds), so the few hundred non-empty tasks of a batch must be spread over ALL SMs with one
+// warp per scheduler, not packed eight to a CTA.  Tasks past a query's count exit at once.
+__global__ void __launch_bounds__(32) rescore_kernel(const float *__restrict__ corpus, int dim, int64_t row_id_base,
+                                                    const float *__restrict__ queries, const double *__restrict__ sq_q,
+                                                    const int32_t *__restrict__ cand, const uint32_t *__restrict__ cnt,
+                                                    int cap, int n_queries, const double *__restrict__ row_sq,
+                                                    double *__restrict__ out_scores, int64_t *__restrict__ out_ids)
 {
-    __shared__ float stage_all[8][32 * 33];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    __shared__ float stage[32 * 33];
+    const int lane = threadIdx.x;
     const int chunks_per_q = (cap + 31) / 32;
-    int64_t warp = blockIdx.x * (int64_t)(blockDim.x >> 5) + wib;
-    int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t w = warp; w < (int64_t)n_queries * chunks_per_q; w += n_warps) {
-        // chunk-major task order: the (few) non-empty chunks of all queries land on distinct warps
+    for (int64_t w = blockIdx.x; w < (int64_t)n_queries * chunks_per_q; w += gridDim.x) {
+        // chunk-major task order: the (few) non-empty chunks of all queries are the first n_queries tasks
         int q = (int)(w % n_queries);
         int chunk = (int)(w / n_queries);
         uint32_t n = min(cnt[q], (uint32_t)cap);
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
         const float *qp[1] = {queries + (int64_t)q * dim};
         NeuSum dot[1], sq;
         // sum(x*x) of a row does not depend on the query: with the ingest-time table only the dot chain remains
-        warp_score_rows<1>(rowptr, qp, dim, stage_all[wib], dot, sq, row_sq == nullptr);
+        warp_score_rows<1>(rowptr, qp, dim, stage, dot, sq, row_sq == nullptr);
         if (row >= 0) {
             const double sq_r = row_sq ? row_sq[row] : sq.result();
             out_scores[(int64_t)q * cap + slot] = cosine_from_sums(dot[0].result(), sq_q[q], sq_r);
@@ -270,7 +270,12 @@ int launch_select_topk(const double *scores, const int64_t *ids, const uint32_t 
 
 int launch_query_sq(const float *queries, int n_queries, int dim, double *sq, cudaStream_t st)
 {
-    query_sq_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, st>>>(queries, n_queries, dim, sq);
+    // a query batch is a handful of warps, each one long dependent chain: one warp per CTA spreads them over the
+    // SMs; the ingest-time sweep over millions of rows (orag_row_sq) keeps eight warps per CTA
+    if (n_queries <= 4096)
+        query_sq_kernel<<<(unsigned)((n_queries + 31) / 32), 32, 0, st>>>(queries, n_queries, dim, sq);
+    else
+        query_sq_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, st>>>(queries, n_queries, dim, sq);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }
@@ -291,12 +296,11 @@ int launch_rescore(const float *corpus, int dim, int64_t row_id_base, const floa
                    const int32_t *cand, const uint32_t *cnt, int cap, int n_queries, const double *row_sq,
                    double *out_scores, int64_t *out_ids, cudaStream_t st)
 {
-    int64_t warps = (int64_t)n_queries * ((cap + 31) / 32);
-    int64_t blocks = (warps + 7) / 8;
-    int64_t lim = (int64_t)sm_count() * 8;
+    int64_t blocks = (int64_t)n_queries * ((cap + 31) / 32);
+    int64_t lim = (int64_t)sm_count() * 32;
     if (blocks > lim) blocks = lim;
     if (blocks < 1) blocks = 1;
-    rescore_kernel<<<(unsigned)blocks, 256, 0, st>>>(corpus, dim, row_id_base, queries, sq_q, cand, cnt, cap,
+    rescore_kernel<<<(unsigned)blocks, 32, 0, st>>>(corpus, dim, row_id_base, queries, sq_q, cand, cnt, cap,
                                                      n_queries, row_sq, out_scores, out_ids);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
