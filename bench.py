@@ -307,7 +307,7 @@ def run_native(args):
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
-        traffic = json.loads(tp.read_text()).get("cosine_scan_bf16" if half else f"cosine_scan_{args.mode}")
+        traffic = json.loads(tp.read_text()).get(f"cosine_scan_{args.mode}")
     hbm = {"bound": "hbm", "achieved": streamed / t_scan / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
            "frac": streamed / t_scan / 1e9 / pk["hbm_gbs"], "traffic": traffic,
            "bytes": f"{args.mode} shadow copy actually streamed (N*D*2)" if half else "fp32 corpus (N*D*4)"}
