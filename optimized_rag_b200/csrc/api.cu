@@ -52,8 +52,28 @@ __global__ void scale_norms_kernel(const float *inv_qnorm_s, const float *scale,
     }
 }
 
-static cudaStream_t g_aux_stream = nullptr;
-static cudaEvent_t g_aux_fork = nullptr, g_aux_join = nullptr;
+// auxiliary stream + fork/join events, one set per device (a stream belongs to the device it was created on)
+constexpr int kMaxDevices = 64;
+struct AuxStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static AuxStream g_aux[kMaxDevices];
+
+static int aux_for_current_device(AuxStream **out)
+{
+    int dev = 0;
+    ORAG_CUDA_CHECK(cudaGetDevice(&dev));
+    ORAG_REQUIRE(dev >= 0 && dev < kMaxDevices, "device ordinal");
+    AuxStream &a = g_aux[dev];
+    if (!a.stream) {
+        ORAG_CUDA_CHECK(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+        ORAG_CUDA_CHECK(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+        ORAG_CUDA_CHECK(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+    }
+    *out = &a;
+    return ORAG_OK;
+}
 
 __global__ void unscale_columns_kernel(float *out, int64_t n, const float *scale, int n_queries)
 {
@@ -256,22 +276,20 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
         const int nq = n_queries - q0 < kGroup ? n_queries - q0 : kGroup;
         const float *q = d_queries + (int64_t)q0 * dim;
         int rc;
+        AuxStream *aux = nullptr;
         const void *qop = q;
         const float *qnorm_scan = w.qnorm, *inv_qnorm_scan = w.inv_qnorm;
         if (f16) {
             // The exact float64 sum(q*q) (one sequential compensated chain per query, ~65 us) is only needed by
             // the final re-score: it runs on an auxiliary stream next to the scan.  The scan's thresholds use fp32
             // norms that fall out of the fp16 conversion of the query block (error far inside the 2.5e-4 slack).
-            if (!g_aux_stream) {
-                ORAG_CUDA_CHECK(cudaStreamCreateWithFlags(&g_aux_stream, cudaStreamNonBlocking));
-                ORAG_CUDA_CHECK(cudaEventCreateWithFlags(&g_aux_fork, cudaEventDisableTiming));
-                ORAG_CUDA_CHECK(cudaEventCreateWithFlags(&g_aux_join, cudaEventDisableTiming));
-            }
-            ORAG_CUDA_CHECK(cudaEventRecord(g_aux_fork, st));
-            ORAG_CUDA_CHECK(cudaStreamWaitEvent(g_aux_stream, g_aux_fork, 0));
-            rc = launch_query_sq(q, nq, dim, w.sq_q, g_aux_stream);
+            rc = aux_for_current_device(&aux);
             if (rc) return rc;
-            ORAG_CUDA_CHECK(cudaEventRecord(g_aux_join, g_aux_stream));
+            ORAG_CUDA_CHECK(cudaEventRecord(aux->fork, st));
+            ORAG_CUDA_CHECK(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+            rc = launch_query_sq(q, nq, dim, w.sq_q, aux->stream);
+            if (rc) return rc;
+            ORAG_CUDA_CHECK(cudaEventRecord(aux->join, aux->stream));
             rc = orag_f32_to_f16_rows(q, nq, dim, w.q_bf16, w.inv_qnorm_s, w.q_scale, st);
             if (rc) return rc;
             scale_norms_kernel<<<(nq + 255) / 256, 256, 0, st>>>(w.inv_qnorm_s, w.q_scale, nq, w.qnorm_s, w.qnorm,
@@ -331,7 +349,7 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
                               w.surv_cnt, d_out_status ? d_out_status + q0 : nullptr, st);
         if (rc) return rc;
         // ... exact float64 re-score of those (the reference's arithmetic), then exact selection
-        if (f16) ORAG_CUDA_CHECK(cudaStreamWaitEvent(st, g_aux_join, 0));
+        if (f16) ORAG_CUDA_CHECK(cudaStreamWaitEvent(st, aux->join, 0));
         rc = launch_rescore(d_corpus, dim, row_id_base, q, w.sq_q, w.surv, w.surv_cnt, kSurvCap, nq, d_row_sq,
                             w.cand_score, w.cand_id, st);
         if (rc) return rc;

@@ -3,8 +3,8 @@
 // Same result as bm25.cu (bit-exact float64 scores of rank_bm25.BM25Okapi.get_scores + the glue at
 // rag/retrieval.py:324-347) at a fraction of the instructions per posting.
 //
-// First-pass view.  The index carries a second tiling of the postings with much larger tiles (up to 16384
-// docs): (doc_in_tile << 16) | fp16(r), r = tf*(k1+1)/(tf + t4[dl]) rounded to nearest, so a posting's
+// First-pass view.  The index carries a second tiling of the postings (4096-doc tiles by default, up to 16384):
+// (doc_in_tile << 16) | fp16(r), r = tf*(k1+1)/(tf + t4[dl]) rounded to nearest, so a posting's
 // contribution is one fp32 multiply w*r (w = fp32 idf, duplicates of a query term merged into one weight)
 // and needs no document-length or table lookup.  Every approximate score s~ satisfies |s~ - s| <= eps*s with
 // eps = 2^-11 (fp16 r) + (n_terms + 2) * 2^-24 (fp32 weight, products, sums) < 5e-4: all terms are positive.
@@ -18,14 +18,19 @@
 // One warp works on one (query, tile) pair at a time with three small shared-memory structures: a bitmap of
 // the tile's docs, per-word prefix popcounts, and a compact fp32 accumulator indexed by a doc's RANK among
 // the marked docs (so the accumulator is sized by the docs a query touches, not by the tile):
-//   E1  mark the docs of the essential runs in the bitmap (shared-memory atomicOr)
+//   E1  mark the docs of the essential runs in the bitmap (shared-memory atomicOr); the runs that were essential
+//       by the threshold of one pair earlier have been copied into a per-warp staging buffer with 16-byte
+//       cp.async (issued right after E2 of the previous pair), the rest is read from global memory
 //   R   prefix popcounts -> rank(d); the number of marked docs must fit the accumulator, otherwise the pair
 //       is processed in doc sub-ranges (runs are doc-sorted: a sub-range is a contiguous part of every run,
-//       found by one binary search per run and boundary)
+//       found by one binary search per run and boundary), re-reading the threshold in between
 //   E2  add the essential contributions into acc[rank(d)]
-//   N   stream the non-essential runs with 16-byte loads; a posting only matters when its doc is marked
-//       (one shared-memory word test), in which case its contribution completes acc[rank(d)]
-//   X   claim every marked doc once, reset, emit those with s~ >= thr'
+//   N   stream the non-essential runs with 16-byte loads (two in flight per lane); a posting only matters when
+//       its doc is marked (one shared-memory word test), in which case its contribution completes acc[rank(d)]
+//   L   (cold sub-ranges only) the k-th largest of the 32 lane maxima of acc is a lower bound of the k-th best
+//       approximate score: publish it as the threshold before anything is emitted
+//   X   lanes walk the RANKS (balanced, conflict-free): read and reset acc[r]; a score that clears thr' gets
+//       its doc id back from the prefix counts (binary search + find-n-th-set-bit) and is emitted
 // Docs are distinct inside a run, and runs are applied one at a time with __syncwarp in between, so plain
 // read-modify-writes suffice (no floating-point atomics).
 //
