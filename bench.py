@@ -89,8 +89,8 @@ def run_reference(args):
     import oracle
     from optimized_rag_b200 import synthetic as syn
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     oracle.build()
+    oracle.set_threads(cores)  # torchrun exports OMP_NUM_THREADS=1: the baseline is "all host cores"
     S, Bs = args.ref_sample_rows, args.ref_sample_queries
     thr = syn.zipf_thresholds(VOCAB)
     corpus = syn.embeddings(syn.SEED_CORPUS, 0, S, DIM)
@@ -348,8 +348,8 @@ def run_native(args):
     if cpu_sample is not None:
         import oracle
         cores = os.cpu_count() or 1
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
         oracle.build()
+        oracle.set_threads(cores)
         c_np, off_np, tok_np = cpu_sample
         S = c_np.shape[0]
         ob = oracle.BM25Index(off_np, tok_np, VOCAB)

@@ -54,6 +54,8 @@ def lib() -> ctypes.CDLL:
     if _lib is None:
         build()
         L = ctypes.CDLL(str(_LIB_PATH))
+        L.orc_set_threads.restype = ctypes.c_int
+        L.orc_set_threads.argtypes = [ctypes.c_int]
         L.orc_cosine.restype = ctypes.c_double
         L.orc_cosine.argtypes = [_c_f32p, _c_f32p, ctypes.c_int, ctypes.c_int]
         L.orc_cosine_scores.restype = None
@@ -93,8 +95,10 @@ def _p(a: np.ndarray, typ):
 
 
 def set_threads(n: int | None) -> None:
+    """Threads of the OpenMP row loop (overrides an OMP_NUM_THREADS=1 exported by a launcher such as torchrun)."""
     if n:
         os.environ["OMP_NUM_THREADS"] = str(n)
+        lib().orc_set_threads(int(n))
 
 
 # --------------------------------------------------------------------------- cosine

@@ -60,6 +60,23 @@ static double sum_prod(const float *a, const float *b, int d, int neumaier)
     return s;
 }
 
+/* Threads of the row loop below (a launcher such as torchrun exports OMP_NUM_THREADS=1, which would turn the
+ * "all host cores" CPU baseline into a single-core one).  Returns the previous maximum. */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+int orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    int prev = omp_get_max_threads();
+    if (n > 0) omp_set_num_threads(n);
+    return prev;
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 double orc_cosine(const float *a, const float *b, int d, int neumaier)
 {
     double dot = sum_prod(a, b, d, neumaier);
