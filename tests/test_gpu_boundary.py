@@ -218,3 +218,39 @@ def test_hybrid_retriever_dispatch(store):
     out = hr.retrieve("w1 w2", ["documents", "archival", "conversation"], top_k=3)
     assert [r["source"] for r in out] == ["archival_memory"] + ["documents"] * 3
     assert hr.retrieve("w1", [], 3) == []
+
+
+def test_gpu_archival_memory_matches_oracle(store):
+    """the archival tier on the same cosine kernel, result keys of
+    database/operations.py:147-156, exact float64 similarities ordered (similarity desc, id asc)."""
+    from datetime import datetime, timezone
+    from optimized_rag_b200.archival import GpuArchivalMemory
+    from optimized_rag_b200.embeddings import SyntheticEmbeddingService
+    from optimized_rag_b200.retrieval import HybridRetriever
+    emb = SyntheticEmbeddingService()
+    t0 = datetime(2026, 1, 1, tzinfo=timezone.utc)
+    mem = GpuArchivalMemory("agent-a", emb, device="cuda:0", now=lambda: t0)
+    assert mem.archival_memory_search("anything", top_k=3) == []
+    texts = [f"memory number {i} about topic t{i % 17} and w{i % 5}" for i in range(300)]
+    ids = [mem.archival_memory_insert(t, {"i": i}) for i, t in enumerate(texts)]
+    assert ids == list(range(1, 301)) and len(mem) == 300
+    with pytest.raises(ValueError):
+        mem.archival_memory_insert("   ")
+    corpus = np.asarray([emb.generate_embedding(t) for t in texts], dtype=np.float32)
+    for query in ("memory number 7 about topic t7 and w2", "something else entirely"):
+        got = mem.archival_memory_search(query, top_k=6)
+        q = np.asarray(emb.generate_embedding(query), dtype=np.float32)
+        wi, ws = oracle.topk(oracle.cosine_scores(corpus, q), 6)
+        assert [g["id"] for g in got] == [int(i) + 1 for i in wi]
+        assert [g["similarity"] for g in got] == ws.tolist()
+        assert set(got[0]) == {"id", "content", "metadata", "similarity", "created_at"}
+        assert got[0]["created_at"] == t0 and got[0]["metadata"] == {"i": int(wi[0])}
+    got[0]["metadata"]["mutated"] = True  # results are fresh dicts
+    assert "mutated" not in mem.archival_memory_search("something else entirely", top_k=1)[0]["metadata"]
+    # the retriever dispatch stays on the GPU path for both sources
+    hr = HybridRetriever(mem, store, "agent-a", device="cuda:0")
+    out = hr.retrieve("memory number 7 about topic t7 and w2", ["archival", "documents"], top_k=4)
+    assert [r["source"] for r in out] == ["archival_memory"] * 4 + ["documents"] * 4
+    assert out[0]["content"] == texts[7]
+    assert mem.delete_archival_memory(8) and not mem.delete_archival_memory(8) and len(mem) == 299
+    assert mem.archival_memory_search("memory number 7 about topic t7 and w2", top_k=1)[0]["id"] != 8
