@@ -71,6 +71,32 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"((uint64_t)(uintptr_t)map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
+// same load, delivered to the same shared-memory offset of every CTA in `cta_mask` (and signalling the mbarrier at the
+// same offset in each of them)
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar,
+                                                      uint16_t cta_mask, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%4, %5}], [%2], %3, %6;"
+        ::"r"(dst), "l"((uint64_t)(uintptr_t)map), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar)
@@ -201,7 +227,7 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(smem_u32(full_bar + s), 1);
-            mbar_init(smem_u32(empty_bar + s), 1);
+            mbar_init(smem_u32(empty_bar + s), p.cluster2 ? 2 : 1);  // cluster2: both CTAs' MMAs release a slot
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(tmem_full + s), 1);
@@ -216,9 +242,14 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (p.cluster2) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // cluster2: both CTAs of a pair run the same number of tiles (they share every query slab); tiles past the
+    // end are all-zero (TMA out-of-bounds fill) and emit nothing
+    const int tile_limit = p.cluster2 ? (int)((p.num_tiles + gridDim.x - 1) / gridDim.x) * (int)gridDim.x : p.num_tiles;
+    const uint32_t cta_rank = p.cluster2 ? cluster_ctarank() : 0u;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -228,7 +259,8 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const uint32_t tx = kABytes + (uint32_t)p.umma_n * 128u;
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int half_rows = p.umma_n >> 1;  // cluster2: this CTA fetches query rows [rank * half, +half)
+            for (int tile = blockIdx.x; tile < tile_limit; tile += gridDim.x) {
                 int64_t row0;
                 int qoff;
                 decode_tile(p, tile, row0, qoff);
@@ -238,7 +270,12 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     const uint32_t fb = smem_u32(full_bar + stage);
                     mbar_expect_tx(fb, tx);
                     tma_load_2d(smem_u32(smem_a + stage * kABytes), &map_a, kc * p.chunk_elems, row, fb, pol_stream);
-                    tma_load_2d(smem_u32(smem_b + stage * kBBytes), &map_b, kc * p.chunk_elems, qoff, fb, pol_keep);
+                    if (p.cluster2)
+                        tma_load_2d_multicast(smem_u32(smem_b + stage * kBBytes) + cta_rank * (uint32_t)half_rows * 128u,
+                                              &map_b, kc * p.chunk_elems, qoff + (int)cta_rank * half_rows, fb,
+                                              (uint16_t)3, pol_keep);
+                    else
+                        tma_load_2d(smem_u32(smem_b + stage * kBBytes), &map_b, kc * p.chunk_elems, qoff, fb, pol_keep);
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -249,7 +286,7 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < tile_limit; tile += gridDim.x, ++it) {
                 const int as = it & 1;
                 mbar_wait(smem_u32(tmem_empty + as), (((uint32_t)it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
@@ -263,7 +300,9 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     for (int k4 = 0; k4 < 4; ++k4)  // 4 x 32 bytes of K per 128-byte chunk
                         tc_mma<kBf16>(d_tmem, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), p.idesc,
                                       (uint32_t)((kc | k4) != 0));
-                    tc_commit(smem_u32(empty_bar + stage));  // frees the smem slot when these MMAs retire
+                    // frees the smem slot when these MMAs retire (cluster2: in both CTAs, whose producers write it)
+                    if (p.cluster2) tc_commit_multicast(smem_u32(empty_bar + stage), (uint16_t)3);
+                    else tc_commit(smem_u32(empty_bar + stage));
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
                 tc_commit(smem_u32(tmem_full + as));  // accumulator ready for the epilogue
@@ -276,7 +315,7 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int half = ew >> 2;    // which 128 query columns
         const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..255
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < tile_limit; tile += gridDim.x, ++it) {
             const int as = it & 1;
             float *thrv = thrv_s + as * kMaxN;
             int64_t row0;
@@ -344,7 +383,8 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (p.cluster2) cluster_sync_all();  // no CTA leaves while its peer can still write its shared memory / barriers
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -476,11 +516,17 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
     if (p.umma_n < 16) p.umma_n = 16;
     int rc = make_map(&map_a, a_base, bf16, p.f16 != 0, a_rows, dim, kTileM);
     if (rc) return rc;
-    rc = make_map(&map_b, q_base, bf16, p.f16 != 0, p.n_queries, dim, p.pair_mode ? kMaxN : p.umma_n);
+    p.num_tiles = (int)((p.row_end - p.row_begin + kTileM - 1) / kTileM);
+    // clusters of two CTAs sharing the query slabs: main scans only, enough tiles to keep every pair busy
+    // (ORAG_SCAN_CLUSTER: 0 = never, 1 = default rule, 2 = whenever there are two tiles -- tests)
+    static const int cluster_mode = getenv("ORAG_SCAN_CLUSTER") ? atoi(getenv("ORAG_SCAN_CLUSTER")) : 1;
+    const int min_tiles = cluster_mode >= 2 ? 2 : 4 * sm_count();
+    p.cluster2 = (cluster_mode && !p.dense && !p.pair_mode && p.umma_n >= 32 && p.num_tiles >= min_tiles) ? 1 : 0;
+    rc = make_map(&map_b, q_base, bf16, p.f16 != 0, p.n_queries, dim,
+                  p.pair_mode ? kMaxN : (p.cluster2 ? p.umma_n / 2 : p.umma_n));
     if (rc) return rc;
     p.chunk_elems = bf16 ? 64 : 32;
     p.k_chunks = dim / p.chunk_elems;
-    p.num_tiles = (int)((p.row_end - p.row_begin + kTileM - 1) / kTileM);
     if (p.pair_mode) {
         const int nb = (p.n_queries + kMaxN - 1) / kMaxN;
         p.num_tiles = nb * (nb + 1);
@@ -488,16 +534,27 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
     }
     p.idesc = make_idesc(bf16, p.f16 != 0, p.umma_n);
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    if (p.cluster2) grid &= ~1;
     if (!p.dense) profile_mark(0, 0, st);
-    if (bf16) {
-        ORAG_CUDA_CHECK(cudaFuncSetAttribute(cosine_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kSmemBytes));
-        cosine_scan_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(map_a, map_b, p);
-    } else {
-        ORAG_CUDA_CHECK(cudaFuncSetAttribute(cosine_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kSmemBytes));
-        cosine_scan_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(map_a, map_b, p);
-    }
+    auto launch = [&](auto kernel) -> int {
+        ORAG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = kSmemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = p.cluster2 ? 2 : 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ORAG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, p));
+        return ORAG_OK;
+    };
+    rc = bf16 ? launch(cosine_scan_kernel<true>) : launch(cosine_scan_kernel<false>);
+    if (rc) return rc;
     if (!p.dense) profile_mark(0, 1, st);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;

@@ -44,6 +44,9 @@ struct ScanParams {
     int k;
     int fixed_thr;          // 1: thresholds are given (pairwise >= t search): no histogram, no tightening
     int pair_mode;          // 1: all-pairs search, queries = corpus rows, triangular (query block, row tile) tiles
+    int cluster2;           // 1: launched as clusters of two CTAs that share every query slab: each CTA fetches half of
+                            //    it from L2 and multicasts it into both CTAs' shared memory (halves the L2 -> SM traffic
+                            //    of the B operand); set by launch_scan
 };
 
 int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_base, int dim, ScanParams p,

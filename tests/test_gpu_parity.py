@@ -5,6 +5,9 @@ Bars (BASELINE.json north_star): BM25 / RRF bit-exact ids, ranks and scores; cos
 scores within 1e-5 relative (we additionally assert bitwise equality, which the float64 re-score
 achieves), ties broken by chunk id.
 """
+import os
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
@@ -16,6 +19,7 @@ from conftest import fromhex
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
+ROOT = Path(__file__).resolve().parents[1]
 
 
 @pytest.fixture(scope="module")
@@ -547,3 +551,27 @@ def test_dense_topk_normalisation_edges(eng):
     assert ids.cpu().tolist() == [[0, 1, 2], [2, 0, 1], [1, 2, 0]]
     assert mx.cpu().tolist() == [1.0, 1.0, 4.0]  # max <= 0 -> divisor 1.0 (rag/retrieval.py:344)
     assert sc.cpu().tolist() == [[0.0, 0.0, 0.0], [-0.5, -1.0, -2.0], [1.0, 1.0, 0.5]]
+
+
+def test_cosine_scan_cluster_pairs_forced_on_small_inputs():
+    """The main scan runs as clusters of two CTAs that multicast the query slabs to each other once a shard has
+    >= 4 tiles per SM; ORAG_SCAN_CLUSTER=2 (read once per process, hence the subprocess) forces that path on small
+    inputs: odd tile counts (one CTA of the last pair gets an all-zero tile), ragged tails, few queries."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from optimized_rag_b200 import engine, synthetic as syn
+for n, dim, nq in [(128 * 5 + 77, 256, 70), (128 * 301, 1536, 256), (4500, 64, 3)]:
+    corpus = torch.from_numpy(syn.embeddings(syn.SEED_CORPUS, 0, n, dim, 2)).cuda()
+    q = torch.from_numpy(syn.query_embeddings(nq, n, dim, dup_per_mille=2)).cuda()
+    want = engine.CosineIndex(corpus, mode="exact").topk(q, 10)
+    for mode in ("f16", "tf32", "bf16"):
+        got = engine.CosineIndex(corpus, mode=mode).topk(q, 10)
+        assert torch.equal(want[0], got[0]) and torch.equal(want[1], got[1]), (n, dim, nq, mode)
+print("cluster ok")
+''' % str(ROOT)
+    env = dict(os.environ, ORAG_SCAN_CLUSTER="2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "cluster ok" in r.stdout, r.stdout + r.stderr
