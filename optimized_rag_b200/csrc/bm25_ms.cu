@@ -335,9 +335,11 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) etot += __shfl_xor_sync(FULL, etot, o);
                 // number of doc sub-ranges: marked docs per sub-range must fit the compact accumulator
-                int nsub = 1;
-                while (nsub * kMsSubTarget < etot && nsub * 32 < T) nsub <<= 1;
-                const int sub_docs = T / nsub;
+                int nsub = 1, sub_docs = T;  // T and nsub are powers of two
+                while (nsub * kMsSubTarget < etot && sub_docs > 32) {
+                    nsub <<= 1;
+                    sub_docs >>= 1;
+                }
                 int cpos = 0;  // this lane's run: first posting of the current sub-range
                 for (int sub = 0; sub < nsub; ++sub) {
                     if (sub > 0) {
