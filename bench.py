@@ -218,7 +218,7 @@ def run_native(args):
     out_ids_h = torch.empty((Bq, k), dtype=torch.int64).pin_memory()
     out_sc_h = torch.empty((Bq, k), dtype=torch.float64).pin_memory()
     h2d = q_emb_h.numel() * 4 + q_tok_h.numel() * 4 + q_len_h.numel() * 4
-    d2h = out_ids_h.numel() * 8 + out_sc_h.numel() * 8
+    d2h = out_ids_h.numel() * 8 + out_sc_h.numel() * 8 + Bq * 4
 
     def barrier():
         if world > 1:
@@ -250,28 +250,39 @@ def run_native(args):
     ev0.record()
     import ctypes
     a, b = ctypes.c_float(), ctypes.c_float()
+    # back-to-back batches, inputs resident: nothing synchronises with the host inside the timed region (the per-query
+    # overflow flags of every step are kept and checked after it -- a flagged step would invalidate the run)
+    flags = []
     for _ in range(args.steps):
-        res = sh.search(q_emb, q_tok, q_len, k)
-        L.orag_profile_read(ctypes.byref(a), ctypes.byref(b))  # waits for the step's scan / BM25 kernels only
-        scan_ms.append(a.value); bm_ms.append(b.value)
+        res = sh.search(q_emb, q_tok, q_len, k, check_overflow=False)
+        flags.append(res["status"])
     ev1.record()
     barrier()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = int(L.orag_launch_count()) - launches0
+    if bool(torch.stack(flags).any()):
+        raise SystemExit("bench: a candidate buffer overflowed inside the timed region; results would need the repair path")
+    L.orag_profile_read(ctypes.byref(a), ctypes.byref(b))  # brackets of the last step's scan / BM25 first-pass kernels
+    scan_ms.append(a.value); bm_ms.append(b.value)
     L.orag_profile_enable(0)
 
     # ---- timed: end to end through the public call with HOST buffers
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    status_h = torch.empty(Bq, dtype=torch.int32).pin_memory()
     for _ in range(args.steps):
         q_emb.copy_(q_emb_h, non_blocking=True)
         q_tok.copy_(q_tok_h, non_blocking=True)
         q_len.copy_(q_len_h, non_blocking=True)
-        r = sh.search(q_emb, q_tok, q_len, k)
+        r = sh.search(q_emb, q_tok, q_len, k, check_overflow=False)
         out_ids_h.copy_(r["ids"], non_blocking=True)
         out_sc_h.copy_(r["rrf_scores"], non_blocking=True)
+        status_h.copy_(r["status"], non_blocking=True)   # the overflow flags travel with the result: ONE sync per step
         torch.cuda.current_stream().synchronize()
+        if int(status_h.max()) != 0:                      # rare: repair through the exhaustive kernels
+            r = sh.search(q_emb, q_tok, q_len, k, check_overflow=True)
+            out_ids_h.copy_(r["ids"]); out_sc_h.copy_(r["rrf_scores"])
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))

@@ -123,6 +123,7 @@ class ShardedHybrid:
         kk = fetch_k + BM25_GUARD
         ci, cs, bi, bs, bm, st = self.shard.local_lists(query_emb, query_terms, query_lens, fetch_k, kk, False)
         out, status = self._exchange(pack_local(ci, cs, bi, bs, bm, st), fetch_k, kk, k)
+        out["status"] = status  # check_overflow=False: no host sync at all; the caller checks it with the results
         if check_overflow and bool(status.any()):
             bad = torch.nonzero(status).flatten()
             lists = self.shard.exact_lists(query_emb[bad].contiguous(), query_terms[bad].contiguous(),
@@ -134,4 +135,5 @@ class ShardedHybrid:
             self._gather_buf = buf
             for key, val in fixed.items():
                 out[key][bad] = val
+            out["status"] = torch.zeros_like(status)
         return out

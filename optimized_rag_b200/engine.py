@@ -346,8 +346,10 @@ class HybridShard:
         lists = torch.stack([ci, bi], dim=1).contiguous()
         fi, fs, src = rrf_fuse(lists, self.rrf_k, k, want_src=True)
         out = {"ids": fi, "rrf_scores": fs, "src_ranks": src, "cos_ids": ci, "cos_scores": cs, "bm25_ids": bi,
-               "bm25_scores": bs, "bm25_max": bmax}
-        # one host round trip per step, after everything has been enqueued (the caller reads the result anyway)
+               "bm25_scores": bs, "bm25_max": bmax, "status": status}
+        # one host round trip per step, after everything has been enqueued (the caller reads the result anyway).
+        # With check_overflow=False nothing synchronises: a caller that pipelines batches checks out["status"]
+        # (non-zero = that query's lists are invalid and must be repaired) whenever it reads the results.
         if check_overflow and bool(status.any()):
             bad = torch.nonzero(status).flatten()
             ci2, cs2, bi2, bs2, bm2 = self.exact_lists(query_emb[bad].contiguous(), query_terms[bad].contiguous(),
@@ -356,4 +358,5 @@ class HybridShard:
             for key, val in (("ids", f2), ("rrf_scores", s2), ("src_ranks", r2), ("cos_ids", ci2), ("cos_scores", cs2),
                              ("bm25_ids", bi2), ("bm25_scores", bs2), ("bm25_max", bm2)):
                 out[key][bad] = val
+            out["status"] = torch.zeros_like(status)
         return out
