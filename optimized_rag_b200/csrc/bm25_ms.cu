@@ -25,8 +25,9 @@
 //       is processed in doc sub-ranges (runs are doc-sorted: a sub-range is a contiguous part of every run,
 //       found by one binary search per run and boundary), re-reading the threshold in between
 //   E2  add the essential contributions into acc[rank(d)]
-//   N   stream the non-essential runs with 16-byte loads (two in flight per lane); a posting only matters when
-//       its doc is marked (one shared-memory word test), in which case its contribution completes acc[rank(d)]
+//   N   stream the non-essential runs with 16-byte loads (two in flight per lane), most valuable term first; a
+//       posting only matters when its doc is marked (one shared-memory word test), in which case its contribution
+//       completes acc[rank(d)]; the remaining runs are skipped once max(acc) + their upper bounds < thr'
 //   L   (cold sub-ranges only) the k-th largest of the 32 lane maxima of acc is a lower bound of the k-th best
 //       approximate score: publish it as the threshold before anything is emitted
 //   X   lanes walk the RANKS (balanced, conflict-free): read and reset acc[r]; a score that clears thr' gets
@@ -453,9 +454,25 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                         staged_next = true;
                     }
                     if (fits) {
-                        // ---- N: non-essential runs complete the marked docs only (streamed, one load ahead)
-                        for (unsigned a = non; a; a &= a - 1) {
-                            const int i = __ffs(a) - 1;
+                        // ---- N: non-essential runs complete the marked docs only (streamed, one load ahead), most
+                        // valuable term first.  Before every run: if even the best partial score plus everything the
+                        // remaining terms could add stays below thr', nothing in this sub-range can be emitted and the
+                        // remaining (longest) runs are not read at all.
+                        bool reachable = true;
+                        for (unsigned a = non; a;) {
+                            const int i = 31 - __clz(a);
+                            a &= ~(1u << i);
+                            {
+                                float mx = 0.f;
+                                for (int r = lane; r < marked; r += 32) mx = fmaxf(mx, acc[r]);
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+                                const float rest = __shfl_sync(FULL, cur.pre, i);  // upper bounds of terms 0..i
+                                if (__fadd_ru(mx, rest) < thr) {
+                                    reachable = false;
+                                    break;
+                                }
+                            }
                             const int len_ = __shfl_sync(FULL, v_len, i);
                             const uint32_t *gp_ = tp + __shfl_sync(FULL, v_rel, i);
                             const float w = __shfl_sync(FULL, cur.w, i);
@@ -537,7 +554,7 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                         for (int r = lane; r < marked; r += 32) {
                             const float v = acc[r];
                             acc[r] = 0.f;
-                            if (v >= thr) {
+                            if (reachable && v >= thr) {
                                 int lo = 0, hi = words - 1;  // last word with pre[word] <= r
                                 while (lo < hi) {
                                     const int mid = (lo + hi + 1) >> 1;
