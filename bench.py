@@ -345,9 +345,13 @@ def run_native(args):
     e2e_val = Bq * args.steps / (e2e_ms * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64 scores (first pass " + args.mode + ")",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": workload_config(args, {"first_pass": args.mode, "rows_per_gpu": n_local,
+            "config": workload_config(args, {"first_pass": args.mode,
+                                             "arithmetic": "results in the reference's float64 arithmetic (bit-exact); "
+                                                           f"candidate generation {args.mode} tensor cores / fp32 BM25 "
+                                                           "with proven error margins, then exact re-score",
+                                             "rows_per_gpu": n_local,
                                              "parallelism": f"row-sharded x{world}", "setup_s": round(t_setup, 1),
                                              "bm25_postings_local": bm25.n_postings}),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
