@@ -292,6 +292,42 @@ class DocumentStore:
             logger.error(f"Hybrid search failed: {e}")
             return []
 
+    # ------------------------------------------------------------------ persistence
+    # The reference's "format" is Postgres rows (DDL rag/document_store.py:190-221).  Here: one directory per store,
+    #   store.json                 documents, per-agent chunk records (content, metadata, filename, document_id, ...)
+    #   <agent>.emb.f32            raw little-endian fp32 [n_chunks, dim] row-major: the packed corpus, memory-mappable
+    # Derived structures (fp16 shadow, norms, BM25 postings) are rebuilt from these on first use after `load`.
+    @_gpu_locked
+    def save(self, directory: str) -> None:
+        import json
+        d = Path(directory)
+        d.mkdir(parents=True, exist_ok=True)
+        agents = {}
+        for n, (agent_id, t) in enumerate(sorted(self._tables.items())):
+            fname = f"agent{n}.emb.f32"
+            t._emb[:len(t)].cpu().numpy().astype("<f4").tofile(d / fname)
+            agents[agent_id] = {"file": fname, "n": len(t), "records": t.records}
+        docs = {str(k): {**v, "uploaded_at": v["uploaded_at"].isoformat()} for k, v in self._documents.items()}
+        (d / "store.json").write_text(json.dumps({"version": 1, "dim": self.embedding_dim, "next_doc_id": self._next_doc_id,
+                                                  "documents": docs, "agents": agents}))
+
+    @_gpu_locked
+    def load(self, directory: str) -> None:
+        import json
+        d = Path(directory)
+        meta = json.loads((d / "store.json").read_text())
+        if meta.get("version") != 1 or meta["dim"] != self.embedding_dim:
+            raise ValueError("incompatible store directory")
+        self._tables, self._documents = {}, {}
+        self._next_doc_id = int(meta["next_doc_id"])
+        for k, v in meta["documents"].items():
+            self._documents[int(k)] = {**v, "uploaded_at": datetime.fromisoformat(v["uploaded_at"])}
+        for agent_id, a in meta["agents"].items():
+            t = self._table(agent_id)
+            emb = np.fromfile(d / a["file"], dtype="<f4").reshape(a["n"], self.embedding_dim)
+            for rec, row in zip(a["records"], emb):
+                t.append(rec, row)
+
     # ------------------------------------------------------------------ bookkeeping (rag/document_store.py:487-542)
     @_gpu_locked
     def list_documents(self, agent_id: str) -> List[Dict[str, Any]]:

@@ -254,3 +254,19 @@ def test_gpu_archival_memory_matches_oracle(store):
     assert out[0]["content"] == texts[7]
     assert mem.delete_archival_memory(8) and not mem.delete_archival_memory(8) and len(mem) == 299
     assert mem.archival_memory_search("memory number 7 about topic t7 and w2", top_k=1)[0]["id"] != 8
+
+
+def test_document_store_save_and_load_round_trip(store, tmp_path):
+    """SURVEY 8f row f2, on-disk format: a saved store reloads into identical search results (cosine + hybrid)."""
+    from optimized_rag_b200.document_store import DocumentStore
+    from optimized_rag_b200.embeddings import SyntheticEmbeddingService
+    store.save(str(tmp_path))
+    assert (tmp_path / "store.json").exists() and any(p.suffix == ".f32" for p in tmp_path.iterdir())
+    st2 = DocumentStore(None, SyntheticEmbeddingService(), WordChunker(), device="cuda:0")
+    st2.load(str(tmp_path))
+    for q in ("w3 w10 w25", "Doc5 w9"):
+        assert st2.search("agent-a", q, top_k=5) == store.search("agent-a", q, top_k=5)
+        assert st2.hybrid_search("agent-a", q, top_k=5) == store.hybrid_search("agent-a", q, top_k=5)
+    assert st2.list_documents("agent-a") == store.list_documents("agent-a")
+    r = st2.upload_and_index("agent-a", "/tmp/new.txt", file_content="w1 w2 w3 brand new text")
+    assert r["success"] and r["document_id"] == store._next_doc_id   # ids continue after a reload
