@@ -69,3 +69,53 @@ class ReciprocalRankFusion:
             fused_results.append(doc)
         logger.info(f"RRF fused {len(result_lists)} lists into {len(fused_results)} results")
         return fused_results
+
+
+class MMRDiversifier:
+    """Drop-in for `MMRDiversifier` (rag/reranker.py:104-195): Maximal Marginal Relevance over results that carry
+    an `embedding`.  All cosines of a call -- query x documents and documents x documents -- come from ONE launch of
+    the float64 cosine kernel (orag_cosine_dense, the reference's arithmetic: rag/reranker.py:196-208); the greedy
+    selection then replays the reference's loop over that matrix (first maximum wins, `mmr_score` written in place).
+    Embeddings are cast to fp32 (what the store / pgvector hold); results whose embedding is empty, non-numeric,
+    non-finite or of another dimension than the query's are filtered out like the reference filters invalid ones.
+    """
+
+    def __init__(self, lambda_param: float = 0.7, device: str | torch.device = "cuda"):
+        self.lambda_param = lambda_param
+        self.device = torch.device(device)
+
+    def diversify(self, query_embedding: List[float], results: List[Dict[str, Any]], top_k: int = 5
+                  ) -> List[Dict[str, Any]]:
+        import math
+        if not results:
+            return []
+        dim = len(query_embedding) if query_embedding else 0
+        valid = [r for r in results
+                 if r.get('embedding') and isinstance(r['embedding'], list) and len(r['embedding']) == dim
+                 and all(isinstance(v, (int, float)) and not math.isnan(v) and not math.isinf(v)
+                         for v in r['embedding'])]
+        if not valid or dim == 0:
+            logger.warning("MMR: No valid embeddings found, returning original results")
+            return results[:top_k]
+        if len(valid) < len(results):
+            logger.warning(f"MMR: Filtered {len(results) - len(valid)} results with invalid embeddings")
+        m = len(valid)
+        with _ffi.GPU_LOCK:
+            emb = torch.tensor([r['embedding'] for r in valid], dtype=torch.float32, device=self.device)
+            q = torch.tensor([query_embedding], dtype=torch.float32, device=self.device)
+            cos = engine.CosineIndex(emb, mode="exact").dense(torch.cat([q, emb]).contiguous()).cpu().tolist()
+        rel, sim = cos[0], cos[1:]          # rel[j] = cos(query, doc j); sim[i][j] = cos(doc i, doc j)
+        selected: List[int] = []
+        remaining = list(range(m))
+        while len(selected) < top_k and remaining:
+            best_j, best_score = None, None
+            for j in remaining:
+                diversity = 1 - max(sim[j][s] for s in selected) if selected else 1.0
+                score = self.lambda_param * rel[j] + (1 - self.lambda_param) * diversity
+                if best_score is None or score > best_score:   # max(): the first maximum wins
+                    best_j, best_score = j, score
+            valid[best_j]['mmr_score'] = best_score
+            selected.append(best_j)
+            remaining.remove(best_j)
+        logger.info(f"MMR diversified to {len(selected)} results")
+        return [valid[j] for j in selected]

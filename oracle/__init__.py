@@ -269,3 +269,22 @@ def hybrid_topk(corpus, queries, bm25: BM25Index, query_tokens, k: int = 10, rrf
         out.append({"cos_ids": ci, "cos_scores": cv, "bm25_ids": bi, "bm25_scores": bv, "bm25_max": m,
                     "ids": fi, "rrf_scores": fv})
     return out
+
+
+# --------------------------------------------------------------------------- MMR (rag/reranker.py:116-193)
+def mmr_select(query, embeddings, lambda_param: float, top_k: int):
+    """Indices and MMR scores picked by the reference's greedy loop (first maximum wins), cosines from `cosine`."""
+    m = len(embeddings)
+    selected, scores, remaining = [], [], list(range(m))
+    while len(selected) < top_k and remaining:
+        best = None
+        for j in remaining:
+            relevance = cosine(query, embeddings[j])
+            diversity = 1 - max(cosine(embeddings[j], embeddings[s]) for s in selected) if selected else 1.0
+            score = lambda_param * relevance + (1 - lambda_param) * diversity
+            if best is None or score > best[0]:
+                best = (score, j)
+        selected.append(best[1])
+        scores.append(best[0])
+        remaining.remove(best[1])
+    return selected, scores

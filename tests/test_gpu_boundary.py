@@ -270,3 +270,24 @@ def test_document_store_save_and_load_round_trip(store, tmp_path):
     assert st2.list_documents("agent-a") == store.list_documents("agent-a")
     r = st2.upload_and_index("agent-a", "/tmp/new.txt", file_content="w1 w2 w3 brand new text")
     assert r["success"] and r["document_id"] == store._next_doc_id   # ids continue after a reload
+
+
+def test_mmr_diversifier_matches_oracle():
+    """MMR over result embeddings, one cosine-matrix launch + the reference's greedy loop."""
+    from optimized_rag_b200.reranker import MMRDiversifier
+    rng = np.random.default_rng(22)
+    emb = rng.standard_normal((40, 96)).astype(np.float32)
+    emb[7] = emb[3]
+    emb[11] = 0.0                                       # zero vector -> cosine 0.0
+    q = rng.standard_normal(96).astype(np.float32)
+    for lam, k in ((0.7, 5), (0.25, 40), (1.0, 8)):
+        docs = [{"content": f"d{i}", "embedding": [float(x) for x in emb[i]]} for i in range(40)]
+        docs.insert(4, {"content": "bad", "embedding": [float("nan")] * 96})
+        docs.insert(9, {"content": "none"})
+        out = MMRDiversifier(lambda_param=lam, device="cuda:0").diversify([float(x) for x in q], docs, top_k=k)
+        sel, sc = oracle.mmr_select(q, emb, lam, k)
+        assert [d["content"] for d in out] == [f"d{i}" for i in sel]
+        assert [d["mmr_score"] for d in out] == sc
+    assert MMRDiversifier(device="cuda:0").diversify([1.0, 2.0], [], 3) == []
+    only_bad = [{"content": "x"}, {"content": "y", "embedding": []}]
+    assert MMRDiversifier(device="cuda:0").diversify([1.0, 2.0], only_bad, 1) == only_bad[:1]

@@ -181,3 +181,21 @@ def test_live_reference_agrees_with_oracle():
         want = h._bm25_scores(" ".join(f"w{t}" for t in q), texts)
         got, _ = ix.scores(q)
         assert got.tolist() == want
+
+
+def test_live_reference_mmr_agrees_with_oracle():
+    """Build container only: the reference's MMRDiversifier (rag/reranker.py:104-195) vs oracle.mmr_select."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    mod = ref_loader.load("reranker")
+    rng = np.random.default_rng(21)
+    emb = rng.standard_normal((14, 48)).astype(np.float32)
+    emb[5] = emb[2]                      # exact duplicate -> tie handling (first maximum wins)
+    q = rng.standard_normal(48).astype(np.float32)
+    for lam, k in ((0.7, 5), (0.3, 14), (1.0, 3)):
+        docs = [{"content": f"d{i}", "embedding": [float(x) for x in emb[i]]} for i in range(14)]
+        out = mod.MMRDiversifier(lambda_param=lam).diversify([float(x) for x in q], docs, top_k=k)
+        sel, sc = oracle.mmr_select(q, emb, lam, k)
+        assert [d["content"] for d in out] == [f"d{i}" for i in sel]
+        assert [d["mmr_score"] for d in out] == sc
