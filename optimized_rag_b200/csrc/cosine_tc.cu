@@ -87,6 +87,48 @@ __device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_m
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(cta_mask) : "memory");
 }
+// 2-SM variants: the load lands in the executing CTA's shared memory but signals the mbarrier of the pair's leader
+// (even CTA: the peer bit of the shared::cluster address is cleared)
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar,
+                                                uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"((uint64_t)(uintptr_t)map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit2_multicast(uint32_t bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
+}
+template <bool kBf16>
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    if constexpr (kBf16) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    }
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta)
+{
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(cta) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -200,21 +242,27 @@ __device__ __forceinline__ void decode_tile(const ScanParams &p, int tile, int64
     qoff = qb * kMaxN;
 }
 
-template <bool kBf16>
+// kMma2: the cta_group::2 flavour is a separate instantiation -- a kernel that contains cta_group::2 instructions can
+// only be launched as clusters of an even size
+template <bool kBf16, bool kMma2>
 __global__ void __launch_bounds__(kThreads, 1)
 cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ ScanParams p)
 {
+    // 2-SM flavour: every CTA stages only half of each query slab, so the same 192 KiB hold six stages instead of four
+    constexpr int kSt = kMma2 ? 6 : kStages;
+    constexpr int kBB = kMma2 ? kBBytes / 2 : kBBytes;
+    static_assert(kSt * (kABytes + kBB) == kStages * kStageBytes, "same shared-memory footprint");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *smem_a = smem;
-    uint8_t *smem_b = smem + kStages * kABytes;
+    uint8_t *smem_b = smem + kSt * kABytes;
     uint64_t *bars = (uint64_t *)(smem + kStages * kStageBytes);
     uint64_t *full_bar = bars;                    // [kStages]
-    uint64_t *empty_bar = bars + kStages;         // [kStages]
-    uint64_t *tmem_full = bars + 2 * kStages;     // [2]
-    uint64_t *tmem_empty = bars + 2 * kStages + 2;  // [2]
-    uint32_t *tmem_ptr = (uint32_t *)(bars + 2 * kStages + 4);
+    uint64_t *empty_bar = bars + 8;               // [kSt] (room for 8 stages)
+    uint64_t *tmem_full = bars + 16;              // [2]
+    uint64_t *tmem_empty = bars + 18;             // [2]
+    uint32_t *tmem_ptr = (uint32_t *)(bars + 20);
     float *thrv_s = (float *)(smem + kStages * kStageBytes + 256);  // [2][kMaxN]
 
     const int warp = threadIdx.x >> 5;
@@ -225,21 +273,28 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)(uintptr_t)&map_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kSt; ++s) {
             mbar_init(smem_u32(full_bar + s), 1);
-            mbar_init(smem_u32(empty_bar + s), p.cluster2 ? 2 : 1);  // cluster2: both CTAs' MMAs release a slot
+            mbar_init(smem_u32(empty_bar + s), (p.cluster2 && !p.mma2) ? 2 : 1);  // multicast pair: both MMAs release a slot
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(tmem_full + s), 1);
-            mbar_init(smem_u32(tmem_empty + s), kEpiThreads / 32);
+            mbar_init(smem_u32(tmem_empty + s), (p.mma2 ? 2 : 1) * (kEpiThreads / 32));  // mma2: both CTAs' epilogues
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                     "r"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (kMma2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                         "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                         "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     if (p.cluster2) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
@@ -268,21 +323,31 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
                     const uint32_t fb = smem_u32(full_bar + stage);
+                    if constexpr (kMma2) {
+                        // both CTAs load their own rows and their half of the query slab (same offsets in both), all
+                        // four loads complete on the LEADER's barrier
+                        if (cta_rank == 0) mbar_expect_tx(fb, 2u * (kABytes + (uint32_t)half_rows * 128u));
+                        tma_load_2d_2sm(smem_u32(smem_a + stage * kABytes), &map_a, kc * p.chunk_elems, row, fb, pol_stream);
+                        tma_load_2d_2sm(smem_u32(smem_b + stage * kBB), &map_b, kc * p.chunk_elems,
+                                        qoff + (int)cta_rank * half_rows, fb, pol_keep);
+                        if (++stage == kSt) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
                     mbar_expect_tx(fb, tx);
                     tma_load_2d(smem_u32(smem_a + stage * kABytes), &map_a, kc * p.chunk_elems, row, fb, pol_stream);
                     if (p.cluster2)
-                        tma_load_2d_multicast(smem_u32(smem_b + stage * kBBytes) + cta_rank * (uint32_t)half_rows * 128u,
+                        tma_load_2d_multicast(smem_u32(smem_b + stage * kBB) + cta_rank * (uint32_t)half_rows * 128u,
                                               &map_b, kc * p.chunk_elems, qoff + (int)cta_rank * half_rows, fb,
                                               (uint16_t)3, pol_keep);
                     else
-                        tma_load_2d(smem_u32(smem_b + stage * kBBytes), &map_b, kc * p.chunk_elems, qoff, fb, pol_keep);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                        tma_load_2d(smem_u32(smem_b + stage * kBB), &map_b, kc * p.chunk_elems, qoff, fb, pol_keep);
+                    if (++stage == kSt) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (mma2: the pair's leader only) =====================
+        if (lane == 0 && !(p.mma2 && cta_rank != 0)) {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -295,17 +360,27 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     mbar_wait(smem_u32(full_bar + stage), phase);
                     tc_fence_after();
                     const uint64_t adesc = umma_desc(smem_u32(smem_a + stage * kABytes));
-                    const uint64_t bdesc = umma_desc(smem_u32(smem_b + stage * kBBytes));
+                    const uint64_t bdesc = umma_desc(smem_u32(smem_b + stage * kBB));
+                    if constexpr (kMma2) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4)  // 4 x 32 bytes of K per 128-byte chunk
-                        tc_mma<kBf16>(d_tmem, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), p.idesc,
-                                      (uint32_t)((kc | k4) != 0));
-                    // frees the smem slot when these MMAs retire (cluster2: in both CTAs, whose producers write it)
-                    if (p.cluster2) tc_commit_multicast(smem_u32(empty_bar + stage), (uint16_t)3);
-                    else tc_commit(smem_u32(empty_bar + stage));
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            tc_mma2<kBf16>(d_tmem, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), p.idesc,
+                                           (uint32_t)((kc | k4) != 0));
+                        tc_commit2_multicast(smem_u32(empty_bar + stage), (uint16_t)3);  // both CTAs' slots
+                    } else {
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)  // 4 x 32 bytes of K per 128-byte chunk
+                            tc_mma<kBf16>(d_tmem, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), p.idesc,
+                                          (uint32_t)((kc | k4) != 0));
+                        // frees the smem slot when these MMAs retire (multicast pair: in both CTAs)
+                        if (p.cluster2) tc_commit_multicast(smem_u32(empty_bar + stage), (uint16_t)3);
+                        else tc_commit(smem_u32(empty_bar + stage));
+                    }
+                    if (++stage == kSt) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(smem_u32(tmem_full + as));  // accumulator ready for the epilogue
+                // accumulator ready for the epilogue (mma2: of both CTAs)
+                if constexpr (kMma2) tc_commit2_multicast(smem_u32(tmem_full + as), (uint16_t)3);
+                else tc_commit(smem_u32(tmem_full + as));
             }
         }
     } else if (warp >= kEpiWarp0) {
@@ -378,7 +453,10 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(tmem_empty + as));
+            if (lane == 0) {
+                if (p.mma2 && cta_rank != 0) mbar_arrive_remote(smem_u32(tmem_empty + as), 0u);  // the leader issues the MMAs
+                else mbar_arrive(smem_u32(tmem_empty + as));
+            }
         }
     }
 
@@ -387,7 +465,10 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if constexpr (kMma2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -522,6 +603,9 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
     static const int cluster_mode = getenv("ORAG_SCAN_CLUSTER") ? atoi(getenv("ORAG_SCAN_CLUSTER")) : 1;
     const int min_tiles = cluster_mode >= 2 ? 2 : 4 * sm_count();
     p.cluster2 = (cluster_mode && !p.dense && !p.pair_mode && p.umma_n >= 32 && p.num_tiles >= min_tiles) ? 1 : 0;
+    // the pairs issue one tcgen05.mma.cta_group::2 per K step unless ORAG_SCAN_2SM=0 (then: multicast pairs)
+    static const int mma2_mode = getenv("ORAG_SCAN_2SM") ? atoi(getenv("ORAG_SCAN_2SM")) : 1;
+    p.mma2 = (mma2_mode && p.cluster2) ? 1 : 0;
     rc = make_map(&map_b, q_base, bf16, p.f16 != 0, p.n_queries, dim,
                   p.pair_mode ? kMaxN : (p.cluster2 ? p.umma_n / 2 : p.umma_n));
     if (rc) return rc;
@@ -533,6 +617,7 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
         p.umma_n = kMaxN;
     }
     p.idesc = make_idesc(bf16, p.f16 != 0, p.umma_n);
+    if (p.mma2) p.idesc = (p.idesc & ~(0x1Fu << 24)) | ((uint32_t)(2 * kTileM >> 4) << 24);  // M = 256 over the pair
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     if (p.cluster2) grid &= ~1;
     if (!p.dense) profile_mark(0, 0, st);
@@ -553,7 +638,8 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
         ORAG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, p));
         return ORAG_OK;
     };
-    rc = bf16 ? launch(cosine_scan_kernel<true>) : launch(cosine_scan_kernel<false>);
+    if (p.mma2) rc = bf16 ? launch(cosine_scan_kernel<true, true>) : launch(cosine_scan_kernel<false, true>);
+    else rc = bf16 ? launch(cosine_scan_kernel<true, false>) : launch(cosine_scan_kernel<false, false>);
     if (rc) return rc;
     if (!p.dense) profile_mark(0, 1, st);
     ORAG_LAUNCH_CHECK();

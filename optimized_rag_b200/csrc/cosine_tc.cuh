@@ -44,6 +44,9 @@ struct ScanParams {
     int k;
     int fixed_thr;          // 1: thresholds are given (pairwise >= t search): no histogram, no tightening
     int pair_mode;          // 1: all-pairs search, queries = corpus rows, triangular (query block, row tile) tiles
+    int mma2;               // 1: the CTA pair issues ONE tcgen05.mma.cta_group::2 (M = 256 over both SMs): each CTA holds its
+                            //    128 rows and HALF of the query slab (six 32 KiB stages instead of four 48 KiB ones);
+                            //    default for main scans (ORAG_SCAN_2SM=0 falls back to the multicast pairs)
     int cluster2;           // 1: launched as clusters of two CTAs that share every query slab: each CTA fetches half of
                             //    it from L2 and multicasts it into both CTAs' shared memory (halves the L2 -> SM traffic
                             //    of the B operand); set by launch_scan

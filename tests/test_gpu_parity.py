@@ -554,9 +554,10 @@ def test_dense_topk_normalisation_edges(eng):
 
 
 def test_cosine_scan_cluster_pairs_forced_on_small_inputs():
-    """The main scan runs as clusters of two CTAs that multicast the query slabs to each other once a shard has
-    >= 4 tiles per SM; ORAG_SCAN_CLUSTER=2 (read once per process, hence the subprocess) forces that path on small
-    inputs: odd tile counts (one CTA of the last pair gets an all-zero tile), ragged tails, few queries."""
+    """The main scan runs as clusters of two CTAs (one cta_group::2 MMA over both SMs, or -- ORAG_SCAN_2SM=0 -- two
+    1-SM MMAs that multicast the query slabs to each other) once a shard has >= 4 tiles per SM; ORAG_SCAN_CLUSTER=2
+    (read once per process, hence the subprocess) forces that path on small inputs: odd tile counts (one CTA of the
+    last pair gets an all-zero tile), ragged tails, few queries."""
     import subprocess
     import sys
     code = r'''
@@ -572,6 +573,7 @@ for n, dim, nq in [(128 * 5 + 77, 256, 70), (128 * 301, 1536, 256), (4500, 64, 3
         assert torch.equal(want[0], got[0]) and torch.equal(want[1], got[1]), (n, dim, nq, mode)
 print("cluster ok")
 ''' % str(ROOT)
-    env = dict(os.environ, ORAG_SCAN_CLUSTER="2")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "cluster ok" in r.stdout, r.stdout + r.stderr
+    for two_sm in ("1", "0"):   # tcgen05.mma.cta_group::2 over the pair (default) / multicast pairs of 1-SM MMAs
+        env = dict(os.environ, ORAG_SCAN_CLUSTER="2", ORAG_SCAN_2SM=two_sm)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "cluster ok" in r.stdout, (two_sm, r.stdout + r.stderr)
