@@ -119,13 +119,17 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 20 ms from BEFORE the warm-up (its start-up alone takes ~0.1 s); only the samples whose
+    timestamps fall inside the timed regions count (`window(t0, t1)` marks them), so that a 30 ms multi-GPU run still
+    gets its clocks and idle set-up time never dilutes them."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, uuid: str):
         self.uuid = uuid
         self.proc = None
+        self.windows = []
         self.path = ROOT / "gpurun_out" / f"clocks_{os.getpid()}.csv"
 
     def start(self):
@@ -133,36 +137,46 @@ class ClockSampler:
             self.path.parent.mkdir(exist_ok=True)
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", self.uuid, f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
     def stop(self):
+        import datetime as dt
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if not self.proc:
             return out
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         self.fh.close()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for ln in self.path.read_text().splitlines():
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = dt.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if any(a <= r[0] <= b for a, b in self.windows)]
+        note = "inside the timed regions"
+        if not inside and rows and self.windows:  # run shorter than the polling period: nearest samples under the same load
+            a, b = min(w[0] for w in self.windows), max(w[1] for w in self.windows)
+            inside = [r for r in rows if a - 0.25 <= r[0] <= b + 0.25]
+            note = "nearest to the timed regions (+-0.25 s, same workload: warm-up / e2e loop)"
+        if inside:
+            out.update(sm_mhz=statistics.median(r[1] for r in inside), sm_max_mhz=max(r[2] for r in inside),
+                       reasons=sorted({n for r in inside for n in r[3]}), samples=len(inside), window=note)
         return out
 
 
@@ -232,21 +246,22 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler is already running: see ClockSampler)
+    uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+    sampler.start()
     res = None
     for _ in range(max(args.warmup, 3)):
         res = sh.search(q_emb, q_tok, q_len, k)
     barrier()
 
     # ---- timed: inputs resident in HBM
-    uuid = str(torch.cuda.get_device_properties(dev).uuid)
-    sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
     L.orag_profile_enable(1)
     scan_ms, bm_ms = [], []
     launches0 = int(L.orag_launch_count())
-    sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
     ev0.record()
     import ctypes
     a, b = ctypes.c_float(), ctypes.c_float()
@@ -258,6 +273,7 @@ def run_native(args):
         flags.append(res["status"])
     ev1.record()
     barrier()
+    sampler.window(w0, time.time())
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = int(L.orag_launch_count()) - launches0
     if bool(torch.stack(flags).any()):
@@ -269,6 +285,7 @@ def run_native(args):
     # ---- timed: end to end through the public call with HOST buffers
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
     e0.record()
     status_h = torch.empty(Bq, dtype=torch.int32).pin_memory()
     for _ in range(args.steps):
@@ -285,6 +302,7 @@ def run_native(args):
             out_ids_h.copy_(r["ids"]); out_sc_h.copy_(r["rrf_scores"])
     e1.record()
     barrier()
+    sampler.window(w0, time.time())
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
 
