@@ -1,11 +1,19 @@
 // cosine_tc.cu -- tcgen05 / TMA / TMEM similarity scan with fused threshold top-k candidate emission.
 //
 // One persistent CTA per SM.  D[128 rows x N queries] += A[128 x K] * B[N x K]^T with
-//   A = corpus tile  (fp32 straight from HBM, kind::tf32  -- or bf16 shadow copy, kind::f16)
+//   A = corpus tile  (fp32 straight from HBM, kind::tf32  -- or fp16 / bf16 shadow copy, kind::f16)
 //   B = query block  (L2-resident, re-streamed per tile)
 // streamed K-chunk by K-chunk (128 bytes of K per stage = one SWIZZLE_128B row) through a
-// 4-stage TMA->smem ring; accumulators live in TMEM (2 stages x 256 columns) so the epilogue of
+// TMA->smem ring; accumulators live in TMEM (2 stages x 256 columns) so the epilogue of
 // tile i overlaps the MMAs of tile i+1.
+//
+// Three flavours of the same kernel (launch_scan picks):
+//   <.., kMma2 = true>  main scans: clusters of two CTAs on adjacent row tiles, ONE tcgen05.mma.cta_group::2
+//                       (M = 256 over both SMs) per K step issued by the pair's leader; every CTA loads its rows
+//                       and half of the query slab (cta_group::2 TMA, completing on the leader's mbarrier);
+//                       six 32 KiB stages
+//   cluster2 (runtime)  pairs of 1-SM MMAs, each CTA multicasts half of the query slab to both (ORAG_SCAN_2SM=0)
+//   plain               one CTA per tile, four 48 KiB stages: seed / dense passes, small inputs, pair mode
 //
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
 // warp 2 = TMEM allocator, warp 3 idle, warps 4-11 = epilogue (two warps per TMEM lane quarter,
