@@ -119,7 +119,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi polled every 20 ms from BEFORE the warm-up (its start-up alone takes ~0.1 s); only the samples whose
+    """nvidia-smi polled every 25 ms (rank 0 only) from BEFORE the warm-up (its start-up alone takes ~0.1 s); only the samples whose
     timestamps fall inside the timed regions count (`window(t0, t1)` marks them), so that a 30 ms multi-GPU run still
     gets its clocks and idle set-up time never dilutes them."""
     FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -137,7 +137,7 @@ class ClockSampler:
             self.path.parent.mkdir(exist_ok=True)
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", self.uuid, f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.fh,
+                                          "--format=csv,noheader,nounits", "-lms", "25"], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -249,7 +249,8 @@ def run_native(args):
     # ---- warm-up (the clock sampler is already running: see ClockSampler)
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
     sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
-    sampler.start()
+    if rank == 0:  # one poller per box: nvidia-smi queries take driver locks that kernel launches also need
+        sampler.start()
     res = None
     for _ in range(max(args.warmup, 3)):
         res = sh.search(q_emb, q_tok, q_len, k)
