@@ -120,7 +120,8 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """nvidia-smi polled every 25 ms (rank 0 only) from BEFORE the warm-up (its start-up alone takes ~0.1 s); only the samples whose
-    timestamps fall inside the timed regions count (`window(t0, t1)` marks them), so that a 30 ms multi-GPU run still
+    timestamps fall inside the device-timed loop count (`window(t0, t1)` marks it; the GPU is continuously busy there,
+    whereas the end-to-end loop idles between steps and would show ramped-down clocks), so that a 30 ms multi-GPU run still
     gets its clocks and idle set-up time never dilutes them."""
     FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -286,7 +287,6 @@ def run_native(args):
     # ---- timed: end to end through the public call with HOST buffers
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0 = time.time()
     e0.record()
     status_h = torch.empty(Bq, dtype=torch.int32).pin_memory()
     for _ in range(args.steps):
@@ -303,7 +303,6 @@ def run_native(args):
             out_ids_h.copy_(r["ids"]); out_sc_h.copy_(r["rrf_scores"])
     e1.record()
     barrier()
-    sampler.window(w0, time.time())
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
 
