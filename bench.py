@@ -275,9 +275,21 @@ def run_native(args):
         flags.append(res["status"])
     ev1.record()
     barrier()
-    sampler.window(w0, time.time())
+    w1 = time.time()
+    sampler.window(w0, w1)
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = int(L.orag_launch_count()) - launches0
+    if dev_ms < 150.0:
+        # the timed loop is shorter than a few polling periods (small shards): keep the same back-to-back load running,
+        # untimed, for ~0.2 s so that the poller sees it.  The step count derives from dev_ms, which is identical on
+        # every rank (max over ranks), so all ranks enter the same number of collectives.
+        n_probe = int(200.0 / max(dev_ms / args.steps, 1e-3)) + 1
+        p0 = time.time()
+        for _ in range(n_probe):
+            sh.search(q_emb, q_tok, q_len, k, check_overflow=False)
+        torch.cuda.synchronize()
+        sampler.window(p0, time.time())
+        barrier()
     if bool(torch.stack(flags).any()):
         raise SystemExit("bench: a candidate buffer overflowed inside the timed region; results would need the repair path")
     L.orag_profile_read(ctypes.byref(a), ctypes.byref(b))  # brackets of the last step's scan / BM25 first-pass kernels
