@@ -124,3 +124,58 @@ def test_sharded_stats_merge_equals_global(built_lib):
     assert np.array_equal(a[0].view(np.uint64), orc.idf.view(np.uint64))
     order = np.argsort(whole.first_seen[whole.df > 0], kind="stable")
     assert np.array_equal(np.nonzero(whole.df > 0)[0][order], orc.first_seen)
+
+
+@pytest.mark.parametrize("n,vocab,lmin,lmax,tile,fp_tile", [(700, 300, 3, 40, 64, 256), (90, 40, 1, 9, 32, 32),
+                                                            (1500, 2000, 20, 60, 128, None)])
+def test_first_pass_view_is_a_rounded_copy_of_the_exact_view(built_lib, n, vocab, lmin, lmax, tile, fp_tile):
+    """The MaxScore first-pass view (csrc/bm25_ms.cu) must hold, for exactly the postings of the exact view,
+    fp16(r) with r = tf*(k1+1)/(tf + t4[dl]) in float64, and term_max_r must bound every r16 of its term: the
+    superset guarantee of the first pass rests on |r16 - r| <= 2^-11 r and on those upper bounds."""
+    from optimized_rag_b200.bm25_index import Bm25Index
+    thr = syn.zipf_thresholds(vocab)
+    doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, lmin, lmax, thr)
+    ix = Bm25Index(torch.from_numpy(doc_off), torch.from_numpy(tok), vocab, tile_docs=tile, fp_tile_docs=fp_tile)
+    assert ix.postings_r16 is not None and not ix.has_negative_idf
+    T, F = ix.tile_docs, ix.fp_tile_docs
+    if fp_tile is None:
+        assert F == min(4096, max(32, 1 << ((n // 16 - 1).bit_length())))
+
+    def decode(post, base, off, tile_docs, n_tiles):
+        post = post.numpy().view(np.uint32)
+        base, off = base.numpy(), off.numpy()
+        out = {}
+        for tl in range(n_tiles):
+            for t in range(vocab):
+                p = post[base[tl] + off[tl, t]:base[tl] + off[tl, t + 1]]
+                d = tl * tile_docs + (p >> 16).astype(np.int64)
+                assert (np.diff(d) > 0).all()  # doc-sorted runs: the kernels binary-search and merge them
+                for di, lo in zip(d.tolist(), (p & 0xFFFF).tolist()):
+                    out[(t, di)] = lo
+        return out
+
+    exact = decode(ix.postings, ix.tile_base, ix.tile_term_off, T, ix.n_tiles)
+    first = decode(ix.postings_r16, ix.fp_tile_base, ix.fp_tile_term_off, F, ix.fp_n_tiles)
+    assert exact.keys() == first.keys() and len(exact) == ix.n_postings
+    t4 = ix.t4_table.numpy()
+    dl = ix.dl.numpy()
+    tmax = np.zeros(vocab, dtype=np.float32)
+    for (t, d), tf in exact.items():
+        r = tf * 2.5 / (tf + t4[dl[d]])
+        r16 = np.float16(np.float32(r))
+        assert first[(t, d)] == int(r16.view(np.uint16)), (t, d)
+        assert abs(float(r16) - r) <= r * 2.0 ** -11 and float(r16) >= 6.2e-5
+        tmax[t] = max(tmax[t], np.float32(r16))
+    assert np.array_equal(ix.term_max_r.numpy(), tmax)
+
+
+def test_first_pass_view_is_dropped_when_idf_goes_negative(built_lib):
+    """When the final idf table keeps a negative entry (common terms whose replacement eps*average_idf is itself
+    negative, rank_bm25's behaviour), pruning by upper bounds is unsound: the index must not build the first-pass
+    view, and the exact tile kernel serves every query."""
+    from optimized_rag_b200.bm25_index import Bm25Index
+    doc_off = np.arange(0, 4 * 40 + 1, 4, dtype=np.int64)
+    tok = np.tile(np.array([0, 1, 2, 3], dtype=np.int32), 40)
+    tok[3::8] = 5
+    ix = Bm25Index(torch.from_numpy(doc_off), torch.from_numpy(tok), 8, tile_docs=32)
+    assert ix.has_negative_idf and ix.postings_r16 is None and ix.struct.d_postings_r16 is None
