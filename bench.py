@@ -383,6 +383,8 @@ def run_native(args):
                                                            "with proven error margins, then exact re-score",
                                              "rows_per_gpu": n_local,
                                              "parallelism": f"row-sharded x{world}", "setup_s": round(t_setup, 1),
+                                             "exchange": ("none (one shard)" if world == 1 else
+                                                          sh.exchange + (f" ({sh.exchange_note})" if sh.exchange_note else "")),
                                              "bm25_postings_local": bm25.n_postings}),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},

@@ -13,8 +13,8 @@
  *   - every function returns 0 on success, a negative ORAG_E* code on failure;
  *     orag_last_error() returns a thread-local message for the last failure.
  *   - all pointers named d_* are DEVICE pointers (sm_100a, current device);
- *     the library never allocates device memory: callers pass every buffer,
- *     including a workspace whose size they query first.
+ *     the library never allocates device memory (sole exception: orag_exchange_alloc):
+ *     callers pass every buffer, including a workspace whose size they query first.
  *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work
  *     (no hidden synchronisation) unless stated otherwise.
  *   - ids are int64 global chunk ids = row_id_base + local row; missing
@@ -23,6 +23,13 @@
  *     (Python's stable sorted(reverse=True) over index-ordered input,
  *     rag/retrieval.py:320), except RRF, whose tie rule is the reference's
  *     dict-insertion order (rag/reranker.py:250-261).
+ *   - concurrency: entry points may be called from any thread, but calls that
+ *     target the same device must not overlap in time (the library keeps one
+ *     auxiliary stream, its fork/join events and the profiling events per
+ *     process; a workspace belongs to the call that was handed it until the
+ *     work enqueued by that call has finished).  One process per GPU, calls
+ *     serialised by the host wrapper (optimized_rag_b200._ffi.GPU_LOCK), is
+ *     the supported arrangement; different processes never share state.
  */
 #ifndef ORAG_H
 #define ORAG_H
@@ -52,6 +59,7 @@ extern "C" {
 #define ORAG_STATUS_OK 0
 #define ORAG_STATUS_OVERFLOW 1 /* candidate buffer overflowed: result for this query is NOT valid,
                                   caller must re-run the query with ORAG_COS_EXACT / dense BM25 */
+#define ORAG_STATUS_EXCHANGE_TIMEOUT 2 /* sharded search: a peer's block did not arrive in time (orag_hybrid_wait) */
 
 int orag_version(void);
 const char *orag_last_error(void);
@@ -238,6 +246,39 @@ int orag_hybrid_merge(const int64_t *d_gathered, int n_shards, int n_queries, in
                       int top_k, int tie_mode, int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_src,
                       int64_t *d_cos_ids, double *d_cos_scores, int64_t *d_bm25_ids, double *d_bm25_scores,
                       double *d_bm25_max, int32_t *d_out_status, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Peer-memory exchange for the row-sharded search (one process per GPU, NVLink / NVSwitch): replaces
+ * "pack + all-gather" in front of orag_hybrid_merge.  The reference has no counterpart (single Postgres);
+ * the data exchanged is the merge input described above.
+ *   setup, once per (n_shards, max_queries, fetch_k, kk):
+ *     orag_exchange_bytes -> orag_exchange_alloc (cudaMalloc + zero fill: the ONE place the library allocates
+ *     device memory, because an IPC handle names a whole allocation) -> orag_exchange_export (64-byte handle,
+ *     sent to the peers by any host channel) -> orag_exchange_open on every peer's handle -> a DEVICE array
+ *     d_peer_bufs[n_shards] of the buffers in rank order (own buffer at index rank) -> host barrier.
+ *   per search, with the same seq = 1, 2, 3, ... on every rank:
+ *     orag_hybrid_push: one launch packs this rank's lists (same arrays / layout as the gathered buffer of
+ *       orag_hybrid_merge: d_cos_* [n_queries, fetch_k], d_bm25_* [n_queries, kk] RAW scores, d_bm25_max
+ *       [n_queries], d_status [n_queries] or NULL) and stores them into slot seq&1 of EVERY peer, then publishes
+ *       seq with a system-scope release store.
+ *     orag_hybrid_wait: one tiny launch that acquires the n_shards sequence numbers in this rank's own buffer;
+ *       *d_gathered (host out) is the [n_shards, n_queries, W] array to hand to orag_hybrid_merge on the same
+ *       stream.  A block that has not arrived after timeout_ms gets ORAG_STATUS_EXCHANGE_TIMEOUT in its status
+ *       words (the merge ORs them into d_out_status) instead of hanging the GPU.
+ *   Every rank must call push and wait for every seq, in order, with the same n_queries / fetch_k / kk.
+ * ------------------------------------------------------------------------- */
+size_t orag_exchange_bytes(int n_shards, int max_queries, int fetch_k, int kk);
+int orag_exchange_alloc(size_t bytes, void **d_buf);
+int orag_exchange_free(void *d_buf);
+int orag_exchange_export(void *d_buf, unsigned char handle[64]);
+int orag_exchange_open(const unsigned char handle[64], void **d_peer_buf);
+int orag_exchange_close(void *d_peer_buf);
+int orag_hybrid_push(const int64_t *d_cos_ids, const double *d_cos_scores, const int64_t *d_bm25_ids,
+                     const double *d_bm25_scores, const double *d_bm25_max, const int32_t *d_status, int n_queries,
+                     int fetch_k, int kk, int rank, int n_shards, int max_queries, void *const *d_peer_bufs,
+                     uint64_t seq, void *stream);
+int orag_hybrid_wait(void *d_buf, int n_shards, int max_queries, int n_queries, int fetch_k, int kk, uint64_t seq,
+                     int timeout_ms, const int64_t **d_gathered, void *stream);
 
 /* Weighted hybrid score of HybridRetriever.hybrid_search (rag/retrieval.py:302):
  * out[i] = (alpha*sem[i] + beta*kw[i]) + gamma*temp[i] in float64 without contraction

@@ -12,6 +12,7 @@ LIB_PATH = Path(__file__).resolve().parent / "csrc" / "liborag.so"
 
 ORAG_COS_EXACT, ORAG_COS_TF32, ORAG_COS_BF16, ORAG_COS_F16 = 0, 1, 2, 3
 ORAG_STATUS_OVERFLOW = 1
+ORAG_STATUS_EXCHANGE_TIMEOUT = 2
 ORAG_BM25_NORMALIZE, ORAG_BM25_FORCE_SPARSE, ORAG_BM25_FORCE_DENSE, ORAG_BM25_EXACT_TILES = 1, 2, 4, 8
 ORAG_BM25_BACKGROUND = 16
 
@@ -27,6 +28,8 @@ SYMBOLS = [
     "orag_topk_merge", "orag_rrf_fuse", "orag_hybrid_merge", "orag_weighted_sum3", "orag_div_scalar",
     "orag_pairwise_workspace_bytes", "orag_pairwise_cosine_threshold",
     "orag_pairwise_tc_workspace_bytes", "orag_pairwise_cosine_threshold_tc",
+    "orag_exchange_bytes", "orag_exchange_alloc", "orag_exchange_free", "orag_exchange_export", "orag_exchange_open",
+    "orag_exchange_close", "orag_hybrid_push", "orag_hybrid_wait",
 ]
 
 
@@ -118,10 +121,19 @@ def lib() -> ctypes.CDLL:
     L.orag_pairwise_tc_workspace_bytes.restype = c_size_t
     L.orag_pairwise_tc_workspace_bytes.argtypes = [c_int64, c_int]
     L.orag_pairwise_cosine_threshold_tc.argtypes = L.orag_pairwise_cosine_threshold.argtypes
+    L.orag_exchange_bytes.restype = c_size_t
+    L.orag_exchange_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    L.orag_exchange_alloc.argtypes = [c_size_t, POINTER(c_void_p)]
+    L.orag_exchange_free.argtypes = [vp]
+    L.orag_exchange_export.argtypes = [vp, ctypes.c_char_p]
+    L.orag_exchange_open.argtypes = [ctypes.c_char_p, POINTER(c_void_p)]
+    L.orag_exchange_close.argtypes = [vp]
+    L.orag_hybrid_push.argtypes = [vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp, c_uint64, vp]
+    L.orag_hybrid_wait.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_uint64, c_int, POINTER(c_void_p), vp]
     for name in SYMBOLS:
         f = getattr(L, name)
         if name not in ("orag_last_error", "orag_launch_count", "orag_cosine_workspace_bytes", "orag_bm25_workspace_bytes",
-                        "orag_pairwise_workspace_bytes", "orag_pairwise_tc_workspace_bytes"):
+                        "orag_pairwise_workspace_bytes", "orag_pairwise_tc_workspace_bytes", "orag_exchange_bytes"):
             f.restype = c_int
     _lib = L
     return L

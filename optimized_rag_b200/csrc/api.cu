@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "cosine_tc.cuh"
 #include "exact.cuh"
@@ -20,12 +22,12 @@ void set_error(const char *fmt, ...)
 }
 
 // ---- profiling hooks ------------------------------------------------------------------------------
-static unsigned long long g_launches = 0;
+static std::atomic<unsigned long long> g_launches{0};
 static int g_profile = 0;
 static cudaEvent_t g_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
 static int g_ev_used[2] = {0, 0};
 
-void count_launch() { ++g_launches; }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void profile_mark(int slot, int end, cudaStream_t st)
 {
@@ -57,6 +59,8 @@ constexpr int kMaxDevices = 64;
 struct AuxStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t prescan = nullptr;  // co-scheduling hook (orag_cosine_mark_prescan)
+    bool prescan_recorded = false;
 };
 static AuxStream g_aux[kMaxDevices];
 
@@ -70,6 +74,7 @@ static int aux_for_current_device(AuxStream **out)
         ORAG_CUDA_CHECK(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
         ORAG_CUDA_CHECK(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
         ORAG_CUDA_CHECK(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+        ORAG_CUDA_CHECK(cudaEventCreateWithFlags(&a.prescan, cudaEventDisableTiming));
     }
     *out = &a;
     return ORAG_OK;
@@ -84,7 +89,6 @@ __global__ void unscale_columns_kernel(float *out, int64_t n, const float *scale
 
 // ---- co-scheduling hook ---------------------------------------------------------------------------
 static int g_mark_prescan = 0;
-static cudaEvent_t g_prescan_ev = nullptr;
 
 // First-pass error bounds in cosine units (DESIGN.md "exactness of the first pass"):
 //   tf32: operands truncated to 10 mantissa bits -> |rel err per product| < 2^-9 + 2^-20
@@ -161,7 +165,7 @@ using namespace orag;
 extern "C" int orag_version(void) { return 1; }
 extern "C" const char *orag_last_error(void) { return orag::g_err; }
 
-extern "C" unsigned long long orag_launch_count(void) { return orag::g_launches; }
+extern "C" unsigned long long orag_launch_count(void) { return orag::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int orag_profile_enable(int on)
 {
@@ -335,8 +339,12 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
         if (rc) return rc;
         // main scan over the rest of the shard (co-scheduling hook: see orag_cosine_mark_prescan)
         if (g_mark_prescan) {
-            if (!g_prescan_ev) ORAG_CUDA_CHECK(cudaEventCreateWithFlags(&g_prescan_ev, cudaEventDisableTiming));
-            ORAG_CUDA_CHECK(cudaEventRecord(g_prescan_ev, st));
+            if (!aux) {
+                rc = aux_for_current_device(&aux);
+                if (rc) return rc;
+            }
+            ORAG_CUDA_CHECK(cudaEventRecord(aux->prescan, st));
+            aux->prescan_recorded = true;
         }
         p.row_begin = n_seed;
         p.row_end = n_rows;
@@ -419,7 +427,10 @@ extern "C" int orag_cosine_mark_prescan(int enable)
 
 extern "C" int orag_stream_wait_prescan(void *stream)
 {
-    if (!orag::g_prescan_ev) return ORAG_OK;  // nothing recorded yet: nothing to wait for
-    ORAG_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, orag::g_prescan_ev, 0));
+    orag::AuxStream *aux = nullptr;
+    int rc = orag::aux_for_current_device(&aux);
+    if (rc) return rc;
+    if (!aux->prescan_recorded) return ORAG_OK;  // nothing recorded yet on this device: nothing to wait for
+    ORAG_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, aux->prescan, 0));
     return ORAG_OK;
 }

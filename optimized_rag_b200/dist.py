@@ -6,11 +6,18 @@ docs.  Queries are replicated.  Per batch the only exchange is ONE all-gather of
 local winners (cosine top-k, BM25 raw top-(k+guard) and the shard's max raw BM25 score), packed
 into a single int64 buffer (~B * (4k + 2*guard + 1) * 8 bytes per rank, tens of KB: latency-bound);
 every rank then runs the G*k -> k merges and RRF itself, so all ranks hold the result.
+Two transports for that exchange: NCCL (`pack_local` + `all_gather_into_tensor`) and `PeerExchange`
+(csrc/exchange.cu): one kernel packs the winners and stores them straight into every peer's buffer over
+NVLink, one tiny kernel waits for the peers' sequence numbers -- no packing kernels, no collective call.
 
 BM25 statistics (N, avgdl, df, first-seen order -> idf, eps) are GLOBAL: `sharded_stats` all-reduces
 them once at index build so that sharded results equal the single-GPU / oracle results bit for bit.
 """
 from __future__ import annotations
+
+import ctypes
+import logging
+import os
 
 import numpy as np
 import torch
@@ -18,6 +25,8 @@ import torch.distributed as dist
 
 from . import _ffi, engine
 from .bm25_index import Bm25Stats, local_stats
+
+logger = logging.getLogger(__name__)
 
 BM25_GUARD = 6  # extra raw-score entries per shard: distinct raw scores that collapse to one normalised double
 
@@ -75,18 +84,22 @@ def unpack_gathered(buf: torch.Tensor, fetch_k: int, kk: int):
     return ci, cs, bi, bs, bm, st
 
 
-def hybrid_merge(gathered: torch.Tensor, fetch_k: int, kk: int, rrf_k: int, k: int):
-    """gathered int64 [G, B, W] -> the result dict of a hybrid search (one launch: csrc/rrf.cu
-    hybrid_merge_kernel) plus the OR of the shards' overflow flags."""
-    G, Bq, W = gathered.shape
-    assert W == 2 * fetch_k + 2 * kk + 2 and gathered.is_contiguous()
-    dev = gathered.device
+def hybrid_merge(gathered, fetch_k: int, kk: int, rrf_k: int, k: int, shape=None, device=None):
+    """gathered int64 [G, B, W] (a tensor, or a raw device pointer with `shape` and `device`) -> the result dict
+    of a hybrid search (one launch: csrc/rrf.cu hybrid_merge_kernel) plus the OR of the shards' status flags."""
+    if isinstance(gathered, torch.Tensor):
+        G, Bq, W = gathered.shape
+        assert gathered.is_contiguous()
+        dev, ptr = gathered.device, gathered.data_ptr()
+    else:
+        (G, Bq, W), dev, ptr = shape, device, int(gathered)
+    assert W == 2 * fetch_k + 2 * kk + 2
     i64 = lambda *shape: torch.empty(shape, dtype=torch.int64, device=dev)
     f64 = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)
     fi, fs, src = i64(Bq, k), f64(Bq, k), torch.empty((Bq, k, 2), dtype=torch.int32, device=dev)
     ci, cs, bi, bs, bmax = i64(Bq, fetch_k), f64(Bq, fetch_k), i64(Bq, fetch_k), f64(Bq, fetch_k), f64(Bq)
     status = torch.empty(Bq, dtype=torch.int32, device=dev)
-    _ffi.check(_ffi.lib().orag_hybrid_merge(gathered.data_ptr(), G, Bq, fetch_k, kk, rrf_k, k, 0, fi.data_ptr(),
+    _ffi.check(_ffi.lib().orag_hybrid_merge(ptr, G, Bq, fetch_k, kk, rrf_k, k, 0, fi.data_ptr(),
                                             fs.data_ptr(), src.data_ptr(), ci.data_ptr(), cs.data_ptr(), bi.data_ptr(),
                                             bs.data_ptr(), bmax.data_ptr(), status.data_ptr(),
                                             torch.cuda.current_stream(dev).cuda_stream), "orag_hybrid_merge")
@@ -94,17 +107,138 @@ def hybrid_merge(gathered: torch.Tensor, fetch_k: int, kk: int, rrf_k: int, k: i
             "bm25_scores": bs, "bm25_max": bmax}, status
 
 
-class ShardedHybrid:
-    """Hybrid (cosine + BM25 -> RRF) search over a corpus row-sharded across the ranks of `group`."""
+class PeerExchange:
+    """Exchange buffers of all ranks of `group`, mapped into this process through CUDA IPC (csrc/exchange.cu).
 
-    def __init__(self, shard: engine.HybridShard, group=None):
+    Collective constructor (every rank, same arguments).  The 64-byte IPC handles travel through
+    `all_gather_object` once; after that an exchange is two kernel launches and no host communication.
+    Every rank must call `exchange` the same number of times with the same shapes."""
+
+    TIMEOUT_MS = int(os.environ.get("ORAG_EXCHANGE_TIMEOUT_MS", "30000"))
+
+    def __init__(self, device: torch.device, max_queries: int, fetch_k: int, kk: int, group=None):
+        L = _ffi.lib()
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.max_queries, self.fetch_k, self.kk = int(max_queries), int(fetch_k), int(kk)
+        self.W = 2 * fetch_k + 2 * kk + 2
+        self.bytes = int(L.orag_exchange_bytes(self.world, self.max_queries, fetch_k, kk))
+        self._mine, self._opened, self.seq = None, [], 0
+        error = None
+        with torch.cuda.device(self.device):
+            handle = ctypes.create_string_buffer(64)
+            try:
+                mine = ctypes.c_void_p()
+                _ffi.check(L.orag_exchange_alloc(self.bytes, ctypes.byref(mine)), "orag_exchange_alloc")
+                self._mine = mine.value
+                _ffi.check(L.orag_exchange_export(self._mine, handle), "orag_exchange_export")
+            except _ffi.OragError as e:
+                error = e
+            handles = [None] * self.world
+            dist.all_gather_object(handles, None if error else handle.raw, group=group)
+            ptrs = []
+            if error is None and all(h is not None for h in handles):
+                try:
+                    for r, h in enumerate(handles):
+                        if r == self.rank:
+                            ptrs.append(self._mine)
+                            continue
+                        p = ctypes.c_void_p()
+                        _ffi.check(L.orag_exchange_open(h, ctypes.byref(p)), "orag_exchange_open")
+                        self._opened.append(p.value)
+                        ptrs.append(p.value)
+                except _ffi.OragError as e:
+                    error = e
+            torch.cuda.synchronize(self.device)
+            # agreement + barrier in one collective: every buffer is zeroed and mapped everywhere before the first
+            # push, or every rank gives up together
+            on_dev = dist.get_backend(group) == "nccl"
+            ok = torch.tensor([0 if (error or len(ptrs) != self.world) else 1], dtype=torch.int32,
+                              device=self.device if on_dev else "cpu")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                for p in self._opened:
+                    L.orag_exchange_close(p)
+                dist.barrier(group=group)
+                if self._mine is not None:
+                    L.orag_exchange_free(self._mine)
+                self._mine, self._opened = None, []
+                raise _ffi.OragError(f"peer exchange setup failed on at least one rank (this rank: {error or 'ok'})")
+        self.peer_ptrs = ptrs
+        self._d_peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+
+    def fits(self, n_queries: int, fetch_k: int, kk: int) -> bool:
+        return n_queries <= self.max_queries and fetch_k == self.fetch_k and kk == self.kk
+
+    def exchange(self, cos_ids, cos_scores, bm_ids, bm_scores, bm_max, status):
+        """Push this rank's lists to every peer, wait for theirs -> (device pointer of [G, B, W], shape)."""
+        L = _ffi.lib()
+        Bq = cos_ids.shape[0]
+        assert self.fits(Bq, cos_ids.shape[1], bm_ids.shape[1])
+        for t in (cos_ids, cos_scores, bm_ids, bm_scores, bm_max, status):
+            assert t.is_contiguous() and t.device == self.device
+        assert status.dtype == torch.int32 and bm_max.dtype == torch.float64
+        self.seq += 1
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _ffi.check(L.orag_hybrid_push(cos_ids.data_ptr(), cos_scores.data_ptr(), bm_ids.data_ptr(), bm_scores.data_ptr(),
+                                      bm_max.data_ptr(), status.data_ptr(), Bq, self.fetch_k, self.kk, self.rank,
+                                      self.world, self.max_queries, self._d_peers.data_ptr(), self.seq, st),
+                   "orag_hybrid_push")
+        out = ctypes.c_void_p()
+        _ffi.check(L.orag_hybrid_wait(self._mine, self.world, self.max_queries, Bq, self.fetch_k, self.kk, self.seq,
+                                      self.TIMEOUT_MS, ctypes.byref(out), st), "orag_hybrid_wait")
+        return out.value, (self.world, Bq, self.W)
+
+    def close(self):
+        """Collective: unmap the peers' buffers, then free the own one (after everybody has unmapped it)."""
+        if self._mine is None:
+            return
+        L = _ffi.lib()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                _ffi.check(L.orag_exchange_close(p), "orag_exchange_close")
+            dist.barrier(group=self.group)
+            _ffi.check(L.orag_exchange_free(self._mine), "orag_exchange_free")
+        self._mine, self._opened = None, []
+
+
+class ShardedHybrid:
+    """Hybrid (cosine + BM25 -> RRF) search over a corpus row-sharded across the ranks of `group`.
+    `exchange`: "peer" (PeerExchange: pack + NVLink peer stores in one kernel) or "nccl" (pack + all-gather);
+    default from ORAG_EXCHANGE, else "peer".  If the peer buffers cannot be set up (no CUDA IPC / peer access between
+    the ranks' devices) ALL ranks switch to "nccl" together and say so in `exchange_note` -- both feed the same merge
+    kernel with the same bytes."""
+
+    def __init__(self, shard: engine.HybridShard, group=None, exchange: str | None = None):
         self.shard = shard
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.exchange = exchange or os.environ.get("ORAG_EXCHANGE", "peer")
+        assert self.exchange in ("nccl", "peer")
+        self.exchange_note = ""
         self._gather_buf = None
+        self._peer: PeerExchange | None = None
 
-    def _exchange(self, mine: torch.Tensor, fetch_k: int, kk: int, k: int):
+    def _exchange(self, lists, fetch_k: int, kk: int, k: int):
+        ci, cs, bi, bs, bm, st = lists
+        if self.exchange == "peer":
+            Bq = ci.shape[0]
+            if self._peer is None or not self._peer.fits(Bq, fetch_k, kk):
+                # collective (every rank sees the same shapes); an outgrown exchange stays mapped until close()
+                try:
+                    self._peer = PeerExchange(ci.device, max(Bq, 256), fetch_k, kk, group=self.group)
+                except _ffi.OragError as e:  # raised on every rank together (see PeerExchange.__init__)
+                    logger.warning("peer exchange unavailable, using the NCCL all-gather: %s", e)
+                    self.exchange, self.exchange_note = "nccl", f"peer setup failed: {e}"
+        if self.exchange == "peer":
+            ptr, shape = self._peer.exchange(ci, cs, bi, bs, bm, st)
+            return hybrid_merge(ptr, fetch_k, kk, self.shard.rrf_k, k, shape=shape, device=ci.device)
+        mine = pack_local(ci, cs, bi, bs, bm, st)
         Bq, W = mine.shape
         if self._gather_buf is None or self._gather_buf.shape != (self.world, Bq, W):
             self._gather_buf = torch.empty((self.world, Bq, W), dtype=torch.int64, device=mine.device)
@@ -122,16 +256,18 @@ class ShardedHybrid:
             return self.shard.search(query_emb, query_terms, query_lens, k, fetch_k, check_overflow)
         kk = fetch_k + BM25_GUARD
         ci, cs, bi, bs, bm, st = self.shard.local_lists(query_emb, query_terms, query_lens, fetch_k, kk, False)
-        out, status = self._exchange(pack_local(ci, cs, bi, bs, bm, st), fetch_k, kk, k)
+        out, status = self._exchange((ci, cs, bi, bs, bm, st), fetch_k, kk, k)
         out["status"] = status  # check_overflow=False: no host sync at all; the caller checks it with the results
         if check_overflow and bool(status.any()):
+            if bool((status & _ffi.ORAG_STATUS_EXCHANGE_TIMEOUT).any()):
+                raise _ffi.OragError("sharded search: a peer's block did not arrive within the exchange timeout")
             bad = torch.nonzero(status).flatten()
             lists = self.shard.exact_lists(query_emb[bad].contiguous(), query_terms[bad].contiguous(),
                                            query_lens[bad].contiguous(), fetch_k, kk, False)
             zero = torch.zeros(bad.numel(), dtype=torch.int32, device=bad.device)
             buf = self._gather_buf
             self._gather_buf = None
-            fixed, _ = self._exchange(pack_local(*lists, zero), fetch_k, kk, k)
+            fixed, _ = self._exchange((*lists, zero), fetch_k, kk, k)
             self._gather_buf = buf
             for key, val in fixed.items():
                 out[key][bad] = val

@@ -309,7 +309,10 @@ class HybridShard:
             if self.coschedule:
                 L.orag_cosine_mark_prescan(1)
         side = self._side
-        side.wait_stream(cur)  # inputs are ready
+        # inputs are ready; also what makes the caching allocator's per-stream pools safe without record_stream():
+        # every side-stream block (BM25 outputs, status) is only ever re-issued to side-stream work of a LATER call,
+        # which this wait orders after everything the current stream has enqueued on those blocks
+        side.wait_stream(cur)
         st_c: list = []
         st_b: list = []
         if self.coschedule and self.cosine.mode != "exact":

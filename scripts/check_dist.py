@@ -37,17 +37,40 @@ q_emb = torch.from_numpy(syn.query_embeddings(B, N, DIM, dup_per_mille=1)).to(de
 qt, ql = syn.keyword_queries(B, VOCAB, thresholds=thr)
 qt, ql = torch.from_numpy(qt).to(dev), torch.from_numpy(ql).to(dev)
 ok = True
+KEYS = ("ids", "rrf_scores", "cos_ids", "cos_scores", "bm25_ids", "bm25_scores", "bm25_max")
 for mode in ("tf32", "f16"):
-    sh = ShardedHybrid(build(lo, hi, lambda o, t: sharded_stats(o, t, VOCAB), mode))
-    res = sh.search(q_emb, qt, ql, K)
-    torch.cuda.synchronize()
-    if rank == 0:
-        ref = build(0, N, None, mode).search(q_emb, qt, ql, K)
-        for key in ("ids", "rrf_scores", "cos_ids", "cos_scores", "bm25_ids", "bm25_scores", "bm25_max"):
-            same = torch.equal(res[key], ref[key])
-            ok &= same
-            print(f"[{mode}] world={world} rows={N}: {key:12s} {'identical' if same else 'DIFFERENT'}", flush=True)
-    dist.barrier()
+    shard = build(lo, hi, lambda o, t: sharded_stats(o, t, VOCAB), mode)
+    ref = build(0, N, None, mode).search(q_emb, qt, ql, K) if rank == 0 else None
+    for exchange in ("nccl", "peer"):
+        sh = ShardedHybrid(shard, exchange=exchange)
+        res = sh.search(q_emb, qt, ql, K)
+        torch.cuda.synchronize()
+        if rank == 0:
+            for key in KEYS:
+                same = torch.equal(res[key], ref[key])
+                ok &= same
+                print(f"[{mode}/{exchange}] world={world} rows={N}: {key:12s} {'identical' if same else 'DIFFERENT'}",
+                      flush=True)
+        # device time and host time per step of back-to-back searches (no host sync inside)
+        for _ in range(5):
+            sh.search(q_emb, qt, ql, K, check_overflow=False)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 100
+        import time
+        e0.record(); t0 = time.perf_counter()
+        for _ in range(steps):
+            last = sh.search(q_emb, qt, ql, K, check_overflow=False)
+        t_host = time.perf_counter() - t0
+        e1.record(); torch.cuda.synchronize()
+        same = all(torch.equal(last[key], res[key]) for key in KEYS) and not bool(last["status"].any())
+        ok &= same
+        t = torch.tensor([e0.elapsed_time(e1) / steps, t_host * 1e3 / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"[{mode}/{exchange}] {steps} back-to-back searches: {t[0]:.3f} ms/step on the device, "
+                  f"{t[1]:.3f} ms/step of host enqueue time; stable={same}", flush=True)
+        dist.barrier()
 if rank == 0:
     print("DIST CHECK", "PASSED" if ok else "FAILED", flush=True)
 dist.destroy_process_group()

@@ -6,6 +6,7 @@ scores within 1e-5 relative (we additionally assert bitwise equality, which the 
 achieves), ties broken by chunk id.
 """
 import os
+import time
 from pathlib import Path
 
 import numpy as np
@@ -319,6 +320,139 @@ def test_hybrid_merge_equals_merge_then_rrf(eng):
                       ("ids", fi), ("rrf_scores", fs), ("src_ranks", src)):
         assert torch.equal(out[key], want), key
     assert status.cpu().tolist() == [1 if b == 7 else 0 for b in range(B)]
+
+
+def _random_lists(rng, g, B, fk, kk):
+    ci = np.stack([rng.permutation(500)[:fk] + 1000 * g for _ in range(B)]).astype(np.int64)
+    cs = rng.integers(0, 6, (B, fk)).astype(np.float64) / 8.0
+    bi = np.stack([rng.permutation(500)[:kk] + 1000 * g for _ in range(B)]).astype(np.int64)
+    bs = rng.integers(1, 9, (B, kk)).astype(np.float64) / 3.0
+    bm = bs.max(1)
+    st = (rng.integers(0, 20, B) == 0).astype(np.int32)
+    return [_t(x) for x in (ci, cs, bi, bs, bm, st)]
+
+
+def test_peer_exchange_kernels_two_virtual_ranks(eng):
+    """exchange_push_kernel + exchange_wait_kernel (csrc/exchange.cu) with both 'ranks' in this process (two local
+    buffers instead of IPC-mapped ones): after the pushes every rank's slot must be exactly the array
+    pack + all-gather builds, search after search (slot alternation, shrinking batch), and the merge over it
+    must equal the merge over the packed tensor."""
+    import ctypes
+    from optimized_rag_b200 import _ffi
+    from optimized_rag_b200.dist import hybrid_merge, pack_local
+    L = _ffi.lib()
+    G, maxq, fk, kk, k = 2, 64, 10, 16, 10
+    W = 2 * fk + 2 * kk + 2
+    nbytes = int(L.orag_exchange_bytes(G, maxq, fk, kk))
+    assert nbytes == 256 + 2 * G * maxq * W * 8
+    bufs = []
+    for _ in range(G):
+        p = ctypes.c_void_p()
+        _ffi.check(L.orag_exchange_alloc(nbytes, ctypes.byref(p)), "alloc")
+        bufs.append(p.value)
+    try:
+        d_peers = torch.tensor(bufs, dtype=torch.int64, device=DEV)
+        st = torch.cuda.current_stream().cuda_stream
+        rng = np.random.default_rng(5)
+        for seq, B in enumerate([64, 64, 37, 64, 1], start=1):
+            lists = [_random_lists(rng, g, B, fk, kk) for g in range(G)]
+            for g in range(G):
+                _ffi.check(L.orag_hybrid_push(*[t.data_ptr() for t in lists[g]], B, fk, kk, g, G, maxq,
+                                              d_peers.data_ptr(), seq, st), "push")
+            want = torch.stack([pack_local(*lists[g]) for g in range(G)]).contiguous()
+            ref, ref_status = hybrid_merge(want, fk, kk, 60, k)
+            for g in range(G):
+                out = ctypes.c_void_p()
+                _ffi.check(L.orag_hybrid_wait(bufs[g], G, maxq, B, fk, kk, seq, 2000, ctypes.byref(out), st), "wait")
+                assert out.value == bufs[g] + 256 + (seq & 1) * G * maxq * W * 8
+                got, status = hybrid_merge(out.value, fk, kk, 60, k, shape=(G, B, W), device=torch.device(DEV))
+                for key in ref:
+                    assert torch.equal(got[key], ref[key]), (seq, g, key)
+                assert torch.equal(status, ref_status)
+        # a block that never arrives: the wait gives up after the timeout and flags every query
+        out = ctypes.c_void_p()
+        t0 = time.perf_counter()
+        _ffi.check(L.orag_hybrid_wait(bufs[0], G, maxq, 8, fk, kk, 99, 50, ctypes.byref(out), st), "wait")
+        _, status = hybrid_merge(out.value, fk, kk, 60, k, shape=(G, 8, W), device=torch.device(DEV))
+        assert bool(((status & _ffi.ORAG_STATUS_EXCHANGE_TIMEOUT) != 0).all())
+        assert time.perf_counter() - t0 < 5.0
+    finally:
+        torch.cuda.synchronize()
+        for b in bufs:
+            _ffi.check(L.orag_exchange_free(b), "free")
+
+
+_PEER_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["ORAG_ROOT"])
+from optimized_rag_b200.dist import PeerExchange, hybrid_merge, pack_local
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+dev = torch.device("cuda", 0)            # both ranks on one GPU: CUDA IPC works between processes of one device
+torch.cuda.set_device(dev)
+fk, kk, k, B = 10, 16, 10, 48
+def lists(seed, g, n):
+    rng = np.random.default_rng(seed * 100 + g)
+    ci = np.stack([rng.permutation(500)[:fk] + 1000 * g for _ in range(n)]).astype(np.int64)
+    cs = rng.integers(0, 6, (n, fk)).astype(np.float64) / 8.0
+    bi = np.stack([rng.permutation(500)[:kk] + 1000 * g for _ in range(n)]).astype(np.int64)
+    bs = rng.integers(1, 9, (n, kk)).astype(np.float64) / 3.0
+    st = (rng.integers(0, 20, n) == 0).astype(np.int32)
+    return [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (ci, cs, bi, bs, bs.max(1), st)]
+# setup failure on ONE rank (its IPC open is made to fail) must surface as the same exception on EVERY rank
+from optimized_rag_b200 import _ffi
+L = _ffi.lib()
+real_open = L.orag_exchange_open
+if rank == 1:
+    L.orag_exchange_open = lambda *a: -2
+try:
+    PeerExchange(dev, 64, fk, kk)
+    ok = False
+except _ffi.OragError:
+    ok = True
+L.orag_exchange_open = real_open
+px = PeerExchange(dev, 64, fk, kk)
+for step, n in enumerate([B, B, 7, 64, B, B]):
+    ptr, shape = px.exchange(*lists(step, rank, n))
+    got, status = hybrid_merge(ptr, fk, kk, 60, k, shape=shape, device=dev)
+    want = torch.stack([pack_local(*lists(step, g, n)) for g in range(world)]).contiguous()
+    ref, ref_status = hybrid_merge(want, fk, kk, 60, k)
+    ok &= all(torch.equal(got[key], ref[key]) for key in ref) and torch.equal(status, ref_status)
+torch.cuda.synchronize()
+px.close()
+dist.destroy_process_group()
+print("PEER_OK" if ok else "PEER_MISMATCH", flush=True)
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_peer_exchange_across_processes_via_cuda_ipc(tmp_path):
+    """PeerExchange end to end between two PROCESSES (IPC export/open, remote stores, sequence numbers, slot re-use,
+    close; a setup failure on one rank raises on both): both ranks share this box's GPU, the host rendezvous is gloo."""
+    import socket
+    import subprocess
+    import sys
+    script = tmp_path / "peer_worker.py"
+    script.write_text(_PEER_WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   ORAG_ROOT=str(Path(__file__).resolve().parents[1]))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            o, _ = p.communicate()
+        outs.append(o)
+    assert all(p.returncode == 0 for p in procs) and all("PEER_OK" in o for o in outs), "\n".join(outs)
 
 
 # ------------------------------------------------------------------------------------------------ pairwise / config 1 / hybrid
