@@ -347,8 +347,12 @@ def run_native(args):
     flops = 2.0 * min(Bq, 256) * n_scan_rows * DIM
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
-    if tp.exists():
-        traffic = json.loads(tp.read_text()).get(f"cosine_scan_{args.mode}")
+    tj = json.loads(tp.read_text()) if tp.exists() else {}
+    # the ncu capture is of ONE launch shape; it says nothing about other shard sizes / batch sizes
+    cap = tj.get("captured_at", {})
+    same_launch = cap.get("rows_per_gpu") == n_local and cap.get("queries") == Bq
+    if same_launch:
+        traffic = tj.get(f"cosine_scan_{args.mode}")
     hbm = {"bound": "hbm", "achieved": streamed / t_scan / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
            "frac": streamed / t_scan / 1e9 / pk["hbm_gbs"], "traffic": traffic,
            "bytes": f"{args.mode} shadow copy actually streamed (N*D*2)" if half else "fp32 corpus (N*D*4)"}
@@ -369,7 +373,7 @@ def run_native(args):
                "unit": "GB/s", "frac": (post_bytes / t_bm / 1e9 / pk["hbm_gbs"]) if t_bm > 0 else None,
                "kernel": "bm25_ms_kernel (fp32 MaxScore first pass over the fp16-r posting view)", "launch_ms": t_bm * 1e3,
                "algorithmic_bytes": post_bytes,
-               "traffic": json.loads(tp.read_text()).get("bm25_ms") if tp.exists() else None}
+               "traffic": tj.get("bm25_ms") if same_launch else None}
 
     value = Bq * args.steps / (dev_ms * 1e-3)
     e2e_val = Bq * args.steps / (e2e_ms * 1e-3)
