@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node G scripts/check_dist.py [rows]
+"""torchrun --nproc-per-node G scripts/check_dist.py [rows] [modes, comma separated: tf32,f16]
 
 Row-sharded hybrid search over G GPUs must equal the single-shard search over the same corpus,
 bit for bit (ids, cosine / BM25 / RRF scores).  Rank 0 additionally builds the whole corpus on its
@@ -38,7 +38,7 @@ qt, ql = syn.keyword_queries(B, VOCAB, thresholds=thr)
 qt, ql = torch.from_numpy(qt).to(dev), torch.from_numpy(ql).to(dev)
 ok = True
 KEYS = ("ids", "rrf_scores", "cos_ids", "cos_scores", "bm25_ids", "bm25_scores", "bm25_max")
-for mode in ("tf32", "f16"):
+for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("tf32", "f16")):
     shard = build(lo, hi, lambda o, t: sharded_stats(o, t, VOCAB), mode)
     ref = build(0, N, None, mode).search(q_emb, qt, ql, K) if rank == 0 else None
     for exchange in ("nccl", "peer"):
