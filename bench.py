@@ -317,6 +317,8 @@ def run_native(args):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
+    exchange_used = "none (one shard)" if world == 1 else sh.exchange + (f" ({sh.exchange_note})" if sh.exchange_note else "")
+    sh.close()  # collective: every rank unmaps its peers' exchange buffers before any rank exits
 
     # ---- self-check outside the timed region: re-derive a few queries' lists with the exact kernels
     verified = None
@@ -387,8 +389,7 @@ def run_native(args):
                                                            "with proven error margins, then exact re-score",
                                              "rows_per_gpu": n_local,
                                              "parallelism": f"row-sharded x{world}", "setup_s": round(t_setup, 1),
-                                             "exchange": ("none (one shard)" if world == 1 else
-                                                          sh.exchange + (f" ({sh.exchange_note})" if sh.exchange_note else "")),
+                                             "exchange": exchange_used,
                                              "bm25_postings_local": bm25.n_postings}),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},

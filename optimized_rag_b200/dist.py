@@ -223,6 +223,7 @@ class ShardedHybrid:
         self.exchange_note = ""
         self._gather_buf = None
         self._peer: PeerExchange | None = None
+        self._retired: list[PeerExchange] = []  # outgrown exchanges: peers may still have them mapped until close()
 
     def _exchange(self, lists, fetch_k: int, kk: int, k: int):
         ci, cs, bi, bs, bm, st = lists
@@ -230,6 +231,9 @@ class ShardedHybrid:
             Bq = ci.shape[0]
             if self._peer is None or not self._peer.fits(Bq, fetch_k, kk):
                 # collective (every rank sees the same shapes); an outgrown exchange stays mapped until close()
+                if self._peer is not None:
+                    self._retired.append(self._peer)
+                    self._peer = None
                 try:
                     self._peer = PeerExchange(ci.device, max(Bq, 256), fetch_k, kk, group=self.group)
                 except _ffi.OragError as e:  # raised on every rank together (see PeerExchange.__init__)
@@ -245,9 +249,16 @@ class ShardedHybrid:
         dist.all_gather_into_tensor(self._gather_buf.view(-1), mine.view(-1), group=self.group)
         return hybrid_merge(self._gather_buf, fetch_k, kk, self.shard.rrf_k, k)
 
+    def close(self):
+        """Collective: unmap / free the peer exchange buffers (call on every rank before the process group goes away,
+        so that no rank frees a buffer another one still has mapped)."""
+        for px in self._retired + ([self._peer] if self._peer is not None else []):
+            px.close()
+        self._retired, self._peer = [], None
+
     def search(self, query_emb, query_terms, query_lens, k: int = 10, fetch_k: int | None = None,
                check_overflow: bool = True):
-        """Per batch: local lists (no host sync) -> ONE all-gather of the packed winners -> ONE merge+RRF launch.
+        """Per batch: local lists (no host sync) -> ONE exchange of the packed winners -> ONE merge+RRF launch.
         Candidate-buffer overflow on any rank is seen by every rank in the gathered status column; the affected
         queries (rare: thousands of duplicates / near-ties) are then repaired by all ranks together through the
         exhaustive kernels and a second, small exchange -- every rank takes the same branch."""

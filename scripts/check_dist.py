@@ -70,6 +70,7 @@ for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("tf32", "f16")):
         if rank == 0:
             print(f"[{mode}/{exchange}] {steps} back-to-back searches: {t[0]:.3f} ms/step on the device, "
                   f"{t[1]:.3f} ms/step of host enqueue time; stable={same}", flush=True)
+        sh.close()
         dist.barrier()
 if rank == 0:
     print("DIST CHECK", "PASSED" if ok else "FAILED", flush=True)
