@@ -174,7 +174,7 @@ class ClockSampler:
         if not inside and rows and self.windows:  # run shorter than the polling period: nearest samples under the same load
             a, b = min(w[0] for w in self.windows), max(w[1] for w in self.windows)
             inside = [r for r in rows if a - 0.25 <= r[0] <= b + 0.25]
-            note = "nearest to the timed regions (+-0.25 s, same workload: warm-up / e2e loop)"
+            note = "nearest to the timed regions (+-0.25 s, same workload: warm-up loop)"
         if inside:
             out.update(sm_mhz=statistics.median(r[1] for r in inside), sm_max_mhz=max(r[2] for r in inside),
                        reasons=sorted({n for r in inside for n in r[3]}), samples=len(inside), window=note)
@@ -296,6 +296,10 @@ def run_native(args):
     scan_ms.append(a.value); bm_ms.append(b.value)
     L.orag_profile_enable(0)
 
+    # the clocks line describes the device-timed loop (see ClockSampler): stop polling before the end-to-end loop, where
+    # every step synchronises with the host and a poller taking driver locks would be measured with it
+    clocks = sampler.stop()
+
     # ---- timed: end to end through the public call with HOST buffers
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -316,7 +320,6 @@ def run_native(args):
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop()
     exchange_used = "none (one shard)" if world == 1 else sh.exchange + (f" ({sh.exchange_note})" if sh.exchange_note else "")
     sh.close()  # collective: every rank unmaps its peers' exchange buffers before any rank exits
 
