@@ -219,6 +219,28 @@ def golden_config1():
             "source": "reference README.md via rag/chunking.py FixedSizeChunker(1200,150)"}
 
 
+def golden_mmr():
+    """MMRDiversifier.diversify (rag/reranker.py:104-195) on seeded embeddings: picked indices + mmr scores."""
+    mod = ref_loader.load("reranker")
+    cases = []
+    for name, m, d, dup, zero_row, params in [
+            ("m24_d96", 24, 96, 0, None, [(0.7, 5), (0.3, 24), (1.0, 4)]),
+            ("m40_d64_dups_zero", 40, 64, 100, 11, [(0.7, 10), (0.0, 6), (0.5, 40)]),
+            ("m3_d1536", 3, 1536, 0, None, [(0.7, 5)])]:
+        emb = syn.embeddings(syn.SEED_CORPUS, 0, m, d, dup)
+        if zero_row is not None:
+            emb[zero_row, :] = 0.0
+        q = syn.query_embeddings(1, m, d, dup_per_mille=dup)[0]
+        runs = []
+        for lam, k in params:
+            docs = [{"content": f"d{i}", "embedding": py_list(emb[i])} for i in range(m)]
+            out = mod.MMRDiversifier(lambda_param=lam).diversify(py_list(q), docs, top_k=k)
+            runs.append({"lambda": lam, "top_k": k, "picked": [int(x["content"][1:]) for x in out],
+                         "mmr_scores": [hx(x["mmr_score"]) for x in out]})
+        cases.append({"name": name, "m": m, "dim": d, "dup_per_mille": dup, "zero_row": zero_row, "runs": runs})
+    return {"cases": cases}
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     data = {
@@ -230,6 +252,7 @@ def main():
         "weighted": golden_weighted(),
         "pairwise": golden_pairwise(),
         "config1": golden_config1(),
+        "mmr": golden_mmr(),
     }
     p = OUT / "golden.json"
     p.write_text(json.dumps(data, separators=(",", ":")))

@@ -143,6 +143,26 @@ def test_pairwise(golden):
     assert got == g["pairs"] and len(got) > 0
 
 
+def mmr_inputs(case):
+    """Embeddings + query of one golden MMR case (shared with the GPU boundary test)."""
+    emb = syn.embeddings(syn.SEED_CORPUS, 0, case["m"], case["dim"], case["dup_per_mille"])
+    if case["zero_row"] is not None:
+        emb[case["zero_row"], :] = 0.0
+    q = syn.query_embeddings(1, case["m"], case["dim"], dup_per_mille=case["dup_per_mille"])[0]
+    return emb, q
+
+
+def test_mmr_golden(golden):
+    """oracle.mmr_select replays what the reference's MMRDiversifier.diversify
+    (rag/reranker.py:104-195) picked and scored, bit for bit (duplicates, a zero row, lambda 0 and 1, top_k > m)."""
+    for case in golden["mmr"]["cases"]:
+        emb, q = mmr_inputs(case)
+        for run in case["runs"]:
+            sel, sc = oracle.mmr_select(q, emb, run["lambda"], run["top_k"])
+            assert sel == run["picked"], (case["name"], run["lambda"])
+            assert sc == [fromhex(x) for x in run["mmr_scores"]], (case["name"], run["lambda"])
+
+
 def test_config1(golden):
     g = golden["config1"]
     n, dim = g["n_chunks"], g["dim"]
