@@ -288,3 +288,15 @@ def mmr_select(query, embeddings, lambda_param: float, top_k: int):
         scores.append(best[0])
         remaining.remove(best[1])
     return selected, scores
+
+
+# --------------------------------------------------------------------------- semantic dedup (rag/data_wrangler.py:295-326)
+def semantic_dedup_keep(embeddings, threshold: float = 0.95):
+    """Indices the reference's greedy loop keeps: chunk i survives unless its cosine with an EARLIER SURVIVOR is
+    >= threshold (same float64 cosine as everywhere else: Neumaier `sum`, dot / (|a| * |b|), 0 for a zero vector)."""
+    emb = np.ascontiguousarray(embeddings, dtype=np.float32)
+    kept: list[int] = []
+    for i in range(len(emb)):
+        if not any(cosine(emb[i], emb[j]) >= threshold for j in kept):
+            kept.append(i)
+    return kept

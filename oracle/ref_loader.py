@@ -38,7 +38,7 @@ def _prepare():
 
 
 def load(name: str):
-    """name in {'retrieval','reranker','chunking','consistency_checker'}."""
+    """name in {'retrieval','reranker','chunking','consistency_checker','data_wrangler'}."""
     if name in _cache:
         return _cache[name]
     if not available():

@@ -241,6 +241,25 @@ def golden_mmr():
     return {"cases": cases}
 
 
+def golden_dedup():
+    """Deduplicator.semantic_dedup (rag/data_wrangler.py:295-326) on seeded embeddings: indices of the survivors."""
+    mod = ref_loader.load("data_wrangler")
+    cases = []
+    for name, m, d, dup, near, thr in [("m60_d64_dups", 60, 64, 200, 0.0, 0.95), ("m40_d96_near", 40, 96, 0, 0.2, 0.95),
+                                       ("m30_d32_low_threshold", 30, 32, 0, 0.0, 0.2), ("m5_d1536", 5, 1536, 0, 0.05, 0.95)]:
+        emb = syn.embeddings(syn.SEED_CORPUS, 0, m, d, dup)
+        if near:
+            for i in range(0, m - 1, 3):   # near-duplicates of an earlier row on both sides of the threshold
+                emb[i + 1] = (emb[i] + np.float32(near * (1 + i % 4)) * emb[i + 1]).astype(np.float32)
+        if name == "m40_d96_near":
+            emb[7, :] = 0.0               # zero vector: cosine 0 with everything, always kept
+        chunks = [{"content": f"c{i}"} for i in range(m)]
+        out = mod.Deduplicator.semantic_dedup(chunks, [py_list(e) for e in emb], threshold=thr)
+        cases.append({"name": name, "m": m, "dim": d, "dup_per_mille": dup, "near": near, "threshold": thr,
+                      "kept": [int(c["content"][1:]) for c in out]})
+    return {"cases": cases}
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     data = {
@@ -253,6 +272,7 @@ def main():
         "pairwise": golden_pairwise(),
         "config1": golden_config1(),
         "mmr": golden_mmr(),
+        "dedup": golden_dedup(),
     }
     p = OUT / "golden.json"
     p.write_text(json.dumps(data, separators=(",", ":")))

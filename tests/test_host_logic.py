@@ -179,3 +179,35 @@ def test_first_pass_view_is_dropped_when_idf_goes_negative(built_lib):
     tok[3::8] = 5
     ix = Bm25Index(torch.from_numpy(doc_off), torch.from_numpy(tok), 8, tile_docs=32)
     assert ix.has_negative_idf and ix.postings_r16 is None and ix.struct.d_postings_r16 is None
+
+
+def test_semantic_dedup_host_logic_with_a_stand_in_cosine_matrix(built_lib, monkeypatch):
+    """Every line of Deduplicator.semantic_dedup except the kernel launch, on the CPU: the cosine index is replaced
+    by a stand-in that serves the oracle's float64 cosines, blocks are forced to be small, and the survivors must be
+    the ones the reference kept (golden vectors).  The real launch is covered by the -m gpu test."""
+    import json
+    from pathlib import Path
+    from optimized_rag_b200 import data_wrangler, engine
+    from test_oracle_golden import dedup_inputs
+    golden = json.loads((Path(__file__).parent / "golden" / "golden.json").read_text())
+
+    class StandIn:
+        def __init__(self, emb, mode="exact"):
+            assert mode == "exact" and emb.dtype == torch.float32
+            self.rows = emb.numpy()
+
+        def dense(self, q):
+            return torch.from_numpy(np.stack([oracle.cosine_scores(self.rows, r) for r in q.numpy()]))
+
+    monkeypatch.setattr(engine, "CosineIndex", StandIn)
+    monkeypatch.setattr(data_wrangler, "BLOCK_ROWS", 7)
+    for case in golden["dedup"]["cases"]:
+        emb = dedup_inputs(case)
+        chunks = [{"content": f"c{i}", "n": i} for i in range(case["m"])]
+        out = data_wrangler.Deduplicator.semantic_dedup(chunks, [[float(x) for x in e] for e in emb],
+                                                        threshold=case["threshold"], device="cpu")
+        assert [c["n"] for c in out] == case["kept"], case["name"]
+        assert all(o is chunks[o["n"]] for o in out)          # the reference returns the same dict objects
+    assert data_wrangler.Deduplicator.semantic_dedup([], [], 0.95, device="cpu") == []
+    one = [{"content": "a"}, {"content": "b"}]
+    assert data_wrangler.Deduplicator.semantic_dedup(one, [[1.0, 0.0]], 0.95, device="cpu") == one[:1]   # zip semantics

@@ -163,6 +163,28 @@ def test_mmr_golden(golden):
             assert sc == [fromhex(x) for x in run["mmr_scores"]], (case["name"], run["lambda"])
 
 
+def dedup_inputs(case):
+    """Embeddings of one golden semantic-dedup case (shared with the host-logic and GPU tests)."""
+    m = case["m"]
+    emb = syn.embeddings(syn.SEED_CORPUS, 0, m, case["dim"], case["dup_per_mille"])
+    if case["near"]:
+        for i in range(0, m - 1, 3):
+            emb[i + 1] = (emb[i] + np.float32(case["near"] * (1 + i % 4)) * emb[i + 1]).astype(np.float32)
+    if case["name"] == "m40_d96_near":
+        emb[7, :] = 0.0
+    return emb
+
+
+def test_dedup_golden(golden):
+    """oracle.semantic_dedup_keep keeps exactly the chunks the reference's
+    Deduplicator.semantic_dedup (rag/data_wrangler.py:295-326) kept (exact duplicates, near-duplicates on both sides
+    of the threshold, a zero vector, a low threshold with chains of drops)."""
+    for case in golden["dedup"]["cases"]:
+        kept = oracle.semantic_dedup_keep(dedup_inputs(case), case["threshold"])
+        assert kept == case["kept"], case["name"]
+        assert 0 < len(kept) < case["m"]
+
+
 def test_config1(golden):
     g = golden["config1"]
     n, dim = g["n_chunks"], g["dim"]
