@@ -297,3 +297,89 @@ class Bm25Index:
         tc = t.clamp(0, self.vocab - 1)
         per = torch.where(mask & idf_nz[tc], df_shard[tc], torch.zeros_like(tc))
         return int(per.sum().item()) * 6
+
+    # ------------------------------------------------------------------ on-disk format
+    # The reference's "format" for the keyword side is nothing at all: `BM25Okapi(tokenized_corpus)` is rebuilt from
+    # the Postgres rows on every call (rag/retrieval.py:334-338).  Here one index = two files:
+    #   <stem>.json   scalars (sizes, avgdl, eps, ...) + a manifest {name: dtype, shape, byte offset}
+    #   <stem>.bin    the arrays of the layout described at the top of this module, little-endian, each aligned to
+    #                 256 bytes, exactly as they sit in HBM -> loading is read (or mmap) + one copy per array
+    FORMAT_VERSION = 1
+    _ARRAYS = ("idf", "dl", "t4_table", "r_table", "postings", "tile_base", "tile_term_off",
+               "postings_r16", "fp_tile_base", "fp_tile_term_off", "term_max_r")
+
+    def save(self, stem) -> None:
+        import json
+        from pathlib import Path
+        stem = Path(stem)
+        arrays = {name: getattr(self, name) for name in self._ARRAYS if getattr(self, name) is not None}
+        arrays["stats_df"] = torch.from_numpy(np.ascontiguousarray(self.stats.df, dtype=np.int64))
+        arrays["stats_first_seen"] = torch.from_numpy(np.ascontiguousarray(self.stats.first_seen, dtype=np.int64))
+        manifest, pos = {}, 0
+        with open(stem.with_suffix(".bin"), "wb") as fh:
+            for name, t in arrays.items():
+                a = np.ascontiguousarray(t.detach().cpu().numpy())
+                a = a.astype(a.dtype.newbyteorder("<"), copy=False)
+                pad = (-pos) % 256
+                fh.write(b"\0" * pad)
+                pos += pad
+                manifest[name] = {"dtype": a.dtype.str, "shape": list(a.shape), "offset": pos}
+                fh.write(a.tobytes())
+                pos += a.nbytes
+        meta = {"format": "orag-bm25-index", "version": self.FORMAT_VERSION, "n_docs": self.n_docs, "vocab": self.vocab,
+                "tile_docs": self.tile_docs, "n_tiles": self.n_tiles, "fp_tile_docs": self.fp_tile_docs,
+                "fp_n_tiles": self.fp_n_tiles, "doc_id_base": self.doc_id_base, "n_postings": self.n_postings,
+                "max_dl": self.max_dl, "has_negative_idf": self.has_negative_idf, "avgdl": float(self.avgdl).hex(),
+                "average_idf": float(self.average_idf).hex(), "eps": float(self.eps).hex(),
+                "stats_n_docs": self.stats.n_docs, "stats_total_len": self.stats.total_len, "bytes": pos,
+                "arrays": manifest}
+        stem.with_suffix(".json").write_text(json.dumps(meta))
+
+    @classmethod
+    def load(cls, stem, device="cuda") -> "Bm25Index":
+        """Re-creates a saved index on `device` without touching the token corpus (no sort, no statistics pass)."""
+        import json
+        from pathlib import Path
+        stem = Path(stem)
+        meta = json.loads(stem.with_suffix(".json").read_text())
+        if meta.get("format") != "orag-bm25-index" or meta.get("version") != cls.FORMAT_VERSION:
+            raise ValueError(f"{stem}: not a version-{cls.FORMAT_VERSION} orag BM25 index")
+        blob = np.memmap(stem.with_suffix(".bin"), dtype=np.uint8, mode="r")
+        if blob.shape[0] != meta["bytes"]:
+            raise ValueError(f"{stem}.bin: truncated ({blob.shape[0]} of {meta['bytes']} bytes)")
+        dev = torch.device(device)
+
+        def arr(name):
+            m = meta["arrays"].get(name)
+            if m is None:
+                return None
+            dt = np.dtype(m["dtype"])
+            count = int(np.prod(m["shape"])) if m["shape"] else 1
+            a = np.frombuffer(blob, dtype=dt, count=count, offset=m["offset"]).reshape(m["shape"])
+            return np.array(a, dtype=dt.newbyteorder("="))  # private, native-endian copy
+
+        self = cls.__new__(cls)
+        self.device = dev
+        for key in ("n_docs", "vocab", "tile_docs", "n_tiles", "fp_tile_docs", "fp_n_tiles", "doc_id_base",
+                    "n_postings", "max_dl"):
+            setattr(self, key, int(meta[key]))
+        self.has_negative_idf = bool(meta["has_negative_idf"])
+        self.avgdl, self.average_idf, self.eps = (float.fromhex(meta[k]) for k in ("avgdl", "average_idf", "eps"))
+        self.stats = Bm25Stats(int(meta["stats_n_docs"]), int(meta["stats_total_len"]), arr("stats_df"),
+                               arr("stats_first_seen"))
+        for name in cls._ARRAYS:
+            a = arr(name)
+            setattr(self, name, None if a is None else torch.from_numpy(a).to(dev))
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        # same field-by-field construction as __init__ (tests/test_host_logic.py compares the two structs)
+        self.struct = _ffi.Bm25IndexStruct(
+            n_docs=self.n_docs, vocab=self.vocab, tile_docs=self.tile_docs, n_tiles=self.n_tiles,
+            has_negative_idf=int(self.has_negative_idf),
+            d_tile_base=ptr(self.tile_base), d_tile_term_off=ptr(self.tile_term_off),
+            max_doc_len=self.max_dl, reserved=0, d_postings=ptr(self.postings), d_doc_len=ptr(self.dl),
+            d_t4_table=ptr(self.t4_table), d_r_table=ptr(self.r_table), d_idf=ptr(self.idf),
+            d_postings_r16=ptr(self.postings_r16), d_term_max_r=ptr(self.term_max_r),
+            fp_tile_docs=self.fp_tile_docs, fp_n_tiles=self.fp_n_tiles,
+            d_fp_tile_base=ptr(self.fp_tile_base), d_fp_tile_term_off=ptr(self.fp_tile_term_off))
+        self._ws = None
+        return self

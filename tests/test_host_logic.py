@@ -211,3 +211,45 @@ def test_semantic_dedup_host_logic_with_a_stand_in_cosine_matrix(built_lib, monk
     assert data_wrangler.Deduplicator.semantic_dedup([], [], 0.95, device="cpu") == []
     one = [{"content": "a"}, {"content": "b"}]
     assert data_wrangler.Deduplicator.semantic_dedup(one, [[1.0, 0.0]], 0.95, device="cpu") == one[:1]   # zip semantics
+
+
+@pytest.mark.parametrize("n,vocab,tile,negative", [(700, 300, 64, False), (40, 8, 32, True), (0, 5, 32, False)])
+def test_bm25_index_save_load_round_trip(built_lib, tmp_path, n, vocab, tile, negative):
+    """On-disk format of the keyword index: every array and scalar survives save -> load bit for
+    bit, and the struct handed to the kernels is field-for-field the one the builder makes (pointers aside)."""
+    from optimized_rag_b200 import _ffi
+    from optimized_rag_b200.bm25_index import Bm25Index
+    if negative:
+        doc_off = np.arange(0, 4 * n + 1, 4, dtype=np.int64)
+        tok = np.tile(np.array([0, 1, 2, 3], dtype=np.int32), n)
+        tok[3::8] = 5
+    else:
+        thr = syn.zipf_thresholds(vocab)
+        doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, 3, 40, thr)
+    ix = Bm25Index(torch.from_numpy(doc_off), torch.from_numpy(tok), vocab, tile_docs=tile, doc_id_base=1234)
+    assert ix.has_negative_idf == negative and (ix.postings_r16 is None) == (negative or n == 0)
+    ix.save(tmp_path / "kw")
+    assert (tmp_path / "kw.bin").stat().st_size % 1 == 0 and (tmp_path / "kw.json").exists()
+    back = Bm25Index.load(tmp_path / "kw", device="cpu")
+    for name in Bm25Index._ARRAYS:
+        a, b = getattr(ix, name), getattr(back, name)
+        assert (a is None) == (b is None), name
+        if a is not None:
+            assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b), name
+    for key in ("n_docs", "vocab", "tile_docs", "n_tiles", "fp_tile_docs", "fp_n_tiles", "doc_id_base", "n_postings",
+                "max_dl", "has_negative_idf", "avgdl", "average_idf", "eps"):
+        assert getattr(ix, key) == getattr(back, key), key
+    assert back.stats.n_docs == ix.stats.n_docs and back.stats.total_len == ix.stats.total_len
+    assert np.array_equal(back.stats.df, ix.stats.df) and np.array_equal(back.stats.first_seen, ix.stats.first_seen)
+    for field, ctype in _ffi.Bm25IndexStruct._fields_:
+        va, vb = getattr(ix.struct, field), getattr(back.struct, field)
+        if field.startswith("d_"):
+            assert (va is None) == (vb is None), field   # same arrays present, each pointing at its own copy
+        else:
+            assert va == vb, field
+    # a damaged file is refused
+    data = (tmp_path / "kw.bin").read_bytes()
+    if len(data) > 16:
+        (tmp_path / "kw.bin").write_bytes(data[:-8])
+        with pytest.raises(ValueError):
+            Bm25Index.load(tmp_path / "kw", device="cpu")

@@ -35,3 +35,24 @@ def test_semantic_dedup_matches_reference_golden_and_oracle(monkeypatch):
     chunks = [{"content": f"c{i}", "n": i} for i in range(300)]
     out = data_wrangler.Deduplicator.semantic_dedup(chunks, [[float(x) for x in e] for e in emb], 0.95, device="cuda:0")
     assert [c["n"] for c in out] == oracle.semantic_dedup_keep(emb, 0.95)
+
+
+def test_bm25_index_loaded_from_disk_answers_like_the_built_one(tmp_path):
+    """Bm25Index.save / load (on-disk format): a loaded index must return bit-identical
+    top-k lists through both kernels (MaxScore first pass and dense)."""
+    from optimized_rag_b200 import synthetic as syn
+    from optimized_rag_b200.bm25_index import Bm25Index
+    dev = "cuda:0"
+    n, vocab = 20000, 3000
+    thr = syn.zipf_thresholds(vocab)
+    doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, 20, 60, thr)
+    ix = Bm25Index(torch.from_numpy(doc_off).to(dev), torch.from_numpy(tok).to(dev), vocab, tile_docs=256, doc_id_base=77)
+    ix.save(tmp_path / "kw")
+    back = Bm25Index.load(tmp_path / "kw", device=dev)
+    qt, ql = syn.keyword_queries(32, vocab, thresholds=thr)
+    qt, ql = torch.from_numpy(qt).to(dev), torch.from_numpy(ql).to(dev)
+    for force in (None, "dense"):
+        a = ix.topk(qt, ql, 10, force=force)
+        b = back.topk(qt, ql, 10, force=force)
+        assert all(torch.equal(x, y) for x, y in zip(a, b)), force
+    assert int(a[0].min()) >= 77
