@@ -191,15 +191,7 @@ def test_semantic_dedup_host_logic_with_a_stand_in_cosine_matrix(built_lib, monk
     from test_oracle_golden import dedup_inputs
     golden = json.loads((Path(__file__).parent / "golden" / "golden.json").read_text())
 
-    class StandIn:
-        def __init__(self, emb, mode="exact"):
-            assert mode == "exact" and emb.dtype == torch.float32
-            self.rows = emb.numpy()
-
-        def dense(self, q):
-            return torch.from_numpy(np.stack([oracle.cosine_scores(self.rows, r) for r in q.numpy()]))
-
-    monkeypatch.setattr(engine, "CosineIndex", StandIn)
+    monkeypatch.setattr(engine, "CosineIndex", _OracleCosineIndex)
     monkeypatch.setattr(data_wrangler, "BLOCK_ROWS", 7)
     for case in golden["dedup"]["cases"]:
         emb = dedup_inputs(case)
@@ -253,3 +245,33 @@ def test_bm25_index_save_load_round_trip(built_lib, tmp_path, n, vocab, tile, ne
         (tmp_path / "kw.bin").write_bytes(data[:-8])
         with pytest.raises(ValueError):
             Bm25Index.load(tmp_path / "kw", device="cpu")
+
+
+class _OracleCosineIndex:
+    """Stand-in for engine.CosineIndex on the CPU: serves the oracle's float64 cosines (host-logic tests only)."""
+
+    def __init__(self, emb, mode="exact"):
+        assert mode == "exact" and emb.dtype == torch.float32
+        self.rows = emb.numpy()
+
+    def dense(self, q):
+        return torch.from_numpy(np.stack([oracle.cosine_scores(self.rows, r) for r in q.numpy()]))
+
+
+def test_mmr_host_logic_replays_the_reference_golden(built_lib, monkeypatch):
+    """MMRDiversifier.diversify with the kernel launch replaced by the oracle's cosines: the greedy loop, tie rule,
+    in-place `mmr_score` and top_k > m behaviour must reproduce what the reference recorded (golden.json "mmr")."""
+    import json
+    from pathlib import Path
+    from optimized_rag_b200 import engine, reranker
+    from test_oracle_golden import mmr_inputs
+    golden = json.loads((Path(__file__).parent / "golden" / "golden.json").read_text())
+    monkeypatch.setattr(engine, "CosineIndex", _OracleCosineIndex)
+    for case in golden["mmr"]["cases"]:
+        emb, q = mmr_inputs(case)
+        for run in case["runs"]:
+            docs = [{"content": f"d{i}", "embedding": [float(x) for x in emb[i]]} for i in range(case["m"])]
+            out = reranker.MMRDiversifier(lambda_param=run["lambda"], device="cpu").diversify(
+                [float(x) for x in q], docs, top_k=run["top_k"])
+            assert [int(d["content"][1:]) for d in out] == run["picked"], (case["name"], run["lambda"])
+            assert [d["mmr_score"].hex() for d in out] == run["mmr_scores"], (case["name"], run["lambda"])

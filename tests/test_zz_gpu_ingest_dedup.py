@@ -1,6 +1,7 @@
-"""GPU test of the ingest-side semantic de-duplication, added after the last GPU session of
-round 1: its host logic is pinned on the CPU (tests/test_host_logic.py), the kernel it launches (orag_cosine_dense)
-by the parity tests; this file runs the two together.  It sorts last on purpose."""
+"""GPU tests added after the last GPU session of round 1: semantic de-duplication, the
+on-disk BM25 index, MMR against the reference's golden vectors.  Their host logic is pinned on the CPU
+(tests/test_host_logic.py) and the kernels they launch by the parity tests; this file runs the two together.
+It sorts last on purpose."""
 import json
 from pathlib import Path
 
@@ -55,3 +56,19 @@ def test_bm25_index_loaded_from_disk_answers_like_the_built_one(tmp_path):
         a = ix.topk(qt, ql, 10, force=force)
         b = back.topk(qt, ql, 10, force=force)
         assert all(torch.equal(x, y) for x, y in zip(a, b)), force
+
+
+def test_mmr_diversifier_reproduces_the_reference_golden():
+    """MMRDiversifier on the GPU against what the reference's MMRDiversifier.diversify recorded (golden.json "mmr":
+    rag/reranker.py:104-195 run on seeded embeddings, incl. duplicates, a zero row, lambda 0 / 1, top_k > m)."""
+    from optimized_rag_b200.reranker import MMRDiversifier
+    from test_oracle_golden import mmr_inputs
+    golden = json.loads((Path(__file__).parent / "golden" / "golden.json").read_text())
+    for case in golden["mmr"]["cases"]:
+        emb, q = mmr_inputs(case)
+        for run in case["runs"]:
+            docs = [{"content": f"d{i}", "embedding": [float(x) for x in emb[i]]} for i in range(case["m"])]
+            out = MMRDiversifier(lambda_param=run["lambda"], device="cuda:0").diversify(
+                [float(x) for x in q], docs, top_k=run["top_k"])
+            assert [int(d["content"][1:]) for d in out] == run["picked"], (case["name"], run["lambda"])
+            assert [d["mmr_score"].hex() for d in out] == run["mmr_scores"], (case["name"], run["lambda"])
