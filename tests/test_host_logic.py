@@ -275,3 +275,45 @@ def test_mmr_host_logic_replays_the_reference_golden(built_lib, monkeypatch):
                 [float(x) for x in q], docs, top_k=run["top_k"])
             assert [int(d["content"][1:]) for d in out] == run["picked"], (case["name"], run["lambda"])
             assert [d["mmr_score"].hex() for d in out] == run["mmr_scores"], (case["name"], run["lambda"])
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_gpu(built_lib):
+    """Error behaviour of the C ABI that needs no device: every entry point validates its arguments first and
+    returns ORAG_EINVAL (-1) / ORAG_EWORKSPACE (-3) with a message in orag_last_error(); size queries are pure host
+    arithmetic."""
+    import ctypes
+    from optimized_rag_b200 import _ffi
+    L = _ffi.lib()
+    assert L.orag_version() == 1
+    # size queries
+    W = 2 * 10 + 2 * 16 + 2
+    assert L.orag_exchange_bytes(8, 256, 10, 16) == 256 + 2 * 8 * 256 * W * 8
+    assert L.orag_exchange_bytes(0, 256, 10, 16) == 0
+    assert L.orag_cosine_workspace_bytes(1000, 1536, 0, 10, _ffi.ORAG_COS_F16) == 0
+    small = L.orag_cosine_workspace_bytes(1000, 1536, 4, 10, _ffi.ORAG_COS_EXACT)
+    assert small >= 4 * 8 + 4 * 1000 * 8
+    assert L.orag_cosine_workspace_bytes(10_000_000, 1536, 256, 10, _ffi.ORAG_COS_F16) < 16 << 20
+    # argument validation
+    rc = L.orag_cosine_topk(None, None, None, None, 10, 1536, 0, None, 4, 10, _ffi.ORAG_COS_F16, None, None, None, None, 0,
+                            None)
+    assert rc == -1 and b"cosine_topk" in L.orag_last_error()
+    with pytest.raises(_ffi.OragError, match="code -1"):
+        _ffi.check(rc, "orag_cosine_topk")
+    assert L.orag_rrf_fuse(None, 1, 2, 10, 60, 10, 0, None, None, None, None) == -1
+    buf = (ctypes.c_int64 * 64)()
+    out_i, out_s = (ctypes.c_int64 * 16)(), (ctypes.c_double * 16)()
+    p = lambda a: ctypes.cast(a, ctypes.c_void_p)
+    assert L.orag_rrf_fuse(p(buf), 1, 9, 10, 60, 10, 0, p(out_i), p(out_s), None, None) == -1       # > 8 lists
+    assert b"rrf_fuse sizes" in L.orag_last_error()
+    assert L.orag_rrf_fuse(p(buf), 1, 2, 100, 60, 10, 0, p(out_i), p(out_s), None, None) == -1      # union > 128
+    assert L.orag_rrf_fuse(p(buf), 0, 2, 10, 60, 10, 0, p(out_i), p(out_s), None, None) == 0        # empty batch: no launch
+    assert L.orag_hybrid_merge(p(buf), 40, 1, 10, 16, 60, 10, 0, *([p(buf)] * 9), None) == -1         # 40 * 16 > 256
+    assert L.orag_hybrid_push(*([p(buf)] * 6), 4, 10, 16, 2, 2, 256, p(buf), 1, None) == -1          # rank >= n_shards
+    assert L.orag_hybrid_push(*([p(buf)] * 6), 300, 10, 16, 0, 2, 256, p(buf), 1, None) == -1        # batch > max_queries
+    assert L.orag_hybrid_push(*([p(buf)] * 6), 4, 10, 16, 0, 2, 256, p(buf), 0, None) == -1          # seq starts at 1
+    got = ctypes.c_void_p()
+    assert L.orag_hybrid_wait(p(buf), 2, 256, 4, 10, 16, 1, 0, ctypes.byref(got), None) == -1         # timeout_ms > 0
+    assert L.orag_exchange_alloc(0, ctypes.byref(got)) == -1
+    assert L.orag_exchange_free(None) == 0 and L.orag_exchange_close(None) == 0
+    assert L.orag_weighted_sum3(None, None, None, 5, 0.5, 0.3, 0.2, None, None) == -1
+    assert L.orag_div_scalar(p(buf), 0, 2.0, p(buf), None) == 0
