@@ -321,7 +321,6 @@ def run_native(args):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     exchange_used = "none (one shard)" if world == 1 else sh.exchange + (f" ({sh.exchange_note})" if sh.exchange_note else "")
-    sh.close()  # collective: every rank unmaps its peers' exchange buffers before any rank exits
 
     # ---- self-check outside the timed region: re-derive a few queries' lists with the exact kernels
     verified = None
@@ -338,6 +337,7 @@ def run_native(args):
 
     if rank != 0:
         if world > 1:
+            sh.close()  # collective with rank 0's call below: nobody frees a buffer a peer still has mapped
             dist.destroy_process_group()
         return
 
@@ -421,6 +421,7 @@ def run_native(args):
                                           f"to {N} rows; BM25Okapi rebuild per call not charged"}
     print(json.dumps(line), flush=True)
     if world > 1:
+        sh.close()
         dist.destroy_process_group()
 
 

@@ -192,18 +192,24 @@ class PeerExchange:
         return out.value, (self.world, Bq, self.W)
 
     def close(self):
-        """Collective: unmap the peers' buffers, then free the own one (after everybody has unmapped it)."""
+        """Collective: unmap the peers' buffers, then free the own one (after everybody has unmapped it).  Never
+        raises between the two barriers (a rank that bailed out would leave the others waiting): failures are logged."""
         if self._mine is None:
             return
         L = _ffi.lib()
+        errors = []
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)
         with torch.cuda.device(self.device):
             for p in self._opened:
-                _ffi.check(L.orag_exchange_close(p), "orag_exchange_close")
+                if L.orag_exchange_close(p) != 0:
+                    errors.append(L.orag_last_error())
             dist.barrier(group=self.group)
-            _ffi.check(L.orag_exchange_free(self._mine), "orag_exchange_free")
+            if L.orag_exchange_free(self._mine) != 0:
+                errors.append(L.orag_last_error())
         self._mine, self._opened = None, []
+        if errors:
+            logger.warning("peer exchange teardown: %s", errors)
 
 
 class ShardedHybrid:
