@@ -300,3 +300,127 @@ def semantic_dedup_keep(embeddings, threshold: float = 0.95):
         if not any(cosine(emb[i], emb[j]) >= threshold for j in kept):
             kept.append(i)
     return kept
+
+
+# --------------------------------------------------------------------------- streamed oracle (BASELINE-size parity gates)
+_stream_ready = False
+
+
+def _stream_lib():
+    global _stream_ready
+    L = lib()
+    if not _stream_ready:
+        u64, i64, i32 = ctypes.c_uint64, ctypes.c_int64, ctypes.c_int
+        _c_u64p = ctypes.POINTER(ctypes.c_uint64)
+        L.orc_gen_embeddings.restype = None
+        L.orc_gen_embeddings.argtypes = [u64, i64, i64, i32, i32, _c_f32p]
+        L.orc_cosine_topk_stream.restype = ctypes.c_int
+        L.orc_cosine_topk_stream.argtypes = [u64, i64, i64, i32, i32, _c_f32p, _c_f32p, i32, i32, i32, _c_i64p, _c_f64p]
+        L.orc_gen_token_corpus.restype = i64
+        L.orc_gen_token_corpus.argtypes = [u64, i64, i64, i32, i32, i32, _c_u64p, _c_i64p, _c_i32p]
+        L.orc_bm25_stream_stats.restype = ctypes.c_int
+        L.orc_bm25_stream_stats.argtypes = [u64, i64, i64, i32, i32, i32, _c_u64p, _c_i64p, _c_i64p, _c_i64p]
+        L.orc_bm25_idf_from_df.restype = ctypes.c_double
+        L.orc_bm25_idf_from_df.argtypes = [i64, i32, _c_i64p, _c_i32p, i32, _c_f64p, _c_f64p]
+        L.orc_bm25_stream_scores.restype = ctypes.c_int
+        L.orc_bm25_stream_scores.argtypes = [u64, i64, i64, i32, i32, i32, _c_u64p, ctypes.c_double, _c_f64p, _c_i32p,
+                                             _c_i32p, i32, i32, _c_f64p]
+        _stream_ready = True
+    return L
+
+
+def gen_embeddings(seed: int, row_start: int, n_rows: int, dim: int = 1536, dup_per_mille: int = 0) -> np.ndarray:
+    """C twin of optimized_rag_b200.synthetic.embeddings (tests check the two agree bit for bit)."""
+    out = np.empty((n_rows, dim), dtype=np.float32)
+    _stream_lib().orc_gen_embeddings(seed, row_start, n_rows, dim, dup_per_mille, _p(out, _c_f32p))
+    return out
+
+
+def gen_token_corpus(seed: int, doc_start: int, n_docs: int, vocab: int, lmin: int, lmax: int, thresholds):
+    """C twin of optimized_rag_b200.synthetic.token_corpus -> (doc_off int64 [n+1], tokens int32 [total])."""
+    thr = np.ascontiguousarray(thresholds, dtype=np.uint64)
+    L = _stream_lib()
+    doc_off = np.zeros(n_docs + 1, dtype=np.int64)
+    up = ctypes.POINTER(ctypes.c_uint64)
+    total = L.orc_gen_token_corpus(seed, doc_start, n_docs, vocab, lmin, lmax, _p(thr, up), _p(doc_off, _c_i64p), None)
+    tok = np.empty(max(int(total), 1), dtype=np.int32)
+    L.orc_gen_token_corpus(seed, doc_start, n_docs, vocab, lmin, lmax, _p(thr, up), _p(doc_off, _c_i64p), _p(tok, _c_i32p))
+    return doc_off, tok[:int(total)]
+
+
+def cosine_topk_stream(queries, k: int, n_rows: int, row_start: int = 0, seed: int | None = None, dim: int = 1536,
+                       dup_per_mille: int = 0, corpus=None, neumaier: bool = True):
+    """Exact cosine top-k (reference arithmetic, rag/retrieval.py:362-371 + :320) of a query batch against the
+    synthetic rows [row_start, row_start + n_rows) REGENERATED from `seed` block by block (no corpus in memory), or
+    against the fp32 block `corpus` whose row r is global row row_start + r.  Queries run side by side (SIMD lanes);
+    every lane performs the scalar code's operations, so scores equal `cosine_scores` bit for bit.
+    Returns ids int64 [B, k] (global rows, -1 padded), scores float64 [B, k]."""
+    queries = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, dim)
+    B = queries.shape[0]
+    ids = np.full((B, k), -1, dtype=np.int64)
+    sc = np.zeros((B, k), dtype=np.float64)
+    cp = None
+    if corpus is not None:
+        corpus = np.ascontiguousarray(corpus, dtype=np.float32)
+        assert corpus.shape == (n_rows, dim)
+        cp = _p(corpus, _c_f32p)
+    elif seed is None:
+        raise ValueError("either a seed or an in-memory corpus block")
+    _stream_lib().orc_cosine_topk_stream(seed or 0, row_start, n_rows, dim, dup_per_mille, cp, _p(queries, _c_f32p), B,
+                                         k, int(neumaier), _p(ids, _c_i64p), _p(sc, _c_f64p))
+    return ids, sc
+
+
+class StreamedBM25:
+    """rank_bm25.BM25Okapi over the synthetic token corpus of `n_docs` docs, WITHOUT holding the corpus: the
+    statistics pass (BM25._initialize + BM25Okapi._calc_idf: df, first-seen order, avgdl, idf, epsilon floor) and the
+    scoring pass (get_scores, rag/retrieval.py:341-345) both regenerate the tokens doc by doc from the seed.  Same
+    arithmetic as `BM25Index`; tests/test_oracle_stream.py requires the two to agree bit for bit."""
+
+    def __init__(self, seed: int, n_docs: int, vocab: int, lmin: int, lmax: int, thresholds):
+        self.seed, self.n_docs, self.vocab, self.lmin, self.lmax = seed, int(n_docs), int(vocab), lmin, lmax
+        self.thr = np.ascontiguousarray(thresholds, dtype=np.uint64)
+        L = _stream_lib()
+        up = ctypes.POINTER(ctypes.c_uint64)
+        self.df = np.zeros(vocab, dtype=np.int64)
+        first = np.zeros(vocab, dtype=np.int64)
+        total = ctypes.c_int64(0)
+        L.orc_bm25_stream_stats(seed, 0, self.n_docs, vocab, lmin, lmax, _p(self.thr, up), _p(self.df, _c_i64p),
+                                _p(first, _c_i64p), ctypes.byref(total))
+        self.total_len = int(total.value)
+        self.avgdl = self.total_len / self.n_docs if self.n_docs else 0.0
+        seen = np.nonzero(self.df > 0)[0]
+        self.order = np.ascontiguousarray(seen[np.argsort(first[seen], kind="stable")], dtype=np.int32)
+        self.idf = np.zeros(vocab, dtype=np.float64)
+        avg = ctypes.c_double(0.0)
+        self.eps = float(L.orc_bm25_idf_from_df(self.n_docs, vocab, _p(self.df, _c_i64p), _p(self.order, _c_i32p),
+                                                len(self.order), _p(self.idf, _c_f64p), ctypes.byref(avg)))
+        self.average_idf = float(avg.value)
+
+    def scores_raw(self, q_terms, q_lens) -> np.ndarray:
+        """Raw float64 scores [B, n_docs] of a padded query batch (int32 [B, lq_max], lens int32 [B])."""
+        qt = np.ascontiguousarray(q_terms, dtype=np.int32)
+        ql = np.ascontiguousarray(q_lens, dtype=np.int32)
+        B, lq = qt.shape
+        raw = np.empty((B, max(self.n_docs, 1)), dtype=np.float64)
+        up = ctypes.POINTER(ctypes.c_uint64)
+        _stream_lib().orc_bm25_stream_scores(self.seed, 0, self.n_docs, self.vocab, self.lmin, self.lmax,
+                                             _p(self.thr, up), self.avgdl, _p(self.idf, _c_f64p), _p(qt, _c_i32p),
+                                             _p(ql, _c_i32p), B, lq, _p(raw, _c_f64p))
+        return raw[:, :self.n_docs]
+
+    def topk(self, q_terms, q_lens, k: int):
+        """(ids int64 [B,k], normalised scores float64 [B,k], divisors [B]): scores / max (rag/retrieval.py:343-345),
+        ranked by (score desc, id asc) as `sorted(..., reverse=True)` over index-ordered input does."""
+        raw = self.scores_raw(q_terms, q_lens)
+        B = raw.shape[0]
+        ids = np.full((B, k), -1, dtype=np.int64)
+        sc = np.zeros((B, k), dtype=np.float64)
+        mx = np.ones(B, dtype=np.float64)
+        norm = np.empty(self.n_docs, dtype=np.float64)
+        for b in range(B):
+            row = np.ascontiguousarray(raw[b])
+            mx[b] = lib().orc_bm25_normalize(_p(row, _c_f64p), self.n_docs, _p(norm, _c_f64p)) if self.n_docs else 1.0
+            i, v = topk(norm, k)
+            ids[b, :len(i)], sc[b, :len(v)] = i, v
+        return ids, sc, mx

@@ -366,4 +366,373 @@ int64_t orc_pairwise_candidates(const float *emb, int64_t m, int d, const int32_
     return cnt;
 }
 
+
+/* ========================================================================= */
+/* Streamed oracle for the BASELINE-size parity gates (SURVEY.md §8d "Parity  */
+/* gates": the streamed oracle at 10M rows on a query subset).  The 10M x 1536 */
+/* fp32 corpus (61.4 GB) and the 2e9-token corpus do not fit host memory, so    */
+/* the functions below REGENERATE the synthetic inputs block by block from the  */
+/* seeds (same counter-based hashes as optimized_rag_b200/synthetic.py and      */
+/* csrc/gen.cu; tests/test_oracle_stream.py checks them against the numpy       */
+/* generators) and apply exactly the arithmetic of the functions above:         */
+/*   cosine  rag/retrieval.py:362-371 per (query, row), top-k by               */
+/*           (score desc, id asc) as rag/retrieval.py:320                      */
+/*   BM25    rank_bm25 0.2.2 BM25Okapi._initialize/_calc_idf/get_scores +      */
+/*           rag/retrieval.py:324-347                                          */
+/* Queries of a batch are evaluated side by side (one SIMD lane per query): each */
+/* lane performs the same sequence of IEEE-754 binary64 operations as the        */
+/* scalar code, so the results are bit-identical to orc_cosine_scores.           */
+/* ========================================================================= */
+
+static inline uint64_t orc_mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+#define ORC_K_ROW 0xD1B54A32D192ED03ull
+#define ORC_K_DOC 0x9FB21C651E98DF25ull
+#define ORC_K_DUP 0xA24BAED4963EE407ull
+
+static inline uint64_t orc_row_key(uint64_t seed, uint64_t row) { return orc_mix64(seed ^ (row * ORC_K_ROW)); }
+
+/* synthetic.source_rows: the row whose values row r carries */
+static inline uint64_t orc_source_row(uint64_t seed, uint64_t row, int dup_per_mille)
+{
+    if (dup_per_mille <= 0 || row == 0) return row;
+    uint64_t h = orc_mix64(seed ^ ORC_K_DUP ^ (row * ORC_K_DOC));
+    if ((h % 1000ull) < (uint64_t)dup_per_mille) return orc_mix64(h) % row;
+    return row;
+}
+
+/* synthetic.embeddings: one row */
+static void orc_gen_row(uint64_t seed, uint64_t row, int dim, int dup_per_mille, float *out)
+{
+    uint64_t key = orc_row_key(seed, orc_source_row(seed, row, dup_per_mille));
+    for (int c = 0; c < dim; ++c) {
+        uint64_t h = orc_mix64(key + (uint64_t)c);
+        int64_t v = (int64_t)(h >> 40) - ((int64_t)1 << 23);
+        out[c] = (float)v * 0x1p-28f;
+    }
+}
+
+void orc_gen_embeddings(uint64_t seed, int64_t row_start, int64_t n_rows, int dim, int dup_per_mille, float *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < n_rows; ++r) orc_gen_row(seed, (uint64_t)(row_start + r), dim, dup_per_mille, out + r * dim);
+}
+
+/* Dot products of one corpus row with ORC_QB queries at once (queries transposed: qt[i * ORC_QB + j]).
+ * Per lane j exactly sum_prod(query_j, row): the argument order of rag/retrieval.py:252-256 (query first) --
+ * products of two widened fp32 values are exact, so the order of the factors does not matter. */
+#define ORC_QB 16
+__attribute__((target_clones("avx512f", "avx2", "default")))
+static void orc_dot_block(const float *row, const double *qt, int d, int neumaier, double *out)
+{
+    double s[ORC_QB], c[ORC_QB];
+    const double a0 = (double)row[0];
+    for (int j = 0; j < ORC_QB; ++j) { s[j] = 0.0 + a0 * qt[j]; c[j] = 0.0; }
+    if (!neumaier) {
+        for (int i = 1; i < d; ++i) {
+            const double a = (double)row[i];
+            const double *q = qt + (size_t)i * ORC_QB;
+            for (int j = 0; j < ORC_QB; ++j) s[j] = s[j] + a * q[j];
+        }
+        for (int j = 0; j < ORC_QB; ++j) out[j] = s[j];
+        return;
+    }
+    for (int i = 1; i < d; ++i) {
+        const double a = (double)row[i];
+        const double *q = qt + (size_t)i * ORC_QB;
+#pragma omp simd
+        for (int j = 0; j < ORC_QB; ++j) {
+            const double x = a * q[j];
+            const double t = s[j] + x;
+            const double big = fabs(s[j]) >= fabs(x) ? s[j] : x;
+            const double small = fabs(s[j]) >= fabs(x) ? x : s[j];
+            c[j] += (big - t) + small;
+            s[j] = t;
+        }
+    }
+    for (int j = 0; j < ORC_QB; ++j) {
+        double r = s[j];
+        if (c[j] != 0.0 && isfinite(c[j])) r += c[j];
+        out[j] = r;
+    }
+}
+
+/* (score desc, id asc) insertion into a k-long list */
+static inline void orc_topk_insert(double s, int64_t id, int k, int *cnt, double *sc, int64_t *ids)
+{
+    if (*cnt == k && !(s > sc[k - 1] || (s == sc[k - 1] && id < ids[k - 1]))) return;
+    int pos = (*cnt < k) ? *cnt : k - 1;
+    while (pos > 0 && (s > sc[pos - 1] || (s == sc[pos - 1] && id < ids[pos - 1]))) {
+        sc[pos] = sc[pos - 1];
+        ids[pos] = ids[pos - 1];
+        --pos;
+    }
+    sc[pos] = s;
+    ids[pos] = id;
+    if (*cnt < k) ++*cnt;
+}
+
+/* Exact cosine top-k of `nq` queries against the synthetic rows [row_start, row_start + n_rows) regenerated from
+ * `seed` (or, with corpus != NULL, against that in-memory fp32 block: row r of it is global row row_start + r).
+ * out_ids/out_scores [nq, k] (-1 / 0.0 padded); ids are global rows.  Returns 0. */
+int orc_cosine_topk_stream(uint64_t seed, int64_t row_start, int64_t n_rows, int dim, int dup_per_mille,
+                           const float *corpus, const float *queries, int nq, int k, int neumaier,
+                           int64_t *out_ids, double *out_scores)
+{
+    const int nqb = (nq + ORC_QB - 1) / ORC_QB;
+    double *qt = (double *)calloc((size_t)nqb * dim * ORC_QB, sizeof(double));
+    double *m1 = (double *)calloc((size_t)nqb * ORC_QB, sizeof(double));
+    for (int q = 0; q < nq; ++q) {
+        for (int i = 0; i < dim; ++i)
+            qt[((size_t)(q / ORC_QB) * dim + i) * ORC_QB + (q % ORC_QB)] = (double)queries[(size_t)q * dim + i];
+        m1[q] = sqrt(sum_prod(queries + (size_t)q * dim, queries + (size_t)q * dim, dim, neumaier));
+    }
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    int *cnts = (int *)calloc((size_t)nthreads * nq, sizeof(int));
+    double *tsc = (double *)malloc((size_t)nthreads * nq * k * sizeof(double));
+    int64_t *tid = (int64_t *)malloc((size_t)nthreads * nq * k * sizeof(int64_t));
+#pragma omp parallel
+    {
+        int th = 0;
+#ifdef _OPENMP
+        th = omp_get_thread_num();
+#endif
+        float *rowbuf = (float *)malloc((size_t)dim * sizeof(float));
+        double dots[ORC_QB];
+        int *cnt = cnts + (size_t)th * nq;
+        double *sc = tsc + (size_t)th * nq * k;
+        int64_t *ids = tid + (size_t)th * nq * k;
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t r = 0; r < n_rows; ++r) {
+            const float *row;
+            if (corpus) row = corpus + (size_t)r * dim;
+            else { orc_gen_row(seed, (uint64_t)(row_start + r), dim, dup_per_mille, rowbuf); row = rowbuf; }
+            const double m2 = sqrt(sum_prod(row, row, dim, neumaier));
+            for (int b = 0; b < nqb; ++b) {
+                orc_dot_block(row, qt + (size_t)b * dim * ORC_QB, dim, neumaier, dots);
+                for (int j = 0; j < ORC_QB; ++j) {
+                    const int q = b * ORC_QB + j;
+                    if (q >= nq) break;
+                    const double s = (m1[q] == 0.0 || m2 == 0.0) ? 0.0 : dots[j] / (m1[q] * m2);
+                    orc_topk_insert(s, row_start + r, k, cnt + q, sc + (size_t)q * k, ids + (size_t)q * k);
+                }
+            }
+        }
+        free(rowbuf);
+    }
+    for (int q = 0; q < nq; ++q) {
+        int cnt = 0;
+        double *sc = out_scores + (size_t)q * k;
+        int64_t *ids = out_ids + (size_t)q * k;
+        for (int i = 0; i < k; ++i) { sc[i] = 0.0; ids[i] = -1; }
+        for (int th = 0; th < nthreads; ++th)
+            for (int i = 0; i < cnts[(size_t)th * nq + q]; ++i)
+                orc_topk_insert(tsc[((size_t)th * nq + q) * k + i], tid[((size_t)th * nq + q) * k + i], k, &cnt, sc, ids);
+    }
+    free(qt); free(m1); free(cnts); free(tsc); free(tid);
+    return 0;
+}
+
+/* ---- token corpus (synthetic.doc_lengths / token_corpus) ---- */
+static inline int32_t orc_doc_len(uint64_t seed, uint64_t doc, int lmin, int lmax)
+{
+    uint64_t h = orc_mix64(seed ^ (doc * ORC_K_DOC));
+    return (int32_t)(lmin + (int64_t)(h % (uint64_t)(lmax - lmin + 1)));
+}
+
+/* token rank = number of thresholds <= u (numpy searchsorted side='right'), clipped to vocab - 1.
+ * `coarse` [4097]: coarse[b] = searchsorted(thr, b << 51, side='right') narrows the binary search. */
+static inline int32_t orc_token_of(uint64_t u, const uint64_t *thr, int vocab, const int32_t *coarse)
+{
+    const uint32_t b = (uint32_t)(u >> 51);
+    int lo = coarse[b], hi = coarse[b + 1];  /* answer in [lo, hi] */
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (thr[mid] <= u) lo = mid + 1; else hi = mid;
+    }
+    return lo < vocab - 1 ? lo : vocab - 1;
+}
+
+static int32_t *orc_coarse_table(const uint64_t *thr, int vocab)
+{
+    int32_t *coarse = (int32_t *)malloc(4098 * sizeof(int32_t));
+    int pos = 0;
+    for (uint32_t b = 0; b <= 4096; ++b) {
+        const uint64_t u = (uint64_t)b << 51;  /* b = 4096 -> 2^63: one past the largest u */
+        while (pos < vocab && thr[pos] <= u) ++pos;
+        coarse[b] = pos;
+    }
+    coarse[4097] = vocab;
+    return coarse;
+}
+
+static inline void orc_gen_doc_tokens(uint64_t seed, uint64_t doc, int len, const uint64_t *thr, int vocab,
+                                      const int32_t *coarse, int32_t *out)
+{
+    const uint64_t key = orc_row_key(seed + 1, doc);
+    for (int j = 0; j < len; ++j) out[j] = orc_token_of(orc_mix64(key + (uint64_t)j) >> 1, thr, vocab, coarse);
+}
+
+/* synthetic.token_corpus into caller-provided arrays (doc_off [n+1], tokens [total]); tokens may be NULL to get
+ * the offsets only.  Returns the total number of tokens. */
+int64_t orc_gen_token_corpus(uint64_t seed, int64_t doc_start, int64_t n_docs, int vocab, int lmin, int lmax,
+                             const uint64_t *thr, int64_t *doc_off, int32_t *tokens)
+{
+    doc_off[0] = 0;
+    for (int64_t d = 0; d < n_docs; ++d)
+        doc_off[d + 1] = doc_off[d] + orc_doc_len(seed, (uint64_t)(doc_start + d), lmin, lmax);
+    if (tokens) {
+        int32_t *coarse = orc_coarse_table(thr, vocab);
+#pragma omp parallel for schedule(dynamic, 1024)
+        for (int64_t d = 0; d < n_docs; ++d)
+            orc_gen_doc_tokens(seed, (uint64_t)(doc_start + d), (int)(doc_off[d + 1] - doc_off[d]), thr, vocab, coarse,
+                               tokens + doc_off[d]);
+        free(coarse);
+    }
+    return doc_off[n_docs];
+}
+
+/* BM25._initialize over the regenerated corpus: df[V], first_pos[V] (global token position of the first occurrence,
+ * INT64_MAX if unseen: ascending first_pos == dict insertion order of `nd`), total token count. */
+int orc_bm25_stream_stats(uint64_t seed, int64_t doc_start, int64_t n_docs, int vocab, int lmin, int lmax,
+                          const uint64_t *thr, int64_t *df, int64_t *first_pos, int64_t *total_len)
+{
+    int32_t *coarse = orc_coarse_table(thr, vocab);
+    const int64_t BLK = 4096;
+    const int64_t n_blk = (n_docs + BLK - 1) / BLK;
+    /* token offset of every block (doc lengths are cheap to recompute) */
+    int64_t *blk_off = (int64_t *)malloc((size_t)(n_blk + 1) * sizeof(int64_t));
+    blk_off[0] = 0;
+    for (int64_t b = 0; b < n_blk; ++b) {
+        int64_t s = 0;
+        const int64_t d1 = (b + 1) * BLK < n_docs ? (b + 1) * BLK : n_docs;
+        for (int64_t d = b * BLK; d < d1; ++d) s += orc_doc_len(seed, (uint64_t)(doc_start + d), lmin, lmax);
+        blk_off[b + 1] = blk_off[b] + s;
+    }
+    *total_len = blk_off[n_blk];
+    for (int t = 0; t < vocab; ++t) { df[t] = 0; first_pos[t] = INT64_MAX; }
+#pragma omp parallel
+    {
+        int64_t *ldf = (int64_t *)calloc((size_t)vocab, sizeof(int64_t));
+        int64_t *lfirst = (int64_t *)malloc((size_t)vocab * sizeof(int64_t));
+        int64_t *last_doc = (int64_t *)malloc((size_t)vocab * sizeof(int64_t));
+        int32_t *tok = (int32_t *)malloc((size_t)(lmax > 0 ? lmax : 1) * sizeof(int32_t));
+        for (int t = 0; t < vocab; ++t) { lfirst[t] = INT64_MAX; last_doc[t] = -1; }
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t b = 0; b < n_blk; ++b) {
+            int64_t pos = blk_off[b];
+            const int64_t d1 = (b + 1) * BLK < n_docs ? (b + 1) * BLK : n_docs;
+            for (int64_t d = b * BLK; d < d1; ++d) {
+                const int len = orc_doc_len(seed, (uint64_t)(doc_start + d), lmin, lmax);
+                orc_gen_doc_tokens(seed, (uint64_t)(doc_start + d), len, thr, vocab, coarse, tok);
+                for (int j = 0; j < len; ++j) {
+                    const int32_t t = tok[j];
+                    if (last_doc[t] != d) { last_doc[t] = d; ldf[t] += 1; }
+                    if (pos + j < lfirst[t]) lfirst[t] = pos + j;
+                }
+                pos += len;
+            }
+        }
+#pragma omp critical
+        for (int t = 0; t < vocab; ++t) {
+            df[t] += ldf[t];
+            if (lfirst[t] < first_pos[t]) first_pos[t] = lfirst[t];
+        }
+        free(ldf); free(lfirst); free(last_doc); free(tok);
+    }
+    free(coarse); free(blk_off);
+    return 0;
+}
+
+/* BM25Okapi._calc_idf from (df, first-seen order): same arithmetic as orc_bm25_build.  order [n_seen] = term ids in
+ * dict insertion order.  Writes idf [vocab] (0 for unseen terms); returns eps, *average_idf. */
+double orc_bm25_idf_from_df(int64_t n_docs, int vocab, const int64_t *df, const int32_t *order, int n_seen,
+                            double *idf, double *average_idf)
+{
+    for (int t = 0; t < vocab; ++t) idf[t] = 0.0;
+    double idf_sum = 0.0;
+    for (int i = 0; i < n_seen; ++i) {
+        const int32_t t = order[i];
+        const double freq = (double)df[t];
+        const double v = log((double)n_docs - freq + 0.5) - log(freq + 0.5);
+        idf[t] = v;
+        idf_sum += v;
+    }
+    const double avg = n_seen > 0 ? idf_sum / (double)n_seen : 0.0;
+    const double eps = 0.25 * avg;
+    for (int i = 0; i < n_seen; ++i)
+        if (idf[order[i]] < 0.0) idf[order[i]] = eps;
+    if (average_idf) *average_idf = avg;
+    return eps;
+}
+
+/* BM25Okapi.get_scores for `nq` queries over the regenerated docs [doc_start, doc_start + n_docs): raw float64
+ * scores raw[q * n_docs + d], same per-document arithmetic and query-token order as orc_bm25_scores_raw.
+ * q_terms int32 [nq, lq_max] (entries outside [0, vocab) are OOV), q_lens [nq]; avgdl / idf are the GLOBAL values. */
+int orc_bm25_stream_scores(uint64_t seed, int64_t doc_start, int64_t n_docs, int vocab, int lmin, int lmax,
+                           const uint64_t *thr, double avgdl, const double *idf, const int32_t *q_terms,
+                           const int32_t *q_lens, int nq, int lq_max, double *raw)
+{
+    const double k1 = 1.5, b = 0.75;
+    const double one_minus_b = 1 - b;
+    int32_t *coarse = orc_coarse_table(thr, vocab);
+    /* slot of every term some query uses */
+    int32_t *slot_of = (int32_t *)malloc((size_t)vocab * sizeof(int32_t));
+    for (int t = 0; t < vocab; ++t) slot_of[t] = -1;
+    int n_slots = 0;
+    for (int q = 0; q < nq; ++q)
+        for (int i = 0; i < q_lens[q] && i < lq_max; ++i) {
+            const int32_t t = q_terms[(size_t)q * lq_max + i];
+            if (t >= 0 && t < vocab && slot_of[t] < 0) slot_of[t] = n_slots++;
+        }
+#pragma omp parallel
+    {
+        int32_t *tok = (int32_t *)malloc((size_t)(lmax > 0 ? lmax : 1) * sizeof(int32_t));
+        int32_t *tf = (int32_t *)calloc((size_t)(n_slots > 0 ? n_slots : 1), sizeof(int32_t));
+#pragma omp for schedule(dynamic, 1024)
+        for (int64_t d = 0; d < n_docs; ++d) {
+            const int len = orc_doc_len(seed, (uint64_t)(doc_start + d), lmin, lmax);
+            orc_gen_doc_tokens(seed, (uint64_t)(doc_start + d), len, thr, vocab, coarse, tok);
+            for (int s = 0; s < n_slots; ++s) tf[s] = 0;
+            for (int j = 0; j < len; ++j) {
+                const int32_t s = slot_of[tok[j]];
+                if (s >= 0) tf[s] += 1;
+            }
+            for (int q = 0; q < nq; ++q) {
+                double score = 0.0;
+                for (int i = 0; i < q_lens[q] && i < lq_max; ++i) {
+                    const int32_t t = q_terms[(size_t)q * lq_max + i];
+                    if (t < 0 || t >= vocab) continue;
+                    const double w = idf[t];
+                    if (w == 0.0) continue;
+                    const int32_t f = tf[slot_of[t]];
+                    if (f == 0) continue;  /* tf == 0 adds +-0.0: a no-op */
+                    const double tfd = (double)f;
+                    const double t1 = b * (double)len;
+                    const double t2 = t1 / avgdl;
+                    const double t3 = one_minus_b + t2;
+                    const double t4 = k1 * t3;
+                    const double den = tfd + t4;
+                    const double num = tfd * (k1 + 1);
+                    const double r = num / den;
+                    const double c = w * r;
+                    score = score + c;
+                }
+                raw[(size_t)q * n_docs + d] = score;
+            }
+        }
+        free(tok); free(tf);
+    }
+    free(coarse); free(slot_of);
+    return 0;
+}
+
 int orc_version(void) { return 1; }
