@@ -1,17 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json metric: hybrid top-10 queries/sec at 10M x 1536 chunks on 1/2/4/8 B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 3|2|4|pairwise] [--batch B]
     torchrun ... bench.py --gpus N ...        (one rank per GPU, corpus row-sharded)
 
-A "step" is one hybrid retrieval (exact cosine top-10 + BM25 top-10 + RRF) of a batch of 256
-queries against the whole synthetic corpus (10M chunks x 1536-d fp32 + Zipf token corpus, V=50k).
-`value` = whole-job queries/s with inputs resident in HBM; `e2e` = the same through the public
-search call with HOST query buffers (H2D + D2H inside the timed region).  One JSON line on rank 0.
+Default (--config 3, the configuration BASELINE's metric is quoted on, sized for N GPUs): a "step" is one hybrid
+retrieval (exact cosine top-10 + BM25 top-10 + RRF) of a batch of 256 queries against the whole synthetic corpus
+(10M chunks x 1536-d fp32 + Zipf token corpus, V=50k).  `value` = whole-job queries/s with inputs resident in HBM;
+`e2e` = the same through the public search call with HOST query buffers (H2D + D2H inside the timed region).
+The other BASELINE configs print the same contract line for their own workload:
+    --config 2         1M x 1536 exact cosine top-10, batch 256 (one GPU)
+    --config 4         BM25-only over the 10M-doc Zipf corpus, batch 1024
+    --config pairwise  consistency-checker claim pairs, 65536 x 1536, threshold 0.85 (config 5, one GPU)
+`--batch B` changes the query batch (SURVEY.md §8d sweep B in {1, 16, 64, 256, 1024}).  One JSON line on rank 0.
+
+Outside the timed regions the results of the last step are compared with the CPU oracle at FULL corpus size on a
+query subset (`verified_against_oracle`); the time the oracle takes for that is the reported `cpu_baseline`.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -25,11 +34,18 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "hybrid_top10_queries_per_sec_10Mx1536"
 UNIT = "queries/s"
 DIM = 1536
 VOCAB = 50000
 TOPK = 10
+LMIN, LMAX = 100, 300
+
+CONFIGS = {
+    "3": {"metric": "hybrid_top10_queries_per_sec_10Mx1536", "rows": 10_000_000, "batch": 256},
+    "2": {"metric": "cosine_top10_queries_per_sec_1Mx1536", "rows": 1_000_000, "batch": 256},
+    "4": {"metric": "bm25_top10_queries_per_sec_10M_docs", "rows": 10_000_000, "batch": 1024},
+    "pairwise": {"metric": "consistency_claim_pairs_per_sec_64kx1536", "rows": 65536, "batch": 0},
+}
 
 
 def peaks():
@@ -47,74 +63,122 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--rows", type=int, default=int(os.environ.get("ORAG_BENCH_ROWS", 10_000_000)))
-    ap.add_argument("--queries", type=int, default=256)
+    ap.add_argument("--config", default="3", choices=list(CONFIGS))
+    ap.add_argument("--rows", type=int, default=None)
+    ap.add_argument("--batch", "--queries", dest="batch", type=int, default=None)
     ap.add_argument("--mode", default=os.environ.get("ORAG_BENCH_MODE", "f16"), choices=["tf32", "bf16", "f16"])
     ap.add_argument("--tile-docs", type=int, default=2048)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
-    ap.add_argument("--ref-sample-rows", type=int, default=20_000)
-    ap.add_argument("--ref-sample-queries", type=int, default=4)
-    return ap.parse_args()
+    ap.add_argument("--verify-queries", type=int, default=None,
+                    help="queries compared with the full-size CPU oracle after the timed loops (0 = skip); default 32 "
+                         "on one GPU, 8 under torchrun")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="alias of --verify-queries 0")
+    ap.add_argument("--ref-sample-rows", type=int, default=None)
+    ap.add_argument("--ref-sample-queries", type=int, default=16)
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.rows is None:
+        args.rows = int(os.environ.get("ORAG_BENCH_ROWS", cfg["rows"]))
+    if args.batch is None:
+        args.batch = cfg["batch"]
+    args.metric = cfg["metric"]
+    if args.no_cpu_baseline:
+        args.verify_queries = 0
+    return args
 
 
 def workload_config(args, extra=None):
-    cfg = {"workload": f"{args.rows} chunks x {DIM}-d fp32 hybrid (exact cosine + BM25 + RRF) top-{TOPK}, "
-                       f"query batch {args.queries}, Zipf(s=1) token corpus V={VOCAB} L~U[100,300]",
-           "rows": args.rows, "dim": DIM, "query_batch": args.queries, "top_k": TOPK, "vocab": VOCAB,
-           "l2": "inputs larger than L2 (corpus streamed from HBM every step)"}
+    if args.config == "3":
+        what = (f"{args.rows} chunks x {DIM}-d fp32 hybrid (exact cosine + BM25 + RRF) top-{TOPK}, query batch "
+                f"{args.batch}, Zipf(s=1) token corpus V={VOCAB} L~U[{LMIN},{LMAX}]")
+    elif args.config == "2":
+        what = f"{args.rows} chunks x {DIM}-d fp32 exact cosine top-{TOPK}, query batch {args.batch}"
+    elif args.config == "4":
+        what = (f"BM25-only top-{TOPK} over {args.rows} chunks, Zipf(s=1) token corpus V={VOCAB} L~U[{LMIN},{LMAX}], "
+                f"query batch {args.batch}")
+    else:
+        what = (f"consistency-checker claim pairs: all i<j of {args.rows} claims x {DIM}-d with doc_idx = i // 16 and "
+                f"float64 cosine >= 0.85 (rag/consistency_checker.py:169-189)")
+    cfg = {"workload": what, "baseline_config": args.config, "rows": args.rows, "dim": DIM, "query_batch": args.batch,
+           "top_k": TOPK, "vocab": VOCAB,
+           "l2": "inputs larger than L2 (corpus / postings streamed from HBM every step)"}
     if extra:
         cfg.update(extra)
     return cfg
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_hybrid_sample(oracle, corpus, bm25, queries, qtok, qlen, k):
-    """One pass of the oracle's hybrid path over a row sample; returns seconds."""
-    t0 = time.perf_counter()
-    for b in range(len(queries)):
-        ci, _ = oracle.topk(oracle.cosine_scores(corpus, queries[b]), k)
-        bi, _, _ = bm25.topk(qtok[b, :qlen[b]], k)
-        oracle.rrf_fuse([ci, bi], 60, k)
-    return time.perf_counter() - t0
-
-
 def run_reference(args):
-    """The reference's CPU path (oracle port of rag/retrieval.py:362-371, 324-347 and rag/reranker.py:224-271;
-    the Python reference itself cannot travel to the GPU box) on the host cores, on a bounded row sample,
+    """The reference's CPU path (oracle port of rag/retrieval.py:362-371, 324-347 and rag/reranker.py:224-271; the
+    Python reference itself cannot travel to the GPU box) on all host cores.  Each step is a bounded sample of the
+    workload -- `--ref-sample-queries` queries against the first rows/40 rows and docs, regenerated from the seeds --
     scaled linearly in N (every piece is O(N) per query)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
+    from oracle import scale_check
     from optimized_rag_b200 import synthetic as syn
     cores = os.cpu_count() or 1
     oracle.build()
     oracle.set_threads(cores)  # torchrun exports OMP_NUM_THREADS=1: the baseline is "all host cores"
-    S, Bs = args.ref_sample_rows, args.ref_sample_queries
+    S = args.ref_sample_rows or max(args.rows // 40, 1000)
+    S = min(S, args.rows)
+    Bs = args.ref_sample_queries
     thr = syn.zipf_thresholds(VOCAB)
-    corpus = syn.embeddings(syn.SEED_CORPUS, 0, S, DIM)
-    queries = syn.query_embeddings(Bs, S, DIM)
-    doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, S, VOCAB, 100, 300, thr)
-    qtok, qlen = syn.keyword_queries(Bs, VOCAB, thresholds=thr)
-    bm25 = oracle.BM25Index(doc_off, tok, VOCAB)
+    if args.config == "pairwise":
+        emb = pairwise_claims_host(S)
+        doc = (np.arange(S) // 16).astype(np.int32)
+
+        def step():
+            t0 = time.perf_counter()
+            oracle.pairwise_candidates(emb, doc, 0.85)
+            return time.perf_counter() - t0
+        unit, per_step = "pairs/s", S * (S - 1) / 2
+        scale = (args.rows * (args.rows - 1) / 2) / per_step
+        sample = f"all pairs of the first {S} claims per step (O(M^2): scaled x{scale:.0f} in time to {args.rows} claims)"
+        value_of = lambda t_total, steps: (args.rows * (args.rows - 1) / 2) / (t_total / steps * scale)
+    else:
+        nq_total = max(args.batch, Bs)
+        q = syn.query_embeddings(nq_total, args.rows, DIM)[:Bs] if args.config in ("3", "2") else None
+        qt, ql = syn.keyword_queries(nq_total, VOCAB, thresholds=thr)
+        qt, ql = qt[:Bs], ql[:Bs]
+        bm25 = oracle.StreamedBM25(syn.SEED_TOKENS, S, VOCAB, LMIN, LMAX, thr) if args.config in ("3", "4") else None
+
+        def step():
+            t0 = time.perf_counter()
+            scale_check.reference_lists(S, DIM, q, qt, ql, TOPK, seed_corpus=syn.SEED_CORPUS, bm25=bm25,
+                                        want_cosine=args.config in ("3", "2"))
+            return time.perf_counter() - t0
+        unit = UNIT
+        scale = args.rows / S
+        sample = (f"{Bs} queries x first {S} rows/docs per step (oracle: cosine fp64 Neumaier + BM25 get_scores + RRF "
+                  f"over inputs regenerated from the seeds), scaled x{scale:.0f} to {args.rows} rows (O(N) per query); "
+                  f"BM25Okapi rebuild per call (rag/retrieval.py:338) NOT charged")
+        value_of = lambda t_total, steps: (Bs * steps) / (t_total * scale)
     for _ in range(args.warmup):
-        cpu_hybrid_sample(oracle, corpus, bm25, queries, qtok, qlen, TOPK)
-    times = [cpu_hybrid_sample(oracle, corpus, bm25, queries, qtok, qlen, TOPK) for _ in range(args.steps)]
-    t = sum(times)
-    scale = args.rows / S
-    value = (Bs * args.steps) / (t * scale)
-    sample = (f"{Bs} queries x {S} rows per step (cosine fp64 Neumaier + BM25 over a prebuilt index + RRF), "
-              f"scaled x{scale:.0f} to {args.rows} rows (O(N) per query); BM25Okapi rebuild per call "
-              f"(rag/retrieval.py:338) NOT charged")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        step()
+    t = sum(step() for _ in range(args.steps))
+    value = value_of(t, args.steps)
+    line = {"impl": "reference", "metric": args.metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(args.steps, 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def pairwise_claims_host(m: int) -> np.ndarray:
+    """Config-5 claims on the host (numpy twin of `pairwise_claims`): synthetic rows, every 64th one a noisy copy of
+    another (cosine ~0.85-0.97 with its source)."""
+    from optimized_rag_b200 import synthetic as syn
+    emb = syn.embeddings(syn.SEED_CORPUS, 0, m, DIM)
+    dst = np.arange(0, m, 64)
+    src = (dst * 7919 + 13) % m
+    w = np.float32(0.25) + np.float32(0.4) * ((dst * 2654435761 % 1000).astype(np.float32) / np.float32(1000))
+    emb[dst] = emb[src] + w[:, None] * emb[dst]
+    return emb
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -169,6 +233,10 @@ class ClockSampler:
                 rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
+        try:
+            self.path.unlink()
+        except OSError:
+            pass
         inside = [r for r in rows if any(a <= r[0] <= b for a, b in self.windows)]
         note = "inside the timed regions"
         if not inside and rows and self.windows:  # run shorter than the polling period: nearest samples under the same load
@@ -182,255 +250,448 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ native arm
-def run_native(args):
-    import torch
-    import torch.distributed as dist
+class Harness:
+    """Process-group set-up, barriers, the device-timed loop, the end-to-end loop, clocks: shared by all configs."""
 
-    from optimized_rag_b200 import _ffi, engine, synthetic as syn
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from optimized_rag_b200 import _ffi
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py (native arm) needs a GPU: there is no CPU fallback for the retrieval hot path")
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.L = _ffi.lib()
+        uuid = str(torch.cuda.get_device_properties(self.dev).uuid)
+        self.sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        self.warmup = max(args.warmup, 3)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms: float) -> float:
+        if self.world == 1:
+            return ms
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def device_timed(self, step):
+        """W warm-up steps, then exactly K steps between two events (barrier + synchronize on both sides, max over
+        ranks).  `step()` enqueues one step without synchronising with the host.  Returns (total ms, launches, brackets)
+        where brackets = per-step CUDA-event durations of the two dominant kernels (library hooks)."""
+        torch, L, args = self.torch, self.L, self.args
+        if self.rank == 0:  # one poller per box: nvidia-smi queries take driver locks that kernel launches also need
+            self.sampler.start()
+        for _ in range(self.warmup):
+            step()
+        self.barrier()
+        L.orag_profile_enable(1)
+        launches0 = int(L.orag_launch_count())
+        self.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        self.barrier()
+        w1 = time.time()
+        self.sampler.window(w0, w1)
+        dev_ms = self.max_over_ranks(ev0.elapsed_time(ev1))
+        launches = int(L.orag_launch_count()) - launches0
+        brackets = []
+        buf = (ctypes.c_float * 256)()
+        for slot in (0, 1):
+            n = int(L.orag_profile_read_all(slot, buf, 256))
+            brackets.append([float(buf[i]) for i in range(max(n, 0))])
+        L.orag_profile_enable(0)
+        if dev_ms < 150.0:
+            # the timed loop is shorter than a few polling periods (small shards): keep the same back-to-back load
+            # running, untimed, for ~0.2 s so that the poller sees it.  The step count derives from dev_ms, which is
+            # identical on every rank (max over ranks), so all ranks enter the same number of collectives.
+            n_probe = int(200.0 / max(dev_ms / args.steps, 1e-3)) + 1
+            p0 = time.time()
+            for _ in range(n_probe):
+                step()
+            torch.cuda.synchronize()
+            self.sampler.window(p0, time.time())
+            self.barrier()
+        # the clocks line describes the device-timed loop: stop polling before the end-to-end loop, where every step
+        # synchronises with the host and a poller taking driver locks would be measured with it
+        self.clocks = self.sampler.stop()
+        return dev_ms, launches, brackets
+
+    def e2e_timed(self, step_with_copies):
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(self.args.steps):
+            step_with_copies()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+    def finish(self, line, closer=None):
+        if self.rank == 0:
+            print(json.dumps(line), flush=True)
+        if self.world > 1:
+            if closer:
+                closer()  # collective: nobody frees a buffer a peer still has mapped
+            self.dist.destroy_process_group()
+
+
+def bracket_stats(ms_list, per_step):
+    """Per-step durations of a kernel that launches `per_step` times per step -> (mean, min, n_steps) in ms."""
+    xs = [x for x in ms_list if x >= 0]
+    if not xs:
+        return None, None, 0
+    if per_step > 1:
+        xs = [sum(xs[i:i + per_step]) for i in range(0, len(xs) - per_step + 1, per_step)]
+    return statistics.mean(xs), min(xs), len(xs)
+
+
+def tensor_roofline(flops_per_step, t_mean_ms, t_min_ms, n, pk, kernel, launches_per_step, traffic=None, extra=None):
+    ach = flops_per_step / (t_mean_ms * 1e-3) / 1e12
+    r = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+         "traffic": traffic, "frac_sustained": ach / pk["tf_sustained"], "frac_burst": ach / pk["tf_burst"],
+         "peak_burst": pk["tf_burst"],
+         "peak_kind": "bf16 dense, measured: sustained (back-to-back 4 s) is `peak`, best-of-10 burst is `peak_burst`",
+         "kernel": kernel, "peak_source": pk["source"], "launch_ms": t_mean_ms / launches_per_step,
+         "launch_ms_min": t_min_ms / launches_per_step, "launches_per_step": launches_per_step, "samples": n,
+         "timing": "CUDA events on the launching stream around every launch of the timed loop (mean; min alongside)"}
+    if extra:
+        r.update(extra)
+    return r
+
+
+def hbm_roofline(bytes_per_step, t_mean_ms, t_min_ms, n, pk, kernel, launches_per_step, what, traffic=None):
+    ach = bytes_per_step / (t_mean_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+            "traffic": traffic, "bytes": what, "algorithmic_bytes": bytes_per_step, "kernel": kernel,
+            "peak_source": pk["source"], "launch_ms": t_mean_ms / launches_per_step,
+            "launch_ms_min": t_min_ms / launches_per_step, "launches_per_step": launches_per_step, "samples": n,
+            "timing": "CUDA events on the launching stream around every launch of the timed loop (mean; min alongside)"}
+
+
+def traffic_for(key, rows_per_gpu, batch):
+    """ncu-measured DRAM bytes per launch of a dominant kernel, only if the capture was of this launch shape."""
+    tp = ROOT / "profiles" / "traffic.json"
+    tj = json.loads(tp.read_text()) if tp.exists() else {}
+    cap = tj.get("captured_at", {})
+    if cap.get("rows_per_gpu") == rows_per_gpu and cap.get("queries") == batch:
+        return tj.get(key)
+    return None
+
+
+def scan_rooflines(args, n_local, brackets, pk):
+    """Roofline of the cosine main scan from the per-launch brackets (slot 0)."""
+    Bq = args.batch
+    groups = (Bq + 255) // 256
+    mean, mn, n = bracket_stats(brackets[0], groups)
+    if mean is None:
+        return None
+    n_scan_rows = max(n_local - 2048, 0)  # the first 2048 rows are the dense seed pass
+    half = args.mode in ("bf16", "f16")
+    streamed = n_scan_rows * DIM * (2 if half else 4) * groups
+    flops = 2.0 * Bq * n_scan_rows * DIM
+    traffic = traffic_for(f"cosine_scan_{args.mode}", n_local, Bq)
+    kernel = f"cosine_scan_kernel<{args.mode}> (main scan, {n_scan_rows} rows x {min(Bq, 256)} queries x {groups} group(s))"
+    hbm = hbm_roofline(streamed, mean, mn, n, pk, kernel, groups,
+                       f"{args.mode} shadow copy actually streamed (N*D*2)" if half else "fp32 corpus (N*D*4)", traffic)
+    tens = tensor_roofline(flops, mean, mn, n, pk, kernel, groups, traffic,
+                           None if half else {"note": "tf32 runs at half the bf16 rate: x2 for the tf32 ceiling"})
+    # which resource bounds the kernel: 16-bit operands at B = 256 have 256 flop/B of streamed data > the ~207 flop/B ridge
+    primary, other = (tens, hbm) if (half and min(Bq, 256) >= 208) else (hbm, tens)
+    out = dict(primary)
+    fp32_bytes = n_scan_rows * DIM * 4 * groups
+    out.update({"fp32_equivalent_gbs": fp32_bytes / (mean * 1e-3) / 1e9,
+                "fp32_equivalent_frac_of_hbm_peak": fp32_bytes / (mean * 1e-3) / 1e9 / pk["hbm_gbs"],
+                "other_view": {k: other[k] for k in ("bound", "achieved", "peak", "unit", "frac")}})
+    return out
+
+
+def bm25_roofline(bm25, q_tok, q_len, brackets, pk, n_local, Bq):
+    mean, mn, n = bracket_stats(brackets[1], 1)
+    if mean is None:
+        return None
+    post_bytes = bm25.posting_bytes(q_tok, q_len)
+    return hbm_roofline(post_bytes, mean, mn, n, pk,
+                        "bm25_ms_kernel (fp32 MaxScore first pass over the fp16-r posting view)", 1,
+                        "6 B per posting of every query term (SURVEY.md §8d): sum_q sum_t df(t) * 6",
+                        traffic_for("bm25_ms", n_local, Bq))
+
+
+def oracle_check(args, h, got, q_emb_np, qt_np, ql_np, want_cosine, want_bm25, thr):
+    """Full-size comparison with the streamed CPU oracle on a query subset (rank 0; outside every timed region).
+    Returns (verified dict, cpu_baseline dict)."""
+    import oracle
+    from oracle import scale_check
+    from optimized_rag_b200 import synthetic as syn
+    nv = args.verify_queries if args.verify_queries is not None else (32 if h.world == 1 else 8)
+    if nv <= 0:
+        return None, None
+    cores = os.cpu_count() or 1
+    oracle.build()
+    oracle.set_threads(cores)
+    Bq = args.batch
+    rows = scale_check.pick_queries(qt_np, ql_np, Bq, min(nv, Bq)) if qt_np is not None else \
+        np.unique(np.linspace(0, Bq - 1, min(nv, Bq)).astype(np.int64))
+    t0 = time.perf_counter()
+    bm = oracle.StreamedBM25(syn.SEED_TOKENS, args.rows, VOCAB, LMIN, LMAX, thr) if want_bm25 else None
+    t_stats = time.perf_counter() - t0
+    want, secs = scale_check.reference_lists(args.rows, DIM, q_emb_np[rows] if want_cosine else None,
+                                             qt_np[rows] if want_bm25 else None, ql_np[rows] if want_bm25 else None,
+                                             TOPK, seed_corpus=syn.SEED_CORPUS, bm25=bm, want_cosine=want_cosine)
+    bad = scale_check.compare(got, want, rows)
+    if bad:
+        raise SystemExit("bench: the CUDA results DIFFER from the CPU oracle at full size: " + "; ".join(bad))
+    t_cpu = sum(secs.values())
+    verified = {"queries": int(len(rows)), "rows": args.rows, "arrays": sorted(want), "bitwise": True,
+                "oracle": "oracle.c streamed restatement (inputs regenerated from the seeds; rag/retrieval.py:362-371, "
+                          "324-347, 320; rag/reranker.py:224-271)"}
+    cpu = {"value": len(rows) / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{len(rows)} queries of the batch against ALL {args.rows} rows/docs (no extrapolation) through the "
+                     f"oracle (C port of the reference arithmetic, OpenMP, queries in SIMD lanes): "
+                     + ", ".join(f"{k} {v:.1f} s" for k, v in secs.items())
+                     + (f"; BM25 statistics pass {t_stats:.1f} s (BM25Okapi rebuild per call, rag/retrieval.py:338) NOT charged"
+                        if want_bm25 else "")}
+    return verified, cpu
+
+
+def run_hybrid_like(args):
+    """Configs 3 (hybrid), 2 (cosine only) and 4 (BM25 only): row-sharded corpus, one search call per step."""
+    h = Harness(args)
+    torch = h.torch
+    from optimized_rag_b200 import engine, synthetic as syn
     from optimized_rag_b200.bm25_index import Bm25Index
-    from optimized_rag_b200.dist import ShardedHybrid, shard_range, sharded_stats
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (native arm) needs a GPU: there is no CPU fallback for the retrieval hot path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    L = _ffi.lib()
-    N, Bq, k = args.rows, args.queries, TOPK
+    from optimized_rag_b200.dist import ShardedBm25, ShardedCosine, ShardedHybrid, shard_range, sharded_stats
+    dev, world, rank = h.dev, h.world, h.rank
+    N, Bq, k = args.rows, args.batch, TOPK
+    want_cos, want_bm = args.config in ("3", "2"), args.config in ("3", "4")
     lo, hi = shard_range(N, rank, world)
     n_local = hi - lo
 
-    # ---- build the shard: embeddings (+ inverse norms, + bf16 shadow), token corpus, inverted index
+    # ---- build the shard: embeddings (+ inverse norms, + 16-bit shadow), token corpus, inverted index
     t_setup = time.perf_counter()
-    corpus = engine.gen_embeddings(n_local, DIM, lo, syn.SEED_CORPUS, 0, device=dev)
-    cos = engine.CosineIndex(corpus, row_id_base=lo, mode=args.mode)
     thr = syn.zipf_thresholds(VOCAB)
-    doc_off, tokens = engine.gen_token_corpus(n_local, lo, syn.SEED_TOKENS, thr, VOCAB, 100, 300, device=dev)
-    stats = sharded_stats(doc_off, tokens, VOCAB)
-    bm25 = Bm25Index(doc_off, tokens, VOCAB, tile_docs=args.tile_docs, stats=stats, doc_id_base=lo)
-    cpu_sample = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        S = min(args.cpu_sample_rows, n_local)
-        cpu_sample = (corpus[:S].cpu().numpy(), doc_off[:S + 1].cpu().numpy(),
-                      tokens[:int(doc_off[S].item())].cpu().numpy())
-    del tokens
-    torch.cuda.empty_cache()
-    shard = engine.HybridShard(cos, bm25)
-    sh = ShardedHybrid(shard)
+    cos = bm25 = None
+    build_s = None
+    if want_cos:
+        corpus = engine.gen_embeddings(n_local, DIM, lo, syn.SEED_CORPUS, 0, device=dev)
+        cos = engine.CosineIndex(corpus, row_id_base=lo, mode=args.mode)
+    if want_bm:
+        doc_off, tokens = engine.gen_token_corpus(n_local, lo, syn.SEED_TOKENS, thr, VOCAB, LMIN, LMAX, device=dev)
+        torch.cuda.synchronize()
+        t_b = time.perf_counter()
+        stats = sharded_stats(doc_off, tokens, VOCAB)
+        bm25 = Bm25Index(doc_off, tokens, VOCAB, tile_docs=args.tile_docs, stats=stats, doc_id_base=lo)
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t_b
+        del tokens
+        torch.cuda.empty_cache()
+    if args.config == "3":
+        sh = ShardedHybrid(engine.HybridShard(cos, bm25))
+    elif args.config == "2":
+        sh = ShardedCosine(cos)
+    else:
+        sh = ShardedBm25(bm25)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
 
     # ---- queries: generated on the host, staged in pinned memory (replicated on every rank)
-    q_emb_h = torch.from_numpy(syn.query_embeddings(Bq, N, DIM)).pin_memory()
-    qt_np, ql_np = syn.keyword_queries(Bq, VOCAB, thresholds=thr)
-    q_tok_h = torch.from_numpy(qt_np).pin_memory()
-    q_len_h = torch.from_numpy(ql_np).pin_memory()
-    q_emb, q_tok, q_len = q_emb_h.to(dev), q_tok_h.to(dev), q_len_h.to(dev)
+    q_emb_np = syn.query_embeddings(Bq, N, DIM) if want_cos else None
+    qt_np, ql_np = syn.keyword_queries(Bq, VOCAB, thresholds=thr) if want_bm else (None, None)
+    host, devt = [], []
+    if want_cos:
+        host.append(torch.from_numpy(q_emb_np).pin_memory())
+    if want_bm:
+        host += [torch.from_numpy(qt_np).pin_memory(), torch.from_numpy(ql_np).pin_memory()]
+    devt = [t.to(dev) for t in host]
     out_ids_h = torch.empty((Bq, k), dtype=torch.int64).pin_memory()
     out_sc_h = torch.empty((Bq, k), dtype=torch.float64).pin_memory()
-    h2d = q_emb_h.numel() * 4 + q_tok_h.numel() * 4 + q_len_h.numel() * 4
+    status_h = torch.empty(Bq, dtype=torch.int32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = out_ids_h.numel() * 8 + out_sc_h.numel() * 8 + Bq * 4
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- warm-up (the clock sampler is already running: see ClockSampler)
-    uuid = str(torch.cuda.get_device_properties(dev).uuid)
-    sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
-    if rank == 0:  # one poller per box: nvidia-smi queries take driver locks that kernel launches also need
-        sampler.start()
-    res = None
-    for _ in range(max(args.warmup, 3)):
-        res = sh.search(q_emb, q_tok, q_len, k)
-    barrier()
-
-    # ---- timed: inputs resident in HBM
-    L.orag_profile_enable(1)
-    scan_ms, bm_ms = [], []
-    launches0 = int(L.orag_launch_count())
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0 = time.time()
-    ev0.record()
-    import ctypes
-    a, b = ctypes.c_float(), ctypes.c_float()
     # back-to-back batches, inputs resident: nothing synchronises with the host inside the timed region (the per-query
     # overflow flags of every step are kept and checked after it -- a flagged step would invalidate the run)
-    flags = []
-    for _ in range(args.steps):
-        res = sh.search(q_emb, q_tok, q_len, k, check_overflow=False)
-        flags.append(res["status"])
-    ev1.record()
-    barrier()
-    w1 = time.time()
-    sampler.window(w0, w1)
-    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = int(L.orag_launch_count()) - launches0
-    if dev_ms < 150.0:
-        # the timed loop is shorter than a few polling periods (small shards): keep the same back-to-back load running,
-        # untimed, for ~0.2 s so that the poller sees it.  The step count derives from dev_ms, which is identical on
-        # every rank (max over ranks), so all ranks enter the same number of collectives.
-        n_probe = int(200.0 / max(dev_ms / args.steps, 1e-3)) + 1
-        p0 = time.time()
-        for _ in range(n_probe):
-            sh.search(q_emb, q_tok, q_len, k, check_overflow=False)
-        torch.cuda.synchronize()
-        sampler.window(p0, time.time())
-        barrier()
-    if bool(torch.stack(flags).any()):
-        raise SystemExit("bench: a candidate buffer overflowed inside the timed region; results would need the repair path")
-    L.orag_profile_read(ctypes.byref(a), ctypes.byref(b))  # brackets of the last step's scan / BM25 first-pass kernels
-    scan_ms.append(a.value); bm_ms.append(b.value)
-    L.orag_profile_enable(0)
+    flags, last = [], {}
 
-    # the clocks line describes the device-timed loop (see ClockSampler): stop polling before the end-to-end loop, where
-    # every step synchronises with the host and a poller taking driver locks would be measured with it
-    clocks = sampler.stop()
+    def step():
+        res = sh.search(*devt, k, check_overflow=False)
+        flags.append(res["status"])
+        last["res"] = res
+
+    dev_ms, launches, brackets = h.device_timed(step)
+    if bool(torch.stack(flags[-args.steps:]).any()):
+        raise SystemExit("bench: a candidate buffer overflowed inside the timed region; results would need the repair path")
+    flags.clear()
 
     # ---- timed: end to end through the public call with HOST buffers
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    status_h = torch.empty(Bq, dtype=torch.int32).pin_memory()
-    for _ in range(args.steps):
-        q_emb.copy_(q_emb_h, non_blocking=True)
-        q_tok.copy_(q_tok_h, non_blocking=True)
-        q_len.copy_(q_len_h, non_blocking=True)
-        r = sh.search(q_emb, q_tok, q_len, k, check_overflow=False)
+    def step_e2e():
+        for d, s in zip(devt, host):
+            d.copy_(s, non_blocking=True)
+        r = sh.search(*devt, k, check_overflow=False)
         out_ids_h.copy_(r["ids"], non_blocking=True)
-        out_sc_h.copy_(r["rrf_scores"], non_blocking=True)
+        out_sc_h.copy_(r["scores"], non_blocking=True)
         status_h.copy_(r["status"], non_blocking=True)   # the overflow flags travel with the result: ONE sync per step
         torch.cuda.current_stream().synchronize()
         if int(status_h.max()) != 0:                      # rare: repair through the exhaustive kernels
-            r = sh.search(q_emb, q_tok, q_len, k, check_overflow=True)
-            out_ids_h.copy_(r["ids"]); out_sc_h.copy_(r["rrf_scores"])
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+            r = sh.search(*devt, k, check_overflow=True)
+            out_ids_h.copy_(r["ids"]); out_sc_h.copy_(r["scores"])
+
+    e2e_ms = h.e2e_timed(step_e2e)
     exchange_used = "none (one shard)" if world == 1 else sh.exchange + (f" ({sh.exchange_note})" if sh.exchange_note else "")
 
-    # ---- self-check outside the timed region: re-derive a few queries' lists with the exact kernels
-    verified = None
-    if world == 1:
-        sub = torch.tensor([0, 1, Bq // 2, Bq - 1], device=dev)
-        ei, es = cos.topk(q_emb[sub].contiguous(), k, mode="exact")
-        bi, bs, _ = bm25.topk(q_tok[sub].contiguous(), q_len[sub].contiguous(), k, force="dense")
-        ok = (torch.equal(ei, res["cos_ids"][sub]) and torch.equal(es, res["cos_scores"][sub])
-              and torch.equal(bi, res["bm25_ids"][sub]) and torch.equal(bs, res["bm25_scores"][sub]))
-        top1 = (res["cos_ids"][:, 0].cpu().numpy() == (np.arange(Bq) * syn.QUERY_STRIDE) % N).all()
-        verified = bool(ok and top1)
-        if not verified:
-            raise SystemExit("bench self-check FAILED: fast path differs from the exact kernels")
-
-    if rank != 0:
-        if world > 1:
-            sh.close()  # collective with rank 0's call below: nobody frees a buffer a peer still has mapped
-            dist.destroy_process_group()
-        return
+    # ---- outside the timed regions: the last step's results against the CPU oracle at full corpus size
+    verified = cpu = None
+    res = last["res"]
+    if rank == 0:
+        keys = {"3": ["cos_ids", "cos_scores", "bm25_ids", "bm25_scores", "bm25_max", "ids", "rrf_scores"],
+                "2": ["cos_ids", "cos_scores"], "4": ["bm25_ids", "bm25_scores", "bm25_max"]}[args.config]
+        got = {key: res[key].cpu().numpy() for key in keys}
+        verified, cpu = oracle_check(args, h, got, q_emb_np, qt_np, ql_np, want_cos, want_bm, thr)
+    h.barrier()
 
     pk = peaks()
-    n_scan_rows = max(n_local - 2048, 0)
-    t_scan = statistics.mean(scan_ms) * 1e-3
-    t_bm = statistics.mean([x for x in bm_ms if x >= 0] or [0.0]) * 1e-3
-    groups = (Bq + 255) // 256
-    fp32_bytes = n_scan_rows * DIM * 4
-    half = args.mode in ("bf16", "f16")
-    streamed = n_scan_rows * DIM * (2 if half else 4)
-    flops = 2.0 * min(Bq, 256) * n_scan_rows * DIM
-    traffic = None
-    tp = ROOT / "profiles" / "traffic.json"
-    tj = json.loads(tp.read_text()) if tp.exists() else {}
-    # the ncu capture is of ONE launch shape; it says nothing about other shard sizes / batch sizes
-    cap = tj.get("captured_at", {})
-    same_launch = cap.get("rows_per_gpu") == n_local and cap.get("queries") == Bq
-    if same_launch:
-        traffic = tj.get(f"cosine_scan_{args.mode}")
-    hbm = {"bound": "hbm", "achieved": streamed / t_scan / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-           "frac": streamed / t_scan / 1e9 / pk["hbm_gbs"], "traffic": traffic,
-           "bytes": f"{args.mode} shadow copy actually streamed (N*D*2)" if half else "fp32 corpus (N*D*4)"}
-    tens = {"bound": "tensor", "achieved": flops / t_scan / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-            "frac": flops / t_scan / 1e12 / pk["tf_sustained"], "traffic": traffic,
-            "peak_kind": "bf16 dense sustained (fp16 and bf16 share the kind::f16 rate)" if half else
-                         "bf16 dense sustained (tf32 runs at half the bf16 rate: x2 for the tf32 ceiling)"}
-    # which resource bounds the kernel: bf16 at B=256 has 256 flop/B of streamed data > the ~207 flop/B ridge
-    primary = tens if (half and Bq >= 208) else hbm
-    roofline = dict(primary)
-    roofline.update({"kernel": f"cosine_scan_kernel<{args.mode}> (main scan, {n_scan_rows} rows x {min(Bq, 256)} queries)",
-                     "peak_source": pk["source"], "launch_ms": t_scan * 1e3 / 1.0, "launches_per_step": groups,
-                     "fp32_equivalent_gbs": fp32_bytes / t_scan / 1e9,
-                     "fp32_equivalent_frac_of_hbm_peak": fp32_bytes / t_scan / 1e9 / pk["hbm_gbs"],
-                     "other_view": tens if primary is hbm else hbm})
-    post_bytes = bm25.posting_bytes(q_tok, q_len)
-    roof_bm = {"bound": "hbm", "achieved": post_bytes / t_bm / 1e9 if t_bm > 0 else None, "peak": pk["hbm_gbs"],
-               "unit": "GB/s", "frac": (post_bytes / t_bm / 1e9 / pk["hbm_gbs"]) if t_bm > 0 else None,
-               "kernel": "bm25_ms_kernel (fp32 MaxScore first pass over the fp16-r posting view)", "launch_ms": t_bm * 1e3,
-               "algorithmic_bytes": post_bytes,
-               "traffic": tj.get("bm25_ms") if same_launch else None}
-
+    roof_scan = scan_rooflines(args, n_local, brackets, pk) if want_cos else None
+    roof_bm = bm25_roofline(bm25, devt[-2], devt[-1], brackets, pk, n_local, Bq) if want_bm else None
     value = Bq * args.steps / (dev_ms * 1e-3)
-    e2e_val = Bq * args.steps / (e2e_ms * 1e-3)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": workload_config(args, {"first_pass": args.mode,
-                                             "arithmetic": "results in the reference's float64 arithmetic (bit-exact); "
-                                                           f"candidate generation {args.mode} tensor cores / fp32 BM25 "
-                                                           "with proven error margins, then exact re-score",
-                                             "rows_per_gpu": n_local,
-                                             "parallelism": f"row-sharded x{world}", "setup_s": round(t_setup, 1),
-                                             "exchange": exchange_used,
-                                             "bm25_postings_local": bm25.n_postings}),
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_bm25": roof_bm,
-            "hbm_roofline_queries_per_sec_fp32_corpus": Bq / (n_local * DIM * 4 / (pk["hbm_gbs"] * 1e9)),
-            "verified_against_exact_kernels": verified}
+    line = {"metric": args.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": h.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, {
+                "first_pass": (args.mode + " tensor cores" if want_cos else "") + (" / " if args.config == "3" else "")
+                              + ("fp32 MaxScore over fp16 impacts" if want_bm else ""),
+                "arithmetic": "results in the reference's float64 arithmetic (bit-exact); candidate generation in low "
+                              "precision with proven error margins, then exact re-score",
+                "rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}", "setup_s": round(t_setup, 1),
+                "exchange": exchange_used,
+                **({"bm25_postings_local": bm25.n_postings, "bm25_index_build_s": round(build_s, 2)} if want_bm else {})}),
+            "e2e": {"value": Bq * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "clocks": h.clocks,
+            "roofline": roof_scan if want_cos else roof_bm}
+    if args.config == "3":
+        line["roofline_bm25"] = roof_bm
+    if want_cos:
+        line["hbm_roofline_queries_per_sec_fp32_corpus"] = Bq / (n_local * DIM * 4 / (pk["hbm_gbs"] * 1e9))
+    line["verified_against_oracle"] = verified
+    if cpu is not None and world == 1:
+        line["cpu_baseline"] = cpu
+    h.finish(line, closer=sh.close)
 
-    if cpu_sample is not None:
+
+def pairwise_claims(m: int, dev):
+    """Config-5 claims on the device: synthetic rows, every 64th one a noisy copy of another claim (cosine ~0.85-0.97
+    with its source) -- the same construction as `pairwise_claims_host`."""
+    import torch
+    from optimized_rag_b200 import engine, synthetic as syn
+    emb = engine.gen_embeddings(m, DIM, 0, syn.SEED_CORPUS, 0, device=dev)
+    dst = torch.arange(0, m, 64, device=dev)
+    src = (dst * 7919 + 13) % m
+    w = 0.25 + 0.4 * ((dst * 2654435761 % 1000).to(torch.float32) / 1000)
+    emb[dst] = emb[src] + w[:, None] * emb[dst]
+    return emb
+
+
+def run_pairwise(args):
+    """Config 5: one step = every claim pair of the matrix through the tensor-core first pass + float64 re-score."""
+    h = Harness(args)
+    if h.world > 1:
+        raise SystemExit("bench --config pairwise: BASELINE config 5 is a one-GPU configuration")
+    torch = h.torch
+    from optimized_rag_b200 import engine
+    dev, M = h.dev, args.rows
+    emb = pairwise_claims(M, dev)
+    doc = (torch.arange(M, device=dev) // 16).to(torch.int32)
+    checker = engine.PairwiseIndex(emb, doc)
+    emb_h = emb.cpu().pin_memory()
+    last = {}
+
+    def step():
+        last["res"] = checker.pairs(0.85, sync=False)
+
+    dev_ms, launches, brackets = h.device_timed(step)
+
+    def step_e2e():
+        emb.copy_(emb_h, non_blocking=True)
+        chk = engine.PairwiseIndex(emb, doc)       # ingest (fp16 shadow, norms) is part of the end-to-end call
+        i, j, s = chk.pairs(0.85, sync=True)
+        last["host"] = (i.cpu(), j.cpu(), s.cpu())
+
+    e2e_ms = h.e2e_timed(step_e2e)
+    gi, gj, gs = checker.pairs(0.85, sync=True)
+    n_pairs = int(gi.numel())
+    # oracle on a sub-block (O(M^2 D) float64 on the CPU): the pairs among the first `sub` claims must be identical
+    verified = cpu = None
+    sub = min(M, 8192)
+    nv = args.verify_queries
+    if nv is None or nv > 0:
         import oracle
         cores = os.cpu_count() or 1
         oracle.build()
         oracle.set_threads(cores)
-        c_np, off_np, tok_np = cpu_sample
-        S = c_np.shape[0]
-        ob = oracle.BM25Index(off_np, tok_np, VOCAB)
-        qs = q_emb_h.numpy()
-        nq_cpu, t_cpu = 0, 0.0
-        while t_cpu < 10.0 and nq_cpu < 64:
-            t_cpu += cpu_hybrid_sample(oracle, c_np, ob, qs[nq_cpu:nq_cpu + 2], qt_np[nq_cpu:nq_cpu + 2],
-                                       ql_np[nq_cpu:nq_cpu + 2], k)
-            nq_cpu += 2
-        scale = N / S
-        line["cpu_baseline"] = {"value": nq_cpu / (t_cpu * scale), "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{nq_cpu} queries x first {S} rows/docs of the same corpus through the "
-                                          f"oracle (C port of the reference arithmetic, OpenMP), scaled x{scale:.0f} "
-                                          f"to {N} rows; BM25Okapi rebuild per call not charged"}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        sh.close()
-        dist.destroy_process_group()
+        t0 = time.perf_counter()
+        oi, oj, osim = oracle.pairwise_candidates_parallel(emb[:sub].cpu().numpy(), doc[:sub].cpu().numpy(), 0.85)
+        t_cpu = time.perf_counter() - t0
+        keep = (gi < sub) & (gj < sub)
+        a = (gi[keep].cpu().numpy(), gj[keep].cpu().numpy(), gs[keep].cpu().numpy())
+        same = (np.array_equal(a[0], oi) and np.array_equal(a[1], oj)
+                and np.array_equal(a[2].view(np.uint64), osim.view(np.uint64)))
+        if not same:
+            raise SystemExit("bench: pair set differs from the CPU oracle on the sub-block")
+        verified = {"claims": sub, "pairs_in_sub_block": int(len(oi)), "bitwise": True,
+                    "oracle": "oracle.c pairwise candidates (rag/consistency_checker.py:169-189, 241-261)"}
+        cpu = {"value": (sub * (sub - 1) / 2) / t_cpu, "unit": "pairs/s", "cores": cores, "kind": "port",
+               "sample": f"all pairs of the first {sub} claims ({t_cpu:.1f} s); O(M^2 D): the rate does not depend on M"}
+    pk = peaks()
+    mean, mn, n = bracket_stats(brackets[0], 1)
+    blocks = (M + 255) // 256
+    flops_required = float(M) * (M - 1) * DIM
+    flops_executed = 2.0 * 128 * 256 * DIM * blocks * (blocks + 1)
+    roof = tensor_roofline(flops_executed, mean, mn, n, pk,
+                           f"cosine_scan_kernel<f16, 2-SM> in pair mode ({blocks * (blocks + 1)} tiles of 128 x 256)", 1,
+                           None, {"flops_required": flops_required, "flops_executed": flops_executed,
+                                  "flops": "executed = every 128x256 tile at or below the diagonal blocks; required = "
+                                           "M(M-1)D for the strict upper triangle (SURVEY.md §8d)",
+                                  "frac_required_flops": flops_required / (mean * 1e-3) / 1e12 / pk["tf_sustained"]}) \
+        if mean else None
+    pairs = M * (M - 1) / 2
+    line = {"metric": args.metric, "value": pairs * args.steps / (dev_ms * 1e-3), "unit": "pairs/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": h.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, {"first_pass": "fp16 shadow (rows scaled by powers of two), tcgen05 kind::f16 "
+                                                           "cta_group::2, fixed threshold 0.85 - eps",
+                                             "pairs_found": n_pairs}),
+            "e2e": {"value": pairs * args.steps / (e2e_ms * 1e-3), "unit": "pairs/s",
+                    "h2d_bytes_per_step": emb_h.numel() * 4,
+                    "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in last["host"])),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "clocks": h.clocks, "roofline": roof, "verified_against_oracle": verified}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    h.finish(line)
 
 
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "pairwise":
+        run_pairwise(args)
     else:
-        run_native(args)
+        run_hybrid_like(args)
 
 
 if __name__ == "__main__":

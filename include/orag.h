@@ -73,6 +73,10 @@ int orag_device_info(int *sm_count, int *cc_major, int *cc_minor);
 unsigned long long orag_launch_count(void);
 int orag_profile_enable(int on);
 int orag_profile_read(float *scan_ms, float *bm25_ms);
+/* Every bracket of one slot (0 = cosine main scan, 1 = BM25 first pass) recorded since orag_profile_enable(1), oldest
+ * first, at most `cap` (the library keeps the last 256): returns the number of durations written to ms[], or a
+ * negative ORAG_E* code.  Synchronises on the events it reads. */
+int orag_profile_read_all(int slot, float *ms, int cap);
 
 /* ---------------------------------------------------------------------------
  * Synthetic inputs: bit-identical to optimized_rag_b200/synthetic.py
@@ -233,6 +237,14 @@ int orag_topk_merge(const int64_t *d_cand_ids, const double *d_cand_scores, int 
 int orag_rrf_fuse(const int64_t *d_list_ids, int n_queries, int n_lists, int list_len, int rrf_k, int top_k,
                   int tie_mode, int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_src, void *stream);
 
+/* Two-list form for the one-shard hybrid step: d_ids_a / d_ids_b [n_queries, list_len] are the ranked lists exactly as
+ * orag_cosine_topk / orag_bm25_topk wrote them (no packing); same arithmetic and tie rule as orag_rrf_fuse with
+ * n_lists = 2 (d_out_src int32 [n_queries, top_k, 2], optional).  d_out_status[q] (optional) = d_status_a[q] |
+ * d_status_b[q] (either may be NULL): the OR of the two candidate-overflow words.  2 * list_len <= 128. */
+int orag_rrf_fuse_pair(const int64_t *d_ids_a, const int64_t *d_ids_b, int n_queries, int list_len, int rrf_k, int top_k,
+                       int tie_mode, const int32_t *d_status_a, const int32_t *d_status_b, int64_t *d_out_ids,
+                       double *d_out_scores, int32_t *d_out_src, int32_t *d_out_status, void *stream);
+
 /* Everything after the all-gather of a row-sharded hybrid search in one launch: d_gathered is
  * [n_shards, n_queries, W] int64 with W = 2*fetch_k + 2*kk + 2 holding, per shard and query,
  * cosine ids | cosine float64 score bits | BM25 ids | BM25 RAW float64 score bits | the shard's max raw
@@ -259,7 +271,8 @@ int orag_hybrid_merge(const int64_t *d_gathered, int n_shards, int n_queries, in
  *   per search, with the same seq = 1, 2, 3, ... on every rank:
  *     orag_hybrid_push: one launch packs this rank's lists (same arrays / layout as the gathered buffer of
  *       orag_hybrid_merge: d_cos_* [n_queries, fetch_k], d_bm25_* [n_queries, kk] RAW scores, d_bm25_max
- *       [n_queries], d_status [n_queries] or NULL) and stores them into slot seq&1 of EVERY peer, then publishes
+ *       [n_queries]; d_status / d_status2 [n_queries] or NULL: the status words of the cosine and the BM25 call,
+ *       OR-ed into the block's status column) and stores them into slot seq&1 of EVERY peer, then publishes
  *       seq with a system-scope release store.
  *     orag_hybrid_wait: one tiny launch that acquires the n_shards sequence numbers in this rank's own buffer;
  *       *d_gathered (host out) is the [n_shards, n_queries, W] array to hand to orag_hybrid_merge on the same
@@ -274,9 +287,9 @@ int orag_exchange_export(void *d_buf, unsigned char handle[64]);
 int orag_exchange_open(const unsigned char handle[64], void **d_peer_buf);
 int orag_exchange_close(void *d_peer_buf);
 int orag_hybrid_push(const int64_t *d_cos_ids, const double *d_cos_scores, const int64_t *d_bm25_ids,
-                     const double *d_bm25_scores, const double *d_bm25_max, const int32_t *d_status, int n_queries,
-                     int fetch_k, int kk, int rank, int n_shards, int max_queries, void *const *d_peer_bufs,
-                     uint64_t seq, void *stream);
+                     const double *d_bm25_scores, const double *d_bm25_max, const int32_t *d_status,
+                     const int32_t *d_status2, int n_queries, int fetch_k, int kk, int rank, int n_shards,
+                     int max_queries, void *const *d_peer_bufs, uint64_t seq, void *stream);
 int orag_hybrid_wait(void *d_buf, int n_shards, int max_queries, int n_queries, int fetch_k, int kk, uint64_t seq,
                      int timeout_ms, const int64_t **d_gathered, void *stream);
 
@@ -299,11 +312,22 @@ int orag_pairwise_cosine_threshold(const float *d_emb, int64_t m, int dim, const
                                    double *d_out_sim, unsigned long long *d_out_count, void *d_workspace,
                                    size_t workspace_bytes, void *stream);
 
-/* Tensor-core variant (BASELINE config 5, 64k x 1536): tcgen05 tf32 first pass with a fixed threshold
- * (threshold - first-pass error bound) over row blocks of 256, then the same float64 re-score and
- * filter -> identical pair set.  Needs dim % 32 == 0 and threshold > 2.3e-3.  d_out_count has TWO
- * elements: [0] = number of pairs, [1] = 1 if a per-row candidate buffer overflowed (result
- * incomplete: re-run with orag_pairwise_cosine_threshold). */
+/* Tensor-core variant (BASELINE config 5, 64k x 1536): a tcgen05 first pass with a fixed threshold
+ * (threshold - first-pass error bound) over the triangular space of (256-row block, 128-row tile) pairs -- fp16
+ * shadow rows scaled by powers of two, kind::f16, CTA pairs with cta_group::2 when dim % 64 == 0, else tf32 off the
+ * fp32 rows -- then the same float64 re-score and filter -> identical pair set.  Needs dim % 32 == 0 and
+ * threshold > ~2.3e-3.  d_out_count has TWO elements: [0] = number of pairs, [1] = 1 if a per-row candidate
+ * buffer overflowed (result incomplete: re-run with orag_pairwise_cosine_threshold).
+ *   orag_pairwise_prepare   once per claim matrix: float64 sum(a*a) of every row, first-pass norms, fp16 shadow, into a
+ *                           caller-owned buffer of orag_pairwise_prepared_bytes(m, dim) bytes
+ *   orag_pairwise_pairs     the search over a prepared matrix (workspace: orag_pairwise_pairs_workspace_bytes(m))
+ *   orag_pairwise_cosine_threshold_tc   both in one call (workspace: orag_pairwise_tc_workspace_bytes) */
+size_t orag_pairwise_prepared_bytes(int64_t m, int dim);
+size_t orag_pairwise_pairs_workspace_bytes(int64_t m);
+int orag_pairwise_prepare(const float *d_emb, int64_t m, int dim, void *d_prepared, size_t prepared_bytes, void *stream);
+int orag_pairwise_pairs(const float *d_emb, const void *d_prepared, int64_t m, int dim, const int32_t *d_doc_idx,
+                        double threshold, int64_t cap, int32_t *d_out_i, int32_t *d_out_j, double *d_out_sim,
+                        unsigned long long *d_out_count, void *d_workspace, size_t workspace_bytes, void *stream);
 size_t orag_pairwise_tc_workspace_bytes(int64_t m, int dim);
 int orag_pairwise_cosine_threshold_tc(const float *d_emb, int64_t m, int dim, const int32_t *d_doc_idx,
                                       double threshold, int64_t cap, int32_t *d_out_i, int32_t *d_out_j,

@@ -19,15 +19,16 @@ ORAG_BM25_BACKGROUND = 16
 # every symbol include/orag.h declares (tests check the .so exports each one)
 SYMBOLS = [
     "orag_version", "orag_last_error", "orag_device_info",
-    "orag_launch_count", "orag_profile_enable", "orag_profile_read",
+    "orag_launch_count", "orag_profile_enable", "orag_profile_read", "orag_profile_read_all",
     "orag_gen_embeddings", "orag_gen_doc_lengths", "orag_gen_tokens",
     "orag_row_inv_norms", "orag_row_sq", "orag_f32_to_bf16", "orag_f32_to_f16_rows",
     "orag_cosine_mark_prescan", "orag_stream_wait_prescan",
     "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_dense", "orag_cosine_firstpass_dense",
     "orag_bm25_workspace_bytes", "orag_bm25_topk", "orag_bm25_dense", "orag_dense_topk",
-    "orag_topk_merge", "orag_rrf_fuse", "orag_hybrid_merge", "orag_weighted_sum3", "orag_div_scalar",
+    "orag_topk_merge", "orag_rrf_fuse", "orag_rrf_fuse_pair", "orag_hybrid_merge", "orag_weighted_sum3", "orag_div_scalar",
     "orag_pairwise_workspace_bytes", "orag_pairwise_cosine_threshold",
     "orag_pairwise_tc_workspace_bytes", "orag_pairwise_cosine_threshold_tc",
+    "orag_pairwise_prepared_bytes", "orag_pairwise_pairs_workspace_bytes", "orag_pairwise_prepare", "orag_pairwise_pairs",
     "orag_exchange_bytes", "orag_exchange_alloc", "orag_exchange_free", "orag_exchange_export", "orag_exchange_open",
     "orag_exchange_close", "orag_hybrid_push", "orag_hybrid_wait",
 ]
@@ -87,6 +88,7 @@ def lib() -> ctypes.CDLL:
     L.orag_launch_count.restype = ctypes.c_ulonglong
     L.orag_profile_enable.argtypes = [c_int]
     L.orag_profile_read.argtypes = [POINTER(ctypes.c_float), POINTER(ctypes.c_float)]
+    L.orag_profile_read_all.argtypes = [c_int, POINTER(ctypes.c_float), c_int]
     L.orag_gen_embeddings.argtypes = [vp, c_int64, c_int, c_int64, c_uint64, c_int, vp]
     L.orag_gen_doc_lengths.argtypes = [vp, c_int64, c_int64, c_uint64, c_int, c_int, vp]
     L.orag_gen_tokens.argtypes = [vp, vp, c_int64, c_int64, c_uint64, vp, c_int, vp]
@@ -110,6 +112,7 @@ def lib() -> ctypes.CDLL:
     L.orag_dense_topk.argtypes = [vp, c_int64, c_int64, c_int, c_int, c_int64, c_int, vp, vp, vp, vp]
     L.orag_topk_merge.argtypes = [vp, vp, c_int, c_int, c_int, vp, c_int, vp, vp, vp, vp]
     L.orag_rrf_fuse.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp]
+    L.orag_rrf_fuse_pair.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp]
     L.orag_hybrid_merge.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp,
                                     vp, vp]
     L.orag_weighted_sum3.argtypes = [vp, vp, vp, c_int64, c_double, c_double, c_double, vp, vp]
@@ -121,6 +124,12 @@ def lib() -> ctypes.CDLL:
     L.orag_pairwise_tc_workspace_bytes.restype = c_size_t
     L.orag_pairwise_tc_workspace_bytes.argtypes = [c_int64, c_int]
     L.orag_pairwise_cosine_threshold_tc.argtypes = L.orag_pairwise_cosine_threshold.argtypes
+    L.orag_pairwise_prepared_bytes.restype = c_size_t
+    L.orag_pairwise_prepared_bytes.argtypes = [c_int64, c_int]
+    L.orag_pairwise_pairs_workspace_bytes.restype = c_size_t
+    L.orag_pairwise_pairs_workspace_bytes.argtypes = [c_int64]
+    L.orag_pairwise_prepare.argtypes = [vp, c_int64, c_int, vp, c_size_t, vp]
+    L.orag_pairwise_pairs.argtypes = [vp, vp, c_int64, c_int, vp, c_double, c_int64, vp, vp, vp, vp, vp, c_size_t, vp]
     L.orag_exchange_bytes.restype = c_size_t
     L.orag_exchange_bytes.argtypes = [c_int, c_int, c_int, c_int]
     L.orag_exchange_alloc.argtypes = [c_size_t, POINTER(c_void_p)]
@@ -128,12 +137,13 @@ def lib() -> ctypes.CDLL:
     L.orag_exchange_export.argtypes = [vp, ctypes.c_char_p]
     L.orag_exchange_open.argtypes = [ctypes.c_char_p, POINTER(c_void_p)]
     L.orag_exchange_close.argtypes = [vp]
-    L.orag_hybrid_push.argtypes = [vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp, c_uint64, vp]
+    L.orag_hybrid_push.argtypes = [vp, vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp, c_uint64, vp]
     L.orag_hybrid_wait.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_uint64, c_int, POINTER(c_void_p), vp]
     for name in SYMBOLS:
         f = getattr(L, name)
         if name not in ("orag_last_error", "orag_launch_count", "orag_cosine_workspace_bytes", "orag_bm25_workspace_bytes",
-                        "orag_pairwise_workspace_bytes", "orag_pairwise_tc_workspace_bytes", "orag_exchange_bytes"):
+                        "orag_pairwise_workspace_bytes", "orag_pairwise_tc_workspace_bytes", "orag_exchange_bytes",
+                        "orag_pairwise_prepared_bytes", "orag_pairwise_pairs_workspace_bytes"):
             f.restype = c_int
     _lib = L
     return L

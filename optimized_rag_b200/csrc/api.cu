@@ -24,20 +24,33 @@ void set_error(const char *fmt, ...)
 // ---- profiling hooks ------------------------------------------------------------------------------
 static std::atomic<unsigned long long> g_launches{0};
 static int g_profile = 0;
-static cudaEvent_t g_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-static int g_ev_used[2] = {0, 0};
+// ring of event pairs per slot: every bracket recorded since orag_profile_enable(1) (up to kProfRing) can be read back,
+// so that a roofline figure rests on all timed steps rather than on the last one
+constexpr int kProfRing = 256;
+static cudaEvent_t g_ev[2][kProfRing][2];
+static bool g_ev_made[2][kProfRing];
+static int g_ev_n[2] = {0, 0};      // completed brackets per slot (may exceed kProfRing: the ring then holds the last ones)
+static int g_ev_open[2] = {-1, -1}; // ring index of the bracket whose start has been recorded
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void profile_mark(int slot, int end, cudaStream_t st)
 {
     if (!g_profile || slot < 0 || slot > 1) return;
-    if (!g_ev[slot][0]) {
-        cudaEventCreate(&g_ev[slot][0]);
-        cudaEventCreate(&g_ev[slot][1]);
+    if (!end) {
+        const int i = g_ev_n[slot] % kProfRing;
+        if (!g_ev_made[slot][i]) {
+            cudaEventCreate(&g_ev[slot][i][0]);
+            cudaEventCreate(&g_ev[slot][i][1]);
+            g_ev_made[slot][i] = true;
+        }
+        cudaEventRecord(g_ev[slot][i][0], st);
+        g_ev_open[slot] = i;
+    } else if (g_ev_open[slot] >= 0) {
+        cudaEventRecord(g_ev[slot][g_ev_open[slot]][1], st);
+        g_ev_open[slot] = -1;
+        ++g_ev_n[slot];
     }
-    cudaEventRecord(g_ev[slot][end ? 1 : 0], st);
-    if (end) g_ev_used[slot] = 1;
 }
 
 // inv_qnorm_s = 1 / (|q| * scale) from the fp16 conversion of the query block -> the other three views of the norm
@@ -96,11 +109,23 @@ static int g_mark_prescan = 0;
 //                                                   -> |rel err per product| < 2^-7 + 2^-16
 //   fp16: both operands rounded to nearest, 11 significant bits, rows and queries pre-scaled by powers of two
 //         (cosine_exact.cu f32_to_f16_rows_kernel)  -> |rel err per product| < 2^-10 + 2^-22
-// sum |a_i b_i| <= |a||b| turns that into an absolute bound on the cosine; 2.5e-4 covers fp32
-// accumulation in the tensor core (1536 terms), the fp32 inv-norm and the epilogue multiply.
-constexpr float kEpsTf32 = 1.954e-3f + 2.5e-4f;
-constexpr float kEpsBf16 = 7.83e-3f + 2.5e-4f;
-constexpr float kEpsF16 = 9.77e-4f + 2.5e-4f;
+// sum |a_i b_i| <= |a||b| turns that into an absolute bound on the cosine.  On top of the operand term comes the
+// accumulation term, which grows with the vector length: a chain of `dim` fp32 additions whose every partial sum is
+// bounded by sum |a_i b_i| contributes at most dim * 2^-23 (round-toward-zero worst case of the tensor core's
+// accumulator), plus 64 * 2^-23 for the fp32 inverse norms, the epilogue multiply and the threshold arithmetic:
+// first_pass_eps(dim) -- 2.5e-4 up to dim = 2033 (the constant the 1536-d captures were taken with), linear beyond.
+constexpr float kOperandTf32 = 1.954e-3f;
+constexpr float kOperandBf16 = 7.83e-3f;
+constexpr float kOperandF16 = 9.77e-4f;
+
+}  // namespace orag
+float orag::tc::first_pass_eps(int mode, int dim)
+{
+    const float operand = mode == ORAG_COS_F16 ? kOperandF16 : mode == ORAG_COS_BF16 ? kOperandBf16 : kOperandTf32;
+    const float accumulate = (float)(dim + 64) * 1.1920929e-7f;  // 2^-23
+    return operand + (accumulate > 2.5e-4f ? accumulate : 2.5e-4f);
+}
+namespace orag {
 
 constexpr int kGroup = 256;     // queries per tensor-core pass (UMMA N)
 constexpr int kSeedRows = 2048; // rows of the dense seed pass that initialises the thresholds
@@ -170,8 +195,24 @@ extern "C" unsigned long long orag_launch_count(void) { return orag::g_launches.
 extern "C" int orag_profile_enable(int on)
 {
     orag::g_profile = on ? 1 : 0;
-    orag::g_ev_used[0] = orag::g_ev_used[1] = 0;
+    orag::g_ev_n[0] = orag::g_ev_n[1] = 0;
+    orag::g_ev_open[0] = orag::g_ev_open[1] = -1;
     return ORAG_OK;
+}
+
+extern "C" int orag_profile_read_all(int slot, float *ms, int cap)
+{
+    ORAG_REQUIRE(slot >= 0 && slot <= 1 && (ms || cap == 0) && cap >= 0, "profile_read_all");
+    const int total = orag::g_ev_n[slot];
+    const int have = total < orag::kProfRing ? total : orag::kProfRing;
+    const int n = have < cap ? have : cap;
+    // oldest first among the brackets still in the ring
+    for (int j = 0; j < n; ++j) {
+        const int i = (total - have + j) % orag::kProfRing;
+        ORAG_CUDA_CHECK(cudaEventSynchronize(orag::g_ev[slot][i][1]));
+        ORAG_CUDA_CHECK(cudaEventElapsedTime(ms + j, orag::g_ev[slot][i][0], orag::g_ev[slot][i][1]));
+    }
+    return n;
 }
 
 extern "C" int orag_profile_read(float *scan_ms, float *bm25_ms)
@@ -180,9 +221,11 @@ extern "C" int orag_profile_read(float *scan_ms, float *bm25_ms)
     for (int s = 0; s < 2; ++s) {
         if (!out[s]) continue;
         *out[s] = -1.f;
-        if (!orag::g_ev_used[s]) continue;
-        ORAG_CUDA_CHECK(cudaEventSynchronize(orag::g_ev[s][1]));
-        ORAG_CUDA_CHECK(cudaEventElapsedTime(out[s], orag::g_ev[s][0], orag::g_ev[s][1]));
+        const int total = orag::g_ev_n[s];
+        if (total <= 0) continue;
+        const int i = (total - 1) % orag::kProfRing;
+        ORAG_CUDA_CHECK(cudaEventSynchronize(orag::g_ev[s][i][1]));
+        ORAG_CUDA_CHECK(cudaEventElapsedTime(out[s], orag::g_ev[s][i][0], orag::g_ev[s][i][1]));
     }
     return ORAG_OK;
 }
@@ -273,7 +316,7 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
                  "16-byte alignment");
     ORAG_REQUIRE(k <= 128, "k <= 128 for tensor-core modes");
     CosineWs w = carve_tc(d_workspace, dim);
-    const float margin = 2.f * (f16 ? kEpsF16 : bf16 ? kEpsBf16 : kEpsTf32);
+    const float margin = 2.f * tc::first_pass_eps(mode, dim);
     const int n_seed = (int)(n_rows < kSeedRows ? n_rows : kSeedRows);
 
     for (int q0 = 0; q0 < n_queries; q0 += kGroup) {

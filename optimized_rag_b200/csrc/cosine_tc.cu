@@ -13,7 +13,7 @@
 //                       and half of the query slab (cta_group::2 TMA, completing on the leader's mbarrier);
 //                       six 32 KiB stages
 //   cluster2 (runtime)  pairs of 1-SM MMAs, each CTA multicasts half of the query slab to both (ORAG_SCAN_2SM=0)
-//   plain               one CTA per tile, four 48 KiB stages: seed / dense passes, small inputs, pair mode
+//   plain               one CTA per tile, four 48 KiB stages: seed / dense passes, small inputs
 //
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
 // warp 2 = TMEM allocator, warp 3 idle, warps 4-11 = epilogue (two warps per TMEM lane quarter,
@@ -606,24 +606,25 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
     int rc = make_map(&map_a, a_base, bf16, p.f16 != 0, a_rows, dim, kTileM);
     if (rc) return rc;
     p.num_tiles = (int)((p.row_end - p.row_begin + kTileM - 1) / kTileM);
-    // clusters of two CTAs sharing the query slabs: main scans only, enough tiles to keep every pair busy
-    // (ORAG_SCAN_CLUSTER: 0 = never, 1 = default rule, 2 = whenever there are two tiles -- tests)
-    static const int cluster_mode = getenv("ORAG_SCAN_CLUSTER") ? atoi(getenv("ORAG_SCAN_CLUSTER")) : 1;
-    const int min_tiles = cluster_mode >= 2 ? 2 : 4 * sm_count();
-    p.cluster2 = (cluster_mode && !p.dense && !p.pair_mode && p.umma_n >= 32 && p.num_tiles >= min_tiles) ? 1 : 0;
-    // the pairs issue one tcgen05.mma.cta_group::2 per K step unless ORAG_SCAN_2SM=0 (then: multicast pairs)
-    static const int mma2_mode = getenv("ORAG_SCAN_2SM") ? atoi(getenv("ORAG_SCAN_2SM")) : 1;
-    p.mma2 = (mma2_mode && p.cluster2) ? 1 : 0;
-    rc = make_map(&map_b, q_base, bf16, p.f16 != 0, p.n_queries, dim,
-                  p.pair_mode ? kMaxN : (p.cluster2 ? p.umma_n / 2 : p.umma_n));
-    if (rc) return rc;
-    p.chunk_elems = bf16 ? 64 : 32;
-    p.k_chunks = dim / p.chunk_elems;
     if (p.pair_mode) {
+        // triangular enumeration: query block qb owns the 2 (qb + 1) row tiles below its end -- an even count starting
+        // at an even index, so the two CTAs of a pair always share their query block
         const int nb = (p.n_queries + kMaxN - 1) / kMaxN;
         p.num_tiles = nb * (nb + 1);
         p.umma_n = kMaxN;
     }
+    // clusters of two CTAs sharing the query slabs: main scans only, enough tiles to keep every pair busy
+    // (ORAG_SCAN_CLUSTER: 0 = never, 1 = default rule, 2 = whenever there are two tiles -- tests)
+    static const int cluster_mode = getenv("ORAG_SCAN_CLUSTER") ? atoi(getenv("ORAG_SCAN_CLUSTER")) : 1;
+    const int min_tiles = cluster_mode >= 2 ? 2 : 4 * sm_count();
+    p.cluster2 = (cluster_mode && !p.dense && p.umma_n >= 32 && p.num_tiles >= min_tiles) ? 1 : 0;
+    // the pairs issue one tcgen05.mma.cta_group::2 per K step unless ORAG_SCAN_2SM=0 (then: multicast pairs)
+    static const int mma2_mode = getenv("ORAG_SCAN_2SM") ? atoi(getenv("ORAG_SCAN_2SM")) : 1;
+    p.mma2 = (mma2_mode && p.cluster2) ? 1 : 0;
+    rc = make_map(&map_b, q_base, bf16, p.f16 != 0, p.n_queries, dim, p.cluster2 ? p.umma_n / 2 : p.umma_n);
+    if (rc) return rc;
+    p.chunk_elems = bf16 ? 64 : 32;
+    p.k_chunks = dim / p.chunk_elems;
     p.idesc = make_idesc(bf16, p.f16 != 0, p.umma_n);
     if (p.mma2) p.idesc = (p.idesc & ~(0x1Fu << 24)) | ((uint32_t)(2 * kTileM >> 4) << 24);  // M = 256 over the pair
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();

@@ -54,6 +54,8 @@ struct ScanParams {
 
 int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_base, int dim, ScanParams p,
                 cudaStream_t st);
+// |first-pass cosine - cosine| bound of a tensor-core mode (ORAG_COS_TF32 / BF16 / F16) at vector length `dim` (api.cu)
+float first_pass_eps(int mode, int dim);
 int launch_seed_finalize(const float *seed, int n_seed, int n_queries, int k, float margin, const float *qnorm,
                          const float *inv_qnorm, uint32_t *thr_key, uint32_t *cnt, uint32_t *hist, int32_t *cand,
                          int cap, cudaStream_t st);

@@ -52,7 +52,8 @@ __device__ __forceinline__ unsigned long long global_ns()
 // CTA p packs this rank's block and stores it into peer p's slot (p == rank: its own buffer).
 __global__ void __launch_bounds__(256) exchange_push_kernel(
     const int64_t *__restrict__ cos_ids, const double *__restrict__ cos_scores, const int64_t *__restrict__ bm_ids,
-    const double *__restrict__ bm_scores, const double *__restrict__ bm_max, const int32_t *__restrict__ status, int B,
+    const double *__restrict__ bm_scores, const double *__restrict__ bm_max, const int32_t *__restrict__ status,
+    const int32_t *__restrict__ status2, int B,
     int fetch_k, int kk, int rank, int G, void *const *__restrict__ peers, size_t flag_bytes, size_t slot_words,
     unsigned long long seq)
 {
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(
         else if (c < 2 * fetch_k + kk) v = bm_ids[q * kk + c - 2 * fetch_k];
         else if (c < 2 * fetch_k + 2 * kk) v = __double_as_longlong(bm_scores[q * kk + c - 2 * fetch_k - kk]);
         else if (c == W - 2) v = __double_as_longlong(bm_max[q]);
-        else v = status ? (int64_t)status[q] : 0;
+        else v = (int64_t)((status ? status[q] : 0) | (status2 ? status2[q] : 0));
         dst[i] = v;
     }
     // every thread's stores are ordered before the flag: fence (system scope), CTA barrier, release store
@@ -154,7 +155,8 @@ extern "C" int orag_exchange_close(void *d_peer_buf)
 
 extern "C" int orag_hybrid_push(const int64_t *d_cos_ids, const double *d_cos_scores, const int64_t *d_bm25_ids,
                                 const double *d_bm25_scores, const double *d_bm25_max, const int32_t *d_status,
-                                int n_queries, int fetch_k, int kk, int rank, int n_shards, int max_queries,
+                                const int32_t *d_status2, int n_queries, int fetch_k, int kk, int rank, int n_shards,
+                                int max_queries,
                                 void *const *d_peer_bufs, uint64_t seq, void *stream)
 {
     ORAG_REQUIRE(d_cos_ids && d_cos_scores && d_bm25_ids && d_bm25_scores && d_bm25_max && d_peer_bufs, "hybrid_push pointers");
@@ -162,7 +164,8 @@ extern "C" int orag_hybrid_push(const int64_t *d_cos_ids, const double *d_cos_sc
     ORAG_REQUIRE(n_queries >= 1 && n_queries <= max_queries && fetch_k >= 1 && kk >= fetch_k && seq >= 1,
                  "hybrid_push sizes");
     exchange_push_kernel<<<n_shards, 256, 0, (cudaStream_t)stream>>>(
-        d_cos_ids, d_cos_scores, d_bm25_ids, d_bm25_scores, d_bm25_max, d_status, n_queries, fetch_k, kk, rank, n_shards,
+        d_cos_ids, d_cos_scores, d_bm25_ids, d_bm25_scores, d_bm25_max, d_status, d_status2, n_queries, fetch_k, kk, rank,
+        n_shards,
         d_peer_bufs, x_flag_bytes(n_shards), x_slot_words(n_shards, max_queries, fetch_k, kk), (unsigned long long)seq);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;

@@ -101,18 +101,34 @@ extern "C" int orag_pairwise_cosine_threshold(const float *d_emb, int64_t m, int
 }
 
 // ================================================================================================
-// Tensor-core path (BASELINE config 5: 64k claims x 1536): the similarity scan of cosine_tc.cu with
-// a FIXED threshold, in pair mode: ONE launch walks the triangular space of (256-row query block j,
-// 128-row tile i below the block's end), tf32 straight off the fp32 embeddings; every (i < j) whose
-// first-pass cosine clears
-// threshold - eps_tf32 is re-scored in the reference's float64 arithmetic and kept if i < j,
-// doc_idx differ and the exact cosine >= threshold.  |first pass - exact| <= eps, so no pair is lost.
+// Tensor-core path (BASELINE config 5: 64k claims x 1536): the similarity scan of cosine_tc.cu with a FIXED
+// threshold, in pair mode: ONE launch walks the triangular space of (256-row query block j, 128-row tile i below
+// the block's end).  Operands: the fp16 shadow of the embeddings, every row scaled by a power of two
+// (orag_f32_to_f16_rows; kind::f16, CTA pairs with one tcgen05.mma.cta_group::2 per K step exactly like the
+// retrieval scan) when dim % 64 == 0, else tf32 straight off the fp32 rows.  The threshold compare runs on the
+// accumulators as they leave TMEM; every (i < j) whose first-pass cosine clears threshold - eps(mode, dim) is
+// re-scored in the reference's float64 arithmetic and kept if doc_idx differ and the exact cosine >= threshold.
+// |first pass - exact| <= eps, so no pair is lost.
+//
+// Ingest and search are separate calls: orag_pairwise_prepare derives, once per claim matrix, the fp16 shadow,
+// the first-pass norms and the float64 sum(a*a) of every row; orag_pairwise_pairs runs the search over them.
 #include "cosine_tc.cuh"
+
+extern "C" int orag_f32_to_f16_rows(const float *d_src, int64_t n_rows, int dim, void *d_dst_f16,
+                                    float *d_inv_norm_scaled, float *d_scale, void *stream);
+extern "C" int orag_row_inv_norms(const float *d_corpus, int64_t n_rows, int dim, float *d_inv_norm, void *stream);
 
 namespace orag {
 
-constexpr int kPairCap = 64;                      // first-pass candidates (i < j) per row j
-constexpr float kPairEps = 1.954e-3f + 2.5e-4f;  // tf32 first-pass bound (see api.cu)
+constexpr int kPairCap = 64;  // first-pass candidates (i < j) per row j
+
+// qnorm[r] = 1 / inv_norm[r]: the row's magnitude in the units of the first-pass accumulators (|x| * scale for the
+// fp16 shadow, |x| for tf32); 0 for an all-zero row
+__global__ void pair_qnorm_kernel(const float *__restrict__ inv_norm, int64_t n, float *__restrict__ qnorm)
+{
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r < n) qnorm[r] = inv_norm[r] > 0.f ? 1.f / inv_norm[r] : 0.f;
+}
 
 __global__ void pair_thr_init_kernel(const float *__restrict__ qnorm, int64_t n, float thr,
                                      uint32_t *__restrict__ thr_key, uint32_t *__restrict__ cnt)
@@ -157,9 +173,39 @@ __global__ void __launch_bounds__(256) pair_filter_kernel(const double *__restri
     }
 }
 
-struct PairWs {
-    double *sq;
-    float *inv_norm, *qnorm, *inv_qnorm;
+static inline bool pair_f16(int dim)
+{
+    static const int force_tf32 = getenv("ORAG_PAIR_TF32") ? atoi(getenv("ORAG_PAIR_TF32")) : 0;
+    return dim % 64 == 0 && !force_tf32;
+}
+
+struct PairPrep {   // per claim matrix (orag_pairwise_prepare)
+    double *sq;      // [m] float64 sum(a*a), reference arithmetic
+    float *inv_norm; // [m] first-pass 1/|row| (fp16 mode: divided by the row's power-of-two scale as well)
+    float *qnorm;    // [m] 1 / inv_norm
+    void *shadow;    // [m, dim] fp16, rows scaled (fp16 mode only)
+    size_t bytes;
+};
+
+static PairPrep carve_prep(void *base, int64_t m, int dim)
+{
+    PairPrep w{};
+    uint8_t *p = (uint8_t *)base;
+    auto take = [&](size_t n) {
+        uint8_t *r = p;
+        p += align_up(n, 256);
+        return r;
+    };
+    const size_t mm = (size_t)(m > 0 ? m : 1);
+    w.sq = (double *)take(mm * 8);
+    w.inv_norm = (float *)take(mm * 4);
+    w.qnorm = (float *)take(mm * 4);
+    w.shadow = pair_f16(dim) ? take(mm * (size_t)dim * 2) : nullptr;
+    w.bytes = (size_t)(p - (uint8_t *)base);
+    return w;
+}
+
+struct PairWs {     // per search (orag_pairwise_pairs)
     uint32_t *thr_key, *cnt;
     int32_t *cand;
     double *scores;
@@ -177,10 +223,6 @@ static PairWs carve_pair(void *base, int64_t m)
         return r;
     };
     const size_t mm = (size_t)(m > 0 ? m : 1);
-    w.sq = (double *)take(mm * 8);
-    w.inv_norm = (float *)take(mm * 4);
-    w.qnorm = (float *)take(mm * 4);
-    w.inv_qnorm = (float *)take(mm * 4);
     w.thr_key = (uint32_t *)take(mm * 4);
     w.cnt = (uint32_t *)take(mm * 4);
     w.cand = (int32_t *)take(mm * kPairCap * 4);
@@ -192,12 +234,93 @@ static PairWs carve_pair(void *base, int64_t m)
 
 }  // namespace orag
 
-extern "C" int orag_row_inv_norms(const float *d_corpus, int64_t n_rows, int dim, float *d_inv_norm, void *stream);
+extern "C" size_t orag_pairwise_prepared_bytes(int64_t m, int dim) { return orag::carve_prep(nullptr, m, dim).bytes; }
+extern "C" size_t orag_pairwise_pairs_workspace_bytes(int64_t m) { return orag::carve_pair(nullptr, m).bytes; }
 
+extern "C" int orag_pairwise_prepare(const float *d_emb, int64_t m, int dim, void *d_prepared, size_t prepared_bytes,
+                                     void *stream)
+{
+    using namespace orag;
+    ORAG_REQUIRE(d_emb && d_prepared && m >= 0 && dim > 0 && dim % 32 == 0 && m < ((int64_t)1 << 31), "pairwise_prepare");
+    ORAG_REQUIRE((reinterpret_cast<uintptr_t>(d_emb) & 15) == 0, "16-byte alignment");
+    if (prepared_bytes < orag_pairwise_prepared_bytes(m, dim)) {
+        set_error("pairwise_prepare: buffer too small");
+        return ORAG_EWORKSPACE;
+    }
+    if (m == 0) return ORAG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    PairPrep w = carve_prep(d_prepared, m, dim);
+    int64_t blocks = ((m + 31) / 32 + 7) / 8;
+    pair_sq_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_emb, m, dim, w.sq);
+    ORAG_LAUNCH_CHECK();
+    int rc = w.shadow ? orag_f32_to_f16_rows(d_emb, m, dim, w.shadow, w.inv_norm, nullptr, st)
+                      : orag_row_inv_norms(d_emb, m, dim, w.inv_norm, st);
+    if (rc) return rc;
+    pair_qnorm_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(w.inv_norm, m, w.qnorm);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+extern "C" int orag_pairwise_pairs(const float *d_emb, const void *d_prepared, int64_t m, int dim,
+                                   const int32_t *d_doc_idx, double threshold, int64_t cap, int32_t *d_out_i,
+                                   int32_t *d_out_j, double *d_out_sim, unsigned long long *d_out_count,
+                                   void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace orag;
+    ORAG_REQUIRE(d_emb && d_prepared && d_doc_idx && d_out_i && d_out_j && d_out_sim && d_out_count && m >= 0 && dim > 0 &&
+                     cap >= 0,
+                 "pairwise_pairs");
+    ORAG_REQUIRE(dim % 32 == 0 && m < ((int64_t)1 << 31), "dim % 32 == 0");
+    ORAG_REQUIRE(m <= 256 * 1024, "pairwise_pairs: at most 262144 rows (triangular tile index)");
+    const bool f16 = pair_f16(dim);
+    const float eps = tc::first_pass_eps(f16 ? ORAG_COS_F16 : ORAG_COS_TF32, dim);
+    ORAG_REQUIRE(threshold > (double)eps, "tensor-core path needs threshold > first-pass error bound");
+    if (workspace_bytes < orag_pairwise_pairs_workspace_bytes(m) || !d_workspace) {
+        set_error("pairwise_pairs: workspace too small");
+        return ORAG_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    ORAG_CUDA_CHECK(cudaMemsetAsync(d_out_count, 0, 2 * sizeof(unsigned long long), st));
+    if (m < 2) return ORAG_OK;
+    PairPrep pre = carve_prep(const_cast<void *>(d_prepared), m, dim);
+    PairWs w = carve_pair(d_workspace, m);
+    pair_thr_init_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(pre.qnorm, m, (float)threshold, w.thr_key, w.cnt);
+    ORAG_LAUNCH_CHECK();
+    // ONE tensor-core launch over the triangular (query block, row tile) space
+    tc::ScanParams p{};
+    p.f16 = f16 ? 1 : 0;
+    p.n_queries = (int)m;
+    p.inv_norm = pre.inv_norm;
+    p.thr_key = w.thr_key;
+    p.cnt = w.cnt;
+    p.hist = nullptr;
+    p.cand = w.cand;
+    p.cap = kPairCap;
+    p.qnorm = pre.qnorm;
+    p.inv_qnorm = nullptr;
+    p.margin = eps + 1e-6f;  // one-sided: cos >= t  =>  first pass >= t - eps (+ float(threshold) rounding)
+    p.k = 0x7fffffff;
+    p.fixed_thr = 1;
+    p.pair_mode = 1;
+    p.row_begin = 0;
+    p.row_end = m;
+    p.dense = 0;
+    const void *op = f16 ? (const void *)pre.shadow : (const void *)d_emb;
+    int rc = tc::launch_scan(f16, op, m, op, dim, p, st);
+    if (rc) return rc;
+    // float64 re-score of every surviving (i, j) in the reference's arithmetic, then the exact filter
+    rc = launch_rescore(d_emb, dim, 0, d_emb, pre.sq, w.cand, w.cnt, kPairCap, (int)m, pre.sq, w.scores, w.ids, st);
+    if (rc) return rc;
+    pair_filter_kernel<<<sm_count() * 8, 256, 0, st>>>(w.scores, w.ids, w.cnt, kPairCap, m, d_doc_idx, threshold, cap,
+                                                       d_out_i, d_out_j, d_out_sim, d_out_count);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+// One-call form: prepare + pairs out of a single workspace.
 extern "C" size_t orag_pairwise_tc_workspace_bytes(int64_t m, int dim)
 {
-    (void)dim;
-    return orag::carve_pair(nullptr, m).bytes;
+    return orag_pairwise_prepared_bytes(m, dim) + orag_pairwise_pairs_workspace_bytes(m);
 }
 
 extern "C" int orag_pairwise_cosine_threshold_tc(const float *d_emb, int64_t m, int dim, const int32_t *d_doc_idx,
@@ -206,53 +329,14 @@ extern "C" int orag_pairwise_cosine_threshold_tc(const float *d_emb, int64_t m, 
                                                  size_t workspace_bytes, void *stream)
 {
     using namespace orag;
-    ORAG_REQUIRE(d_emb && d_doc_idx && d_out_i && d_out_j && d_out_sim && d_out_count && m >= 0 && dim > 0 && cap >= 0,
-                 "pairwise_tc");
-    ORAG_REQUIRE(dim % 32 == 0 && m < ((int64_t)1 << 31), "dim % 32 == 0");
-    ORAG_REQUIRE(m <= 256 * 1024, "pairwise_tc: at most 262144 rows (triangular tile index)");
-    ORAG_REQUIRE(threshold > (double)kPairEps, "tensor-core path needs threshold > first-pass error bound");
-    if (workspace_bytes < orag_pairwise_tc_workspace_bytes(m, dim) || !d_workspace) {
+    ORAG_REQUIRE(d_workspace && dim > 0 && m >= 0, "pairwise_tc");
+    if (workspace_bytes < orag_pairwise_tc_workspace_bytes(m, dim)) {
         set_error("pairwise_tc: workspace too small");
         return ORAG_EWORKSPACE;
     }
-    cudaStream_t st = (cudaStream_t)stream;
-    ORAG_CUDA_CHECK(cudaMemsetAsync(d_out_count, 0, 2 * sizeof(unsigned long long), st));
-    if (m < 2) return ORAG_OK;
-    PairWs w = carve_pair(d_workspace, m);
-    int64_t blocks = ((m + 31) / 32 + 7) / 8;
-    pair_sq_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_emb, m, dim, w.sq);
-    ORAG_LAUNCH_CHECK();
-    int rc = orag_row_inv_norms(d_emb, m, dim, w.inv_norm, st);
+    const size_t pb = orag_pairwise_prepared_bytes(m, dim);
+    int rc = orag_pairwise_prepare(d_emb, m, dim, d_workspace, pb, stream);
     if (rc) return rc;
-    rc = tc::launch_query_norms(w.sq, (int)m, w.qnorm, w.inv_qnorm, st);
-    if (rc) return rc;
-    pair_thr_init_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(w.qnorm, m, (float)threshold, w.thr_key, w.cnt);
-    ORAG_LAUNCH_CHECK();
-    // ONE tensor-core launch over the triangular (query block, row tile) space
-    tc::ScanParams p{};
-    p.n_queries = (int)m;
-    p.inv_norm = w.inv_norm;
-    p.thr_key = w.thr_key;
-    p.cnt = w.cnt;
-    p.hist = nullptr;
-    p.cand = w.cand;
-    p.cap = kPairCap;
-    p.qnorm = w.qnorm;
-    p.inv_qnorm = w.inv_qnorm;
-    p.margin = kPairEps + 1e-6f;  // one-sided: cos >= t  =>  first pass >= t - eps (+ float(threshold) rounding)
-    p.k = 0x7fffffff;
-    p.fixed_thr = 1;
-    p.pair_mode = 1;
-    p.row_begin = 0;
-    p.row_end = m;
-    p.dense = 0;
-    rc = tc::launch_scan(false, d_emb, m, d_emb, dim, p, st);
-    if (rc) return rc;
-    // float64 re-score of every surviving (i, j) in the reference's arithmetic, then the exact filter
-    rc = launch_rescore(d_emb, dim, 0, d_emb, w.sq, w.cand, w.cnt, kPairCap, (int)m, w.sq, w.scores, w.ids, st);
-    if (rc) return rc;
-    pair_filter_kernel<<<sm_count() * 8, 256, 0, st>>>(w.scores, w.ids, w.cnt, kPairCap, m, d_doc_idx, threshold, cap,
-                                                       d_out_i, d_out_j, d_out_sim, d_out_count);
-    ORAG_LAUNCH_CHECK();
-    return ORAG_OK;
+    return orag_pairwise_pairs(d_emb, d_workspace, m, dim, d_doc_idx, threshold, cap, d_out_i, d_out_j, d_out_sim,
+                               d_out_count, (uint8_t *)d_workspace + pb, workspace_bytes - pb, stream);
 }

@@ -77,6 +77,27 @@ __global__ void __launch_bounds__(128) rrf_kernel(const int64_t *__restrict__ li
             out_src ? out_src + (int64_t)q * top_k * n_lists : nullptr);
 }
 
+// The one-shard hybrid step: the two ranked lists live in two separate arrays (the outputs of orag_cosine_topk and
+// orag_bm25_topk); fuse them in place and OR the two per-query status words -- no packing kernel in between.
+__global__ void __launch_bounds__(128) rrf_pair_kernel(const int64_t *__restrict__ ids_a, const int64_t *__restrict__ ids_b,
+                                                      int n_queries, int list_len, int rrf_k, int top_k, int tie_mode,
+                                                      const int32_t *__restrict__ status_a,
+                                                      const int32_t *__restrict__ status_b,
+                                                      int64_t *__restrict__ out_ids, double *__restrict__ out_scores,
+                                                      int32_t *__restrict__ out_src, int32_t *__restrict__ out_status)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries) return;
+    int64_t both[kRrfMaxUnion];
+    for (int r = 0; r < list_len; ++r) {
+        both[r] = ids_a[(int64_t)q * list_len + r];
+        both[list_len + r] = ids_b[(int64_t)q * list_len + r];
+    }
+    rrf_one(both, 2, list_len, list_len, rrf_k, top_k, tie_mode, out_ids + (int64_t)q * top_k,
+            out_scores + (int64_t)q * top_k, out_src ? out_src + (int64_t)q * top_k * 2 : nullptr);
+    if (out_status) out_status[q] = (status_a ? status_a[q] : 0) | (status_b ? status_b[q] : 0);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Everything that follows the all-gather of a row-sharded hybrid search, in ONE launch (one 64-thread
 // CTA per query): merge the G shards' cosine winners by (score desc, id asc); divide the shards' raw
@@ -172,6 +193,22 @@ extern "C" int orag_rrf_fuse(const int64_t *d_list_ids, int n_queries, int n_lis
     if (n_queries == 0) return ORAG_OK;
     orag::rrf_kernel<<<(n_queries + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         d_list_ids, n_queries, n_lists, list_len, rrf_k, top_k, tie_mode, d_out_ids, d_out_scores, d_out_src);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
+extern "C" int orag_rrf_fuse_pair(const int64_t *d_ids_a, const int64_t *d_ids_b, int n_queries, int list_len, int rrf_k,
+                                  int top_k, int tie_mode, const int32_t *d_status_a, const int32_t *d_status_b,
+                                  int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_src, int32_t *d_out_status,
+                                  void *stream)
+{
+    ORAG_REQUIRE(d_ids_a && d_ids_b && d_out_ids && d_out_scores, "rrf_fuse_pair pointers");
+    ORAG_REQUIRE(n_queries >= 0 && list_len >= 1 && 2 * list_len <= orag::kRrfMaxUnion && top_k >= 1 && rrf_k >= 0,
+                 "rrf_fuse_pair sizes (2 * list_len <= 128)");
+    if (n_queries == 0) return ORAG_OK;
+    orag::rrf_pair_kernel<<<(n_queries + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        d_ids_a, d_ids_b, n_queries, list_len, rrf_k, top_k, tie_mode, d_status_a, d_status_b, d_out_ids, d_out_scores,
+        d_out_src, d_out_status);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }

@@ -103,7 +103,7 @@ def hybrid_merge(gathered, fetch_k: int, kk: int, rrf_k: int, k: int, shape=None
                                             fs.data_ptr(), src.data_ptr(), ci.data_ptr(), cs.data_ptr(), bi.data_ptr(),
                                             bs.data_ptr(), bmax.data_ptr(), status.data_ptr(),
                                             torch.cuda.current_stream(dev).cuda_stream), "orag_hybrid_merge")
-    return {"ids": fi, "rrf_scores": fs, "src_ranks": src, "cos_ids": ci, "cos_scores": cs, "bm25_ids": bi,
+    return {"ids": fi, "rrf_scores": fs, "scores": fs, "src_ranks": src, "cos_ids": ci, "cos_scores": cs, "bm25_ids": bi,
             "bm25_scores": bs, "bm25_max": bmax}, status
 
 
@@ -172,18 +172,21 @@ class PeerExchange:
     def fits(self, n_queries: int, fetch_k: int, kk: int) -> bool:
         return n_queries <= self.max_queries and fetch_k == self.fetch_k and kk == self.kk
 
-    def exchange(self, cos_ids, cos_scores, bm_ids, bm_scores, bm_max, status):
-        """Push this rank's lists to every peer, wait for theirs -> (device pointer of [G, B, W], shape)."""
+    def exchange(self, cos_ids, cos_scores, bm_ids, bm_scores, bm_max, status, status2=None):
+        """Push this rank's lists to every peer, wait for theirs -> (device pointer of [G, B, W], shape).  `status` and
+        the optional `status2` (the cosine and the BM25 call's overflow words) are OR-ed by the push kernel."""
         L = _ffi.lib()
         Bq = cos_ids.shape[0]
         assert self.fits(Bq, cos_ids.shape[1], bm_ids.shape[1])
         for t in (cos_ids, cos_scores, bm_ids, bm_scores, bm_max, status):
             assert t.is_contiguous() and t.device == self.device
         assert status.dtype == torch.int32 and bm_max.dtype == torch.float64
+        assert status2 is None or (status2.dtype == torch.int32 and status2.is_contiguous())
         self.seq += 1
         st = torch.cuda.current_stream(self.device).cuda_stream
         _ffi.check(L.orag_hybrid_push(cos_ids.data_ptr(), cos_scores.data_ptr(), bm_ids.data_ptr(), bm_scores.data_ptr(),
-                                      bm_max.data_ptr(), status.data_ptr(), Bq, self.fetch_k, self.kk, self.rank,
+                                      bm_max.data_ptr(), status.data_ptr(),
+                                      status2.data_ptr() if status2 is not None else None, Bq, self.fetch_k, self.kk, self.rank,
                                       self.world, self.max_queries, self._d_peers.data_ptr(), self.seq, st),
                    "orag_hybrid_push")
         out = ctypes.c_void_p()
@@ -232,7 +235,7 @@ class ShardedHybrid:
         self._retired: list[PeerExchange] = []  # outgrown exchanges: peers may still have them mapped until close()
 
     def _exchange(self, lists, fetch_k: int, kk: int, k: int):
-        ci, cs, bi, bs, bm, st = lists
+        ci, cs, bi, bs, bm, st, st2 = lists
         if self.exchange == "peer":
             Bq = ci.shape[0]
             if self._peer is None or not self._peer.fits(Bq, fetch_k, kk):
@@ -246,9 +249,9 @@ class ShardedHybrid:
                     logger.warning("peer exchange unavailable, using the NCCL all-gather: %s", e)
                     self.exchange, self.exchange_note = "nccl", f"peer setup failed: {e}"
         if self.exchange == "peer":
-            ptr, shape = self._peer.exchange(ci, cs, bi, bs, bm, st)
+            ptr, shape = self._peer.exchange(ci, cs, bi, bs, bm, st, st2)
             return hybrid_merge(ptr, fetch_k, kk, self.shard.rrf_k, k, shape=shape, device=ci.device)
-        mine = pack_local(ci, cs, bi, bs, bm, st)
+        mine = pack_local(ci, cs, bi, bs, bm, st if st2 is None else st | st2)
         Bq, W = mine.shape
         if self._gather_buf is None or self._gather_buf.shape != (self.world, Bq, W):
             self._gather_buf = torch.empty((self.world, Bq, W), dtype=torch.int64, device=mine.device)
@@ -272,8 +275,8 @@ class ShardedHybrid:
         if self.world == 1:
             return self.shard.search(query_emb, query_terms, query_lens, k, fetch_k, check_overflow)
         kk = fetch_k + BM25_GUARD
-        ci, cs, bi, bs, bm, st = self.shard.local_lists(query_emb, query_terms, query_lens, fetch_k, kk, False)
-        out, status = self._exchange((ci, cs, bi, bs, bm, st), fetch_k, kk, k)
+        lists = self.shard.local_lists(query_emb, query_terms, query_lens, fetch_k, kk, False)
+        out, status = self._exchange(lists, fetch_k, kk, k)
         out["status"] = status  # check_overflow=False: no host sync at all; the caller checks it with the results
         if check_overflow and bool(status.any()):
             if bool((status & _ffi.ORAG_STATUS_EXCHANGE_TIMEOUT).any()):
@@ -284,9 +287,91 @@ class ShardedHybrid:
             zero = torch.zeros(bad.numel(), dtype=torch.int32, device=bad.device)
             buf = self._gather_buf
             self._gather_buf = None
-            fixed, _ = self._exchange((*lists, zero), fetch_k, kk, k)
+            fixed, _ = self._exchange((*lists, zero, None), fetch_k, kk, k)
             self._gather_buf = buf
             for key, val in fixed.items():
                 out[key][bad] = val
             out["status"] = torch.zeros_like(status)
         return out
+
+
+class _ShardedList:
+    """Shared plumbing of the single-list sharded searches below: one NCCL all-gather of each rank's packed winners
+    ([B, width] int64 words) per batch, then one merge launch.  (The hybrid search, the BASELINE metric, has the fused
+    peer-memory exchange above; these two serve BASELINE configs 2 and 4.)"""
+
+    exchange = "nccl"
+    exchange_note = ""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._buf = None
+
+    def _gather(self, mine: torch.Tensor) -> torch.Tensor:
+        """mine int64 [B, w] -> [B, G, w] (shard-major inside a query)."""
+        Bq, w = mine.shape
+        if self._buf is None or self._buf.shape != (self.world, Bq, w):
+            self._buf = torch.empty((self.world, Bq, w), dtype=torch.int64, device=mine.device)
+        dist.all_gather_into_tensor(self._buf.view(-1), mine.contiguous().view(-1), group=self.group)
+        return self._buf.permute(1, 0, 2)
+
+    def close(self):
+        self._buf = None
+
+
+class ShardedCosine(_ShardedList):
+    """Exact cosine top-k over a row-sharded corpus (BASELINE config 2 at N GPUs): local `CosineIndex.topk`, all-gather
+    of the G * k winners, `orag_topk_merge` by (score desc, id asc)."""
+
+    def __init__(self, index: engine.CosineIndex, group=None):
+        super().__init__(group)
+        self.index = index
+
+    def search(self, query_emb, k: int = 10, check_overflow: bool = True):
+        st: list = []
+        ids, sc = self.index.topk(query_emb, k, check_overflow=check_overflow, status_out=st)
+        status = st[0] if not check_overflow else torch.zeros_like(st[0])
+        if self.world > 1:
+            mine = torch.cat([ids, sc.view(torch.int64), status.long()[:, None]], dim=1)
+            g = self._gather(mine)
+            Bq = ids.shape[0]
+            ids, sc, _ = engine.topk_merge(g[:, :, :k].reshape(Bq, -1).contiguous(),
+                                           g[:, :, k:2 * k].reshape(Bq, -1).contiguous().view(torch.float64), k)
+            status = g[:, :, 2 * k].amax(dim=1).to(torch.int32)
+            if check_overflow and bool(status.any()):
+                raise _ffi.OragError("sharded cosine search: a shard reported an unrepaired candidate overflow")
+        return {"ids": ids, "scores": sc, "cos_ids": ids, "cos_scores": sc, "status": status}
+
+
+class ShardedBm25(_ShardedList):
+    """BM25 top-k over a doc-sharded inverted index with GLOBAL statistics (BASELINE config 4 at N GPUs): local RAW
+    top-(k + guard) and the shard's max raw score, all-gather, division by the global max and merge in one launch
+    (`orag_topk_merge` with shard maxima: rag/retrieval.py:343-345 over the whole corpus)."""
+
+    def __init__(self, index, group=None):
+        super().__init__(group)
+        self.index = index
+
+    def search(self, query_terms, query_lens, k: int = 10, check_overflow: bool = True):
+        st: list = []
+        if self.world == 1:
+            ids, sc, mx = self.index.topk(query_terms, query_lens, k, normalize=True, check_overflow=check_overflow,
+                                          status_out=st)
+            status = st[0] if not check_overflow else torch.zeros_like(st[0])
+        else:
+            kk = k + BM25_GUARD
+            ids, raw, mx = self.index.topk(query_terms, query_lens, kk, normalize=False, check_overflow=check_overflow,
+                                           status_out=st)
+            status = st[0] if not check_overflow else torch.zeros_like(st[0])
+            mine = torch.cat([ids, raw.view(torch.int64), mx.view(torch.int64)[:, None], status.long()[:, None]], dim=1)
+            g = self._gather(mine)
+            Bq = ids.shape[0]
+            ids, sc, mx = engine.topk_merge(g[:, :, :kk].reshape(Bq, -1).contiguous(),
+                                            g[:, :, kk:2 * kk].reshape(Bq, -1).contiguous().view(torch.float64), k,
+                                            shard_max=g[:, :, 2 * kk].contiguous().view(torch.float64))
+            status = g[:, :, 2 * kk + 1].amax(dim=1).to(torch.int32)
+            if check_overflow and bool(status.any()):
+                raise _ffi.OragError("sharded BM25 search: a shard reported an unrepaired candidate overflow")
+        return {"ids": ids, "scores": sc, "bm25_ids": ids, "bm25_scores": sc, "bm25_max": mx, "status": status}

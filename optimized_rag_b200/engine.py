@@ -219,6 +219,28 @@ def rrf_fuse(list_ids: torch.Tensor, rrf_k: int = 60, top_k: int = 10, tie: str 
     return (ids, sc, src) if want_src else (ids, sc)
 
 
+def rrf_fuse_pair(ids_a: torch.Tensor, ids_b: torch.Tensor, rrf_k: int = 60, top_k: int = 10,
+                  status_a: torch.Tensor | None = None, status_b: torch.Tensor | None = None, tie: str = "reference"):
+    """RRF of two ranked lists held in separate [B, len] tensors (no packing launch) -> fused ids, scores, src ranks
+    [B, top_k, 2], status int32 [B] = status_a | status_b."""
+    _require_cuda(ids_a, "ids_a")
+    assert ids_a.dtype == torch.int64 and ids_b.dtype == torch.int64 and ids_a.shape == ids_b.shape
+    assert ids_a.is_contiguous() and ids_b.is_contiguous()
+    Bq, n = ids_a.shape
+    dev = ids_a.device
+    ids = torch.empty((Bq, top_k), dtype=torch.int64, device=dev)
+    sc = torch.empty((Bq, top_k), dtype=torch.float64, device=dev)
+    src = torch.empty((Bq, top_k, 2), dtype=torch.int32, device=dev)
+    status = torch.empty(Bq, dtype=torch.int32, device=dev)
+    _ffi.check(_ffi.lib().orag_rrf_fuse_pair(ids_a.data_ptr(), ids_b.data_ptr(), Bq, n, rrf_k, top_k,
+                                             0 if tie == "reference" else 1,
+                                             status_a.data_ptr() if status_a is not None else None,
+                                             status_b.data_ptr() if status_b is not None else None, ids.data_ptr(),
+                                             sc.data_ptr(), src.data_ptr(), status.data_ptr(), _stream(dev)),
+               "orag_rrf_fuse_pair")
+    return ids, sc, src, status
+
+
 def weighted_sum3(sem: torch.Tensor, kw: torch.Tensor, temp: torch.Tensor | None, alpha: float, beta: float,
                   gamma: float) -> torch.Tensor:
     """(alpha*sem + beta*kw) + gamma*temp in float64 without contraction (rag/retrieval.py:302)."""
@@ -281,6 +303,58 @@ def pairwise_cosine_threshold(emb: torch.Tensor, doc_idx: torch.Tensor, threshol
     return oi[:n][order], oj[:n][order], osim[:n][order]
 
 
+class PairwiseIndex:
+    """A claim-embedding matrix prepared for the all-pairs search of `ConsistencyChecker._find_contradictions`
+    (rag/consistency_checker.py:163-189; BASELINE config 5): fp32 rows + doc_idx, and -- derived once at construction by
+    orag_pairwise_prepare -- the fp16 shadow (rows scaled by powers of two), first-pass norms and float64 sum(a*a).
+    `pairs(threshold)` = every i < j with doc_idx[i] != doc_idx[j] and float64 cosine >= threshold."""
+
+    def __init__(self, emb: torch.Tensor, doc_idx: torch.Tensor):
+        _require_cuda(emb, "emb")
+        assert emb.dtype == torch.float32 and emb.dim() == 2 and emb.is_contiguous()
+        assert doc_idx.dtype == torch.int32 and doc_idx.is_contiguous() and doc_idx.shape[0] == emb.shape[0]
+        self.emb, self.doc_idx = emb, doc_idx
+        self.m, self.dim = emb.shape
+        self.device = emb.device
+        self.tensor_cores = self.m >= 2048 and self.dim % 32 == 0
+        self._ws = None
+        if self.tensor_cores:
+            L = _ffi.lib()
+            self.prepared = torch.empty(max(int(L.orag_pairwise_prepared_bytes(self.m, self.dim)), 256), dtype=torch.uint8,
+                                        device=self.device)
+            _ffi.check(L.orag_pairwise_prepare(emb.data_ptr(), self.m, self.dim, self.prepared.data_ptr(),
+                                               self.prepared.numel(), _stream(self.device)), "orag_pairwise_prepare")
+
+    def pairs(self, threshold: float = 0.85, cap: int = 1 << 20, sync: bool = True):
+        """(i int32, j int32, sim float64) sorted by (i, j).  With sync=False nothing synchronises with the host: the raw
+        output buffers and the device-side count are returned instead ((i, j, sim, count[2]); count[1] != 0 = a per-row
+        candidate buffer overflowed and the caller must use the exact sweep)."""
+        if not self.tensor_cores or threshold <= 0.01:
+            assert sync, "the exact sweep is the small-input path"
+            return pairwise_cosine_threshold(self.emb, self.doc_idx, threshold, cap, mode="exact")
+        L = _ffi.lib()
+        dev = self.device
+        if self._ws is None:
+            self._ws = torch.empty(max(int(L.orag_pairwise_pairs_workspace_bytes(self.m)), 256), dtype=torch.uint8, device=dev)
+        oi = torch.empty(cap, dtype=torch.int32, device=dev)
+        oj = torch.empty(cap, dtype=torch.int32, device=dev)
+        osim = torch.empty(cap, dtype=torch.float64, device=dev)
+        cnt = torch.empty(2, dtype=torch.int64, device=dev)
+        _ffi.check(L.orag_pairwise_pairs(self.emb.data_ptr(), self.prepared.data_ptr(), self.m, self.dim,
+                                         self.doc_idx.data_ptr(), threshold, cap, oi.data_ptr(), oj.data_ptr(),
+                                         osim.data_ptr(), cnt.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                         _stream(dev)), "orag_pairwise_pairs")
+        if not sync:
+            return oi, oj, osim, cnt
+        n, overflow = (int(x) for x in cnt.tolist())
+        if overflow:  # a row had more first-pass candidates than slots: exact sweep instead
+            return pairwise_cosine_threshold(self.emb, self.doc_idx, threshold, cap, mode="exact")
+        if n > cap:
+            raise _ffi.OragError(f"pair capacity exceeded ({n} > {cap})")
+        order = torch.argsort(oi[:n].long() * self.m + oj[:n].long())
+        return oi[:n][order], oj[:n][order], osim[:n][order]
+
+
 # --------------------------------------------------------------------------- hybrid (one shard)
 class HybridShard:
     """Cosine list + BM25 list -> RRF for the rows/docs of one GPU (SURVEY.md 'three facts' #1:
@@ -299,8 +373,9 @@ class HybridShard:
         """Cosine top-fetch_k and BM25 top-bm25_k of this shard, enqueued WITHOUT any host synchronisation.
         The BM25 pipeline runs on a side stream next to the cosine pipeline, so the small latency-bound kernels
         of either (query norms, candidate re-score, selection, finalize) overlap the other's main kernel.
-        Returns (cos ids, cos scores, bm25 ids, bm25 scores, bm25 max, status) where status int32 [B] is the OR
-        of both candidate-overflow flags; callers check it once, at the end of the whole step (`repair`)."""
+        Returns (cos ids, cos scores, bm25 ids, bm25 scores, bm25 max, cosine status, BM25 status): the two int32 [B]
+        candidate-overflow words are OR-ed by the kernel that consumes the lists (orag_rrf_fuse_pair / orag_hybrid_push);
+        callers check the result once, at the end of the whole step (`repair`)."""
         dev = query_emb.device
         cur = torch.cuda.current_stream(dev)
         L = _ffi.lib()
@@ -331,8 +406,7 @@ class HybridShard:
                                               check_overflow=False, status_out=st_b)
             ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=False, status_out=st_c)
         cur.wait_stream(side)
-        status = st_c[0] | st_b[0]
-        return ci, cs, bi, bs, bmax, status
+        return ci, cs, bi, bs, bmax, st_c[0], st_b[0]
 
     def exact_lists(self, query_emb: torch.Tensor, query_terms: torch.Tensor, query_lens: torch.Tensor, fetch_k: int,
                     bm25_k: int, normalize: bool):
@@ -345,10 +419,9 @@ class HybridShard:
     def search(self, query_emb: torch.Tensor, query_terms: torch.Tensor, query_lens: torch.Tensor, k: int = 10,
                fetch_k: int | None = None, check_overflow: bool = True):
         fetch_k = fetch_k or k
-        ci, cs, bi, bs, bmax, status = self.local_lists(query_emb, query_terms, query_lens, fetch_k, fetch_k, True)
-        lists = torch.stack([ci, bi], dim=1).contiguous()
-        fi, fs, src = rrf_fuse(lists, self.rrf_k, k, want_src=True)
-        out = {"ids": fi, "rrf_scores": fs, "src_ranks": src, "cos_ids": ci, "cos_scores": cs, "bm25_ids": bi,
+        ci, cs, bi, bs, bmax, st_c, st_b = self.local_lists(query_emb, query_terms, query_lens, fetch_k, fetch_k, True)
+        fi, fs, src, status = rrf_fuse_pair(ci, bi, self.rrf_k, k, st_c, st_b)
+        out = {"ids": fi, "rrf_scores": fs, "scores": fs, "src_ranks": src, "cos_ids": ci, "cos_scores": cs, "bm25_ids": bi,
                "bm25_scores": bs, "bm25_max": bmax, "status": status}
         # one host round trip per step, after everything has been enqueued (the caller reads the result anyway).
         # With check_overflow=False nothing synchronises: a caller that pipelines batches checks out["status"]
@@ -358,7 +431,7 @@ class HybridShard:
             ci2, cs2, bi2, bs2, bm2 = self.exact_lists(query_emb[bad].contiguous(), query_terms[bad].contiguous(),
                                                        query_lens[bad].contiguous(), fetch_k, fetch_k, True)
             f2, s2, r2 = rrf_fuse(torch.stack([ci2, bi2], dim=1).contiguous(), self.rrf_k, k, want_src=True)
-            for key, val in (("ids", f2), ("rrf_scores", s2), ("src_ranks", r2), ("cos_ids", ci2), ("cos_scores", cs2),
+            for key, val in (("ids", f2), ("rrf_scores", s2), ("src_ranks", r2), ("cos_ids", ci2), ("cos_scores", cs2),  # "scores" aliases "rrf_scores"
                              ("bm25_ids", bi2), ("bm25_scores", bs2), ("bm25_max", bm2)):
                 out[key][bad] = val
             out["status"] = torch.zeros_like(status)

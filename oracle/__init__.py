@@ -255,6 +255,24 @@ def pairwise_candidates(emb, doc_idx, thr: float = 0.85, neumaier: bool = True, 
     return oi[:cnt].copy(), oj[:cnt].copy(), os_[:cnt].copy()
 
 
+def pairwise_candidates_parallel(emb, doc_idx, thr: float = 0.85, neumaier: bool = True, cap: int = 1 << 22):
+    """`pairwise_candidates` on all host cores with 16 partner rows per SIMD block: same pairs, same float64 bits
+    (tests/test_oracle_stream.py), fast enough for an 8k-claim sub-block of BASELINE config 5."""
+    emb = np.ascontiguousarray(emb, dtype=np.float32)
+    doc_idx = np.ascontiguousarray(doc_idx, dtype=np.int32)
+    m, d = emb.shape
+    L = lib()
+    L.orc_pairwise_candidates_blocked.restype = ctypes.c_int64
+    L.orc_pairwise_candidates_blocked.argtypes = L.orc_pairwise_candidates.argtypes
+    oi = np.empty(cap, dtype=np.int32)
+    oj = np.empty(cap, dtype=np.int32)
+    os_ = np.empty(cap, dtype=np.float64)
+    cnt = L.orc_pairwise_candidates_blocked(_p(emb, _c_f32p), m, d, _p(doc_idx, _c_i32p), thr, int(neumaier), cap,
+                                            _p(oi, _c_i32p), _p(oj, _c_i32p), _p(os_, _c_f64p))
+    assert cnt <= cap, "pair cap exceeded"
+    return oi[:cnt].copy(), oj[:cnt].copy(), os_[:cnt].copy()
+
+
 # --------------------------------------------------------------------------- hybrid (composition)
 def hybrid_topk(corpus, queries, bm25: BM25Index, query_tokens, k: int = 10, rrf_k: int = 60,
                 fetch_k: int | None = None, id_base: int = 0):

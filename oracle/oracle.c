@@ -735,4 +735,69 @@ int orc_bm25_stream_scores(uint64_t seed, int64_t doc_start, int64_t n_docs, int
     return 0;
 }
 
+
+/* orc_pairwise_candidates on all cores, 16 partner rows per SIMD block (rag/consistency_checker.py:169-189, 241-261):
+ * the same float64 operations per pair (products of widened fp32 values are exact and commute, so is m1 * m2), results
+ * in (i, j) lexicographic order.  Returns the number of pairs found (writes at most cap). */
+typedef struct { int32_t i, j; double s; } orc_pair_t;
+static int orc_pair_cmp(const void *a, const void *b)
+{
+    const orc_pair_t *x = (const orc_pair_t *)a, *y = (const orc_pair_t *)b;
+    if (x->i != y->i) return x->i < y->i ? -1 : 1;
+    return x->j < y->j ? -1 : (x->j > y->j ? 1 : 0);
+}
+int64_t orc_pairwise_candidates_blocked(const float *emb, int64_t m, int d, const int32_t *doc_idx, double thr,
+                                        int neumaier, int64_t cap, int32_t *out_i, int32_t *out_j, double *out_sim)
+{
+    const int64_t nb = (m + ORC_QB - 1) / ORC_QB;
+    double *qt = (double *)calloc((size_t)nb * d * ORC_QB, sizeof(double));
+    double *mag = (double *)malloc((size_t)(m > 0 ? m : 1) * sizeof(double));
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < m; ++r) {
+        for (int i = 0; i < d; ++i) qt[((size_t)(r / ORC_QB) * d + i) * ORC_QB + (r % ORC_QB)] = (double)emb[r * d + i];
+        mag[r] = sqrt(sum_prod(emb + r * d, emb + r * d, d, neumaier));
+    }
+    orc_pair_t *all = NULL;
+    int64_t n_all = 0, cap_all = 0;
+#pragma omp parallel
+    {
+        orc_pair_t *mine = NULL;
+        int64_t n_mine = 0, cap_mine = 0;
+        double dots[ORC_QB];
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t i = 0; i < m; ++i) {
+            for (int64_t b = (i + 1) / ORC_QB; b < nb; ++b) {
+                orc_dot_block(emb + i * d, qt + (size_t)b * d * ORC_QB, d, neumaier, dots);
+                for (int l = 0; l < ORC_QB; ++l) {
+                    const int64_t j = b * ORC_QB + l;
+                    if (j <= i || j >= m || doc_idx[i] == doc_idx[j]) continue;
+                    const double s = (mag[i] == 0.0 || mag[j] == 0.0) ? 0.0 : dots[l] / (mag[i] * mag[j]);
+                    if (s >= thr) {
+                        if (n_mine == cap_mine) {
+                            cap_mine = cap_mine ? 2 * cap_mine : 1024;
+                            mine = (orc_pair_t *)realloc(mine, (size_t)cap_mine * sizeof(orc_pair_t));
+                        }
+                        mine[n_mine].i = (int32_t)i; mine[n_mine].j = (int32_t)j; mine[n_mine].s = s;
+                        ++n_mine;
+                    }
+                }
+            }
+        }
+#pragma omp critical
+        {
+            if (n_all + n_mine > cap_all) {
+                cap_all = 2 * (n_all + n_mine) + 16;
+                all = (orc_pair_t *)realloc(all, (size_t)cap_all * sizeof(orc_pair_t));
+            }
+            if (n_mine) memcpy(all + n_all, mine, (size_t)n_mine * sizeof(orc_pair_t));
+            n_all += n_mine;
+        }
+        free(mine);
+    }
+    if (n_all) qsort(all, (size_t)n_all, sizeof(orc_pair_t), orc_pair_cmp);
+    for (int64_t t = 0; t < n_all && t < cap; ++t) { out_i[t] = all[t].i; out_j[t] = all[t].j; out_sim[t] = all[t].s; }
+    free(all); free(qt); free(mag);
+    return n_all;
+}
+
 int orc_version(void) { return 1; }

@@ -23,6 +23,21 @@ def _bits(a):
     return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
 
 
+def pick_queries(qt, ql, n_total: int, n_pick: int = 32) -> np.ndarray:
+    """Query subset for a full-size check: evenly spaced over the batch plus the special keyword queries (a rank<10
+    term -> epsilon idf, df ~ N posting list; an OOV token + a duplicated term).  Sorted indices, len <= n_pick."""
+    n_pick = min(n_pick, n_total)
+    special = [b for b in range(n_total) if ((qt[b, :ql[b]] >= 0) & (qt[b, :ql[b]] < 10)).any()][:5] + \
+              [b for b in range(n_total) if (qt[b, :ql[b]] == -1).any()][:3]
+    special = special[:max(n_pick // 4, 1)]
+    even = [int(x) for x in np.linspace(0, n_total - 1, n_pick)]
+    picked = sorted(set(special + even))
+    while len(picked) > n_pick:
+        drop = next((b for b in picked[1:-1] if b not in special), picked[1])
+        picked.remove(drop)
+    return np.array(picked, dtype=np.int64)
+
+
 def reference_lists(n_rows: int, dim: int, q_emb, q_terms, q_lens, k: int, fetch_k: int | None = None, rrf_k: int = 60,
                     *, seed_corpus: int, bm25: "oracle.StreamedBM25 | None" = None, want_cosine: bool = True):
     """Oracle results for a query subset at full corpus size.  Returns (dict of arrays, dict of seconds)."""

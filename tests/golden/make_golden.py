@@ -260,6 +260,28 @@ def golden_dedup():
     return {"cases": cases}
 
 
+def golden_consistency():
+    """ConsistencyChecker.check_consistency (rag/consistency_checker.py:33-112) end to end on the documents and the
+    embedder of tests/consistency_fixture.py: extracted claims, per-pair heuristic verdicts, the result dicts."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import consistency_fixture as fx
+    cc = ref_loader.load("consistency_checker")
+    out = {"cases": []}
+    for thr in (0.85, 0.5):
+        chk = cc.ConsistencyChecker(fx.TopicEmbedder(), similarity_threshold=thr)
+        claims = [chk._extract_claims(d["content"]) for d in fx.DOCUMENTS]
+        res = chk.check_consistency(fx.DOCUMENTS, "what does the plant do")
+        res_two = chk.check_consistency(fx.DOCUMENTS[:2], "q")
+        flat = [c for cl in claims for c in cl]
+        heur = [[int(chk._is_contradiction(a, b)) for b in flat] for a in flat]
+        out["cases"].append({"threshold": thr, "claims": claims, "result": res, "result_first_two": res_two,
+                             "is_contradiction": heur})
+    chk = cc.ConsistencyChecker(fx.TopicEmbedder())
+    out["single_doc"] = chk.check_consistency(fx.DOCUMENTS[:1], "q")
+    out["few_claims"] = chk.check_consistency([{"content": "Tiny."}, {"content": "Alpha reactor output is 40 megawatts"}], "q")
+    return out
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     data = {
@@ -273,6 +295,7 @@ def main():
         "config1": golden_config1(),
         "mmr": golden_mmr(),
         "dedup": golden_dedup(),
+        "consistency": golden_consistency(),
     }
     p = OUT / "golden.json"
     p.write_text(json.dumps(data, separators=(",", ":")))

@@ -357,7 +357,7 @@ def test_peer_exchange_kernels_two_virtual_ranks(eng):
         for seq, B in enumerate([64, 64, 37, 64, 1], start=1):
             lists = [_random_lists(rng, g, B, fk, kk) for g in range(G)]
             for g in range(G):
-                _ffi.check(L.orag_hybrid_push(*[t.data_ptr() for t in lists[g]], B, fk, kk, g, G, maxq,
+                _ffi.check(L.orag_hybrid_push(*[t.data_ptr() for t in lists[g]], None, B, fk, kk, g, G, maxq,
                                               d_peers.data_ptr(), seq, st), "push")
             want = torch.stack([pack_local(*lists[g]) for g in range(G)]).contiguous()
             ref, ref_status = hybrid_merge(want, fk, kk, 60, k)

@@ -308,9 +308,9 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu(built_lib):
     assert L.orag_rrf_fuse(p(buf), 1, 2, 100, 60, 10, 0, p(out_i), p(out_s), None, None) == -1      # union > 128
     assert L.orag_rrf_fuse(p(buf), 0, 2, 10, 60, 10, 0, p(out_i), p(out_s), None, None) == 0        # empty batch: no launch
     assert L.orag_hybrid_merge(p(buf), 40, 1, 10, 16, 60, 10, 0, *([p(buf)] * 9), None) == -1         # 40 * 16 > 256
-    assert L.orag_hybrid_push(*([p(buf)] * 6), 4, 10, 16, 2, 2, 256, p(buf), 1, None) == -1          # rank >= n_shards
-    assert L.orag_hybrid_push(*([p(buf)] * 6), 300, 10, 16, 0, 2, 256, p(buf), 1, None) == -1        # batch > max_queries
-    assert L.orag_hybrid_push(*([p(buf)] * 6), 4, 10, 16, 0, 2, 256, p(buf), 0, None) == -1          # seq starts at 1
+    assert L.orag_hybrid_push(*([p(buf)] * 6), None, 4, 10, 16, 2, 2, 256, p(buf), 1, None) == -1          # rank >= n_shards
+    assert L.orag_hybrid_push(*([p(buf)] * 6), None, 300, 10, 16, 0, 2, 256, p(buf), 1, None) == -1        # batch > max_queries
+    assert L.orag_hybrid_push(*([p(buf)] * 6), None, 4, 10, 16, 0, 2, 256, p(buf), 0, None) == -1          # seq starts at 1
     got = ctypes.c_void_p()
     assert L.orag_hybrid_wait(p(buf), 2, 256, 4, 10, 16, 1, 0, ctypes.byref(got), None) == -1         # timeout_ms > 0
     assert L.orag_exchange_alloc(0, ctypes.byref(got)) == -1

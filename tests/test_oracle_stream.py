@@ -94,3 +94,28 @@ def test_scale_check_reference_lists_and_compare():
     got["ids"][19, 0] += 1
     bad = scale_check.compare(got, sub, rows)
     assert len(bad) == 2 and bad[0].startswith("cos_scores: 1 of") and bad[1].startswith("ids: 1 of")
+
+
+def test_blocked_pairwise_equals_scalar_pairwise():
+    m, dim = 300, 160
+    emb = syn.embeddings(syn.SEED_CORPUS, 0, m, dim, 0)
+    emb[10] = emb[3] + np.float32(0.3) * emb[10]      # planted similar claims
+    emb[200] = emb[77] * np.float32(2.0)              # cosine exactly 1 up to rounding
+    emb[5] = 0.0                                      # zero vector -> cosine 0.0
+    doc = (np.arange(m) // 4).astype(np.int32)
+    for thr in (0.85, 0.05, -1.0):
+        a = oracle.pairwise_candidates(emb, doc, thr)
+        b = oracle.pairwise_candidates_parallel(emb, doc, thr)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert np.array_equal(a[2].view(np.uint64), b[2].view(np.uint64))
+    assert len(oracle.pairwise_candidates_parallel(emb, doc, 0.85)[0]) >= 2
+
+
+def test_pick_queries_includes_special_keyword_queries():
+    from oracle import scale_check
+    thr = syn.zipf_thresholds(50000)
+    qt, ql = syn.keyword_queries(1024, 50000, thresholds=thr)
+    rows = scale_check.pick_queries(qt, ql, 1024, 32)
+    assert len(rows) == 32 and len(set(rows.tolist())) == 32 and rows.min() >= 0 and rows.max() < 1024
+    assert any(((qt[b, :ql[b]] >= 0) & (qt[b, :ql[b]] < 10)).any() for b in rows) and any((qt[b, :ql[b]] == -1).any() for b in rows)
+    assert len(scale_check.pick_queries(qt, ql, 4, 32)) == 4

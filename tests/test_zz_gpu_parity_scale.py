@@ -30,16 +30,7 @@ if os.environ.get("ORAG_SCALE_TEST", "1") == "0":
     pytest.skip("ORAG_SCALE_TEST=0", allow_module_level=True)
 
 
-def _subset(qt, ql, n_total, n_pick=32):
-    """Evenly spaced queries plus the special ones (common rank<10 term -> epsilon idf; OOV + duplicated term)."""
-    special = [b for b in range(n_total) if (qt[b, :ql[b]] < 10).any()][:5] + \
-              [b for b in range(n_total) if (qt[b, :ql[b]] == -1).any()][:3]
-    even = [int(x) for x in np.linspace(0, n_total - 1, n_pick)]
-    picked = sorted(set(special + even))
-    while len(picked) > n_pick:
-        drop = next(b for b in picked[1:-1] if b not in special)
-        picked.remove(drop)
-    return np.array(picked, dtype=np.int64)
+_subset = scale_check.pick_queries
 
 
 def _np(res, keys):
