@@ -474,7 +474,7 @@ def run_hybrid_like(args):
     torch = h.torch
     from optimized_rag_b200 import engine, synthetic as syn
     from optimized_rag_b200.bm25_index import Bm25Index
-    from optimized_rag_b200.dist import ShardedBm25, ShardedCosine, ShardedHybrid, shard_range, sharded_stats
+    from optimized_rag_b200.dist import ShardedBm25, ShardedCosine, ShardedHybrid, shard_range, sharded_plan
     dev, world, rank = h.dev, h.world, h.rank
     N, Bq, k = args.rows, args.batch, TOPK
     want_cos, want_bm = args.config in ("3", "2"), args.config in ("3", "4")
@@ -493,11 +493,11 @@ def run_hybrid_like(args):
         doc_off, tokens = engine.gen_token_corpus(n_local, lo, syn.SEED_TOKENS, thr, VOCAB, LMIN, LMAX, device=dev)
         torch.cuda.synchronize()
         t_b = time.perf_counter()
-        stats = sharded_stats(doc_off, tokens, VOCAB)
-        bm25 = Bm25Index(doc_off, tokens, VOCAB, tile_docs=args.tile_docs, stats=stats, doc_id_base=lo)
+        plan, stats = sharded_plan(doc_off, tokens, VOCAB, tile_docs=args.tile_docs)
+        bm25 = Bm25Index.from_plan(plan, stats, doc_id_base=lo)
         torch.cuda.synchronize()
         build_s = time.perf_counter() - t_b
-        del tokens
+        del tokens, plan
         torch.cuda.empty_cache()
     if args.config == "3":
         sh = ShardedHybrid(engine.HybridShard(cos, bm25))

@@ -166,7 +166,8 @@ typedef struct orag_bm25_index {
     int32_t n_tiles;               /* ceil(n_docs / tile_docs) */
     int32_t has_negative_idf;      /* 1 if a negative idf survives the epsilon floor (forces the dense path) */
     int32_t max_doc_len;           /* size of d_t4_table - 1 */
-    int32_t reserved;
+    int32_t reserved;              /* bit 0: first-pass runs are 16-byte aligned and padded to four postings
+                                      (the layout orag_bm25_index_fill writes; required by the first-pass kernel) */
     const int64_t *d_tile_base;    /* [n_tiles + 1] first posting of each tile */
     const int32_t *d_tile_term_off;/* [n_tiles, vocab + 1] term offsets relative to the tile base */
     const uint32_t *d_postings;    /* [P] (doc_in_tile << 16) | tf, ascending doc within (tile, term) */
@@ -177,7 +178,8 @@ typedef struct orag_bm25_index {
     /* Optional first-pass view (pointers NULL = float64 scatter kernel only): a second tiling of the same
      * postings with tiles of fp_tile_docs docs (power of two, 32..16384),
      * (doc_in_tile << 16) | fp16 bits of r = tf*(k1+1)/(tf + t4[dl]) rounded to nearest (every r must be a
-     * NORMAL fp16 number), 16-byte aligned, ascending doc within (tile, term).
+     * NORMAL fp16 number), 16-byte aligned, ascending doc within (tile, term); runs padded as described at
+     * orag_bm25_index_plan.
      * d_term_max_r[t] = max over this shard's postings of term t of that fp16 value (0 if none). */
     const uint32_t *d_postings_r16;
     const float *d_term_max_r;          /* [vocab] */
@@ -186,6 +188,38 @@ typedef struct orag_bm25_index {
     const int64_t *d_fp_tile_base;      /* [fp_n_tiles + 1] */
     const int32_t *d_fp_tile_term_off;  /* [fp_n_tiles, vocab + 1] */
 } orag_bm25_index_t;
+
+/* ---------------------------------------------------------------------------
+ * Index build (ingest): token corpus -> the two posting tilings above.  Replaces what `BM25Okapi(tokenized_corpus)`
+ * derives on every call (rag/retrieval.py:334-338; rank_bm25 0.2.2 BM25._initialize): per-document term
+ * frequencies and lengths, document frequencies, the first-seen order of the vocabulary.
+ *   d_doc_off int64 [n_docs + 1], d_tokens int32 [d_doc_off[n_docs]] (ids in [0, vocab)); tile_docs / fp_tile_docs
+ *   powers of two (32..65536 / 32..16384).  The first-pass view built here has every (tile, term) run start on a
+ *   16-byte boundary and padded to a multiple of four postings with copies of its last doc carrying impact +0.0; set
+ *   bit 0 of orag_bm25_index_t.reserved to tell orag_bm25_topk so.
+ * Phase 1, orag_bm25_index_plan (SYNCHRONISES: the array sizes are an output): writes d_doc_len [n_docs], ADDS this
+ *   shard's document frequencies to d_df [vocab] and min-s the global token position of every term's first occurrence
+ *   (token_pos_base + local position) into d_first_pos [vocab] (callers initialise them to 0 / INT64_MAX; summing /
+ *   min-ing over shards gives the global statistics), writes the final d_tile_base [n_tiles + 1], d_tile_term_off
+ *   [n_tiles, vocab + 1] and their fp_ twins, d_info[0..3] = {max tf, max doc length, error bits (1 token id out of
+ *   range, 2 doc longer than 65535, 4 internal table overflow, 8 tile >= 2^31 postings, 16 set by the fill: an impact
+ *   that is not a normal fp16 number -> first-pass view unusable), 0}, and h_totals[0..1] (HOST) = postings of the
+ *   exact view, postings (padded) of the first-pass view.
+ * Phase 2, orag_bm25_index_fill: scatters every posting to its slot (same workspace, untouched in between).
+ *   d_t4_table [max_doc_len + 1] from the GLOBAL avgdl; d_postings [h_totals[0] + 4]; d_postings_r16 [h_totals[1] + 4]
+ *   (16-byte aligned) and d_term_max_r [vocab], or both NULL for an index without first-pass view.
+ * ------------------------------------------------------------------------- */
+size_t orag_bm25_build_workspace_bytes(int64_t n_docs, int vocab, int tile_docs, int fp_tile_docs);
+int orag_bm25_index_plan(const int64_t *d_doc_off, const int32_t *d_tokens, int64_t n_docs, int vocab, int tile_docs,
+                         int fp_tile_docs, int64_t token_pos_base, int32_t *d_doc_len, int64_t *d_df,
+                         int64_t *d_first_pos, int64_t *d_tile_base, int32_t *d_tile_term_off, int64_t *d_fp_tile_base,
+                         int32_t *d_fp_tile_term_off, int32_t *d_info, void *d_workspace, size_t workspace_bytes,
+                         int64_t *h_totals, void *stream);
+int orag_bm25_index_fill(const int64_t *d_doc_off, const int32_t *d_tokens, int64_t n_docs, int vocab, int tile_docs,
+                         int fp_tile_docs, const double *d_t4_table, int max_doc_len, const int64_t *d_tile_base,
+                         const int32_t *d_tile_term_off, uint32_t *d_postings, const int64_t *d_fp_tile_base,
+                         const int32_t *d_fp_tile_term_off, uint32_t *d_postings_r16, float *d_term_max_r,
+                         int32_t *d_info, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /*   d_query_terms int32 [n_queries, max_terms], entries < 0 or >= vocab are OOV / padding
  *   d_query_lens  int32 [n_queries]

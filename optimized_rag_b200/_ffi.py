@@ -24,6 +24,7 @@ SYMBOLS = [
     "orag_row_inv_norms", "orag_row_sq", "orag_f32_to_bf16", "orag_f32_to_f16_rows",
     "orag_cosine_mark_prescan", "orag_stream_wait_prescan",
     "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_dense", "orag_cosine_firstpass_dense",
+    "orag_bm25_build_workspace_bytes", "orag_bm25_index_plan", "orag_bm25_index_fill",
     "orag_bm25_workspace_bytes", "orag_bm25_topk", "orag_bm25_dense", "orag_dense_topk",
     "orag_topk_merge", "orag_rrf_fuse", "orag_rrf_fuse_pair", "orag_hybrid_merge", "orag_weighted_sum3", "orag_div_scalar",
     "orag_pairwise_workspace_bytes", "orag_pairwise_cosine_threshold",
@@ -104,6 +105,12 @@ def lib() -> ctypes.CDLL:
                                    c_size_t, vp]
     L.orag_cosine_dense.argtypes = [vp, c_int64, c_int, vp, c_int, vp, vp]
     L.orag_cosine_firstpass_dense.argtypes = [vp, vp, vp, c_int64, c_int, vp, c_int, c_int, vp, vp, c_size_t, vp]
+    L.orag_bm25_build_workspace_bytes.restype = c_size_t
+    L.orag_bm25_build_workspace_bytes.argtypes = [c_int64, c_int, c_int, c_int]
+    L.orag_bm25_index_plan.argtypes = [vp, vp, c_int64, c_int, c_int, c_int, c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                       c_size_t, POINTER(c_int64), vp]
+    L.orag_bm25_index_fill.argtypes = [vp, vp, c_int64, c_int, c_int, c_int, vp, c_int, vp, vp, vp, vp, vp, vp, vp, vp,
+                                       vp, c_size_t, vp]
     L.orag_bm25_workspace_bytes.restype = c_size_t
     L.orag_bm25_workspace_bytes.argtypes = [POINTER(Bm25IndexStruct), c_int, c_int, c_int]
     L.orag_bm25_topk.argtypes = [POINTER(Bm25IndexStruct), c_int64, vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp, vp,
@@ -143,7 +150,8 @@ def lib() -> ctypes.CDLL:
         f = getattr(L, name)
         if name not in ("orag_last_error", "orag_launch_count", "orag_cosine_workspace_bytes", "orag_bm25_workspace_bytes",
                         "orag_pairwise_workspace_bytes", "orag_pairwise_tc_workspace_bytes", "orag_exchange_bytes",
-                        "orag_pairwise_prepared_bytes", "orag_pairwise_pairs_workspace_bytes"):
+                        "orag_pairwise_prepared_bytes", "orag_pairwise_pairs_workspace_bytes",
+                        "orag_bm25_build_workspace_bytes"):
             f.restype = c_int
     _lib = L
     return L

@@ -1,6 +1,8 @@
-"""GPU-resident, doc-range-tiled BM25 index (ingest side; torch is used for the sort/scan plumbing).
+"""GPU-resident, doc-range-tiled BM25 index (ingest side).
 
-Layout consumed by csrc/bm25.cu (see include/orag.h `orag_bm25_index_t`):
+The token corpus is turned into the layout of include/orag.h `orag_bm25_index_t` by the library's own builder
+(csrc/bm25_build.cu: orag_bm25_index_plan / orag_bm25_index_fill); this module only owns the arrays, reduces the
+statistics and evaluates the handful of scalars that must come out of CPython's `math.log` (idf):
   tile t = docs [t*T, (t+1)*T) of the shard
   postings      uint32 [(doc_in_tile << 16) | tf], grouped by (tile, term), ascending doc
   tile_base     int64 [n_tiles+1]   first posting of each tile
@@ -8,7 +10,8 @@ Layout consumed by csrc/bm25.cu (see include/orag.h `orag_bm25_index_t`):
   doc_len       int32 [n_docs]; t4_table float64 [max_dl+1] = k1*(1 - b + b*dl/avgdl) (global avgdl)
   idf           float64 [V]         global idf with the epsilon floor (rank_bm25 0.2.2 BM25Okapi._calc_idf)
   first-pass view (csrc/bm25_ms.cu), a second tiling with tiles of fp_tile_docs (up to 16384) docs:
-  postings_r16  uint32 [(doc_in_tile << 16) | fp16(tf*(k1+1)/(tf + t4[dl]))], fp_tile_base, fp_tile_term_off
+  postings_r16  uint32 [(doc_in_tile << 16) | fp16(tf*(k1+1)/(tf + t4[dl]))], fp_tile_base, fp_tile_term_off; every run
+                starts on a 16-byte boundary and is padded to four postings (copies of its last doc, impact 0)
   term_max_r    float32 [V]         max fp16 r over this shard's postings of each term (MaxScore upper bounds)
 
 Global statistics (N, avgdl, df, first-seen order -> idf, eps) follow the reference's
@@ -29,6 +32,7 @@ from . import _ffi
 K1 = 1.5
 B = 0.75
 EPSILON = 0.25
+INT64_MAX = np.iinfo(np.int64).max
 
 
 @dataclass
@@ -82,153 +86,154 @@ def t4_table(max_dl: int, avgdl: float) -> np.ndarray:
     return K1 * (1 - B + B * dl / avgdl)
 
 
-def local_stats(doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, token_pos_base: int = 0,
-                chunk_docs: int = 1 << 20) -> Bm25Stats:
-    """df / first-seen / lengths of one shard.  doc_off int64 [n+1], tokens int32 [total] (same device)."""
-    dev = tokens.device
-    n = doc_off.numel() - 1
-    df = torch.zeros(vocab, dtype=torch.int64, device=dev)
-    big = torch.iinfo(torch.int64).max
-    first = torch.full((vocab,), big, dtype=torch.int64, device=dev)
-    total = int(doc_off[-1].item()) if n > 0 else 0
-    for d0 in range(0, n, chunk_docs):
-        d1 = min(n, d0 + chunk_docs)
-        lo, hi = int(doc_off[d0].item()), int(doc_off[d1].item())
-        if hi == lo:
-            continue
-        tok = tokens[lo:hi].long()
-        pos = torch.arange(lo, hi, dtype=torch.int64, device=dev) + token_pos_base
-        first.scatter_reduce_(0, tok, pos, reduce="amin", include_self=True)
-        lens = (doc_off[d0 + 1:d1 + 1] - doc_off[d0:d1])
-        doc = torch.repeat_interleave(torch.arange(d1 - d0, dtype=torch.int64, device=dev), lens)
-        pair = torch.unique(doc * vocab + tok)
-        df += torch.bincount(pair % vocab, minlength=vocab)
-        del tok, pos, doc, pair
-    return Bm25Stats(n, total, df.cpu().numpy(), first.cpu().numpy())
+def default_fp_tile_docs(n_docs: int) -> int:
+    # measured on B200 (scripts/debug_bm25.py): 4096..8192-doc tiles are within 5 % of each other stand-alone;
+    # 4096 keeps the per-warp bitmap small enough for the background configuration (csrc/bm25_ms.cu)
+    return min(4096, max(32, 1 << max(0, (max(n_docs, 1) // 16 - 1).bit_length())))
+
+
+class Bm25Plan:
+    """Phase 1 of the index build (orag_bm25_index_plan): one counting pass over the shard's token corpus gives the
+    doc lengths, the local df / first-seen statistics, and the final run offsets + tile bases of both tilings.
+    `local_stats` is what a multi-GPU build all-reduces (dist.reduce_stats) before `Bm25Index.from_plan`."""
+
+    def __init__(self, doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, tile_docs: int = 1024,
+                 fp_tile_docs: int | None = None, token_pos_base: int = 0):
+        assert doc_off.dtype == torch.int64 and tokens.dtype == torch.int32
+        if not tokens.is_cuda or not doc_off.is_cuda:
+            raise _ffi.OragError("the BM25 index is built on the GPU (csrc/bm25_build.cu): doc_off / tokens must be CUDA "
+                                 "tensors -- there is no CPU builder")
+        assert tile_docs & (tile_docs - 1) == 0 and 32 <= tile_docs <= 2048
+        dev = tokens.device
+        self.device, self.vocab, self.tile_docs = dev, int(vocab), int(tile_docs)
+        self.doc_off, self.tokens = doc_off.contiguous(), tokens.contiguous()
+        self.n_docs = int(doc_off.numel() - 1)
+        self.fp_tile_docs = int(fp_tile_docs or default_fp_tile_docs(self.n_docs))
+        assert self.fp_tile_docs & (self.fp_tile_docs - 1) == 0 and 32 <= self.fp_tile_docs <= 16384
+        self.n_tiles = (self.n_docs + self.tile_docs - 1) // self.tile_docs
+        self.fp_n_tiles = (self.n_docs + self.fp_tile_docs - 1) // self.fp_tile_docs
+        L = _ffi.lib()
+        V1 = self.vocab + 1
+        i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
+        i64 = lambda *shape: torch.empty(shape, dtype=torch.int64, device=dev)
+        self.dl = i32(max(self.n_docs, 1))[:self.n_docs]
+        self.tile_base, self.fp_tile_base = i64(self.n_tiles + 1), i64(self.fp_n_tiles + 1)
+        self.tile_term_off, self.fp_tile_term_off = i32(self.n_tiles, V1), i32(self.fp_n_tiles, V1)
+        df = torch.zeros(self.vocab, dtype=torch.int64, device=dev)
+        first = torch.full((self.vocab,), INT64_MAX, dtype=torch.int64, device=dev)
+        self.info = torch.zeros(4, dtype=torch.int32, device=dev)
+        need = int(L.orag_bm25_build_workspace_bytes(self.n_docs, self.vocab, self.tile_docs, self.fp_tile_docs))
+        self.ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+        totals = (ctypes.c_int64 * 2)()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _ffi.check(L.orag_bm25_index_plan(self.doc_off.data_ptr(), self.tokens.data_ptr(), self.n_docs, self.vocab,
+                                          self.tile_docs, self.fp_tile_docs, int(token_pos_base), self.dl.data_ptr(),
+                                          df.data_ptr(), first.data_ptr(), self.tile_base.data_ptr(),
+                                          self.tile_term_off.data_ptr(), self.fp_tile_base.data_ptr(),
+                                          self.fp_tile_term_off.data_ptr(), self.info.data_ptr(), self.ws.data_ptr(),
+                                          self.ws.numel(), totals, st), "orag_bm25_index_plan")
+        self.n_postings, self.n_postings_fp = int(totals[0]), int(totals[1])
+        max_tf, max_dl, err, _ = self.info.tolist()
+        if err & 1:
+            raise ValueError("token ids must lie in [0, vocab)")
+        if err & 2:
+            raise ValueError("documents longer than 65535 tokens are not representable in the tile layout")
+        if err & 4:
+            raise _ffi.OragError("bm25 build: term de-duplication table overflow")
+        if err & 8:
+            raise ValueError("a tile holds 2^31 or more postings")
+        if max_tf > 0xFFFF:
+            raise ValueError("term frequency above 65535 is not representable in the posting format")
+        self.max_dl = int(max_dl)
+        total_len = int(doc_off[-1].item()) if self.n_docs > 0 else 0
+        self.df_local = df.cpu().numpy()
+        self.local_stats = Bm25Stats(self.n_docs, total_len, self.df_local, first.cpu().numpy())
+
+
+def local_stats(doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, token_pos_base: int = 0) -> Bm25Stats:
+    """df / first-seen / lengths of one shard (a by-product of `Bm25Plan`; callers that go on to build the index should
+    create the plan themselves and keep it)."""
+    return Bm25Plan(doc_off, tokens, vocab, token_pos_base=token_pos_base).local_stats
 
 
 class Bm25Index:
     """One shard of the inverted index, resident on `device`."""
 
     def __init__(self, doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, tile_docs: int = 1024,
-                 stats: Bm25Stats | None = None, doc_id_base: int = 0, chunk_docs: int = 1 << 20,
-                 first_pass: bool = True, fp_tile_docs: int | None = None):
-        assert doc_off.dtype == torch.int64 and tokens.dtype == torch.int32
-        assert tile_docs & (tile_docs - 1) == 0 and 32 <= tile_docs <= 2048
-        dev = tokens.device
-        self.device = dev
-        self.vocab = int(vocab)
-        self.tile_docs = int(tile_docs)
-        self.n_docs = int(doc_off.numel() - 1)
-        self.doc_id_base = int(doc_id_base)
-        self.n_tiles = (self.n_docs + tile_docs - 1) // tile_docs
-        if stats is None:
-            stats = local_stats(doc_off, tokens, vocab, chunk_docs=chunk_docs)
+                 stats: Bm25Stats | None = None, doc_id_base: int = 0, first_pass: bool = True,
+                 fp_tile_docs: int | None = None, plan: Bm25Plan | None = None):
+        if plan is None:
+            plan = Bm25Plan(doc_off, tokens, vocab, tile_docs, fp_tile_docs)
+        self._from_plan(plan, stats or plan.local_stats, doc_id_base, first_pass)
+
+    @classmethod
+    def from_plan(cls, plan: Bm25Plan, stats: Bm25Stats | None = None, doc_id_base: int = 0,
+                  first_pass: bool = True) -> "Bm25Index":
+        self = cls.__new__(cls)
+        self._from_plan(plan, stats or plan.local_stats, doc_id_base, first_pass)
+        return self
+
+    def _from_plan(self, plan: Bm25Plan, stats: Bm25Stats, doc_id_base: int, first_pass: bool):
+        dev = plan.device
+        L = _ffi.lib()
+        self.device, self.vocab, self.tile_docs = dev, plan.vocab, plan.tile_docs
+        self.n_docs, self.doc_id_base = plan.n_docs, int(doc_id_base)
+        self.n_tiles, self.fp_tile_docs, self.fp_n_tiles = plan.n_tiles, plan.fp_tile_docs, plan.fp_n_tiles
         self.stats = stats
+        self.df_local = plan.df_local
         idf, self.average_idf, self.eps = idf_table(stats)
         self.avgdl = stats.avgdl
         self.has_negative_idf = bool((idf < 0).any())
         self.idf = torch.from_numpy(idf).to(dev)
-
-        dl = (doc_off[1:] - doc_off[:-1])
-        self.dl = dl.to(torch.int32)
-        max_dl = int(dl.max().item()) if self.n_docs else 0
-        if max_dl > 0xFFFF:
-            raise ValueError("documents longer than 65535 tokens are not representable in the tile layout")
-        self.max_dl = max_dl
-        t4_np = t4_table(max_dl, self.avgdl)
+        self.dl, self.max_dl = plan.dl, plan.max_dl
+        t4_np = t4_table(self.max_dl, self.avgdl)
         self.t4_table = torch.from_numpy(t4_np).to(dev)
         # r[dl, tf-1] = tf*(k1+1) / (tf + t4[dl]) for tf = 1..4, numpy float64 in rank_bm25's operation order
         tf_np = np.arange(1, 5)[None, :]
         self.r_table = torch.from_numpy(np.ascontiguousarray(tf_np * (K1 + 1) / (tf_np + t4_np[:, None]))).to(dev)
-
-        # exact view: (doc_in_tile << 16) | tf over tiles of `tile_docs` docs
-        self.postings, self.tile_base, self.tile_term_off, _ = self._tiled_view(doc_off, tokens, dl, self.tile_docs,
-                                                                               chunk_docs, want_r16=False)
-        self.n_postings = int(self.tile_base[-1].item())
-        # first-pass view: (doc_in_tile << 16) | fp16(r) over (much larger) tiles of `fp_tile_docs` docs
-        self.postings_r16 = self.term_max_r = self.fp_tile_base = self.fp_tile_term_off = None
-        if fp_tile_docs is None:
-            # measured on B200 (scripts/debug_bm25.py): 4096..8192-doc tiles are within 5 % of each other stand-alone;
-            # 4096 keeps the per-warp bitmap small enough for the background configuration (csrc/bm25_ms.cu)
-            fp_tile_docs = min(4096, max(32, 1 << max(0, (max(self.n_docs, 1) // 16 - 1).bit_length())))
-        assert fp_tile_docs & (fp_tile_docs - 1) == 0 and 32 <= fp_tile_docs <= 16384
-        self.fp_tile_docs = int(fp_tile_docs)
-        self.fp_n_tiles = (self.n_docs + self.fp_tile_docs - 1) // self.fp_tile_docs
-        if first_pass and not self.has_negative_idf and self.n_docs > 0:
-            post, base, off, tmax = self._tiled_view(doc_off, tokens, dl, self.fp_tile_docs, chunk_docs, want_r16=True)
-            if post is not None:
-                self.postings_r16, self.fp_tile_base, self.fp_tile_term_off, self.term_max_r = post, base, off, tmax
-                assert self.postings_r16.data_ptr() % 16 == 0
-
-        self.struct = _ffi.Bm25IndexStruct(
-            n_docs=self.n_docs, vocab=self.vocab, tile_docs=self.tile_docs, n_tiles=self.n_tiles,
-            has_negative_idf=int(self.has_negative_idf),
-            d_tile_base=self.tile_base.data_ptr(), d_tile_term_off=self.tile_term_off.data_ptr(),
-            max_doc_len=self.max_dl, reserved=0, d_postings=self.postings.data_ptr(), d_doc_len=self.dl.data_ptr(),
-            d_t4_table=self.t4_table.data_ptr(), d_r_table=self.r_table.data_ptr(), d_idf=self.idf.data_ptr(),
-            d_postings_r16=self.postings_r16.data_ptr() if self.postings_r16 is not None else None,
-            d_term_max_r=self.term_max_r.data_ptr() if self.term_max_r is not None else None,
-            fp_tile_docs=self.fp_tile_docs, fp_n_tiles=self.fp_n_tiles,
-            d_fp_tile_base=self.fp_tile_base.data_ptr() if self.fp_tile_base is not None else None,
-            d_fp_tile_term_off=self.fp_tile_term_off.data_ptr() if self.fp_tile_term_off is not None else None)
+        self.tile_base, self.tile_term_off = plan.tile_base, plan.tile_term_off
+        self.fp_tile_base, self.fp_tile_term_off = plan.fp_tile_base, plan.fp_tile_term_off
+        self.n_postings, self.n_postings_fp = plan.n_postings, plan.n_postings_fp
+        # (+4 entries: 16-byte reads of the last run never leave the allocation)
+        self.postings = torch.empty(self.n_postings + 4, dtype=torch.int32, device=dev)
+        self.postings[self.n_postings:].zero_()
+        want_fp = first_pass and not self.has_negative_idf and self.n_docs > 0
+        self.postings_r16 = torch.empty(self.n_postings_fp + 4, dtype=torch.int32, device=dev) if want_fp else None
+        if want_fp:
+            self.postings_r16[self.n_postings_fp:].zero_()
+        self.term_max_r = torch.zeros(self.vocab, dtype=torch.float32, device=dev) if want_fp else None
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _ffi.check(L.orag_bm25_index_fill(plan.doc_off.data_ptr(), plan.tokens.data_ptr(), self.n_docs, self.vocab,
+                                          self.tile_docs, self.fp_tile_docs, self.t4_table.data_ptr(), self.max_dl,
+                                          self.tile_base.data_ptr(), self.tile_term_off.data_ptr(),
+                                          self.postings.data_ptr(), self.fp_tile_base.data_ptr(),
+                                          self.fp_tile_term_off.data_ptr(),
+                                          self.postings_r16.data_ptr() if want_fp else None,
+                                          self.term_max_r.data_ptr() if want_fp else None, plan.info.data_ptr(),
+                                          plan.ws.data_ptr(), plan.ws.numel(), st), "orag_bm25_index_fill")
+        err = int(plan.info[2].item())
+        if err & 4:
+            raise _ffi.OragError("bm25 build: term de-duplication table overflow")
+        if err & 16:  # an impact that is not a normal fp16 number: no first-pass view (the float64 kernel serves alone)
+            self.postings_r16 = self.term_max_r = None
+        if self.postings_r16 is None:
+            self.fp_tile_base = self.fp_tile_term_off = None
+        plan.ws = plan.doc_off = plan.tokens = None  # the cursors are spent: a plan fills one index
+        self._make_struct()
         self._ws = None
 
-    def _tiled_view(self, doc_off, tokens, dl, T: int, chunk_docs: int, want_r16: bool):
-        """Postings sorted by (tile, term, doc_in_tile) for tiles of T docs -> (postings int32, tile_base int64
-        [n_tiles+1], tile_term_off int32 [n_tiles, V+1], term_max_r float32 [V] | None).  With want_r16 the low
-        half-word is fp16(tf*(k1+1)/(tf + t4[dl])) instead of tf; returns (None,)*4 if an r is not a normal fp16."""
-        dev = self.device
-        V1 = self.vocab + 1
-        n_tiles = (self.n_docs + T - 1) // T
-        chunk_docs = max(T, chunk_docs // T * T)
-        post_chunks, cnt_chunks = [], []
-        term_max = torch.zeros(self.vocab, dtype=torch.float32, device=dev) if want_r16 else None
-        for d0 in range(0, self.n_docs, chunk_docs):
-            d1 = min(self.n_docs, d0 + chunk_docs)
-            lo, hi = int(doc_off[d0].item()), int(doc_off[d1].item())
-            n_t = (d1 - d0 + T - 1) // T
-            if hi == lo:
-                cnt_chunks.append(torch.zeros(n_t * self.vocab, dtype=torch.int64, device=dev))
-                continue
-            tok = tokens[lo:hi].long()
-            doc = torch.repeat_interleave(torch.arange(d1 - d0, dtype=torch.int64, device=dev), dl[d0:d1])
-            # key orders postings by (tile, term, doc_in_tile)
-            key = ((doc // T) * self.vocab + tok) * T + (doc % T)
-            del tok, doc
-            key, tf = torch.unique(key, return_counts=True)  # sorted
-            if int(tf.max().item()) > 0xFFFF:
-                raise ValueError("term frequency above 65535 is not representable in the posting format")
-            tt = key // T
-            cnt_chunks.append(torch.bincount(tt, minlength=n_t * self.vocab))
-            if not want_r16:
-                post_chunks.append((((key % T) << 16) | tf).to(torch.int32))
-            else:
-                doc_abs = (tt // self.vocab) * T + (key % T) + d0
-                tf_f = tf.double()
-                r = tf_f * (K1 + 1) / (tf_f + self.t4_table[self.dl[doc_abs].long()])
-                r16 = r.to(torch.float32).to(torch.float16)
-                if float(r16.min().item()) < 6.2e-5 or not bool(torch.isfinite(r16).all()):
-                    return None, None, None, None
-                term_max.scatter_reduce_(0, tt % self.vocab, r16.float(), reduce="amax", include_self=True)
-                post_chunks.append((((key % T) << 16) | (r16.view(torch.int16).long() & 0xFFFF)).to(torch.int32))
-                del doc_abs, tf_f, r, r16
-            del key, tf, tt
-        post_chunks.append(torch.zeros(4, dtype=torch.int32, device=dev))  # padding (16-byte reads never fault)
-        postings = torch.cat(post_chunks)
-        del post_chunks
-        if cnt_chunks:
-            counts = torch.cat(cnt_chunks).view(n_tiles, self.vocab)
-        else:
-            counts = torch.zeros((0, self.vocab), dtype=torch.int64, device=dev)
-        off = torch.zeros((n_tiles, V1), dtype=torch.int64, device=dev)
-        torch.cumsum(counts, dim=1, out=off[:, 1:])
-        per_tile = off[:, -1] if n_tiles else torch.zeros(0, dtype=torch.int64, device=dev)
-        tile_base = torch.zeros(n_tiles + 1, dtype=torch.int64, device=dev)
-        if n_tiles:
-            torch.cumsum(per_tile, dim=0, out=tile_base[1:])
-            assert int(per_tile.max().item()) < 2 ** 31
-        return postings, tile_base, off.to(torch.int32).contiguous(), term_max
+    def _make_struct(self):
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        # reserved bit 0: first-pass runs are 16-byte aligned and padded to four postings (csrc/bm25_build.cu)
+        self.struct = _ffi.Bm25IndexStruct(
+            n_docs=self.n_docs, vocab=self.vocab, tile_docs=self.tile_docs, n_tiles=self.n_tiles,
+            has_negative_idf=int(self.has_negative_idf), max_doc_len=self.max_dl,
+            reserved=1 if self.postings_r16 is not None else 0,
+            d_tile_base=ptr(self.tile_base), d_tile_term_off=ptr(self.tile_term_off), d_postings=ptr(self.postings),
+            d_doc_len=ptr(self.dl), d_t4_table=ptr(self.t4_table), d_r_table=ptr(self.r_table), d_idf=ptr(self.idf),
+            d_postings_r16=ptr(self.postings_r16), d_term_max_r=ptr(self.term_max_r),
+            fp_tile_docs=self.fp_tile_docs, fp_n_tiles=self.fp_n_tiles,
+            d_fp_tile_base=ptr(self.fp_tile_base), d_fp_tile_term_off=ptr(self.fp_tile_term_off))
 
     @property
     def doc_t4(self) -> torch.Tensor:
@@ -287,16 +292,15 @@ class Bm25Index:
                                               query_lens.data_ptr(), Bq, mt, out.data_ptr(), st), "orag_bm25_dense")
         return out
 
-    def posting_bytes(self, query_terms: torch.Tensor, query_lens: torch.Tensor) -> int:
-        """Algorithmic bytes of a batch: sum over query tokens of df_shard(t) * 6."""
-        off = self.tile_term_off.long()
-        df_shard = (off[:, 1:] - off[:, :-1]).sum(dim=0)
-        idf_nz = self.idf != 0
-        t = query_terms.long()
-        mask = (t >= 0) & (t < self.vocab) & (torch.arange(t.shape[1], device=t.device)[None, :] < query_lens[:, None])
-        tc = t.clamp(0, self.vocab - 1)
-        per = torch.where(mask & idf_nz[tc], df_shard[tc], torch.zeros_like(tc))
-        return int(per.sum().item()) * 6
+    def posting_bytes(self, query_terms, query_lens) -> int:
+        """Algorithmic bytes of a batch: sum over query tokens of df_shard(t) * 6 (host arithmetic on
+        the shard's document frequencies; a measurement helper, not part of the search)."""
+        t = query_terms.cpu().numpy() if isinstance(query_terms, torch.Tensor) else np.asarray(query_terms)
+        n = query_lens.cpu().numpy() if isinstance(query_lens, torch.Tensor) else np.asarray(query_lens)
+        mask = (t >= 0) & (t < self.vocab) & (np.arange(t.shape[1])[None, :] < n[:, None])
+        tc = np.clip(t, 0, self.vocab - 1)
+        idf_nz = self.idf.cpu().numpy() != 0
+        return int(np.where(mask & idf_nz[tc], self.df_local[tc], 0).sum()) * 6
 
     # ------------------------------------------------------------------ on-disk format (SURVEY.md §8f row f2)
     # The reference's "format" for the keyword side is nothing at all: `BM25Okapi(tokenized_corpus)` is rebuilt from
@@ -304,7 +308,7 @@ class Bm25Index:
     #   <stem>.json   scalars (sizes, avgdl, eps, ...) + a manifest {name: dtype, shape, byte offset}
     #   <stem>.bin    the arrays of the layout described at the top of this module, little-endian, each aligned to
     #                 256 bytes, exactly as they sit in HBM -> loading is read (or mmap) + one copy per array
-    FORMAT_VERSION = 1
+    FORMAT_VERSION = 2  # 2: first-pass runs 16-byte aligned and padded to four postings
     _ARRAYS = ("idf", "dl", "t4_table", "r_table", "postings", "tile_base", "tile_term_off",
                "postings_r16", "fp_tile_base", "fp_tile_term_off", "term_max_r")
 
@@ -313,6 +317,7 @@ class Bm25Index:
         from pathlib import Path
         stem = Path(stem)
         arrays = {name: getattr(self, name) for name in self._ARRAYS if getattr(self, name) is not None}
+        arrays["df_local"] = torch.from_numpy(np.ascontiguousarray(self.df_local, dtype=np.int64))
         arrays["stats_df"] = torch.from_numpy(np.ascontiguousarray(self.stats.df, dtype=np.int64))
         arrays["stats_first_seen"] = torch.from_numpy(np.ascontiguousarray(self.stats.first_seen, dtype=np.int64))
         manifest, pos = {}, 0
@@ -329,7 +334,7 @@ class Bm25Index:
         meta = {"format": "orag-bm25-index", "version": self.FORMAT_VERSION, "n_docs": self.n_docs, "vocab": self.vocab,
                 "tile_docs": self.tile_docs, "n_tiles": self.n_tiles, "fp_tile_docs": self.fp_tile_docs,
                 "fp_n_tiles": self.fp_n_tiles, "doc_id_base": self.doc_id_base, "n_postings": self.n_postings,
-                "max_dl": self.max_dl, "has_negative_idf": self.has_negative_idf, "avgdl": float(self.avgdl).hex(),
+                "n_postings_fp": self.n_postings_fp, "max_dl": self.max_dl, "has_negative_idf": self.has_negative_idf, "avgdl": float(self.avgdl).hex(),
                 "average_idf": float(self.average_idf).hex(), "eps": float(self.eps).hex(),
                 "stats_n_docs": self.stats.n_docs, "stats_total_len": self.stats.total_len, "bytes": pos,
                 "arrays": manifest}
@@ -361,7 +366,7 @@ class Bm25Index:
         self = cls.__new__(cls)
         self.device = dev
         for key in ("n_docs", "vocab", "tile_docs", "n_tiles", "fp_tile_docs", "fp_n_tiles", "doc_id_base",
-                    "n_postings", "max_dl"):
+                    "n_postings", "n_postings_fp", "max_dl"):
             setattr(self, key, int(meta[key]))
         self.has_negative_idf = bool(meta["has_negative_idf"])
         self.avgdl, self.average_idf, self.eps = (float.fromhex(meta[k]) for k in ("avgdl", "average_idf", "eps"))
@@ -370,16 +375,7 @@ class Bm25Index:
         for name in cls._ARRAYS:
             a = arr(name)
             setattr(self, name, None if a is None else torch.from_numpy(a).to(dev))
-        ptr = lambda t: t.data_ptr() if t is not None else None
-        # same field-by-field construction as __init__ (tests/test_host_logic.py compares the two structs)
-        self.struct = _ffi.Bm25IndexStruct(
-            n_docs=self.n_docs, vocab=self.vocab, tile_docs=self.tile_docs, n_tiles=self.n_tiles,
-            has_negative_idf=int(self.has_negative_idf),
-            d_tile_base=ptr(self.tile_base), d_tile_term_off=ptr(self.tile_term_off),
-            max_doc_len=self.max_dl, reserved=0, d_postings=ptr(self.postings), d_doc_len=ptr(self.dl),
-            d_t4_table=ptr(self.t4_table), d_r_table=ptr(self.r_table), d_idf=ptr(self.idf),
-            d_postings_r16=ptr(self.postings_r16), d_term_max_r=ptr(self.term_max_r),
-            fp_tile_docs=self.fp_tile_docs, fp_n_tiles=self.fp_n_tiles,
-            d_fp_tile_base=ptr(self.fp_tile_base), d_fp_tile_term_off=ptr(self.fp_tile_term_off))
+        self.df_local = arr("df_local")
+        self._make_struct()
         self._ws = None
         return self

@@ -13,7 +13,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "liborag.so"
-SOURCES = ["api.cu", "gen.cu", "cosine_exact.cu", "cosine_tc.cu", "bm25.cu", "bm25_ms.cu", "rrf.cu", "pairwise.cu", "exchange.cu"]
+SOURCES = ["api.cu", "gen.cu", "cosine_exact.cu", "cosine_tc.cu", "bm25.cu", "bm25_ms.cu", "bm25_build.cu", "rrf.cu", "pairwise.cu", "exchange.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: the float64 paths must perform one IEEE rounding per Python-level operation
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",

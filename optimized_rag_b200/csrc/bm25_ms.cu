@@ -3,48 +3,52 @@
 // Same result as bm25.cu (bit-exact float64 scores of rank_bm25.BM25Okapi.get_scores + the glue at
 // rag/retrieval.py:324-347) at a fraction of the instructions per posting.
 //
-// First-pass view.  The index carries a second tiling of the postings (4096-doc tiles by default, up to 16384):
-// (doc_in_tile << 16) | fp16(r), r = tf*(k1+1)/(tf + t4[dl]) rounded to nearest, so a posting's
-// contribution is one fp32 multiply w*r (w = fp32 idf, duplicates of a query term merged into one weight)
-// and needs no document-length or table lookup.  Every approximate score s~ satisfies |s~ - s| <= eps*s with
-// eps = 2^-11 (fp16 r) + (n_terms + 2) * 2^-24 (fp32 weight, products, sums) < 5e-4: all terms are positive.
+// First-pass view (built by bm25_build.cu).  A second tiling of the postings (4096-doc tiles by default, up to
+// 16384): (doc_in_tile << 16) | fp16(r), r = tf*(k1+1)/(tf + t4[dl]) rounded to nearest, so a posting's
+// contribution is one fp32 multiply w*r (w = fp32 idf, duplicates of a query term merged into one weight) and needs
+// no document-length or table lookup.  Every (tile, term) run starts on a 16-byte boundary and is padded to a
+// multiple of four postings with copies of its last doc carrying impact 0, so runs are only ever moved as uint4.
+// Every approximate score s~ satisfies |s~ - s| <= eps*s with eps = 2^-11 (fp16 r) + (n_terms + 2) * 2^-24 (fp32
+// weight, products, sums in any order) < 5e-4: all terms are positive.
 //
-// MaxScore.  prepare_queries_kernel sorts a query's terms by ascending upper bound
-// ub_t = w_t * max_r(t) (max over the shard's postings of t) and stores the inclusive prefix sums.
-// With the query's running threshold thr (a lower bound of the k-th best s~ seen so far, from the same
-// log-scale histogram bm25.cu uses) the terms whose prefix sum stays below thr' = thr * (1 - 2^-9) are
-// "non-essential": a document that contains only those cannot reach thr'.
+// MaxScore.  prepare_queries_kernel sorts a query's terms by ascending upper bound ub_t = w_t * max_r(t) (max over
+// the shard's postings of t) and stores the inclusive prefix sums.  With the query's running threshold thr (a lower
+// bound of the k-th best s~ seen so far, from the same log-scale histogram bm25.cu uses) the terms whose prefix sum
+// stays below thr' = thr * (1 - 2^-9) are "non-essential": a document that contains only those cannot reach thr'.
+// Any SUPERSET of the essential terms is just as valid, so the partition taken when a pair's postings are staged (one
+// pair ahead, with the threshold of that moment -- thresholds only rise) is the partition the pair is processed with.
 //
-// One warp works on one (query, tile) pair at a time with three small shared-memory structures: a bitmap of
-// the tile's docs, per-word prefix popcounts, and a compact fp32 accumulator indexed by a doc's RANK among
-// the marked docs (so the accumulator is sized by the docs a query touches, not by the tile):
-//   E1  mark the docs of the essential runs in the bitmap (shared-memory atomicOr); the runs that were essential
-//       by the threshold of one pair earlier have been copied into a per-warp staging buffer with 16-byte
-//       cp.async (issued right after E2 of the previous pair), the rest is read from global memory
-//   R   prefix popcounts -> rank(d); the number of marked docs must fit the accumulator, otherwise the pair
-//       is processed in doc sub-ranges (runs are doc-sorted: a sub-range is a contiguous part of every run,
-//       found by one binary search per run and boundary), re-reading the threshold in between
-//   E2  add the essential contributions into acc[rank(d)]
-//   N   stream the non-essential runs with 16-byte loads (two in flight per lane), most valuable term first; a
-//       posting only matters when its doc is marked (one shared-memory word test), in which case its contribution
-//       completes acc[rank(d)]; the remaining runs are skipped once max(acc) + their upper bounds < thr'
-//   L   (cold sub-ranges only) the k-th largest of the 32 lane maxima of acc is a lower bound of the k-th best
-//       approximate score: publish it as the threshold before anything is emitted
-//   X   lanes walk the RANKS (balanced, conflict-free): read and reset acc[r]; a score that clears thr' gets
-//       its doc id back from the prefix counts (binary search + find-n-th-set-bit) and is emitted
-// Docs are distinct inside a run, and runs are applied one at a time with __syncwarp in between, so plain
-// read-modify-writes suffice (no floating-point atomics).
+// One warp works on one (query, tile) pair at a time with four small shared-memory structures: a staging buffer that
+// holds the postings of ALL essential runs of the pair back to back (16-byte cp.async, issued while the previous pair
+// is being finished), a bitmap of the tile's docs, per-word prefix popcounts, and a compact fp32 accumulator indexed
+// by a doc's RANK among the marked docs (sized by the docs a query touches, not by the tile):
+//   E1  one flat loop over the staged postings marks their docs in the bitmap
+//   R   prefix popcounts -> rank(d)
+//   E2  one flat loop adds w_run * r into acc[rank(d)] (the run of a staged posting comes from a tiny table of run
+//       ends; two runs may hold the same doc, hence shared-memory atomic adds -- the order of fp32 additions is
+//       covered by eps)
+//   N   the non-essential runs are streamed from global memory with 16-byte loads (two in flight per lane), most
+//       valuable term first; a posting only matters when its doc is marked (one shared-memory word test), in which
+//       case its contribution completes acc[rank(d)].  Before every run: if the best partial score (kept up to date
+//       with one warp-wide REDUX per run) plus the upper bounds of the remaining terms stays below thr', nothing of
+//       this pair can be emitted and the remaining (longest) runs are not read at all
+//   X   only if the best score reaches thr': lanes walk the RANKS, and a score that clears thr' gets its doc id back
+//       from the prefix counts (binary search + find-n-th-set-bit) and is emitted.  Otherwise acc is just zeroed.
+// A pair whose essential postings do not fit the staging buffer (cold start: thr = 0 makes every term essential; or a
+// very dense query) takes the same steps in doc sub-ranges: runs are doc-sorted, so a sub-range is a contiguous slice
+// of every run (one binary search per run and boundary); the threshold is re-read between sub-ranges, and before a
+// cold sub-range emits anything it derives a LOCAL threshold -- the k-th largest of the 32 lane maxima of its own
+// scores, a valid lower bound of the global k-th best -- and publishes it.
 //
-// Superset argument (as for the cosine first pass): let S_k be the true k-th best score and S~_k the k-th
-// best approximate score.  At most k-1 docs have s > S_k, so S~_k <= S_k (1 + eps); thr <= S~_k always.  A
-// true top-k doc (or a tie with the k-th) has s~ >= S_k (1 - eps) >= thr (1 - eps) / (1 + eps) > thr', so it
-// is never pruned and always emitted; 2^-9 also covers the rounding of the bounds themselves (prefix sums
-// are rounded up, thr' down).  ms_finalize_kernel keeps the candidates with s~ >= final thr', re-scores them
-// with score_doc() (float64, query order, duplicates twice) and selects by (score desc, id asc).
+// Superset argument (as for the cosine first pass): let S_k be the true k-th best score and S~_k the k-th best
+// approximate score.  At most k-1 docs have s > S_k, so S~_k <= S_k (1 + eps); thr <= S~_k always.  A true top-k doc
+// (or a tie with the k-th) has s~ >= S_k (1 - eps) >= thr (1 - eps) / (1 + eps) > thr', so it is never pruned and
+// always emitted; 2^-9 also covers the rounding of the bounds themselves (prefix sums are rounded up, thr' down).
+// ms_finalize_kernel keeps the candidates with s~ >= final thr', re-scores them with score_doc() (float64, query
+// order, duplicates twice) and selects by (score desc, id asc).
 //
-// Work items are (tile, slice of the query batch), handed out through an atomic counter; the prepared query
-// of pair i+2 and the run offsets (+ an L2 prefetch of the run heads) of pair i+1 are in flight while pair i
-// is consumed.
+// Work items are (tile, slice of the query batch), handed out through an atomic counter; the prepared query of pair
+// i+2 and the run offsets (+ an L2 prefetch of the run heads) of pair i+1 are in flight while pair i is consumed.
 #include <cuda_fp16.h>
 
 #include "bm25_shared.cuh"
@@ -56,22 +60,20 @@ constexpr int kMsWarps = 16;      // warps per CTA of the stand-alone configurat
 constexpr int kMsThreads = kMsWarps * 32;
 constexpr int kMsBgWarps = 8;     // ... and of the background configuration (see ms_topk)
 constexpr int kMsTerms = 32;      // scoring terms per query on this path (one per lane)
-// per-warp working set: {marked docs per (query, tile sub-range), essential postings per sub-range the splitter
-// aims for, postings of the essential runs staged in shared memory per pair (multiple of 4)}
-struct MsShape {
-    int acc_cap, sub_target, stage;
-};
-constexpr MsShape kMsAlone = {1024, 512, 512};
-constexpr MsShape kMsBackground = {512, 256, 256};
+constexpr int kMsWarpBytes = 7168;    // shared memory per warp, stand-alone: 2 CTAs x (16 x 7168 + 1 KiB) fit one SM
+constexpr int kMsBgWarpBytes = 3840;  // background: 8 warps < 31 KB next to a resident cosine scan CTA
 constexpr int kMsMaxTile = 16384;
 constexpr int kMsSurvCap = 2048;  // candidates re-scored per query
 constexpr int kMsContrib = 4096;  // (survivor, token) contributions staged in shared memory by ms_finalize_kernel
 constexpr float kMsGuard = 1.0f - 1.0f / 512.0f;
 
-// per-warp shared memory: staging buffer | compact accumulator | bitmap | per-word ranks
-__host__ __device__ inline size_t ms_smem_per_warp(int words, const MsShape &sh)
+// per-warp shared memory: staging buffer [cap] | compact accumulator [cap] | bitmap [words] | per-word ranks [words]
+// | run table (ends [32], weights [32]).  cap = postings of the essential runs of one pair (or sub-range) = upper
+// bound of the docs it can mark; a multiple of 4.
+__host__ __device__ inline int ms_cap(int words, int warp_bytes)
 {
-    return ((size_t)sh.stage * 4 + (size_t)sh.acc_cap * 4 + (size_t)words * 4 + (size_t)words * 2 + 15) & ~(size_t)15;
+    const int left = warp_bytes - words * 6 - 260;  // run table (256 B) + alignment slack
+    return left < 64 ? 0 : (left / 8) & ~3;
 }
 
 struct MsParams {
@@ -93,12 +95,11 @@ struct MsParams {
     int cap;
     int32_t *surv_doc;  // [n_queries, kMsSurvCap]
     double *surv_score; // [n_queries, kMsSurvCap]
-    uint32_t *work;     // [2] next work item of the seed / main launch
+    uint32_t *work;     // next work item
     int32_t *status;    // [n_queries] or null
     int q_split;
     int n_items;
-    int tile_begin;     // this launch covers tiles [tile_begin, tile_begin + n_items / q_split)
-    MsShape shape;
+    int warp_bytes;     // kMsWarpBytes or kMsBgWarpBytes
 };
 
 // One thread per query: drop OOV / zero-idf tokens, merge duplicates, sort by upper bound.
@@ -175,24 +176,30 @@ __device__ __forceinline__ float post_r(uint32_t post)
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+
+// warp-wide maximum of non-negative floats: their bit patterns order like unsigned integers -> one REDUX
+__device__ __forceinline__ float warp_max_nonneg(float v)
+{
+    return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
+}
+
 struct MsDesc {  // lane i = i-th term of the prepared query
     int term;
     float w, pre;
     int n, q;
 };
-struct MsRun {
-    int rel;     // first posting of the run relative to the tile's 16-byte aligned base pointer
-    int len;
+struct MsRun {   // lane i = i-th term's run in the current tile, in units of four postings (uint4)
+    int rel4, len4;
     float w, pre;
     int n, q;
-    int soff;    // position of the run's first posting in the staging buffer
-    int slen;    // leading postings of the run available in the staging buffer (0 = not staged)
+    int soff4;   // essential lanes: position of the run in the staging buffer
+    int n_ne;    // warp-uniform: number of non-essential terms (a prefix of the lanes) as decided at staging time
+    int e4;      // warp-uniform: staged uint4s in total, or -1 when the pair does not fit (sub-range path)
 };
-
-__device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void *gmem_src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
-}
 
 __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_constant__ MsParams p)
 {
@@ -200,45 +207,41 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
     const int T = p.ix.fp_tile_docs;
     const int words = (T + 31) >> 5;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int kMsStage = p.shape.stage, kMsAccCap = p.shape.acc_cap, kMsSubTarget = p.shape.sub_target;
-    const size_t per_warp = ms_smem_per_warp(words, p.shape);
-    uint8_t *mine = reinterpret_cast<uint8_t *>(ms_smem) + wib * per_warp;
-    uint32_t *stage = reinterpret_cast<uint32_t *>(mine);                             // [kMsStage] essential runs
-    float *acc = reinterpret_cast<float *>(mine + (size_t)kMsStage * 4);              // [kMsAccCap], zero between pairs
-    uint32_t *bm = reinterpret_cast<uint32_t *>(mine + (size_t)(kMsStage + kMsAccCap) * 4);  // [words] marked docs
-    uint16_t *pre = reinterpret_cast<uint16_t *>(bm + words);                         // [words] rank of a word's bit 0
+    const int cap = ms_cap(words, p.warp_bytes);
+    uint8_t *mine = reinterpret_cast<uint8_t *>(ms_smem) + (size_t)wib * p.warp_bytes;
+    uint32_t *stage = reinterpret_cast<uint32_t *>(mine);                      // [cap] essential postings, back to back
+    float *acc = reinterpret_cast<float *>(mine + (size_t)cap * 4);            // [cap], zero between pairs
+    uint32_t *bm = reinterpret_cast<uint32_t *>(mine + (size_t)cap * 8);       // [words] marked docs, zero between pairs
+    uint16_t *pre = reinterpret_cast<uint16_t *>(bm + words);                  // [words] rank of a word's bit 0
+    int *rend = reinterpret_cast<int *>(mine + (((size_t)cap * 8 + (size_t)words * 6 + 3) & ~(size_t)3));  // [32] run ends
+    float *rw = reinterpret_cast<float *>(rend + 32);                          // [32] run weights
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
     for (int i = lane; i < words; i += 32) bm[i] = 0u;
-    for (int i = lane; i < kMsAccCap; i += 32) acc[i] = 0.f;
+    for (int i = lane; i < cap; i += 32) acc[i] = 0.f;
     __syncwarp();
 
     const int V1 = p.ix.vocab + 1;
     const int nq = p.n_queries;
     const unsigned FULL = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int S = p.q_split;
     const int4 *qd = reinterpret_cast<const int4 *>(p.qd);
     const int wpl = (words + 31) >> 5;  // bitmap words per lane in the rank pass
-    const bool wpl4 = words == 128;     // (bm and pre are 16-byte aligned: see ms_smem_per_warp)
-
-    auto rank_of = [&](uint32_t d) -> int {
-        const uint32_t wd = bm[d >> 5];
-        return (int)pre[d >> 5] + __popc(wd & ((1u << (d & 31)) - 1u));
-    };
+    const bool wpl4 = words == 128;     // (bm and pre are 16-byte aligned: cap is a multiple of 4)
+    const int k = p.k;
 
     for (;;) {
         int item = 0;
         if (lane == 0) item = (int)atomicAdd(p.work, 1u);
         item = __shfl_sync(FULL, item, 0);
         if (item >= p.n_items) break;
-        const int tile_rel = item / S;
-        const int part = item - tile_rel * S;
-        const int tile = p.tile_begin + tile_rel;
+        const int tile = item / S;
+        const int part = item - tile * S;
         const int qi0 = (int)(((int64_t)nq * part) / S);
         const int qi1 = (int)(((int64_t)nq * (part + 1)) / S);
         const int64_t base_doc = (int64_t)tile * T;
-        const int64_t tile_g0 = p.ix.d_fp_tile_base[tile];
-        const int tb = (int)(tile_g0 & 3);
-        const uint32_t *tp = p.ix.d_postings_r16 + (tile_g0 - tb);  // 16-byte aligned; run offsets get +tb
+        const uint32_t *tp = p.ix.d_postings_r16 + p.ix.d_fp_tile_base[tile];  // 16-byte aligned (padded layout)
+        const uint4 *tp4 = reinterpret_cast<const uint4 *>(tp);
         const int32_t *toff = p.ix.d_fp_tile_term_off + (int64_t)tile * V1;
         // stagger the query order across tiles so a query's threshold is established by few warps
         const int q_shift = (int)(((int64_t)tile * 7919) % nq);
@@ -262,53 +265,46 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
         // ---- stage B: run offsets inside this tile, L2 prefetch of the head of every run
         auto stage_run = [&](const MsDesc &d) -> MsRun {
             MsRun r;
-            r.rel = 0; r.len = 0; r.w = d.w; r.pre = d.pre; r.n = d.n; r.q = d.q; r.soff = 0; r.slen = 0;
+            r.rel4 = 0; r.len4 = 0; r.w = d.w; r.pre = d.pre; r.n = d.n; r.q = d.q; r.soff4 = 0; r.n_ne = 0; r.e4 = 0;
             if (lane < d.n) {
-                r.rel = __ldg(toff + d.term);
-                r.len = __ldg(toff + d.term + 1) - r.rel;
-                r.rel += tb;
-                if (r.len > 0) {
-                    prefetch_l2(tp + r.rel);
-                    if (r.len > 32) prefetch_l2(tp + r.rel + 32);
-                    if (r.len > 64) prefetch_l2(tp + r.rel + 64);
-                    if (r.len > 96) prefetch_l2(tp + r.rel + 96);
+                const int o0 = __ldg(toff + d.term), o1 = __ldg(toff + d.term + 1);
+                r.rel4 = o0 >> 2;
+                r.len4 = (o1 - o0) >> 2;
+                if (r.len4 > 0) {
+                    prefetch_l2(tp4 + r.rel4);
+                    if (r.len4 > 8) prefetch_l2(tp4 + r.rel4 + 8);
+                    if (r.len4 > 16) prefetch_l2(tp4 + r.rel4 + 16);
+                    if (r.len4 > 24) prefetch_l2(tp4 + r.rel4 + 24);
                 }
             }
             return r;
         };
-        // ---- stage C: copy the runs that are (by the threshold as of now) essential into the staging buffer,
-        // most valuable term first, through 16-byte aligned source windows
+        // ---- stage C: partition by the threshold as of now; copy the essential runs, back to back, into the staging
+        // buffer (the buffer must be free: called after E2 of the pair in front)
         auto stage_posts = [&](MsRun &run) {
             float thr_now = 0.f;
             if (run.n > 0) thr_now = thr_to_float(__ldcg(p.thr_bits + run.q));
-            const bool want = lane < run.n && run.len > 0 && !(run.pre < thr_now);
-            const int shift = run.rel & 3;
-            const int alen = want ? ((shift + run.len + 3) & ~3) : 0;
-            int incl = alen;  // suffix sums: lanes above this one come first in the buffer
+            run.n_ne = __popc(__ballot_sync(FULL, lane < run.n && run.pre < thr_now));  // a prefix of the lanes
+            const bool want = lane < run.n && lane >= run.n_ne && run.len4 > 0;
+            const int alen = want ? run.len4 : 0;
+            int incl = alen;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_down_sync(FULL, incl, d);
-                if (lane + d < 32) incl += v;
+                const int v = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += v;
             }
-            const int excl = incl - alen;
-            const int avail = max(0, min(alen, kMsStage - excl));  // multiple of 4
-            run.soff = excl + shift;
-            run.slen = max(0, min(run.len, avail - shift));
-            const int n16 = run.slen > 0 ? (avail >> 2) : 0;
-            const uint32_t dst_s = stage_s + (uint32_t)excl * 4u;
-            const uint32_t *src = tp + (run.rel & ~3);
-            if (n16 > 0) cp_async16_s(dst_s, src);
-            if (n16 > 1) cp_async16_s(dst_s + 16, src + 4);
-            unsigned active = __ballot_sync(FULL, n16 > 2);
-            while (active) {
-                const int i = __ffs(active) - 1;
-                active &= active - 1;
-                const uint32_t d0 = __shfl_sync(FULL, dst_s, i);
-                const unsigned long long s0 = __shfl_sync(FULL, (unsigned long long)(uintptr_t)src, i);
-                const int cnt = __shfl_sync(FULL, n16, i);
-                const uint32_t *sp = reinterpret_cast<const uint32_t *>((uintptr_t)s0);
+            run.soff4 = incl - alen;
+            const int e4 = __shfl_sync(FULL, incl, 31);
+            run.e4 = (e4 * 4 <= cap) ? e4 : -1;
+            if (run.e4 > 0) {
+                for (unsigned a = __ballot_sync(FULL, want); a; a &= a - 1) {
+                    const int i = __ffs(a) - 1;
+                    const int cnt = __shfl_sync(FULL, alen, i);
+                    const uint32_t dst = stage_s + 16u * (uint32_t)__shfl_sync(FULL, run.soff4, i);
+                    const uint4 *src = tp4 + __shfl_sync(FULL, run.rel4, i);
 #pragma unroll 1
-                for (int c = 2 + lane; c < cnt; c += 32) cp_async16_s(d0 + 16u * c, sp + 4 * c);
+                    for (int c = lane; c < cnt; c += 32) cp_async16_s(dst + 16u * c, src + c);
+                }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -319,75 +315,105 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
         MsDesc descA = stage_desc(qi0 + 2);
 
         for (int qi = qi0; qi < qi1; ++qi) {
-            unsigned long long thr_bits = 0;
-            if (cur.n > 0) thr_bits = __ldcg(p.thr_bits + cur.q);
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
-
             const int n = cur.n;  // warp-uniform
-            float thr = thr_to_float(thr_bits);
             const int q = cur.q;
-            const bool mine_ok = lane < n && cur.len > 0;
-            int n_ne = __popc(__ballot_sync(FULL, lane < n && cur.pre < thr));  // a prefix of the lanes
-            unsigned ess = __ballot_sync(FULL, mine_ok && lane >= n_ne);
             bool staged_next = false;
+            const bool mine_ok = lane < n && cur.len4 > 0;
+            int n_ne = cur.n_ne;
+            unsigned ess = __ballot_sync(FULL, mine_ok && lane >= n_ne);
             if (ess) {
-                int etot = (mine_ok && lane >= n_ne) ? cur.len : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) etot += __shfl_xor_sync(FULL, etot, o);
-                // number of doc sub-ranges: marked docs per sub-range must fit the compact accumulator
-                int nsub = 1, sub_docs = T;  // T and nsub are powers of two
-                while (nsub * kMsSubTarget < etot && sub_docs > 32) {
-                    nsub <<= 1;
-                    sub_docs >>= 1;
+                float thr = thr_to_float(__ldcg(p.thr_bits + q));
+                const bool fast = cur.e4 > 0;
+                // sub-ranges (slow path only): marked docs per sub-range must fit the compact accumulator
+                int nsub = 1, sub_docs = T;
+                if (!fast) {
+                    int etot = (mine_ok && lane >= n_ne) ? cur.len4 * 4 : 0;
+                    etot = __reduce_add_sync(FULL, etot);
+                    while (nsub * (cap >> 1) < etot && sub_docs > 32) {
+                        nsub <<= 1;
+                        sub_docs >>= 1;
+                    }
                 }
-                int cpos = 0;  // this lane's run: first posting of the current sub-range
+                int cpos = 0;  // slow path: this lane's run, first posting of the current sub-range
                 for (int sub = 0; sub < nsub; ++sub) {
-                    if (sub > 0) {
-                        // a pair that needs several sub-ranges is a cold one: its own emissions have raised the
-                        // threshold since, so re-read it and re-partition (fewer essential runs, fewer emissions)
-                        thr = thr_to_float(__ldcg(p.thr_bits + q));
-                        n_ne = __popc(__ballot_sync(FULL, lane < n && cur.pre < thr));
-                        ess = __ballot_sync(FULL, mine_ok && lane >= n_ne);
-                        if (!ess) break;  // nothing left in this tile can reach the threshold
-                    }
-                    const unsigned non = __ballot_sync(FULL, mine_ok && lane < n_ne);
-                    int s_end = cur.len;
-                    if (sub + 1 < nsub && mine_ok) {
-                        // first posting of this lane's run with doc >= the sub-range's upper boundary
-                        const uint32_t bound = (uint32_t)((sub + 1) * sub_docs);
-                        int lo = cpos, hi = cur.len;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if ((__ldg(tp + cur.rel + mid) >> 16) < bound) lo = mid + 1; else hi = mid;
+                    int E;              // staged postings of this (sub-)range
+                    int n4_lo, n4_cnt;  // this lane's run: uint4 slice the N phase streams
+                    if (fast) {
+                        E = cur.e4 * 4;
+                        n4_lo = cur.rel4;
+                        n4_cnt = cur.len4;
+                        if (mine_ok && lane >= n_ne) {
+                            const int r = __popc(ess & lt_mask);
+                            rend[r] = (cur.soff4 + cur.len4) * 4;
+                            rw[r] = cur.w;
                         }
-                        s_end = lo;
-                    }
-                    // this lane's view of its run in the sub-range: global part + staged prefix
-                    const int v_rel = cur.rel + cpos;
-                    const int v_len = mine_ok ? s_end - cpos : 0;
-                    const int v_sl = staged_next ? 0 : max(0, min(v_len, cur.slen - cpos));
-                    const int v_so = cur.soff + cpos;
-                    cpos = s_end;
-#define MS_VIEW(i)                                         \
-    const int len_ = __shfl_sync(FULL, v_len, i);          \
-    const int sl_ = __shfl_sync(FULL, v_sl, i);            \
-    const uint32_t *sp_ = stage + __shfl_sync(FULL, v_so, i); \
-    const uint32_t *gp_ = tp + __shfl_sync(FULL, v_rel, i)
-                    // ---- E1: mark the docs of the essential runs
-                    for (unsigned a = ess; a; a &= a - 1) {
-                        const int i = __ffs(a) - 1;
-                        MS_VIEW(i);
+                    } else {
+                        if (sub > 0) {
+                            // a pair that needs several sub-ranges is a cold one: its own emissions have raised the
+                            // threshold since, so re-read it and re-partition (fewer essential runs, fewer emissions)
+                            thr = thr_to_float(__ldcg(p.thr_bits + q));
+                            n_ne = max(n_ne, __popc(__ballot_sync(FULL, lane < n && cur.pre < thr)));
+                            ess = __ballot_sync(FULL, mine_ok && lane >= n_ne);
+                            if (!ess) break;  // nothing left in this tile can reach the threshold
+                        }
+                        int s_end = cur.len4 * 4;
+                        if (sub + 1 < nsub && mine_ok) {
+                            // first posting of this lane's run with doc >= the sub-range's upper boundary
+                            const uint32_t bound = (uint32_t)((sub + 1) * sub_docs);
+                            int lo = cpos, hi = s_end;
+                            const uint32_t *run = tp + cur.rel4 * 4;
+                            while (lo < hi) {
+                                const int mid = (lo + hi) >> 1;
+                                if ((__ldg(run + mid) >> 16) < bound) lo = mid + 1; else hi = mid;
+                            }
+                            s_end = lo;
+                        }
+                        const int v_len = mine_ok ? s_end - cpos : 0;
+                        // non-essential lanes stream the 16-byte aligned superset of their slice (postings outside the
+                        // sub-range belong to unmarked docs)
+                        n4_lo = cur.rel4 + (cpos >> 2);
+                        n4_cnt = v_len > 0 ? ((s_end + 3) >> 2) - (cpos >> 2) : 0;
+                        // essential slices: copied back to back into the staging buffer
+                        const bool is_ess = mine_ok && lane >= n_ne;
+                        const int alen = is_ess ? v_len : 0;
+                        int incl = alen;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int v = __shfl_up_sync(FULL, incl, d);
+                            if (lane >= d) incl += v;
+                        }
+                        E = __shfl_sync(FULL, incl, 31);
+                        const int soff = incl - alen;
+                        const int src0 = cur.rel4 * 4 + cpos;
+                        cpos = s_end;
+                        if (E > cap) {
+                            // a skewed sub-range holds more essential postings than the buffer: the caller re-runs the query
+                            if (p.status && lane == 0) atomicOr(p.status + q, ORAG_STATUS_OVERFLOW);
+                            continue;
+                        }
+                        if (is_ess) {
+                            const int r = __popc(ess & lt_mask);
+                            rend[r] = soff + alen;
+                            rw[r] = cur.w;
+                        }
+                        for (unsigned a = ess; a; a &= a - 1) {
+                            const int i = __ffs(a) - 1;
+                            const int cnt = __shfl_sync(FULL, alen, i);
+                            const int dst = __shfl_sync(FULL, soff, i);
+                            const uint32_t *src = tp + __shfl_sync(FULL, src0, i);
 #pragma unroll 1
-                        for (int j = lane; j < sl_; j += 32) {
-                            const uint32_t d = sp_[j] >> 16;
-                            atomicOr(bm + (d >> 5), 1u << (d & 31));
+                            for (int c = lane; c < cnt; c += 32) stage[dst + c] = __ldg(src + c);
                         }
+                        if (E == 0) continue;
+                    }
+                    __syncwarp();
+                    // ---- E1: mark the docs of every staged posting
 #pragma unroll 1
-                        for (int j = sl_ + lane; j < len_; j += 32) {
-                            const uint32_t d = __ldg(gp_ + j) >> 16;
-                            atomicOr(bm + (d >> 5), 1u << (d & 31));
-                        }
+                    for (int j = lane; j < E; j += 32) {
+                        const uint32_t d = stage[j] >> 16;
+                        atomicOr(bm + (d >> 5), 1u << (d & 31));
                     }
                     __syncwarp();
                     // ---- R: prefix popcounts (lane l owns words [l*wpl, (l+1)*wpl))
@@ -409,7 +435,7 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                         const int v = __shfl_up_sync(FULL, incl, o);
                         if (lane >= o) incl += v;
                     }
-                    const int marked = __shfl_sync(FULL, incl, 31);
+                    const int marked = __shfl_sync(FULL, incl, 31);  // <= E <= cap
                     const int my_base = incl - mycnt;
                     if (wpl4) {
                         const uint32_t p0 = (uint32_t)my_base, p1 = p0 + __popc(w4.x), p2 = p1 + __popc(w4.y),
@@ -426,135 +452,111 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                         }
                     }
                     __syncwarp();
-                    const bool fits = marked <= kMsAccCap;
-                    if (fits) {
-                        // ---- E2: essential contributions into the compact accumulator
-                        for (unsigned a = ess; a; a &= a - 1) {
-                            const int i = __ffs(a) - 1;
-                            MS_VIEW(i);
-                            const float w = __shfl_sync(FULL, cur.w, i);
+                    // ---- E2: essential contributions into the compact accumulator, one flat loop
+                    {
+                        int r = 0;
 #pragma unroll 1
-                            for (int j = lane; j < sl_; j += 32) {
-                                const uint32_t post = sp_[j];
-                                float *slot = acc + rank_of(post >> 16);
-                                *slot = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
+                        for (int j = lane; j < E; j += 32) {
+                            while (j >= rend[r]) ++r;
+                            const uint32_t post = stage[j];
+                            if (post & 0xFFFFu) {  // (padding postings carry impact 0)
+                                const uint32_t d = post >> 16;
+                                const uint32_t wd = bm[d >> 5];
+                                atomicAdd(acc + (int)pre[d >> 5] + __popc(wd & ((1u << (d & 31)) - 1u)),
+                                          __fmul_rn(rw[r], post_r(post)));
                             }
-#pragma unroll 1
-                            for (int j = sl_ + lane; j < len_; j += 32) {
-                                const uint32_t post = __ldg(gp_ + j);
-                                float *slot = acc + rank_of(post >> 16);
-                                *slot = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
-                            }
-                            __syncwarp();
                         }
                     }
+                    __syncwarp();
                     // the staging buffer is free from here on: start copying the next pair's essential runs
-                    if (!staged_next) {
+                    if (fast) {
                         stage_posts(nxt);
                         staged_next = true;
                     }
-                    if (fits) {
-                        // ---- N: non-essential runs complete the marked docs only (streamed, one load ahead), most
-                        // valuable term first.  Before every run: if even the best partial score plus everything the
-                        // remaining terms could add stays below thr', nothing in this sub-range can be emitted and the
-                        // remaining (longest) runs are not read at all.
-                        bool reachable = true;
-                        for (unsigned a = non; a;) {
-                            const int i = 31 - __clz(a);
-                            a &= ~(1u << i);
-                            {
-                                float mx = 0.f;
-                                for (int r = lane; r < marked; r += 32) mx = fmaxf(mx, acc[r]);
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
-                                const float rest = __shfl_sync(FULL, cur.pre, i);  // upper bounds of terms 0..i
-                                if (__fadd_ru(mx, rest) < thr) {
-                                    reachable = false;
-                                    break;
-                                }
-                            }
-                            const int len_ = __shfl_sync(FULL, v_len, i);
-                            const uint32_t *gp_ = tp + __shfl_sync(FULL, v_rel, i);
-                            const float w = __shfl_sync(FULL, cur.w, i);
-                            auto one = [&](uint32_t post) {
+                    // best partial score so far
+                    float mx = 0.f;
+                    for (int r = lane; r < marked; r += 32) mx = fmaxf(mx, acc[r]);
+                    mx = warp_max_nonneg(mx);
+                    // ---- N: non-essential runs complete the marked docs only, most valuable term first.  Before every
+                    // run: if even the best partial score plus everything the remaining terms could add stays below
+                    // thr', nothing of this (sub-)range can be emitted and the remaining (longest) runs are not read.
+                    bool reachable = true;
+                    for (unsigned a = __ballot_sync(FULL, mine_ok && lane < n_ne); a;) {
+                        const int i = 31 - __clz(a);
+                        a &= ~(1u << i);
+                        const float rest = __shfl_sync(FULL, cur.pre, i);  // upper bounds of terms 0..i
+                        if (__fadd_ru(mx, rest) < thr) {
+                            reachable = false;
+                            break;
+                        }
+                        const int body4 = __shfl_sync(FULL, n4_cnt, i);
+                        const uint4 *g4 = tp4 + __shfl_sync(FULL, n4_lo, i);
+                        const float w = __shfl_sync(FULL, cur.w, i);
+                        float hmax = 0.f;
+                        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+                        if (lane < body4) v0 = __ldg(g4 + lane);
+                        if (lane + 32 < body4) v1 = __ldg(g4 + lane + 32);
+#pragma unroll 1
+                        for (int c = lane; c < body4; c += 64) {
+                            const uint4 u0 = v0, u1 = v1;
+                            if (c + 64 < body4) v0 = __ldg(g4 + c + 64);
+                            if (c + 96 < body4) v1 = __ldg(g4 + c + 96);
+                            // test all eight postings first (branch-free), then visit the rare hits in one divergent
+                            // loop: ~3 % of the postings hit, but some lane of the warp does in most groups of 32, so a
+                            // branch per posting would run the update path almost every time
+                            auto bit = [&](uint32_t post) -> uint32_t {
+                                return (bm[post >> 21] >> ((post >> 16) & 31u)) & 1u;
+                            };
+                            uint32_t hits = bit(u0.x) | (bit(u0.y) << 1) | (bit(u0.z) << 2) | (bit(u0.w) << 3);
+                            if (c + 32 < body4)
+                                hits |= (bit(u1.x) << 4) | (bit(u1.y) << 5) | (bit(u1.z) << 6) | (bit(u1.w) << 7);
+                            while (hits) {
+                                const int b = __ffs(hits) - 1;
+                                hits &= hits - 1;
+                                const uint4 u = (b & 4) ? u1 : u0;
+                                const uint32_t lo2 = (b & 1) ? u.y : u.x, hi2 = (b & 1) ? u.w : u.z;
+                                const uint32_t post = (b & 2) ? hi2 : lo2;
                                 const uint32_t d = post >> 16;
                                 const uint32_t wd = bm[d >> 5];
-                                if ((wd >> (d & 31)) & 1u) {
-                                    float *slot = acc + (int)pre[d >> 5] + __popc(wd & ((1u << (d & 31)) - 1u));
-                                    *slot = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
-                                }
-                            };
-                            // up to 3 head and 3 tail postings around the 16-byte aligned body
-                            const int head = min(len_, (int)((16u - ((uint32_t)(uintptr_t)gp_ & 15u)) & 15u) >> 2);
-                            const int body4 = (len_ - head) >> 2;
-                            const int tail = len_ - head - 4 * body4;
-                            const uint4 *g4 = reinterpret_cast<const uint4 *>(gp_ + head);
-                            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-                            if (lane < body4) v0 = __ldg(g4 + lane);
-                            if (lane + 32 < body4) v1 = __ldg(g4 + lane + 32);
-                            {
-                                int idx = -1;
-                                if (lane < head) idx = lane;
-                                else if (lane >= 3 && lane - 3 < tail) idx = head + 4 * body4 + (lane - 3);
-                                if (idx >= 0) one(__ldg(gp_ + idx));
-                            }
-#pragma unroll 1
-                            for (int c = lane; c < body4; c += 64) {
-                                const uint4 u0 = v0, u1 = v1;
-                                if (c + 64 < body4) v0 = __ldg(g4 + c + 64);
-                                if (c + 96 < body4) v1 = __ldg(g4 + c + 96);
-                                // test all eight postings first (branch-free), then visit the rare hits in one
-                                // divergent loop: ~3 % of the postings hit, but some lane of the warp does in most
-                                // groups of 32, so a branch per posting would run the update path almost every time
-                                auto bit = [&](uint32_t post) -> uint32_t {
-                                    return (bm[post >> 21] >> ((post >> 16) & 31u)) & 1u;
-                                };
-                                uint32_t hits = bit(u0.x) | (bit(u0.y) << 1) | (bit(u0.z) << 2) | (bit(u0.w) << 3);
-                                if (c + 32 < body4)
-                                    hits |= (bit(u1.x) << 4) | (bit(u1.y) << 5) | (bit(u1.z) << 6) | (bit(u1.w) << 7);
-                                while (hits) {
-                                    const int b = __ffs(hits) - 1;
-                                    hits &= hits - 1;
-                                    const uint4 u = (b & 4) ? u1 : u0;
-                                    const uint32_t lo2 = (b & 1) ? u.y : u.x, hi2 = (b & 1) ? u.w : u.z;
-                                    const uint32_t post = (b & 2) ? hi2 : lo2;
-                                    const uint32_t d = post >> 16;
-                                    const uint32_t wd = bm[d >> 5];
-                                    float *slot = acc + (int)pre[d >> 5] + __popc(wd & ((1u << (d & 31)) - 1u));
-                                    *slot = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
-                                }
-                            }
-                            __syncwarp();
-                        }
-                        // ---- cold pair: before emitting, derive a threshold from this sub-range alone.  Every lane
-                        // takes the maximum of a strided subset of the marked docs' scores; the k-th largest of the 32
-                        // lane maxima is the score of k distinct docs' worth of evidence, i.e. a lower bound of the k-th
-                        // best approximate score overall -- publish it and emit only what clears it.
-                        if ((nsub > 1 || thr == 0.f) && p.k <= 32 && marked >= 2 * p.k) {
-                            float mx = 0.f;
-                            for (int r = lane; r < marked; r += 32) mx = fmaxf(mx, acc[r]);
-                            float kth = 0.f;
-                            for (int r = 0; r < p.k; ++r) {
-                                float m = mx;
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
-                                kth = m;
-                                const unsigned who = __ballot_sync(FULL, mx == m);
-                                if (lane == __ffs(who) - 1) mx = -1.f;
-                            }
-                            if (kth > 0.f) {
-                                const unsigned long long kb = (unsigned long long)__double_as_longlong((double)kth);
-                                if (lane == 0) atomicMax(p.thr_bits + q, kb);
-                                thr = fmaxf(thr, thr_to_float(kb));
+                                // docs are distinct inside a run (a padding posting repeats the last doc with impact 0,
+                                // in the same lane): plain read-modify-write
+                                float *slot = acc + (int)pre[d >> 5] + __popc(wd & ((1u << (d & 31)) - 1u));
+                                const float nv = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
+                                *slot = nv;
+                                hmax = fmaxf(hmax, nv);
                             }
                         }
-                        // ---- X: claim by RANK (lane-balanced, conflict-free): read and reset acc[r]; only the rare
-                        // score that clears the threshold needs its doc id -- the word whose rank range holds r
-                        // (binary search in the prefix counts), then the (r - pre[word])-th set bit of that word
+                        __syncwarp();
+                        mx = fmaxf(mx, warp_max_nonneg(hmax));
+                    }
+                    // ---- cold pair: before emitting, derive a threshold from this sub-range alone.  Every lane takes
+                    // the maximum of a strided subset of the marked docs' scores; the k-th largest of the 32 lane maxima
+                    // is the score of k distinct docs' worth of evidence, i.e. a lower bound of the k-th best
+                    // approximate score overall -- publish it and emit only what clears it.
+                    if (reachable && (nsub > 1 || thr == 0.f) && k <= 32 && marked >= 2 * k) {
+                        float lm = 0.f;
+                        for (int r = lane; r < marked; r += 32) lm = fmaxf(lm, acc[r]);
+                        float kth = 0.f;
+                        for (int r = 0; r < k; ++r) {
+                            const float m = warp_max_nonneg(fmaxf(lm, 0.f));
+                            kth = m;
+                            const unsigned who = __ballot_sync(FULL, lm == m);
+                            if (lane == __ffs(who) - 1) lm = -1.f;
+                        }
+                        if (kth > 0.f) {
+                            const unsigned long long kb = (unsigned long long)__double_as_longlong((double)kth);
+                            if (lane == 0) atomicMax(p.thr_bits + q, kb);
+                            thr = fmaxf(thr, thr_to_float(kb));
+                        }
+                    }
+                    // ---- X: only when something can clear the threshold, claim by RANK (lane-balanced, conflict-free):
+                    // read and reset acc[r]; the rare score that clears the threshold needs its doc id -- the word whose
+                    // rank range holds r (binary search in the prefix counts), then the (r - pre[word])-th set bit
+                    if (reachable && mx >= thr) {
                         for (int r = lane; r < marked; r += 32) {
                             const float v = acc[r];
                             acc[r] = 0.f;
-                            if (reachable && v >= thr) {
+                            if (v >= thr) {
                                 int lo = 0, hi = words - 1;  // last word with pre[word] <= r
                                 while (lo < hi) {
                                     const int mid = (lo + hi + 1) >> 1;
@@ -564,14 +566,13 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                                 ms_emit(p, q, (int32_t)(base_doc + lo * 32 + b), v);
                             }
                         }
-                        __syncwarp();
-                        for (int i = lane; i < words; i += 32) bm[i] = 0u;
                     } else {
-                        // a skewed sub-range marked more docs than the accumulator holds: the caller re-runs the query
-                        if (p.status && lane == 0) atomicOr(p.status + q, ORAG_STATUS_OVERFLOW);
-                        for (int i = lane; i < words; i += 32) bm[i] = 0u;
+                        for (int r = lane; r < marked; r += 32) acc[r] = 0.f;
                     }
-#undef MS_VIEW
+                    __syncwarp();
+                    if (wpl4) reinterpret_cast<uint4 *>(bm)[lane] = make_uint4(0u, 0u, 0u, 0u);
+                    else
+                        for (int i = lane; i < words; i += 32) bm[i] = 0u;
                     __syncwarp();
                 }
             }
@@ -656,10 +657,10 @@ __global__ void ms_init_state_kernel(unsigned long long *thr_bits, uint32_t *cnt
         cnt[i] = 0;
         topbin[i] = 0;
     }
-    if (i == 0) work[0] = work[1] = 0;
+    if (i == 0) work[0] = 0;
 }
 
-static int ms_cap(int n_queries)
+static int ms_cand_cap(int n_queries)
 {
     // ~128 MiB of candidate storage shared by the batch, at least 8192 slots per query
     int64_t cap = ((int64_t)128 << 20) / 8 / (n_queries > 0 ? n_queries : 1);
@@ -670,10 +671,12 @@ static int ms_cap(int n_queries)
 
 bool ms_eligible(const orag_bm25_index_t *ix, int max_terms, int flags)
 {
+    // (reserved & 1): the first-pass runs are 16-byte aligned and padded to four postings (bm25_build.cu layout)
     return ix->d_postings_r16 != nullptr && ix->d_term_max_r != nullptr && ix->d_fp_tile_base != nullptr &&
-           ix->d_fp_tile_term_off != nullptr && !ix->has_negative_idf && max_terms <= kMsTerms &&
+           ix->d_fp_tile_term_off != nullptr && (ix->reserved & 1) && !ix->has_negative_idf && max_terms <= kMsTerms &&
            !(flags & (ORAG_BM25_EXACT_TILES | ORAG_BM25_FORCE_DENSE)) && ix->fp_tile_docs >= 32 &&
-           ix->fp_tile_docs <= kMsMaxTile && (ix->fp_tile_docs & (ix->fp_tile_docs - 1)) == 0;
+           ix->fp_tile_docs <= kMsMaxTile && (ix->fp_tile_docs & (ix->fp_tile_docs - 1)) == 0 &&
+           (reinterpret_cast<uintptr_t>(ix->d_postings_r16) & 15) == 0;
 }
 
 struct MsCarve {
@@ -691,7 +694,7 @@ static MsCarve ms_carve(void *base, int n_queries)
         return r;
     };
     const size_t nq = (size_t)n_queries;
-    const int cap = ms_cap(n_queries);
+    const int cap = ms_cand_cap(n_queries);
     c.p.cap = cap;
     c.p.thr_bits = (unsigned long long *)take(nq * 8);
     c.p.cnt = (uint32_t *)take(nq * 4);
@@ -736,18 +739,15 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
     }
     if (ix->fp_n_tiles > 0) {
         const int words = (ix->fp_tile_docs + 31) / 32;
-        // Stand-alone: 2 CTAs x 16 warps per SM (64 registers per thread; 32 resident warps hide the shared-memory and
-        // L2 latencies better than 24 warps at 80 registers: 1.56 -> 1.40 ms at 10M docs).  Background (ORAG_BM25_BACKGROUND): CTAs of 8 warps and < 31 KB of
-        // shared memory, so that ONE of them fits next to a resident CTA of the cosine scan (199.9 KB, 384 threads,
-        // 96 registers) -- the issue-bound BM25 pass then rides along the tensor-bound scan on the SM resources
-        // the scan leaves idle; at most two per SM once the scan has left, which keeps registers free for the
-        // small re-score / selection kernels of the cosine pipeline.
+        // Stand-alone: 2 CTAs x 16 warps per SM (64 registers per thread, 7 KiB of shared memory per warp).  Background
+        // (ORAG_BM25_BACKGROUND): CTAs of 8 warps and < 31 KB of shared memory, so that ONE of them fits next to a
+        // resident CTA of the cosine scan (199.9 KB, 384 threads, 96 registers) and rides along on the SM resources the
+        // tensor-bound scan leaves idle.
         const int warps = background ? kMsBgWarps : kMsWarps;
-        p.shape = background ? kMsBackground : kMsAlone;
-        const size_t smem = (size_t)warps * ms_smem_per_warp(words, p.shape);
+        p.warp_bytes = background ? kMsBgWarpBytes : kMsWarpBytes;
+        const size_t smem = (size_t)warps * p.warp_bytes;
         const int lim = sm_count() * 2;
         ORAG_CUDA_CHECK(cudaFuncSetAttribute(bm25_ms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uint32_t *work = p.work;
         profile_mark(1, 0, st);
         {
             const int tiles = ix->fp_n_tiles;
@@ -756,10 +756,8 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
             int64_t split = (want + tiles - 1) / tiles;
             if (split > n_queries) split = n_queries;
             if (split < 1) split = 1;
-            p.tile_begin = 0;
             p.q_split = (int)split;
             p.n_items = (int)((int64_t)tiles * split);
-            p.work = work;
             int grid = (p.n_items + warps - 1) / warps;
             if (grid > lim) grid = lim;
             bm25_ms_kernel<<<grid, warps * 32, smem, st>>>(p);

@@ -24,7 +24,7 @@ import torch
 import torch.distributed as dist
 
 from . import _ffi, engine
-from .bm25_index import Bm25Stats, local_stats
+from .bm25_index import Bm25Plan, Bm25Stats
 
 logger = logging.getLogger(__name__)
 
@@ -38,26 +38,54 @@ def shard_range(n_total: int, rank: int, world: int):
     return lo, hi
 
 
-def sharded_stats(doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, group=None) -> Bm25Stats:
-    """Global Bm25Stats from each rank's local docs (ranks hold consecutive doc ranges in rank order)."""
+def _coll_device(group, device):
+    """Tensors of a collective live where the backend wants them (NCCL: the GPU; gloo: the host)."""
+    return device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def token_position_base(n_local: int, total_local: int, group=None, device=None):
+    """(global position of this rank's first token, docs of all ranks, tokens of all ranks): ranks hold consecutive doc
+    ranges in rank order, so a term's first-seen position is comparable across shards."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
-        return local_stats(doc_off, tokens, vocab)
+        return 0, n_local, total_local
     rank = dist.get_rank(group)
-    dev = tokens.device
-    n_local = doc_off.numel() - 1
-    total_local = int(doc_off[-1].item()) if n_local > 0 else 0
+    dev = _coll_device(group, device)
     sizes = torch.zeros(world, 2, dtype=torch.int64, device=dev)
     mine = torch.tensor([n_local, total_local], dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(sizes.view(-1), mine, group=group)
-    token_base = int(sizes[:rank, 1].sum().item())
-    st = local_stats(doc_off, tokens, vocab, token_pos_base=token_base)
-    df = torch.from_numpy(st.df).to(dev)
-    first = torch.from_numpy(st.first_seen).to(dev)
+    sizes = sizes.cpu()
+    return int(sizes[:rank, 1].sum()), int(sizes[:, 0].sum()), int(sizes[:, 1].sum())
+
+
+def reduce_stats(local: Bm25Stats, n_total: int, total_len: int, group=None, device=None) -> Bm25Stats:
+    """Global Bm25Stats from every rank's local ones (df summed, first-seen positions -- already global -- min-ed)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    dev = _coll_device(group, device)
+    df = torch.from_numpy(np.ascontiguousarray(local.df)).to(dev)
+    first = torch.from_numpy(np.ascontiguousarray(local.first_seen)).to(dev)
     dist.all_reduce(df, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(first, op=dist.ReduceOp.MIN, group=group)
-    return Bm25Stats(int(sizes[:, 0].sum().item()), int(sizes[:, 1].sum().item()), df.cpu().numpy(),
-                     first.cpu().numpy())
+    return Bm25Stats(n_total, total_len, df.cpu().numpy(), first.cpu().numpy())
+
+
+def sharded_plan(doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, tile_docs: int = 1024,
+                 fp_tile_docs: int | None = None, group=None):
+    """(Bm25Plan of this rank's docs, GLOBAL Bm25Stats): the counting pass of the index build runs once per shard and
+    its by-products (df, first-seen positions) are all-reduced; `Bm25Index.from_plan(plan, stats, doc_id_base)` then
+    fills the shard's index with the global idf / avgdl."""
+    n_local = doc_off.numel() - 1
+    total_local = int(doc_off[-1].item()) if n_local > 0 else 0
+    base, n_total, total_len = token_position_base(n_local, total_local, group, tokens.device)
+    plan = Bm25Plan(doc_off, tokens, vocab, tile_docs, fp_tile_docs, token_pos_base=base)
+    return plan, reduce_stats(plan.local_stats, n_total, total_len, group, tokens.device)
+
+
+def sharded_stats(doc_off: torch.Tensor, tokens: torch.Tensor, vocab: int, group=None) -> Bm25Stats:
+    """Global statistics only (callers that go on to build the index should use `sharded_plan` and keep the plan)."""
+    return sharded_plan(doc_off, tokens, vocab, group=group)[1]
 
 
 def pack_local(cos_ids, cos_scores, bm_ids, bm_scores, bm_max, status):

@@ -18,7 +18,11 @@ V = 50000
 thr = syn.zipf_thresholds(V)
 doc_off, tokens = engine.gen_token_corpus(n, 0, syn.SEED_TOKENS, thr, V, 100, 300, device=dev)
 fp_tile = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else None
+import time
+torch.cuda.synchronize(); _t0 = time.perf_counter()
 ix = Bm25Index(doc_off, tokens, V, tile_docs=tile, fp_tile_docs=fp_tile)
+torch.cuda.synchronize()
+print(f"index build ({n} docs, {ix.n_postings} postings, fp view {ix.n_postings_fp} incl. padding): {time.perf_counter() - _t0:.3f} s", flush=True)
 del tokens
 qt, ql = syn.keyword_queries(B, V, thresholds=thr)
 qt_d, ql_d = torch.from_numpy(qt).to(dev), torch.from_numpy(ql).to(dev)

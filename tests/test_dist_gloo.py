@@ -14,6 +14,10 @@ import torch.multiprocessing as mp
 import oracle
 from optimized_rag_b200 import synthetic as syn
 
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+
 N, DIM, VOCAB, NQ, K = 600, 64, 300, 6, 10
 
 
@@ -30,12 +34,16 @@ def _worker(rank, world, port, out_q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from optimized_rag_b200.bm25_index import idf_table
-        from optimized_rag_b200.dist import BM25_GUARD, pack_local, shard_range, sharded_stats, unpack_gathered
+        from optimized_rag_b200.dist import (BM25_GUARD, pack_local, reduce_stats, shard_range, token_position_base,
+                                             unpack_gathered)
+        from test_host_logic import _numpy_stats
         thr = syn.zipf_thresholds(VOCAB)
         lo, hi = shard_range(N, rank, world)
         # --- global statistics from local shards
         off, tok = syn.token_corpus(syn.SEED_TOKENS, lo, hi - lo, VOCAB, 5, 40, thr)
-        st = sharded_stats(torch.from_numpy(off), torch.from_numpy(tok), VOCAB)
+        # (the per-shard counting pass is a CUDA kernel; numpy stands in for it here: the collective half is under test)
+        base, n_total, total_len = token_position_base(hi - lo, int(off[-1]))
+        st = reduce_stats(_numpy_stats(off, tok, VOCAB, pos_base=base), n_total, total_len)
         g_off, g_tok = syn.token_corpus(syn.SEED_TOKENS, 0, N, VOCAB, 5, 40, thr)
         orc = oracle.BM25Index(g_off, g_tok, VOCAB)
         idf, avg_idf, eps = idf_table(st)

@@ -74,111 +74,59 @@ def test_synthetic_generators_are_shard_consistent():
     assert ql.min() >= 3 and ql.max() <= 8 and ((q == -1).sum(axis=1) > 0).sum() > 0
 
 
-@pytest.mark.parametrize("n,vocab,lmin,lmax,tile", [(300, 200, 3, 40, 64), (1000, 5000, 20, 60, 256), (5, 8, 1, 6, 32)])
-def test_index_builder_layout_matches_oracle(built_lib, n, vocab, lmin, lmax, tile):
-    """The torch-built tiled index decodes to exactly the oracle's postings / idf / t4."""
-    from optimized_rag_b200.bm25_index import Bm25Index
-    thr = syn.zipf_thresholds(vocab)
-    doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, lmin, lmax, thr)
-    ix = Bm25Index(torch.from_numpy(doc_off), torch.from_numpy(tok), vocab, tile_docs=tile)
-    orc = oracle.BM25Index(doc_off, tok, vocab)
-    assert ix.avgdl == orc.avgdl and ix.average_idf == orc.average_idf and ix.eps == orc.eps
-    assert np.array_equal(ix.idf.numpy().view(np.uint64), orc.idf.view(np.uint64))
-    assert ix.has_negative_idf == bool((orc.idf < 0).any())
-    # t4 = k1 * (1 - b + b * dl / avgdl) in the oracle's operation order
-    dl = orc.dl.astype(np.float64)
-    assert np.array_equal(ix.doc_t4.numpy(), 1.5 * (0.25 + (0.75 * dl) / orc.avgdl))
-    off, pdoc, ptf = orc.postings()
-    post = ix.postings.numpy().view(np.uint32)
-    tbase = ix.tile_base.numpy()
-    toff = ix.tile_term_off.numpy()
-    assert ix.n_postings == len(pdoc)
-    for t in range(vocab):
-        docs, tfs = [], []
-        for tl in range(ix.n_tiles):
-            s, e = tbase[tl] + toff[tl, t], tbase[tl] + toff[tl, t + 1]
-            p = post[s:e]
-            docs.extend((tl * tile + (p >> 16)).tolist())
-            tfs.extend((p & 0xFFFF).tolist())
-        assert docs == pdoc[off[t]:off[t + 1]].tolist(), t
-        assert tfs == ptf[off[t]:off[t + 1]].tolist(), t
+def _numpy_stats(doc_off, tok, vocab, pos_base=0):
+    """Bm25Stats of a token corpus with plain numpy (what csrc/bm25_build.cu's counting pass produces on the GPU)."""
+    from optimized_rag_b200.bm25_index import Bm25Stats
+    n = len(doc_off) - 1
+    df = np.zeros(vocab, dtype=np.int64)
+    first = np.full(vocab, np.iinfo(np.int64).max, dtype=np.int64)
+    for d in range(n):
+        df[np.unique(tok[doc_off[d]:doc_off[d + 1]])] += 1
+    for pos in range(len(tok) - 1, -1, -1):
+        first[tok[pos]] = pos + pos_base
+    return Bm25Stats(n, int(doc_off[-1]), df, first)
 
 
 def test_sharded_stats_merge_equals_global(built_lib):
-    from optimized_rag_b200.bm25_index import idf_table, local_stats
+    """Host half of the multi-shard index build: per-shard (df, first-seen position) merge into the global statistics,
+    and `idf_table` turns those into the oracle's idf / epsilon bit for bit (dict-insertion order included)."""
+    from optimized_rag_b200.bm25_index import idf_table, t4_table
     vocab, n = 400, 900
     thr = syn.zipf_thresholds(vocab)
     doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, 5, 50, thr)
-    whole = local_stats(torch.from_numpy(doc_off), torch.from_numpy(tok), vocab)
+    whole = _numpy_stats(doc_off, tok, vocab)
     parts = None
     for s, e in [(0, 300), (300, 650), (650, 900)]:
-        off = doc_off[s:e + 1] - doc_off[s]
-        st = local_stats(torch.from_numpy(off), torch.from_numpy(tok[doc_off[s]:doc_off[e]]), vocab,
-                         token_pos_base=int(doc_off[s]))
+        st = _numpy_stats(doc_off[s:e + 1] - doc_off[s], tok[doc_off[s]:doc_off[e]], vocab, pos_base=int(doc_off[s]))
         parts = st if parts is None else parts.merged(st)
     assert parts.n_docs == whole.n_docs and parts.total_len == whole.total_len
     assert np.array_equal(parts.df, whole.df) and np.array_equal(parts.first_seen, whole.first_seen)
     a, b = idf_table(parts), idf_table(whole)
     assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
     orc = oracle.BM25Index(doc_off, tok, vocab)
-    assert np.array_equal(a[0].view(np.uint64), orc.idf.view(np.uint64))
+    assert np.array_equal(a[0].view(np.uint64), orc.idf.view(np.uint64)) and a[1] == orc.average_idf and a[2] == orc.eps
+    assert whole.avgdl == orc.avgdl
     order = np.argsort(whole.first_seen[whole.df > 0], kind="stable")
     assert np.array_equal(np.nonzero(whole.df > 0)[0][order], orc.first_seen)
+    # t4 = k1 * (1 - b + b * dl / avgdl) in the oracle's operation order
+    dl = orc.dl.astype(np.float64)
+    assert np.array_equal(t4_table(int(dl.max()), orc.avgdl)[orc.dl], 1.5 * (0.25 + (0.75 * dl) / orc.avgdl))
 
 
-@pytest.mark.parametrize("n,vocab,lmin,lmax,tile,fp_tile", [(700, 300, 3, 40, 64, 256), (90, 40, 1, 9, 32, 32),
-                                                            (1500, 2000, 20, 60, 128, None)])
-def test_first_pass_view_is_a_rounded_copy_of_the_exact_view(built_lib, n, vocab, lmin, lmax, tile, fp_tile):
-    """The MaxScore first-pass view (csrc/bm25_ms.cu) must hold, for exactly the postings of the exact view,
-    fp16(r) with r = tf*(k1+1)/(tf + t4[dl]) in float64, and term_max_r must bound every r16 of its term: the
-    superset guarantee of the first pass rests on |r16 - r| <= 2^-11 r and on those upper bounds."""
-    from optimized_rag_b200.bm25_index import Bm25Index
-    thr = syn.zipf_thresholds(vocab)
-    doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, lmin, lmax, thr)
-    ix = Bm25Index(torch.from_numpy(doc_off), torch.from_numpy(tok), vocab, tile_docs=tile, fp_tile_docs=fp_tile)
-    assert ix.postings_r16 is not None and not ix.has_negative_idf
-    T, F = ix.tile_docs, ix.fp_tile_docs
-    if fp_tile is None:
-        assert F == min(4096, max(32, 1 << ((n // 16 - 1).bit_length())))
-
-    def decode(post, base, off, tile_docs, n_tiles):
-        post = post.numpy().view(np.uint32)
-        base, off = base.numpy(), off.numpy()
-        out = {}
-        for tl in range(n_tiles):
-            for t in range(vocab):
-                p = post[base[tl] + off[tl, t]:base[tl] + off[tl, t + 1]]
-                d = tl * tile_docs + (p >> 16).astype(np.int64)
-                assert (np.diff(d) > 0).all()  # doc-sorted runs: the kernels binary-search and merge them
-                for di, lo in zip(d.tolist(), (p & 0xFFFF).tolist()):
-                    out[(t, di)] = lo
-        return out
-
-    exact = decode(ix.postings, ix.tile_base, ix.tile_term_off, T, ix.n_tiles)
-    first = decode(ix.postings_r16, ix.fp_tile_base, ix.fp_tile_term_off, F, ix.fp_n_tiles)
-    assert exact.keys() == first.keys() and len(exact) == ix.n_postings
-    t4 = ix.t4_table.numpy()
-    dl = ix.dl.numpy()
-    tmax = np.zeros(vocab, dtype=np.float32)
-    for (t, d), tf in exact.items():
-        r = tf * 2.5 / (tf + t4[dl[d]])
-        r16 = np.float16(np.float32(r))
-        assert first[(t, d)] == int(r16.view(np.uint16)), (t, d)
-        assert abs(float(r16) - r) <= r * 2.0 ** -11 and float(r16) >= 6.2e-5
-        tmax[t] = max(tmax[t], np.float32(r16))
-    assert np.array_equal(ix.term_max_r.numpy(), tmax)
-
-
-def test_first_pass_view_is_dropped_when_idf_goes_negative(built_lib):
-    """When the final idf table keeps a negative entry (common terms whose replacement eps*average_idf is itself
-    negative, rank_bm25's behaviour), pruning by upper bounds is unsound: the index must not build the first-pass
-    view, and the exact tile kernel serves every query."""
-    from optimized_rag_b200.bm25_index import Bm25Index
-    doc_off = np.arange(0, 4 * 40 + 1, 4, dtype=np.int64)
-    tok = np.tile(np.array([0, 1, 2, 3], dtype=np.int32), 40)
-    tok[3::8] = 5
-    ix = Bm25Index(torch.from_numpy(doc_off), torch.from_numpy(tok), 8, tile_docs=32)
-    assert ix.has_negative_idf and ix.postings_r16 is None and ix.struct.d_postings_r16 is None
+def test_index_build_refuses_host_tensors(built_lib):
+    """The tiled index is built by the library's CUDA builder only (csrc/bm25_build.cu): no CPU / torch stand-in."""
+    from optimized_rag_b200 import _ffi
+    from optimized_rag_b200.bm25_index import Bm25Index, default_fp_tile_docs
+    doc_off = torch.tensor([0, 2, 5], dtype=torch.int64)
+    tok = torch.tensor([0, 1, 1, 2, 3], dtype=torch.int32)
+    with pytest.raises(_ffi.OragError, match="no CPU builder"):
+        Bm25Index(doc_off, tok, 8, tile_docs=32)
+    assert default_fp_tile_docs(10_000_000) == 4096 and default_fp_tile_docs(700) == 64 and default_fp_tile_docs(0) == 32
+    L = _ffi.lib()
+    assert L.orag_bm25_build_workspace_bytes(1000, 50, 64, 256) > 0
+    assert L.orag_bm25_build_workspace_bytes(1000, 50, 48, 256) == 0       # tile sizes are powers of two
+    assert L.orag_bm25_index_plan(None, None, 10, 50, 64, 256, 0, None, None, None, None, None, None, None, None, None,
+                                  0, None, None) == -1
 
 
 def test_semantic_dedup_host_logic_with_a_stand_in_cosine_matrix(built_lib, monkeypatch):
@@ -203,48 +151,6 @@ def test_semantic_dedup_host_logic_with_a_stand_in_cosine_matrix(built_lib, monk
     assert data_wrangler.Deduplicator.semantic_dedup([], [], 0.95, device="cpu") == []
     one = [{"content": "a"}, {"content": "b"}]
     assert data_wrangler.Deduplicator.semantic_dedup(one, [[1.0, 0.0]], 0.95, device="cpu") == one[:1]   # zip semantics
-
-
-@pytest.mark.parametrize("n,vocab,tile,negative", [(700, 300, 64, False), (40, 8, 32, True), (0, 5, 32, False)])
-def test_bm25_index_save_load_round_trip(built_lib, tmp_path, n, vocab, tile, negative):
-    """On-disk format of the keyword index: every array and scalar survives save -> load bit for
-    bit, and the struct handed to the kernels is field-for-field the one the builder makes (pointers aside)."""
-    from optimized_rag_b200 import _ffi
-    from optimized_rag_b200.bm25_index import Bm25Index
-    if negative:
-        doc_off = np.arange(0, 4 * n + 1, 4, dtype=np.int64)
-        tok = np.tile(np.array([0, 1, 2, 3], dtype=np.int32), n)
-        tok[3::8] = 5
-    else:
-        thr = syn.zipf_thresholds(vocab)
-        doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, 3, 40, thr)
-    ix = Bm25Index(torch.from_numpy(doc_off), torch.from_numpy(tok), vocab, tile_docs=tile, doc_id_base=1234)
-    assert ix.has_negative_idf == negative and (ix.postings_r16 is None) == (negative or n == 0)
-    ix.save(tmp_path / "kw")
-    assert (tmp_path / "kw.bin").stat().st_size % 1 == 0 and (tmp_path / "kw.json").exists()
-    back = Bm25Index.load(tmp_path / "kw", device="cpu")
-    for name in Bm25Index._ARRAYS:
-        a, b = getattr(ix, name), getattr(back, name)
-        assert (a is None) == (b is None), name
-        if a is not None:
-            assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b), name
-    for key in ("n_docs", "vocab", "tile_docs", "n_tiles", "fp_tile_docs", "fp_n_tiles", "doc_id_base", "n_postings",
-                "max_dl", "has_negative_idf", "avgdl", "average_idf", "eps"):
-        assert getattr(ix, key) == getattr(back, key), key
-    assert back.stats.n_docs == ix.stats.n_docs and back.stats.total_len == ix.stats.total_len
-    assert np.array_equal(back.stats.df, ix.stats.df) and np.array_equal(back.stats.first_seen, ix.stats.first_seen)
-    for field, ctype in _ffi.Bm25IndexStruct._fields_:
-        va, vb = getattr(ix.struct, field), getattr(back.struct, field)
-        if field.startswith("d_"):
-            assert (va is None) == (vb is None), field   # same arrays present, each pointing at its own copy
-        else:
-            assert va == vb, field
-    # a damaged file is refused
-    data = (tmp_path / "kw.bin").read_bytes()
-    if len(data) > 16:
-        (tmp_path / "kw.bin").write_bytes(data[:-8])
-        with pytest.raises(ValueError):
-            Bm25Index.load(tmp_path / "kw", device="cpu")
 
 
 class _OracleCosineIndex:
