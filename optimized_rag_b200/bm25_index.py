@@ -87,9 +87,10 @@ def t4_table(max_dl: int, avgdl: float) -> np.ndarray:
 
 
 def default_fp_tile_docs(n_docs: int) -> int:
-    # measured on B200 (scripts/debug_bm25.py): 4096..8192-doc tiles are within 5 % of each other stand-alone;
-    # 4096 keeps the per-warp bitmap small enough for the background configuration (csrc/bm25_ms.cu)
-    return min(4096, max(32, 1 << max(0, (max(n_docs, 1) // 16 - 1).bit_length())))
+    # measured on B200 (scripts/debug_bm25.py, 10M docs x 256 queries): 4096-doc tiles 1.27 ms, 8192 0.93 ms, 16384
+    # 1.34 ms (the per-(query, tile) fixed cost halves with every doubling until the docs a pair marks outgrow the
+    # per-warp accumulator); small corpora keep >= 16 tiles for the work hand-out
+    return min(8192, max(32, 1 << max(0, (max(n_docs, 1) // 16 - 1).bit_length())))
 
 
 class Bm25Plan:

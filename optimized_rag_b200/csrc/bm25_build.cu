@@ -393,10 +393,9 @@ extern "C" int orag_bm25_index_plan(const int64_t *d_doc_off, const int32_t *d_t
     Geometry g;
     int rc = geometry(n_docs, vocab, tile_docs, fp_tile_docs, &g);
     if (rc) return rc;
-    ORAG_REQUIRE(d_doc_off && d_doc_len && d_df && d_first_pos && d_tile_base && d_tile_term_off && d_fp_tile_base &&
-                     d_fp_tile_term_off && d_info && h_totals,
+    ORAG_REQUIRE(d_doc_off && d_df && d_first_pos && d_tile_base && d_fp_tile_base && d_info && h_totals,
                  "bm25_index_plan pointers");
-    ORAG_REQUIRE(n_docs == 0 || d_tokens, "tokens");
+    ORAG_REQUIRE(n_docs == 0 || (d_tokens && d_doc_len && d_tile_term_off && d_fp_tile_term_off), "per-document arrays");
     if (!d_workspace || workspace_bytes < carve(nullptr, g).bytes) {
         set_error("bm25_index_plan: workspace too small");
         return ORAG_EWORKSPACE;
@@ -447,9 +446,9 @@ extern "C" int orag_bm25_index_fill(const int64_t *d_doc_off, const int32_t *d_t
     Geometry g;
     int rc = geometry(n_docs, vocab, tile_docs, fp_tile_docs, &g);
     if (rc) return rc;
-    ORAG_REQUIRE(d_doc_off && d_t4_table && d_tile_base && d_tile_term_off && d_postings && d_fp_tile_base &&
-                     d_fp_tile_term_off && d_info && max_doc_len >= 0,
+    ORAG_REQUIRE(d_doc_off && d_t4_table && d_tile_base && d_postings && d_fp_tile_base && d_info && max_doc_len >= 0,
                  "bm25_index_fill pointers");
+    ORAG_REQUIRE(n_docs == 0 || (d_tokens && d_tile_term_off && d_fp_tile_term_off), "per-document arrays");
     ORAG_REQUIRE(!d_postings_r16 || d_term_max_r, "term_max_r goes with the first-pass view");
     ORAG_REQUIRE(!d_postings_r16 || (reinterpret_cast<uintptr_t>(d_postings_r16) & 15) == 0, "postings_r16 16-byte aligned");
     if (!d_workspace || workspace_bytes < carve(nullptr, g).bytes) {

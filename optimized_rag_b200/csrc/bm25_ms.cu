@@ -3,42 +3,42 @@
 // Same result as bm25.cu (bit-exact float64 scores of rank_bm25.BM25Okapi.get_scores + the glue at
 // rag/retrieval.py:324-347) at a fraction of the instructions per posting.
 //
-// First-pass view (built by bm25_build.cu).  A second tiling of the postings (4096-doc tiles by default, up to
+// First-pass view (built by bm25_build.cu).  A second tiling of the postings (8192-doc tiles by default, up to
 // 16384): (doc_in_tile << 16) | fp16(r), r = tf*(k1+1)/(tf + t4[dl]) rounded to nearest, so a posting's
 // contribution is one fp32 multiply w*r (w = fp32 idf, duplicates of a query term merged into one weight) and needs
 // no document-length or table lookup.  Every (tile, term) run starts on a 16-byte boundary and is padded to a
-// multiple of four postings with copies of its last doc carrying impact 0, so runs are only ever moved as uint4.
-// Every approximate score s~ satisfies |s~ - s| <= eps*s with eps = 2^-11 (fp16 r) + (n_terms + 2) * 2^-24 (fp32
-// weight, products, sums in any order) < 5e-4: all terms are positive.
+// multiple of four postings with copies of its last doc carrying impact 0, so the long runs are only ever moved as
+// uint4.  Every approximate score s~ satisfies |s~ - s| <= eps*s with eps = 2^-11 (fp16 r) + (n_terms + 2) * 2^-24
+// (fp32 weight, products, sums) < 5e-4: all terms are positive.
 //
 // MaxScore.  prepare_queries_kernel sorts a query's terms by ascending upper bound ub_t = w_t * max_r(t) (max over
 // the shard's postings of t) and stores the inclusive prefix sums.  With the query's running threshold thr (a lower
 // bound of the k-th best s~ seen so far, from the same log-scale histogram bm25.cu uses) the terms whose prefix sum
 // stays below thr' = thr * (1 - 2^-9) are "non-essential": a document that contains only those cannot reach thr'.
-// Any SUPERSET of the essential terms is just as valid, so the partition taken when a pair's postings are staged (one
-// pair ahead, with the threshold of that moment -- thresholds only rise) is the partition the pair is processed with.
 //
-// One warp works on one (query, tile) pair at a time with four small shared-memory structures: a staging buffer that
-// holds the postings of ALL essential runs of the pair back to back (16-byte cp.async, issued while the previous pair
-// is being finished), a bitmap of the tile's docs, per-word prefix popcounts, and a compact fp32 accumulator indexed
-// by a doc's RANK among the marked docs (sized by the docs a query touches, not by the tile):
-//   E1  one flat loop over the staged postings marks their docs in the bitmap
+// One warp works on one (query, tile) pair at a time with three small shared-memory structures -- a bitmap of the
+// tile's docs, per-word prefix popcounts, and a compact fp32 accumulator indexed by a doc's RANK among the marked docs
+// (sized by the docs a query touches, not by the tile) -- and reads the postings straight from L2, where a prefetch
+// issued one pair ahead has put them (the whole run of a term that is essential by the threshold of that moment, the
+// first 512 bytes of the others):
+//   E1  mark the docs of the essential runs in the bitmap (shared-memory atomicOr)
 //   R   prefix popcounts -> rank(d)
-//   E2  one flat loop adds w_run * r into acc[rank(d)] (the run of a staged posting comes from a tiny table of run
-//       ends; two runs may hold the same doc, hence shared-memory atomic adds -- the order of fp32 additions is
-//       covered by eps)
-//   N   the non-essential runs are streamed from global memory with 16-byte loads (two in flight per lane), most
-//       valuable term first; a posting only matters when its doc is marked (one shared-memory word test), in which
-//       case its contribution completes acc[rank(d)].  Before every run: if the best partial score (kept up to date
-//       with one warp-wide REDUX per run) plus the upper bounds of the remaining terms stays below thr', nothing of
-//       this pair can be emitted and the remaining (longest) runs are not read at all
+//   E2  add the essential contributions w * r into acc[rank(d)], run by run (docs are distinct inside a run, so plain
+//       read-modify-writes suffice), tracking the best partial score
+//   N   the non-essential runs are streamed with 16-byte loads (two in flight per lane), most valuable term first; a
+//       posting only matters when its doc is marked (one shared-memory word test), in which case its contribution
+//       completes acc[rank(d)].  Before every run: if the best partial score (kept up to date with one warp-wide
+//       REDUX per run) plus the upper bounds of the remaining terms stays below thr', nothing of this pair can be
+//       emitted and the remaining (longest) runs are not read at all
 //   X   only if the best score reaches thr': lanes walk the RANKS, and a score that clears thr' gets its doc id back
 //       from the prefix counts (binary search + find-n-th-set-bit) and is emitted.  Otherwise acc is just zeroed.
-// A pair whose essential postings do not fit the staging buffer (cold start: thr = 0 makes every term essential; or a
-// very dense query) takes the same steps in doc sub-ranges: runs are doc-sorted, so a sub-range is a contiguous slice
-// of every run (one binary search per run and boundary); the threshold is re-read between sub-ranges, and before a
-// cold sub-range emits anything it derives a LOCAL threshold -- the k-th largest of the 32 lane maxima of its own
-// scores, a valid lower bound of the global k-th best -- and publishes it.
+// A pair whose essential postings outnumber the accumulator slots (cold start: thr = 0 makes every term essential;
+// or a very dense query) takes the same steps in doc sub-ranges: runs are doc-sorted, so a sub-range is a contiguous
+// slice of every run (one binary search per run and boundary); the threshold is re-read between sub-ranges, and
+// before a cold sub-range emits anything it derives a LOCAL threshold -- the k-th largest of the 32 lane maxima of
+// its own scores, a valid lower bound of the global k-th best -- and publishes it.
+// (An earlier build staged the essential runs in shared memory with cp.async; dropping that buffer doubled the
+// accumulator, which is what lets the tiles grow to 8192 docs: 1.20 -> 0.93 ms at 10M docs x 256 queries.)
 //
 // Superset argument (as for the cosine first pass): let S_k be the true k-th best score and S~_k the k-th best
 // approximate score.  At most k-1 docs have s > S_k, so S~_k <= S_k (1 + eps); thr <= S~_k always.  A true top-k doc
@@ -67,13 +67,12 @@ constexpr int kMsSurvCap = 2048;  // candidates re-scored per query
 constexpr int kMsContrib = 4096;  // (survivor, token) contributions staged in shared memory by ms_finalize_kernel
 constexpr float kMsGuard = 1.0f - 1.0f / 512.0f;
 
-// per-warp shared memory: staging buffer [cap] | compact accumulator [cap] | bitmap [words] | per-word ranks [words]
-// | run table (ends [32], weights [32]).  cap = postings of the essential runs of one pair (or sub-range) = upper
-// bound of the docs it can mark; a multiple of 4.
+// per-warp shared memory: compact accumulator [cap] | bitmap [words] | per-word ranks [words].  cap = docs one
+// (query, tile sub-range) may mark; a multiple of 4.
 __host__ __device__ inline int ms_cap(int words, int warp_bytes)
 {
-    const int left = warp_bytes - words * 6 - 260;  // run table (256 B) + alignment slack
-    return left < 64 ? 0 : (left / 8) & ~3;
+    const int left = warp_bytes - words * 6;
+    return left < 256 ? 0 : (left / 4) & ~3;
 }
 
 struct MsParams {
@@ -176,11 +175,6 @@ __device__ __forceinline__ float post_r(uint32_t post)
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void *gmem_src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
-}
-
 // warp-wide maximum of non-negative floats: their bit patterns order like unsigned integers -> one REDUX
 __device__ __forceinline__ float warp_max_nonneg(float v)
 {
@@ -196,9 +190,6 @@ struct MsRun {   // lane i = i-th term's run in the current tile, in units of fo
     int rel4, len4;
     float w, pre;
     int n, q;
-    int soff4;   // essential lanes: position of the run in the staging buffer
-    int n_ne;    // warp-uniform: number of non-essential terms (a prefix of the lanes) as decided at staging time
-    int e4;      // warp-uniform: staged uint4s in total, or -1 when the pair does not fit (sub-range path)
 };
 
 __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_constant__ MsParams p)
@@ -209,13 +200,9 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int cap = ms_cap(words, p.warp_bytes);
     uint8_t *mine = reinterpret_cast<uint8_t *>(ms_smem) + (size_t)wib * p.warp_bytes;
-    uint32_t *stage = reinterpret_cast<uint32_t *>(mine);                      // [cap] essential postings, back to back
-    float *acc = reinterpret_cast<float *>(mine + (size_t)cap * 4);            // [cap], zero between pairs
-    uint32_t *bm = reinterpret_cast<uint32_t *>(mine + (size_t)cap * 8);       // [words] marked docs, zero between pairs
+    float *acc = reinterpret_cast<float *>(mine);                              // [cap], zero between pairs
+    uint32_t *bm = reinterpret_cast<uint32_t *>(mine + (size_t)cap * 4);       // [words] marked docs, zero between pairs
     uint16_t *pre = reinterpret_cast<uint16_t *>(bm + words);                  // [words] rank of a word's bit 0
-    int *rend = reinterpret_cast<int *>(mine + (((size_t)cap * 8 + (size_t)words * 6 + 3) & ~(size_t)3));  // [32] run ends
-    float *rw = reinterpret_cast<float *>(rend + 32);                          // [32] run weights
-    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
     for (int i = lane; i < words; i += 32) bm[i] = 0u;
     for (int i = lane; i < cap; i += 32) acc[i] = 0.f;
     __syncwarp();
@@ -223,12 +210,17 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
     const int V1 = p.ix.vocab + 1;
     const int nq = p.n_queries;
     const unsigned FULL = 0xffffffffu;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int S = p.q_split;
     const int4 *qd = reinterpret_cast<const int4 *>(p.qd);
     const int wpl = (words + 31) >> 5;  // bitmap words per lane in the rank pass
-    const bool wpl4 = words == 128;     // (bm and pre are 16-byte aligned: cap is a multiple of 4)
+    const bool wpl4 = words == 128;     // 4096-doc tiles (bm and pre are 16-byte aligned: cap is a multiple of 4)
+    const bool wpl8 = words == 256;     // 8192-doc tiles
     const int k = p.k;
+
+    auto rank_of = [&](uint32_t d) -> int {
+        const uint32_t wd = bm[d >> 5];
+        return (int)pre[d >> 5] + __popc(wd & ((1u << (d & 31)) - 1u));
+    };
 
     for (;;) {
         int item = 0;
@@ -262,99 +254,59 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
             }
             return d;
         };
-        // ---- stage B: run offsets inside this tile, L2 prefetch of the head of every run
+        // ---- stage B: run offsets inside this tile; L2 prefetch of the runs one pair ahead: the head (512 bytes) of
+        // every run, and all of a run (up to 4 KiB) whose term is essential by the threshold as of now
         auto stage_run = [&](const MsDesc &d) -> MsRun {
             MsRun r;
-            r.rel4 = 0; r.len4 = 0; r.w = d.w; r.pre = d.pre; r.n = d.n; r.q = d.q; r.soff4 = 0; r.n_ne = 0; r.e4 = 0;
+            r.rel4 = 0; r.len4 = 0; r.w = d.w; r.pre = d.pre; r.n = d.n; r.q = d.q;
             if (lane < d.n) {
                 const int o0 = __ldg(toff + d.term), o1 = __ldg(toff + d.term + 1);
                 r.rel4 = o0 >> 2;
                 r.len4 = (o1 - o0) >> 2;
                 if (r.len4 > 0) {
-                    prefetch_l2(tp4 + r.rel4);
-                    if (r.len4 > 8) prefetch_l2(tp4 + r.rel4 + 8);
-                    if (r.len4 > 16) prefetch_l2(tp4 + r.rel4 + 16);
-                    if (r.len4 > 24) prefetch_l2(tp4 + r.rel4 + 24);
+                    const float thr_now = thr_to_float(__ldcg(p.thr_bits + d.q));
+                    const int lines = !(d.pre < thr_now) ? min((r.len4 + 7) >> 3, 32) : min((r.len4 + 7) >> 3, 4);
+                    for (int l = 0; l < lines; ++l) prefetch_l2(tp4 + r.rel4 + 8 * l);
                 }
             }
             return r;
         };
-        // ---- stage C: partition by the threshold as of now; copy the essential runs, back to back, into the staging
-        // buffer (the buffer must be free: called after E2 of the pair in front)
-        auto stage_posts = [&](MsRun &run) {
-            float thr_now = 0.f;
-            if (run.n > 0) thr_now = thr_to_float(__ldcg(p.thr_bits + run.q));
-            run.n_ne = __popc(__ballot_sync(FULL, lane < run.n && run.pre < thr_now));  // a prefix of the lanes
-            const bool want = lane < run.n && lane >= run.n_ne && run.len4 > 0;
-            const int alen = want ? run.len4 : 0;
-            int incl = alen;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, d);
-                if (lane >= d) incl += v;
-            }
-            run.soff4 = incl - alen;
-            const int e4 = __shfl_sync(FULL, incl, 31);
-            run.e4 = (e4 * 4 <= cap) ? e4 : -1;
-            if (run.e4 > 0) {
-                for (unsigned a = __ballot_sync(FULL, want); a; a &= a - 1) {
-                    const int i = __ffs(a) - 1;
-                    const int cnt = __shfl_sync(FULL, alen, i);
-                    const uint32_t dst = stage_s + 16u * (uint32_t)__shfl_sync(FULL, run.soff4, i);
-                    const uint4 *src = tp4 + __shfl_sync(FULL, run.rel4, i);
-#pragma unroll 1
-                    for (int c = lane; c < cnt; c += 32) cp_async16_s(dst + 16u * c, src + c);
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
 
         MsRun cur = stage_run(stage_desc(qi0));
-        stage_posts(cur);
         MsRun nxt = stage_run(stage_desc(qi0 + 1));
         MsDesc descA = stage_desc(qi0 + 2);
 
         for (int qi = qi0; qi < qi1; ++qi) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
             const int n = cur.n;  // warp-uniform
             const int q = cur.q;
-            bool staged_next = false;
             const bool mine_ok = lane < n && cur.len4 > 0;
-            int n_ne = cur.n_ne;
+            float thr = 0.f;
+            if (n > 0) thr = thr_to_float(__ldcg(p.thr_bits + q));
+            int n_ne = __popc(__ballot_sync(FULL, lane < n && cur.pre < thr));  // a prefix of the lanes
             unsigned ess = __ballot_sync(FULL, mine_ok && lane >= n_ne);
             if (ess) {
-                float thr = thr_to_float(__ldcg(p.thr_bits + q));
-                const bool fast = cur.e4 > 0;
-                // sub-ranges (slow path only): marked docs per sub-range must fit the compact accumulator
+                // essential postings of the pair; more than the accumulator holds -> doc sub-ranges
+                const int etot = __reduce_add_sync(FULL, (mine_ok && lane >= n_ne) ? cur.len4 * 4 : 0);
                 int nsub = 1, sub_docs = T;
-                if (!fast) {
-                    int etot = (mine_ok && lane >= n_ne) ? cur.len4 * 4 : 0;
-                    etot = __reduce_add_sync(FULL, etot);
-                    while (nsub * (cap >> 1) < etot && sub_docs > 32) {
-                        nsub <<= 1;
-                        sub_docs >>= 1;
-                    }
+                while (nsub * (etot > cap ? (cap >> 1) : cap) < etot && sub_docs > 32) {
+                    nsub <<= 1;
+                    sub_docs >>= 1;
                 }
-                int cpos = 0;  // slow path: this lane's run, first posting of the current sub-range
+                int cpos = 0;  // this lane's run: first posting of the current sub-range
                 for (int sub = 0; sub < nsub; ++sub) {
-                    int E;              // staged postings of this (sub-)range
-                    int n4_lo, n4_cnt;  // this lane's run: uint4 slice the N phase streams
-                    if (fast) {
-                        E = cur.e4 * 4;
+                    int v_rel, v_len;   // this lane's run in the (sub-)range: posting slice relative to tp
+                    int n4_lo, n4_cnt;  // ... and the 16-byte aligned superset of it the N phase streams
+                    if (nsub == 1) {
+                        v_rel = cur.rel4 * 4;
+                        v_len = mine_ok ? cur.len4 * 4 : 0;
                         n4_lo = cur.rel4;
                         n4_cnt = cur.len4;
-                        if (mine_ok && lane >= n_ne) {
-                            const int r = __popc(ess & lt_mask);
-                            rend[r] = (cur.soff4 + cur.len4) * 4;
-                            rw[r] = cur.w;
-                        }
                     } else {
                         if (sub > 0) {
                             // a pair that needs several sub-ranges is a cold one: its own emissions have raised the
                             // threshold since, so re-read it and re-partition (fewer essential runs, fewer emissions)
                             thr = thr_to_float(__ldcg(p.thr_bits + q));
-                            n_ne = max(n_ne, __popc(__ballot_sync(FULL, lane < n && cur.pre < thr)));
+                            n_ne = __popc(__ballot_sync(FULL, lane < n && cur.pre < thr));
                             ess = __ballot_sync(FULL, mine_ok && lane >= n_ne);
                             if (!ess) break;  // nothing left in this tile can reach the threshold
                         }
@@ -370,59 +322,38 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                             }
                             s_end = lo;
                         }
-                        const int v_len = mine_ok ? s_end - cpos : 0;
-                        // non-essential lanes stream the 16-byte aligned superset of their slice (postings outside the
-                        // sub-range belong to unmarked docs)
+                        v_rel = cur.rel4 * 4 + cpos;
+                        v_len = mine_ok ? s_end - cpos : 0;
                         n4_lo = cur.rel4 + (cpos >> 2);
                         n4_cnt = v_len > 0 ? ((s_end + 3) >> 2) - (cpos >> 2) : 0;
-                        // essential slices: copied back to back into the staging buffer
-                        const bool is_ess = mine_ok && lane >= n_ne;
-                        const int alen = is_ess ? v_len : 0;
-                        int incl = alen;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const int v = __shfl_up_sync(FULL, incl, d);
-                            if (lane >= d) incl += v;
-                        }
-                        E = __shfl_sync(FULL, incl, 31);
-                        const int soff = incl - alen;
-                        const int src0 = cur.rel4 * 4 + cpos;
                         cpos = s_end;
-                        if (E > cap) {
-                            // a skewed sub-range holds more essential postings than the buffer: the caller re-runs the query
-                            if (p.status && lane == 0) atomicOr(p.status + q, ORAG_STATUS_OVERFLOW);
-                            continue;
-                        }
-                        if (is_ess) {
-                            const int r = __popc(ess & lt_mask);
-                            rend[r] = soff + alen;
-                            rw[r] = cur.w;
-                        }
-                        for (unsigned a = ess; a; a &= a - 1) {
-                            const int i = __ffs(a) - 1;
-                            const int cnt = __shfl_sync(FULL, alen, i);
-                            const int dst = __shfl_sync(FULL, soff, i);
-                            const uint32_t *src = tp + __shfl_sync(FULL, src0, i);
-#pragma unroll 1
-                            for (int c = lane; c < cnt; c += 32) stage[dst + c] = __ldg(src + c);
-                        }
-                        if (E == 0) continue;
                     }
-                    __syncwarp();
-                    // ---- E1: mark the docs of every staged posting
-#pragma unroll 1
-                    for (int j = lane; j < E; j += 32) {
-                        const uint32_t d = stage[j] >> 16;
-                        atomicOr(bm + (d >> 5), 1u << (d & 31));
+#define MS_VIEW(i)                                  \
+    const int len_ = __shfl_sync(FULL, v_len, i);   \
+    const uint32_t *gp_ = tp + __shfl_sync(FULL, v_rel, i)
+                    // ---- E1: mark the docs of the essential runs (L2-resident: prefetched one pair ahead)
+                    for (unsigned a = ess; a; a &= a - 1) {
+                        const int i = __ffs(a) - 1;
+                        MS_VIEW(i);
+#pragma unroll 2
+                        for (int j = lane; j < len_; j += 32) {
+                            const uint32_t d = __ldg(gp_ + j) >> 16;
+                            atomicOr(bm + (d >> 5), 1u << (d & 31));
+                        }
                     }
                     __syncwarp();
                     // ---- R: prefix popcounts (lane l owns words [l*wpl, (l+1)*wpl))
                     int mycnt = 0;
-                    uint4 w4 = make_uint4(0u, 0u, 0u, 0u);
+                    uint4 w4 = make_uint4(0u, 0u, 0u, 0u), x4 = w4;
                     if (wpl4) {
                         // 4096-doc tiles: one 16-byte load, one 8-byte store per lane
                         w4 = reinterpret_cast<const uint4 *>(bm)[lane];
                         mycnt = __popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w);
+                    } else if (wpl8) {
+                        w4 = reinterpret_cast<const uint4 *>(bm)[2 * lane];
+                        x4 = reinterpret_cast<const uint4 *>(bm)[2 * lane + 1];
+                        mycnt = __popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w) + __popc(x4.x) + __popc(x4.y) +
+                                __popc(x4.z) + __popc(x4.w);
                     } else {
                         for (int t = 0; t < wpl; ++t) {
                             const int wi = lane * wpl + t;
@@ -435,12 +366,19 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                         const int v = __shfl_up_sync(FULL, incl, o);
                         if (lane >= o) incl += v;
                     }
-                    const int marked = __shfl_sync(FULL, incl, 31);  // <= E <= cap
+                    const int marked = __shfl_sync(FULL, incl, 31);
                     const int my_base = incl - mycnt;
-                    if (wpl4) {
+                    if (wpl4 || wpl8) {
                         const uint32_t p0 = (uint32_t)my_base, p1 = p0 + __popc(w4.x), p2 = p1 + __popc(w4.y),
                                        p3 = p2 + __popc(w4.z);
-                        reinterpret_cast<uint2 *>(pre)[lane] = make_uint2(p0 | (p1 << 16), p2 | (p3 << 16));
+                        if (wpl4) {
+                            reinterpret_cast<uint2 *>(pre)[lane] = make_uint2(p0 | (p1 << 16), p2 | (p3 << 16));
+                        } else {
+                            const uint32_t p4 = p3 + __popc(w4.w), p5 = p4 + __popc(x4.x), p6 = p5 + __popc(x4.y),
+                                           p7 = p6 + __popc(x4.z);
+                            reinterpret_cast<uint4 *>(pre)[lane] =
+                                make_uint4(p0 | (p1 << 16), p2 | (p3 << 16), p4 | (p5 << 16), p6 | (p7 << 16));
+                        }
                     } else {
                         int run_sum = my_base;
                         for (int t = 0; t < wpl; ++t) {
@@ -452,103 +390,104 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                         }
                     }
                     __syncwarp();
-                    // ---- E2: essential contributions into the compact accumulator, one flat loop
-                    {
-                        int r = 0;
-#pragma unroll 1
-                        for (int j = lane; j < E; j += 32) {
-                            while (j >= rend[r]) ++r;
-                            const uint32_t post = stage[j];
-                            if (post & 0xFFFFu) {  // (padding postings carry impact 0)
-                                const uint32_t d = post >> 16;
-                                const uint32_t wd = bm[d >> 5];
-                                atomicAdd(acc + (int)pre[d >> 5] + __popc(wd & ((1u << (d & 31)) - 1u)),
-                                          __fmul_rn(rw[r], post_r(post)));
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    // the staging buffer is free from here on: start copying the next pair's essential runs
-                    if (fast) {
-                        stage_posts(nxt);
-                        staged_next = true;
-                    }
-                    // best partial score so far
+                    const bool fits = marked <= cap;
                     float mx = 0.f;
-                    for (int r = lane; r < marked; r += 32) mx = fmaxf(mx, acc[r]);
-                    mx = warp_max_nonneg(mx);
-                    // ---- N: non-essential runs complete the marked docs only, most valuable term first.  Before every
-                    // run: if even the best partial score plus everything the remaining terms could add stays below
-                    // thr', nothing of this (sub-)range can be emitted and the remaining (longest) runs are not read.
-                    bool reachable = true;
-                    for (unsigned a = __ballot_sync(FULL, mine_ok && lane < n_ne); a;) {
-                        const int i = 31 - __clz(a);
-                        a &= ~(1u << i);
-                        const float rest = __shfl_sync(FULL, cur.pre, i);  // upper bounds of terms 0..i
-                        if (__fadd_ru(mx, rest) < thr) {
-                            reachable = false;
-                            break;
+                    bool reachable = fits;
+                    if (fits) {
+                        // ---- E2: essential contributions into the compact accumulator.  Docs are distinct inside a run
+                        // (a padding posting repeats the last doc with impact 0: skipped) and runs are applied one at a
+                        // time, so plain read-modify-writes suffice.
+                        float lmax = 0.f;
+                        for (unsigned a = ess; a; a &= a - 1) {
+                            const int i = __ffs(a) - 1;
+                            MS_VIEW(i);
+                            const float w = __shfl_sync(FULL, cur.w, i);
+#pragma unroll 2
+                            for (int j = lane; j < len_; j += 32) {
+                                const uint32_t post = __ldg(gp_ + j);
+                                if (post & 0xFFFFu) {
+                                    float *slot = acc + rank_of(post >> 16);
+                                    const float nv = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
+                                    *slot = nv;
+                                    lmax = fmaxf(lmax, nv);
+                                }
+                            }
+                            __syncwarp();
                         }
-                        const int body4 = __shfl_sync(FULL, n4_cnt, i);
-                        const uint4 *g4 = tp4 + __shfl_sync(FULL, n4_lo, i);
-                        const float w = __shfl_sync(FULL, cur.w, i);
-                        float hmax = 0.f;
-                        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-                        if (lane < body4) v0 = __ldg(g4 + lane);
-                        if (lane + 32 < body4) v1 = __ldg(g4 + lane + 32);
+                        mx = warp_max_nonneg(lmax);  // best partial score so far
+                        // ---- N: non-essential runs complete the marked docs only, most valuable term first.  Before
+                        // every run: if even the best partial score plus everything the remaining terms could add stays
+                        // below thr', nothing of this (sub-)range can be emitted and the remaining (longest) runs are
+                        // not read.
+                        for (unsigned a = __ballot_sync(FULL, mine_ok && lane < n_ne); a;) {
+                            const int i = 31 - __clz(a);
+                            a &= ~(1u << i);
+                            const float rest = __shfl_sync(FULL, cur.pre, i);  // upper bounds of terms 0..i
+                            if (__fadd_ru(mx, rest) < thr) {
+                                reachable = false;
+                                break;
+                            }
+                            const int body4 = __shfl_sync(FULL, n4_cnt, i);
+                            const uint4 *g4 = tp4 + __shfl_sync(FULL, n4_lo, i);
+                            const float w = __shfl_sync(FULL, cur.w, i);
+                            float hmax = 0.f;
+                            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+                            if (lane < body4) v0 = __ldg(g4 + lane);
+                            if (lane + 32 < body4) v1 = __ldg(g4 + lane + 32);
 #pragma unroll 1
-                        for (int c = lane; c < body4; c += 64) {
-                            const uint4 u0 = v0, u1 = v1;
-                            if (c + 64 < body4) v0 = __ldg(g4 + c + 64);
-                            if (c + 96 < body4) v1 = __ldg(g4 + c + 96);
-                            // test all eight postings first (branch-free), then visit the rare hits in one divergent
-                            // loop: ~3 % of the postings hit, but some lane of the warp does in most groups of 32, so a
-                            // branch per posting would run the update path almost every time
-                            auto bit = [&](uint32_t post) -> uint32_t {
-                                return (bm[post >> 21] >> ((post >> 16) & 31u)) & 1u;
-                            };
-                            uint32_t hits = bit(u0.x) | (bit(u0.y) << 1) | (bit(u0.z) << 2) | (bit(u0.w) << 3);
-                            if (c + 32 < body4)
-                                hits |= (bit(u1.x) << 4) | (bit(u1.y) << 5) | (bit(u1.z) << 6) | (bit(u1.w) << 7);
-                            while (hits) {
-                                const int b = __ffs(hits) - 1;
-                                hits &= hits - 1;
-                                const uint4 u = (b & 4) ? u1 : u0;
-                                const uint32_t lo2 = (b & 1) ? u.y : u.x, hi2 = (b & 1) ? u.w : u.z;
-                                const uint32_t post = (b & 2) ? hi2 : lo2;
-                                const uint32_t d = post >> 16;
-                                const uint32_t wd = bm[d >> 5];
-                                // docs are distinct inside a run (a padding posting repeats the last doc with impact 0,
-                                // in the same lane): plain read-modify-write
-                                float *slot = acc + (int)pre[d >> 5] + __popc(wd & ((1u << (d & 31)) - 1u));
-                                const float nv = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
-                                *slot = nv;
-                                hmax = fmaxf(hmax, nv);
+                            for (int c = lane; c < body4; c += 64) {
+                                const uint4 u0 = v0, u1 = v1;
+                                if (c + 64 < body4) v0 = __ldg(g4 + c + 64);
+                                if (c + 96 < body4) v1 = __ldg(g4 + c + 96);
+                                // test all eight postings first (branch-free), then visit the rare hits in one divergent
+                                // loop: ~3 % of the postings hit, but some lane of the warp does in most groups of 32, so
+                                // a branch per posting would run the update path almost every time
+                                auto bit = [&](uint32_t post) -> uint32_t {
+                                    return (bm[post >> 21] >> ((post >> 16) & 31u)) & 1u;
+                                };
+                                uint32_t hits = bit(u0.x) | (bit(u0.y) << 1) | (bit(u0.z) << 2) | (bit(u0.w) << 3);
+                                if (c + 32 < body4)
+                                    hits |= (bit(u1.x) << 4) | (bit(u1.y) << 5) | (bit(u1.z) << 6) | (bit(u1.w) << 7);
+                                while (hits) {
+                                    const int b = __ffs(hits) - 1;
+                                    hits &= hits - 1;
+                                    const uint4 u = (b & 4) ? u1 : u0;
+                                    const uint32_t lo2 = (b & 1) ? u.y : u.x, hi2 = (b & 1) ? u.w : u.z;
+                                    const uint32_t post = (b & 2) ? hi2 : lo2;
+                                    float *slot = acc + rank_of(post >> 16);
+                                    const float nv = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
+                                    *slot = nv;
+                                    hmax = fmaxf(hmax, nv);
+                                }
+                            }
+                            __syncwarp();
+                            mx = fmaxf(mx, warp_max_nonneg(hmax));
+                        }
+                        // ---- cold pair: before emitting, derive a threshold from this sub-range alone.  Every lane
+                        // takes the maximum of a strided subset of the marked docs' scores; the k-th largest of the 32
+                        // lane maxima is the score of k distinct docs' worth of evidence, i.e. a lower bound of the k-th
+                        // best approximate score overall -- publish it and emit only what clears it.
+                        if (reachable && (nsub > 1 || thr == 0.f) && k <= 32 && marked >= 2 * k) {
+                            float lm = 0.f;
+                            for (int r = lane; r < marked; r += 32) lm = fmaxf(lm, acc[r]);
+                            float kth = 0.f;
+                            for (int r = 0; r < k; ++r) {
+                                const float m = warp_max_nonneg(fmaxf(lm, 0.f));
+                                kth = m;
+                                const unsigned who = __ballot_sync(FULL, lm == m);
+                                if (lane == __ffs(who) - 1) lm = -1.f;
+                            }
+                            if (kth > 0.f) {
+                                const unsigned long long kb = (unsigned long long)__double_as_longlong((double)kth);
+                                if (lane == 0) atomicMax(p.thr_bits + q, kb);
+                                thr = fmaxf(thr, thr_to_float(kb));
                             }
                         }
-                        __syncwarp();
-                        mx = fmaxf(mx, warp_max_nonneg(hmax));
+                    } else if (p.status && lane == 0) {
+                        // a skewed sub-range marked more docs than the accumulator holds: the caller re-runs the query
+                        atomicOr(p.status + q, ORAG_STATUS_OVERFLOW);
                     }
-                    // ---- cold pair: before emitting, derive a threshold from this sub-range alone.  Every lane takes
-                    // the maximum of a strided subset of the marked docs' scores; the k-th largest of the 32 lane maxima
-                    // is the score of k distinct docs' worth of evidence, i.e. a lower bound of the k-th best
-                    // approximate score overall -- publish it and emit only what clears it.
-                    if (reachable && (nsub > 1 || thr == 0.f) && k <= 32 && marked >= 2 * k) {
-                        float lm = 0.f;
-                        for (int r = lane; r < marked; r += 32) lm = fmaxf(lm, acc[r]);
-                        float kth = 0.f;
-                        for (int r = 0; r < k; ++r) {
-                            const float m = warp_max_nonneg(fmaxf(lm, 0.f));
-                            kth = m;
-                            const unsigned who = __ballot_sync(FULL, lm == m);
-                            if (lane == __ffs(who) - 1) lm = -1.f;
-                        }
-                        if (kth > 0.f) {
-                            const unsigned long long kb = (unsigned long long)__double_as_longlong((double)kth);
-                            if (lane == 0) atomicMax(p.thr_bits + q, kb);
-                            thr = fmaxf(thr, thr_to_float(kb));
-                        }
-                    }
+#undef MS_VIEW
                     // ---- X: only when something can clear the threshold, claim by RANK (lane-balanced, conflict-free):
                     // read and reset acc[r]; the rare score that clears the threshold needs its doc id -- the word whose
                     // rank range holds r (binary search in the prefix counts), then the (r - pre[word])-th set bit
@@ -566,7 +505,7 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                                 ms_emit(p, q, (int32_t)(base_doc + lo * 32 + b), v);
                             }
                         }
-                    } else {
+                    } else if (fits) {
                         for (int r = lane; r < marked; r += 32) acc[r] = 0.f;
                     }
                     __syncwarp();
@@ -576,13 +515,10 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                     __syncwarp();
                 }
             }
-            if (!staged_next) stage_posts(nxt);
             cur = nxt;
             nxt = stage_run(descA);
             descA = stage_desc(qi + 3);
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
     }
 }
 
@@ -738,7 +674,6 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
         ORAG_LAUNCH_CHECK();
     }
     if (ix->fp_n_tiles > 0) {
-        const int words = (ix->fp_tile_docs + 31) / 32;
         // Stand-alone: 2 CTAs x 16 warps per SM (64 registers per thread, 7 KiB of shared memory per warp).  Background
         // (ORAG_BM25_BACKGROUND): CTAs of 8 warps and < 31 KB of shared memory, so that ONE of them fits next to a
         // resident CTA of the cosine scan (199.9 KB, 384 threads, 96 registers) and rides along on the SM resources the

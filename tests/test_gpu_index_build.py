@@ -64,7 +64,7 @@ def test_index_builder_layout_matches_oracle(n, vocab, lmin, lmax, tile, fp_tile
     want = {(t, int(d)): int(f) for t in range(vocab) for d, f in zip(pdoc[off[t]:off[t + 1]], ptf[off[t]:off[t + 1]])}
     assert exact == want
     if fp_tile is None:
-        assert ix.fp_tile_docs == min(4096, max(32, 1 << ((n // 16 - 1).bit_length())))
+        assert ix.fp_tile_docs == min(8192, max(32, 1 << ((n // 16 - 1).bit_length())))
     if ix.has_negative_idf:
         assert ix.postings_r16 is None
         return

@@ -121,7 +121,7 @@ def test_index_build_refuses_host_tensors(built_lib):
     tok = torch.tensor([0, 1, 1, 2, 3], dtype=torch.int32)
     with pytest.raises(_ffi.OragError, match="no CPU builder"):
         Bm25Index(doc_off, tok, 8, tile_docs=32)
-    assert default_fp_tile_docs(10_000_000) == 4096 and default_fp_tile_docs(700) == 64 and default_fp_tile_docs(0) == 32
+    assert default_fp_tile_docs(10_000_000) == 8192 and default_fp_tile_docs(700) == 64 and default_fp_tile_docs(0) == 32
     L = _ffi.lib()
     assert L.orag_bm25_build_workspace_bytes(1000, 50, 64, 256) > 0
     assert L.orag_bm25_build_workspace_bytes(1000, 50, 48, 256) == 0       # tile sizes are powers of two
