@@ -284,15 +284,19 @@ class Harness:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def device_timed(self, step):
+    def device_timed(self, step, drain=None):
         """W warm-up steps, then exactly K steps between two events (barrier + synchronize on both sides, max over
-        ranks).  `step()` enqueues one step without synchronising with the host.  Returns (total ms, launches, brackets)
-        where brackets = per-step CUDA-event durations of the two dominant kernels (library hooks)."""
+        ranks).  `step()` enqueues one step without synchronising with the host; `drain()` (optional) makes the
+        current stream wait for everything the steps submitted and is called before every closing event / barrier.
+        Returns (total ms, launches, brackets[, what the timed loop's drain() returned]) where brackets = per-step
+        CUDA-event durations of the two dominant kernels (library hooks)."""
+        drain = drain or (lambda: None)
         torch, L, args = self.torch, self.L, self.args
         if self.rank == 0:  # one poller per box: nvidia-smi queries take driver locks that kernel launches also need
             self.sampler.start()
         for _ in range(self.warmup):
             step()
+        drain()
         self.barrier()
         L.orag_profile_enable(1)
         launches0 = int(L.orag_launch_count())
@@ -302,6 +306,7 @@ class Harness:
         ev0.record()
         for _ in range(args.steps):
             step()
+        drained = drain()
         ev1.record()
         self.barrier()
         w1 = time.time()
@@ -322,21 +327,24 @@ class Harness:
             p0 = time.time()
             for _ in range(n_probe):
                 step()
+            drain()
             torch.cuda.synchronize()
             self.sampler.window(p0, time.time())
             self.barrier()
         # the clocks line describes the device-timed loop: stop polling before the end-to-end loop, where every step
         # synchronises with the host and a poller taking driver locks would be measured with it
         self.clocks = self.sampler.stop()
-        return dev_ms, launches, brackets
+        return (dev_ms, launches, brackets) if drained is None else (dev_ms, launches, brackets, drained)
 
-    def e2e_timed(self, step_with_copies):
+    def e2e_timed(self, step_with_copies, drain=None):
         torch = self.torch
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(self.args.steps):
             step_with_copies()
+        if drain:
+            drain()
         e1.record()
         self.barrier()
         return self.max_over_ranks(e0.elapsed_time(e1))
@@ -523,39 +531,73 @@ def run_hybrid_like(args):
     h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = out_ids_h.numel() * 8 + out_sc_h.numel() * 8 + Bq * 4
 
-    # back-to-back batches, inputs resident: nothing synchronises with the host inside the timed region (the per-query
-    # overflow flags of every step are kept and checked after it -- a flagged step would invalidate the run)
-    flags, last = [], {}
+    # back-to-back batches, inputs resident: nothing synchronises with the host inside the timed region.  Batches are
+    # SUBMITTED (two in flight: the latency-bound tail of batch i runs under the scan of batch i+1) and all of them are
+    # waited for before the closing event; the per-query overflow flags of every step are kept and checked after it --
+    # a flagged step would invalidate the run.
+    tickets, last = [], {}
 
     def step():
-        res = sh.search(*devt, k, check_overflow=False)
-        flags.append(res["status"])
+        tickets.append(sh.submit(*devt, k))
+
+    def drain():
+        res = None
+        flags = []
+        for t in tickets:
+            res = t.wait()          # orders the current stream after that search; no host synchronisation
+            flags.append(res["status"])
+        tickets.clear()
         last["res"] = res
+        return flags
 
-    dev_ms, launches, brackets = h.device_timed(step)
-    if bool(torch.stack(flags).any()):  # warm-up, timed and probe steps alike
+    dev_ms, launches, brackets, flags = h.device_timed(step, drain)
+    if bool(torch.stack(flags).any()):
         raise SystemExit("bench: a candidate buffer overflowed inside the timed region; results would need the repair path")
-    flags.clear()
 
-    # ---- timed: end to end through the public call with HOST buffers
+    # ---- timed: end to end through the public call with HOST buffers, two batches in flight: while batch i computes,
+    # the results of batch i-1 travel to the host and are read there (ONE host synchronisation per step)
+    dev_sets = [devt, [t.clone() for t in devt]]
+    outs_h = [(out_ids_h, out_sc_h, status_h),
+              (torch.empty_like(out_ids_h).pin_memory(), torch.empty_like(out_sc_h).pin_memory(),
+               torch.empty_like(status_h).pin_memory())]
+    state = {"i": 0, "prev": None}
+
+    def finish(ticket, slot):
+        r = ticket.wait()
+        ids_h, sc_h, st_h = outs_h[slot]
+        ids_h.copy_(r["ids"], non_blocking=True)
+        sc_h.copy_(r["scores"], non_blocking=True)
+        st_h.copy_(r["status"], non_blocking=True)   # the overflow flags travel with the result
+        torch.cuda.current_stream().synchronize()      # (the batch submitted after this one keeps running on its lane)
+        if int(st_h.max()) != 0:                       # rare: repair through the exhaustive kernels
+            torch.cuda.synchronize()
+            r = sh.search(*ticket_inputs[slot], k, check_overflow=True)
+            ids_h.copy_(r["ids"]); sc_h.copy_(r["scores"])
+
+    ticket_inputs = [None, None]
+
     def step_e2e():
-        for d, s in zip(devt, host):
-            d.copy_(s, non_blocking=True)
-        r = sh.search(*devt, k, check_overflow=False)
-        out_ids_h.copy_(r["ids"], non_blocking=True)
-        out_sc_h.copy_(r["scores"], non_blocking=True)
-        status_h.copy_(r["status"], non_blocking=True)   # the overflow flags travel with the result: ONE sync per step
-        torch.cuda.current_stream().synchronize()
-        if int(status_h.max()) != 0:                      # rare: repair through the exhaustive kernels
-            r = sh.search(*devt, k, check_overflow=True)
-            out_ids_h.copy_(r["ids"]); out_sc_h.copy_(r["scores"])
+        i = state["i"]
+        bufs = dev_sets[i & 1]
+        for dst, src in zip(bufs, host):
+            dst.copy_(src, non_blocking=True)
+        t = sh.submit(*bufs, k)
+        ticket_inputs[i & 1] = bufs
+        if state["prev"] is not None:
+            finish(state["prev"], (i - 1) & 1)
+        state["prev"], state["i"] = t, i + 1
 
-    e2e_ms = h.e2e_timed(step_e2e)
+    def drain_e2e():
+        if state["prev"] is not None:
+            finish(state["prev"], (state["i"] - 1) & 1)
+            state["prev"] = None
+
+    e2e_ms = h.e2e_timed(step_e2e, drain_e2e)
     exchange_used = "none (one shard)" if world == 1 else sh.exchange + (f" ({sh.exchange_note})" if sh.exchange_note else "")
 
     # ---- outside the timed regions: the last step's results against the CPU oracle at full corpus size
     verified = cpu = None
-    res = last["res"]
+    res = last["res"]   # the results of the last submitted batch of the device-timed loop
     if rank == 0:
         keys = {"3": ["cos_ids", "cos_scores", "bm25_ids", "bm25_scores", "bm25_max", "ids", "rrf_scores"],
                 "2": ["cos_ids", "cos_scores"], "4": ["bm25_ids", "bm25_scores", "bm25_max"]}[args.config]

@@ -306,13 +306,14 @@ int orag_hybrid_merge(const int64_t *d_gathered, int n_shards, int n_queries, in
  *     orag_hybrid_push: one launch packs this rank's lists (same arrays / layout as the gathered buffer of
  *       orag_hybrid_merge: d_cos_* [n_queries, fetch_k], d_bm25_* [n_queries, kk] RAW scores, d_bm25_max
  *       [n_queries]; d_status / d_status2 [n_queries] or NULL: the status words of the cosine and the BM25 call,
- *       OR-ed into the block's status column) and stores them into slot seq&1 of EVERY peer, then publishes
+ *       OR-ed into the block's status column) and stores them into slot seq&3 of EVERY peer, then publishes
  *       seq with a system-scope release store.
  *     orag_hybrid_wait: one tiny launch that acquires the n_shards sequence numbers in this rank's own buffer;
  *       *d_gathered (host out) is the [n_shards, n_queries, W] array to hand to orag_hybrid_merge on the same
  *       stream.  A block that has not arrived after timeout_ms gets ORAG_STATUS_EXCHANGE_TIMEOUT in its status
  *       words (the merge ORs them into d_out_status) instead of hanging the GPU.
- *   Every rank must call push and wait for every seq, in order, with the same n_queries / fetch_k / kk.
+ *   Every rank must call push and wait for every seq, in order, with the same n_queries / fetch_k / kk.  Two searches
+ *   may be in flight at once on two streams (even / odd seq, each in stream order): the buffer has four slots.
  * ------------------------------------------------------------------------- */
 size_t orag_exchange_bytes(int n_shards, int max_queries, int fetch_k, int kk);
 int orag_exchange_alloc(size_t bytes, void **d_buf);

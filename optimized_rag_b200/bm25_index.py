@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -109,7 +110,7 @@ class Bm25Plan:
         self.device, self.vocab, self.tile_docs = dev, int(vocab), int(tile_docs)
         self.doc_off, self.tokens = doc_off.contiguous(), tokens.contiguous()
         self.n_docs = int(doc_off.numel() - 1)
-        self.fp_tile_docs = int(fp_tile_docs or default_fp_tile_docs(self.n_docs))
+        self.fp_tile_docs = int(fp_tile_docs or os.environ.get("ORAG_FP_TILE_DOCS") or default_fp_tile_docs(self.n_docs))
         assert self.fp_tile_docs & (self.fp_tile_docs - 1) == 0 and 32 <= self.fp_tile_docs <= 16384
         self.n_tiles = (self.n_docs + self.tile_docs - 1) // self.tile_docs
         self.fp_n_tiles = (self.n_docs + self.fp_tile_docs - 1) // self.fp_tile_docs
@@ -221,7 +222,7 @@ class Bm25Index:
             self.fp_tile_base = self.fp_tile_term_off = None
         plan.ws = plan.doc_off = plan.tokens = None  # the cursors are spent: a plan fills one index
         self._make_struct()
-        self._ws = None
+        self._ws = self._lane_ws = None
 
     def _make_struct(self):
         ptr = lambda t: t.data_ptr() if t is not None else None
@@ -241,15 +242,21 @@ class Bm25Index:
         return self.t4_table[self.dl.long()]
 
     # ------------------------------------------------------------------ queries
-    def _workspace(self, n_queries: int, k: int, flags: int) -> torch.Tensor:
+    def _workspace(self, n_queries: int, k: int, flags: int, lane: int = 0) -> torch.Tensor:
+        """One workspace per lane (calls of different lanes may be in flight at the same time); `_ws` = lane 0's."""
         need = int(_ffi.lib().orag_bm25_workspace_bytes(ctypes.byref(self.struct), n_queries, k, flags))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
-        return self._ws
+        if self._lane_ws is None:
+            self._lane_ws = {}
+        ws = self._lane_ws.get(lane)
+        if ws is None or ws.numel() < need:
+            ws = self._lane_ws[lane] = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+        if lane == 0:
+            self._ws = ws
+        return ws
 
     def topk(self, query_terms: torch.Tensor, query_lens: torch.Tensor, k: int, normalize: bool = True,
              force: str | None = None, check_overflow: bool = True, status_out: list | None = None,
-             background: bool = False):
+             background: bool = False, lane: int = 0):
         """query_terms int32 [B, max_terms] (negative = OOV/padding), query_lens int32 [B].
         `status_out` (a list) receives the per-query status tensor so that a caller can defer the overflow
         check and pay one host sync for several calls (see engine.HybridShard.local_lists).
@@ -266,7 +273,7 @@ class Bm25Index:
         sc = torch.empty((Bq, k), dtype=torch.float64, device=self.device)
         mx = torch.empty(Bq, dtype=torch.float64, device=self.device)
         status = torch.empty(Bq, dtype=torch.int32, device=self.device)
-        ws = self._workspace(Bq, k, flags)
+        ws = self._workspace(Bq, k, flags, lane)
         st = torch.cuda.current_stream(self.device).cuda_stream
         _ffi.check(_ffi.lib().orag_bm25_topk(ctypes.byref(self.struct), self.doc_id_base, query_terms.data_ptr(),
                                              query_lens.data_ptr(), Bq, mt, k, flags, ids.data_ptr(), sc.data_ptr(),
@@ -279,7 +286,7 @@ class Bm25Index:
             if bad.numel():
                 # candidate buffer overflowed for these queries: exact dense path (never a CPU fallback)
                 i2, s2, m2 = self.topk(query_terms[bad].contiguous(), query_lens[bad].contiguous(), k, normalize,
-                                       force="dense", check_overflow=False)
+                                       force="dense", check_overflow=False, lane=lane)
                 ids[bad], sc[bad], mx[bad] = i2, s2, m2
         return ids, sc, mx
 
@@ -378,5 +385,5 @@ class Bm25Index:
             setattr(self, name, None if a is None else torch.from_numpy(a).to(dev))
         self.df_local = arr("df_local")
         self._make_struct()
-        self._ws = None
+        self._ws = self._lane_ws = None
         return self

@@ -9,10 +9,12 @@
 // acquires the G sequence numbers in the rank's OWN buffer, after which the slot is exactly the
 // [G, B, W] array orag_hybrid_merge reads.  Two launches replace ~6 packing kernels + the collective.
 //
-// Buffer of one rank (orag_exchange_bytes):   uint64 seq[2][G] (padded to 256 B) | int64 slot[2][G * max_queries * W]
-// A search with sequence number s uses slot s & 1.  Re-use is safe with two slots: rank r writes slot s&1
-// of peer p for search s+2 only after its own wait for search s+1 returned, i.e. after p published s+1,
-// which p does (stream order) after its merge of search s has finished reading that slot.
+// Buffer of one rank (orag_exchange_bytes):   uint64 seq[4][G] (padded to 256 B) | int64 slot[4][G * max_queries * W]
+// A search with sequence number s uses slot s & 3, and callers may keep two searches in flight on two streams
+// ("lanes": even and odd sequence numbers, each lane in stream order).  Re-use is safe with four slots: rank r writes
+// slot s&3 of peer p for search s+4 after -- same lane, stream order -- its own wait for search s+2 returned, i.e.
+// after p published s+2, which p does (its lane of s, stream order) after its merge of search s has finished reading
+// that slot.
 //
 // A wait that does not see a peer's sequence number within the timeout does not hang the GPU: it sets
 // ORAG_STATUS_EXCHANGE_TIMEOUT in the status word of every query of that shard's block, which the merge ORs
@@ -23,7 +25,7 @@
 
 namespace orag {
 
-constexpr int kXSlots = 2;
+constexpr int kXSlots = 4;
 constexpr int kXMaxShards = 64;
 
 static inline size_t x_flag_bytes(int n_shards) { return align_up((size_t)kXSlots * n_shards * 8, 256); }
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(
     unsigned long long seq)
 {
     const int p = blockIdx.x;
-    const int slot = (int)(seq & 1ull);
+    const int slot = (int)(seq & (unsigned long long)(kXSlots - 1));
     const int W = 2 * fetch_k + 2 * kk + 2;
     uint8_t *base = (uint8_t *)peers[p];
     int64_t *dst = (int64_t *)(base + flag_bytes) + (size_t)slot * slot_words + (size_t)rank * B * W;
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(kXMaxShards) exchange_wait_kernel(uint8_t *min
 {
     const int g = threadIdx.x;
     if (g >= G) return;
-    const int slot = (int)(seq & 1ull);
+    const int slot = (int)(seq & (unsigned long long)(kXSlots - 1));
     const unsigned long long *flag = (const unsigned long long *)mine + (size_t)slot * G + g;
     const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(flag) < seq) {
@@ -184,6 +186,6 @@ extern "C" int orag_hybrid_wait(void *d_buf, int n_shards, int max_queries, int 
                                                                       (unsigned long long)seq,
                                                                       (unsigned long long)timeout_ms * 1000000ull);
     ORAG_LAUNCH_CHECK();
-    *d_gathered = (const int64_t *)((uint8_t *)d_buf + fb) + (size_t)(seq & 1ull) * sw;
+    *d_gathered = (const int64_t *)((uint8_t *)d_buf + fb) + (size_t)(seq & (uint64_t)(kXSlots - 1)) * sw;
     return ORAG_OK;
 }

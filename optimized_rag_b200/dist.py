@@ -200,9 +200,10 @@ class PeerExchange:
     def fits(self, n_queries: int, fetch_k: int, kk: int) -> bool:
         return n_queries <= self.max_queries and fetch_k == self.fetch_k and kk == self.kk
 
-    def exchange(self, cos_ids, cos_scores, bm_ids, bm_scores, bm_max, status, status2=None):
+    def exchange(self, cos_ids, cos_scores, bm_ids, bm_scores, bm_max, status, status2=None, seq: int | None = None):
         """Push this rank's lists to every peer, wait for theirs -> (device pointer of [G, B, W], shape).  `status` and
-        the optional `status2` (the cosine and the BM25 call's overflow words) are OR-ed by the push kernel."""
+        the optional `status2` (the cosine and the BM25 call's overflow words) are OR-ed by the push kernel.  `seq`:
+        the search's sequence number (same on every rank, strictly increasing; default: one more than the last)."""
         L = _ffi.lib()
         Bq = cos_ids.shape[0]
         assert self.fits(Bq, cos_ids.shape[1], bm_ids.shape[1])
@@ -210,7 +211,8 @@ class PeerExchange:
             assert t.is_contiguous() and t.device == self.device
         assert status.dtype == torch.int32 and bm_max.dtype == torch.float64
         assert status2 is None or (status2.dtype == torch.int32 and status2.is_contiguous())
-        self.seq += 1
+        assert seq is None or seq > self.seq
+        self.seq = self.seq + 1 if seq is None else int(seq)
         st = torch.cuda.current_stream(self.device).cuda_stream
         _ffi.check(L.orag_hybrid_push(cos_ids.data_ptr(), cos_scores.data_ptr(), bm_ids.data_ptr(), bm_scores.data_ptr(),
                                       bm_max.data_ptr(), status.data_ptr(),
@@ -258,11 +260,13 @@ class ShardedHybrid:
         self.exchange = exchange or os.environ.get("ORAG_EXCHANGE", "peer")
         assert self.exchange in ("nccl", "peer")
         self.exchange_note = ""
-        self._gather_buf = None
+        self._gather_buf: dict = {}   # lane -> NCCL all-gather buffer
         self._peer: PeerExchange | None = None
         self._retired: list[PeerExchange] = []  # outgrown exchanges: peers may still have them mapped until close()
+        self._searches = 0            # searches issued so far (all ranks count alike): lane = parity of the next one
+        self._lane_streams: dict = {}
 
-    def _exchange(self, lists, fetch_k: int, kk: int, k: int):
+    def _exchange(self, lists, fetch_k: int, kk: int, k: int, lane: int = 0):
         ci, cs, bi, bs, bm, st, st2 = lists
         if self.exchange == "peer":
             Bq = ci.shape[0]
@@ -277,14 +281,15 @@ class ShardedHybrid:
                     logger.warning("peer exchange unavailable, using the NCCL all-gather: %s", e)
                     self.exchange, self.exchange_note = "nccl", f"peer setup failed: {e}"
         if self.exchange == "peer":
-            ptr, shape = self._peer.exchange(ci, cs, bi, bs, bm, st, st2)
+            ptr, shape = self._peer.exchange(ci, cs, bi, bs, bm, st, st2, seq=self._searches)
             return hybrid_merge(ptr, fetch_k, kk, self.shard.rrf_k, k, shape=shape, device=ci.device)
         mine = pack_local(ci, cs, bi, bs, bm, st if st2 is None else st | st2)
         Bq, W = mine.shape
-        if self._gather_buf is None or self._gather_buf.shape != (self.world, Bq, W):
-            self._gather_buf = torch.empty((self.world, Bq, W), dtype=torch.int64, device=mine.device)
-        dist.all_gather_into_tensor(self._gather_buf.view(-1), mine.view(-1), group=self.group)
-        return hybrid_merge(self._gather_buf, fetch_k, kk, self.shard.rrf_k, k)
+        buf = self._gather_buf.get(lane)
+        if buf is None or buf.shape != (self.world, Bq, W):
+            buf = self._gather_buf[lane] = torch.empty((self.world, Bq, W), dtype=torch.int64, device=mine.device)
+        dist.all_gather_into_tensor(buf.view(-1), mine.view(-1), group=self.group)
+        return hybrid_merge(buf, fetch_k, kk, self.shard.rrf_k, k)
 
     def close(self):
         """Collective: unmap / free the peer exchange buffers (call on every rank before the process group goes away,
@@ -294,17 +299,20 @@ class ShardedHybrid:
         self._retired, self._peer = [], None
 
     def search(self, query_emb, query_terms, query_lens, k: int = 10, fetch_k: int | None = None,
-               check_overflow: bool = True):
+               check_overflow: bool = True, lane: int | None = None):
         """Per batch: local lists (no host sync) -> ONE exchange of the packed winners -> ONE merge+RRF launch.
         Candidate-buffer overflow on any rank is seen by every rank in the gathered status column; the affected
         queries (rare: thousands of duplicates / near-ties) are then repaired by all ranks together through the
         exhaustive kernels and a second, small exchange -- every rank takes the same branch."""
         fetch_k = fetch_k or k
+        if lane is None:  # the lane of a search is the parity of its exchange sequence number (PeerExchange slots)
+            lane = (self._searches + 1) & 1
+        self._searches += 1
         if self.world == 1:
-            return self.shard.search(query_emb, query_terms, query_lens, k, fetch_k, check_overflow)
+            return self.shard.search(query_emb, query_terms, query_lens, k, fetch_k, check_overflow, lane=lane)
         kk = fetch_k + BM25_GUARD
-        lists = self.shard.local_lists(query_emb, query_terms, query_lens, fetch_k, kk, False)
-        out, status = self._exchange(lists, fetch_k, kk, k)
+        lists = self.shard.local_lists(query_emb, query_terms, query_lens, fetch_k, kk, False, lane=lane)
+        out, status = self._exchange(lists, fetch_k, kk, k, lane)
         out["status"] = status  # check_overflow=False: no host sync at all; the caller checks it with the results
         if check_overflow and bool(status.any()):
             if bool((status & _ffi.ORAG_STATUS_EXCHANGE_TIMEOUT).any()):
@@ -313,14 +321,51 @@ class ShardedHybrid:
             lists = self.shard.exact_lists(query_emb[bad].contiguous(), query_terms[bad].contiguous(),
                                            query_lens[bad].contiguous(), fetch_k, kk, False)
             zero = torch.zeros(bad.numel(), dtype=torch.int32, device=bad.device)
-            buf = self._gather_buf
-            self._gather_buf = None
-            fixed, _ = self._exchange((*lists, zero, None), fetch_k, kk, k)
-            self._gather_buf = buf
+            # the repair exchange takes a sequence number (and an all-gather buffer) of its own; it is a synchronous
+            # path: callers that keep batches in flight (`submit`) drain them before repairing
+            self._searches += 1
+            fixed, _ = self._exchange((*lists, zero, None), fetch_k, kk, k, lane=2)
             for key, val in fixed.items():
                 out[key][bad] = val
             out["status"] = torch.zeros_like(status)
         return out
+
+    # ------------------------------------------------------------------ two batches in flight
+    def submit(self, query_emb, query_terms, query_lens, k: int = 10, fetch_k: int | None = None) -> "Ticket":
+        """Enqueue one search WITHOUT waiting for the one before it: consecutive submissions alternate between two
+        lanes (streams with their own workspaces and exchange slots), so the latency-bound tail of batch i -- candidate
+        re-scores, selection, exchange, merge -- runs under the scan of batch i+1.  Nothing synchronises with the host.
+        `Ticket.wait()` orders the caller's stream after the search and hands out the result dict (with the per-query
+        `status` word: non-zero = that query must be repeated through `search(check_overflow=True)`).  Every rank
+        must submit the same sequence of batches."""
+        dev = query_emb.device
+        lane = (self._searches + 1) & 1
+        if lane not in self._lane_streams:
+            self._lane_streams[lane] = torch.cuda.Stream(dev)
+        stream = self._lane_streams[lane]
+        stream.wait_stream(torch.cuda.current_stream(dev))   # the inputs are ready
+        with torch.cuda.stream(stream):
+            out = self.search(query_emb, query_terms, query_lens, k, fetch_k, check_overflow=False, lane=lane)
+            done = torch.cuda.Event()
+            done.record(stream)
+        return Ticket(out, done, dev, (query_emb, query_terms, query_lens))
+
+
+class Ticket:
+    """Handle of a submitted search (ShardedHybrid.submit)."""
+
+    def __init__(self, out: dict, done: "torch.cuda.Event", device, inputs):
+        self._out, self._done, self._device, self._inputs = out, done, device, inputs
+
+    def wait(self) -> dict:
+        """The result dict; the CURRENT stream is ordered after the search (no host synchronisation)."""
+        cur = torch.cuda.current_stream(self._device)
+        cur.wait_event(self._done)
+        for t in self._out.values():
+            if isinstance(t, torch.Tensor):
+                t.record_stream(cur)   # produced on the lane's stream, consumed on the caller's
+        self._inputs = None
+        return self._out
 
 
 class _ShardedList:
@@ -347,6 +392,15 @@ class _ShardedList:
 
     def close(self):
         self._buf = None
+
+    def submit(self, *args, **kw) -> "Ticket":
+        """Same calling convention as ShardedHybrid.submit; these single-list searches run on the caller's stream (one
+        batch at a time), the ticket only marks their completion."""
+        dev = args[0].device
+        out = self.search(*args, check_overflow=False, **kw)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(dev))
+        return Ticket(out, done, dev, args)
 
 
 class ShardedCosine(_ShardedList):

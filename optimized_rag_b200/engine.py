@@ -99,16 +99,18 @@ class CosineIndex:
                                               _stream(self.device)), "orag_row_sq")
         self._ws = {}
 
-    def _workspace(self, n_queries: int, k: int, mode: int) -> torch.Tensor:
+    def _workspace(self, n_queries: int, k: int, mode: int, lane: int = 0) -> torch.Tensor:
+        """One workspace per (mode, lane): calls of different lanes may be in flight at the same time (see
+        dist.ShardedHybrid.submit), a workspace belongs to one call until its work has finished."""
         need = int(_ffi.lib().orag_cosine_workspace_bytes(self.n_rows, self.dim, n_queries, k, mode))
-        ws = self._ws.get(mode)
+        ws = self._ws.get((mode, lane))
         if ws is None or ws.numel() < need:
             ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
-            self._ws[mode] = ws
+            self._ws[(mode, lane)] = ws
         return ws
 
     def topk(self, queries: torch.Tensor, k: int, mode: str | None = None, check_overflow: bool = True,
-             status_out: list | None = None):
+             status_out: list | None = None, lane: int = 0):
         """queries fp32 [B, dim] on the same device -> (ids int64 [B,k], scores float64 [B,k]).
         `status_out` (a list) receives the per-query status tensor for a deferred overflow check."""
         _require_cuda(queries, "queries")
@@ -122,7 +124,7 @@ class CosineIndex:
         ids = torch.empty((Bq, k), dtype=torch.int64, device=self.device)
         sc = torch.empty((Bq, k), dtype=torch.float64, device=self.device)
         status = torch.empty(Bq, dtype=torch.int32, device=self.device)
-        ws = self._workspace(Bq, k, m)
+        ws = self._workspace(Bq, k, m, lane)
         _ffi.check(_ffi.lib().orag_cosine_topk(
             self.corpus.data_ptr(), self.inv_norm.data_ptr() if self.inv_norm is not None else None,
             self.shadow.data_ptr() if self.shadow is not None else None,
@@ -135,7 +137,7 @@ class CosineIndex:
             bad = torch.nonzero(status != 0).flatten()
             if bad.numel():
                 # more near-ties than candidate slots: exact scan for these queries (still on the GPU)
-                i2, s2 = self.topk(queries[bad].contiguous(), k, mode="exact", check_overflow=False)
+                i2, s2 = self.topk(queries[bad].contiguous(), k, mode="exact", check_overflow=False, lane=lane)
                 ids[bad], sc[bad] = i2, s2
         return ids, sc
 
@@ -365,11 +367,11 @@ class HybridShard:
         self.cosine = cosine
         self.bm25 = bm25
         self.rrf_k = rrf_k
-        self._side = None
+        self._side: dict = {}   # lane -> side stream of the BM25 pipeline
         self.coschedule = os.environ.get("ORAG_COSCHEDULE", "0") == "1"
 
     def local_lists(self, query_emb: torch.Tensor, query_terms: torch.Tensor, query_lens: torch.Tensor, fetch_k: int,
-                    bm25_k: int, normalize: bool):
+                    bm25_k: int, normalize: bool, lane: int = 0):
         """Cosine top-fetch_k and BM25 top-bm25_k of this shard, enqueued WITHOUT any host synchronisation.
         The BM25 pipeline runs on a side stream next to the cosine pipeline, so the small latency-bound kernels
         of either (query norms, candidate re-score, selection, finalize) overlap the other's main kernel.
@@ -379,11 +381,11 @@ class HybridShard:
         dev = query_emb.device
         cur = torch.cuda.current_stream(dev)
         L = _ffi.lib()
-        if self._side is None:
-            self._side = torch.cuda.Stream(dev)
+        if lane not in self._side:
+            self._side[lane] = torch.cuda.Stream(dev)
             if self.coschedule:
                 L.orag_cosine_mark_prescan(1)
-        side = self._side
+        side = self._side[lane]
         # inputs are ready; also what makes the caching allocator's per-stream pools safe without record_stream():
         # every side-stream block (BM25 outputs, status) is only ever re-issued to side-stream work of a LATER call,
         # which this wait orders after everything the current stream has enqueued on those blocks
@@ -395,16 +397,16 @@ class HybridShard:
             # resident scan CTA of every SM.  Measured on B200 at 10M x 256: one step 9.05 ms instead of 9.3, but in
             # a sustained loop the GPU sits at its power cap and the overlap buys nothing (9.76 vs 9.63 ms/step),
             # hence off by default (ORAG_COSCHEDULE=1 turns it on).
-            ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=False, status_out=st_c)
+            ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=False, status_out=st_c, lane=lane)
             with torch.cuda.stream(side):
                 _ffi.check(L.orag_stream_wait_prescan(side.cuda_stream), "orag_stream_wait_prescan")
                 bi, bs, bmax = self.bm25.topk(query_terms, query_lens, bm25_k, normalize=normalize,
-                                              check_overflow=False, status_out=st_b, background=True)
+                                              check_overflow=False, status_out=st_b, background=True, lane=lane)
         else:
             with torch.cuda.stream(side):
                 bi, bs, bmax = self.bm25.topk(query_terms, query_lens, bm25_k, normalize=normalize,
-                                              check_overflow=False, status_out=st_b)
-            ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=False, status_out=st_c)
+                                              check_overflow=False, status_out=st_b, lane=lane)
+            ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=False, status_out=st_c, lane=lane)
         cur.wait_stream(side)
         return ci, cs, bi, bs, bmax, st_c[0], st_b[0]
 
@@ -417,9 +419,10 @@ class HybridShard:
         return ci, cs, bi, bs, bmax
 
     def search(self, query_emb: torch.Tensor, query_terms: torch.Tensor, query_lens: torch.Tensor, k: int = 10,
-               fetch_k: int | None = None, check_overflow: bool = True):
+               fetch_k: int | None = None, check_overflow: bool = True, lane: int = 0):
         fetch_k = fetch_k or k
-        ci, cs, bi, bs, bmax, st_c, st_b = self.local_lists(query_emb, query_terms, query_lens, fetch_k, fetch_k, True)
+        ci, cs, bi, bs, bmax, st_c, st_b = self.local_lists(query_emb, query_terms, query_lens, fetch_k, fetch_k, True,
+                                                            lane=lane)
         fi, fs, src, status = rrf_fuse_pair(ci, bi, self.rrf_k, k, st_c, st_b)
         out = {"ids": fi, "rrf_scores": fs, "scores": fs, "src_ranks": src, "cos_ids": ci, "cos_scores": cs, "bm25_ids": bi,
                "bm25_scores": bs, "bm25_max": bmax, "status": status}

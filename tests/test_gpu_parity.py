@@ -364,7 +364,7 @@ def test_peer_exchange_kernels_two_virtual_ranks(eng):
             for g in range(G):
                 out = ctypes.c_void_p()
                 _ffi.check(L.orag_hybrid_wait(bufs[g], G, maxq, B, fk, kk, seq, 2000, ctypes.byref(out), st), "wait")
-                assert out.value == bufs[g] + 256 + (seq & 1) * G * maxq * W * 8
+                assert out.value == bufs[g] + 256 + (seq & 3) * G * maxq * W * 8
                 got, status = hybrid_merge(out.value, fk, kk, 60, k, shape=(G, B, W), device=torch.device(DEV))
                 for key in ref:
                     assert torch.equal(got[key], ref[key]), (seq, g, key)
@@ -711,3 +711,29 @@ print("cluster ok")
         env = dict(os.environ, ORAG_SCAN_CLUSTER="2", ORAG_SCAN_2SM=two_sm)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "cluster ok" in r.stdout, (two_sm, r.stdout + r.stderr)
+
+
+def test_submit_keeps_two_batches_in_flight_and_equals_search(eng):
+    """ShardedHybrid.submit (two lanes: own streams, workspaces, exchange slots) over a sequence of DIFFERENT batches:
+    every ticket's result equals the plain search of its batch, bit for bit, whatever order the lanes finish in."""
+    from optimized_rag_b200.bm25_index import Bm25Index
+    from optimized_rag_b200.dist import ShardedHybrid
+    n, dim, vocab, k = 30000, 256, 3000, 10
+    thr = syn.zipf_thresholds(vocab)
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim, 5)
+    doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, 20, 80, thr)
+    sh = ShardedHybrid(eng.HybridShard(eng.CosineIndex(_t(corpus), mode="f16"),
+                                       Bm25Index(_t(doc_off), _t(tok), vocab, tile_docs=1024)))
+    batches = []
+    for i, nq in enumerate([64, 17, 64, 1, 40, 64, 64]):
+        q = syn.query_embeddings(nq, n, dim, query_seed=syn.SEED_QUERIES + i, dup_per_mille=5)
+        qt, ql = syn.keyword_queries(nq, vocab, seed=syn.SEED_KWQUERIES + 10 * i, min_rank=10, thresholds=thr)
+        batches.append((_t(q), _t(qt), _t(ql)))
+    tickets = [sh.submit(*b, k) for b in batches]          # nothing waits in between
+    got = [t.wait() for t in tickets]
+    torch.cuda.synchronize()
+    for b, g in zip(batches, got):
+        want = sh.search(*b, k)
+        assert int(g["status"].max().item()) == 0
+        for key in ("ids", "rrf_scores", "cos_ids", "cos_scores", "bm25_ids", "bm25_scores", "bm25_max"):
+            assert torch.equal(g[key], want[key]), key

@@ -193,7 +193,7 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu(built_lib):
     assert L.orag_version() == 1
     # size queries
     W = 2 * 10 + 2 * 16 + 2
-    assert L.orag_exchange_bytes(8, 256, 10, 16) == 256 + 2 * 8 * 256 * W * 8
+    assert L.orag_exchange_bytes(8, 256, 10, 16) == 256 + 4 * 8 * 256 * W * 8   # flags (padded) + four slots
     assert L.orag_exchange_bytes(0, 256, 10, 16) == 0
     assert L.orag_cosine_workspace_bytes(1000, 1536, 0, 10, _ffi.ORAG_COS_F16) == 0
     small = L.orag_cosine_workspace_bytes(1000, 1536, 4, 10, _ffi.ORAG_COS_EXACT)
