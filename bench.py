@@ -336,6 +336,27 @@ class Harness:
         self.clocks = self.sampler.stop()
         return (dev_ms, launches, brackets) if drained is None else (dev_ms, launches, brackets, drained)
 
+    def kernel_brackets(self, plain_step):
+        """Per-launch CUDA-event durations of the two dominant kernels over K PLAIN steps (one batch at a time, nothing
+        else in flight): the figures the rooflines are computed from.  (Inside the submitted loop above two batches
+        overlap, so a bracket there also measures the other batch's kernels competing for the SMs.)"""
+        L, torch = self.L, self.torch
+        for _ in range(3):
+            plain_step()
+        torch.cuda.synchronize()
+        L.orag_profile_enable(1)
+        for _ in range(self.args.steps):
+            plain_step()
+        torch.cuda.synchronize()
+        buf = (ctypes.c_float * 256)()
+        out = []
+        for slot in (0, 1):
+            n = int(L.orag_profile_read_all(slot, buf, 256))
+            out.append([float(buf[i]) for i in range(max(n, 0))])
+        L.orag_profile_enable(0)
+        self.barrier()
+        return out
+
     def e2e_timed(self, step_with_copies, drain=None):
         torch = self.torch
         self.barrier()
@@ -368,6 +389,11 @@ def bracket_stats(ms_list, per_step):
     return statistics.mean(xs), min(xs), len(xs)
 
 
+TIMING_NOTE = ("CUDA events on the launching stream around every launch of K plain steps run right after the timed loop "
+               "(mean; min alongside); `launch_ms_in_timed_loop` = the same bracket inside the timed loop, where two "
+               "submitted batches overlap")
+
+
 def tensor_roofline(flops_per_step, t_mean_ms, t_min_ms, n, pk, kernel, launches_per_step, traffic=None, extra=None):
     ach = flops_per_step / (t_mean_ms * 1e-3) / 1e12
     r = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
@@ -376,7 +402,7 @@ def tensor_roofline(flops_per_step, t_mean_ms, t_min_ms, n, pk, kernel, launches
          "peak_kind": "bf16 dense, measured: sustained (back-to-back 4 s) is `peak`, best-of-10 burst is `peak_burst`",
          "kernel": kernel, "peak_source": pk["source"], "launch_ms": t_mean_ms / launches_per_step,
          "launch_ms_min": t_min_ms / launches_per_step, "launches_per_step": launches_per_step, "samples": n,
-         "timing": "CUDA events on the launching stream around every launch of the timed loop (mean; min alongside)"}
+         "timing": TIMING_NOTE}
     if extra:
         r.update(extra)
     return r
@@ -388,7 +414,7 @@ def hbm_roofline(bytes_per_step, t_mean_ms, t_min_ms, n, pk, kernel, launches_pe
             "traffic": traffic, "bytes": what, "algorithmic_bytes": bytes_per_step, "kernel": kernel,
             "peak_source": pk["source"], "launch_ms": t_mean_ms / launches_per_step,
             "launch_ms_min": t_min_ms / launches_per_step, "launches_per_step": launches_per_step, "samples": n,
-            "timing": "CUDA events on the launching stream around every launch of the timed loop (mean; min alongside)"}
+            "timing": TIMING_NOTE}
 
 
 def traffic_for(key, rows_per_gpu, batch):
@@ -550,9 +576,10 @@ def run_hybrid_like(args):
         last["res"] = res
         return flags
 
-    dev_ms, launches, brackets, flags = h.device_timed(step, drain)
+    dev_ms, launches, brackets_overlapped, flags = h.device_timed(step, drain)
     if bool(torch.stack(flags).any()):
         raise SystemExit("bench: a candidate buffer overflowed inside the timed region; results would need the repair path")
+    brackets = h.kernel_brackets(lambda: sh.search(*devt, k, check_overflow=False))
 
     # ---- timed: end to end through the public call with HOST buffers, two batches in flight: while batch i computes,
     # the results of batch i-1 travel to the host and are read there (ONE host synchronisation per step)
@@ -608,6 +635,11 @@ def run_hybrid_like(args):
     pk = peaks()
     roof_scan = scan_rooflines(args, n_local, brackets, pk) if want_cos else None
     roof_bm = bm25_roofline(bm25, devt[-2], devt[-1], brackets, pk, n_local, Bq) if want_bm else None
+    groups = (Bq + 255) // 256
+    for roof, slot, per in ((roof_scan, 0, groups), (roof_bm, 1, 1)):
+        if roof is not None:
+            m = bracket_stats(brackets_overlapped[slot], per)[0]
+            roof["launch_ms_in_timed_loop"] = None if m is None else m / per
     value = Bq * args.steps / (dev_ms * 1e-3)
     line = {"metric": args.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": h.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -707,7 +739,9 @@ def run_pairwise(args):
                            None, {"flops_required": flops_required, "flops_executed": flops_executed,
                                   "flops": "executed = every 128x256 tile at or below the diagonal blocks; required = "
                                            "M(M-1)D for the strict upper triangle (SURVEY.md §8d)",
-                                  "frac_required_flops": flops_required / (mean * 1e-3) / 1e12 / pk["tf_sustained"]}) \
+                                  "frac_required_flops": flops_required / (mean * 1e-3) / 1e12 / pk["tf_sustained"],
+                                  "timing": "CUDA events on the launching stream around every launch of the timed loop "
+                                            "(mean; min alongside)"}) \
         if mean else None
     pairs = M * (M - 1) / 2
     line = {"metric": args.metric, "value": pairs * args.steps / (dev_ms * 1e-3), "unit": "pairs/s", "n_gpus": 1,

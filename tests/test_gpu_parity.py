@@ -344,7 +344,7 @@ def test_peer_exchange_kernels_two_virtual_ranks(eng):
     G, maxq, fk, kk, k = 2, 64, 10, 16, 10
     W = 2 * fk + 2 * kk + 2
     nbytes = int(L.orag_exchange_bytes(G, maxq, fk, kk))
-    assert nbytes == 256 + 2 * G * maxq * W * 8
+    assert nbytes == 256 + 4 * G * maxq * W * 8   # flags (padded) + four slots
     bufs = []
     for _ in range(G):
         p = ctypes.c_void_p()
