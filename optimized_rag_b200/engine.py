@@ -368,7 +368,8 @@ class HybridShard:
         self.bm25 = bm25
         self.rrf_k = rrf_k
         self._side: dict = {}   # lane -> side stream of the BM25 pipeline
-        self.coschedule = os.environ.get("ORAG_COSCHEDULE", "0") == "1"
+        # BM25 first pass NEXT TO the scan (see local_lists): ORAG_COSCHEDULE=0/1 forces it, default on
+        self.coschedule = os.environ.get("ORAG_COSCHEDULE", "1") == "1"
 
     def local_lists(self, query_emb: torch.Tensor, query_terms: torch.Tensor, query_lens: torch.Tensor, fetch_k: int,
                     bm25_k: int, normalize: bool, lane: int = 0):
@@ -394,9 +395,9 @@ class HybridShard:
         st_b: list = []
         if self.coschedule and self.cosine.mode != "exact":
             # the scan takes the SMs first; the BM25 first pass (8-warp CTAs, < 31 KB smem) then runs NEXT TO the
-            # resident scan CTA of every SM.  Measured on B200 at 10M x 256: one step 9.05 ms instead of 9.3, but in
-            # a sustained loop the GPU sits at its power cap and the overlap buys nothing (9.76 vs 9.63 ms/step),
-            # hence off by default (ORAG_COSCHEDULE=1 turns it on).
+            # resident scan CTA of every SM, on the issue slots the tensor-bound scan leaves idle.  Measured on B200
+            # with two batches in flight (bench.py --rows R): 1.25M rows 1.33 -> 1.28 ms/step, 2.5M 2.25 -> 2.20,
+            # 5M 4.11 -> 3.83 (ORAG_COSCHEDULE=0 turns it off).
             ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=False, status_out=st_c, lane=lane)
             with torch.cuda.stream(side):
                 _ffi.check(L.orag_stream_wait_prescan(side.cuda_stream), "orag_stream_wait_prescan")
