@@ -221,7 +221,8 @@ int orag_bm25_index_fill(const int64_t *d_doc_off, const int32_t *d_tokens, int6
                          const int32_t *d_fp_tile_term_off, uint32_t *d_postings_r16, float *d_term_max_r,
                          int32_t *d_info, void *d_workspace, size_t workspace_bytes, void *stream);
 
-/*   d_query_terms int32 [n_queries, max_terms], entries < 0 or >= vocab are OOV / padding
+/*   d_query_terms int32 [n_queries, max_terms], entries < 0 or >= vocab are OOV / padding; max_terms <= 64 on the
+ *   candidate paths, any length with ORAG_BM25_FORCE_DENSE and in orag_bm25_dense (per-document evaluation)
  *   d_query_lens  int32 [n_queries]
  *   outputs: top-k by (normalised score desc, id asc) with ORAG_BM25_NORMALIZE, and
  *   d_out_max[q] = the divisor the reference uses (max raw score, or 1.0 when that max is <= 0);

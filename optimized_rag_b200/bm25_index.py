@@ -264,6 +264,8 @@ class Bm25Index:
         assert query_terms.dtype == torch.int32 and query_lens.dtype == torch.int32
         assert query_terms.is_cuda and query_terms.is_contiguous() and query_lens.is_contiguous()
         Bq, mt = query_terms.shape
+        if mt > 64 and force != "dense":
+            force = "dense"   # the candidate kernels hold <= 64 terms per query; the dense path takes any length
         flags = (_ffi.ORAG_BM25_NORMALIZE if normalize else 0)
         flags |= {None: 0, "sparse": _ffi.ORAG_BM25_FORCE_SPARSE, "dense": _ffi.ORAG_BM25_FORCE_DENSE,
                   "exact_tiles": _ffi.ORAG_BM25_FORCE_SPARSE | _ffi.ORAG_BM25_EXACT_TILES}[force]

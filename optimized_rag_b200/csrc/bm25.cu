@@ -428,6 +428,31 @@ extern "C" size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *ix, int n_q
     return b > ms ? b : ms;
 }
 
+// Queries longer than kMaxTerms tokens (the tile kernels keep one term per lane slot): one thread per (query, doc)
+// walks the query's tokens in order and looks each up in the doc's tile (score_doc) -- the reference's arithmetic and
+// summation order for any query length, at O(tokens * log(run)) per document.
+__global__ void __launch_bounds__(256) dense_by_doc_kernel(orag_bm25_index_t ix, const int32_t *__restrict__ q_terms,
+                                                          const int32_t *__restrict__ q_lens, int n_queries,
+                                                          int max_terms, double *__restrict__ out)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_queries * ix.n_docs) return;
+    const int q = (int)(i / ix.n_docs);
+    const int64_t d = i - (int64_t)q * ix.n_docs;
+    const int nt = min(q_lens[q], max_terms);
+    out[i] = orag::bm25::score_doc(ix, q_terms + (int64_t)q * max_terms, nt, d);
+}
+
+static int launch_by_doc(const orag_bm25_index_t *ix, const int32_t *q_terms, const int32_t *q_lens, int n_queries,
+                         int max_terms, double *out, cudaStream_t st)
+{
+    const int64_t total = (int64_t)n_queries * ix->n_docs;
+    if (total == 0) return ORAG_OK;
+    dense_by_doc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(*ix, q_terms, q_lens, n_queries, max_terms, out);
+    ORAG_LAUNCH_CHECK();
+    return ORAG_OK;
+}
+
 static int launch_tiles(const Params &p, bool dense, cudaStream_t st)
 {
     const size_t smem = (size_t)orag::bm25::kWarps * ((size_t)p.ix.tile_docs * 10 + 2 * orag::bm25::kStage * 4) +
@@ -468,10 +493,11 @@ extern "C" int orag_bm25_dense(const orag_bm25_index_t *ix, const int32_t *d_que
 {
     int rc = validate_index(ix);
     if (rc) return rc;
-    ORAG_REQUIRE(d_query_terms && d_query_lens && d_out && n_queries > 0, "bm25_dense");
-    ORAG_REQUIRE(max_terms > 0 && max_terms <= orag::bm25::kMaxTerms, "max_terms in [1, 64]");
+    ORAG_REQUIRE(d_query_terms && d_query_lens && d_out && n_queries > 0 && max_terms > 0, "bm25_dense");
     cudaStream_t st = (cudaStream_t)stream;
     if (ix->n_docs == 0) return ORAG_OK;
+    if (max_terms > orag::bm25::kMaxTerms)  // long queries: per-document evaluation, any length
+        return launch_by_doc(ix, d_query_terms, d_query_lens, n_queries, max_terms, d_out, st);
     ORAG_CUDA_CHECK(cudaMemsetAsync(d_out, 0, (size_t)n_queries * ix->n_docs * sizeof(double), st));
     Params p{};
     p.ix = *ix;
@@ -491,8 +517,10 @@ extern "C" int orag_bm25_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, 
 {
     int rc = validate_index(ix);
     if (rc) return rc;
-    ORAG_REQUIRE(d_query_terms && d_query_lens && d_out_ids && d_out_scores && n_queries > 0 && k > 0, "bm25_topk");
-    ORAG_REQUIRE(max_terms > 0 && max_terms <= orag::bm25::kMaxTerms, "max_terms in [1, 64]");
+    ORAG_REQUIRE(d_query_terms && d_query_lens && d_out_ids && d_out_scores && n_queries > 0 && k > 0 && max_terms > 0,
+                 "bm25_topk");
+    ORAG_REQUIRE(max_terms <= orag::bm25::kMaxTerms || (flags & ORAG_BM25_FORCE_DENSE),
+                 "queries longer than 64 tokens take the dense path: pass ORAG_BM25_FORCE_DENSE");
     cudaStream_t st = (cudaStream_t)stream;
     const int normalize = (flags & ORAG_BM25_NORMALIZE) ? 1 : 0;
     if (workspace_bytes < orag_bm25_workspace_bytes(ix, n_queries, k, flags) || (!d_workspace && ix->n_docs > 0)) {
@@ -507,7 +535,10 @@ extern "C" int orag_bm25_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, 
         double *dense = (double *)d_workspace;
         for (int q0 = 0; q0 < n_queries; q0 += chunk) {
             const int nq = (n_queries - q0) < chunk ? (n_queries - q0) : chunk;
-            if (ix->n_docs > 0) {
+            if (ix->n_docs > 0 && max_terms > orag::bm25::kMaxTerms) {
+                rc = launch_by_doc(ix, d_query_terms + (int64_t)q0 * max_terms, d_query_lens + q0, nq, max_terms, dense, st);
+                if (rc) return rc;
+            } else if (ix->n_docs > 0) {
                 ORAG_CUDA_CHECK(cudaMemsetAsync(dense, 0, (size_t)nq * ix->n_docs * sizeof(double), st));
                 Params p{};
                 p.ix = *ix;

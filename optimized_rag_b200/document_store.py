@@ -64,7 +64,13 @@ class TextVocab:
 
 
 class ChunkTable:
-    """All chunks of one agent: host records + device embeddings + lazily built GPU indices."""
+    """All chunks of one agent: host records + device embeddings + GPU indices.
+
+    The cosine side is maintained INCREMENTALLY: the fp32 rows, their fp16 shadow, inverse norms and float64 sum(a*a)
+    live in capacity-doubling device buffers and only the rows that arrive are converted (`extend`); deleting a
+    document compacts all four with one gather each.  The BM25 side cannot be appended to -- every impact depends on
+    the corpus-wide avgdl and every idf on N and df -- so it is rebuilt by the library's builder (csrc/bm25_build.cu,
+    ~0.05 s per million chunks) the first time a search needs it after a change."""
 
     def __init__(self, dim: int, device: torch.device, tile_docs: int = 1024):
         self.dim = dim
@@ -73,33 +79,61 @@ class ChunkTable:
         self.records: List[Dict[str, Any]] = []     # content, metadata, filename, file_type, document_id, chunk_index
         self.tokens: List[np.ndarray] = []
         self.vocab = TextVocab()
-        self._emb = torch.empty((0, dim), dtype=torch.float32, device=device)
         self._n = 0
+        self._alloc(0)
         self._cosine: Optional[engine.CosineIndex] = None
         self._bm25: Optional[Bm25Index] = None
+
+    def _alloc(self, cap: int):
+        dev = self.device
+        self._emb = torch.empty((cap, self.dim), dtype=torch.float32, device=dev)
+        self._shadow = torch.empty((cap, self.dim), dtype=torch.float16, device=dev)
+        self._inv_norm = torch.empty(cap, dtype=torch.float32, device=dev)
+        self._row_sq = torch.empty(cap, dtype=torch.float64, device=dev)
+
+    def _arrays(self):
+        return self._emb, self._shadow, self._inv_norm, self._row_sq
 
     def __len__(self):
         return self._n
 
-    def append(self, record: Dict[str, Any], embedding: np.ndarray):
-        if self._n == self._emb.shape[0]:
-            cap = max(256, 2 * self._emb.shape[0])
-            grown = torch.empty((cap, self.dim), dtype=torch.float32, device=self.device)
-            grown[:self._n] = self._emb[:self._n]
-            self._emb = grown
-        self._emb[self._n] = torch.from_numpy(np.ascontiguousarray(embedding, dtype=np.float32)).to(self.device)
-        self.records.append(record)
-        self.tokens.append(self.vocab.encode_doc(record["content"]))
-        self._n += 1
+    @property
+    def shadow_usable(self) -> bool:
+        return self.dim % 64 == 0
+
+    def extend(self, records: List[Dict[str, Any]], embeddings: np.ndarray):
+        """Append chunks (records[i] <-> embeddings[i], fp32 [m, dim]); converts only the new rows."""
+        m = len(records)
+        if m == 0:
+            return
+        embeddings = np.ascontiguousarray(embeddings, dtype=np.float32).reshape(m, self.dim)
+        n0, n1 = self._n, self._n + m
+        if n1 > self._emb.shape[0]:
+            old = self._arrays()
+            self._alloc(max(256, 2 * self._emb.shape[0], n1))
+            for new, prev in zip(self._arrays(), old):
+                new[:n0] = prev[:n0]
+        self._emb[n0:n1] = torch.from_numpy(embeddings).to(self.device)
+        if self.shadow_usable:
+            engine.CosineIndex.derive_rows(self._emb[n0:n1], self._shadow[n0:n1], self._inv_norm[n0:n1],
+                                           self._row_sq[n0:n1])
+        self.records.extend(records)
+        self.tokens.extend(self.vocab.encode_doc(r["content"]) for r in records)
+        self._n = n1
         self._cosine = self._bm25 = None
+
+    def append(self, record: Dict[str, Any], embedding: np.ndarray):
+        self.extend([record], np.asarray(embedding, dtype=np.float32)[None, :])
 
     def remove_document(self, document_id: int) -> int:
         keep = [i for i, r in enumerate(self.records) if r["document_id"] != document_id]
         removed = self._n - len(keep)
         if removed:
             idx = torch.tensor(keep, dtype=torch.int64, device=self.device)
-            self._emb = self._emb[:self._n][idx].contiguous() if keep else \
-                torch.empty((0, self.dim), dtype=torch.float32, device=self.device)
+            old = self._arrays()
+            self._alloc(max(256, len(keep)))
+            for new, prev in zip(self._arrays(), old):
+                new[:len(keep)] = prev[:self._n][idx]
             self.records = [self.records[i] for i in keep]
             self.tokens = [self.tokens[i] for i in keep]
             self._n = len(keep)
@@ -107,20 +141,39 @@ class ChunkTable:
         return removed
 
     def cosine(self) -> engine.CosineIndex:
+        """Exact scan for small tables, fp16 tensor-core first pass over the incrementally kept shadow otherwise (a
+        view: nothing is recomputed)."""
         if self._cosine is None:
-            self._cosine = engine.CosineIndex(self._emb[:self._n].contiguous(), mode="auto")
+            n = self._n
+            if n < engine.SMALL_N or not self.shadow_usable:
+                self._cosine = engine.CosineIndex.from_arrays(self._emb[:n], None, None, None, "exact")
+            else:
+                self._cosine = engine.CosineIndex.from_arrays(self._emb[:n], self._inv_norm[:n], self._shadow[:n],
+                                                              self._row_sq[:n], "f16")
         return self._cosine
+
+    def token_arrays(self):
+        lens = np.asarray([len(t) for t in self.tokens], dtype=np.int64)
+        off = np.zeros(self._n + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        toks = np.concatenate(self.tokens) if self._n and off[-1] > 0 else np.zeros(0, dtype=np.int32)
+        return off, toks.astype(np.int32)
 
     def bm25(self) -> Bm25Index:
         if self._bm25 is None:
-            lens = np.asarray([len(t) for t in self.tokens], dtype=np.int64)
-            off = np.zeros(self._n + 1, dtype=np.int64)
-            np.cumsum(lens, out=off[1:])
-            toks = np.concatenate(self.tokens) if self._n and off[-1] > 0 else np.zeros(0, dtype=np.int32)
-            self._bm25 = Bm25Index(torch.from_numpy(off).to(self.device),
-                                   torch.from_numpy(toks.astype(np.int32)).to(self.device), max(len(self.vocab), 1),
-                                   tile_docs=self.tile_docs)
+            off, toks = self.token_arrays()
+            self._bm25 = Bm25Index(torch.from_numpy(off).to(self.device), torch.from_numpy(toks).to(self.device),
+                                   max(len(self.vocab), 1), tile_docs=self.tile_docs)
         return self._bm25
+
+    def adopt_bm25(self, index: Bm25Index) -> bool:
+        """Use a saved index instead of rebuilding, if it describes exactly this table's chunks."""
+        off, _ = self.token_arrays()
+        if index.n_docs != self._n or index.vocab != max(len(self.vocab), 1) or index.tile_docs != self.tile_docs or \
+                index.stats.total_len != int(off[-1]):
+            return False
+        self._bm25 = index
+        return True
 
 
 class DocumentStore:
@@ -163,9 +216,12 @@ class DocumentStore:
             t = self._tables[agent_id] = ChunkTable(self.embedding_dim, self.device)
         return t
 
-    @_gpu_locked
     def upload_and_index(self, agent_id: str, file_path: str, file_content: Optional[str] = None,
                          metadata: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+        """Wrangle, chunk, embed and validate FIRST (no lock, nothing changed yet -- these are the slow, fallible steps:
+        the reference generates its embeddings before it opens the transaction that deletes and inserts,
+        rag/document_store.py:317-389); only then, under the lock, replace the document's chunks in one step.  A failure
+        anywhere before that leaves an earlier upload of the same file fully searchable."""
         try:
             file_path_obj = Path(file_path)
             filename = file_path_obj.name
@@ -178,41 +234,44 @@ class DocumentStore:
                 content, quality_score, extracted = raw, None, {}
             full_metadata = {**extracted, **(metadata or {})}
             content = content.replace('\x00', '')
-            # same (agent, filename) replaces the earlier upload (ON CONFLICT ... DO UPDATE in the reference)
-            document_id = next((d for d, r in self._documents.items()
-                                if r["agent_id"] == agent_id and r["filename"] == filename), None)
-            table = self._table(agent_id)
-            if document_id is None:
-                document_id = self._next_doc_id
-                self._next_doc_id += 1
-            else:
-                table.remove_document(document_id)
-            self._documents[document_id] = {"agent_id": agent_id, "filename": filename, "file_type": file_type,
-                                            "quality_score": quality_score, "metadata": full_metadata,
-                                            "uploaded_at": datetime.now(timezone.utc)}
             chunks = self.chunker.chunk(content)
-            if len(chunks) == 0:
-                return {"document_id": document_id, "filename": filename, "chunk_count": 0, "chunks_created": 0,
-                        "chunks_skipped": 0, "quality_score": quality_score, "success": True,
-                        "error": "No chunks generated from document"}
-            embeddings = self.embeddings.generate_embeddings_batch([c['content'] for c in chunks])
-            inserted = skipped = 0
-            for i, (chunk, emb) in enumerate(zip(chunks, embeddings)):
-                if emb is None or len(emb) == 0:
-                    logger.warning(f"Skipping chunk {i}: empty embedding")
-                    skipped += 1
-                    continue
-                if any(math.isnan(v) or math.isinf(v) for v in emb):
-                    logger.warning(f"Skipping chunk {i}: embedding contains NaN or Inf")
-                    skipped += 1
-                    continue
-                if len(emb) != self.embedding_dim:
-                    raise ValueError(f"embedding dimension {len(emb)} != {self.embedding_dim}")
-                table.append({"content": chunk['content'].replace('\x00', ''),
-                              "metadata": {**full_metadata, **(chunk.get('metadata', {}))},
-                              "filename": filename, "file_type": file_type, "document_id": document_id,
-                              "chunk_index": i}, np.asarray(emb, dtype=np.float32))
-                inserted += 1
+            records, rows, skipped = [], [], 0
+            if len(chunks) > 0:
+                embeddings = self.embeddings.generate_embeddings_batch([c['content'] for c in chunks])
+                for i, (chunk, emb) in enumerate(zip(chunks, embeddings)):
+                    if emb is None or len(emb) == 0:
+                        logger.warning(f"Skipping chunk {i}: empty embedding")
+                        skipped += 1
+                        continue
+                    if any(math.isnan(v) or math.isinf(v) for v in emb):
+                        logger.warning(f"Skipping chunk {i}: embedding contains NaN or Inf")
+                        skipped += 1
+                        continue
+                    if len(emb) != self.embedding_dim:
+                        raise ValueError(f"embedding dimension {len(emb)} != {self.embedding_dim}")
+                    records.append({"content": chunk['content'].replace('\x00', ''),
+                                    "metadata": {**full_metadata, **(chunk.get('metadata', {}))},
+                                    "filename": filename, "file_type": file_type, "chunk_index": i})
+                    rows.append(np.asarray(emb, dtype=np.float32))
+            with _ffi.GPU_LOCK:
+                # same (agent, filename) replaces the earlier upload (ON CONFLICT ... DO UPDATE in the reference)
+                document_id = next((d for d, r in self._documents.items()
+                                    if r["agent_id"] == agent_id and r["filename"] == filename), None)
+                if document_id is None:
+                    document_id = self._next_doc_id
+                    self._next_doc_id += 1
+                self._documents[document_id] = {"agent_id": agent_id, "filename": filename, "file_type": file_type,
+                                                "quality_score": quality_score, "metadata": full_metadata,
+                                                "uploaded_at": datetime.now(timezone.utc)}
+                if len(chunks) == 0:   # the reference returns before it touches any chunk row
+                    return {"document_id": document_id, "filename": filename, "chunk_count": 0, "chunks_created": 0,
+                            "chunks_skipped": 0, "quality_score": quality_score, "success": True,
+                            "error": "No chunks generated from document"}
+                table = self._table(agent_id)
+                table.remove_document(document_id)
+                for r in records:
+                    r["document_id"] = document_id
+                table.extend(records, np.stack(rows) if rows else np.zeros((0, self.embedding_dim), np.float32))
             if self.kg_extractor:
                 try:
                     triples = self.kg_extractor.extract_triples(text=content, source_doc_id=document_id, max_triples=20)
@@ -220,7 +279,7 @@ class DocumentStore:
                 except Exception as e:  # noqa: BLE001 - mirrors the reference's blanket handler
                     logger.warning(f"KG extraction failed: {e}")
             return {"document_id": document_id, "filename": filename, "chunk_count": len(chunks),
-                    "chunks_created": inserted, "chunks_skipped": skipped, "quality_score": quality_score,
+                    "chunks_created": len(records), "chunks_skipped": skipped, "quality_score": quality_score,
                     "success": True}
         except Exception as e:  # noqa: BLE001
             logger.error(f"Upload and index failed: {e}")
@@ -232,65 +291,79 @@ class DocumentStore:
         return {"content": rec["content"], "filename": rec["filename"], "file_type": rec["file_type"],
                 "score": float(score), "metadata": dict(rec["metadata"])}
 
-    @_gpu_locked
     def search(self, agent_id: str, query: str, top_k: int = 5) -> List[Dict[str, Any]]:
         """Search document chunks (rag/document_store.py:424-485)."""
         try:
             if self.retrieval_mode == "hybrid":
                 return self.hybrid_search(agent_id, query, top_k)
-            query_embedding = self.embeddings.generate_embedding(query)
-            table = self._tables.get(agent_id)
-            if table is None or len(table) == 0 or top_k <= 0:
-                return []
-            q = torch.tensor([query_embedding], dtype=torch.float32, device=self.device)
-            ids, scores = table.cosine().topk(q, min(top_k, len(table)))
-            return [self._result(table.records[i], s)
-                    for i, s in zip(ids[0].cpu().tolist(), scores[0].cpu().tolist()) if i >= 0]
+            query_embedding = self.embeddings.generate_embedding(query)   # (a network call in the reference: no lock)
+            with _ffi.GPU_LOCK:
+                return self._semantic(agent_id, query_embedding, top_k)
         except Exception as e:  # noqa: BLE001
             logger.error(f"Search failed: {e}")
             return []
 
-    @_gpu_locked
+    def _semantic(self, agent_id: str, query_embedding, top_k: int) -> List[Dict[str, Any]]:
+        table = self._tables.get(agent_id)
+        if table is None or len(table) == 0 or top_k <= 0:
+            return []
+        q = torch.tensor([query_embedding], dtype=torch.float32, device=self.device)
+        k = min(top_k, len(table))
+        index = table.cosine()
+        # the tensor-core first pass keeps at most 128 winners per query: larger requests take the exact scan
+        ids, scores = index.topk(q, k, mode="exact" if k > 128 else None)
+        return [self._result(table.records[i], s)
+                for i, s in zip(ids[0].cpu().tolist(), scores[0].cpu().tolist()) if i >= 0]
+
     def hybrid_search(self, agent_id: str, query: str, top_k: int = 5, fetch_k: Optional[int] = None
                       ) -> List[Dict[str, Any]]:
         """Cosine top-fetch_k + BM25 top-fetch_k -> RRF top_k, all on the GPU."""
         try:
             query_embedding = self.embeddings.generate_embedding(query)
-            table = self._tables.get(agent_id)
-            if table is None or len(table) == 0 or top_k <= 0:
-                return []
-            n = len(table)
-            fetch_k = min(fetch_k or max(top_k, 10), n)
-            q = torch.tensor([query_embedding], dtype=torch.float32, device=self.device)
-            terms = table.vocab.encode_query(query)
-            qt = torch.from_numpy(terms if len(terms) else np.full(1, -1, np.int32)).to(self.device)[None, :].contiguous()
-            ql = torch.tensor([len(terms)], dtype=torch.int32, device=self.device)
-            shard = engine.HybridShard(table.cosine(), table.bm25(), self.rrf_k)
-            res = shard.search(q, qt, ql, k=min(top_k, n), fetch_k=fetch_k)
-            ids = res["ids"][0].cpu().tolist()
-            rrf = res["rrf_scores"][0].cpu().tolist()
-            src = res["src_ranks"][0].cpu().tolist()
-            cos_of = dict(zip(res["cos_ids"][0].cpu().tolist(), res["cos_scores"][0].cpu().tolist()))
-            kw_of = dict(zip(res["bm25_ids"][0].cpu().tolist(), res["bm25_scores"][0].cpu().tolist()))
-            missing = [i for i in ids if i >= 0 and i not in cos_of]
-            if missing:  # fused items that came from the BM25 list only: their cosine, same float64 arithmetic
-                sub = engine.CosineIndex(table._emb[torch.tensor(missing, device=self.device)].contiguous(), mode="exact")
-                for i, s in zip(missing, sub.dense(q)[0].cpu().tolist()):
-                    cos_of[i] = s
-            out = []
-            for i, r, sr in zip(ids, rrf, src):
-                if i < 0:
-                    continue
-                d = self._result(table.records[i], cos_of[i])
-                d["rrf_score"] = r
-                d["keyword_score"] = kw_of.get(i)
-                d["semantic_rank"] = sr[0] or None
-                d["keyword_rank"] = sr[1] or None
-                out.append(d)
-            return out
+            with _ffi.GPU_LOCK:
+                return self._hybrid(agent_id, query, query_embedding, top_k, fetch_k)
         except Exception as e:  # noqa: BLE001
             logger.error(f"Hybrid search failed: {e}")
             return []
+
+    def _hybrid(self, agent_id, query, query_embedding, top_k, fetch_k):
+        table = self._tables.get(agent_id)
+        if table is None or len(table) == 0 or top_k <= 0:
+            return []
+        n = len(table)
+        fetch_k = min(fetch_k or max(top_k, 10), n)
+        if fetch_k > 64 or min(top_k, n) > 64:
+            # the fusion kernel holds two lists of at most 64: beyond that the semantic ranking alone is returned
+            logger.warning("hybrid search: top_k above 64 is served by the semantic ranking only")
+            return self._semantic(agent_id, query_embedding, top_k)
+        q = torch.tensor([query_embedding], dtype=torch.float32, device=self.device)
+        terms = table.vocab.encode_query(query)
+        terms = terms[terms >= 0]   # out-of-vocabulary tokens score an exact 0.0 (rank_bm25: `idf.get(q) or 0`)
+        qt = torch.from_numpy(terms if len(terms) else np.full(1, -1, np.int32)).to(self.device)[None, :].contiguous()
+        ql = torch.tensor([len(terms)], dtype=torch.int32, device=self.device)
+        shard = engine.HybridShard(table.cosine(), table.bm25(), self.rrf_k)
+        res = shard.search(q, qt, ql, k=min(top_k, n), fetch_k=fetch_k)
+        ids = res["ids"][0].cpu().tolist()
+        rrf = res["rrf_scores"][0].cpu().tolist()
+        src = res["src_ranks"][0].cpu().tolist()
+        cos_of = dict(zip(res["cos_ids"][0].cpu().tolist(), res["cos_scores"][0].cpu().tolist()))
+        kw_of = dict(zip(res["bm25_ids"][0].cpu().tolist(), res["bm25_scores"][0].cpu().tolist()))
+        missing = [i for i in ids if i >= 0 and i not in cos_of]
+        if missing:  # fused items that came from the BM25 list only: their cosine, same float64 arithmetic
+            sub = engine.CosineIndex(table._emb[torch.tensor(missing, device=self.device)].contiguous(), mode="exact")
+            for i, s in zip(missing, sub.dense(q)[0].cpu().tolist()):
+                cos_of[i] = s
+        out = []
+        for i, r, sr in zip(ids, rrf, src):
+            if i < 0:
+                continue
+            d = self._result(table.records[i], cos_of[i])
+            d["rrf_score"] = r
+            d["keyword_score"] = kw_of.get(i)
+            d["semantic_rank"] = sr[0] or None
+            d["keyword_rank"] = sr[1] or None
+            out.append(d)
+        return out
 
     # ------------------------------------------------------------------ persistence
     # The reference's "format" is Postgres rows (DDL rag/document_store.py:190-221).  Here: one directory per store,
@@ -306,7 +379,10 @@ class DocumentStore:
         for n, (agent_id, t) in enumerate(sorted(self._tables.items())):
             fname = f"agent{n}.emb.f32"
             t._emb[:len(t)].cpu().numpy().astype("<f4").tofile(d / fname)
-            agents[agent_id] = {"file": fname, "n": len(t), "records": t.records}
+            agents[agent_id] = {"file": fname, "n": len(t), "records": t.records, "bm25": None}
+            if len(t) > 0:   # the keyword index as it sits in HBM: adopted by `load` instead of a rebuild
+                t.bm25().save(d / f"agent{n}.bm25")
+                agents[agent_id]["bm25"] = f"agent{n}.bm25"
         docs = {str(k): {**v, "uploaded_at": v["uploaded_at"].isoformat()} for k, v in self._documents.items()}
         (d / "store.json").write_text(json.dumps({"version": 1, "dim": self.embedding_dim, "next_doc_id": self._next_doc_id,
                                                   "documents": docs, "agents": agents}))
@@ -325,8 +401,13 @@ class DocumentStore:
         for agent_id, a in meta["agents"].items():
             t = self._table(agent_id)
             emb = np.fromfile(d / a["file"], dtype="<f4").reshape(a["n"], self.embedding_dim)
-            for rec, row in zip(a["records"], emb):
-                t.append(rec, row)
+            t.extend(a["records"], emb)   # one copy + one conversion launch for the whole table
+            if a.get("bm25"):
+                try:
+                    if not t.adopt_bm25(Bm25Index.load(d / a["bm25"], device=self.device)):
+                        logger.warning(f"saved keyword index of {agent_id} does not match its chunks: it will be rebuilt")
+                except (OSError, ValueError) as e:
+                    logger.warning(f"saved keyword index of {agent_id} unusable ({e}): it will be rebuilt")
 
     # ------------------------------------------------------------------ bookkeeping (rag/document_store.py:487-542)
     @_gpu_locked

@@ -99,6 +99,37 @@ class CosineIndex:
                                               _stream(self.device)), "orag_row_sq")
         self._ws = {}
 
+    @classmethod
+    def from_arrays(cls, corpus: torch.Tensor, inv_norm: torch.Tensor | None, shadow: torch.Tensor | None,
+                    row_sq: torch.Tensor | None, mode: str, row_id_base: int = 0) -> "CosineIndex":
+        """A view over arrays the caller maintains itself (e.g. row by row as chunks arrive: `derive_rows`) -- nothing
+        is recomputed here.  `mode` "exact" needs only the corpus; "f16" / "bf16" the 16-bit shadow + scaled inverse
+        norms + row_sq; "tf32" the inverse norms + row_sq."""
+        _require_cuda(corpus, "corpus")
+        assert corpus.dtype == torch.float32 and corpus.dim() == 2 and corpus.is_contiguous() and mode in MODE
+        self = cls.__new__(cls)
+        self.corpus, self.device = corpus, corpus.device
+        self.n_rows, self.dim = corpus.shape
+        self.row_id_base, self.mode = int(row_id_base), mode
+        self.inv_norm, self.shadow, self.row_sq = inv_norm, shadow, row_sq
+        if mode != "exact":
+            assert inv_norm is not None and row_sq is not None and inv_norm.shape[0] == self.n_rows
+            assert mode == "tf32" or (shadow is not None and shadow.shape == corpus.shape)
+        self._ws = {}
+        return self
+
+    @staticmethod
+    def derive_rows(corpus: torch.Tensor, shadow_f16: torch.Tensor, inv_norm: torch.Tensor, row_sq: torch.Tensor):
+        """Fill the derived arrays of the "f16" mode for the given rows (all four tensors are row-aligned slices):
+        fp16 shadow scaled by powers of two + its inverse norms (orag_f32_to_f16_rows) and the float64 sum(a*a)."""
+        n, dim = corpus.shape
+        if n == 0:
+            return
+        st = _stream(corpus.device)
+        _ffi.check(_ffi.lib().orag_f32_to_f16_rows(corpus.data_ptr(), n, dim, shadow_f16.data_ptr(), inv_norm.data_ptr(),
+                                                   None, st), "orag_f32_to_f16_rows")
+        _ffi.check(_ffi.lib().orag_row_sq(corpus.data_ptr(), n, dim, row_sq.data_ptr(), st), "orag_row_sq")
+
     def _workspace(self, n_queries: int, k: int, mode: int, lane: int = 0) -> torch.Tensor:
         """One workspace per (mode, lane): calls of different lanes may be in flight at the same time (see
         dist.ShardedHybrid.submit), a workspace belongs to one call until its work has finished."""

@@ -145,8 +145,7 @@ class HybridRetriever:
             return torch.zeros(n, dtype=torch.float64, device=self.device)
         ix, vocab = self._bm25_index(corpus)
         terms = vocab.encode_query(query)
-        if len(terms) > 64:
-            raise ValueError("queries longer than 64 tokens are not supported by orag_bm25_dense")
+        terms = terms[terms >= 0]   # out-of-vocabulary tokens add an exact 0.0; any length is fine (orag_bm25_dense)
         qt = torch.from_numpy(terms if len(terms) else np.full(1, -1, np.int32)).to(self.device)[None, :].contiguous()
         ql = torch.tensor([len(terms)], dtype=torch.int32, device=self.device)
         raw = ix.dense_scores(qt, ql)[0].contiguous()

@@ -291,3 +291,116 @@ def test_mmr_diversifier_matches_oracle():
     assert MMRDiversifier(device="cuda:0").diversify([1.0, 2.0], [], 3) == []
     only_bad = [{"content": "x"}, {"content": "y", "embedding": []}]
     assert MMRDiversifier(device="cuda:0").diversify([1.0, 2.0], only_bad, 1) == only_bad[:1]
+
+
+# ------------------------------------------------------------------------------------------------ ingest robustness
+class _FlakyEmbeddings:
+    """SyntheticEmbeddingService that can be told to fail (a network error in the reference's real service)."""
+
+    def __init__(self):
+        from optimized_rag_b200.embeddings import SyntheticEmbeddingService
+        self._inner = SyntheticEmbeddingService()
+        self.fail = False
+
+    def get_embedding_dimension(self):
+        return self._inner.get_embedding_dimension()
+
+    def generate_embedding(self, text):
+        return self._inner.generate_embedding(text)
+
+    def generate_embeddings_batch(self, texts):
+        if self.fail:
+            raise RuntimeError("embedding service unavailable")
+        return self._inner.generate_embeddings_batch(texts)
+
+
+def test_failed_reupload_keeps_the_old_chunks_searchable():
+    """rag/document_store.py:317-389 embeds before it opens the DELETE + INSERT transaction: a re-upload that fails
+    (embedding service down, wrong dimension) or that yields no chunks must leave the earlier upload intact."""
+    from optimized_rag_b200.document_store import DocumentStore
+    emb = _FlakyEmbeddings()
+    st = DocumentStore(None, emb, WordChunker(), device="cuda:0")
+    first = st.upload_and_index("a", "/tmp/report.txt", file_content="alpha beta gamma delta " * 10)
+    assert first["success"] and first["chunks_created"] > 0
+    before = st.search("a", "alpha beta", 3)
+    assert before
+    emb.fail = True
+    bad = st.upload_and_index("a", "/tmp/report.txt", file_content="completely new words here " * 10)
+    assert bad["success"] is False and "unavailable" in bad["error"]
+    emb.fail = False
+    assert st.search("a", "alpha beta", 3) == before and len(st.list_documents("a")) == 1
+    empty = st.upload_and_index("a", "/tmp/report.txt", file_content="   ")
+    assert empty["success"] and empty["chunk_count"] == 0 and empty["document_id"] == first["document_id"]
+    assert st.search("a", "alpha beta", 3) == before              # "No chunks generated": nothing was deleted
+    # a successful re-upload replaces the chunks in one step
+    good = st.upload_and_index("a", "/tmp/report.txt", file_content="completely new words here " * 10)
+    assert good["success"] and good["document_id"] == first["document_id"]
+    after = st.search("a", "alpha beta", 3)
+    assert after and all("alpha" not in r["content"] for r in after)
+
+
+def test_incremental_table_equals_a_fresh_index_and_large_k(store):
+    """Chunks arrive upload by upload (only new rows are converted), one document is deleted in between: the table's
+    cosine view must answer exactly like an index built from scratch over the same rows -- on the tensor-core path
+    (>= 4096 chunks) as well -- and top_k beyond the kernels' list limits is still served."""
+    from optimized_rag_b200.document_store import DocumentStore
+    from optimized_rag_b200.embeddings import SyntheticEmbeddingService
+    from optimized_rag_b200 import engine
+    st = DocumentStore(None, SyntheticEmbeddingService(dimensions=128), WordChunker(words=3), device="cuda:0")
+    texts = _corpus_text(n_docs=300, seed=11)
+    for d, text in enumerate(texts):
+        assert st.upload_and_index("big", f"/tmp/f{d}.txt", file_content=text)["success"]
+    assert st.delete_document("big", 7)
+    table = st._tables["big"]
+    assert len(table) >= engine.SMALL_N and table.cosine().mode == "f16"
+    fresh = engine.CosineIndex(table._emb[:len(table)].clone(), mode="f16")
+    q = torch.tensor([st.embeddings.generate_embedding("w3 w7 unique5"), st.embeddings.generate_embedding("w1 w2")],
+                     dtype=torch.float32, device="cuda:0")
+    a, b = table.cosine().topk(q, 10), fresh.topk(q, 10)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    emb = table._emb[:len(table)].cpu().numpy()
+    wi, wv = oracle.topk(oracle.cosine_scores(emb, q[0].cpu().numpy()), 200)
+    res = st.search("big", "w3 w7 unique5", top_k=200)            # > 128: the exact scan takes over
+    assert [r["score"] for r in res] == wv.tolist()
+    assert len(st.hybrid_search("big", "w3 w7 unique5", top_k=100)) == 100   # > 64: semantic ranking, not []
+
+
+def test_queries_longer_than_64_words_through_the_drop_ins(store):
+    """The reference handles any query length (rag/retrieval.py:334-341); the candidate kernels hold 64 terms, longer
+    queries take the per-document dense kernel -- same float64 scores as the oracle."""
+    from optimized_rag_b200.retrieval import HybridRetriever
+    table = store._tables["agent-a"]
+    words = [f"w{i % 37}" for i in range(90)] + ["unique5", "notinvocab"]
+    query = " ".join(words)
+    res = store.hybrid_search("agent-a", query, top_k=5)
+    assert len(res) == 5 and all(r["keyword_score"] is None or 0.0 <= r["keyword_score"] <= 1.0 for r in res)
+    off, toks = table.token_arrays()
+    orc = oracle.BM25Index(off, toks, len(table.vocab))
+    q_ids = table.vocab.encode_query(query)
+    want, m = orc.scores(q_ids[q_ids >= 0])
+    wi, wv = oracle.topk(want, 10)
+    kw = {r["content"]: r["keyword_score"] for r in res if r["keyword_rank"]}
+    for i, v in zip(wi, wv):
+        c = table.records[i]["content"]
+        if c in kw:
+            assert kw[c] == v
+    hr = HybridRetriever(None, store, "agent-a")
+    corpus = [r["content"] for r in table.records[:50]]
+    got = hr._bm25_scores(query, corpus)
+    import oracle.rank_bm25 as rb
+    ref = rb.BM25Okapi([d.lower().split() for d in corpus]).get_scores(query.lower().split())
+    mx = max(ref) if len(ref) and max(ref) > 0 else 1.0
+    assert got == [float(s / mx) for s in ref]
+
+
+def test_load_adopts_the_saved_keyword_index(store, tmp_path):
+    from optimized_rag_b200.document_store import DocumentStore
+    store.hybrid_search("agent-a", "w3 w7", 5)      # makes sure the index exists
+    store.save(str(tmp_path))
+    back = DocumentStore(None, store.embeddings, WordChunker(), device="cuda:0", retrieval_mode="hybrid")
+    back.load(str(tmp_path))
+    t = back._tables["agent-a"]
+    assert t._bm25 is not None and t._bm25.n_docs == len(t)      # adopted, not rebuilt
+    a = store.hybrid_search("agent-a", "w3 w7 unique5", 5)
+    b = back.hybrid_search("agent-a", "w3 w7 unique5", 5)
+    assert a == b and a
