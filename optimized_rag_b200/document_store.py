@@ -379,7 +379,10 @@ class DocumentStore:
         for n, (agent_id, t) in enumerate(sorted(self._tables.items())):
             fname = f"agent{n}.emb.f32"
             t._emb[:len(t)].cpu().numpy().astype("<f4").tofile(d / fname)
-            agents[agent_id] = {"file": fname, "n": len(t), "records": t.records, "bm25": None}
+            # the vocabulary in id order: ids are assigned in first-seen order and survive deletions, so the saved
+            # keyword index is only meaningful together with the very mapping it was built under
+            agents[agent_id] = {"file": fname, "n": len(t), "records": t.records, "bm25": None,
+                                "vocab": list(t.vocab.ids)}
             if len(t) > 0:   # the keyword index as it sits in HBM: adopted by `load` instead of a rebuild
                 t.bm25().save(d / f"agent{n}.bm25")
                 agents[agent_id]["bm25"] = f"agent{n}.bm25"
@@ -401,6 +404,7 @@ class DocumentStore:
         for agent_id, a in meta["agents"].items():
             t = self._table(agent_id)
             emb = np.fromfile(d / a["file"], dtype="<f4").reshape(a["n"], self.embedding_dim)
+            t.vocab.ids = {w: i for i, w in enumerate(a.get("vocab", []))}
             t.extend(a["records"], emb)   # one copy + one conversion launch for the whole table
             if a.get("bm25"):
                 try:
