@@ -406,7 +406,7 @@ class DocumentStore:
             emb = np.fromfile(d / a["file"], dtype="<f4").reshape(a["n"], self.embedding_dim)
             t.vocab.ids = {w: i for i, w in enumerate(a.get("vocab", []))}
             t.extend(a["records"], emb)   # one copy + one conversion launch for the whole table
-            if a.get("bm25"):
+            if a.get("bm25") and "vocab" in a:   # (term ids are only stable under the saved mapping)
                 try:
                     if not t.adopt_bm25(Bm25Index.load(d / a["bm25"], device=self.device)):
                         logger.warning(f"saved keyword index of {agent_id} does not match its chunks: it will be rebuilt")
