@@ -173,6 +173,30 @@ __global__ void __launch_bounds__(64) hybrid_merge_kernel(const int64_t *__restr
         bm_scores[(int64_t)q * fetch_k + i] = l_sc[fetch_k + i];
     }
     if (threadIdx.x == 0) {
+        // Truncation check of the BM25 lists.  Shards rank by RAW score (the divisor is only known after the
+        // exchange); x -> x / max can map two or three neighbouring raw values to the same normalised double, and
+        // the global order inside such a group is by id.  A shard whose FULL list ends inside the group of the
+        // k-th normalised value may have cut off a member with a lower id than one it kept -- possible only if the
+        // group mixes raw values (or a raw value just below the last kept one still lands in it).  Equal raw values
+        // are harmless: the shard kept its lowest ids, and fewer than kk are ever needed from one shard.  Flag such
+        // queries; the caller repairs them through the exhaustive path (max first, then ranking).
+        const int64_t kth_id = lists[fetch_k + fetch_k - 1];
+        if (kth_id >= 0) {
+            const double vk = l_sc[fetch_k + fetch_k - 1];
+            for (int g = 0; g < G; ++g) {
+                const int64_t *row = gathered + ((int64_t)g * B + q) * W + 2 * fetch_k;
+                if (row[kk - 1] < 0) continue;  // shard list not full: nothing was cut off
+                const double raw_last = __longlong_as_double(row[kk + kk - 1]);
+                if (__ddiv_rn(raw_last, s_max) != vk) continue;
+                bool mixed = raw_last > 0.0 &&
+                             __ddiv_rn(__longlong_as_double(__double_as_longlong(raw_last) - 1), s_max) == vk;
+                for (int r = 0; r < kk - 1 && !mixed; ++r) {
+                    const double raw = __longlong_as_double(row[kk + r]);
+                    mixed = raw != raw_last && __ddiv_rn(raw, s_max) == vk;
+                }
+                if (mixed) s_status |= ORAG_STATUS_OVERFLOW;
+            }
+        }
         bm_max[q] = s_max;
         if (out_status) out_status[q] = s_status;
         rrf_one(lists, 2, fetch_k, fetch_k, rrf_k, top_k, tie_mode, out_ids + (int64_t)q * top_k,

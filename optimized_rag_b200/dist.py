@@ -28,7 +28,13 @@ from .bm25_index import Bm25Plan, Bm25Stats
 
 logger = logging.getLogger(__name__)
 
-BM25_GUARD = 6  # extra raw-score entries per shard: distinct raw scores that collapse to one normalised double
+# Extra raw-score entries per shard beyond fetch_k.  Shards rank their docs by RAW score (the divisor -- the global max --
+# is only known after the exchange) and x -> x / max can fold neighbouring raw values into one normalised double, inside
+# which the order is by id: a shard list that ends in such a group may have cut off a doc it should have kept.  The
+# guard makes that rare; it is NOT what correctness rests on: orag_hybrid_merge detects every list that ends inside
+# the k-th value's group with mixed raw values and flags the query, and the repair path (`_exact_lists_global_max`)
+# exchanges the maxima first and ranks by the normalised value on every shard.
+BM25_GUARD = 6
 
 
 def shard_range(n_total: int, rank: int, world: int):
@@ -313,22 +319,53 @@ class ShardedHybrid:
         kk = fetch_k + BM25_GUARD
         lists = self.shard.local_lists(query_emb, query_terms, query_lens, fetch_k, kk, False, lane=lane)
         out, status = self._exchange(lists, fetch_k, kk, k, lane)
+        if os.environ.get("ORAG_TEST_FORCE_REPAIR") == "1":   # test hook (scripts/check_dist.py): every query repaired
+            status = status | _ffi.ORAG_STATUS_OVERFLOW
         out["status"] = status  # check_overflow=False: no host sync at all; the caller checks it with the results
         if check_overflow and bool(status.any()):
             if bool((status & _ffi.ORAG_STATUS_EXCHANGE_TIMEOUT).any()):
                 raise _ffi.OragError("sharded search: a peer's block did not arrive within the exchange timeout")
             bad = torch.nonzero(status).flatten()
-            lists = self.shard.exact_lists(query_emb[bad].contiguous(), query_terms[bad].contiguous(),
-                                           query_lens[bad].contiguous(), fetch_k, kk, False)
+            lists, gmax = self._exact_lists_global_max(query_emb[bad].contiguous(), query_terms[bad].contiguous(),
+                                                       query_lens[bad].contiguous(), fetch_k, kk)
             zero = torch.zeros(bad.numel(), dtype=torch.int32, device=bad.device)
             # the repair exchange takes a sequence number (and an all-gather buffer) of its own; it is a synchronous
             # path: callers that keep batches in flight (`submit`) drain them before repairing
             self._searches += 1
             fixed, _ = self._exchange((*lists, zero, None), fetch_k, kk, k, lane=2)
+            fixed["bm25_max"] = gmax
             for key, val in fixed.items():
                 out[key][bad] = val
             out["status"] = torch.zeros_like(status)
         return out
+
+    def _exact_lists_global_max(self, query_emb, query_terms, query_lens, fetch_k: int, kk: int):
+        """The repair path's lists: exhaustive kernels, and -- unlike the fast path, which ranks a shard's docs by RAW
+        score because the divisor is only known after the exchange -- the BM25 divisor FIRST (an all-reduce of the
+        shards' maxima), then every shard ranks its docs by (score / global max desc, id asc) exactly as the
+        single-GPU path does.  No truncation hazard remains: the merge of per-shard exact top lists is exact.
+        Returns ((cos ids, cos scores, bm25 ids, NORMALISED bm25 scores, ones), global max)."""
+        shard = self.shard
+        ci, cs = shard.cosine.topk(query_emb, fetch_k, mode="exact", check_overflow=False)
+        ix = shard.bm25
+        nb = query_terms.shape[0]
+        dev = query_terms.device
+        bi = torch.empty((nb, kk), dtype=torch.int64, device=dev)
+        bs = torch.empty((nb, kk), dtype=torch.float64, device=dev)
+        gmax = torch.empty(nb, dtype=torch.float64, device=dev)
+        ids_row = torch.arange(ix.n_docs, dtype=torch.int64, device=dev) + ix.doc_id_base
+        step = max(1, (256 << 20) // max(8 * ix.n_docs, 1))
+        for lo in range(0, nb, step):
+            hi = min(nb, lo + step)
+            raw = ix.dense_scores(query_terms[lo:hi].contiguous(), query_lens[lo:hi].contiguous())
+            m = raw.amax(dim=1).clamp_min(0.0) if ix.n_docs else torch.zeros(hi - lo, dtype=torch.float64, device=dev)
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+            gmax[lo:hi] = torch.where(m > 0, m, torch.ones_like(m))
+            i2, s2, _ = engine.topk_merge(ids_row.expand(hi - lo, -1).contiguous(), raw.contiguous(), kk,
+                                          shard_max=m[:, None].contiguous())
+            bi[lo:hi], bs[lo:hi] = i2, s2
+        ones = torch.ones(nb, dtype=torch.float64, device=dev)
+        return (ci, cs, bi, bs, ones), gmax
 
     # ------------------------------------------------------------------ two batches in flight
     def submit(self, query_emb, query_terms, query_lens, k: int = 10, fetch_k: int | None = None) -> "Ticket":

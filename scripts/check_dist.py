@@ -51,6 +51,24 @@ for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("tf32", "f16")):
                 ok &= same
                 print(f"[{mode}/{exchange}] world={world} rows={N}: {key:12s} {'identical' if same else 'DIFFERENT'}",
                       flush=True)
+        # the repair path (every query forced through it): maxima first, ranking by the normalised value on every shard
+        import os
+        os.environ["ORAG_TEST_FORCE_REPAIR"] = "1"
+        rep = sh.search(q_emb, qt, ql, K)
+        os.environ.pop("ORAG_TEST_FORCE_REPAIR")
+        torch.cuda.synchronize()
+        if rank == 0:
+            same = all(torch.equal(rep[key], ref[key]) for key in KEYS) and not bool(rep["status"].any())
+            ok &= same
+            print(f"[{mode}/{exchange}] repair path (all queries): {'identical' if same else 'DIFFERENT'}", flush=True)
+        # two batches in flight: tickets of interleaved submissions
+        tickets = [sh.submit(q_emb, qt, ql, K) for _ in range(6)]
+        outs = [tk.wait() for tk in tickets]
+        torch.cuda.synchronize()
+        if rank == 0:
+            same = all(torch.equal(o[key], ref[key]) for o in outs for key in KEYS)
+            ok &= same
+            print(f"[{mode}/{exchange}] 6 submitted batches (two in flight): {'identical' if same else 'DIFFERENT'}", flush=True)
         # device time and host time per step of back-to-back searches (no host sync inside)
         for _ in range(5):
             sh.search(q_emb, qt, ql, K, check_overflow=False)

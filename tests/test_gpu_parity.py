@@ -737,3 +737,46 @@ def test_submit_keeps_two_batches_in_flight_and_equals_search(eng):
         assert int(g["status"].max().item()) == 0
         for key in ("ids", "rrf_scores", "cos_ids", "cos_scores", "bm25_ids", "bm25_scores", "bm25_max"):
             assert torch.equal(g[key], want[key]), key
+
+
+def test_hybrid_merge_flags_lists_cut_inside_a_collapsed_tie_group(eng):
+    """Shards rank BM25 by raw score; dividing by the global max can fold two neighbouring raw values into one
+    normalised double, inside which the order is by id.  orag_hybrid_merge must flag a query when a shard's FULL list
+    ends inside the k-th value's group and that group mixes raw values (something may have been cut off), and must
+    not flag equal-raw ties or lists that end below the k-th value."""
+    from optimized_rag_b200.dist import hybrid_merge, pack_local
+    M = 3.0
+    a = None
+    x = 1.9
+    for _ in range(10000):     # a raw value whose lower neighbour normalises to the same double
+        x = np.nextafter(x, 0.0)
+        if x / M == np.nextafter(x, 0.0) / M:
+            a = float(x)
+            break
+    assert a is not None
+    b = float(np.nextafter(a, 0.0))
+    lone = a
+    while lone / M == np.nextafter(lone, 0.0) / M or lone / M == np.nextafter(lone, 4.0) / M:
+        lone = float(np.nextafter(lone, 0.0))   # a raw value with no collapsing neighbour
+    fk, kk, k = 2, 3, 2
+
+    def shard(ids, raws, smax):
+        ci = np.array([[100 + ids[0], 101 + ids[0]]], dtype=np.int64)
+        cs = np.array([[0.5, 0.25]])
+        return pack_local(_t(ci), _t(cs), _t(np.array([ids], dtype=np.int64)), _t(np.array([raws])),
+                          _t(np.array([smax])), _t(np.zeros(1, dtype=np.int32)))
+
+    other = shard([50, -1, -1], [0.5, 0.0, 0.0], 0.5)                 # second shard: short list, far below
+    cases = [
+        ([1, 9, 3], [M, a, b], 1, [1, 3]),      # full list ends in the k-th value's group, raws a != b collapse: flag
+        ([1, 9, 12], [M, a, a], 1, [1, 9]),     # equal raws, but a's lower neighbour would collapse too: flag
+        ([1, 9, 12], [M, lone, lone], 0, [1, 9]),   # equal raws, nothing else can collapse: the lowest ids were kept
+        ([1, 9, 3], [M, a, 0.7], 0, [1, 9]),    # the list ends below the k-th value
+        ([1, 9, -1], [M, a, 0.0], 0, [1, 9]),   # the list is not full: nothing was cut off
+    ]
+    for ids, raws, flag, want_ids in cases:
+        g = torch.stack([shard(ids, raws, M), other]).contiguous()
+        out, status = hybrid_merge(g, fk, kk, 60, k)
+        assert int(status.item()) == flag, (ids, raws)
+        assert out["bm25_ids"][0].cpu().tolist() == want_ids
+        assert out["bm25_scores"][0].cpu().tolist() == [1.0, raws[1] / M]
