@@ -780,3 +780,30 @@ def test_hybrid_merge_flags_lists_cut_inside_a_collapsed_tie_group(eng):
         assert int(status.item()) == flag, (ids, raws)
         assert out["bm25_ids"][0].cpu().tolist() == want_ids
         assert out["bm25_scores"][0].cpu().tolist() == [1.0, raws[1] / M]
+
+
+@pytest.mark.parametrize("mode", ["f16", "tf32", "bf16"])
+def test_cosine_dim_3072_with_planted_near_ties(eng, mode):
+    """dim = 3072 (text-embedding-3-large): the first-pass margin is a function of the vector length (accumulation
+    error grows with dim: api.cu first_pass_eps), and the final order of rows whose cosines differ by 1e-7 .. 1e-6 --
+    far below what the 16-bit / tf32 first pass can resolve -- must still be the oracle's, bit for bit."""
+    n, dim, nq, k = 12000, 3072, 5, 10
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim, 0)
+    queries = syn.query_embeddings(nq, n, dim)
+    rng = np.random.default_rng(11)
+    for b in range(nq):
+        q = queries[b].astype(np.float64)
+        u = rng.standard_normal(dim)
+        u -= q * (u @ q) / (q @ q)                       # orthogonal to the query
+        u *= np.linalg.norm(q) / np.linalg.norm(u)
+        for j in range(24):                              # cos = 1 / sqrt(1 + eps^2): 24 rows within ~2e-5 of each other
+            eps = 0.30 + 2.5e-6 * j
+            corpus[(b * 997 + j * 31 + 5) % n] = ((q + eps * u) * (0.5 + 0.25 * (j % 3))).astype(np.float32)
+        corpus[(b * 997 + 3) % n] = corpus[(b * 997 + 5) % n]      # exact duplicate: tie broken by row id
+    index = eng.CosineIndex(_t(corpus), mode=mode)
+    ids, sc = index.topk(_t(queries), k)
+    want_i, want_s = oracle.cosine_topk(corpus, queries, k)
+    assert np.array_equal(ids.cpu().numpy(), want_i)
+    assert np.array_equal(_bits(sc.cpu().numpy()), _bits(want_s))
+    gaps = np.diff(want_s, axis=1)
+    assert (np.abs(gaps) < 1e-5).sum() >= nq * 5         # the planted rows really are the ones being ranked
