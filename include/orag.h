@@ -141,6 +141,13 @@ int orag_stream_wait_prescan(void *stream);
 int orag_cosine_dense(const float *d_corpus, int64_t n_rows, int dim, const float *d_queries, int n_queries,
                       double *d_out, void *stream);
 
+/* The three float64 sums of the reference's cosine WITHOUT the final sqrt / divide, for callers whose reference
+ * finishes differently -- `cosine_similarity` of rag/nodes/helpers.py:266-290 takes the magnitudes as `sum ** 0.5`
+ * (libm pow), not sqrt: d_out_dots[q * n_rows + r] = sum(a*b) (Neumaier, reference order), d_out_row_sq[r] = sum(a*a)
+ * of corpus row r, d_out_query_sq[q] likewise for the queries. */
+int orag_dot_dense(const float *d_corpus, int64_t n_rows, int dim, const float *d_queries, int n_queries,
+                   double *d_out_dots, double *d_out_row_sq, double *d_out_query_sq, void *stream);
+
 /* First-pass debug/test hook: raw tensor-core similarities (dot * inv_norm[row]) for rows
  * [0, n_rows) as fp32 d_out[r * 256 + q]; n_rows is rounded up to 128 internally, d_out must
  * hold round_up(n_rows,128) * 256 floats.  mode = ORAG_COS_TF32 / ORAG_COS_BF16 / ORAG_COS_F16 (the 16-bit modes need a

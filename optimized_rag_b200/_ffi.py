@@ -23,7 +23,7 @@ SYMBOLS = [
     "orag_gen_embeddings", "orag_gen_doc_lengths", "orag_gen_tokens",
     "orag_row_inv_norms", "orag_row_sq", "orag_f32_to_bf16", "orag_f32_to_f16_rows",
     "orag_cosine_mark_prescan", "orag_stream_wait_prescan",
-    "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_dense", "orag_cosine_firstpass_dense",
+    "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_dense", "orag_dot_dense", "orag_cosine_firstpass_dense",
     "orag_bm25_build_workspace_bytes", "orag_bm25_index_plan", "orag_bm25_index_fill",
     "orag_bm25_workspace_bytes", "orag_bm25_topk", "orag_bm25_dense", "orag_dense_topk",
     "orag_topk_merge", "orag_rrf_fuse", "orag_rrf_fuse_pair", "orag_hybrid_merge", "orag_weighted_sum3", "orag_div_scalar",
@@ -104,6 +104,7 @@ def lib() -> ctypes.CDLL:
     L.orag_cosine_topk.argtypes = [vp, vp, vp, vp, c_int64, c_int, c_int64, vp, c_int, c_int, c_int, vp, vp, vp, vp,
                                    c_size_t, vp]
     L.orag_cosine_dense.argtypes = [vp, c_int64, c_int, vp, c_int, vp, vp]
+    L.orag_dot_dense.argtypes = [vp, c_int64, c_int, vp, c_int, vp, vp, vp, vp]
     L.orag_cosine_firstpass_dense.argtypes = [vp, vp, vp, c_int64, c_int, vp, c_int, c_int, vp, vp, c_size_t, vp]
     L.orag_bm25_build_workspace_bytes.restype = c_size_t
     L.orag_bm25_build_workspace_bytes.argtypes = [c_int64, c_int, c_int, c_int]

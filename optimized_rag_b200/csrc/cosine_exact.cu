@@ -121,9 +121,12 @@ __global__ void __launch_bounds__(256) query_sq_kernel(const float *__restrict__
 constexpr int kDenseQB = 4;
 
 // out[q * n_rows + r] = cosine(query q, row r)
+// raw_row_sq != nullptr: out receives the plain dot products and raw_row_sq[r] the row's sum of squares (callers that
+// finish the cosine themselves, e.g. with `** 0.5` instead of sqrt: rag/nodes/helpers.py:266-290)
 __global__ void __launch_bounds__(256) cosine_dense_kernel(const float *__restrict__ corpus, int64_t n_rows, int dim,
                                                           const float *__restrict__ queries, int n_queries,
-                                                          const double *__restrict__ sq_q, double *__restrict__ out)
+                                                          const double *__restrict__ sq_q, double *__restrict__ out,
+                                                          double *__restrict__ raw_row_sq)
 {
     __shared__ float stage_all[8][32 * 33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -141,12 +144,16 @@ __global__ void __launch_bounds__(256) cosine_dense_kernel(const float *__restri
             for (int b = 0; b < kDenseQB; ++b) qp[b] = (q0 + b < n_queries) ? queries + (int64_t)(q0 + b) * dim : nullptr;
             NeuSum dot[kDenseQB], sq;
             warp_score_rows<kDenseQB>(rowptr, qp, dim, stage, dot, sq, q0 == 0);
-            if (q0 == 0) sq_r = sq.result();
+            if (q0 == 0) {
+                sq_r = sq.result();
+                if (raw_row_sq && r < n_rows) raw_row_sq[r] = sq_r;
+            }
             if (r < n_rows) {
 #pragma unroll
                 for (int b = 0; b < kDenseQB; ++b)
                     if (q0 + b < n_queries)
-                        out[(int64_t)(q0 + b) * n_rows + r] = cosine_from_sums(dot[b].result(), sq_q[q0 + b], sq_r);
+                        out[(int64_t)(q0 + b) * n_rows + r] =
+                            raw_row_sq ? dot[b].result() : cosine_from_sums(dot[b].result(), sq_q[q0 + b], sq_r);
             }
         }
     }
@@ -281,13 +288,13 @@ int launch_query_sq(const float *queries, int n_queries, int dim, double *sq, cu
 }
 
 int launch_cosine_dense(const float *corpus, int64_t n_rows, int dim, const float *queries, int n_queries,
-                        const double *sq_q, double *out, cudaStream_t st)
+                        const double *sq_q, double *out, cudaStream_t st, double *raw_row_sq)
 {
     int64_t blocks = ((n_rows + 31) / 32 + 7) / 8;
     int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    cosine_dense_kernel<<<(unsigned)blocks, 256, 0, st>>>(corpus, n_rows, dim, queries, n_queries, sq_q, out);
+    cosine_dense_kernel<<<(unsigned)blocks, 256, 0, st>>>(corpus, n_rows, dim, queries, n_queries, sq_q, out, raw_row_sq);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }
@@ -509,6 +516,19 @@ extern "C" int orag_topk_merge(const int64_t *d_cand_ids, const double *d_cand_s
     return orag::launch_select_topk(d_cand_scores, d_cand_ids, nullptr, m, m, n_queries, k, 0, normalize, d_shard_max,
                                     normalize ? n_shards : 0, d_out_ids, d_out_scores, d_out_max, nullptr,
                                     (cudaStream_t)stream);
+}
+
+extern "C" int orag_dot_dense(const float *d_corpus, int64_t n_rows, int dim, const float *d_queries, int n_queries,
+                              double *d_out_dots, double *d_out_row_sq, double *d_out_query_sq, void *stream)
+{
+    ORAG_REQUIRE(d_corpus && d_queries && d_out_dots && d_out_row_sq && d_out_query_sq && n_rows >= 0 && dim > 0 &&
+                     n_queries > 0,
+                 "dot_dense");
+    int rc = orag::launch_query_sq(d_queries, n_queries, dim, d_out_query_sq, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (n_rows == 0) return ORAG_OK;
+    return orag::launch_cosine_dense(d_corpus, n_rows, dim, d_queries, n_queries, d_out_query_sq, d_out_dots,
+                                     (cudaStream_t)stream, d_out_row_sq);
 }
 
 extern "C" int orag_cosine_dense(const float *d_corpus, int64_t n_rows, int dim, const float *d_queries, int n_queries,

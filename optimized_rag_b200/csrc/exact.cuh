@@ -82,7 +82,7 @@ int launch_select_topk(const double *scores, const int64_t *ids, const uint32_t 
                        int64_t *out_ids, double *out_scores, double *out_max, int32_t *status, cudaStream_t st);
 int launch_query_sq(const float *queries, int n_queries, int dim, double *sq, cudaStream_t st);
 int launch_cosine_dense(const float *corpus, int64_t n_rows, int dim, const float *queries, int n_queries,
-                        const double *sq_q, double *out, cudaStream_t st);
+                        const double *sq_q, double *out, cudaStream_t st, double *raw_row_sq = nullptr);
 int launch_prefilter(const float *corpus, int dim, const float *queries, const float *inv_qnorm, const int32_t *cand,
                      const uint32_t *cnt, int cap, int n_queries, int k, float *cos32, int cap2, int32_t *surv,
                      uint32_t *surv_cnt, int32_t *status, cudaStream_t st);

@@ -180,6 +180,18 @@ class CosineIndex:
                                                 buf.data_ptr(), _stream(self.device)), "orag_cosine_dense")
         return buf[:Bq * self.n_rows].view(Bq, self.n_rows)
 
+    def dots(self, queries: torch.Tensor):
+        """(dots float64 [B, n_rows], row_sq float64 [n_rows], query_sq float64 [B]): the reference's three sums without
+        the final sqrt / divide (orag_dot_dense)."""
+        Bq = queries.shape[0]
+        dots = torch.empty((Bq, max(self.n_rows, 1)), dtype=torch.float64, device=self.device)[:, :self.n_rows].contiguous()
+        row_sq = torch.empty(max(self.n_rows, 1), dtype=torch.float64, device=self.device)[:self.n_rows]
+        q_sq = torch.empty(Bq, dtype=torch.float64, device=self.device)
+        _ffi.check(_ffi.lib().orag_dot_dense(self.corpus.data_ptr(), self.n_rows, self.dim, queries.data_ptr(), Bq,
+                                             dots.data_ptr(), row_sq.data_ptr(), q_sq.data_ptr(), _stream(self.device)),
+                   "orag_dot_dense")
+        return dots, row_sq, q_sq
+
     def firstpass_dense(self, queries: torch.Tensor, mode: str) -> torch.Tensor:
         """Raw tensor-core first-pass values (dot * inv_norm[row]) fp32 [n_rows, B] -- test hook."""
         Bq = queries.shape[0]

@@ -109,6 +109,16 @@ def cosine(a, b, neumaier: bool = True) -> float:
     return float(lib().orc_cosine(_p(a, _c_f32p), _p(b, _c_f32p), a.shape[0], int(neumaier)))
 
 
+def dot(a, b, neumaier: bool = True) -> float:
+    """sum(x*y for x, y in zip(a, b)) in the reference's float64 arithmetic (Neumaier `sum` under CPython >= 3.12)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    L = lib()
+    L.orc_dot.restype = ctypes.c_double
+    L.orc_dot.argtypes = [_c_f32p, _c_f32p, ctypes.c_int, ctypes.c_int]
+    return float(L.orc_dot(_p(a, _c_f32p), _p(b, _c_f32p), min(a.shape[0], b.shape[0]), int(neumaier)))
+
+
 def cosine_scores(corpus, query, neumaier: bool = True) -> np.ndarray:
     """float64 cosine of `query` against every row of `corpus` (fp32 [n, d])."""
     corpus = np.ascontiguousarray(corpus, dtype=np.float32)

@@ -77,6 +77,10 @@ int orc_set_threads(int n)
 #endif
 }
 
+/* sum(a*b for a,b in zip(v1,v2)) alone (callers that finish the cosine differently, e.g. rag/nodes/helpers.py:266-290
+ * with `** 0.5`) */
+double orc_dot(const float *a, const float *b, int d, int neumaier) { return sum_prod(a, b, d, neumaier); }
+
 double orc_cosine(const float *a, const float *b, int d, int neumaier)
 {
     double dot = sum_prod(a, b, d, neumaier);

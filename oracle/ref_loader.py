@@ -38,7 +38,7 @@ def _prepare():
 
 
 def load(name: str):
-    """name in {'retrieval','reranker','chunking','consistency_checker','data_wrangler'}."""
+    """name in {'retrieval','reranker','chunking','consistency_checker','data_wrangler','context_compressor','helpers'}."""
     if name in _cache:
         return _cache[name]
     if not available():
@@ -53,7 +53,34 @@ def load(name: str):
             mem.embeddings = emb
             sys.modules["memory"] = mem
             sys.modules["memory.embeddings"] = emb
-    path = REF_ROOT / "rag" / f"{name}.py"
+    if name in ("context_compressor", "helpers"):
+        # `from rag.models.intent_analysis import QueryIntent` would import the rag package (langdetect, langgraph, ...):
+        # register the package shells and load the one light module by path; langdetect itself is only used by
+        # helpers.detect_language, never on the paths recorded here
+        for pkg in ("rag", "rag.models"):
+            if pkg not in sys.modules:
+                sys.modules[pkg] = types.ModuleType(pkg)
+                sys.modules[pkg].__path__ = []
+        if "rag.models.intent_analysis" not in sys.modules:
+            spec = importlib.util.spec_from_file_location("rag.models.intent_analysis",
+                                                          REF_ROOT / "rag" / "models" / "intent_analysis.py")
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules["rag.models.intent_analysis"] = mod
+            spec.loader.exec_module(mod)
+        if "langdetect" not in sys.modules:
+            ld = types.ModuleType("langdetect")
+            ld.detect = lambda text: "en"
+            lde = types.ModuleType("langdetect.lang_detect_exception")
+            lde.LangDetectException = type("LangDetectException", (Exception,), {})
+            sys.modules["langdetect"], sys.modules["langdetect.lang_detect_exception"] = ld, lde
+        if "memory" not in sys.modules:
+            mem = types.ModuleType("memory")
+            emb = types.ModuleType("memory.embeddings")
+            emb.EmbeddingService = type("EmbeddingService", (), {})
+            mem.embeddings = emb
+            sys.modules["memory"] = mem
+            sys.modules["memory.embeddings"] = emb
+    path = REF_ROOT / "rag" / ("nodes/helpers.py" if name == "helpers" else f"{name}.py")
     spec = importlib.util.spec_from_file_location(f"_orag_ref_{name}", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

@@ -282,6 +282,59 @@ def golden_consistency():
     return out
 
 
+class _HashEmbedder:
+    """Embedding service stand-in shared by the helper goldens: fp32 values of a counter-based hash row of the text,
+    with generate_embedding / generate_embeddings_batch returning Python-float lists (sha256 -> synthetic.embeddings)."""
+
+    def __init__(self, dim):
+        self.dim = dim
+
+    def generate_embedding(self, text):
+        seed = int.from_bytes(hashlib.sha256(text.encode("utf-8")).digest()[:8], "little") & 0x7FFFFFFFFFFFFFFF
+        return py_list(syn.embeddings(seed, 0, 1, self.dim)[0])
+
+    def generate_embeddings_batch(self, texts):
+        return [self.generate_embedding(t) if t.strip() else [] for t in texts]
+
+
+def golden_helpers():
+    """apply_mmr / cosine_similarity of rag/nodes/helpers.py:183-290 (magnitudes via `** 0.5`)."""
+    h = ref_loader.load("helpers")
+    cases = []
+    for name, m, d, dup, lam, k, missing in [("m12_d96", 12, 96, 0, 0.7, 5, [2, 7]), ("m30_d64_dups", 30, 64, 150, 0.3, 8, []),
+                                             ("m6_d1536", 6, 1536, 0, 1.0, 3, [0]), ("m4_k9", 4, 32, 0, 0.5, 9, [])]:
+        emb = syn.embeddings(syn.SEED_CORPUS, 0, m, d, dup)
+        docs = [{"content": f"doc {i} text", "embedding": py_list(emb[i])} for i in range(m)]
+        for i in missing:
+            del docs[i]["embedding"]          # generated by the service, stored in place (:215-223)
+        out = h.apply_mmr("which doc is it", docs, lam, k, _HashEmbedder(d))
+        cases.append({"name": name, "m": m, "dim": d, "dup_per_mille": dup, "lambda": lam, "k": k, "missing": missing,
+                      "picked": [int(x["content"].split()[1]) for x in out]})
+    a, b = syn.embeddings(syn.SEED_CORPUS, 0, 2, 200)
+    pairs = [(py_list(a), py_list(b)), (py_list(a), py_list(a)), (py_list(a[:50]), py_list(b)), ([0.0] * 8, py_list(b[:8])),
+             ([3.0, 4.0], [4.0, 3.0])]
+    return {"cases": cases, "cosine": [hx(h.cosine_similarity(x, y)) for x, y in pairs],
+            "cosine_inputs": "rows 0/1 of synthetic.embeddings(SEED_CORPUS, 0, 2, 200): (a,b) (a,a) (a[:50],b) (zeros8,b[:8]) ([3,4],[4,3])"}
+
+
+def golden_compressor():
+    """ContextCompressor._score_sentences_hybrid / _split_sentences / _score_sentence_lexical
+    (rag/context_compressor.py:206-289) on the documents of tests/consistency_fixture.py."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import consistency_fixture as fx
+    cc = ref_loader.load("context_compressor")
+    comp = cc.ContextCompressor(embedding_service=_HashEmbedder(128))
+    out = []
+    for query in ("Alpha reactor output megawatts", "the and of", "bravo pipeline is pressurised during the night shift"):
+        for doc in fx.DOCUMENTS:
+            text = doc["content"] + " Tail sentence without a final stop that is long enough"
+            sents = comp._split_sentences(text)
+            scored = comp._score_sentences_hybrid(query, sents)
+            out.append({"query": query, "sentences": sents, "hybrid": [hx(s) for _, s in scored],
+                        "lexical": [hx(comp._score_sentence_lexical(query, s)) for s in sents]})
+    return {"dim": 128, "cases": out}
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     data = {
@@ -296,6 +349,8 @@ def main():
         "mmr": golden_mmr(),
         "dedup": golden_dedup(),
         "consistency": golden_consistency(),
+        "helpers": golden_helpers(),
+        "compressor": golden_compressor(),
     }
     p = OUT / "golden.json"
     p.write_text(json.dumps(data, separators=(",", ":")))
