@@ -319,7 +319,25 @@ def test_hybrid_merge_equals_merge_then_rrf(eng):
     for key, want in (("cos_ids", ci), ("cos_scores", cs), ("bm25_ids", bi), ("bm25_scores", bs), ("bm25_max", bmax),
                       ("ids", fi), ("rrf_scores", fs), ("src_ranks", src)):
         assert torch.equal(out[key], want), key
-    assert status.cpu().tolist() == [1 if b == 7 else 0 for b in range(B)]
+    # status = OR of the shards' words, plus the truncation rule of the BM25 lists (csrc/rrf.cu): a full shard list whose
+    # last entry normalises to the k-th merged value while a different raw value (an entry of the list, or the double just
+    # below the last one) lands on the same normalised double
+    want_status = []
+    gbs_np, gbi_np = gbs.cpu().numpy().reshape(B, G, kk), gbi.cpu().numpy().reshape(B, G, kk)
+    for b in range(B):
+        flag = 1 if b == 7 else 0
+        M = float(bmax[b].item())
+        vk = float(bs[b, fk - 1].item())
+        if int(bi[b, fk - 1].item()) >= 0:
+            for g in range(G):
+                raws = gbs_np[b, g]
+                if gbi_np[b, g, kk - 1] < 0 or raws[-1] / M != vk:
+                    continue
+                if (raws[-1] > 0 and np.nextafter(raws[-1], 0.0) / M == vk) or \
+                        any(r != raws[-1] and r / M == vk for r in raws[:-1]):
+                    flag |= 1
+        want_status.append(flag)
+    assert status.cpu().tolist() == want_status and sum(want_status) > 1
 
 
 def _random_lists(rng, g, B, fk, kk):
