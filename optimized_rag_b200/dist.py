@@ -267,7 +267,9 @@ class ShardedHybrid:
         assert self.exchange in ("nccl", "peer")
         self.exchange_note = ""
         self._gather_buf: dict = {}   # lane -> NCCL all-gather buffer
-        self._peer: PeerExchange | None = None
+        self._peer: PeerExchange | None = None      # the exchange of the most recent search
+        self._peers: dict = {}                      # (fetch_k, kk) -> PeerExchange
+        self._poisoned = ""
         self._retired: list[PeerExchange] = []  # outgrown exchanges: peers may still have them mapped until close()
         self._searches = 0            # searches issued so far (all ranks count alike): lane = parity of the next one
         self._lane_streams: dict = {}
@@ -276,16 +278,19 @@ class ShardedHybrid:
         ci, cs, bi, bs, bm, st, st2 = lists
         if self.exchange == "peer":
             Bq = ci.shape[0]
-            if self._peer is None or not self._peer.fits(Bq, fetch_k, kk):
-                # collective (every rank sees the same shapes); an outgrown exchange stays mapped until close()
-                if self._peer is not None:
-                    self._retired.append(self._peer)
-                    self._peer = None
+            peer = self._peers.get((fetch_k, kk))
+            if peer is None or not peer.fits(Bq, fetch_k, kk):
+                # collective (every rank sees the same shapes).  One exchange per (fetch_k, kk), kept for the life of the
+                # object: a serving loop that alternates top_k re-uses them instead of allocating and IPC-mapping a new
+                # buffer per switch; only a larger batch replaces one (the outgrown buffer stays mapped until close()).
+                if peer is not None:
+                    self._retired.append(peer)
                 try:
-                    self._peer = PeerExchange(ci.device, max(Bq, 256), fetch_k, kk, group=self.group)
+                    peer = self._peers[(fetch_k, kk)] = PeerExchange(ci.device, max(Bq, 256), fetch_k, kk, group=self.group)
                 except _ffi.OragError as e:  # raised on every rank together (see PeerExchange.__init__)
                     logger.warning("peer exchange unavailable, using the NCCL all-gather: %s", e)
                     self.exchange, self.exchange_note = "nccl", f"peer setup failed: {e}"
+            self._peer = peer if self.exchange == "peer" else None
         if self.exchange == "peer":
             ptr, shape = self._peer.exchange(ci, cs, bi, bs, bm, st, st2, seq=self._searches)
             return hybrid_merge(ptr, fetch_k, kk, self.shard.rrf_k, k, shape=shape, device=ci.device)
@@ -300,9 +305,9 @@ class ShardedHybrid:
     def close(self):
         """Collective: unmap / free the peer exchange buffers (call on every rank before the process group goes away,
         so that no rank frees a buffer another one still has mapped)."""
-        for px in self._retired + ([self._peer] if self._peer is not None else []):
+        for px in self._retired + list(self._peers.values()):
             px.close()
-        self._retired, self._peer = [], None
+        self._retired, self._peer, self._peers = [], None, {}
 
     def search(self, query_emb, query_terms, query_lens, k: int = 10, fetch_k: int | None = None,
                check_overflow: bool = True, lane: int | None = None):
@@ -311,20 +316,35 @@ class ShardedHybrid:
         queries (rare: thousands of duplicates / near-ties) are then repaired by all ranks together through the
         exhaustive kernels and a second, small exchange -- every rank takes the same branch."""
         fetch_k = fetch_k or k
+        if self._poisoned:
+            raise _ffi.OragError(f"sharded search is shut down: {self._poisoned}")
         if lane is None:  # the lane of a search is the parity of its exchange sequence number (PeerExchange slots)
             lane = (self._searches + 1) & 1
         self._searches += 1
         if self.world == 1:
             return self.shard.search(query_emb, query_terms, query_lens, k, fetch_k, check_overflow, lane=lane)
         kk = fetch_k + BM25_GUARD
+        if self.world * kk > 256 or fetch_k > 64:
+            raise _ffi.OragError(f"sharded search: n_shards * (fetch_k + {BM25_GUARD}) must be <= 256 and fetch_k <= 64 "
+                                 f"(orag_hybrid_merge); got {self.world} shards, fetch_k {fetch_k}")
         lists = self.shard.local_lists(query_emb, query_terms, query_lens, fetch_k, kk, False, lane=lane)
         out, status = self._exchange(lists, fetch_k, kk, k, lane)
         if os.environ.get("ORAG_TEST_FORCE_REPAIR") == "1":   # test hook (scripts/check_dist.py): every query repaired
             status = status | _ffi.ORAG_STATUS_OVERFLOW
         out["status"] = status  # check_overflow=False: no host sync at all; the caller checks it with the results
-        if check_overflow and bool(status.any()):
-            if bool((status & _ffi.ORAG_STATUS_EXCHANGE_TIMEOUT).any()):
-                raise _ffi.OragError("sharded search: a peer's block did not arrive within the exchange timeout")
+        if check_overflow:
+            # A timeout is only visible to the rank that waited in vain: agree on it (one tiny all-reduce; this checked
+            # path synchronises with the host anyway) so that every rank takes the same branch.  After a timeout the
+            # slot re-use invariant of the exchange no longer holds: the object is shut down on all ranks together.
+            # Callers that pass check_overflow=False (batches in flight) must look at out["status"] themselves before the
+            # next search: bit 2 set = stop using this object.
+            flags = torch.stack([(status & _ffi.ORAG_STATUS_EXCHANGE_TIMEOUT).any(), status.any()]).to(torch.int32)
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group)
+            timed_out, any_bad = (bool(x) for x in flags.tolist())
+            if timed_out:
+                self._poisoned = "a peer's block did not arrive within the exchange timeout"
+                raise _ffi.OragError("sharded search: " + self._poisoned)
+        if check_overflow and any_bad:
             bad = torch.nonzero(status).flatten()
             lists, gmax = self._exact_lists_global_max(query_emb[bad].contiguous(), query_terms[bad].contiguous(),
                                                        query_lens[bad].contiguous(), fetch_k, kk)
