@@ -206,10 +206,9 @@ class PeerExchange:
     def fits(self, n_queries: int, fetch_k: int, kk: int) -> bool:
         return n_queries <= self.max_queries and fetch_k == self.fetch_k and kk == self.kk
 
-    def exchange(self, cos_ids, cos_scores, bm_ids, bm_scores, bm_max, status, status2=None, seq: int | None = None):
-        """Push this rank's lists to every peer, wait for theirs -> (device pointer of [G, B, W], shape).  `status` and
-        the optional `status2` (the cosine and the BM25 call's overflow words) are OR-ed by the push kernel.  `seq`:
-        the search's sequence number (same on every rank, strictly increasing; default: one more than the last)."""
+    def push(self, cos_ids, cos_scores, bm_ids, bm_scores, bm_max, status, status2=None, seq: int | None = None) -> int:
+        """Pack this rank's lists and store them into every peer's slot of search `seq` (default: one more than the
+        last; same on every rank, strictly increasing), then publish the sequence number.  Returns seq."""
         L = _ffi.lib()
         Bq = cos_ids.shape[0]
         assert self.fits(Bq, cos_ids.shape[1], bm_ids.shape[1])
@@ -225,10 +224,22 @@ class PeerExchange:
                                       status2.data_ptr() if status2 is not None else None, Bq, self.fetch_k, self.kk, self.rank,
                                       self.world, self.max_queries, self._d_peers.data_ptr(), self.seq, st),
                    "orag_hybrid_push")
+        return self.seq
+
+    def wait(self, n_queries: int, seq: int | None = None):
+        """Acquire every rank's block of search `seq` (default: the last pushed) -> (device pointer of [G, B, W], shape)."""
         out = ctypes.c_void_p()
-        _ffi.check(L.orag_hybrid_wait(self._mine, self.world, self.max_queries, Bq, self.fetch_k, self.kk, self.seq,
-                                      self.TIMEOUT_MS, ctypes.byref(out), st), "orag_hybrid_wait")
-        return out.value, (self.world, Bq, self.W)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _ffi.check(_ffi.lib().orag_hybrid_wait(self._mine, self.world, self.max_queries, n_queries, self.fetch_k, self.kk,
+                                               self.seq if seq is None else int(seq), self.TIMEOUT_MS, ctypes.byref(out),
+                                               st), "orag_hybrid_wait")
+        return out.value, (self.world, n_queries, self.W)
+
+    def exchange(self, cos_ids, cos_scores, bm_ids, bm_scores, bm_max, status, status2=None, seq: int | None = None):
+        """push + wait: this rank's lists to every peer, theirs back -> (device pointer of [G, B, W], shape).  `status`
+        and the optional `status2` (the cosine and the BM25 call's overflow words) are OR-ed by the push kernel."""
+        self.push(cos_ids, cos_scores, bm_ids, bm_scores, bm_max, status, status2, seq)
+        return self.wait(cos_ids.shape[0])
 
     def close(self):
         """Collective: unmap the peers' buffers, then free the own one (after everybody has unmapped it).  Never

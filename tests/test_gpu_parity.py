@@ -432,11 +432,19 @@ except _ffi.OragError:
 L.orag_exchange_open = real_open
 px = PeerExchange(dev, 64, fk, kk)
 for step, n in enumerate([B, B, 7, 64, B, B]):
-    ptr, shape = px.exchange(*lists(step, rank, n))
+    # Both ranks share ONE GPU here, and kernels of different processes that wait on one another are not guaranteed
+    # to run at the same time (B200_PROFILING.md): push, make sure on the HOST that every rank's push has finished,
+    # and only then launch the wait kernel -- it finds all sequence numbers published and never spins.
+    px.push(*lists(step, rank, n))
+    torch.cuda.synchronize()
+    dist.barrier()
+    ptr, shape = px.wait(n)
     got, status = hybrid_merge(ptr, fk, kk, 60, k, shape=shape, device=dev)
     want = torch.stack([pack_local(*lists(step, g, n)) for g in range(world)]).contiguous()
     ref, ref_status = hybrid_merge(want, fk, kk, 60, k)
     ok &= all(torch.equal(got[key], ref[key]) for key in ref) and torch.equal(status, ref_status)
+    torch.cuda.synchronize()
+    dist.barrier()          # nobody pushes search s+1 into a slot a peer may still be reading
 torch.cuda.synchronize()
 px.close()
 dist.destroy_process_group()
