@@ -8,14 +8,14 @@ from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 from optimized_rag_b200 import engine, synthetic as syn  # noqa: E402
 from optimized_rag_b200.bm25_index import Bm25Index  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
 dev = torch.device("cuda:0")
-peaks = json.loads((Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").read_text()) \
-    if (Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6544.3}
+peaks = json.loads((Path(__file__).resolve().parents[2] / "MEASURED_PEAKS.json").read_text()) \
+    if (Path(__file__).resolve().parents[2] / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6544.3}
 
 
 def timed(fn, steps=20, warm=3):

@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 from optimized_rag_b200 import engine, synthetic as syn  # noqa: E402
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
@@ -47,8 +47,8 @@ same = all(torch.equal(x, y) for x, y in zip(a, b))
 flops_tri = float(M) * (M - 1) * DIM                      # upper triangle actually required
 blocks = (M + 255) // 256
 flops_done = sum(2.0 * 256 * min(M, (j + 1) * 256) * DIM for j in range(blocks))  # rows [0, j0+256) per query block
-peaks = json.loads((Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").read_text()) \
-    if (Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").exists() else {"bf16_tflops_sustained": 1400.0}
+peaks = json.loads((Path(__file__).resolve().parents[2] / "MEASURED_PEAKS.json").read_text()) \
+    if (Path(__file__).resolve().parents[2] / "MEASURED_PEAKS.json").exists() else {"bf16_tflops_sustained": 1400.0}
 print(json.dumps({"config": f"pairwise cosine {M} x {DIM}, threshold {THR}, doc_idx = i // 16", "ms": ms,
                   "pairs_found": n_pairs, "subblock_equals_exact_sweep": bool(same),
                   "tflops_required_triangle": flops_tri / ms / 1e9,

@@ -4,7 +4,7 @@ from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 from optimized_rag_b200 import engine, synthetic as syn  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000

@@ -5,7 +5,7 @@ from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 from optimized_rag_b200 import engine, synthetic as syn  # noqa: E402
 from optimized_rag_b200.bm25_index import Bm25Index  # noqa: E402
 
