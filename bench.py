@@ -588,6 +588,19 @@ def run_hybrid_like(args):
     brackets = h.kernel_brackets(lambda: sh.search(*devt, k, check_overflow=False))
     if cosched:
         shard_obj.coschedule = True
+    # per-rank view of the two dominant kernels (mean launch duration: plain steps / inside the submitted loop): the
+    # sharded step runs at the pace of the slowest GPU of the box
+    per_rank = None
+    if world > 1:
+        groups_ = (Bq + 255) // 256
+        mine = [bracket_stats(brackets[0], groups_)[0] or 0.0, bracket_stats(brackets[1], 1)[0] or 0.0,
+                bracket_stats(brackets_overlapped[0], groups_)[0] or 0.0, bracket_stats(brackets_overlapped[1], 1)[0] or 0.0]
+        allr = torch.zeros(world * 4, dtype=torch.float64, device=dev)
+        h.dist.all_gather_into_tensor(allr, torch.tensor(mine, dtype=torch.float64, device=dev))
+        allr = allr.view(world, 4).cpu().tolist()
+        per_rank = {"scan_ms": [round(r[0], 4) for r in allr], "bm25_ms": [round(r[1], 4) for r in allr],
+                    "scan_ms_in_timed_loop": [round(r[2], 4) for r in allr],
+                    "bm25_ms_in_timed_loop": [round(r[3], 4) for r in allr]}
 
     # ---- timed: end to end through the public call with HOST buffers, two batches in flight: while batch i computes,
     # the results of batch i-1 travel to the host and are read there (ONE host synchronisation per step)
@@ -670,6 +683,8 @@ def run_hybrid_like(args):
     if want_cos:
         line["hbm_roofline_queries_per_sec_fp32_corpus"] = Bq / (n_local * DIM * 4 / (pk["hbm_gbs"] * 1e9))
     line["verified_against_oracle"] = verified
+    if per_rank is not None:
+        line["per_rank_kernel_ms"] = per_rank
     if cpu is not None and world == 1:
         line["cpu_baseline"] = cpu
     h.finish(line, closer=sh.close)

@@ -335,10 +335,19 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                     for (unsigned a = ess; a; a &= a - 1) {
                         const int i = __ffs(a) - 1;
                         MS_VIEW(i);
-#pragma unroll 2
-                        for (int j = lane; j < len_; j += 32) {
-                            const uint32_t d = __ldg(gp_ + j) >> 16;
-                            atomicOr(bm + (d >> 5), 1u << (d & 31));
+                        // four loads per lane in flight before the first is consumed: one L2 round trip per 128 postings
+#pragma unroll 1
+                        for (int j0 = lane; j0 < len_; j0 += 128) {
+                            uint32_t pz[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) pz[u] = j0 + 32 * u < len_ ? __ldg(gp_ + j0 + 32 * u) : 0u;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (j0 + 32 * u < len_) {
+                                    const uint32_t d = pz[u] >> 16;
+                                    atomicOr(bm + (d >> 5), 1u << (d & 31));
+                                }
+                            }
                         }
                     }
                     __syncwarp();
@@ -402,14 +411,20 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                             const int i = __ffs(a) - 1;
                             MS_VIEW(i);
                             const float w = __shfl_sync(FULL, cur.w, i);
-#pragma unroll 2
-                            for (int j = lane; j < len_; j += 32) {
-                                const uint32_t post = __ldg(gp_ + j);
-                                if (post & 0xFFFFu) {
-                                    float *slot = acc + rank_of(post >> 16);
-                                    const float nv = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
-                                    *slot = nv;
-                                    lmax = fmaxf(lmax, nv);
+#pragma unroll 1
+                            for (int j0 = lane; j0 < len_; j0 += 128) {
+                                uint32_t pz[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) pz[u] = j0 + 32 * u < len_ ? __ldg(gp_ + j0 + 32 * u) : 0u;
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const uint32_t post = pz[u];
+                                    if (post & 0xFFFFu) {  // (a padding posting, or past the end of the run: impact 0)
+                                        float *slot = acc + rank_of(post >> 16);
+                                        const float nv = __fadd_rn(*slot, __fmul_rn(w, post_r(post)));
+                                        *slot = nv;
+                                        lmax = fmaxf(lmax, nv);
+                                    }
                                 }
                             }
                             __syncwarp();
