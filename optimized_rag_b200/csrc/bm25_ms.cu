@@ -192,14 +192,18 @@ struct MsRun {   // lane i = i-th term's run in the current tile, in units of fo
     int n, q;
 };
 
+// kT: docs per first-pass tile when known at compile time (8192 / 4096 in the stand-alone configuration: every
+// shared-memory offset becomes an immediate and the bitmap loops unroll), 0 = read tile size and layout from the call.
+template <int kT>
 __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_constant__ MsParams p)
 {
     extern __shared__ uint4 ms_smem[];
-    const int T = p.ix.fp_tile_docs;
+    const int T = kT ? kT : p.ix.fp_tile_docs;
     const int words = (T + 31) >> 5;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int cap = ms_cap(words, p.warp_bytes);
-    uint8_t *mine = reinterpret_cast<uint8_t *>(ms_smem) + (size_t)wib * p.warp_bytes;
+    const int warp_bytes = kT ? kMsWarpBytes : p.warp_bytes;
+    const int cap = ms_cap(words, warp_bytes);
+    uint8_t *mine = reinterpret_cast<uint8_t *>(ms_smem) + (size_t)wib * warp_bytes;
     float *acc = reinterpret_cast<float *>(mine);                              // [cap], zero between pairs
     uint32_t *bm = reinterpret_cast<uint32_t *>(mine + (size_t)cap * 4);       // [words] marked docs, zero between pairs
     uint16_t *pre = reinterpret_cast<uint16_t *>(bm + words);                  // [words] rank of a word's bit 0
@@ -697,7 +701,9 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
         p.warp_bytes = background ? kMsBgWarpBytes : kMsWarpBytes;
         const size_t smem = (size_t)warps * p.warp_bytes;
         const int lim = sm_count() * 2;
-        ORAG_CUDA_CHECK(cudaFuncSetAttribute(bm25_ms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int fixed_t = background ? 0 : ix->fp_tile_docs;
+        auto kernel = fixed_t == 8192 ? bm25_ms_kernel<8192> : fixed_t == 4096 ? bm25_ms_kernel<4096> : bm25_ms_kernel<0>;
+        ORAG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         profile_mark(1, 0, st);
         {
             const int tiles = ix->fp_n_tiles;
@@ -710,7 +716,7 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
             p.n_items = (int)((int64_t)tiles * split);
             int grid = (p.n_items + warps - 1) / warps;
             if (grid > lim) grid = lim;
-            bm25_ms_kernel<<<grid, warps * 32, smem, st>>>(p);
+            kernel<<<grid, warps * 32, smem, st>>>(p);
             ORAG_LAUNCH_CHECK();
         }
         profile_mark(1, 1, st);
