@@ -72,6 +72,9 @@ def parse_args():
                     help="queries compared with the full-size CPU oracle after the timed loops (0 = skip); default 32 "
                          "on one GPU, 8 under torchrun")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="alias of --verify-queries 0")
+    ap.add_argument("--timeline", default=None, metavar="FILE",
+                    help="after the timed loop, record start/end of every tagged launch of 8 more submitted steps "
+                         "(orag_timeline_*) and write them to FILE (.rankN appended under torchrun)")
     ap.add_argument("--ref-sample-rows", type=int, default=None)
     ap.add_argument("--ref-sample-queries", type=int, default=16)
     args = ap.parse_args()
@@ -379,6 +382,43 @@ class Harness:
             self.dist.destroy_process_group()
 
 
+TIMELINE_TAGS = ["", "query_prep", "seed_scan", "seed_finalize", "main_scan", "prefilter", "rescore", "select",
+                 "bm25_prepare", "bm25_first_pass", "bm25_finalize", "rrf", "push", "merge", "query_sq", "wait"]
+
+
+def write_timeline(h, step, drain, path, n_steps=8):
+    """Diagnostic: the per-launch picture of `n_steps` submitted steps (how the batches in flight overlap)."""
+    L, torch = h.L, h.torch
+    for _ in range(4):
+        step()
+    drain()
+    h.barrier()
+    L.orag_timeline_enable(1)
+    for _ in range(n_steps):
+        step()
+    drain()
+    torch.cuda.synchronize()
+    cap = 4096
+    tags, t0, t1 = (ctypes.c_int * cap)(), (ctypes.c_float * cap)(), (ctypes.c_float * cap)()
+    n = int(L.orag_timeline_read(tags, t0, t1, cap))
+    L.orag_timeline_enable(0)
+    h.barrier()
+    rows = sorted((float(t0[i]), float(t1[i]), TIMELINE_TAGS[tags[i]], i) for i in range(max(n, 0)))
+    with open(path, "w") as f:
+        f.write("# start_ms end_ms dur_ms tag (events on the launching stream: `start` = the stream reached the launch, "
+                "`end` = the kernel(s) finished)\n")
+        for a, b, tag, _ in rows:
+            f.write(f"{a:9.4f} {b:9.4f} {b - a:8.4f} {tag}\n")
+        scans = [(a, b) for a, b, tag, _ in rows if tag == "main_scan"]
+        if len(scans) > 1:
+            gaps = [scans[i + 1][0] - scans[i][1] for i in range(len(scans) - 1)]
+            per = [scans[i + 1][1] - scans[i][1] for i in range(len(scans) - 1)]
+            f.write("# main scan: durations " + " ".join(f"{b - a:.4f}" for a, b in scans) + "\n")
+            f.write("# gap between the end of one main scan and the start event of the next: " +
+                    " ".join(f"{g:.4f}" for g in gaps) + "\n")
+            f.write("# end-to-end period (scan end to scan end): " + " ".join(f"{g:.4f}" for g in per) + "\n")
+
+
 def bracket_stats(ms_list, per_step):
     """Per-step durations of a kernel that launches `per_step` times per step -> (mean, min, n_steps) in ms."""
     xs = [x for x in ms_list if x >= 0]
@@ -579,6 +619,8 @@ def run_hybrid_like(args):
     dev_ms, launches, brackets_overlapped, flags = h.device_timed(step, drain)
     if bool(torch.stack(flags).any()):
         raise SystemExit("bench: a candidate buffer overflowed inside the timed region; results would need the repair path")
+    if args.timeline:
+        write_timeline(h, step, drain, args.timeline + (f".rank{h.rank}" if world > 1 else ""))
     # (plain steps run the BM25 first pass BEFORE the scan, both with the whole GPU: with co-scheduling it is sized to
     # hide behind the scan on leftover SM resources, and its own duration says nothing about the kernel)
     shard_obj = getattr(sh, "shard", None)
@@ -671,7 +713,7 @@ def run_hybrid_like(args):
                 "arithmetic": "results in the reference's float64 arithmetic (bit-exact); candidate generation in low "
                               "precision with proven error margins, then exact re-score",
                 "rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}", "setup_s": round(t_setup, 1),
-                "exchange": exchange_used, "batches_in_flight": 2,
+                "exchange": exchange_used, "batches_in_flight": getattr(sh, "lanes", 1),
                 "bm25_co_scheduled_with_scan": cosched if args.config == "3" else None,
                 **({"bm25_postings_local": bm25.n_postings, "bm25_index_build_s": round(build_s, 2)} if want_bm else {})}),
             "e2e": {"value": Bq * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -60,6 +60,10 @@ extern "C" {
 #define ORAG_STATUS_OVERFLOW 1 /* candidate buffer overflowed: result for this query is NOT valid,
                                   caller must re-run the query with ORAG_COS_EXACT / dense BM25 */
 #define ORAG_STATUS_EXCHANGE_TIMEOUT 2 /* sharded search: a peer's block did not arrive in time (orag_hybrid_wait) */
+/* diagnostic detail, set together with ORAG_STATUS_OVERFLOW by the BM25 first pass: which of its buffers was too small */
+#define ORAG_STATUS_WHERE_TILE 16        /* a tile sub-range marked more docs than the per-warp accumulator holds */
+#define ORAG_STATUS_WHERE_CANDIDATES 32  /* more first-pass candidates than slots */
+#define ORAG_STATUS_WHERE_SURVIVORS 64   /* more candidates above the final threshold than re-score slots (2048) */
 
 int orag_version(void);
 const char *orag_last_error(void);
@@ -77,6 +81,13 @@ int orag_profile_read(float *scan_ms, float *bm25_ms);
  * first, at most `cap` (the library keeps the last 256): returns the number of durations written to ms[], or a
  * negative ORAG_E* code.  Synchronises on the events it reads. */
 int orag_profile_read_all(int slot, float *ms, int cap);
+/* Timeline of the hybrid step (diagnostic, scripts/timeline.py): after orag_timeline_enable(1) every tagged launch of
+ * the path (tags: csrc/common.cuh TimelineTag -- query prep, seed scan, seed finalize, main scan, prefilter, re-score,
+ * selection, BM25 prepare / first pass / finalize, RRF, push, wait, merge) records a start and an end event on its own
+ * stream; orag_timeline_read synchronises the device and returns up to `cap` (at most 4096 are kept) records as
+ * milliseconds since the enable call.  Both calls synchronise the device; disabled (the default) the marks cost nothing. */
+int orag_timeline_enable(int on);
+int orag_timeline_read(int *tags, float *begin_ms, float *end_ms, int cap);
 
 /* ---------------------------------------------------------------------------
  * Synthetic inputs: bit-identical to optimized_rag_b200/synthetic.py
@@ -128,11 +139,34 @@ int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, const void 
                      int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_status, void *d_workspace,
                      size_t workspace_bytes, void *stream);
 
+/* The same search in separate calls, so that a caller can keep all scans back to back on ONE stream while the query
+ * preparation of the next batch and the latency-bound tails of earlier batches run on others: ORAG_PHASE_PREP enqueues
+ * the query conversion and norms, ORAG_PHASE_SCAN the seed pass and the main scan (candidate lists stay in
+ * d_workspace), ORAG_PHASE_FINISH the candidate re-scores and the selection into d_out_*.  Same arguments in every call
+ * (the same d_workspace; d_out_status is cleared by the preparation phase); the caller orders each phase's stream
+ * after the previous phase's, and issues all calls of a batch before the preparation phase of the next batch on the
+ * same device.  At most 256 queries, tensor-core modes only.  phases = ORAG_PHASE_ALL is orag_cosine_topk. */
+#define ORAG_PHASE_SCAN 1
+#define ORAG_PHASE_FINISH 2
+#define ORAG_PHASE_PREP 4
+#define ORAG_PHASE_ALL 7
+int orag_cosine_topk_phase(const float *d_corpus, const float *d_inv_norm, const void *d_shadow, const double *d_row_sq,
+                           int64_t n_rows, int dim, int64_t row_id_base, const float *d_queries, int n_queries, int k,
+                           int mode, int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_status, void *d_workspace,
+                           size_t workspace_bytes, int phases, void *stream);
+
+/* Diagnostic: per-query sizes of the candidate sets of the LAST tensor-core search (<= 256 queries) that used
+ * d_workspace -- first-pass candidates (may exceed the 4096 slots: overflow) and survivors of the fp32 re-score --
+ * copied to HOST arrays of n_queries words; synchronises `stream`. */
+int orag_cosine_last_counts(const void *d_workspace, int dim, int n_queries, uint32_t *h_candidates,
+                            uint32_t *h_survivors, void *stream);
+
 /* Co-scheduling hook: with orag_cosine_mark_prescan(1), every orag_cosine_topk in a tensor-core mode records an
  * internal CUDA event on its stream right BEFORE launching the main scan kernel; orag_stream_wait_prescan(s) makes
- * stream s wait for that event (cudaStreamWaitEvent; no host sync).  A BM25 call enqueued on s afterwards with
- * ORAG_BM25_BACKGROUND starts once the scan's CTAs are (about to be) resident and fills the SM resources the scan
- * leaves idle, instead of grabbing the SMs first and delaying the scan. */
+ * stream s wait for that event (cudaStreamWaitEvent; no host sync).  A BM25 call with ORAG_BM25_BACKGROUND does that
+ * wait itself, between its query preparation and its first-pass kernel: the first pass starts once the scan's CTAs are
+ * (about to be) resident and fills the SM resources the scan leaves idle, instead of grabbing the SMs first and delaying
+ * the scan.  (Issue the cosine call of a batch before its BM25 call.) */
 int orag_cosine_mark_prescan(int enable);
 int orag_stream_wait_prescan(void *stream);
 
@@ -241,8 +275,8 @@ int orag_bm25_index_fill(const int64_t *d_doc_off, const int32_t *d_tokens, int6
 #define ORAG_BM25_EXACT_TILES 8  /* candidate path through the float64 scatter kernel even when the index carries
                                     the fp16 first-pass view (A/B tests; queries longer than 32 terms use it anyway) */
 #define ORAG_BM25_BACKGROUND 16  /* size the first-pass launch (8-warp CTAs, < 31 KB shared memory) so that it runs NEXT TO a
-                                    resident cosine scan CTA on every SM instead of after it; meant for a side stream,
-                                    enqueued after orag_stream_wait_prescan (below) */
+                                    resident cosine scan CTA on every SM instead of after it; meant for a side stream:
+                                    the first-pass launch waits for the latest pre-scan event (orag_cosine_mark_prescan) */
 size_t orag_bm25_workspace_bytes(const orag_bm25_index_t *index, int n_queries, int k, int flags);
 int orag_bm25_topk(const orag_bm25_index_t *index, int64_t doc_id_base, const int32_t *d_query_terms,
                    const int32_t *d_query_lens, int n_queries, int max_terms, int k, int flags,
@@ -314,14 +348,14 @@ int orag_hybrid_merge(const int64_t *d_gathered, int n_shards, int n_queries, in
  *     orag_hybrid_push: one launch packs this rank's lists (same arrays / layout as the gathered buffer of
  *       orag_hybrid_merge: d_cos_* [n_queries, fetch_k], d_bm25_* [n_queries, kk] RAW scores, d_bm25_max
  *       [n_queries]; d_status / d_status2 [n_queries] or NULL: the status words of the cosine and the BM25 call,
- *       OR-ed into the block's status column) and stores them into slot seq&3 of EVERY peer, then publishes
+ *       OR-ed into the block's status column) and stores them into slot seq % 6 of EVERY peer, then publishes
  *       seq with a system-scope release store.
  *     orag_hybrid_wait: one tiny launch that acquires the n_shards sequence numbers in this rank's own buffer;
  *       *d_gathered (host out) is the [n_shards, n_queries, W] array to hand to orag_hybrid_merge on the same
  *       stream.  A block that has not arrived after timeout_ms gets ORAG_STATUS_EXCHANGE_TIMEOUT in its status
  *       words (the merge ORs them into d_out_status) instead of hanging the GPU.
- *   Every rank must call push and wait for every seq, in order, with the same n_queries / fetch_k / kk.  Two searches
- *   may be in flight at once on two streams (even / odd seq, each in stream order): the buffer has four slots.
+ *   Every rank must call push and wait for every seq, in order, with the same n_queries / fetch_k / kk.  Three searches
+ *   may be in flight at once on three streams (lane = seq % 3, each lane in stream order): the buffer has six slots.
  * ------------------------------------------------------------------------- */
 size_t orag_exchange_bytes(int n_shards, int max_queries, int fetch_k, int kk);
 int orag_exchange_alloc(size_t bytes, void **d_buf);

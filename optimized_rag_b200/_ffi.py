@@ -15,15 +15,16 @@ ORAG_STATUS_OVERFLOW = 1
 ORAG_STATUS_EXCHANGE_TIMEOUT = 2
 ORAG_BM25_NORMALIZE, ORAG_BM25_FORCE_SPARSE, ORAG_BM25_FORCE_DENSE, ORAG_BM25_EXACT_TILES = 1, 2, 4, 8
 ORAG_BM25_BACKGROUND = 16
+ORAG_PHASE_SCAN, ORAG_PHASE_FINISH, ORAG_PHASE_PREP, ORAG_PHASE_ALL = 1, 2, 4, 7
 
 # every symbol include/orag.h declares (tests check the .so exports each one)
 SYMBOLS = [
     "orag_version", "orag_last_error", "orag_device_info",
-    "orag_launch_count", "orag_profile_enable", "orag_profile_read", "orag_profile_read_all",
+    "orag_launch_count", "orag_profile_enable", "orag_profile_read", "orag_profile_read_all", "orag_timeline_enable", "orag_timeline_read",
     "orag_gen_embeddings", "orag_gen_doc_lengths", "orag_gen_tokens",
     "orag_row_inv_norms", "orag_row_sq", "orag_f32_to_bf16", "orag_f32_to_f16_rows",
     "orag_cosine_mark_prescan", "orag_stream_wait_prescan",
-    "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_dense", "orag_dot_dense", "orag_cosine_firstpass_dense",
+    "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_topk_phase", "orag_cosine_last_counts", "orag_cosine_dense", "orag_dot_dense", "orag_cosine_firstpass_dense",
     "orag_bm25_build_workspace_bytes", "orag_bm25_index_plan", "orag_bm25_index_fill",
     "orag_bm25_workspace_bytes", "orag_bm25_topk", "orag_bm25_dense", "orag_dense_topk",
     "orag_topk_merge", "orag_rrf_fuse", "orag_rrf_fuse_pair", "orag_hybrid_merge", "orag_weighted_sum3", "orag_div_scalar",
@@ -90,6 +91,8 @@ def lib() -> ctypes.CDLL:
     L.orag_profile_enable.argtypes = [c_int]
     L.orag_profile_read.argtypes = [POINTER(ctypes.c_float), POINTER(ctypes.c_float)]
     L.orag_profile_read_all.argtypes = [c_int, POINTER(ctypes.c_float), c_int]
+    L.orag_timeline_enable.argtypes = [c_int]
+    L.orag_timeline_read.argtypes = [POINTER(c_int), POINTER(ctypes.c_float), POINTER(ctypes.c_float), c_int]
     L.orag_gen_embeddings.argtypes = [vp, c_int64, c_int, c_int64, c_uint64, c_int, vp]
     L.orag_gen_doc_lengths.argtypes = [vp, c_int64, c_int64, c_uint64, c_int, c_int, vp]
     L.orag_gen_tokens.argtypes = [vp, vp, c_int64, c_int64, c_uint64, vp, c_int, vp]
@@ -103,6 +106,9 @@ def lib() -> ctypes.CDLL:
     L.orag_cosine_workspace_bytes.argtypes = [c_int64, c_int, c_int, c_int, c_int]
     L.orag_cosine_topk.argtypes = [vp, vp, vp, vp, c_int64, c_int, c_int64, vp, c_int, c_int, c_int, vp, vp, vp, vp,
                                    c_size_t, vp]
+    L.orag_cosine_topk_phase.argtypes = [vp, vp, vp, vp, c_int64, c_int, c_int64, vp, c_int, c_int, c_int, vp, vp, vp, vp,
+                                         c_size_t, c_int, vp]
+    L.orag_cosine_last_counts.argtypes = [vp, c_int, c_int, vp, vp, vp]
     L.orag_cosine_dense.argtypes = [vp, c_int64, c_int, vp, c_int, vp, vp]
     L.orag_dot_dense.argtypes = [vp, c_int64, c_int, vp, c_int, vp, vp, vp, vp]
     L.orag_cosine_firstpass_dense.argtypes = [vp, vp, vp, c_int64, c_int, vp, c_int, c_int, vp, vp, c_size_t, vp]

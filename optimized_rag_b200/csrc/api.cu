@@ -53,6 +53,29 @@ void profile_mark(int slot, int end, cudaStream_t st)
     }
 }
 
+// timeline: up to kTlCap tagged (start, end) event pairs since orag_timeline_enable(1)
+constexpr int kTlCap = 4096;
+static int g_timeline = 0;
+static cudaEvent_t g_tl_epoch = nullptr;
+static cudaEvent_t g_tl_ev[kTlCap][2];
+static int g_tl_tag[kTlCap];
+static int g_tl_made = 0;
+static std::atomic<int> g_tl_n{0};
+
+int timeline_mark(int tag, int handle, cudaStream_t st)
+{
+    if (!g_timeline) return -1;
+    if (handle < 0) {
+        const int i = g_tl_n.fetch_add(1, std::memory_order_relaxed);
+        if (i >= g_tl_made) return -1;
+        g_tl_tag[i] = tag;
+        cudaEventRecord(g_tl_ev[i][0], st);
+        return i;
+    }
+    cudaEventRecord(g_tl_ev[handle][1], st);
+    return handle;
+}
+
 // inv_qnorm_s = 1 / (|q| * scale) from the fp16 conversion of the query block -> the other three views of the norm
 __global__ void scale_norms_kernel(const float *inv_qnorm_s, const float *scale, int n, float *qnorm_s, float *qnorm,
                                    float *inv_qnorm)
@@ -93,6 +116,17 @@ static int aux_for_current_device(AuxStream **out)
     return ORAG_OK;
 }
 
+// co-scheduling (orag_cosine_mark_prescan): make `st` wait for the point right before the latest main scan
+int wait_prescan(cudaStream_t st)
+{
+    AuxStream *aux = nullptr;
+    int rc = aux_for_current_device(&aux);
+    if (rc) return rc;
+    if (!aux->prescan_recorded) return ORAG_OK;  // nothing recorded yet on this device: nothing to wait for
+    ORAG_CUDA_CHECK(cudaStreamWaitEvent(st, aux->prescan, 0));
+    return ORAG_OK;
+}
+
 __global__ void unscale_columns_kernel(float *out, int64_t n, const float *scale, int n_queries)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -128,7 +162,11 @@ float orag::tc::first_pass_eps(int mode, int dim)
 namespace orag {
 
 constexpr int kGroup = 256;     // queries per tensor-core pass (UMMA N)
-constexpr int kSeedRows = 2048; // rows of the dense seed pass that initialises the thresholds
+// Rows of the dense seed pass that initialises the thresholds (64 tiles: the pass needs whole SMs, and with fewer CTAs
+// than SMs it can start while the last CTAs of the previous batch's scan are still draining).  The first wave of the main
+// scan (two tiles per CTA in flight, ~38k rows) still runs on the seed's threshold, which passes k / kSeedRows of the
+// rows: with 2048 seed rows that wave alone left ~190 candidates per query (k = 10) for the fp32 re-score, with 8192 ~45.
+constexpr int kSeedRows = 64 * 128;
 constexpr int kCandCap = 4096;  // first-pass candidate slots per query
 constexpr int kSurvCap = 512;   // candidates that survive the fp32 re-score (k <= 128 leaves ample room)
 
@@ -145,7 +183,7 @@ struct CosineWs {
     uint32_t *surv_cnt; // [G]
     double *cand_score; // [G, cap2]  float64 cosines of the survivors
     int64_t *cand_id;   // [G, cap2]
-    float *seed;        // [kSeedRows, 256]
+    float *seed;        // [256, kSeedRows] (transposed: one row of first-pass values per query)
     void *q_bf16;       // [G, dim] bf16 / fp16 copy of the query block
     float *q_scale;     // [G] power-of-two scale of each fp16 query row
     float *qnorm_s;     // [G] |q| * scale     (the units the fp16 scan's accumulators are in)
@@ -197,6 +235,51 @@ extern "C" int orag_profile_enable(int on)
     orag::g_profile = on ? 1 : 0;
     orag::g_ev_n[0] = orag::g_ev_n[1] = 0;
     orag::g_ev_open[0] = orag::g_ev_open[1] = -1;
+    return ORAG_OK;
+}
+
+extern "C" int orag_timeline_enable(int on)
+{
+    orag::g_timeline = 0;
+    if (on) {
+        ORAG_CUDA_CHECK(cudaDeviceSynchronize());
+        if (!orag::g_tl_epoch) ORAG_CUDA_CHECK(cudaEventCreate(&orag::g_tl_epoch));
+        for (; orag::g_tl_made < orag::kTlCap; ++orag::g_tl_made) {
+            ORAG_CUDA_CHECK(cudaEventCreate(&orag::g_tl_ev[orag::g_tl_made][0]));
+            ORAG_CUDA_CHECK(cudaEventCreate(&orag::g_tl_ev[orag::g_tl_made][1]));
+        }
+        orag::g_tl_n.store(0);
+        ORAG_CUDA_CHECK(cudaEventRecord(orag::g_tl_epoch, 0));
+        ORAG_CUDA_CHECK(cudaDeviceSynchronize());
+        orag::g_timeline = 1;
+    }
+    return ORAG_OK;
+}
+
+extern "C" int orag_timeline_read(int *tags, float *begin_ms, float *end_ms, int cap)
+{
+    ORAG_REQUIRE((tags && begin_ms && end_ms) || cap == 0, "timeline_read");
+    ORAG_CUDA_CHECK(cudaDeviceSynchronize());
+    int n = orag::g_tl_n.load();
+    if (n > orag::g_tl_made) n = orag::g_tl_made;
+    if (n > cap) n = cap;
+    for (int i = 0; i < n; ++i) {
+        tags[i] = orag::g_tl_tag[i];
+        ORAG_CUDA_CHECK(cudaEventElapsedTime(begin_ms + i, orag::g_tl_epoch, orag::g_tl_ev[i][0]));
+        ORAG_CUDA_CHECK(cudaEventElapsedTime(end_ms + i, orag::g_tl_epoch, orag::g_tl_ev[i][1]));
+    }
+    return n;
+}
+
+extern "C" int orag_cosine_last_counts(const void *d_workspace, int dim, int n_queries, uint32_t *h_candidates,
+                                       uint32_t *h_survivors, void *stream)
+{
+    ORAG_REQUIRE(d_workspace && n_queries >= 1 && n_queries <= kGroup && h_candidates && h_survivors, "last_counts");
+    CosineWs w = carve_tc(const_cast<void *>(d_workspace), dim);
+    cudaStream_t st = (cudaStream_t)stream;
+    ORAG_CUDA_CHECK(cudaMemcpyAsync(h_candidates, w.cnt, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, st));
+    ORAG_CUDA_CHECK(cudaMemcpyAsync(h_survivors, w.surv_cnt, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, st));
+    ORAG_CUDA_CHECK(cudaStreamSynchronize(st));
     return ORAG_OK;
 }
 
@@ -285,14 +368,19 @@ extern "C" int orag_f32_to_bf16(const float *d_src, void *d_dst, int64_t count, 
 extern "C" int orag_f32_to_f16_rows(const float *d_src, int64_t n_rows, int dim, void *d_dst_f16,
                                     float *d_inv_norm_scaled, float *d_scale, void *stream);
 
-extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, const void *d_shadow,
-                                const double *d_row_sq, int64_t n_rows,
-                                int dim, int64_t row_id_base, const float *d_queries, int n_queries, int k, int mode,
-                                int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_status, void *d_workspace,
-                                size_t workspace_bytes, void *stream)
+extern "C" int orag_cosine_topk_phase(const float *d_corpus, const float *d_inv_norm, const void *d_shadow,
+                                      const double *d_row_sq, int64_t n_rows,
+                                      int dim, int64_t row_id_base, const float *d_queries, int n_queries, int k, int mode,
+                                      int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_status, void *d_workspace,
+                                      size_t workspace_bytes, int phases, void *stream)
 {
     ORAG_REQUIRE(d_queries && d_out_ids && d_out_scores && n_queries > 0 && k > 0 && dim > 0 && n_rows >= 0,
                  "cosine_topk");
+    ORAG_REQUIRE(phases >= 1 && phases <= ORAG_PHASE_ALL, "phases");
+    ORAG_REQUIRE(phases == ORAG_PHASE_ALL || (n_queries <= kGroup && mode != ORAG_COS_EXACT),
+                 "split phases: at most 256 queries, tensor-core modes only");
+    const bool do_prep = (phases & ORAG_PHASE_PREP) != 0, do_scan = (phases & ORAG_PHASE_SCAN) != 0,
+               do_finish = (phases & ORAG_PHASE_FINISH) != 0;
     ORAG_REQUIRE(n_rows == 0 || d_corpus, "corpus");
     ORAG_REQUIRE(n_rows < ((int64_t)1 << 31), "n_rows per shard must fit int32");
     cudaStream_t st = (cudaStream_t)stream;
@@ -301,7 +389,8 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
         set_error("cosine_topk: workspace too small (%zu < %zu)", workspace_bytes, need);
         return ORAG_EWORKSPACE;
     }
-    if (d_out_status) ORAG_CUDA_CHECK(cudaMemsetAsync(d_out_status, 0, (size_t)n_queries * sizeof(int32_t), st));
+    if (d_out_status && do_prep)
+        ORAG_CUDA_CHECK(cudaMemsetAsync(d_out_status, 0, (size_t)n_queries * sizeof(int32_t), st));
     if (mode == ORAG_COS_EXACT)
         return cosine_exact_path(d_corpus, n_rows, dim, row_id_base, d_queries, n_queries, k, d_out_ids, d_out_scores,
                                  d_workspace, st);
@@ -324,92 +413,127 @@ extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, 
         const float *q = d_queries + (int64_t)q0 * dim;
         int rc;
         AuxStream *aux = nullptr;
-        const void *qop = q;
-        const float *qnorm_scan = w.qnorm, *inv_qnorm_scan = w.inv_qnorm;
-        if (f16) {
-            // The exact float64 sum(q*q) (one sequential compensated chain per query, ~65 us) is only needed by
-            // the final re-score: it runs on an auxiliary stream next to the scan.  The scan's thresholds use fp32
-            // norms that fall out of the fp16 conversion of the query block (error far inside the 2.5e-4 slack).
+        if (f16 || g_mark_prescan) {
             rc = aux_for_current_device(&aux);
             if (rc) return rc;
-            ORAG_CUDA_CHECK(cudaEventRecord(aux->fork, st));
-            ORAG_CUDA_CHECK(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
-            rc = launch_query_sq(q, nq, dim, w.sq_q, aux->stream);
-            if (rc) return rc;
-            ORAG_CUDA_CHECK(cudaEventRecord(aux->join, aux->stream));
-            rc = orag_f32_to_f16_rows(q, nq, dim, w.q_bf16, w.inv_qnorm_s, w.q_scale, st);
-            if (rc) return rc;
-            scale_norms_kernel<<<(nq + 255) / 256, 256, 0, st>>>(w.inv_qnorm_s, w.q_scale, nq, w.qnorm_s, w.qnorm,
-                                                               w.inv_qnorm);
-            ORAG_LAUNCH_CHECK();
-            qop = w.q_bf16;
-            qnorm_scan = w.qnorm_s;
-            inv_qnorm_scan = w.inv_qnorm_s;
-        } else {
-            rc = launch_query_sq(q, nq, dim, w.sq_q, st);
-            if (rc) return rc;
-            rc = tc::launch_query_norms(w.sq_q, nq, w.qnorm, w.inv_qnorm, st);
-            if (rc) return rc;
-            if (bf16) {
-                rc = orag_f32_to_bf16(q, w.q_bf16, (int64_t)nq * dim, st);
+        }
+        const void *qop = bf16 ? (const void *)w.q_bf16 : (const void *)q;
+        const float *qnorm_scan = f16 ? w.qnorm_s : w.qnorm, *inv_qnorm_scan = f16 ? w.inv_qnorm_s : w.inv_qnorm;
+        if (do_prep) {
+            if (f16) {
+                // The exact float64 sum(q*q) (one sequential compensated chain per query, ~65 us) is only needed by
+                // the final re-score: it runs on an auxiliary stream next to the scan.  The scan's thresholds use fp32
+                // norms that fall out of the fp16 conversion of the query block (error far inside the 2.5e-4 slack).
+                ORAG_CUDA_CHECK(cudaEventRecord(aux->fork, st));
+                ORAG_CUDA_CHECK(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+                {
+                    TimelineScope tl(TL_QUERY_SQ, aux->stream);
+                    rc = launch_query_sq(q, nq, dim, w.sq_q, aux->stream);
+                }
                 if (rc) return rc;
-                qop = w.q_bf16;
+                ORAG_CUDA_CHECK(cudaEventRecord(aux->join, aux->stream));
+                TimelineScope tl(TL_QUERY_PREP, st);
+                rc = orag_f32_to_f16_rows(q, nq, dim, w.q_bf16, w.inv_qnorm_s, w.q_scale, st);
+                if (rc) return rc;
+                scale_norms_kernel<<<(nq + 255) / 256, 256, 0, st>>>(w.inv_qnorm_s, w.q_scale, nq, w.qnorm_s, w.qnorm,
+                                                                   w.inv_qnorm);
+                ORAG_LAUNCH_CHECK();
+            } else {
+                rc = launch_query_sq(q, nq, dim, w.sq_q, st);
+                if (rc) return rc;
+                rc = tc::launch_query_norms(w.sq_q, nq, w.qnorm, w.inv_qnorm, st);
+                if (rc) return rc;
+                if (bf16) {
+                    rc = orag_f32_to_bf16(q, w.q_bf16, (int64_t)nq * dim, st);
+                    if (rc) return rc;
+                }
             }
         }
-        const void *aop = bf16 ? d_shadow : (const void *)d_corpus;
-        tc::ScanParams p{};
-        p.f16 = f16 ? 1 : 0;
-        p.n_queries = nq;
-        p.inv_norm = d_inv_norm;
-        p.thr_key = w.thr_key;
-        p.cnt = w.cnt;
-        p.hist = w.hist;
-        p.cand = w.cand;
-        p.cap = kCandCap;
-        p.qnorm = qnorm_scan;
-        p.inv_qnorm = inv_qnorm_scan;
-        p.margin = margin;
-        p.k = k;
-        // seed: dense first pass over the first rows -> histogram, threshold, first candidates
-        p.row_begin = 0;
-        p.row_end = n_seed;
-        p.dense = 1;
-        p.dense_out = w.seed;
-        rc = tc::launch_scan(bf16, aop, n_rows, qop, dim, p, st);
-        if (rc) return rc;
-        rc = tc::launch_seed_finalize(w.seed, n_seed, nq, k, margin, qnorm_scan, inv_qnorm_scan, w.thr_key, w.cnt, w.hist,
-                                      w.cand, kCandCap, st);
-        if (rc) return rc;
-        // main scan over the rest of the shard (co-scheduling hook: see orag_cosine_mark_prescan)
-        if (g_mark_prescan) {
-            if (!aux) {
-                rc = aux_for_current_device(&aux);
-                if (rc) return rc;
+        if (do_scan) {
+            const void *aop = bf16 ? d_shadow : (const void *)d_corpus;
+            tc::ScanParams p{};
+            p.f16 = f16 ? 1 : 0;
+            p.n_queries = nq;
+            p.inv_norm = d_inv_norm;
+            p.thr_key = w.thr_key;
+            p.cnt = w.cnt;
+            p.hist = w.hist;
+            p.cand = w.cand;
+            p.cand_v = w.cos32;  // first-pass values; the fp32 re-score overwrites them in place
+            p.cap = kCandCap;
+            p.qnorm = qnorm_scan;
+            p.inv_qnorm = inv_qnorm_scan;
+            p.margin = margin;
+            p.k = k;
+            // seed: dense first pass over the first rows -> histogram, threshold, first candidates
+            p.row_begin = 0;
+            p.row_end = n_seed;
+            p.dense = 2;
+            p.dense_out = w.seed;
+            p.dense_ld = kSeedRows;
+            {
+                TimelineScope tl(TL_SEED_SCAN, st);
+                rc = tc::launch_scan(bf16, aop, n_rows, qop, dim, p, st);
             }
-            ORAG_CUDA_CHECK(cudaEventRecord(aux->prescan, st));
-            aux->prescan_recorded = true;
+            if (rc) return rc;
+            {
+                TimelineScope tl(TL_SEED_FINALIZE, st);
+                rc = tc::launch_seed_finalize(w.seed, kSeedRows, n_seed, nq, k, margin, qnorm_scan, inv_qnorm_scan, w.thr_key, w.cnt,
+                                              w.hist, w.cand, w.cos32, kCandCap, st);
+            }
+            if (rc) return rc;
+            // main scan over the rest of the shard (co-scheduling hook: see orag_cosine_mark_prescan)
+            if (g_mark_prescan) {
+                ORAG_CUDA_CHECK(cudaEventRecord(aux->prescan, st));
+                aux->prescan_recorded = true;
+            }
+            p.row_begin = n_seed;
+            p.row_end = n_rows;
+            p.dense = 0;
+            p.dense_out = nullptr;
+            {
+                TimelineScope tl(TL_MAIN_SCAN, st);
+                rc = tc::launch_scan(bf16, aop, n_rows, qop, dim, p, st);
+            }
+            if (rc) return rc;
         }
-        p.row_begin = n_seed;
-        p.row_end = n_rows;
-        p.dense = 0;
-        p.dense_out = nullptr;
-        rc = tc::launch_scan(bf16, aop, n_rows, qop, dim, p, st);
-        if (rc) return rc;
+        if (!do_finish) continue;
         // fp32 re-score of the candidate set -> the few rows that can still reach the top-k ...
-        rc = launch_prefilter(d_corpus, dim, q, w.inv_qnorm, w.cand, w.cnt, kCandCap, nq, k, w.cos32, kSurvCap, w.surv,
-                              w.surv_cnt, d_out_status ? d_out_status + q0 : nullptr, st);
+        {
+            TimelineScope tl(TL_PREFILTER, st);
+            rc = launch_prefilter(d_corpus, dim, q, w.inv_qnorm, w.cand, w.cnt, kCandCap, nq, k, w.cos32, kSurvCap, w.surv,
+                                  w.surv_cnt, d_out_status ? d_out_status + q0 : nullptr, st, w.thr_key, qnorm_scan,
+                                  margin);
+        }
         if (rc) return rc;
-        // ... exact float64 re-score of those (the reference's arithmetic), then exact selection
+        // ... exact float64 re-score of those (the reference's arithmetic), then exact selection.  (A split call's
+        // finish phase waits for the sum(q*q) its own scan phase -- the latest one on this device -- put on the
+        // auxiliary stream: callers issue scan and finish of one batch back to back.)
         if (f16) ORAG_CUDA_CHECK(cudaStreamWaitEvent(st, aux->join, 0));
-        rc = launch_rescore(d_corpus, dim, row_id_base, q, w.sq_q, w.surv, w.surv_cnt, kSurvCap, nq, d_row_sq,
-                            w.cand_score, w.cand_id, st);
+        {
+            TimelineScope tl(TL_RESCORE, st);
+            rc = launch_rescore(d_corpus, dim, row_id_base, q, w.sq_q, w.surv, w.surv_cnt, kSurvCap, nq, d_row_sq,
+                                w.cand_score, w.cand_id, st);
+        }
         if (rc) return rc;
+        TimelineScope tl_sel(TL_SELECT, st);
         rc = launch_select_topk(w.cand_score, w.cand_id, w.surv_cnt, kSurvCap, kSurvCap, nq, k, 0, 0, nullptr, 0,
                                 d_out_ids + (int64_t)q0 * k, d_out_scores + (int64_t)q0 * k, nullptr,
                                 d_out_status ? d_out_status + q0 : nullptr, st);
         if (rc) return rc;
     }
     return ORAG_OK;
+}
+
+extern "C" int orag_cosine_topk(const float *d_corpus, const float *d_inv_norm, const void *d_shadow,
+                                const double *d_row_sq, int64_t n_rows,
+                                int dim, int64_t row_id_base, const float *d_queries, int n_queries, int k, int mode,
+                                int64_t *d_out_ids, double *d_out_scores, int32_t *d_out_status, void *d_workspace,
+                                size_t workspace_bytes, void *stream)
+{
+    return orag_cosine_topk_phase(d_corpus, d_inv_norm, d_shadow, d_row_sq, n_rows, dim, row_id_base, d_queries, n_queries,
+                                  k, mode, d_out_ids, d_out_scores, d_out_status, d_workspace, workspace_bytes,
+                                  ORAG_PHASE_ALL, stream);
 }
 
 extern "C" int orag_cosine_firstpass_dense(const float *d_corpus, const float *d_inv_norm, const void *d_shadow,
@@ -468,12 +592,4 @@ extern "C" int orag_cosine_mark_prescan(int enable)
     return ORAG_OK;
 }
 
-extern "C" int orag_stream_wait_prescan(void *stream)
-{
-    orag::AuxStream *aux = nullptr;
-    int rc = orag::aux_for_current_device(&aux);
-    if (rc) return rc;
-    if (!aux->prescan_recorded) return ORAG_OK;  // nothing recorded yet on this device: nothing to wait for
-    ORAG_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, aux->prescan, 0));
-    return ORAG_OK;
-}
+extern "C" int orag_stream_wait_prescan(void *stream) { return orag::wait_prescan((cudaStream_t)stream); }

@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
         const int qi0 = (int)(((int64_t)nq * part) / S);
         const int qi1 = (int)(((int64_t)nq * (part + 1)) / S);
         const int64_t base_doc = (int64_t)tile * T;
+        const int tile_docs = (int)min((int64_t)T, (int64_t)p.ix.n_docs - base_doc);
         const uint32_t *tp = p.ix.d_postings_r16 + p.ix.d_fp_tile_base[tile];  // 16-byte aligned (padded layout)
         const uint4 *tp4 = reinterpret_cast<const uint4 *>(tp);
         const int32_t *toff = p.ix.d_fp_tile_term_off + (int64_t)tile * V1;
@@ -291,10 +292,13 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
             if (ess) {
                 // essential postings of the pair; more than the accumulator holds -> doc sub-ranges
                 const int etot = __reduce_add_sync(FULL, (mine_ok && lane >= n_ne) ? cur.len4 * 4 : 0);
-                int nsub = 1, sub_docs = T;
-                while (nsub * (etot > cap ? (cap >> 1) : cap) < etot && sub_docs > 32) {
+                // (the doc range that is split is the tile's OWN: the last tile of a shard may hold a fraction of T docs, and
+                // equal slices of T would put all of its postings into the first few sub-ranges; a sub-range of at most
+                // `cap` docs cannot overflow whatever the postings are, so the halving stops there)
+                int nsub = 1, sub_docs = tile_docs;
+                while (nsub * (etot > cap ? (cap >> 1) : cap) < etot && sub_docs > 32 && sub_docs > cap) {
                     nsub <<= 1;
-                    sub_docs >>= 1;
+                    sub_docs = (tile_docs + nsub - 1) / nsub;
                 }
                 int cpos = 0;  // this lane's run: first posting of the current sub-range
                 for (int sub = 0; sub < nsub; ++sub) {
@@ -504,7 +508,7 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
                         }
                     } else if (p.status && lane == 0) {
                         // a skewed sub-range marked more docs than the accumulator holds: the caller re-runs the query
-                        atomicOr(p.status + q, ORAG_STATUS_OVERFLOW);
+                        atomicOr(p.status + q, ORAG_STATUS_OVERFLOW | ORAG_STATUS_WHERE_TILE);
                     }
 #undef MS_VIEW
                     // ---- X: only when something can clear the threshold, claim by RANK (lane-balanced, conflict-free):
@@ -556,8 +560,10 @@ __global__ void __launch_bounds__(1024) ms_finalize_kernel(const __grid_constant
     __syncthreads();
     uint32_t n = p.cnt[q];
     bool overflow = false;
+    int where = 0;
     if (n > (uint32_t)p.cap) {
         overflow = true;
+        where |= ORAG_STATUS_WHERE_CANDIDATES;
         n = p.cap;
     }
     const float thr = thr_to_float(p.thr_bits[q]);
@@ -575,9 +581,10 @@ __global__ void __launch_bounds__(1024) ms_finalize_kernel(const __grid_constant
     uint32_t ns = s_n;
     if (ns > (uint32_t)kMsSurvCap) {
         overflow = true;
+        where |= ORAG_STATUS_WHERE_SURVIVORS;
         ns = kMsSurvCap;
     }
-    if (overflow && status && threadIdx.x == 0) status[q] |= ORAG_STATUS_OVERFLOW;
+    if (overflow && status && threadIdx.x == 0) status[q] |= ORAG_STATUS_OVERFLOW | where;
     const int32_t *terms = p.q_terms + (int64_t)q * p.max_terms;
     const int nt = min(p.q_lens[q], p.max_terms);
     // exact re-score: one thread per (survivor, query token) runs the binary search, then one thread per survivor
@@ -685,6 +692,7 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
     p.k = k;
     p.status = d_out_status;
     {
+        TimelineScope tl(TL_BM25_PREPARE, st);
         int64_t total = (int64_t)n_queries * kHistBins;
         ms_init_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.thr_bits, p.cnt, p.hist, p.topbin,
                                                                               p.work, n_queries);
@@ -704,8 +712,15 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
         const int fixed_t = background ? 0 : ix->fp_tile_docs;
         auto kernel = fixed_t == 8192 ? bm25_ms_kernel<8192> : fixed_t == 4096 ? bm25_ms_kernel<4096> : bm25_ms_kernel<0>;
         ORAG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (background) {
+            // the query preparation above may run whenever the SMs have room; the first pass itself is ordered after the
+            // point right before the latest cosine main scan, so that the scan's CTAs take the SMs first
+            int rc = wait_prescan(st);
+            if (rc) return rc;
+        }
         profile_mark(1, 0, st);
         {
+            TimelineScope tl(TL_BM25_FIRST_PASS, st);
             const int tiles = ix->fp_n_tiles;
             // ~8 work items per resident warp so that the atomic hand-out can balance uneven pairs
             int64_t want = (int64_t)8 * lim * warps;
@@ -721,6 +736,7 @@ int ms_topk(const orag_bm25_index_t *ix, int64_t doc_id_base, const int32_t *d_q
         }
         profile_mark(1, 1, st);
     }
+    TimelineScope tl_fin(TL_BM25_FINALIZE, st);
     ms_finalize_kernel<<<n_queries, 1024, 0, st>>>(p, doc_id_base, normalize, d_out_ids, d_out_scores, d_out_max,
                                                    d_out_status);
     ORAG_LAUNCH_CHECK();

@@ -14,6 +14,20 @@ void set_error(const char *fmt, ...);
 // dominant kernels (slot 0 = cosine main scan, slot 1 = BM25 tile kernel)
 void count_launch();
 void profile_mark(int slot, int end, cudaStream_t st);
+// timeline (api.cu, orag_timeline_enable): start / end events of every tagged launch of the hybrid step, readable as
+// times since one epoch event -- the per-stream picture of how the batches in flight overlap.  No-ops when disabled.
+enum TimelineTag {
+    TL_QUERY_PREP = 1, TL_SEED_SCAN, TL_SEED_FINALIZE, TL_MAIN_SCAN, TL_PREFILTER, TL_RESCORE, TL_SELECT,
+    TL_BM25_PREPARE, TL_BM25_FIRST_PASS, TL_BM25_FINALIZE, TL_RRF, TL_PUSH, TL_MERGE, TL_QUERY_SQ, TL_WAIT
+};
+int timeline_mark(int tag, int handle, cudaStream_t st);
+int wait_prescan(cudaStream_t st);  // api.cu: order `st` after the point right before the latest cosine main scan
+struct TimelineScope {
+    int h;
+    cudaStream_t st;
+    TimelineScope(int tag, cudaStream_t s) : h(timeline_mark(tag, -1, s)), st(s) {}
+    ~TimelineScope() { if (h >= 0) timeline_mark(0, h, st); }
+};
 
 #define ORAG_CUDA_CHECK(expr)                                                              \
     do {                                                                                   \

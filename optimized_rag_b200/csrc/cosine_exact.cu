@@ -326,7 +326,9 @@ __global__ void __launch_bounds__(256) prefilter_kernel(const float *__restrict_
                                                        const float *__restrict__ queries,
                                                        const float *__restrict__ inv_qnorm,
                                                        const int32_t *__restrict__ cand, const uint32_t *__restrict__ cnt,
-                                                       int cap, int n_queries, float *__restrict__ out_cos)
+                                                       int cap, int n_queries, float *__restrict__ out_cos,
+                                                       const uint32_t *__restrict__ thr_key,
+                                                       const float *__restrict__ qnorm_scan, float margin)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -341,6 +343,17 @@ __global__ void __launch_bounds__(256) prefilter_kernel(const float *__restrict_
         const int q = (int)(t % n_queries);
         const uint32_t slot = (uint32_t)(t / n_queries);
         if (slot >= min(cnt[q], (uint32_t)cap)) continue;
+        if (thr_key) {
+            // out_cos arrives holding the first-pass value the scan emitted this candidate with.  The threshold only ever
+            // rose during the scan and every value it took admits all true top-k rows, so its FINAL value does too: a
+            // candidate emitted early, under a looser threshold, that the final one would reject needs no re-score
+            // (about four in five at k = 10; same expression as the scan's own test).
+            const float tv = (ordered_to_float(thr_key[q]) - margin) * qnorm_scan[q];
+            if (out_cos[(int64_t)q * cap + slot] < tv) {
+                if (lane == 0) out_cos[(int64_t)q * cap + slot] = -INFINITY;
+                continue;
+            }
+        }
         const int32_t row = cand[(int64_t)q * cap + slot];
         const float4 *rp = reinterpret_cast<const float4 *>(corpus + (int64_t)row * dim);
         const float4 *qp = reinterpret_cast<const float4 *>(queries + (int64_t)q * dim);
@@ -427,9 +440,11 @@ __global__ void __launch_bounds__(256) prune_kernel(const float *__restrict__ co
 
 int launch_prefilter(const float *corpus, int dim, const float *queries, const float *inv_qnorm, const int32_t *cand,
                      const uint32_t *cnt, int cap, int n_queries, int k, float *cos32, int cap2, int32_t *surv,
-                     uint32_t *surv_cnt, int32_t *status, cudaStream_t st)
+                     uint32_t *surv_cnt, int32_t *status, cudaStream_t st, const uint32_t *thr_key, const float *qnorm_scan,
+                     float margin)
 {
-    prefilter_kernel<<<sm_count() * 8, 256, 0, st>>>(corpus, dim, queries, inv_qnorm, cand, cnt, cap, n_queries, cos32);
+    prefilter_kernel<<<sm_count() * 8, 256, 0, st>>>(corpus, dim, queries, inv_qnorm, cand, cnt, cap, n_queries, cos32,
+                                                     thr_key, qnorm_scan, margin);
     ORAG_LAUNCH_CHECK();
     prune_kernel<<<n_queries, 256, 0, st>>>(cos32, cand, cnt, cap, k, cap2, eps32(dim), surv, surv_cnt, status);
     ORAG_LAUNCH_CHECK();

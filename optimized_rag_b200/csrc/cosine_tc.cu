@@ -211,7 +211,10 @@ __device__ __forceinline__ float bin_floor(int b) { return (float)b * (2.0f / kH
 __device__ __noinline__ void emit_candidate(const ScanParams &p, int q, int32_t local_row, float v)
 {
     const uint32_t slot = atomicAdd(p.cnt + q, 1u);
-    if (slot < (uint32_t)p.cap) p.cand[(int64_t)q * p.cap + slot] = local_row;
+    if (slot < (uint32_t)p.cap) {
+        p.cand[(int64_t)q * p.cap + slot] = local_row;
+        if (p.cand_v) p.cand_v[(int64_t)q * p.cap + slot] = v;
+    }
     if (p.fixed_thr) return;
     const int bin = cos_bin(v * p.inv_qnorm[q]);
     uint32_t *h = p.hist + (int64_t)q * kHistBins;
@@ -252,26 +255,28 @@ __device__ __forceinline__ void decode_tile(const ScanParams &p, int tile, int64
 
 // kMma2: the cta_group::2 flavour is a separate instantiation -- a kernel that contains cta_group::2 instructions can
 // only be launched as clusters of an even size
-template <bool kBf16, bool kMma2>
+// (Tried and dropped: capping the registers at 80 and a five-stage ring for the 2-SM flavour, to leave room on every SM for
+// the tail kernels of the previous batch next to the scan and the background BM25 CTA -- the main scan lost 5 % and 16 %.)
+template <bool kBf16, bool kMma2, int kSt>
 __global__ void __launch_bounds__(kThreads, 1)
 cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ ScanParams p)
 {
-    // 2-SM flavour: every CTA stages only half of each query slab, so the same 192 KiB hold six stages instead of four
-    constexpr int kSt = kMma2 ? 6 : kStages;
+    // 2-SM flavour: every CTA stages only half of each query slab (32 KiB stages instead of 48 KiB)
     constexpr int kBB = kMma2 ? kBBytes / 2 : kBBytes;
-    static_assert(kSt * (kABytes + kBB) == kStages * kStageBytes, "same shared-memory footprint");
+    constexpr int kRing = kSt * (kABytes + kBB);
+    static_assert(kSt <= 8 && scan_smem_bytes(kMma2, kSt) <= 227 * 1024, "ring");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + kSt * kABytes;
-    uint64_t *bars = (uint64_t *)(smem + kStages * kStageBytes);
-    uint64_t *full_bar = bars;                    // [kStages]
-    uint64_t *empty_bar = bars + 8;               // [kSt] (room for 8 stages)
+    uint64_t *bars = (uint64_t *)(smem + kRing);
+    uint64_t *full_bar = bars;                    // [kSt] (room for 8 stages)
+    uint64_t *empty_bar = bars + 8;               // [kSt]
     uint64_t *tmem_full = bars + 16;              // [2]
     uint64_t *tmem_empty = bars + 18;             // [2]
     uint32_t *tmem_ptr = (uint32_t *)(bars + 20);
-    float *thrv_s = (float *)(smem + kStages * kStageBytes + 256);  // [2][kMaxN]
+    float *thrv_s = (float *)(smem + kRing + 256);  // [2][kMaxN]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -428,7 +433,16 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 uint32_t r[32];
                 tmem_ld32(taddr0 + (uint32_t)(c * 32), r);
                 tmem_ld_wait();
-                if (p.dense) {
+                if (p.dense == 2) {
+                    // transposed (seed pass): dense_out[q * dense_ld + row] -- the 32 lanes of a warp hold 32 consecutive
+                    // rows, so every store instruction writes one 128-byte line
+                    if (valid) {
+                        float *dst = p.dense_out + (int64_t)col0 * p.dense_ld + (row - p.row_begin);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.n_queries) dst[(int64_t)j * p.dense_ld] = __uint_as_float(r[j]) * scale;
+                    }
+                } else if (p.dense) {
                     if (valid) {
                         float4 *dst = reinterpret_cast<float4 *>(p.dense_out + (row - p.row_begin) * kMaxN + col0);
 #pragma unroll
@@ -481,13 +495,15 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 }
 
 // ---- seed finalisation ----------------------------------------------------------------------
-// One CTA per query over the dense first-pass values of the first `n_seed` rows:
+// One CTA per query over the dense first-pass values of the first `n_seed` rows (transposed: seed_t[q * seed_ld + row]):
 // histogram -> threshold; survivors -> candidate list.
-__global__ void __launch_bounds__(256) seed_finalize_kernel(const float *__restrict__ seed, int n_seed, int n_queries,
+__global__ void __launch_bounds__(256) seed_finalize_kernel(const float *__restrict__ seed_t, int seed_ld, int n_seed,
+                                                           int n_queries,
                                                            int k, float margin, const float *__restrict__ qnorm,
                                                            const float *__restrict__ inv_qnorm,
                                                            uint32_t *__restrict__ thr_key, uint32_t *__restrict__ cnt,
-                                                           uint32_t *__restrict__ hist, int32_t *__restrict__ cand, int cap)
+                                                           uint32_t *__restrict__ hist, int32_t *__restrict__ cand,
+                                                           float *__restrict__ cand_v, int cap)
 {
     __shared__ uint32_t h[kHistBins];
     __shared__ uint32_t s_cnt;
@@ -496,11 +512,15 @@ __global__ void __launch_bounds__(256) seed_finalize_kernel(const float *__restr
     for (int b = threadIdx.x; b < kHistBins; b += blockDim.x) h[b] = 0;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
+    const float *__restrict__ seed = seed_t + (int64_t)q * seed_ld;  // this query's values, one per seed row
     const float qn = qnorm[q], iqn = inv_qnorm[q];
     if (qn == 0.f) {
         // zero query: every cosine is 0.0 -> the answer is rows 0..k-1 (ties by id); nothing else may pass
         const int m = n_seed < k ? n_seed : k;
-        for (int r = threadIdx.x; r < m && r < cap; r += blockDim.x) cand[(int64_t)q * cap + r] = r;
+        for (int r = threadIdx.x; r < m && r < cap; r += blockDim.x) {
+            cand[(int64_t)q * cap + r] = r;
+            cand_v[(int64_t)q * cap + r] = 0.f;
+        }
         for (int b = threadIdx.x; b < kHistBins; b += blockDim.x) hist[(int64_t)q * kHistBins + b] = 0;
         if (threadIdx.x == 0) {
             cnt[q] = m;
@@ -508,7 +528,31 @@ __global__ void __launch_bounds__(256) seed_finalize_kernel(const float *__restr
         }
         return;
     }
-    for (int r = threadIdx.x; r < n_seed; r += blockDim.x) atomicAdd(&h[cos_bin(seed[(int64_t)r * kMaxN + q] * iqn)], 1u);
+    // Only the top of the distribution matters.  Each thread's largest value is a distinct row, so the k-th largest of
+    // the 256 per-thread maxima (`low`) is a lower bound of the k-th best seed value: rows below it need no histogram
+    // entry (the bins under `low` stay under-counted, which can only make a threshold more conservative), and the
+    // shared-memory atomics no longer pile up on the few bins around cosine 0.
+    __shared__ float s_max[256];
+    __shared__ float s_low;
+    float mine = -INFINITY;
+    for (int r = threadIdx.x; r < n_seed; r += blockDim.x) mine = fmaxf(mine, seed[r]);
+    s_max[threadIdx.x] = mine;
+    if (threadIdx.x == 0) s_low = -INFINITY;
+    __syncthreads();
+    if (k <= (int)blockDim.x) {
+        int above = 0;  // maxima ranked before mine under (value desc, thread asc)
+        for (int t = 0; t < (int)blockDim.x; ++t) {
+            const float o = s_max[t];
+            above += (o > mine || (o == mine && t < (int)threadIdx.x)) ? 1 : 0;
+        }
+        if (above == k - 1) s_low = mine;  // exactly one thread; -inf when fewer than k threads saw a row
+    }
+    __syncthreads();
+    const float low = s_low;
+    for (int r = threadIdx.x; r < n_seed; r += blockDim.x) {
+        const float v = seed[r];
+        if (v >= low) atomicAdd(&h[cos_bin(v * iqn)], 1u);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
@@ -524,9 +568,12 @@ __global__ void __launch_bounds__(256) seed_finalize_kernel(const float *__restr
     const float tv = (thr - margin) * qn;
     for (int b = threadIdx.x; b < kHistBins; b += blockDim.x) hist[(int64_t)q * kHistBins + b] = h[b];
     for (int r = threadIdx.x; r < n_seed; r += blockDim.x) {
-        if (seed[(int64_t)r * kMaxN + q] >= tv) {
+        if (seed[r] >= tv) {
             uint32_t slot = atomicAdd(&s_cnt, 1u);
-            if (slot < (uint32_t)cap) cand[(int64_t)q * cap + slot] = r;
+            if (slot < (uint32_t)cap) {
+                cand[(int64_t)q * cap + slot] = r;
+                cand_v[(int64_t)q * cap + slot] = seed[r];
+            }
         }
     }
     __syncthreads();
@@ -630,12 +677,12 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     if (p.cluster2) grid &= ~1;
     if (!p.dense) profile_mark(0, 0, st);
-    auto launch = [&](auto kernel) -> int {
-        ORAG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    auto launch = [&](auto kernel, size_t smem_bytes) -> int {
+        ORAG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = kSmemBytes;
+        cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -647,20 +694,24 @@ int launch_scan(bool bf16, const void *a_base, int64_t a_rows, const void *q_bas
         ORAG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, p));
         return ORAG_OK;
     };
-    if (p.mma2) rc = bf16 ? launch(cosine_scan_kernel<true, true>) : launch(cosine_scan_kernel<false, true>);
-    else rc = bf16 ? launch(cosine_scan_kernel<true, false>) : launch(cosine_scan_kernel<false, false>);
+    if (p.mma2)
+        rc = bf16 ? launch(cosine_scan_kernel<true, true, kStages2>, scan_smem_bytes(true, kStages2))
+                  : launch(cosine_scan_kernel<false, true, kStages2>, scan_smem_bytes(true, kStages2));
+    else
+        rc = bf16 ? launch(cosine_scan_kernel<true, false, kStages>, scan_smem_bytes(false, kStages))
+                  : launch(cosine_scan_kernel<false, false, kStages>, scan_smem_bytes(false, kStages));
     if (rc) return rc;
     if (!p.dense) profile_mark(0, 1, st);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }
 
-int launch_seed_finalize(const float *seed, int n_seed, int n_queries, int k, float margin, const float *qnorm,
+int launch_seed_finalize(const float *seed, int seed_ld, int n_seed, int n_queries, int k, float margin, const float *qnorm,
                          const float *inv_qnorm, uint32_t *thr_key, uint32_t *cnt, uint32_t *hist, int32_t *cand,
-                         int cap, cudaStream_t st)
+                         float *cand_v, int cap, cudaStream_t st)
 {
-    seed_finalize_kernel<<<n_queries, 256, 0, st>>>(seed, n_seed, n_queries, k, margin, qnorm, inv_qnorm, thr_key, cnt,
-                                                    hist, cand, cap);
+    seed_finalize_kernel<<<n_queries, 256, 0, st>>>(seed, seed_ld, n_seed, n_queries, k, margin, qnorm, inv_qnorm, thr_key, cnt,
+                                                    hist, cand, cand_v, cap);
     ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }

@@ -85,7 +85,8 @@ int launch_cosine_dense(const float *corpus, int64_t n_rows, int dim, const floa
                         const double *sq_q, double *out, cudaStream_t st, double *raw_row_sq = nullptr);
 int launch_prefilter(const float *corpus, int dim, const float *queries, const float *inv_qnorm, const int32_t *cand,
                      const uint32_t *cnt, int cap, int n_queries, int k, float *cos32, int cap2, int32_t *surv,
-                     uint32_t *surv_cnt, int32_t *status, cudaStream_t st);
+                     uint32_t *surv_cnt, int32_t *status, cudaStream_t st, const uint32_t *thr_key = nullptr,
+                     const float *qnorm_scan = nullptr, float margin = 0.f);
 int launch_rescore(const float *corpus, int dim, int64_t row_id_base, const float *queries, const double *sq_q,
                    const int32_t *cand, const uint32_t *cnt, int cap, int n_queries, const double *row_sq,
                    double *out_scores, int64_t *out_ids, cudaStream_t st);

@@ -9,12 +9,11 @@
 // acquires the G sequence numbers in the rank's OWN buffer, after which the slot is exactly the
 // [G, B, W] array orag_hybrid_merge reads.  Two launches replace ~6 packing kernels + the collective.
 //
-// Buffer of one rank (orag_exchange_bytes):   uint64 seq[4][G] (padded to 256 B) | int64 slot[4][G * max_queries * W]
-// A search with sequence number s uses slot s & 3, and callers may keep two searches in flight on two streams
-// ("lanes": even and odd sequence numbers, each lane in stream order).  Re-use is safe with four slots: rank r writes
-// slot s&3 of peer p for search s+4 after -- same lane, stream order -- its own wait for search s+2 returned, i.e.
-// after p published s+2, which p does (its lane of s, stream order) after its merge of search s has finished reading
-// that slot.
+// Buffer of one rank (orag_exchange_bytes):   uint64 seq[6][G] (padded to 256 B) | int64 slot[6][G * max_queries * W]
+// A search with sequence number s uses slot s % 6, and callers may keep three searches in flight on three streams
+// ("lanes": lane = s % 3, each lane in stream order).  Re-use is safe with 2 x lanes slots: rank r writes slot s % 6 of
+// peer p for search s+6 after -- same lane, stream order -- its own wait for search s+3 returned, i.e. after p
+// published s+3, which p does (its lane of s, stream order) after its merge of search s has finished reading that slot.
 //
 // A wait that does not see a peer's sequence number within the timeout does not hang the GPU: it sets
 // ORAG_STATUS_EXCHANGE_TIMEOUT in the status word of every query of that shard's block, which the merge ORs
@@ -25,7 +24,7 @@
 
 namespace orag {
 
-constexpr int kXSlots = 4;
+constexpr int kXSlots = 6;  // 2 x lanes (see above)
 constexpr int kXMaxShards = 64;
 
 static inline size_t x_flag_bytes(int n_shards) { return align_up((size_t)kXSlots * n_shards * 8, 256); }
@@ -60,7 +59,7 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(
     unsigned long long seq)
 {
     const int p = blockIdx.x;
-    const int slot = (int)(seq & (unsigned long long)(kXSlots - 1));
+    const int slot = (int)(seq % (unsigned long long)kXSlots);
     const int W = 2 * fetch_k + 2 * kk + 2;
     uint8_t *base = (uint8_t *)peers[p];
     int64_t *dst = (int64_t *)(base + flag_bytes) + (size_t)slot * slot_words + (size_t)rank * B * W;
@@ -90,7 +89,7 @@ __global__ void __launch_bounds__(kXMaxShards) exchange_wait_kernel(uint8_t *min
 {
     const int g = threadIdx.x;
     if (g >= G) return;
-    const int slot = (int)(seq & (unsigned long long)(kXSlots - 1));
+    const int slot = (int)(seq % (unsigned long long)kXSlots);
     const unsigned long long *flag = (const unsigned long long *)mine + (size_t)slot * G + g;
     const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(flag) < seq) {
@@ -165,6 +164,7 @@ extern "C" int orag_hybrid_push(const int64_t *d_cos_ids, const double *d_cos_sc
     ORAG_REQUIRE(n_shards >= 1 && n_shards <= kXMaxShards && rank >= 0 && rank < n_shards, "hybrid_push shards");
     ORAG_REQUIRE(n_queries >= 1 && n_queries <= max_queries && fetch_k >= 1 && kk >= fetch_k && seq >= 1,
                  "hybrid_push sizes");
+    orag::TimelineScope tl(orag::TL_PUSH, (cudaStream_t)stream);
     exchange_push_kernel<<<n_shards, 256, 0, (cudaStream_t)stream>>>(
         d_cos_ids, d_cos_scores, d_bm25_ids, d_bm25_scores, d_bm25_max, d_status, d_status2, n_queries, fetch_k, kk, rank,
         n_shards,
@@ -182,10 +182,11 @@ extern "C" int orag_hybrid_wait(void *d_buf, int n_shards, int max_queries, int 
                  "hybrid_wait sizes");
     const size_t fb = x_flag_bytes(n_shards), sw = x_slot_words(n_shards, max_queries, fetch_k, kk);
     const int W = 2 * fetch_k + 2 * kk + 2;
+    orag::TimelineScope tl(orag::TL_WAIT, (cudaStream_t)stream);
     exchange_wait_kernel<<<1, kXMaxShards, 0, (cudaStream_t)stream>>>((uint8_t *)d_buf, n_shards, n_queries, W, fb, sw,
                                                                       (unsigned long long)seq,
                                                                       (unsigned long long)timeout_ms * 1000000ull);
     ORAG_LAUNCH_CHECK();
-    *d_gathered = (const int64_t *)((uint8_t *)d_buf + fb) + (size_t)(seq & (uint64_t)(kXSlots - 1)) * sw;
+    *d_gathered = (const int64_t *)((uint8_t *)d_buf + fb) + (size_t)(seq % (uint64_t)kXSlots) * sw;
     return ORAG_OK;
 }

@@ -230,6 +230,7 @@ extern "C" int orag_rrf_fuse_pair(const int64_t *d_ids_a, const int64_t *d_ids_b
     ORAG_REQUIRE(n_queries >= 0 && list_len >= 1 && 2 * list_len <= orag::kRrfMaxUnion && top_k >= 1 && rrf_k >= 0,
                  "rrf_fuse_pair sizes (2 * list_len <= 128)");
     if (n_queries == 0) return ORAG_OK;
+    orag::TimelineScope tl(orag::TL_RRF, (cudaStream_t)stream);
     orag::rrf_pair_kernel<<<(n_queries + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         d_ids_a, d_ids_b, n_queries, list_len, rrf_k, top_k, tie_mode, d_status_a, d_status_b, d_out_ids, d_out_scores,
         d_out_src, d_out_status);
@@ -249,6 +250,7 @@ extern "C" int orag_hybrid_merge(const int64_t *d_gathered, int n_shards, int n_
                  "hybrid_merge sizes");
     ORAG_REQUIRE(n_shards * kk <= orag::kMergeMax && fetch_k <= 64, "n_shards * kk <= 256 and fetch_k <= 64");
     if (n_queries == 0) return ORAG_OK;
+    orag::TimelineScope tl(orag::TL_MERGE, (cudaStream_t)stream);
     orag::hybrid_merge_kernel<<<n_queries, 64, 0, (cudaStream_t)stream>>>(
         d_gathered, n_shards, n_queries, fetch_k, kk, rrf_k, top_k, tie_mode, d_out_ids, d_out_scores, d_out_src,
         d_cos_ids, d_cos_scores, d_bm25_ids, d_bm25_scores, d_bm25_max, d_out_status);

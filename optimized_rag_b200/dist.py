@@ -35,6 +35,11 @@ logger = logging.getLogger(__name__)
 # the k-th value's group with mixed raw values and flags the query, and the repair path (`_exact_lists_global_max`)
 # exchanges the maxima first and ranks by the normalised value on every shard.
 BM25_GUARD = 6
+# Searches in flight per ShardedHybrid (`submit`): lane = sequence number % LANES, each lane with its own stream and
+# workspaces.  The tails of the batches cannot run while a scan and the background BM25 CTA fill the SMs, so the steady
+# state is LANES scans back to back, then the tails of all of them together: three lanes amortise that phase better than
+# two (1.25M rows per GPU: 1.24 -> 1.21 ms per batch).  The peer exchange has 2 x LANES slots (csrc/exchange.cu).
+LANES = 3
 
 
 def shard_range(n_total: int, rank: int, world: int):
@@ -284,6 +289,7 @@ class ShardedHybrid:
         self._retired: list[PeerExchange] = []  # outgrown exchanges: peers may still have them mapped until close()
         self._searches = 0            # searches issued so far (all ranks count alike): lane = parity of the next one
         self._lane_streams: dict = {}
+        self.lanes = LANES
 
     def _exchange(self, lists, fetch_k: int, kk: int, k: int, lane: int = 0):
         ci, cs, bi, bs, bm, st, st2 = lists
@@ -329,8 +335,8 @@ class ShardedHybrid:
         fetch_k = fetch_k or k
         if self._poisoned:
             raise _ffi.OragError(f"sharded search is shut down: {self._poisoned}")
-        if lane is None:  # the lane of a search is the parity of its exchange sequence number (PeerExchange slots)
-            lane = (self._searches + 1) & 1
+        if lane is None:  # the lane of a search follows from its exchange sequence number (PeerExchange slots)
+            lane = (self._searches + 1) % LANES
         self._searches += 1
         if self.world == 1:
             return self.shard.search(query_emb, query_terms, query_lens, k, fetch_k, check_overflow, lane=lane)
@@ -363,7 +369,7 @@ class ShardedHybrid:
             # the repair exchange takes a sequence number (and an all-gather buffer) of its own; it is a synchronous
             # path: callers that keep batches in flight (`submit`) drain them before repairing
             self._searches += 1
-            fixed, _ = self._exchange((*lists, zero, None), fetch_k, kk, k, lane=2)
+            fixed, _ = self._exchange((*lists, zero, None), fetch_k, kk, k, lane=LANES)
             fixed["bm25_max"] = gmax
             for key, val in fixed.items():
                 out[key][bad] = val
@@ -407,7 +413,7 @@ class ShardedHybrid:
         `status` word: non-zero = that query must be repeated through `search(check_overflow=True)`).  Every rank
         must submit the same sequence of batches."""
         dev = query_emb.device
-        lane = (self._searches + 1) & 1
+        lane = (self._searches + 1) % LANES
         if lane not in self._lane_streams:
             self._lane_streams[lane] = torch.cuda.Stream(dev)
         stream = self._lane_streams[lane]

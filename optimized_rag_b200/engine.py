@@ -155,13 +155,7 @@ class CosineIndex:
         ids = torch.empty((Bq, k), dtype=torch.int64, device=self.device)
         sc = torch.empty((Bq, k), dtype=torch.float64, device=self.device)
         status = torch.empty(Bq, dtype=torch.int32, device=self.device)
-        ws = self._workspace(Bq, k, m, lane)
-        _ffi.check(_ffi.lib().orag_cosine_topk(
-            self.corpus.data_ptr(), self.inv_norm.data_ptr() if self.inv_norm is not None else None,
-            self.shadow.data_ptr() if self.shadow is not None else None,
-            self.row_sq.data_ptr() if (self.row_sq is not None and m != _ffi.ORAG_COS_EXACT) else None,
-            self.n_rows, self.dim, self.row_id_base, queries.data_ptr(), Bq, k, m, ids.data_ptr(), sc.data_ptr(), status.data_ptr(), ws.data_ptr(),
-            ws.numel(), _stream(self.device)), "orag_cosine_topk")
+        self._call(queries, k, m, ids, sc, status, lane, _ffi.ORAG_PHASE_ALL)
         if status_out is not None:
             status_out.append(status)
         if check_overflow and m != _ffi.ORAG_COS_EXACT:
@@ -171,6 +165,58 @@ class CosineIndex:
                 i2, s2 = self.topk(queries[bad].contiguous(), k, mode="exact", check_overflow=False, lane=lane)
                 ids[bad], sc[bad] = i2, s2
         return ids, sc
+
+    def _call(self, queries, k, m, ids, sc, status, lane, phases):
+        Bq = queries.shape[0]
+        ws = self._workspace(Bq, k, m, lane)
+        _ffi.check(_ffi.lib().orag_cosine_topk_phase(
+            self.corpus.data_ptr(), self.inv_norm.data_ptr() if self.inv_norm is not None else None,
+            self.shadow.data_ptr() if self.shadow is not None else None,
+            self.row_sq.data_ptr() if (self.row_sq is not None and m != _ffi.ORAG_COS_EXACT) else None,
+            self.n_rows, self.dim, self.row_id_base, queries.data_ptr(), Bq, k, m, ids.data_ptr(), sc.data_ptr(),
+            status.data_ptr(), ws.data_ptr(), ws.numel(), phases, _stream(self.device)), "orag_cosine_topk_phase")
+
+    def topk_scan(self, queries: torch.Tensor, k: int, lane: int = 0, stream: "torch.cuda.Stream | None" = None):
+        """First half of `topk` (tensor-core modes, <= 256 queries; orag_cosine_topk_phase): query preparation on the
+        current stream, then seed pass and main scan on `stream` (default: the current one), ordered after everything
+        the current stream holds; the candidates stay in the lane's workspace.  The output tensors are allocated here, on
+        the CURRENT stream -- the one `topk_finish` will run on.  Returns the handle `topk_finish` takes; the caller
+        orders that stream after `stream`."""
+        _require_cuda(queries, "queries")
+        assert queries.dtype == torch.float32 and queries.is_contiguous() and queries.shape[1] == self.dim
+        m = MODE[self.mode]
+        if m == _ffi.ORAG_COS_EXACT or queries.shape[0] > 256:
+            raise _ffi.OragError("topk_scan: tensor-core modes and at most 256 queries")
+        Bq = queries.shape[0]
+        ids = torch.empty((Bq, k), dtype=torch.int64, device=self.device)
+        sc = torch.empty((Bq, k), dtype=torch.float64, device=self.device)
+        status = torch.empty(Bq, dtype=torch.int32, device=self.device)
+        # query conversion / norms on the CURRENT stream: they run as soon as the inputs are there, next to whatever scan
+        # occupies the SMs, not in the gap between two scans
+        self._call(queries, k, m, ids, sc, status, lane, _ffi.ORAG_PHASE_PREP)
+        if stream is None:
+            self._call(queries, k, m, ids, sc, status, lane, _ffi.ORAG_PHASE_SCAN)
+        else:
+            stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(stream):
+                self._call(queries, k, m, ids, sc, status, lane, _ffi.ORAG_PHASE_SCAN)
+        return queries, k, m, ids, sc, status, lane
+
+    def last_counts(self, n_queries: int, k: int, lane: int = 0):
+        """(first-pass candidates, fp32 survivors) per query of the last tensor-core search of `lane` (diagnostic)."""
+        import numpy as np
+        ws = self._workspace(n_queries, k, MODE[self.mode], lane)
+        c = np.zeros(n_queries, dtype=np.uint32)
+        v = np.zeros(n_queries, dtype=np.uint32)
+        _ffi.check(_ffi.lib().orag_cosine_last_counts(ws.data_ptr(), self.dim, n_queries, c.ctypes.data, v.ctypes.data,
+                                                      _stream(self.device)), "orag_cosine_last_counts")
+        return c, v
+
+    def topk_finish(self, handle):
+        """Second half: candidate re-scores and selection on the current stream -> (ids, scores, status)."""
+        queries, k, m, ids, sc, status, lane = handle
+        self._call(queries, k, m, ids, sc, status, lane, _ffi.ORAG_PHASE_FINISH)
+        return ids, sc, status
 
     def dense(self, queries: torch.Tensor) -> torch.Tensor:
         """float64 cosine matrix [B, n_rows] (reference arithmetic; tests, small corpora, weighted hybrid)."""
@@ -411,6 +457,8 @@ class HybridShard:
         self.bm25 = bm25
         self.rrf_k = rrf_k
         self._side: dict = {}   # lane -> side stream of the BM25 pipeline
+        self._head = None       # the stream every scan of this shard is enqueued on (co-scheduled searches)
+        self.head_stream = os.environ.get("ORAG_HEAD_STREAM", "0") == "1"
         # BM25 first pass NEXT TO the scan (see local_lists): ORAG_COSCHEDULE=0/1 forces it, default on
         self.coschedule = os.environ.get("ORAG_COSCHEDULE", "1") == "1"
 
@@ -441,11 +489,29 @@ class HybridShard:
             # resident scan CTA of every SM, on the issue slots the tensor-bound scan leaves idle.  Measured on B200
             # with two batches in flight (bench.py --rows R): 1.25M rows 1.33 -> 1.28 ms/step, 2.5M 2.25 -> 2.20,
             # 5M 4.11 -> 3.83 (ORAG_COSCHEDULE=0 turns it off).
-            ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=False, status_out=st_c, lane=lane)
+            # All scans go back to back on ONE high-priority stream (`_head`); the tails -- candidate re-scores,
+            # selection, and whatever the caller appends: fusion, exchange, merge -- stay on the caller's (lane) stream.
+            # With the whole pipeline of a batch on its lane's stream, the next batch of that lane could not start its
+            # query preparation and seed pass before those tails had drained, and the tails cannot run while a scan CTA
+            # and a background BM25 CTA fill every SM's shared memory: the scans ended up ~0.14 ms apart.
+            if query_emb.shape[0] <= 256 and self.head_stream:
+                if self._head is None:
+                    self._head = torch.cuda.Stream(dev, priority=-1)
+                # (topk_scan orders _head after cur: inputs ready, the lane's workspace free -- tails of its last batch)
+                handle = self.cosine.topk_scan(query_emb, fetch_k, lane=lane, stream=self._head)
+                scanned = torch.cuda.Event()
+                scanned.record(self._head)
+            else:
+                handle = None
+                ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=False, status_out=st_c, lane=lane)
             with torch.cuda.stream(side):
-                _ffi.check(L.orag_stream_wait_prescan(side.cuda_stream), "orag_stream_wait_prescan")
+                # (ORAG_BM25_BACKGROUND: the first-pass launch waits for the pre-scan event recorded just above)
                 bi, bs, bmax = self.bm25.topk(query_terms, query_lens, bm25_k, normalize=normalize,
                                               check_overflow=False, status_out=st_b, background=True, lane=lane)
+            if handle is not None:
+                cur.wait_event(scanned)
+                ci, cs, st = self.cosine.topk_finish(handle)
+                st_c.append(st)
         else:
             with torch.cuda.stream(side):
                 bi, bs, bmax = self.bm25.topk(query_terms, query_lens, bm25_k, normalize=normalize,

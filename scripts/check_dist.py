@@ -51,6 +51,15 @@ for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("tf32", "f16")):
                 ok &= same
                 print(f"[{mode}/{exchange}] world={world} rows={N}: {key:12s} {'identical' if same else 'DIFFERENT'}",
                       flush=True)
+        # which of the two first passes flags candidate overflow on this shard (flagged queries are repaired: correct, slower)
+        for cos_on in (True, False):
+            shard.coschedule = cos_on
+            for lane in range(3):
+                ll = shard.local_lists(q_emb, qt, ql, K, K + 6, False, lane=lane)
+                torch.cuda.synchronize()
+                print(f"[{mode}/{exchange}] rank {rank} coschedule {cos_on} lane {lane}: cosine flagged "
+                      f"{int((ll[5] != 0).sum())}, bm25 flagged {int((ll[6] != 0).sum())}", flush=True)
+        shard.coschedule = True
         # the repair path (every query forced through it): maxima first, ranking by the normalised value on every shard
         import os
         os.environ["ORAG_TEST_FORCE_REPAIR"] = "1"
@@ -67,8 +76,15 @@ for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("tf32", "f16")):
         torch.cuda.synchronize()
         if rank == 0:
             same = all(torch.equal(o[key], ref[key]) for o in outs for key in KEYS)
+            flagged = [int((o["status"] != 0).sum()) for o in outs]
+            same &= not any(flagged)
             ok &= same
-            print(f"[{mode}/{exchange}] 6 submitted batches (two in flight): {'identical' if same else 'DIFFERENT'}", flush=True)
+            print(f"[{mode}/{exchange}] 6 submitted batches (three in flight): {'identical' if same else 'DIFFERENT'}", flush=True)
+            if not same:
+                for i, o in enumerate(outs):
+                    diff = [key for key in KEYS if not torch.equal(o[key], ref[key])]
+                    print(f"    batch {i}: differing {diff}; flagged queries {flagged[i]}; status bits "
+                          f"{sorted(set(o['status'].tolist()))}", flush=True)
         # device time and host time per step of back-to-back searches (no host sync inside)
         for _ in range(5):
             sh.search(q_emb, qt, ql, K, check_overflow=False)

@@ -362,7 +362,7 @@ def test_peer_exchange_kernels_two_virtual_ranks(eng):
     G, maxq, fk, kk, k = 2, 64, 10, 16, 10
     W = 2 * fk + 2 * kk + 2
     nbytes = int(L.orag_exchange_bytes(G, maxq, fk, kk))
-    assert nbytes == 256 + 4 * G * maxq * W * 8   # flags (padded) + four slots
+    assert nbytes == 256 + 6 * G * maxq * W * 8   # flags (padded) + six slots
     bufs = []
     for _ in range(G):
         p = ctypes.c_void_p()
@@ -372,7 +372,7 @@ def test_peer_exchange_kernels_two_virtual_ranks(eng):
         d_peers = torch.tensor(bufs, dtype=torch.int64, device=DEV)
         st = torch.cuda.current_stream().cuda_stream
         rng = np.random.default_rng(5)
-        for seq, B in enumerate([64, 64, 37, 64, 1], start=1):
+        for seq, B in enumerate([64, 64, 37, 64, 1, 64, 5, 64], start=1):   # wraps around the six slots
             lists = [_random_lists(rng, g, B, fk, kk) for g in range(G)]
             for g in range(G):
                 _ffi.check(L.orag_hybrid_push(*[t.data_ptr() for t in lists[g]], None, B, fk, kk, g, G, maxq,
@@ -382,7 +382,7 @@ def test_peer_exchange_kernels_two_virtual_ranks(eng):
             for g in range(G):
                 out = ctypes.c_void_p()
                 _ffi.check(L.orag_hybrid_wait(bufs[g], G, maxq, B, fk, kk, seq, 2000, ctypes.byref(out), st), "wait")
-                assert out.value == bufs[g] + 256 + (seq & 3) * G * maxq * W * 8
+                assert out.value == bufs[g] + 256 + (seq % 6) * G * maxq * W * 8
                 got, status = hybrid_merge(out.value, fk, kk, 60, k, shape=(G, B, W), device=torch.device(DEV))
                 for key in ref:
                     assert torch.equal(got[key], ref[key]), (seq, g, key)
@@ -739,9 +739,12 @@ print("cluster ok")
         assert r.returncode == 0 and "cluster ok" in r.stdout, (two_sm, r.stdout + r.stderr)
 
 
-def test_submit_keeps_two_batches_in_flight_and_equals_search(eng):
-    """ShardedHybrid.submit (two lanes: own streams, workspaces, exchange slots) over a sequence of DIFFERENT batches:
-    every ticket's result equals the plain search of its batch, bit for bit, whatever order the lanes finish in."""
+@pytest.mark.parametrize("head_stream", [False, True])
+def test_submit_keeps_batches_in_flight_and_equals_search(eng, head_stream):
+    """ShardedHybrid.submit (three lanes: own streams, workspaces, exchange slots) over a sequence of DIFFERENT batches:
+    every ticket's result equals the plain search of its batch, bit for bit, whatever order the lanes finish in.
+    head_stream=True drives the cosine search through the split entry point (orag_cosine_topk_phase: preparation on the
+    lane's stream, every scan on one shared stream, re-scores and selection back on the lane's stream)."""
     from optimized_rag_b200.bm25_index import Bm25Index
     from optimized_rag_b200.dist import ShardedHybrid
     n, dim, vocab, k = 30000, 256, 3000, 10
@@ -750,6 +753,7 @@ def test_submit_keeps_two_batches_in_flight_and_equals_search(eng):
     doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, 20, 80, thr)
     sh = ShardedHybrid(eng.HybridShard(eng.CosineIndex(_t(corpus), mode="f16"),
                                        Bm25Index(_t(doc_off), _t(tok), vocab, tile_docs=1024)))
+    sh.shard.head_stream = head_stream
     batches = []
     for i, nq in enumerate([64, 17, 64, 1, 40, 64, 64]):
         q = syn.query_embeddings(nq, n, dim, query_seed=syn.SEED_QUERIES + i, dup_per_mille=5)
@@ -833,3 +837,29 @@ def test_cosine_dim_3072_with_planted_near_ties(eng, mode):
     assert np.array_equal(_bits(sc.cpu().numpy()), _bits(want_s))
     gaps = np.diff(want_s, axis=1)
     assert (np.abs(gaps) < 1e-5).sum() >= nq * 5         # the planted rows really are the ones being ranked
+
+
+@pytest.mark.parametrize("n_docs", [8192 + 2000, 3 * 8192 + 700])
+def test_bm25_first_pass_on_a_mostly_empty_last_tile(n_docs):
+    """A shard whose last 8192-doc first-pass tile holds a fraction of the docs: the doc sub-ranges of a cold, dense
+    (query, tile) pair must be cut from the tile's own doc range -- equal slices of the full tile put every posting
+    into the first few sub-ranges and overflowed the per-warp accumulator (flagged queries, repaired, but on every
+    batch).  No query may be flagged, in the stand-alone and in the background configuration, and the lists must equal
+    the dense path's."""
+    from optimized_rag_b200 import engine
+    from optimized_rag_b200.bm25_index import Bm25Index, Bm25Plan
+    vocab = 50000
+    thr = syn.zipf_thresholds(vocab)
+    off, tok = engine.gen_token_corpus(n_docs, 0, syn.SEED_TOKENS, thr, vocab, 100, 300, device=torch.device(DEV))
+    ix = Bm25Index.from_plan(Bm25Plan(off, tok, vocab))
+    assert ix.struct.fp_tile_docs == 8192
+    qt, ql = syn.keyword_queries(256, vocab, thresholds=thr)
+    qt, ql = torch.from_numpy(qt).to(DEV), torch.from_numpy(ql).to(DEV)
+    for k in (10, 16):
+        want = ix.topk(qt, ql, k, normalize=False, force="dense", check_overflow=False)
+        for background in (False, True):
+            st = []
+            got = ix.topk(qt, ql, k, normalize=False, check_overflow=False, status_out=st, background=background)
+            assert int((st[0] != 0).sum()) == 0, (k, background, sorted(set(st[0].tolist())))
+            for g, w in zip(got, want):
+                assert torch.equal(g, w), (k, background)

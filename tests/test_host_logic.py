@@ -193,12 +193,12 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu(built_lib):
     assert L.orag_version() == 1
     # size queries
     W = 2 * 10 + 2 * 16 + 2
-    assert L.orag_exchange_bytes(8, 256, 10, 16) == 256 + 4 * 8 * 256 * W * 8   # flags (padded) + four slots
+    assert L.orag_exchange_bytes(8, 256, 10, 16) == 512 + 6 * 8 * 256 * W * 8   # flags (6 slots x 8 shards x 8 B, padded to 256) + six slots
     assert L.orag_exchange_bytes(0, 256, 10, 16) == 0
     assert L.orag_cosine_workspace_bytes(1000, 1536, 0, 10, _ffi.ORAG_COS_F16) == 0
     small = L.orag_cosine_workspace_bytes(1000, 1536, 4, 10, _ffi.ORAG_COS_EXACT)
     assert small >= 4 * 8 + 4 * 1000 * 8
-    assert L.orag_cosine_workspace_bytes(10_000_000, 1536, 256, 10, _ffi.ORAG_COS_F16) < 16 << 20
+    assert L.orag_cosine_workspace_bytes(10_000_000, 1536, 256, 10, _ffi.ORAG_COS_F16) < 24 << 20
     # argument validation
     rc = L.orag_cosine_topk(None, None, None, None, 10, 1536, 0, None, 4, 10, _ffi.ORAG_COS_F16, None, None, None, None, 0,
                             None)
