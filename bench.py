@@ -625,11 +625,14 @@ def run_hybrid_like(args):
     # hide behind the scan on leftover SM resources, and its own duration says nothing about the kernel)
     shard_obj = getattr(sh, "shard", None)
     cosched = bool(shard_obj is not None and shard_obj.coschedule)
-    if cosched:
-        shard_obj.coschedule = False
+    if shard_obj is not None:
+        shard_obj.coschedule, shard_obj.serial = False, True
     brackets = h.kernel_brackets(lambda: sh.search(*devt, k, check_overflow=False))
-    if cosched:
-        shard_obj.coschedule = True
+    if shard_obj is not None:
+        shard_obj.coschedule, shard_obj.serial = cosched, False
+    if os.environ.get("ORAG_BENCH_DEBUG") and rank == 0:
+        print("plain-step brackets (ms): scan", [round(x, 3) for x in brackets[0]], "bm25", [round(x, 3) for x in brackets[1]],
+              file=sys.stderr, flush=True)
     # per-rank view of the two dominant kernels (mean launch duration: plain steps / inside the submitted loop): the
     # sharded step runs at the pace of the slowest GPU of the box
     per_rank = None

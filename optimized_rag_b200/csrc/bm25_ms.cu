@@ -236,7 +236,6 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
         const int qi0 = (int)(((int64_t)nq * part) / S);
         const int qi1 = (int)(((int64_t)nq * (part + 1)) / S);
         const int64_t base_doc = (int64_t)tile * T;
-        const int tile_docs = (int)min((int64_t)T, (int64_t)p.ix.n_docs - base_doc);
         const uint32_t *tp = p.ix.d_postings_r16 + p.ix.d_fp_tile_base[tile];  // 16-byte aligned (padded layout)
         const uint4 *tp4 = reinterpret_cast<const uint4 *>(tp);
         const int32_t *toff = p.ix.d_fp_tile_term_off + (int64_t)tile * V1;
@@ -292,13 +291,14 @@ __global__ void __launch_bounds__(kMsThreads, 2) bm25_ms_kernel(const __grid_con
             if (ess) {
                 // essential postings of the pair; more than the accumulator holds -> doc sub-ranges
                 const int etot = __reduce_add_sync(FULL, (mine_ok && lane >= n_ne) ? cur.len4 * 4 : 0);
-                // (the doc range that is split is the tile's OWN: the last tile of a shard may hold a fraction of T docs, and
-                // equal slices of T would put all of its postings into the first few sub-ranges; a sub-range of at most
-                // `cap` docs cannot overflow whatever the postings are, so the halving stops there)
-                int nsub = 1, sub_docs = tile_docs;
-                while (nsub * (etot > cap ? (cap >> 1) : cap) < etot && sub_docs > 32 && sub_docs > cap) {
+                // (the doc range that is split is the tile's OWN, rounded up to a power of two: the last tile of a shard may
+                // hold a fraction of T docs, and equal slices of T would put all of its postings into the first few
+                // sub-ranges; the rounding costs at most a factor of two, which the cap / 2 target absorbs)
+                const int64_t left = (int64_t)p.ix.n_docs - (int64_t)tile * T;
+                int nsub = 1, sub_docs = left >= T ? T : 1 << (32 - __clz((int)left - 1 | 31));
+                while (nsub * (etot > cap ? (cap >> 1) : cap) < etot && sub_docs > 32) {
                     nsub <<= 1;
-                    sub_docs = (tile_docs + nsub - 1) / nsub;
+                    sub_docs >>= 1;
                 }
                 int cpos = 0;  // this lane's run: first posting of the current sub-range
                 for (int sub = 0; sub < nsub; ++sub) {

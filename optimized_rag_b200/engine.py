@@ -459,6 +459,7 @@ class HybridShard:
         self._side: dict = {}   # lane -> side stream of the BM25 pipeline
         self._head = None       # the stream every scan of this shard is enqueued on (co-scheduled searches)
         self.head_stream = os.environ.get("ORAG_HEAD_STREAM", "0") == "1"
+        self.serial = False     # no side stream at all (measurement: see local_lists)
         # BM25 first pass NEXT TO the scan (see local_lists): ORAG_COSCHEDULE=0/1 forces it, default on
         self.coschedule = os.environ.get("ORAG_COSCHEDULE", "1") == "1"
 
@@ -513,7 +514,9 @@ class HybridShard:
                 ci, cs, st = self.cosine.topk_finish(handle)
                 st_c.append(st)
         else:
-            with torch.cuda.stream(side):
+            # (`serial`: both pipelines on the caller's stream, one after the other -- what bench.py brackets the two
+            # dominant kernels in, each with the whole GPU)
+            with torch.cuda.stream(cur if self.serial else side):
                 bi, bs, bmax = self.bm25.topk(query_terms, query_lens, bm25_k, normalize=normalize,
                                               check_overflow=False, status_out=st_b, lane=lane)
             ci, cs = self.cosine.topk(query_emb, fetch_k, check_overflow=False, status_out=st_c, lane=lane)

@@ -851,7 +851,7 @@ def test_bm25_first_pass_on_a_mostly_empty_last_tile(n_docs):
     vocab = 50000
     thr = syn.zipf_thresholds(vocab)
     off, tok = engine.gen_token_corpus(n_docs, 0, syn.SEED_TOKENS, thr, vocab, 100, 300, device=torch.device(DEV))
-    ix = Bm25Index.from_plan(Bm25Plan(off, tok, vocab))
+    ix = Bm25Index.from_plan(Bm25Plan(off, tok, vocab, fp_tile_docs=8192))
     assert ix.struct.fp_tile_docs == 8192
     qt, ql = syn.keyword_queries(256, vocab, thresholds=thr)
     qt, ql = torch.from_numpy(qt).to(DEV), torch.from_numpy(ql).to(DEV)
