@@ -228,7 +228,15 @@ typedef struct orag_bm25_index {
     int32_t fp_n_tiles;                 /* ceil(n_docs / fp_tile_docs) */
     const int64_t *d_fp_tile_base;      /* [fp_n_tiles + 1] */
     const int32_t *d_fp_tile_term_off;  /* [fp_n_tiles, vocab + 1] */
+    /* Optional threshold warm start of the first pass (NULL = start cold): d_term_kth_r[l * vocab + t] = the K_l-th
+     * largest fp16 impact among this shard's postings of term t, K = {10, 16, 32, 64, 128}, 0 when the term has fewer
+     * postings (orag_bm25_term_kth).  K_l docs score at least weight(t) * that value whatever else they contain (all
+     * contributions are >= 0), so max over a query's terms is a lower bound of its K_l-th best score: the first pass
+     * starts with the frequent, low-idf terms already non-essential instead of scoring whole tiles until the running
+     * threshold has caught up. */
+    const float *d_term_kth_r;          /* [ORAG_BM25_KTH_LEVELS, vocab] */
 } orag_bm25_index_t;
+#define ORAG_BM25_KTH_LEVELS 5
 
 /* ---------------------------------------------------------------------------
  * Index build (ingest): token corpus -> the two posting tilings above.  Replaces what `BM25Okapi(tokenized_corpus)`
@@ -251,6 +259,8 @@ typedef struct orag_bm25_index {
  *   (16-byte aligned) and d_term_max_r [vocab], or both NULL for an index without first-pass view.
  * ------------------------------------------------------------------------- */
 size_t orag_bm25_build_workspace_bytes(int64_t n_docs, int vocab, int tile_docs, int fp_tile_docs);
+/* After the fill: d_term_kth_r [ORAG_BM25_KTH_LEVELS, vocab] from the first-pass view of `index` (see the struct). */
+int orag_bm25_term_kth(const orag_bm25_index_t *index, float *d_term_kth_r, void *stream);
 int orag_bm25_index_plan(const int64_t *d_doc_off, const int32_t *d_tokens, int64_t n_docs, int vocab, int tile_docs,
                          int fp_tile_docs, int64_t token_pos_base, int32_t *d_doc_len, int64_t *d_df,
                          int64_t *d_first_pos, int64_t *d_tile_base, int32_t *d_tile_term_off, int64_t *d_fp_tile_base,

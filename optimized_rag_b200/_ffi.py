@@ -15,6 +15,7 @@ ORAG_STATUS_OVERFLOW = 1
 ORAG_STATUS_EXCHANGE_TIMEOUT = 2
 ORAG_BM25_NORMALIZE, ORAG_BM25_FORCE_SPARSE, ORAG_BM25_FORCE_DENSE, ORAG_BM25_EXACT_TILES = 1, 2, 4, 8
 ORAG_BM25_BACKGROUND = 16
+ORAG_BM25_KTH_LEVELS = 5
 ORAG_PHASE_SCAN, ORAG_PHASE_FINISH, ORAG_PHASE_PREP, ORAG_PHASE_ALL = 1, 2, 4, 7
 
 # every symbol include/orag.h declares (tests check the .so exports each one)
@@ -25,7 +26,7 @@ SYMBOLS = [
     "orag_row_inv_norms", "orag_row_sq", "orag_f32_to_bf16", "orag_f32_to_f16_rows",
     "orag_cosine_mark_prescan", "orag_stream_wait_prescan",
     "orag_cosine_workspace_bytes", "orag_cosine_topk", "orag_cosine_topk_phase", "orag_cosine_last_counts", "orag_cosine_dense", "orag_dot_dense", "orag_cosine_firstpass_dense",
-    "orag_bm25_build_workspace_bytes", "orag_bm25_index_plan", "orag_bm25_index_fill",
+    "orag_bm25_build_workspace_bytes", "orag_bm25_index_plan", "orag_bm25_index_fill", "orag_bm25_term_kth",
     "orag_bm25_workspace_bytes", "orag_bm25_topk", "orag_bm25_dense", "orag_dense_topk",
     "orag_topk_merge", "orag_rrf_fuse", "orag_rrf_fuse_pair", "orag_hybrid_merge", "orag_weighted_sum3", "orag_div_scalar",
     "orag_pairwise_workspace_bytes", "orag_pairwise_cosine_threshold",
@@ -62,6 +63,7 @@ class Bm25IndexStruct(Structure):
         ("fp_n_tiles", c_int32),
         ("d_fp_tile_base", c_void_p),
         ("d_fp_tile_term_off", c_void_p),
+        ("d_term_kth_r", c_void_p),
     ]
 
 
@@ -118,6 +120,7 @@ def lib() -> ctypes.CDLL:
                                        c_size_t, POINTER(c_int64), vp]
     L.orag_bm25_index_fill.argtypes = [vp, vp, c_int64, c_int, c_int, c_int, vp, c_int, vp, vp, vp, vp, vp, vp, vp, vp,
                                        vp, c_size_t, vp]
+    L.orag_bm25_term_kth.argtypes = [POINTER(Bm25IndexStruct), vp, vp]
     L.orag_bm25_workspace_bytes.restype = c_size_t
     L.orag_bm25_workspace_bytes.argtypes = [POINTER(Bm25IndexStruct), c_int, c_int, c_int]
     L.orag_bm25_topk.argtypes = [POINTER(Bm25IndexStruct), c_int64, vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp, vp,

@@ -226,6 +226,19 @@ class Bm25Index:
 
     def _make_struct(self):
         ptr = lambda t: t.data_ptr() if t is not None else None
+        self.term_kth_r = None
+        self._fill_struct(ptr)
+        if (self.postings_r16 is not None and self.postings_r16.is_cuda
+                and os.environ.get("ORAG_BM25_WARM_START", "1") == "1"):
+            # threshold warm start of the first pass: K-th largest impact of every term, derived from the first-pass
+            # view itself (a few ms at 10M docs; recomputed on load rather than stored)
+            self.term_kth_r = torch.empty((_ffi.ORAG_BM25_KTH_LEVELS, self.vocab), dtype=torch.float32, device=self.device)
+            _ffi.check(_ffi.lib().orag_bm25_term_kth(ctypes.byref(self.struct), self.term_kth_r.data_ptr(),
+                                                     torch.cuda.current_stream(self.device).cuda_stream),
+                       "orag_bm25_term_kth")
+            self._fill_struct(ptr)
+
+    def _fill_struct(self, ptr):
         # reserved bit 0: first-pass runs are 16-byte aligned and padded to four postings (csrc/bm25_build.cu)
         self.struct = _ffi.Bm25IndexStruct(
             n_docs=self.n_docs, vocab=self.vocab, tile_docs=self.tile_docs, n_tiles=self.n_tiles,
@@ -235,7 +248,8 @@ class Bm25Index:
             d_doc_len=ptr(self.dl), d_t4_table=ptr(self.t4_table), d_r_table=ptr(self.r_table), d_idf=ptr(self.idf),
             d_postings_r16=ptr(self.postings_r16), d_term_max_r=ptr(self.term_max_r),
             fp_tile_docs=self.fp_tile_docs, fp_n_tiles=self.fp_n_tiles,
-            d_fp_tile_base=ptr(self.fp_tile_base), d_fp_tile_term_off=ptr(self.fp_tile_term_off))
+            d_fp_tile_base=ptr(self.fp_tile_base), d_fp_tile_term_off=ptr(self.fp_tile_term_off),
+            d_term_kth_r=ptr(self.term_kth_r))
 
     @property
     def doc_t4(self) -> torch.Tensor:

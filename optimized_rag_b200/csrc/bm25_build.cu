@@ -371,6 +371,83 @@ static int grid_for(int n_super)
     return grid < 1 ? 1 : (grid > lim ? lim : grid);
 }
 
+
+// ---- k-th largest impact of every term (threshold warm start of the first pass) ---------------------------------
+// One CTA per term: two passes over the term's first-pass runs -- a histogram of the high byte of the fp16 impact
+// bits (positive fp16 numbers order like their bit patterns), then, for each of the ORAG_BM25_KTH_LEVELS ranks, a
+// histogram of the low byte inside the bin that holds it.  Padding postings (impact +0.0) are not counted.
+__constant__ int c_kth_k[ORAG_BM25_KTH_LEVELS] = {10, 16, 32, 64, 128};
+
+__global__ void __launch_bounds__(256) term_kth_kernel(int vocab, int fp_n_tiles, const long long *__restrict__ fp_tile_base,
+                                                      const int32_t *__restrict__ fp_tile_term_off,
+                                                      const uint32_t *__restrict__ postings_r16, float *__restrict__ kth)
+{
+    __shared__ uint32_t h1[256];
+    __shared__ uint32_t h2[ORAG_BM25_KTH_LEVELS][256];
+    __shared__ int s_bin[ORAG_BM25_KTH_LEVELS];
+    __shared__ uint32_t s_rank[ORAG_BM25_KTH_LEVELS];
+    const int t = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t V1 = (int64_t)vocab + 1;
+    h1[threadIdx.x] = 0;
+    for (int l = 0; l < ORAG_BM25_KTH_LEVELS; ++l) h2[l][threadIdx.x] = 0;
+    __syncthreads();
+    for (int tile = warp; tile < fp_n_tiles; tile += 8) {
+        const int32_t *off = fp_tile_term_off + (int64_t)tile * V1 + t;
+        const int lo = __ldg(off), hi = __ldg(off + 1);
+        const uint32_t *run = postings_r16 + fp_tile_base[tile];
+        for (int i = lo + lane; i < hi; i += 32) {
+            const uint32_t key = __ldg(run + i) & 0xFFFFu;
+            if (key) atomicAdd(&h1[key >> 8], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < ORAG_BM25_KTH_LEVELS) {
+        const uint32_t want = (uint32_t)c_kth_k[threadIdx.x];
+        uint32_t acc = 0;
+        int b = 255;
+        for (; b >= 0; --b) {
+            if (acc + h1[b] >= want) break;
+            acc += h1[b];
+        }
+        s_bin[threadIdx.x] = b;            // -1: the term has fewer postings than this rank
+        s_rank[threadIdx.x] = want - acc;  // rank inside the bin, 1-based
+    }
+    __syncthreads();
+    bool any = false;
+    for (int l = 0; l < ORAG_BM25_KTH_LEVELS; ++l) any |= s_bin[l] >= 0;
+    if (any) {
+        for (int tile = warp; tile < fp_n_tiles; tile += 8) {
+            const int32_t *off = fp_tile_term_off + (int64_t)tile * V1 + t;
+            const int lo = __ldg(off), hi = __ldg(off + 1);
+            const uint32_t *run = postings_r16 + fp_tile_base[tile];
+            for (int i = lo + lane; i < hi; i += 32) {
+                const uint32_t key = __ldg(run + i) & 0xFFFFu;
+                if (!key) continue;
+                const int hb = (int)(key >> 8);
+#pragma unroll
+                for (int l = 0; l < ORAG_BM25_KTH_LEVELS; ++l)
+                    if (hb == s_bin[l]) atomicAdd(&h2[l][key & 255u], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < ORAG_BM25_KTH_LEVELS) {
+        const int l = threadIdx.x;
+        float v = 0.f;
+        if (s_bin[l] >= 0) {
+            uint32_t acc = 0;
+            int b = 255;
+            for (; b > 0; --b) {
+                acc += h2[l][b];
+                if (acc >= s_rank[l]) break;
+            }
+            v = __half2float(__ushort_as_half((unsigned short)((s_bin[l] << 8) | b)));
+        }
+        kth[(int64_t)l * vocab + t] = v;
+    }
+}
+
 }  // namespace build
 }  // namespace orag
 
@@ -482,5 +559,20 @@ extern "C" int orag_bm25_index_fill(const int64_t *d_doc_off, const int32_t *d_t
                                                                     d_fp_tile_term_off, w.cur_f, d_postings_r16);
         ORAG_LAUNCH_CHECK();
     }
+    return ORAG_OK;
+}
+
+extern "C" int orag_bm25_term_kth(const orag_bm25_index_t *index, float *d_term_kth_r, void *stream)
+{
+    ORAG_REQUIRE(index && d_term_kth_r && index->vocab > 0, "bm25_term_kth");
+    ORAG_REQUIRE(index->d_postings_r16 && index->d_fp_tile_base && index->d_fp_tile_term_off, "index without first-pass view");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (index->n_docs == 0 || index->fp_n_tiles == 0) {
+        ORAG_CUDA_CHECK(cudaMemsetAsync(d_term_kth_r, 0, (size_t)ORAG_BM25_KTH_LEVELS * index->vocab * sizeof(float), st));
+        return ORAG_OK;
+    }
+    term_kth_kernel<<<index->vocab, 256, 0, st>>>(index->vocab, index->fp_n_tiles, (const long long *)index->d_fp_tile_base,
+                                                  index->d_fp_tile_term_off, index->d_postings_r16, d_term_kth_r);
+    ORAG_LAUNCH_CHECK();
     return ORAG_OK;
 }

@@ -135,6 +135,16 @@ __global__ void prepare_queries_kernel(const __grid_constant__ MsParams p)
         }
         term[b + 1] = t; w[b + 1] = ww; ub[b + 1] = uu;
     }
+    // Warm start (index->d_term_kth_r): K >= k docs contain term t with an impact of at least r_K(t), and each of them
+    // scores at least fl(w_t * r_K(t)) in this pass's own arithmetic (every contribution is >= 0 and rounding is
+    // monotone), so the best of these is a lower bound of the k-th best approximate score -- a valid threshold.
+    if (p.ix.d_term_kth_r && p.k <= 128) {
+        const int level = p.k <= 10 ? 0 : p.k <= 16 ? 1 : p.k <= 32 ? 2 : p.k <= 64 ? 3 : 4;
+        float t0 = 0.f;
+        for (int j = 0; j < n; ++j)
+            t0 = fmaxf(t0, __fmul_rn(w[j], p.ix.d_term_kth_r[(int64_t)level * p.ix.vocab + term[j]]));
+        if (t0 > 0.f) p.thr_bits[q] = (unsigned long long)__double_as_longlong((double)t0);
+    }
     float pre = 0.f;
     for (int j = 0; j < kMsTerms; ++j) {
         if (j < n) pre = __fadd_ru(pre, ub[j]);

@@ -81,6 +81,17 @@ def test_index_builder_layout_matches_oracle(n, vocab, lmin, lmax, tile, fp_tile
         assert abs(float(r16) - r) <= r * 2.0 ** -11 and float(r16) >= 6.2e-5
         tmax[t] = max(tmax[t], np.float32(r16))
     assert np.array_equal(ix.term_max_r.cpu().numpy(), tmax)
+    # threshold warm start: the K-th largest fp16 impact of every term (0 when the term has fewer postings)
+    per_term = [[] for _ in range(vocab)]
+    for (t, d), bits in first.items():
+        per_term[t].append(bits)
+    kth = ix.term_kth_r.cpu().numpy()
+    for level, K in enumerate((10, 16, 32, 64, 128)):
+        want_k = np.zeros(vocab, dtype=np.float32)
+        for t in range(vocab):
+            if len(per_term[t]) >= K:
+                want_k[t] = np.float32(np.uint16(sorted(per_term[t], reverse=True)[K - 1]).view(np.float16))
+        assert np.array_equal(kth[level], want_k), K
 
 
 def test_long_and_repetitive_documents():
