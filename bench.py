@@ -647,13 +647,17 @@ def run_hybrid_like(args):
                     "scan_ms_in_timed_loop": [round(r[2], 4) for r in allr],
                     "bm25_ms_in_timed_loop": [round(r[3], 4) for r in allr]}
 
-    # ---- timed: end to end through the public call with HOST buffers, two batches in flight: while batch i computes,
-    # the results of batch i-1 travel to the host and are read there (ONE host synchronisation per step)
-    dev_sets = [devt, [t.clone() for t in devt]]
-    outs_h = [(out_ids_h, out_sc_h, status_h),
-              (torch.empty_like(out_ids_h).pin_memory(), torch.empty_like(out_sc_h).pin_memory(),
-               torch.empty_like(status_h).pin_memory())]
-    state = {"i": 0, "prev": None}
+    # ---- timed: end to end through the public call with HOST buffers, as many batches in flight as the search has
+    # lanes: while batch i is submitted, the results of batch i - (depth - 1) travel to the host and are read there (ONE
+    # host synchronisation per step, on a batch that has had depth - 1 steps to finish)
+    import collections
+    depth = max(2, int(getattr(sh, "lanes", 2)))
+    dev_sets = [devt] + [[t.clone() for t in devt] for _ in range(depth - 1)]
+    outs_h = [(out_ids_h, out_sc_h, status_h)] + [
+        (torch.empty_like(out_ids_h).pin_memory(), torch.empty_like(out_sc_h).pin_memory(),
+         torch.empty_like(status_h).pin_memory()) for _ in range(depth - 1)]
+    state = {"i": 0}
+    pending = collections.deque()
 
     def finish(ticket, slot):
         r = ticket.wait()
@@ -661,29 +665,25 @@ def run_hybrid_like(args):
         ids_h.copy_(r["ids"], non_blocking=True)
         sc_h.copy_(r["scores"], non_blocking=True)
         st_h.copy_(r["status"], non_blocking=True)   # the overflow flags travel with the result
-        torch.cuda.current_stream().synchronize()      # (the batch submitted after this one keeps running on its lane)
+        torch.cuda.current_stream().synchronize()      # (the batches submitted after this one keep running on their lanes)
         if int(st_h.max()) != 0:                       # rare: repair through the exhaustive kernels
             torch.cuda.synchronize()
-            r = sh.search(*ticket_inputs[slot], k, check_overflow=True)
+            r = sh.search(*dev_sets[slot], k, check_overflow=True)
             ids_h.copy_(r["ids"]); sc_h.copy_(r["scores"])
-
-    ticket_inputs = [None, None]
 
     def step_e2e():
         i = state["i"]
-        bufs = dev_sets[i & 1]
-        for dst, src in zip(bufs, host):
+        slot = i % depth
+        for dst, src in zip(dev_sets[slot], host):
             dst.copy_(src, non_blocking=True)
-        t = sh.submit(*bufs, k)
-        ticket_inputs[i & 1] = bufs
-        if state["prev"] is not None:
-            finish(state["prev"], (i - 1) & 1)
-        state["prev"], state["i"] = t, i + 1
+        pending.append((sh.submit(*dev_sets[slot], k), slot))
+        if len(pending) >= depth:
+            finish(*pending.popleft())
+        state["i"] = i + 1
 
     def drain_e2e():
-        if state["prev"] is not None:
-            finish(state["prev"], (state["i"] - 1) & 1)
-            state["prev"] = None
+        while pending:
+            finish(*pending.popleft())
 
     e2e_ms = h.e2e_timed(step_e2e, drain_e2e)
     exchange_used = "none (one shard)" if world == 1 else sh.exchange + (f" ({sh.exchange_note})" if sh.exchange_note else "")

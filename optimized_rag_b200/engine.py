@@ -460,8 +460,13 @@ class HybridShard:
         self._head = None       # the stream every scan of this shard is enqueued on (co-scheduled searches)
         self.head_stream = os.environ.get("ORAG_HEAD_STREAM", "0") == "1"
         self.serial = False     # no side stream at all (measurement: see local_lists)
-        # BM25 first pass NEXT TO the scan (see local_lists): ORAG_COSCHEDULE=0/1 forces it, default on
-        self.coschedule = os.environ.get("ORAG_COSCHEDULE", "1") == "1"
+        self._marked = False
+        # BM25 first pass NEXT TO the scan (see local_lists): ORAG_COSCHEDULE=0/1 forces it; by default only for large
+        # shards.  Measured on B200, three batches in flight (bench.py --rows R, ms per batch, on / off): 10M rows 8.11 /
+        # 8.33, 5M 4.12 / 4.12, 2.5M 2.15 / 2.12, 1.25M 1.21 / 1.16 -- next to a short scan the background CTAs mostly
+        # keep the tail kernels of the previous batch off the SMs.
+        env = os.environ.get("ORAG_COSCHEDULE")
+        self.coschedule = (env == "1") if env in ("0", "1") else cosine.n_rows >= 6_000_000
 
     def local_lists(self, query_emb: torch.Tensor, query_terms: torch.Tensor, query_lens: torch.Tensor, fetch_k: int,
                     bm25_k: int, normalize: bool, lane: int = 0):
@@ -476,8 +481,9 @@ class HybridShard:
         L = _ffi.lib()
         if lane not in self._side:
             self._side[lane] = torch.cuda.Stream(dev)
-            if self.coschedule:
-                L.orag_cosine_mark_prescan(1)
+        if self.coschedule and not self._marked:
+            L.orag_cosine_mark_prescan(1)   # (process-wide; the cosine calls record one more event each from now on)
+            self._marked = True
         side = self._side[lane]
         # inputs are ready; also what makes the caching allocator's per-stream pools safe without record_stream():
         # every side-stream block (BM25 outputs, status) is only ever re-issued to side-stream work of a LATER call,

@@ -181,7 +181,9 @@ def test_bm25_index_save_load_round_trip(tmp_path, n, vocab, tile, negative):
     assert np.array_equal(back.df_local, ix.df_local)
     for field, ctype in _ffi.Bm25IndexStruct._fields_:
         va, vb = getattr(ix.struct, field), getattr(back.struct, field)
-        if field.startswith("d_"):
+        if field == "d_term_kth_r":
+            assert vb is None   # derived on the GPU from the first-pass view (orag_bm25_term_kth): not for a host copy
+        elif field.startswith("d_"):
             assert (va is None) == (vb is None), field   # same arrays present, each pointing at its own copy
         else:
             assert va == vb, field
@@ -193,6 +195,9 @@ def test_bm25_index_save_load_round_trip(tmp_path, n, vocab, tile, negative):
         a = ix.topk(torch.from_numpy(qt).to(DEV), torch.from_numpy(ql).to(DEV), 5, force="sparse")
         b = dev_ix.topk(torch.from_numpy(qt).to(DEV), torch.from_numpy(ql).to(DEV), 5, force="sparse")
         assert all(torch.equal(x, y) for x, y in zip(a, b))
+        assert (dev_ix.term_kth_r is None) == (ix.term_kth_r is None)
+        if ix.term_kth_r is not None:
+            assert torch.equal(dev_ix.term_kth_r, ix.term_kth_r)   # recomputed on load, not stored
     # a damaged file is refused
     data = (tmp_path / "kw.bin").read_bytes()
     if len(data) > 16:

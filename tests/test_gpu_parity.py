@@ -739,8 +739,8 @@ print("cluster ok")
         assert r.returncode == 0 and "cluster ok" in r.stdout, (two_sm, r.stdout + r.stderr)
 
 
-@pytest.mark.parametrize("head_stream", [False, True])
-def test_submit_keeps_batches_in_flight_and_equals_search(eng, head_stream):
+@pytest.mark.parametrize("head_stream,coschedule", [(False, True), (True, True), (False, False)])
+def test_submit_keeps_batches_in_flight_and_equals_search(eng, head_stream, coschedule):
     """ShardedHybrid.submit (three lanes: own streams, workspaces, exchange slots) over a sequence of DIFFERENT batches:
     every ticket's result equals the plain search of its batch, bit for bit, whatever order the lanes finish in.
     head_stream=True drives the cosine search through the split entry point (orag_cosine_topk_phase: preparation on the
@@ -753,7 +753,7 @@ def test_submit_keeps_batches_in_flight_and_equals_search(eng, head_stream):
     doc_off, tok = syn.token_corpus(syn.SEED_TOKENS, 0, n, vocab, 20, 80, thr)
     sh = ShardedHybrid(eng.HybridShard(eng.CosineIndex(_t(corpus), mode="f16"),
                                        Bm25Index(_t(doc_off), _t(tok), vocab, tile_docs=1024)))
-    sh.shard.head_stream = head_stream
+    sh.shard.head_stream, sh.shard.coschedule = head_stream, coschedule   # (default: co-scheduled for large shards only)
     batches = []
     for i, nq in enumerate([64, 17, 64, 1, 40, 64, 64]):
         q = syn.query_embeddings(nq, n, dim, query_seed=syn.SEED_QUERIES + i, dup_per_mille=5)
