@@ -190,9 +190,9 @@ class ClockSampler:
     timestamps fall inside the device-timed loop count (`window(t0, t1)` marks it; the GPU is continuously busy there,
     whereas the end-to-end loop idles between steps and would show ramped-down clocks), so that a 30 ms multi-GPU run still
     gets its clocks and idle set-up time never dilutes them."""
-    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw.instant,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_power_cap,power.limit")
 
     def __init__(self, uuid: str):
         self.uuid = uuid
@@ -233,7 +233,8 @@ class ClockSampler:
                 continue
             try:
                 ts = dt.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
+                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")],
+                             _num(f[3]), _num(f[8]) if len(f) > 8 else None))
             except ValueError:
                 continue
         try:
@@ -249,7 +250,18 @@ class ClockSampler:
         if inside:
             out.update(sm_mhz=statistics.median(r[1] for r in inside), sm_max_mhz=max(r[2] for r in inside),
                        reasons=sorted({n for r in inside for n in r[3]}), samples=len(inside), window=note)
+            watts = [r[4] for r in inside if r[4] is not None]
+            limit = [r[5] for r in inside if r[5] is not None]
+            if watts:   # the hybrid step runs at the board's power limit: the SM clock is what the cap leaves
+                out.update(power_w=statistics.median(watts), power_limit_w=max(limit) if limit else None)
         return out
+
+
+def _num(text):
+    try:
+        return float(text)
+    except ValueError:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------ native arm

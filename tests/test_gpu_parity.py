@@ -863,3 +863,33 @@ def test_bm25_first_pass_on_a_mostly_empty_last_tile(n_docs):
             assert int((st[0] != 0).sum()) == 0, (k, background, sorted(set(st[0].tolist())))
             for g, w in zip(got, want):
                 assert torch.equal(g, w), (k, background)
+
+
+def test_timeline_and_candidate_count_hooks(eng):
+    """Diagnostic entry points (bench.py --timeline, DESIGN.md candidate statistics): after orag_timeline_enable(1) a
+    search leaves one (tag, begin, end) record per tagged launch, begin <= end, the main scan among them; the candidate
+    counts of the last search are at least k per query and the fp32 survivors at most the candidates."""
+    import ctypes
+    from optimized_rag_b200 import _ffi
+    L = _ffi.lib()
+    n, dim, k = 40000, 256, 10
+    corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim, 0)
+    ix = eng.CosineIndex(_t(corpus), mode="f16")
+    q = _t(syn.query_embeddings(64, n, dim))
+    ix.topk(q, k)
+    torch.cuda.synchronize()
+    assert L.orag_timeline_enable(1) == 0
+    ids, _ = ix.topk(q, k)
+    cap = 64
+    tags, t0, t1 = (ctypes.c_int * cap)(), (ctypes.c_float * cap)(), (ctypes.c_float * cap)()
+    got = int(L.orag_timeline_read(tags, t0, t1, cap))
+    assert L.orag_timeline_enable(0) == 0
+    assert 6 <= got <= cap
+    seen = {int(tags[i]) for i in range(got)}
+    assert {2, 3, 4, 5, 6, 7} <= seen                      # seed scan, seed finalize, main scan, prefilter, rescore, select
+    assert all(0.0 <= t0[i] <= t1[i] for i in range(got))
+    cand, surv = ix.last_counts(64, k)
+    assert (cand >= k).all() and (surv >= k).all() and (surv <= cand).all() and int(cand.max()) <= 4096
+    # disabled again: nothing is recorded
+    ix.topk(q, k)
+    assert int(L.orag_timeline_read(tags, t0, t1, cap)) == got
