@@ -223,3 +223,29 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu(built_lib):
     assert L.orag_exchange_free(None) == 0 and L.orag_exchange_close(None) == 0
     assert L.orag_weighted_sum3(None, None, None, 5, 0.5, 0.3, 0.2, None, None) == -1
     assert L.orag_div_scalar(p(buf), 0, 2.0, p(buf), None) == 0
+
+
+def test_c_abi_rejects_bad_arguments_of_the_round_2_entry_points(built_lib):
+    """Same for the entry points added in the second half of round 2: the split-phase cosine search, the per-term
+    K-th impacts, the diagnostic hooks."""
+    import ctypes
+    from optimized_rag_b200 import _ffi
+    L = _ffi.lib()
+    buf = (ctypes.c_int64 * 64)()
+    p = lambda a: ctypes.cast(a, ctypes.c_void_p)
+    args = (p(buf), p(buf), p(buf), p(buf), 1000, 1536, 0, p(buf), 4, 10, _ffi.ORAG_COS_F16, p(buf), p(buf), p(buf), p(buf),
+            1 << 30)
+    assert L.orag_cosine_topk_phase(*args, 0, None) == -1 and b"phases" in L.orag_last_error()
+    assert L.orag_cosine_topk_phase(*args, 8, None) == -1
+    many = args[:8] + (300,) + args[9:]                     # split phases hold one query group
+    assert L.orag_cosine_topk_phase(*many, _ffi.ORAG_PHASE_SCAN, None) == -1 and b"split phases" in L.orag_last_error()
+    exact = args[:10] + (_ffi.ORAG_COS_EXACT,) + args[11:]  # ... and exist for the tensor-core modes only
+    assert L.orag_cosine_topk_phase(*exact, _ffi.ORAG_PHASE_FINISH, None) == -1
+    assert _ffi.ORAG_PHASE_PREP | _ffi.ORAG_PHASE_SCAN | _ffi.ORAG_PHASE_FINISH == _ffi.ORAG_PHASE_ALL
+    ix = _ffi.Bm25IndexStruct(n_docs=10, vocab=5)
+    assert L.orag_bm25_term_kth(ctypes.byref(ix), p(buf), None) == -1 and b"first-pass view" in L.orag_last_error()
+    assert L.orag_bm25_term_kth(None, p(buf), None) == -1
+    assert L.orag_cosine_last_counts(None, 1536, 4, p(buf), p(buf), None) == -1
+    assert L.orag_cosine_last_counts(p(buf), 1536, 300, p(buf), p(buf), None) == -1
+    assert L.orag_timeline_read(None, None, None, 4) == -1
+    assert L.orag_timeline_enable(0) == 0
