@@ -413,6 +413,13 @@ class ShardedHybrid:
         `status` word: non-zero = that query must be repeated through `search(check_overflow=True)`).  Every rank
         must submit the same sequence of batches."""
         dev = query_emb.device
+        if query_emb.shape[0] > 256:
+            # one search per 256-query group (the tensor-core scan's block), each on the next lane: the groups of one
+            # call overlap like separate batches instead of running scan -> tail -> scan -> tail on one stream
+            # (batch 1024 on one GPU, 10M rows: 38.7 -> 35.9 ms per batch)
+            parts = [self.submit(query_emb[i:i + 256], query_terms[i:i + 256], query_lens[i:i + 256], k, fetch_k)
+                     for i in range(0, query_emb.shape[0], 256)]
+            return _TicketGroup(parts)
         lane = (self._searches + 1) % LANES
         if lane not in self._lane_streams:
             self._lane_streams[lane] = torch.cuda.Stream(dev)
@@ -440,6 +447,18 @@ class Ticket:
                 t.record_stream(cur)   # produced on the lane's stream, consumed on the caller's
         self._inputs = None
         return self._out
+
+
+class _TicketGroup:
+    """The tickets of one call that was split into 256-query groups: `wait` concatenates their results in order."""
+
+    def __init__(self, parts):
+        self._parts = parts
+
+    def wait(self) -> dict:
+        outs = [t.wait() for t in self._parts]
+        return {key: (torch.cat([o[key] for o in outs], dim=0) if isinstance(outs[0][key], torch.Tensor) else outs[0][key])
+                for key in outs[0]}
 
 
 class _ShardedList:

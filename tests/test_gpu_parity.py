@@ -755,7 +755,7 @@ def test_submit_keeps_batches_in_flight_and_equals_search(eng, head_stream, cosc
                                        Bm25Index(_t(doc_off), _t(tok), vocab, tile_docs=1024)))
     sh.shard.head_stream, sh.shard.coschedule = head_stream, coschedule   # (default: co-scheduled for large shards only)
     batches = []
-    for i, nq in enumerate([64, 17, 64, 1, 40, 64, 64]):
+    for i, nq in enumerate([64, 17, 64, 1, 40, 300, 64]):   # 300: split into two 256-query groups on two lanes
         q = syn.query_embeddings(nq, n, dim, query_seed=syn.SEED_QUERIES + i, dup_per_mille=5)
         qt, ql = syn.keyword_queries(nq, vocab, seed=syn.SEED_KWQUERIES + 10 * i, min_rank=10, thresholds=thr)
         batches.append((_t(q), _t(qt), _t(ql)))
