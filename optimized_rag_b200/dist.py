@@ -473,26 +473,38 @@ class _ShardedList:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self._buf = None
+        self._bufs: dict = {}          # lane -> all-gather buffer
+        self._lane_streams: dict = {}
+        self._submitted = 0
+        self.lanes = LANES
 
-    def _gather(self, mine: torch.Tensor) -> torch.Tensor:
+    def _gather(self, mine: torch.Tensor, lane: int = 0) -> torch.Tensor:
         """mine int64 [B, w] -> [B, G, w] (shard-major inside a query)."""
         Bq, w = mine.shape
-        if self._buf is None or self._buf.shape != (self.world, Bq, w):
-            self._buf = torch.empty((self.world, Bq, w), dtype=torch.int64, device=mine.device)
-        dist.all_gather_into_tensor(self._buf.view(-1), mine.contiguous().view(-1), group=self.group)
-        return self._buf.permute(1, 0, 2)
+        buf = self._bufs.get(lane)
+        if buf is None or buf.shape != (self.world, Bq, w):
+            buf = self._bufs[lane] = torch.empty((self.world, Bq, w), dtype=torch.int64, device=mine.device)
+        dist.all_gather_into_tensor(buf.view(-1), mine.contiguous().view(-1), group=self.group)
+        return buf.permute(1, 0, 2)
 
     def close(self):
-        self._buf = None
+        self._bufs = {}
 
     def submit(self, *args, **kw) -> "Ticket":
-        """Same calling convention as ShardedHybrid.submit; these single-list searches run on the caller's stream (one
-        batch at a time), the ticket only marks their completion."""
+        """Same calling convention as ShardedHybrid.submit: consecutive submissions rotate over LANES streams (own
+        workspaces and gather buffers), so the re-scores / selection / merge of one batch run under the first pass of
+        the next.  Every rank must submit the same sequence of batches."""
         dev = args[0].device
-        out = self.search(*args, check_overflow=False, **kw)
-        done = torch.cuda.Event()
-        done.record(torch.cuda.current_stream(dev))
+        lane = self._submitted % LANES
+        self._submitted += 1
+        if lane not in self._lane_streams:
+            self._lane_streams[lane] = torch.cuda.Stream(dev)
+        stream = self._lane_streams[lane]
+        stream.wait_stream(torch.cuda.current_stream(dev))   # the inputs are ready
+        with torch.cuda.stream(stream):
+            out = self.search(*args, check_overflow=False, lane=lane, **kw)
+            done = torch.cuda.Event()
+            done.record(stream)
         return Ticket(out, done, dev, args)
 
 
@@ -504,13 +516,13 @@ class ShardedCosine(_ShardedList):
         super().__init__(group)
         self.index = index
 
-    def search(self, query_emb, k: int = 10, check_overflow: bool = True):
+    def search(self, query_emb, k: int = 10, check_overflow: bool = True, lane: int = 0):
         st: list = []
-        ids, sc = self.index.topk(query_emb, k, check_overflow=check_overflow, status_out=st)
+        ids, sc = self.index.topk(query_emb, k, check_overflow=check_overflow, status_out=st, lane=lane)
         status = st[0] if not check_overflow else torch.zeros_like(st[0])
         if self.world > 1:
             mine = torch.cat([ids, sc.view(torch.int64), status.long()[:, None]], dim=1)
-            g = self._gather(mine)
+            g = self._gather(mine, lane)
             Bq = ids.shape[0]
             ids, sc, _ = engine.topk_merge(g[:, :, :k].reshape(Bq, -1).contiguous(),
                                            g[:, :, k:2 * k].reshape(Bq, -1).contiguous().view(torch.float64), k)
@@ -529,19 +541,19 @@ class ShardedBm25(_ShardedList):
         super().__init__(group)
         self.index = index
 
-    def search(self, query_terms, query_lens, k: int = 10, check_overflow: bool = True):
+    def search(self, query_terms, query_lens, k: int = 10, check_overflow: bool = True, lane: int = 0):
         st: list = []
         if self.world == 1:
             ids, sc, mx = self.index.topk(query_terms, query_lens, k, normalize=True, check_overflow=check_overflow,
-                                          status_out=st)
+                                          status_out=st, lane=lane)
             status = st[0] if not check_overflow else torch.zeros_like(st[0])
         else:
             kk = k + BM25_GUARD
             ids, raw, mx = self.index.topk(query_terms, query_lens, kk, normalize=False, check_overflow=check_overflow,
-                                           status_out=st)
+                                           status_out=st, lane=lane)
             status = st[0] if not check_overflow else torch.zeros_like(st[0])
             mine = torch.cat([ids, raw.view(torch.int64), mx.view(torch.int64)[:, None], status.long()[:, None]], dim=1)
-            g = self._gather(mine)
+            g = self._gather(mine, lane)
             Bq = ids.shape[0]
             ids, sc, mx = engine.topk_merge(g[:, :, :kk].reshape(Bq, -1).contiguous(),
                                             g[:, :, kk:2 * kk].reshape(Bq, -1).contiguous().view(torch.float64), k,
