@@ -166,7 +166,7 @@ constexpr int kGroup = 256;     // queries per tensor-core pass (UMMA N)
 // than SMs it can start while the last CTAs of the previous batch's scan are still draining).  The first wave of the main
 // scan (two tiles per CTA in flight, ~38k rows) still runs on the seed's threshold, which passes k / kSeedRows of the
 // rows: with 2048 seed rows that wave alone left ~190 candidates per query (k = 10) for the fp32 re-score, with 8192 ~45.
-constexpr int kSeedRows = 64 * 128;
+constexpr int kSeedRows = 64 * 128;   // (= 256 threads x 32 values of seed_finalize_kernel)
 constexpr int kCandCap = 4096;  // first-pass candidate slots per query
 constexpr int kSurvCap = 512;   // candidates that survive the fp32 re-score (k <= 128 leaves ample room)
 

@@ -495,6 +495,8 @@ cosine_scan_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 }
 
 // ---- seed finalisation ----------------------------------------------------------------------
+constexpr int kSeedPerThread = 32;  // seed values per thread of seed_finalize_kernel: seed_ld = 256 * 32 rows
+
 // One CTA per query over the dense first-pass values of the first `n_seed` rows (transposed: seed_t[q * seed_ld + row]):
 // histogram -> threshold; survivors -> candidate list.
 __global__ void __launch_bounds__(256) seed_finalize_kernel(const float *__restrict__ seed_t, int seed_ld, int n_seed,
@@ -528,6 +530,18 @@ __global__ void __launch_bounds__(256) seed_finalize_kernel(const float *__restr
         }
         return;
     }
+    // Every thread keeps its 32 consecutive seed values in registers (eight 16-byte loads in flight at once; three
+    // strided passes over global memory cost 36 us, this 22): all later passes run on registers.
+    float v[kSeedPerThread];
+    const int r0 = threadIdx.x * kSeedPerThread;
+#pragma unroll
+    for (int j = 0; j < kSeedPerThread; j += 4) {
+        const float4 x = *reinterpret_cast<const float4 *>(seed + r0 + j);
+        v[j] = x.x; v[j + 1] = x.y; v[j + 2] = x.z; v[j + 3] = x.w;
+    }
+#pragma unroll
+    for (int j = 0; j < kSeedPerThread; ++j)
+        if (r0 + j >= n_seed) v[j] = -INFINITY;   // (rows the seed pass did not write)
     // Only the top of the distribution matters.  Each thread's largest value is a distinct row, so the k-th largest of
     // the 256 per-thread maxima (`low`) is a lower bound of the k-th best seed value: rows below it need no histogram
     // entry (the bins under `low` stay under-counted, which can only make a threshold more conservative), and the
@@ -535,7 +549,8 @@ __global__ void __launch_bounds__(256) seed_finalize_kernel(const float *__restr
     __shared__ float s_max[256];
     __shared__ float s_low;
     float mine = -INFINITY;
-    for (int r = threadIdx.x; r < n_seed; r += blockDim.x) mine = fmaxf(mine, seed[r]);
+#pragma unroll
+    for (int j = 0; j < kSeedPerThread; ++j) mine = fmaxf(mine, v[j]);
     s_max[threadIdx.x] = mine;
     if (threadIdx.x == 0) s_low = -INFINITY;
     __syncthreads();
@@ -549,30 +564,47 @@ __global__ void __launch_bounds__(256) seed_finalize_kernel(const float *__restr
     }
     __syncthreads();
     const float low = s_low;
-    for (int r = threadIdx.x; r < n_seed; r += blockDim.x) {
-        const float v = seed[r];
-        if (v >= low) atomicAdd(&h[cos_bin(v * iqn)], 1u);
-    }
+#pragma unroll
+    for (int j = 0; j < kSeedPerThread; ++j)
+        if (v[j] >= low && r0 + j < n_seed) atomicAdd(&h[cos_bin(v[j] * iqn)], 1u);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        int b = kHistBins - 1;
-        for (; b >= 0; --b) {
-            acc += h[b];
-            if (acc >= (uint32_t)k) break;
+    if (threadIdx.x < 32) {
+        // largest bin b with count(bins >= b) >= k: lane i sums the 16 bins [512 - 16 (i + 1), 512 - 16 i), a warp scan
+        // finds the lane whose chunk crosses k, that lane walks its chunk
+        const int lane = threadIdx.x;
+        const int hi = kHistBins - 16 * lane;   // one past my top bin
+        uint32_t sum = 0;
+        for (int b = hi - 1; b >= hi - 16; --b) sum += h[b];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
         }
-        s_thr = (b >= 1) ? bin_floor(b) : -INFINITY;  // fewer than k rows seen: keep everything
+        const unsigned crossed = __ballot_sync(0xffffffffu, incl >= (uint32_t)k);
+        if (crossed == 0) {
+            if (lane == 0) s_thr = -INFINITY;   // fewer than k rows seen: keep everything
+        } else if (lane == __ffs(crossed) - 1) {
+            uint32_t acc = incl - sum;
+            int b = hi - 1;
+            for (; b >= hi - 16; --b) {
+                acc += h[b];
+                if (acc >= (uint32_t)k) break;
+            }
+            s_thr = (b >= 1) ? bin_floor(b) : -INFINITY;
+        }
     }
     __syncthreads();
     const float thr = s_thr;
     const float tv = (thr - margin) * qn;
     for (int b = threadIdx.x; b < kHistBins; b += blockDim.x) hist[(int64_t)q * kHistBins + b] = h[b];
-    for (int r = threadIdx.x; r < n_seed; r += blockDim.x) {
-        if (seed[r] >= tv) {
-            uint32_t slot = atomicAdd(&s_cnt, 1u);
+#pragma unroll
+    for (int j = 0; j < kSeedPerThread; ++j) {
+        if (v[j] >= tv && r0 + j < n_seed) {
+            const uint32_t slot = atomicAdd(&s_cnt, 1u);
             if (slot < (uint32_t)cap) {
-                cand[(int64_t)q * cap + slot] = r;
-                cand_v[(int64_t)q * cap + slot] = seed[r];
+                cand[(int64_t)q * cap + slot] = r0 + j;
+                cand_v[(int64_t)q * cap + slot] = v[j];
             }
         }
     }
@@ -710,6 +742,8 @@ int launch_seed_finalize(const float *seed, int seed_ld, int n_seed, int n_queri
                          const float *inv_qnorm, uint32_t *thr_key, uint32_t *cnt, uint32_t *hist, int32_t *cand,
                          float *cand_v, int cap, cudaStream_t st)
 {
+    ORAG_REQUIRE(seed_ld == 256 * kSeedPerThread && n_seed <= seed_ld && (reinterpret_cast<uintptr_t>(seed) & 15) == 0,
+                 "seed_finalize: seed buffer of 256 x 32 values per query");
     seed_finalize_kernel<<<n_queries, 256, 0, st>>>(seed, seed_ld, n_seed, n_queries, k, margin, qnorm, inv_qnorm, thr_key, cnt,
                                                     hist, cand, cand_v, cap);
     ORAG_LAUNCH_CHECK();
