@@ -570,11 +570,11 @@ def test_pairwise_tensor_core_equals_exact(eng):
 # ------------------------------------------------------------------------------------------------ edge cases
 @pytest.mark.parametrize("mode", ["tf32", "bf16", "f16"])
 def test_cosine_tc_ragged_sizes_and_batches(eng, mode):
-    """N not a multiple of the 128-row tile, B > 256 (two query groups), B = 1, k = 1 and k = 64, id base."""
+    """N not a multiple of the 128-row tile, B > 256 (two query groups), B = 1, k = 1, 64 and 128, id base."""
     n, dim = 4097 + 128 * 3 + 5, 192
     corpus = syn.embeddings(syn.SEED_CORPUS, 0, n, dim, 3)
     idx = eng.CosineIndex(_t(corpus), row_id_base=10_000_000_000, mode=mode)
-    for nq, k in [(300, 10), (1, 1), (7, 64)]:
+    for nq, k in [(300, 10), (1, 1), (7, 64), (5, 128)]:
         queries = syn.query_embeddings(nq, n, dim, dup_per_mille=3)
         ids, sc = idx.topk(_t(queries), k)
         sub = sorted(set([0, nq - 1, nq // 2, min(nq - 1, 257)]))
@@ -671,7 +671,7 @@ def test_bm25_first_pass_tile_sizes_and_shapes(eng, fp_tile):
     qt2, ql2 = np.concatenate([wide, long_q]), np.concatenate([ql, long_len])
     for background in (False, True):
         _check_bm25_vs_oracle(ix, orc, qt2, ql2, "sparse", background=background)
-    for k in (1, 32, 50):   # k > 32 switches the in-tile local threshold off
+    for k in (1, 32, 50, 100):   # k > 32 switches the in-tile local threshold off; 10 / 16 / 32 / 64 / 128 = warm-start levels
         _check_bm25_vs_oracle(ix, orc, qt2[:6], ql2[:6], "sparse", k=k)
 
 
