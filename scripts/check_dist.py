@@ -13,7 +13,7 @@ import torch.distributed as dist
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from optimized_rag_b200 import engine, synthetic as syn  # noqa: E402
 from optimized_rag_b200.bm25_index import Bm25Index  # noqa: E402
-from optimized_rag_b200.dist import ShardedHybrid, shard_range, sharded_stats  # noqa: E402
+from optimized_rag_b200.dist import ShardedBm25, ShardedCosine, ShardedHybrid, shard_range, sharded_stats  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 300_000
 DIM, VOCAB, B, K = 1536, 50000, 64, 10
@@ -105,6 +105,21 @@ for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("tf32", "f16")):
             print(f"[{mode}/{exchange}] {steps} back-to-back searches: {t[0]:.3f} ms/step on the device, "
                   f"{t[1]:.3f} ms/step of host enqueue time; stable={same}", flush=True)
         sh.close()
+        dist.barrier()
+    # the single-list searches (BASELINE configs 2 and 4 under torchrun): plain and with six batches submitted on the
+    # lanes, against the matching lists of the single-shard hybrid result
+    for name, obj, args, keys in (("cosine", ShardedCosine(shard.cosine), (q_emb,), ("cos_ids", "cos_scores")),
+                                  ("bm25", ShardedBm25(shard.bm25), (qt, ql), ("bm25_ids", "bm25_scores", "bm25_max"))):
+        plain = obj.search(*args, K)
+        outs = [tk.wait() for tk in [obj.submit(*args, K) for _ in range(6)]]
+        torch.cuda.synchronize()
+        if rank == 0:
+            same = all(torch.equal(o[key], ref[key]) for o in [plain] + outs for key in keys)
+            same &= not any(bool(o["status"].any()) for o in outs)
+            ok &= same
+            print(f"[{mode}] sharded {name}-only search, plain + 6 submitted: {'identical' if same else 'DIFFERENT'}",
+                  flush=True)
+        obj.close()
         dist.barrier()
 if rank == 0:
     print("DIST CHECK", "PASSED" if ok else "FAILED", flush=True)
