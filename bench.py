@@ -663,11 +663,11 @@ def run_hybrid_like(args):
     # while batch i is submitted, the results of batch i - (depth - 1) travel to the host and are read there (ONE host
     # synchronisation per step, on a batch that has had depth - 1 steps to finish)
     import collections
-    # (twice the lanes: the host only blocks on a batch that is `depth - 1` submissions old, so every lane always has
-    # its next batch queued behind the one it is working on -- with depth = lanes the submission of batch i waited for
-    # the completion of batch i - 2, tail included, and the GPU ran with one batch less in flight than the device-timed
-    # loop: 1.53 instead of 1.28 ms per batch at 1.25M rows per GPU on two GPUs)
-    depth = 2 * max(1, int(getattr(sh, "lanes", 1)))
+    # (four times the lanes: the host only blocks on a batch that is `depth - 1` submissions old.  With depth = lanes the
+    # submission of batch i waited for the completion of batch i - 2, tail included, and the GPU ran with one batch less
+    # in flight than the device-timed loop.  Measured at 1.25M rows per GPU on two GPUs, 60 steps, ms per batch, device
+    # loop 1.23: depth 3 1.30, 6 1.32, 12 1.25.  ORAG_BENCH_E2E_DEPTH overrides.)
+    depth = int(os.environ.get("ORAG_BENCH_E2E_DEPTH") or 4 * max(1, int(getattr(sh, "lanes", 1))))
     dev_sets = [devt] + [[t.clone() for t in devt] for _ in range(depth - 1)]
     outs_h = [(out_ids_h, out_sc_h, status_h)] + [
         (torch.empty_like(out_ids_h).pin_memory(), torch.empty_like(out_sc_h).pin_memory(),
