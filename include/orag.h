@@ -230,7 +230,9 @@ typedef struct orag_bm25_index {
     const int32_t *d_fp_tile_term_off;  /* [fp_n_tiles, vocab + 1] */
     /* Optional threshold warm start of the first pass (NULL = start cold): d_term_kth_r[l * vocab + t] = the K_l-th
      * largest fp16 impact among this shard's postings of term t, K = {10, 16, 32, 64, 128}, 0 when the term has fewer
-     * postings (orag_bm25_term_kth).  K_l docs score at least weight(t) * that value whatever else they contain (all
+     * postings (orag_bm25_term_kth; for a term with 16384 or more postings inside a block of 256 first-pass tiles: the
+     * K_l-th largest among the postings up to the end of that block -- any subset gives a valid bound).  K_l docs
+     * score at least weight(t) * that value whatever else they contain (all
      * contributions are >= 0), so max over a query's terms is a lower bound of its K_l-th best score: the first pass
      * starts with the frequent, low-idf terms already non-essential instead of scoring whole tiles until the running
      * threshold has caught up. */

@@ -376,7 +376,45 @@ static int grid_for(int n_super)
 // One CTA per term: two passes over the term's first-pass runs -- a histogram of the high byte of the fp16 impact
 // bits (positive fp16 numbers order like their bit patterns), then, for each of the ORAG_BM25_KTH_LEVELS ranks, a
 // histogram of the low byte inside the bin that holds it.  Padding postings (impact +0.0) are not counted.
+// The K-th largest impact of ANY subset of the postings is a valid (if weaker) bound, so a term's scan stops after the
+// first block of 256 tiles that brings it to kKthEnough postings: a term that occurs in every document is done after
+// one block instead of streaming 10M postings through one CTA (the table cost 0.24 s of a 0.70 s build before, ~10 ms
+// now); rare terms -- the ones whose high idf makes their bound the query's threshold -- are always scanned in full.
+// Inside a block every lane looks up the run of one tile (32 tiles per warp and round trip), then the warp walks the
+// non-empty runs together with four loads per lane in flight.
 __constant__ int c_kth_k[ORAG_BM25_KTH_LEVELS] = {10, 16, 32, 64, 128};
+constexpr uint32_t kKthEnough = 16384;
+
+template <typename F>
+__device__ __forceinline__ void kth_walk_block(int block, int t, int vocab, int fp_n_tiles,
+                                               const long long *__restrict__ fp_tile_base,
+                                               const int32_t *__restrict__ fp_tile_term_off,
+                                               const uint32_t *__restrict__ postings_r16, F &&visit)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = (block * 8 + warp) * 32 + lane;
+    int lo = 0, hi = 0;
+    long long base = 0;
+    if (tile < fp_n_tiles) {
+        const int32_t *off = fp_tile_term_off + (int64_t)tile * ((int64_t)vocab + 1) + t;
+        lo = __ldg(off);
+        hi = __ldg(off + 1);
+        base = fp_tile_base[tile];
+    }
+    for (unsigned todo = __ballot_sync(0xffffffffu, hi > lo); todo; todo &= todo - 1) {
+        const int j = __ffs(todo) - 1;
+        const int rlo = __shfl_sync(0xffffffffu, lo, j), rhi = __shfl_sync(0xffffffffu, hi, j);
+        const uint32_t *run = postings_r16 + __shfl_sync(0xffffffffu, base, j);
+        for (int i = rlo + lane; i < rhi; i += 128) {
+            uint32_t key[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) key[u] = i + 32 * u < rhi ? __ldg(run + i + 32 * u) & 0xFFFFu : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (key[u]) visit(key[u]);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256) term_kth_kernel(int vocab, int fp_n_tiles, const long long *__restrict__ fp_tile_base,
                                                       const int32_t *__restrict__ fp_tile_term_off,
@@ -386,22 +424,26 @@ __global__ void __launch_bounds__(256) term_kth_kernel(int vocab, int fp_n_tiles
     __shared__ uint32_t h2[ORAG_BM25_KTH_LEVELS][256];
     __shared__ int s_bin[ORAG_BM25_KTH_LEVELS];
     __shared__ uint32_t s_rank[ORAG_BM25_KTH_LEVELS];
+    __shared__ uint32_t s_seen;
     const int t = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t V1 = (int64_t)vocab + 1;
     h1[threadIdx.x] = 0;
     for (int l = 0; l < ORAG_BM25_KTH_LEVELS; ++l) h2[l][threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_seen = 0;
     __syncthreads();
-    for (int tile = warp; tile < fp_n_tiles; tile += 8) {
-        const int32_t *off = fp_tile_term_off + (int64_t)tile * V1 + t;
-        const int lo = __ldg(off), hi = __ldg(off + 1);
-        const uint32_t *run = postings_r16 + fp_tile_base[tile];
-        for (int i = lo + lane; i < hi; i += 32) {
-            const uint32_t key = __ldg(run + i) & 0xFFFFu;
-            if (key) atomicAdd(&h1[key >> 8], 1u);
-        }
+    const int n_blocks = (fp_n_tiles + 255) / 256;
+    int used = 0;   // blocks of 256 tiles that make up the subset both passes look at
+    for (; used < n_blocks;) {
+        uint32_t mine = 0;
+        kth_walk_block(used, t, vocab, fp_n_tiles, fp_tile_base, fp_tile_term_off, postings_r16, [&](uint32_t key) {
+            atomicAdd(&h1[key >> 8], 1u);
+            ++mine;
+        });
+        if (mine) atomicAdd(&s_seen, mine);
+        ++used;
+        __syncthreads();
+        if (s_seen >= kKthEnough) break;   // (uniform: read after the barrier, written before it)
+        __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x < ORAG_BM25_KTH_LEVELS) {
         const uint32_t want = (uint32_t)c_kth_k[threadIdx.x];
         uint32_t acc = 0;
@@ -410,26 +452,20 @@ __global__ void __launch_bounds__(256) term_kth_kernel(int vocab, int fp_n_tiles
             if (acc + h1[b] >= want) break;
             acc += h1[b];
         }
-        s_bin[threadIdx.x] = b;            // -1: the term has fewer postings than this rank
+        s_bin[threadIdx.x] = b;            // -1: the subset holds fewer postings than this rank
         s_rank[threadIdx.x] = want - acc;  // rank inside the bin, 1-based
     }
     __syncthreads();
     bool any = false;
     for (int l = 0; l < ORAG_BM25_KTH_LEVELS; ++l) any |= s_bin[l] >= 0;
     if (any) {
-        for (int tile = warp; tile < fp_n_tiles; tile += 8) {
-            const int32_t *off = fp_tile_term_off + (int64_t)tile * V1 + t;
-            const int lo = __ldg(off), hi = __ldg(off + 1);
-            const uint32_t *run = postings_r16 + fp_tile_base[tile];
-            for (int i = lo + lane; i < hi; i += 32) {
-                const uint32_t key = __ldg(run + i) & 0xFFFFu;
-                if (!key) continue;
+        for (int blk = 0; blk < used; ++blk)
+            kth_walk_block(blk, t, vocab, fp_n_tiles, fp_tile_base, fp_tile_term_off, postings_r16, [&](uint32_t key) {
                 const int hb = (int)(key >> 8);
 #pragma unroll
                 for (int l = 0; l < ORAG_BM25_KTH_LEVELS; ++l)
                     if (hb == s_bin[l]) atomicAdd(&h2[l][key & 255u], 1u);
-            }
-        }
+            });
     }
     __syncthreads();
     if (threadIdx.x < ORAG_BM25_KTH_LEVELS) {

@@ -204,3 +204,35 @@ def test_bm25_index_save_load_round_trip(tmp_path, n, vocab, tile, negative):
         (tmp_path / "kw.bin").write_bytes(data[:-8])
         with pytest.raises(ValueError):
             Bm25Index.load(tmp_path / "kw", device="cpu")
+
+
+def test_term_kth_scans_a_frequent_term_only_until_it_has_enough_postings():
+    """orag_bm25_term_kth: a term with >= 16384 postings inside the first block of 256 first-pass tiles is bounded from
+    that block alone (any subset of the postings gives a valid K-th largest impact); a term that only occurs beyond
+    that block is still scanned in full.  The searches stay exact with the weaker bound."""
+    rng = np.random.default_rng(11)
+    n, vocab, fp_tile = 40000, 60, 128
+    cut = 256 * fp_tile                       # docs of the first block
+    docs = []
+    for d in range(n):
+        body = [0] * int(rng.integers(1, 5)) + rng.integers(2, vocab, int(rng.integers(3, 30))).tolist()
+        if d >= cut + 100 and d % 3 == 0:
+            body += [1] * int(rng.integers(1, 4))
+        docs.append(body)
+    doc_off = np.zeros(n + 1, dtype=np.int64)
+    doc_off[1:] = np.cumsum([len(x) for x in docs])
+    tok = np.concatenate([np.asarray(x, dtype=np.int32) for x in docs])
+    ix = _build(doc_off, tok, vocab, tile_docs=128, fp_tile_docs=fp_tile)
+    assert ix.fp_n_tiles > 256 and ix.term_kth_r is not None
+    first = _decode(ix.postings_r16, ix.fp_tile_base, ix.fp_tile_term_off, fp_tile, ix.fp_n_tiles, vocab, padded=True)
+    kth = ix.term_kth_r.cpu().numpy()
+    for term, limit in ((0, cut), (1, n)):
+        bits = sorted((b for (t, d), b in first.items() if t == term and d < limit), reverse=True)
+        assert len(bits) >= 128
+        for level, K in enumerate((10, 16, 32, 64, 128)):
+            assert kth[level, term] == np.float32(np.uint16(bits[K - 1]).view(np.float16)), (term, K)
+    qt = torch.tensor([[0, 1, 5], [1, 7, -2], [0, -2, -2]], dtype=torch.int32, device=DEV)
+    ql = torch.tensor([3, 2, 1], dtype=torch.int32, device=DEV)
+    got = ix.topk(qt, ql, 10, normalize=False, force="sparse")
+    dense = ix.topk(qt, ql, 10, normalize=False, force="dense")
+    assert all(torch.equal(g, w) for g, w in zip(got, dense))
