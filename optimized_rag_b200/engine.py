@@ -493,14 +493,11 @@ class HybridShard:
         st_b: list = []
         if self.coschedule and self.cosine.mode != "exact":
             # the scan takes the SMs first; the BM25 first pass (8-warp CTAs, < 31 KB smem) then runs NEXT TO the
-            # resident scan CTA of every SM, on the issue slots the tensor-bound scan leaves idle.  Measured on B200
-            # with two batches in flight (bench.py --rows R): 1.25M rows 1.33 -> 1.28 ms/step, 2.5M 2.25 -> 2.20,
-            # 5M 4.11 -> 3.83 (ORAG_COSCHEDULE=0 turns it off).
-            # All scans go back to back on ONE high-priority stream (`_head`); the tails -- candidate re-scores,
-            # selection, and whatever the caller appends: fusion, exchange, merge -- stay on the caller's (lane) stream.
-            # With the whole pipeline of a batch on its lane's stream, the next batch of that lane could not start its
-            # query preparation and seed pass before those tails had drained, and the tails cannot run while a scan CTA
-            # and a background BM25 CTA fill every SM's shared memory: the scans ended up ~0.14 ms apart.
+            # resident scan CTA of every SM (see __init__ for when that pays: long scans only).
+            # head_stream (off by default -- measured: no gain, the tails cannot run next to a resident scan either
+            # way): all scans back to back on ONE high-priority stream (`_head`) through the split entry point; the
+            # tails -- candidate re-scores, selection, and whatever the caller appends: fusion, exchange, merge -- stay
+            # on the caller's (lane) stream.
             if query_emb.shape[0] <= 256 and self.head_stream:
                 if self._head is None:
                     self._head = torch.cuda.Stream(dev, priority=-1)
