@@ -249,3 +249,22 @@ def test_c_abi_rejects_bad_arguments_of_the_round_2_entry_points(built_lib):
     assert L.orag_cosine_last_counts(p(buf), 1536, 300, p(buf), p(buf), None) == -1
     assert L.orag_timeline_read(None, None, None, 4) == -1
     assert L.orag_timeline_enable(0) == 0
+
+
+def test_ticket_group_concatenates_the_groups_of_a_split_submission(built_lib):
+    """dist._TicketGroup (a submission of more than 256 queries is split into 256-query groups over the lanes): `wait`
+    returns one dict with every tensor concatenated in submission order."""
+    import torch
+    from optimized_rag_b200.dist import _TicketGroup
+
+    class Fake:
+        def __init__(self, lo, n):
+            self.out = {"ids": torch.arange(lo, lo + n).view(n, 1), "status": torch.zeros(n, dtype=torch.int32),
+                        "src": torch.full((n, 2, 2), lo)}
+
+        def wait(self):
+            return self.out
+
+    got = _TicketGroup([Fake(0, 256), Fake(256, 256), Fake(512, 88)]).wait()
+    assert got["ids"].shape == (600, 1) and got["ids"][:, 0].tolist() == list(range(600))
+    assert got["status"].shape == (600,) and got["src"].shape == (600, 2, 2) and int(got["src"][599, 0, 0]) == 512
