@@ -113,7 +113,7 @@ def workload_config(args, extra=None):
 def run_reference(args):
     """The reference's CPU path (oracle port of rag/retrieval.py:362-371, 324-347 and rag/reranker.py:224-271; the
     Python reference itself cannot travel to the GPU box) on all host cores.  Each step is a bounded sample of the
-    workload -- `--ref-sample-queries` queries against the first rows/40 rows and docs, regenerated from the seeds --
+    workload -- `--ref-sample-queries` queries against the first rows/8 rows and docs, regenerated from the seeds --
     scaled linearly in N (every piece is O(N) per query)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -124,7 +124,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     oracle.build()
     oracle.set_threads(cores)  # torchrun exports OMP_NUM_THREADS=1: the baseline is "all host cores"
-    S = args.ref_sample_rows or max(args.rows // 40, 1000)
+    S = args.ref_sample_rows or max(args.rows // 8, 1000)
     S = min(S, args.rows)
     Bs = args.ref_sample_queries
     thr = syn.zipf_thresholds(VOCAB)
